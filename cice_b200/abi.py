@@ -1,0 +1,109 @@
+"""ctypes mirror of include/evp_b200.h (structs and enums only; no library is loaded here).
+
+The product binding (cice_b200.dyn_evp) and the test oracle binding (oracle/oracle.py) both
+describe their buffers with these structs, so a test feeds both sides from one set of arrays.
+"""
+import ctypes as C
+
+import numpy as np
+
+ABI_VERSION = 1
+
+BNDY_OPEN, BNDY_CLOSED, BNDY_CYCLIC, BNDY_TRIPOLE = 0, 1, 2, 3
+BNDY_NAMES = {"open": BNDY_OPEN, "closed": BNDY_CLOSED, "cyclic": BNDY_CYCLIC, "tripole": BNDY_TRIPOLE}
+
+MODE_EXACT, MODE_FAST = 0, 1
+KERNEL_AUTO, KERNEL_SPLIT, KERNEL_FUSED, KERNEL_PERSISTENT = 0, 1, 2, 3
+KERNEL_NAMES = {"auto": 0, "split": 1, "fused": 2, "persistent": 3}
+
+UNIQUE_ID_BYTES = 128
+
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int32)
+
+GRID_STATIC = ("dxT", "dyT", "dxhy", "dyhx", "cxp", "cyp", "cxm", "cym", "DminTarea", "uarear")
+
+
+class Grid(C.Structure):
+    _fields_ = (
+        [(n, C.c_int32) for n in ("abi_version", "nx_block", "ny_block", "nblocks", "max_blocks", "nghost",
+                                  "nx_global", "ny_global", "ew_boundary_type", "ns_boundary_type")]
+        + [(n, _pi) for n in ("ilo", "ihi", "jlo", "jhi", "i_glob", "j_glob")]
+        + [(n, _pd) for n in GRID_STATIC]
+    )
+
+
+class Params(C.Structure):
+    _fields_ = (
+        [(n, C.c_int32) for n in ("ndte", "mode", "kernel", "reserved")]
+        + [(n, C.c_double) for n in ("arlx1i", "denom1", "revp", "brlx", "e_factor", "epp2i", "capping",
+                                     "Ktens", "u0", "cosw", "sinw", "rhow")]
+    )
+
+
+STRESS = tuple(f"stress{k}_{n}" for k in ("p", "m", "12") for n in (1, 2, 3, 4))
+FIELDS_IN = ("strength", "cdn_ocnU", "aiU", "uocnU", "vocnU", "waterxU", "wateryU", "forcexU", "forceyU",
+             "umassdti", "fmU", "TbU")
+FIELDS_INOUT = STRESS + ("strintxU", "strintyU", "taubxU", "taubyU", "uvel", "vvel")
+FIELDS_MASK = ("iceTmask", "iceUmask")
+# struct order == argument order of dyn_evp1d_run (ice_dyn_evp1d.F90:119-153)
+FIELDS_ORDER = (STRESS + ("strength", "cdn_ocnU", "aiU", "uocnU", "vocnU", "waterxU", "wateryU", "forcexU",
+                          "forceyU", "umassdti", "fmU", "strintxU", "strintyU", "TbU", "taubxU", "taubyU",
+                          "uvel", "vvel"))
+
+
+class Fields(C.Structure):
+    _fields_ = [(n, _pd) for n in FIELDS_ORDER] + [(n, _pi) for n in FIELDS_MASK]
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def as_f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+def make_grid(g):
+    """Build a Grid struct from a dict of numpy arrays / ints. Returns (struct, keepalive)."""
+    keep = {}
+    s = Grid()
+    s.abi_version = ABI_VERSION
+    for n in ("nx_block", "ny_block", "nblocks", "max_blocks", "nghost", "nx_global", "ny_global",
+              "ew_boundary_type", "ns_boundary_type"):
+        setattr(s, n, int(g[n]))
+    for n in ("ilo", "ihi", "jlo", "jhi", "i_glob", "j_glob"):
+        keep[n] = np.ascontiguousarray(g[n], dtype=np.int32)
+        setattr(s, n, _ptr(keep[n], C.c_int32))
+    for n in GRID_STATIC:
+        keep[n] = as_f64(g[n])
+        assert keep[n].size == s.nx_block * s.ny_block * s.max_blocks, n
+        setattr(s, n, _ptr(keep[n], C.c_double))
+    return s, keep
+
+
+def make_params(p):
+    s = Params()
+    for n, _ in Params._fields_:
+        if n in p:
+            setattr(s, n, p[n])
+    return s
+
+
+def make_fields(f, npl_total):
+    """Fields struct over the arrays in dict f (must already be C-contiguous with the right dtype:
+    they are written in place by run calls). Returns (struct, keepalive)."""
+    s = Fields()
+    keep = {}
+    for n in FIELDS_ORDER:
+        a = f[n]
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == npl_total, n
+        keep[n] = a
+        setattr(s, n, _ptr(a, C.c_double))
+    for n in FIELDS_MASK:
+        a = f[n]
+        assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"] and a.size == npl_total, n
+        keep[n] = a
+        setattr(s, n, _ptr(a, C.c_int32))
+    return s, keep

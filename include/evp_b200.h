@@ -1,0 +1,180 @@
+/*
+ * evp_b200.h -- C ABI of the B200-native EVP subcycling path.
+ *
+ * This is the drop-in boundary for ONE path of CICE: the elastic-viscous-plastic
+ * subcycling loop of `evp(dt)` on the B grid,
+ *
+ *     do ksub = 1,ndte:  stress ; stepu ; halo(uvel,vvel)
+ *     (cicecore/cicedyn/dynamics/ice_dyn_evp.F90:859-913)
+ *
+ * Every entry point below is what a Fortran ISO_C_BINDING interface (see
+ * fortran/ice_dyn_evp_b200.F90 and INTEGRATION.md) binds.  The seam is the one the
+ * reference already has for its own 1-D solver:
+ *
+ *     evp_b200_init        <->  dyn_evp1d_init      ice_dyn_evp1d.F90:73-115, called from ice_dyn_evp.F90:153-155
+ *     evp_b200_run_bgrid   <->  dyn_evp1d_run       ice_dyn_evp1d.F90:119-310, called from ice_dyn_evp.F90:848-856
+ *     evp_b200_finalize    <->  dyn_evp1d_finalize  ice_dyn_evp1d.F90:314-330
+ *
+ * Conventions
+ *  - plain C, no C++ or torch types; pointers address the FIRST element of a Fortran
+ *    array `real(dbl_kind) :: a(nx_block, ny_block, max_blocks)` (column major, i fastest)
+ *    (cicecore/cicedyn/infrastructure/ice_blocks.F90:48-49,169-170).
+ *  - Fortran `logical(log_kind)` is not C-interoperable; masks cross as int32 0/1.
+ *  - all indices in evp_b200_grid_t are Fortran 1-based, exactly as in `type(block)`
+ *    (ice_blocks.F90:22-41).
+ *  - every function returns 0 on success and non-zero on failure and never calls exit();
+ *    the message is available from evp_b200_last_error().  The Fortran shim turns
+ *    non-zero into `abort_ice(...)` (comm/mpi/ice_exit.F90).
+ *  - the library is entered single-threaded, once per MPI rank per dynamics step
+ *    (the reference opens its OpenMP regions inside evp, ice_dyn_evp.F90:861);
+ *    one rank <-> one GPU.  Not re-entrant.
+ *  - the host owns all host arrays; the library owns device memory and keeps no host
+ *    pointer past the return of a call.
+ */
+#ifndef EVP_B200_H
+#define EVP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVP_B200_ABI_VERSION 1
+
+/* boundary types: domain_nml ew_boundary_type / ns_boundary_type
+ * (cicecore/cicedyn/infrastructure/ice_domain.F90:186-240) */
+enum {
+  EVP_B200_BNDY_OPEN    = 0,
+  EVP_B200_BNDY_CLOSED  = 1,
+  EVP_B200_BNDY_CYCLIC  = 2,
+  EVP_B200_BNDY_TRIPOLE = 3   /* u-fold tripole, ns only */
+};
+
+/* arithmetic mode of the device kernels */
+enum {
+  EVP_B200_MODE_EXACT = 0,  /* no FMA contraction, source evaluation order: bit-identical to the
+                               -ffp-contract=off CPU oracle */
+  EVP_B200_MODE_FAST  = 1   /* FMA contraction allowed (nvcc default); within 1e-10 relative */
+};
+
+/* kernel strategy (0 lets the library choose from the sub-domain size) */
+enum {
+  EVP_B200_KERNEL_AUTO       = 0,
+  EVP_B200_KERNEL_SPLIT      = 1,  /* stress kernel + stepu kernel per subcycle (first correct path) */
+  EVP_B200_KERNEL_FUSED      = 2,  /* one fused stress+stepu kernel per subcycle, CUDA-graphed */
+  EVP_B200_KERNEL_PERSISTENT = 3   /* all ndte subcycles in one cooperative launch, state on chip */
+};
+
+/*
+ * Static description of this rank's part of the domain; passed once.
+ * Mirrors what dyn_evp1d_init gathers (ice_dyn_evp1d.F90:73-115) plus the block table
+ * of ice_blocks.F90:22-41 and the static arrays the 2-D `stress`/`stepu` read
+ * (ice_dyn_evp.F90:1457-1500, ice_dyn_shared.F90:847-890).
+ */
+typedef struct {
+  int32_t abi_version;        /* EVP_B200_ABI_VERSION */
+  int32_t nx_block, ny_block; /* block_size + 2*nghost                         ice_blocks.F90:169-170 */
+  int32_t nblocks;            /* blocks owned by this rank                     ice_domain.F90 nblocks */
+  int32_t max_blocks;         /* third extent of every field array             ice_domain_size.F90    */
+  int32_t nghost;             /* must be 1                                     ice_blocks.F90:48      */
+  int32_t nx_global, ny_global;
+  int32_t ew_boundary_type;   /* EVP_B200_BNDY_*                                                      */
+  int32_t ns_boundary_type;
+
+  /* per local block n = 0..nblocks-1 (Fortran iblk = n+1) */
+  const int32_t *ilo, *ihi, *jlo, *jhi; /* [nblocks]  first/last interior index, 1-based               */
+  const int32_t *i_glob;      /* [nx_block*nblocks] global i of local column i; 0 = outside a closed edge */
+  const int32_t *j_glob;      /* [ny_block*nblocks] global j of local row j                             */
+
+  /* static geometry, each (nx_block,ny_block,max_blocks) f64 */
+  const double *dxT, *dyT;    /* ice_grid.F90:3086-3131, 3197-3241 */
+  const double *dxhy, *dyhx;  /* ice_dyn_shared.F90:401-424        */
+  const double *cxp, *cyp, *cxm, *cym; /* ice_dyn_shared.F90:426-441 */
+  const double *DminTarea;    /* ice_dyn_shared.F90:384-388        */
+  const double *uarear;       /* ice_grid.F90:681-715              */
+} evp_b200_grid_t;
+
+/*
+ * Scalars of one dynamics step, passed by value in the struct.
+ * ice_dyn_shared.F90:66-89 (declarations), :453-486 (set_evp_parameters).
+ */
+typedef struct {
+  int32_t ndte;               /* number of subcycles                         */
+  int32_t mode;               /* EVP_B200_MODE_*                             */
+  int32_t kernel;             /* EVP_B200_KERNEL_*                           */
+  int32_t reserved;
+  double arlx1i, denom1, revp, brlx;
+  double e_factor, epp2i, capping, Ktens;
+  double u0, cosw, sinw;      /* ice_dyn_shared.F90:66-70                    */
+  double rhow;                /* icepack_query_parameters(rhow_out=...)      */
+} evp_b200_params_t;
+
+/*
+ * Time-varying fields of one call, the argument list of dyn_evp1d_run
+ * (ice_dyn_evp1d.F90:119-153) in the same order.  All (nx_block,ny_block,max_blocks).
+ */
+typedef struct {
+  /* inout: carried dynamics state (ice_restart_driver.F90:150-231) */
+  double *stressp_1, *stressp_2, *stressp_3, *stressp_4;
+  double *stressm_1, *stressm_2, *stressm_3, *stressm_4;
+  double *stress12_1, *stress12_2, *stress12_3, *stress12_4;
+  /* in */
+  const double *strength;
+  const double *cdn_ocnU, *aiU, *uocnU, *vocnU;
+  const double *waterxU, *wateryU, *forcexU, *forceyU;
+  const double *umassdti, *fmU;
+  /* inout: written only where iceUmask is true (ice_dyn_shared.F90:925-966) */
+  double *strintxU, *strintyU;
+  /* in */
+  const double *TbU;
+  /* inout */
+  double *taubxU, *taubyU;
+  double *uvel, *vvel;
+  /* in: 0/1 */
+  const int32_t *iceTmask, *iceUmask;
+} evp_b200_fields_t;
+
+/* ---- multi-GPU bootstrap (optional; omit for one GPU) ---------------------------------
+ * Replaces ice_boundary's MPI halo for the dyn fields (ice_boundary.F90:1066-1760 reached
+ * through dyn_haloUpdate, ice_dyn_shared.F90:2518-2574).  Rank 0 obtains a 128-byte id,
+ * the host broadcasts it with its own transport (MPI_Bcast in the Fortran shim,
+ * torch.distributed in the Python tests), then every rank calls evp_b200_comm_init
+ * BEFORE evp_b200_init. */
+#define EVP_B200_UNIQUE_ID_BYTES 128
+int evp_b200_get_unique_id(void *id128);
+int evp_b200_comm_init(int32_t rank, int32_t nranks, const void *id128);
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+int evp_b200_set_device(int32_t device_ordinal);           /* default: current device */
+int evp_b200_init(const evp_b200_grid_t *grid);
+int evp_b200_finalize(void);
+const char *evp_b200_last_error(void);
+
+/* ---- the hot path ------------------------------------------------------------------------
+ * One call = the whole `do ksub=1,ndte` loop of ice_dyn_evp.F90:859-913 on this rank's
+ * blocks, including the per-subcycle (uvel,vvel) halo update.  Host buffers in, host
+ * buffers out: H2D of the fields, the device loop, D2H of the inout fields. */
+int evp_b200_run_bgrid(const evp_b200_params_t *params, evp_b200_fields_t *fields);
+
+/* The same call split in three so that a caller which keeps dynamics state on the device
+ *  -- and bench.py's device-resident timing -- can run the loop alone.
+ * run_bgrid == upload + subcycle + download. */
+int evp_b200_upload(const evp_b200_fields_t *fields);
+int evp_b200_subcycle(const evp_b200_params_t *params);
+int evp_b200_download(evp_b200_fields_t *fields);
+
+/* ---- measurement hooks (not part of the reference seam) ---------------------------------- */
+/* device time of the most recent evp_b200_subcycle in ms (CUDA events on the library's stream) */
+int evp_b200_last_loop_ms(double *ms);
+/* number of kernel launches issued by the most recent evp_b200_subcycle */
+int evp_b200_last_launches(int64_t *n);
+/* raw CUDA stream handle (cudaStream_t) the library launches on, for external event timing */
+int evp_b200_stream(void **stream);
+/* report the chosen tiling/kernel as a short static string */
+const char *evp_b200_describe(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVP_B200_H */

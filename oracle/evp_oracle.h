@@ -1,0 +1,73 @@
+/*
+ * evp_oracle.h -- CPU oracle for the EVP subcycling path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library, and only as the checker or the timed CPU baseline.  The product
+ * (cice_b200/) never links, imports or calls it.
+ *
+ * PARITY UNPINNED BY VECTORS: the reference (Fortran) cannot be compiled in this image
+ * (no f951 / MPI / csh) and ships no golden vectors for this path, so this
+ * restatement is pinned by the properties the reference itself asserts (bit-for-bit under
+ * any block decomposition, 2-D == 1-D formulation, halochk closed-form halo values), not
+ * by outputs of the reference binary.
+ *
+ * The entry points take the SAME structs as the product's C ABI (include/evp_b200.h) so a
+ * test feeds both sides from one set of buffers.
+ */
+#ifndef EVP_ORACLE_H
+#define EVP_ORACLE_H
+
+#include "evp_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* 2-D blocked path: ice_dyn_evp.F90:859-913 (loop), :1457-1743 (stress),
+ * ice_dyn_shared.F90:847-968 (stepu), halo via the halochk semantics.
+ * `grid` must describe ALL blocks of the global domain (serial-comm view).
+ * nthreads <= 0: use omp_get_max_threads(). Returns 0 on success. */
+int orc_evp_run_bgrid(const evp_b200_grid_t *grid, const evp_b200_params_t *params,
+                      evp_b200_fields_t *fields, int nthreads);
+
+/* 1-D gather-indexed path: ice_dyn_evp1d.F90:119-310 + ice_dyn_core1d.F90.
+ * Needs HTE/HTN instead of the precomputed cxp.. arrays, exactly like the reference 1-D
+ * solver (ice_dyn_core1d.F90:191-199).  Single block covering the whole domain only
+ * (the reference gathers to one global array first, ice_dyn_evp1d.F90:178-195). */
+int orc_evp_run_bgrid_1d(const evp_b200_grid_t *grid, const double *HTE, const double *HTN,
+                         double deltaminEVP, const evp_b200_params_t *params,
+                         evp_b200_fields_t *fields, int nthreads);
+
+/* NE-corner / vector halo update of nfld fields, the dyn_haloUpdate call of
+ * ice_dyn_evp.F90:908-910 (ice_boundary.F90:1066-1760; expectations halochk.F90:530-830).
+ * field_loc: 0 center, 1 NE corner; field_type: 0 scalar, 1 vector. */
+int orc_halo_update(const evp_b200_grid_t *grid, double **flds, int nfld,
+                    int field_loc, int field_type);
+
+/* single calls, for kernel-level tests (one block, arrays (nx_block,ny_block)) */
+void orc_stress_block(int nx_block, int ny_block, int icellT, const int *indxTi, const int *indxTj,
+                      const double *uvel, const double *vvel,
+                      const double *dxT, const double *dyT, const double *dxhy, const double *dyhx,
+                      const double *cxp, const double *cyp, const double *cxm, const double *cym,
+                      const double *DminTarea, const double *strength,
+                      double *stressp_1, double *stressp_2, double *stressp_3, double *stressp_4,
+                      double *stressm_1, double *stressm_2, double *stressm_3, double *stressm_4,
+                      double *stress12_1, double *stress12_2, double *stress12_3, double *stress12_4,
+                      double *str, const evp_b200_params_t *p);
+
+void orc_stepu_block(int nx_block, int ny_block, int icellU, const int *indxUi, const int *indxUj,
+                     const double *Cw, const double *aiX, const double *str,
+                     const double *uocn, const double *vocn, const double *waterx, const double *watery,
+                     const double *forcex, const double *forcey, const double *Umassdti,
+                     const double *fm, const double *uarear,
+                     double *strintx, double *strinty, double *taubx, double *tauby,
+                     const double *uvel_init, const double *vvel_init,
+                     double *uvel, double *vvel, const double *TbU, const evp_b200_params_t *p);
+
+const char *orc_last_error(void);
+int orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,103 @@
+"""ctypes binding of the C oracle (oracle/evp_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module;
+the product package (cice_b200) never does.  Parity is unpinned by reference vectors -- see the
+header of evp_oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from cice_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+_libs = {}
+
+
+def build(force=False):
+    """compile the oracle with the committed Makefile (gcc only; no reference build system)."""
+    need = force or not all(os.path.exists(os.path.join(_BUILD, f"liboracle_{v}.so")) for v in ("exact", "fast"))
+    if not need:
+        src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("evp_oracle.c", "evp_oracle.h"))
+        need = any(os.path.getmtime(os.path.join(_BUILD, f"liboracle_{v}.so")) < src_m for v in ("exact", "fast"))
+    if need:
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+
+
+def _cpu_has_avx2_fma():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            flags = fh.read()
+        return " avx2" in flags and " fma" in flags
+    except OSError:
+        return False
+
+
+def lib(variant="exact"):
+    """variant 'exact' (-O2 -ffp-contract=off: defines the answer) or 'fast' (timed CPU baseline)."""
+    if variant == "fast" and not _cpu_has_avx2_fma():
+        variant = "exact"
+    if variant not in _libs:
+        path = os.path.join(_BUILD, f"liboracle_{variant}.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_evp_run_bgrid.argtypes = [C.POINTER(abi.Grid), C.POINTER(abi.Params), C.POINTER(abi.Fields), C.c_int]
+        L.orc_evp_run_bgrid.restype = C.c_int
+        L.orc_evp_run_bgrid_1d.argtypes = [C.POINTER(abi.Grid), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                           C.c_double, C.POINTER(abi.Params), C.POINTER(abi.Fields), C.c_int]
+        L.orc_evp_run_bgrid_1d.restype = C.c_int
+        L.orc_halo_update.argtypes = [C.POINTER(abi.Grid), C.POINTER(C.POINTER(C.c_double)), C.c_int, C.c_int, C.c_int]
+        L.orc_halo_update.restype = C.c_int
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_num_threads.restype = C.c_int
+        _libs[variant] = L
+    return _libs[variant]
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def _npl(grid):
+    return int(grid["nx_block"]) * int(grid["ny_block"]) * int(grid["max_blocks"])
+
+
+def evp_run_bgrid(grid, params, fields, nthreads=0, variant="exact"):
+    """run the 2-D blocked oracle IN PLACE on the arrays of `fields`."""
+    L = lib(variant)
+    g, kg = abi.make_grid(grid)
+    p = abi.make_params(params)
+    f, kf = abi.make_fields(fields, _npl(grid))
+    rc = L.orc_evp_run_bgrid(C.byref(g), C.byref(p), C.byref(f), int(nthreads))
+    if rc:
+        raise RuntimeError("oracle: " + L.orc_last_error().decode())
+    return fields
+
+
+def evp_run_bgrid_1d(grid, HTE, HTN, deltaminEVP, params, fields, nthreads=0, variant="exact"):
+    L = lib(variant)
+    g, kg = abi.make_grid(grid)
+    p = abi.make_params(params)
+    f, kf = abi.make_fields(fields, _npl(grid))
+    hte = abi.as_f64(HTE)
+    htn = abi.as_f64(HTN)
+    rc = L.orc_evp_run_bgrid_1d(C.byref(g), hte.ctypes.data_as(C.POINTER(C.c_double)),
+                                htn.ctypes.data_as(C.POINTER(C.c_double)), float(deltaminEVP),
+                                C.byref(p), C.byref(f), int(nthreads))
+    if rc:
+        raise RuntimeError("oracle1d: " + L.orc_last_error().decode())
+    return fields
+
+
+def halo_update(grid, arrays, field_loc=1, field_type=1, variant="exact"):
+    L = lib(variant)
+    g, kg = abi.make_grid(grid)
+    n = len(arrays)
+    ptrs = (C.POINTER(C.c_double) * n)(*[a.ctypes.data_as(C.POINTER(C.c_double)) for a in arrays])
+    rc = L.orc_halo_update(C.byref(g), ptrs, n, field_loc, field_type)
+    if rc:
+        raise RuntimeError("oracle halo: " + L.orc_last_error().decode())
