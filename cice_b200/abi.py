@@ -1,6 +1,6 @@
 """ctypes mirror of include/evp_b200.h (structs and enums only; no library is loaded here).
 
-The product binding (cice_b200.dyn_evp) and the test oracle binding (oracle/oracle.py) both
+The product binding (cice_b200.dyn_evp) and the test-side checker binding both
 describe their buffers with these structs, so a test feeds both sides from one set of arrays.
 """
 import ctypes as C

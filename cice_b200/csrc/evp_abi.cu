@@ -1,0 +1,497 @@
+// evp_abi.cu -- the C ABI of include/evp_b200.h: device memory, host<->device staging in the
+// reference's block layout, sub-domain stitching, the subcycle driver (CUDA-graphed) and the halo.
+//
+// Host side of the seam this replaces: dyn_evp1d_init / dyn_evp1d_run / dyn_evp1d_finalize
+// (cicecore/cicedyn/dynamics/ice_dyn_evp1d.F90:73-330) as dispatched from evp()
+// (ice_dyn_evp.F90:153-155, 846-914).  Where the reference's 1-D solver gathers every field to the
+// master task and converts 2-D -> 1-D (ice_dyn_evp1d.F90:178-208), this library keeps the data
+// distributed: each rank stitches its own blocks into one rectangle ("dom") on its GPU.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "evp_b200.h"
+#include "evp_internal.h"
+#include "evp_halo.h"
+
+namespace evp {
+
+static char g_err[1024] = "";
+static int fail(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// pack / unpack kernels between the reference's block layout and the dom layout
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_f64(double *__restrict__ dst, const double *__restrict__ src, const int *__restrict__ gsrc, int n) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int s = gsrc[k];
+    dst[k] = (s >= 0) ? src[s] : 0.0;
+  }
+}
+__global__ void pack_mask(unsigned char *__restrict__ dst, const int *__restrict__ src, const int *__restrict__ gsrc,
+                          int n) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int s = gsrc[k];
+    dst[k] = (s >= 0 && src[s] != 0) ? 1 : 0;
+  }
+}
+__global__ void unpack_f64(double *__restrict__ dst_blk, const double *__restrict__ src_dom, const int *__restrict__ lin,
+                           const int *__restrict__ dom, int n) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) dst_blk[lin[k]] = src_dom[dom[k]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+enum FieldId {
+  // inout state (order of evp_b200_fields_t)
+  F_SIG0 = 0,                                    // 12 stresses
+  F_STRINTX = 12, F_STRINTY, F_TAUBX, F_TAUBY, F_U, F_V,  // 18 inout in total
+  // per-step inputs
+  F_STRENGTH = 18, F_CDN, F_AIU, F_UOCN, F_VOCN, F_WATERX, F_WATERY, F_FORCEX, F_FORCEY, F_UMASSDTI, F_FM, F_TBU,
+  NF_STEP = 30,
+  // static geometry
+  G_DXT = 30, G_DYT, G_DXHY, G_DYHX, G_CXP, G_CYP, G_CXM, G_CYM, G_DMIN, G_UAREAR,
+  NF_TOTAL = 40
+};
+
+struct Ctx {
+  bool inited = false;
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // host-side description
+  int nx_block = 0, ny_block = 0, nblocks = 0, max_blocks = 0, nxg = 0, nyg = 0, ew = 0, ns = 0;
+  size_t nblk_elems = 0;  // nx_block*ny_block*max_blocks
+  int gi0 = 0, gj0 = 0;   // global index of dom interior (1,1)
+  size_t ndom = 0;        // ld*nyd
+
+  Dom dom{};
+  // device memory
+  double *dfield[NF_TOTAL] = {};  // dom-layout arrays (sig/u/v: copy 0)
+  double *dsig1[12] = {}, *du1 = nullptr, *dv1 = nullptr;  // ping-pong copy 1
+  double *duinit = nullptr, *dvinit = nullptr;
+  double *dstr[8] = {};
+  unsigned char *dmaskT = nullptr, *dmaskU = nullptr;
+  double *stage[NF_STEP] = {};    // block-layout staging, one per time-varying field
+  int *stage_mask = nullptr;
+  int *d_gsrc = nullptr;
+  int *d_uv_lin = nullptr, *d_uv_dom = nullptr, n_uv = 0;
+  int *d_sig_lin = nullptr, *d_sig_dom = nullptr, n_sig = 0;
+  int *d_int_lin = nullptr, *d_int_dom = nullptr, n_int = 0;
+
+  // loop state
+  int cur = 0;
+  bool uploaded = false;
+  float last_ms = 0.f;
+  int64_t last_launches = 0;
+  std::string desc;
+
+  // cached graph of the whole ndte loop
+  cudaGraphExec_t gexec = nullptr;
+  evp_b200_params_t gparams{};
+  int64_t glaunches = 0;
+  int gcur_end = 0;
+
+  HaloPlan halo;
+};
+static Ctx g;
+static CommState g_comm;
+
+static int grid_blocks(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 16); }
+
+static void destroy_graph() {
+  if (g.gexec) {
+    cudaGraphExecDestroy(g.gexec);
+    g.gexec = nullptr;
+  }
+}
+
+static int free_all() {
+  destroy_graph();
+  auto F = [](auto *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  for (auto &p : g.dfield) F(p);
+  for (auto &p : g.dsig1) F(p);
+  F(g.du1); F(g.dv1); F(g.duinit); F(g.dvinit);
+  for (auto &p : g.dstr) F(p);
+  F(g.dmaskT); F(g.dmaskU);
+  for (auto &p : g.stage) F(p);
+  F(g.stage_mask); F(g.d_gsrc);
+  F(g.d_uv_lin); F(g.d_uv_dom); F(g.d_sig_lin); F(g.d_sig_dom); F(g.d_int_lin); F(g.d_int_dom);
+  g.halo.release();
+  if (g.ev0) cudaEventDestroy(g.ev0);
+  if (g.ev1) cudaEventDestroy(g.ev1);
+  if (g.stream) cudaStreamDestroy(g.stream);
+  g = Ctx{};
+  return 0;
+}
+
+template <class T>
+static int upload_vec(T *&dptr, const std::vector<T> &h) {
+  CK(cudaMalloc(&dptr, std::max<size_t>(h.size(), 1) * sizeof(T)));
+  if (!h.empty()) CK(cudaMemcpy(dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int do_init(const evp_b200_grid_t *gr) {
+  if (!gr) return fail("evp_b200_init: null grid");
+  if (gr->abi_version != EVP_B200_ABI_VERSION) return fail("evp_b200_init: abi_version %d != %d", gr->abi_version, EVP_B200_ABI_VERSION);
+  if (gr->nghost != 1) return fail("evp_b200_init: nghost must be 1 (ice_blocks.F90:48), got %d", gr->nghost);
+  if (gr->nblocks < 1 || gr->nblocks > gr->max_blocks) return fail("evp_b200_init: nblocks=%d max_blocks=%d", gr->nblocks, gr->max_blocks);
+  if (gr->nx_block < 3 || gr->ny_block < 3) return fail("evp_b200_init: block too small");
+  if (gr->ns_boundary_type == EVP_B200_BNDY_TRIPOLE && gr->ew_boundary_type != EVP_B200_BNDY_CYCLIC)
+    return fail("evp_b200_init: tripole requires ew_boundary_type cyclic");
+  if (g.inited) { const int dev = g.device; free_all(); g.device = dev; }
+
+  if (g.device < 0) CK(cudaGetDevice(&g.device));
+  CK(cudaSetDevice(g.device));
+  CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&g.ev0));
+  CK(cudaEventCreate(&g.ev1));
+
+  g.nx_block = gr->nx_block; g.ny_block = gr->ny_block; g.nblocks = gr->nblocks; g.max_blocks = gr->max_blocks;
+  g.nxg = gr->nx_global; g.nyg = gr->ny_global; g.ew = gr->ew_boundary_type; g.ns = gr->ns_boundary_type;
+  const int nxb = g.nx_block, nyb = g.ny_block;
+  g.nblk_elems = (size_t)nxb * nyb * g.max_blocks;
+  if (g.nblk_elems > 0x7fffffffULL) return fail("evp_b200_init: block arrays exceed 2^31 elements");
+
+  // ---- the rank's rectangle --------------------------------------------------------------------
+  int gi0 = 1 << 30, gi1 = -1, gj0 = 1 << 30, gj1 = -1;
+  size_t ncell = 0;
+  for (int b = 0; b < g.nblocks; ++b) {
+    const int32_t *ig = gr->i_glob + (size_t)b * nxb, *jg = gr->j_glob + (size_t)b * nyb;
+    const int ilo = gr->ilo[b], ihi = gr->ihi[b], jlo = gr->jlo[b], jhi = gr->jhi[b];
+    if (ilo != 2 || jlo != 2 || ihi < ilo || jhi < jlo || ihi > nxb - 1 || jhi > nyb - 1)
+      return fail("evp_b200_init: block %d has bad interior bounds", b + 1);
+    if (ig[ilo - 1] < 1 || ig[ihi - 1] > g.nxg || jg[jlo - 1] < 1 || jg[jhi - 1] > g.nyg || ig[ihi - 1] - ig[ilo - 1] != ihi - ilo ||
+        jg[jhi - 1] - jg[jlo - 1] != jhi - jlo)
+      return fail("evp_b200_init: block %d has inconsistent i_glob/j_glob", b + 1);
+    gi0 = std::min(gi0, (int)ig[ilo - 1]); gi1 = std::max(gi1, (int)ig[ihi - 1]);
+    gj0 = std::min(gj0, (int)jg[jlo - 1]); gj1 = std::max(gj1, (int)jg[jhi - 1]);
+    ncell += (size_t)(ihi - ilo + 1) * (jhi - jlo + 1);
+  }
+  const int nx = gi1 - gi0 + 1, ny = gj1 - gj0 + 1;
+  if (ncell != (size_t)nx * ny)
+    return fail("evp_b200_init: the rank's blocks do not tile a rectangle (%zu cells vs %dx%d); use a cartesian "
+                "distribution without land-block elimination", ncell, nx, ny);
+  g.gi0 = gi0; g.gj0 = gj0;
+  Dom &d = g.dom;
+  d.nx = nx; d.ny = ny; d.nyd = ny + 2;
+  d.ld = ((nx + 2 + 15) / 16) * 16;
+  g.ndom = (size_t)d.ld * d.nyd;
+  if (g.ndom > 0x7fffffffULL) return fail("evp_b200_init: sub-domain exceeds 2^31 cells");
+
+  // ---- index maps -------------------------------------------------------------------------------
+  std::vector<int> gsrc(g.ndom, -1), uv_lin, uv_dom, sig_lin, sig_dom, int_lin, int_dom;
+  std::vector<unsigned char> owned(g.ndom, 0);
+  for (int b = 0; b < g.nblocks; ++b) {
+    const int32_t *ig = gr->i_glob + (size_t)b * nxb, *jg = gr->j_glob + (size_t)b * nyb;
+    const int ilo = gr->ilo[b], ihi = gr->ihi[b], jlo = gr->jlo[b], jhi = gr->jhi[b];
+    const int oi = ig[ilo - 1] - gi0 + 1 - ilo, oj = jg[jlo - 1] - gj0 + 1 - jlo;  // dom = local + o
+    for (int lj = jlo - 1; lj <= jhi + 1; ++lj)
+      for (int li = ilo - 1; li <= ihi + 1; ++li) {
+        const int di = li + oi, dj = lj + oj;
+        if (di < 0 || di > nx + 1 || dj < 0 || dj > ny + 1) return fail("evp_b200_init: internal: dom index out of range");
+        const int lin = (li - 1) + nxb * ((lj - 1) + nyb * b);
+        const int dm = dj * d.ld + di;
+        const bool interior = (li >= ilo && li <= ihi && lj >= jlo && lj <= jhi);
+        const bool ring = (di == 0 || di == nx + 1 || dj == 0 || dj == ny + 1);
+        if (interior) {
+          if (owned[dm]) return fail("evp_b200_init: blocks overlap");
+          owned[dm] = 1;
+          gsrc[dm] = lin;
+          int_lin.push_back(lin); int_dom.push_back(dm);
+        } else if (ring && gsrc[dm] < 0) {
+          gsrc[dm] = lin;
+        }
+        uv_lin.push_back(lin); uv_dom.push_back(dm);
+        if (li >= ilo && lj >= jlo) { sig_lin.push_back(lin); sig_dom.push_back(dm); }
+      }
+  }
+  g.n_uv = (int)uv_lin.size(); g.n_sig = (int)sig_lin.size(); g.n_int = (int)int_lin.size();
+  if (upload_vec(g.d_gsrc, gsrc) || upload_vec(g.d_uv_lin, uv_lin) || upload_vec(g.d_uv_dom, uv_dom) ||
+      upload_vec(g.d_sig_lin, sig_lin) || upload_vec(g.d_sig_dom, sig_dom) || upload_vec(g.d_int_lin, int_lin) ||
+      upload_vec(g.d_int_dom, int_dom))
+    return 1;
+
+  // ---- device memory ----------------------------------------------------------------------------
+  const size_t bdom = g.ndom * sizeof(double), bblk = g.nblk_elems * sizeof(double);
+  for (int f = 0; f < NF_TOTAL; ++f) { CK(cudaMalloc(&g.dfield[f], bdom)); CK(cudaMemsetAsync(g.dfield[f], 0, bdom, g.stream)); }
+  for (int q = 0; q < 12; ++q) { CK(cudaMalloc(&g.dsig1[q], bdom)); CK(cudaMemsetAsync(g.dsig1[q], 0, bdom, g.stream)); }
+  CK(cudaMalloc(&g.du1, bdom)); CK(cudaMalloc(&g.dv1, bdom)); CK(cudaMalloc(&g.duinit, bdom)); CK(cudaMalloc(&g.dvinit, bdom));
+  CK(cudaMemsetAsync(g.du1, 0, bdom, g.stream)); CK(cudaMemsetAsync(g.dv1, 0, bdom, g.stream));
+  CK(cudaMemsetAsync(g.duinit, 0, bdom, g.stream)); CK(cudaMemsetAsync(g.dvinit, 0, bdom, g.stream));
+  for (int q = 0; q < 8; ++q) { CK(cudaMalloc(&g.dstr[q], bdom)); CK(cudaMemsetAsync(g.dstr[q], 0, bdom, g.stream)); }
+  CK(cudaMalloc(&g.dmaskT, g.ndom)); CK(cudaMalloc(&g.dmaskU, g.ndom));
+  CK(cudaMemsetAsync(g.dmaskT, 0, g.ndom, g.stream)); CK(cudaMemsetAsync(g.dmaskU, 0, g.ndom, g.stream));
+  for (int f = 0; f < NF_STEP; ++f) CK(cudaMalloc(&g.stage[f], bblk));
+  CK(cudaMalloc(&g.stage_mask, g.nblk_elems * sizeof(int)));
+
+  // ---- static geometry --------------------------------------------------------------------------
+  const double *geo[10] = {gr->dxT, gr->dyT, gr->dxhy, gr->dyhx, gr->cxp, gr->cyp, gr->cxm, gr->cym, gr->DminTarea, gr->uarear};
+  for (int q = 0; q < 10; ++q) {
+    if (!geo[q]) return fail("evp_b200_init: null geometry array %d", q);
+    CK(cudaMemcpyAsync(g.stage[q], geo[q], bblk, cudaMemcpyHostToDevice, g.stream));
+    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(g.dfield[G_DXT + q], g.stage[q], g.d_gsrc, (int)g.ndom);
+  }
+  CK(cudaGetLastError());
+
+  // ---- Dom ----------------------------------------------------------------------------------------
+  for (int q = 0; q < 12; ++q) { d.sig[0][q] = g.dfield[F_SIG0 + q]; d.sig[1][q] = g.dsig1[q]; }
+  d.u[0] = g.dfield[F_U]; d.u[1] = g.du1; d.v[0] = g.dfield[F_V]; d.v[1] = g.dv1;
+  d.strength = g.dfield[F_STRENGTH];
+  d.dxT = g.dfield[G_DXT]; d.dyT = g.dfield[G_DYT]; d.dxhy = g.dfield[G_DXHY]; d.dyhx = g.dfield[G_DYHX];
+  d.cxp = g.dfield[G_CXP]; d.cyp = g.dfield[G_CYP]; d.cxm = g.dfield[G_CXM]; d.cym = g.dfield[G_CYM];
+  d.DminTarea = g.dfield[G_DMIN]; d.uarear = g.dfield[G_UAREAR];
+  d.cdn = g.dfield[F_CDN]; d.aiu = g.dfield[F_AIU]; d.uocn = g.dfield[F_UOCN]; d.vocn = g.dfield[F_VOCN];
+  d.waterx = g.dfield[F_WATERX]; d.watery = g.dfield[F_WATERY]; d.forcex = g.dfield[F_FORCEX]; d.forcey = g.dfield[F_FORCEY];
+  d.umassdti = g.dfield[F_UMASSDTI]; d.fm = g.dfield[F_FM]; d.TbU = g.dfield[F_TBU];
+  d.uinit = g.duinit; d.vinit = g.dvinit;
+  d.strintx = g.dfield[F_STRINTX]; d.strinty = g.dfield[F_STRINTY]; d.taubx = g.dfield[F_TAUBX]; d.tauby = g.dfield[F_TAUBY];
+  for (int q = 0; q < 8; ++q) d.str[q] = g.dstr[q];
+  d.maskT = g.dmaskT; d.maskU = g.dmaskU;
+
+  // ---- halo plan ----------------------------------------------------------------------------------
+  if (g.halo.build(g_comm, gi0, gj0, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, g_err, sizeof g_err)) return 1;
+  d.wrap_ew = g.halo.wrap_ew; d.wrap_ns = g.halo.wrap_ns;
+
+  CK(cudaStreamSynchronize(g.stream));
+  g.inited = true;
+  char buf[256];
+  snprintf(buf, sizeof buf, "dom %dx%d (ld %d) at global (%d,%d) of %dx%d; %d block(s) %dx%d; rank %d/%d; halo: %s",
+           nx, ny, d.ld, gi0, gj0, g.nxg, g.nyg, g.nblocks, nxb, nyb, g_comm.rank, g_comm.nranks, g.halo.describe().c_str());
+  g.desc = buf;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload / download
+// ------------------------------------------------------------------------------------------------
+static int do_upload(const evp_b200_fields_t *f) {
+  if (!g.inited) return fail("evp_b200_upload: evp_b200_init has not been called");
+  if (!f) return fail("evp_b200_upload: null fields");
+  const double *src[NF_STEP] = {
+      f->stressp_1, f->stressp_2, f->stressp_3, f->stressp_4, f->stressm_1, f->stressm_2, f->stressm_3, f->stressm_4,
+      f->stress12_1, f->stress12_2, f->stress12_3, f->stress12_4, f->strintxU, f->strintyU, f->taubxU, f->taubyU,
+      f->uvel, f->vvel, f->strength, f->cdn_ocnU, f->aiU, f->uocnU, f->vocnU, f->waterxU, f->wateryU, f->forcexU,
+      f->forceyU, f->umassdti, f->fmU, f->TbU};
+  const size_t bblk = g.nblk_elems * sizeof(double), bdom = g.ndom * sizeof(double);
+  CK(cudaSetDevice(g.device));
+  for (int q = 0; q < NF_STEP; ++q) {
+    if (!src[q]) return fail("evp_b200_upload: null field %d", q);
+    CK(cudaMemcpyAsync(g.stage[q], src[q], bblk, cudaMemcpyHostToDevice, g.stream));
+    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(g.dfield[q], g.stage[q], g.d_gsrc, (int)g.ndom);
+  }
+  if (!f->iceTmask || !f->iceUmask) return fail("evp_b200_upload: null mask");
+  CK(cudaMemcpyAsync(g.stage_mask, f->iceTmask, g.nblk_elems * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+  pack_mask<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(g.dmaskT, g.stage_mask, g.d_gsrc, (int)g.ndom);
+  CK(cudaMemcpyAsync(g.stage_mask, f->iceUmask, g.nblk_elems * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+  pack_mask<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(g.dmaskU, g.stage_mask, g.d_gsrc, (int)g.ndom);
+  CK(cudaGetLastError());
+  // both ping-pong copies start identical: cells off the ice are never written again
+  for (int q = 0; q < 12; ++q) CK(cudaMemcpyAsync(g.dsig1[q], g.dfield[F_SIG0 + q], bdom, cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaMemcpyAsync(g.du1, g.dfield[F_U], bdom, cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaMemcpyAsync(g.dv1, g.dfield[F_V], bdom, cudaMemcpyDeviceToDevice, g.stream));
+  g.cur = 0;
+  g.uploaded = true;
+  return 0;
+}
+
+static int do_download(evp_b200_fields_t *f) {
+  if (!g.inited || !g.uploaded) return fail("evp_b200_download: nothing uploaded");
+  double *dst[18] = {f->stressp_1, f->stressp_2, f->stressp_3, f->stressp_4, f->stressm_1, f->stressm_2,
+                     f->stressm_3, f->stressm_4, f->stress12_1, f->stress12_2, f->stress12_3, f->stress12_4,
+                     f->strintxU, f->strintyU, f->taubxU, f->taubyU, f->uvel, f->vvel};
+  const size_t bblk = g.nblk_elems * sizeof(double);
+  CK(cudaSetDevice(g.device));
+  const Dom &d = g.dom;
+  for (int q = 0; q < 18; ++q) {
+    if (!dst[q]) return fail("evp_b200_download: null field %d", q);
+    // the staging copy still holds the host array as uploaded: cells the loop does not own keep their values
+    if (q < 12)
+      unpack_f64<<<grid_blocks(g.n_sig), 256, 0, g.stream>>>(g.stage[q], d.sig[g.cur][q], g.d_sig_lin, g.d_sig_dom, g.n_sig);
+    else if (q < 16)
+      unpack_f64<<<grid_blocks(g.n_int), 256, 0, g.stream>>>(g.stage[q], g.dfield[q], g.d_int_lin, g.d_int_dom, g.n_int);
+    else
+      unpack_f64<<<grid_blocks(g.n_uv), 256, 0, g.stream>>>(g.stage[q], q == 16 ? d.u[g.cur] : d.v[g.cur], g.d_uv_lin, g.d_uv_dom, g.n_uv);
+    CK(cudaMemcpyAsync(dst[q], g.stage[q], bblk, cudaMemcpyDeviceToHost, g.stream));
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the subcycle loop
+// ------------------------------------------------------------------------------------------------
+static KParams kparams(const evp_b200_params_t *p) {
+  KParams k;
+  k.arlx1i = p->arlx1i; k.denom1 = p->denom1; k.revp = p->revp; k.brlx = p->brlx;
+  k.e_factor = p->e_factor; k.epp2i = p->epp2i; k.capping = p->capping; k.Ktens = p->Ktens;
+  k.u0 = p->u0; k.cosw = p->cosw; k.sinw = p->sinw; k.rhow = p->rhow;
+  return k;
+}
+
+static int choose_kernel(const evp_b200_params_t *p) {
+  int kern = p->kernel;
+  if (kern == EVP_B200_KERNEL_AUTO) kern = EVP_B200_KERNEL_FUSED;
+  return kern;
+}
+
+// enqueue the whole `do ksub = 1,ndte` loop (ice_dyn_evp.F90:859-913) on g.stream, starting from cur=0
+static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launches) {
+  const KParams k = kparams(p);
+  const bool exact = (p->mode == EVP_B200_MODE_EXACT);
+  const int kern = choose_kernel(p);
+  int cur = 0;
+  int64_t nl = 0;
+  for (int ksub = 0; ksub < p->ndte; ++ksub) {
+    if (kern == EVP_B200_KERNEL_SPLIT) {
+      CK(exact ? exact::launch_stress(g.dom, k, cur, g.stream) : fast::launch_stress(g.dom, k, cur, g.stream));
+      CK(exact ? exact::launch_stepu(g.dom, k, cur, g.stream) : fast::launch_stepu(g.dom, k, cur, g.stream));
+      nl += 2;
+    } else if (kern == EVP_B200_KERNEL_FUSED) {
+      CK(exact ? exact::launch_fused(g.dom, k, cur, g.stream) : fast::launch_fused(g.dom, k, cur, g.stream));
+      cur ^= 1;
+      nl += 1;
+    } else {
+      return fail("evp_b200_subcycle: kernel strategy %d not available", kern);
+    }
+    // the part of dyn_haloUpdate(uvel,vvel) that is not an on-rank wrap: neighbour ranks, tripole fold
+    int hl = 0;
+    if (g.halo.exchange(g_comm, g.dom.u[cur], g.dom.v[cur], g.stream, &hl, g_err, sizeof g_err)) return 1;
+    nl += hl;
+  }
+  *cur_end = cur;
+  *launches = nl;
+  return 0;
+}
+
+static int do_subcycle(const evp_b200_params_t *p) {
+  if (!g.inited || !g.uploaded) return fail("evp_b200_subcycle: no fields uploaded");
+  if (!p) return fail("evp_b200_subcycle: null params");
+  if (p->ndte < 0) return fail("evp_b200_subcycle: ndte < 0");
+  if (p->mode != EVP_B200_MODE_EXACT && p->mode != EVP_B200_MODE_FAST) return fail("evp_b200_subcycle: unknown mode %d", p->mode);
+  CK(cudaSetDevice(g.device));
+  const size_t bdom = g.ndom * sizeof(double);
+
+  // normalise to cur = 0 (a previous loop may have ended on copy 1)
+  if (g.cur == 1) {
+    std::swap(g.dom.u[0], g.dom.u[1]);
+    std::swap(g.dom.v[0], g.dom.v[1]);
+    for (int q = 0; q < 12; ++q) std::swap(g.dom.sig[0][q], g.dom.sig[1][q]);
+    g.cur = 0;
+    destroy_graph();  // pointers baked into the graph changed
+  }
+  // uvel_init = uvel at entry (ice_dyn_shared.F90:787-788; ice_dyn_evp1d.F90:939-940)
+  CK(cudaMemcpyAsync(g.duinit, g.dom.u[0], bdom, cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaMemcpyAsync(g.dvinit, g.dom.v[0], bdom, cudaMemcpyDeviceToDevice, g.stream));
+
+  const bool use_graph = g.halo.graph_safe();
+  int cur_end = 0;
+  int64_t nl = 0;
+  if (use_graph) {
+    if (!g.gexec || memcmp(&g.gparams, p, sizeof *p) != 0) {
+      destroy_graph();
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+      int rc = enqueue_loop(p, &cur_end, &nl);
+      cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+      CK(ce);
+      CK(cudaGraphInstantiate(&g.gexec, graph, 0));
+      CK(cudaGraphDestroy(graph));
+      g.gparams = *p; g.glaunches = nl; g.gcur_end = cur_end;
+    }
+    CK(cudaEventRecord(g.ev0, g.stream));
+    CK(cudaGraphLaunch(g.gexec, g.stream));
+    CK(cudaEventRecord(g.ev1, g.stream));
+    cur_end = g.gcur_end; nl = g.glaunches;
+  } else {
+    CK(cudaEventRecord(g.ev0, g.stream));
+    if (enqueue_loop(p, &cur_end, &nl)) return 1;
+    CK(cudaEventRecord(g.ev1, g.stream));
+  }
+  g.cur = cur_end;
+  g.last_launches = nl;
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1));
+  return 0;
+}
+
+}  // namespace evp
+
+// ------------------------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------------------------
+using namespace evp;
+
+extern "C" {
+
+const char *evp_b200_last_error(void) { return g_err; }
+const char *evp_b200_describe(void) { return g.desc.c_str(); }
+
+int evp_b200_set_device(int32_t dev) {
+  int n = 0;
+  CK(cudaGetDeviceCount(&n));
+  if (dev < 0 || dev >= n) return fail("evp_b200_set_device: device %d of %d", dev, n);
+  if (g.inited && dev != g.device) return fail("evp_b200_set_device: already initialised on device %d", g.device);
+  g.device = dev;
+  CK(cudaSetDevice(dev));
+  return 0;
+}
+
+int evp_b200_get_unique_id(void *id128) { return comm_get_unique_id(id128, g_err, sizeof g_err); }
+
+int evp_b200_comm_init(int32_t rank, int32_t nranks, const void *id128) {
+  if (g.inited) return fail("evp_b200_comm_init: call before evp_b200_init");
+  if (g.device < 0) CK(cudaGetDevice(&g.device));
+  CK(cudaSetDevice(g.device));
+  return comm_init(g_comm, rank, nranks, id128, g_err, sizeof g_err);
+}
+
+int evp_b200_init(const evp_b200_grid_t *grid) {
+  int rc = do_init(grid);
+  if (rc) { std::string keep = g_err; free_all(); snprintf(g_err, sizeof g_err, "%s", keep.c_str()); }
+  return rc;
+}
+
+int evp_b200_finalize(void) {
+  free_all();
+  comm_destroy(g_comm);
+  return 0;
+}
+
+int evp_b200_upload(const evp_b200_fields_t *f) { return do_upload(f); }
+int evp_b200_subcycle(const evp_b200_params_t *p) { return do_subcycle(p); }
+int evp_b200_download(evp_b200_fields_t *f) { return do_download(f); }
+
+int evp_b200_run_bgrid(const evp_b200_params_t *p, evp_b200_fields_t *f) {
+  if (do_upload(f)) return 1;
+  if (do_subcycle(p)) return 1;
+  return do_download(f);
+}
+
+int evp_b200_last_loop_ms(double *ms) { if (!ms) return fail("null"); *ms = g.last_ms; return 0; }
+int evp_b200_last_launches(int64_t *n) { if (!n) return fail("null"); *n = g.last_launches; return 0; }
+int evp_b200_stream(void **s) { if (!s) return fail("null"); *s = (void *)g.stream; return 0; }
+
+}  // extern "C"

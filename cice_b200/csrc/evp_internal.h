@@ -1,0 +1,56 @@
+// evp_internal.h -- types shared by the C-ABI translation unit and the two kernel translation
+// units (exact: -fmad=false, fast: default FMA contraction).  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace evp {
+
+// Device sub-domain ("dom"): this rank's rectangle of the global grid with its 1-cell ghost ring,
+// every field one 2-D array, i fastest, row pitch ld doubles.  dom (i,j): 0 = W/S ghost,
+// 1..nx / 1..ny interior, nx+1 / ny+1 = E/N ghost.  This is the reference's block with nghost=1
+// (ice_blocks.F90:48-49) for the rank's stitched rectangle of blocks.
+struct Dom {
+  int nx, ny;  // interior extent
+  int ld;      // row pitch (doubles)
+  int nyd;     // ny + 2
+  int wrap_ew; // E-W ghost columns are the rank's own opposite interior columns (cyclic, whole width local)
+  int wrap_ns; // same for N-S (cyclic)
+
+  // carried state
+  double *u[2], *v[2];  // velocity ping-pong (fused kernels read [cur], write [cur^1])
+  double *sig[2][12];   // stressp_1..4, stressm_1..4, stress12_1..4, same ping-pong
+  // per-step inputs at T points
+  const double *strength;
+  // static geometry at T points
+  const double *dxT, *dyT, *dxhy, *dyhx, *cxp, *cyp, *cxm, *cym, *DminTarea;
+  // per-step inputs at U points
+  const double *cdn, *aiu, *uocn, *vocn, *waterx, *watery, *forcex, *forcey, *umassdti, *fm, *TbU;
+  const double *uarear;
+  double *uinit, *vinit;
+  // diagnostics written by stepu
+  double *strintx, *strinty, *taubx, *tauby;
+  // split-kernel temporaries: the reference's strtmp(nx_block,ny_block,8) (ice_dyn_evp.F90:328)
+  double *str[8];
+  // ice masks, 1 byte per cell
+  const unsigned char *maskT, *maskU;
+};
+
+// scalars of set_evp_parameters (ice_dyn_shared.F90:453-486) and friends
+struct KParams {
+  double arlx1i, denom1, revp, brlx;
+  double e_factor, epp2i, capping, Ktens;
+  double u0, cosw, sinw, rhow;
+};
+
+// launchers implemented once per arithmetic mode (namespace exact / fast)
+#define EVP_DECLARE_LAUNCHERS(NS)                                                                   \
+  namespace NS {                                                                                    \
+  cudaError_t launch_stress(const Dom &d, const KParams &p, int cur, cudaStream_t s);               \
+  cudaError_t launch_stepu(const Dom &d, const KParams &p, int cur, cudaStream_t s);                \
+  cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s);                \
+  }
+EVP_DECLARE_LAUNCHERS(exact)
+EVP_DECLARE_LAUNCHERS(fast)
+
+}  // namespace evp

@@ -1,0 +1,106 @@
+"""Host-side mirror of the reference seam for the EVP path, over the C ABI (include/evp_b200.h).
+
+The reference dispatches its own 1-D solver with three calls (ice_dyn_evp1d.F90:25):
+
+    dyn_evp1d_init()            ice_dyn_evp.F90:153-155
+    dyn_evp1d_run(31 arrays)    ice_dyn_evp.F90:848-856
+    dyn_evp1d_finalize()
+
+and this module offers the same three with the same argument meaning, so the parity tests read
+like a caller of the reference would:
+
+    dyn_evp_b200_init(grid)               static block table + geometry, once
+    dyn_evp_b200_run(params, fields)      one dynamics step: the whole ndte subcycle loop, in place
+    dyn_evp_b200_finalize()
+
+`fields` is a dict of numpy arrays in the reference's memory layout: Fortran
+`a(nx_block,ny_block,max_blocks)` == C-ordered (max_blocks, ny_block, nx_block).  Errors raise
+EvpB200Error (the Fortran shim calls abort_ice instead).  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from ._lib import load, check, EvpB200Error  # noqa: F401
+
+_state = {"grid": None, "keep": None, "npl": 0}
+
+
+def set_device(ordinal):
+    check(load().evp_b200_set_device(int(ordinal)), "evp_b200_set_device")
+
+
+def get_unique_id():
+    buf = C.create_string_buffer(abi.UNIQUE_ID_BYTES)
+    check(load().evp_b200_get_unique_id(buf), "evp_b200_get_unique_id")
+    return buf.raw
+
+
+def comm_init(rank, nranks, unique_id):
+    buf = C.create_string_buffer(bytes(unique_id), abi.UNIQUE_ID_BYTES)
+    check(load().evp_b200_comm_init(int(rank), int(nranks), buf), "evp_b200_comm_init")
+
+
+def dyn_evp_b200_init(grid):
+    """grid: dict as built by cice_b200.synth (block table + static geometry of THIS rank)."""
+    g, keep = abi.make_grid(grid)
+    check(load().evp_b200_init(C.byref(g)), "evp_b200_init")
+    _state.update(grid=g, keep=keep, npl=int(grid["nx_block"]) * int(grid["ny_block"]) * int(grid["max_blocks"]))
+
+
+def _fields(fields):
+    if _state["grid"] is None:
+        raise EvpB200Error("dyn_evp_b200_init has not been called")
+    return abi.make_fields(fields, _state["npl"])
+
+
+def dyn_evp_b200_run(params, fields):
+    """the hot path: host arrays in, host arrays out (inout arrays are updated in place)."""
+    p = abi.make_params(params)
+    f, keep = _fields(fields)
+    check(load().evp_b200_run_bgrid(C.byref(p), C.byref(f)), "evp_b200_run_bgrid")
+    return fields
+
+
+def upload(fields):
+    f, keep = _fields(fields)
+    check(load().evp_b200_upload(C.byref(f)), "evp_b200_upload")
+
+
+def subcycle(params):
+    p = abi.make_params(params)
+    check(load().evp_b200_subcycle(C.byref(p)), "evp_b200_subcycle")
+
+
+def download(fields):
+    f, keep = _fields(fields)
+    check(load().evp_b200_download(C.byref(f)), "evp_b200_download")
+    return fields
+
+
+def last_loop_ms():
+    v = C.c_double()
+    check(load().evp_b200_last_loop_ms(C.byref(v)), "evp_b200_last_loop_ms")
+    return v.value
+
+
+def last_launches():
+    v = C.c_int64()
+    check(load().evp_b200_last_launches(C.byref(v)), "evp_b200_last_launches")
+    return v.value
+
+
+def stream_handle():
+    v = C.c_void_p()
+    check(load().evp_b200_stream(C.byref(v)), "evp_b200_stream")
+    return v.value
+
+
+def describe():
+    return load().evp_b200_describe().decode()
+
+
+def dyn_evp_b200_finalize():
+    check(load().evp_b200_finalize(), "evp_b200_finalize")
+    _state.update(grid=None, keep=None, npl=0)

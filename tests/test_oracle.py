@@ -1,0 +1,177 @@
+"""CPU tests of the oracle (the checker must be trusted before it checks anything).
+
+The reference stores no golden vectors for this path, so the oracle is pinned by
+the properties the reference asserts: bit-for-bit results under any block decomposition
+(decomp_suite / perf_suite BFB columns), 2-D == 1-D formulation (core1d.F90:196), the halochk
+closed-form halo values, plus an independent numpy restatement of one subcycle.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cice_b200 import abi, synth
+from tests.util import run_oracle, assert_bitwise
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_checksums.json")
+
+
+def gathered(case, f):
+    return {n: synth.gather(f[n], case.blocks) for n in abi.FIELDS_INOUT}
+
+
+@pytest.mark.parametrize("bs", [(12, 10), (8, 7), (24, 5), (5, 20), (7, 9)])
+def test_decomposition_invariance_tiny(oracle_mod, bs):
+    ref = synth.make_case("tiny", seed=11)
+    G = gathered(ref, run_oracle(oracle_mod, ref, 1))
+    c = synth.make_case("tiny", seed=11, block_size=bs)
+    g2 = gathered(c, run_oracle(oracle_mod, c))
+    for n in abi.FIELDS_INOUT:
+        assert np.array_equal(G[n], g2[n]), n
+
+
+@pytest.mark.parametrize("bs", [(25, 29), (32, 40)])
+def test_decomposition_invariance_gx3(oracle_mod, bs):
+    ref = synth.make_case("gx3", ndte=20)
+    G = gathered(ref, run_oracle(oracle_mod, ref, 1))
+    c = synth.make_case("gx3", ndte=20, block_size=bs)
+    g2 = gathered(c, run_oracle(oracle_mod, c))
+    for n in abi.FIELDS_INOUT:
+        assert np.array_equal(G[n], g2[n]), n
+
+
+def test_thread_count_invariance(oracle_mod):
+    c = synth.make_case("gx3", ndte=10, block_size=(25, 29), seed=3)
+    assert_bitwise(run_oracle(oracle_mod, c, 1), run_oracle(oracle_mod, c, 4))
+
+
+@pytest.mark.parametrize("cfg,kw", [("tiny", dict(seed=2)), ("gx3", dict(ndte=25)), ("gx3", dict(ndte=8, seed=9, revised_evp=True))])
+def test_2d_equals_1d(oracle_mod, cfg, kw):
+    """standard_2d vs shared_mem_1d: same arithmetic, gather-indexed, geometry recomputed from HTE/HTN."""
+    c = synth.make_case(cfg, **kw)
+    f2 = run_oracle(oracle_mod, c, 1)
+    f1 = c.copy_fields()
+    oracle_mod.evp_run_bgrid_1d(c.grid, c.X["HTE"], c.X["HTN"], 1e-11, c.params, f1, 1)
+    for n in abi.FIELDS_INOUT:
+        a, b = synth.gather(f2[n], c.blocks), synth.gather(f1[n], c.blocks)
+        assert np.array_equal(a, b), n
+
+
+# ---- independent numpy restatement of ONE subcycle (array form, written from the equations) -------
+def numpy_subcycle(c, f):
+    g, p = c.grid, c.params
+    A = lambda a: a[0]  # single block
+    u, v = A(f["uvel"]).copy(), A(f["vvel"]).copy()
+    sh = lambda a, di, dj: np.roll(np.roll(a, -dj, 0), -di, 1)  # value at (i+di, j+dj)
+    ucc, uee, use_, une = u, sh(u, -1, 0), sh(u, 0, -1), sh(u, -1, -1)
+    vcc, vee, vse, vne = v, sh(v, -1, 0), sh(v, 0, -1), sh(v, -1, -1)
+    dxT, dyT, cxp, cyp, cxm, cym = (A(g[k]) for k in ("dxT", "dyT", "cxp", "cyp", "cxm", "cym"))
+    dxhy, dyhx, dmin = A(g["dxhy"]), A(g["dyhx"]), A(g["DminTarea"])
+    div = [cyp * ucc - dyT * uee + cxp * vcc - dxT * vse, cym * uee + dyT * ucc + cxp * vee - dxT * vne,
+           cym * une + dyT * use_ + cxm * vne + dxT * vee, cyp * use_ - dyT * une + cxm * vse + dxT * vcc]
+    ten = [-cym * ucc - dyT * uee + cxm * vcc + dxT * vse, -cyp * uee + dyT * ucc + cxm * vee + dxT * vne,
+           -cyp * une + dyT * use_ + cxp * vne - dxT * vee, -cym * use_ - dyT * une + cxp * vse - dxT * vcc]
+    shr = [-cym * vcc - dyT * vee - cxm * ucc - dxT * use_, -cyp * vee + dyT * vcc - cxm * uee - dxT * une,
+           -cyp * vne + dyT * vse - cxp * une + dxT * uee, -cym * vse - dyT * vne - cxp * use_ + dxT * ucc]
+    mT = A(f["iceTmask"]).astype(bool).copy()
+    ny_b, nx_b = mT.shape
+    mT[0, :] = False
+    mT[:, 0] = False
+    P, M, S = [], [], []
+    relax = 1.0 - p["arlx1i"] * p["revp"]
+    for k in range(4):
+        Delta = np.sqrt(div[k] * div[k] + p["e_factor"] * (ten[k] * ten[k] + shr[k] * shr[k]))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tmp = p["capping"] * (A(f["strength"]) / np.maximum(Delta, dmin)) + (1 - p["capping"]) * (A(f["strength"]) / (Delta + dmin))
+        z = (1 + p["Ktens"]) * tmp
+        rp = (1 - p["Ktens"]) * tmp * Delta
+        e = p["epp2i"] * z
+        sp = (A(f[f"stressp_{k+1}"]) * relax + p["arlx1i"] * (z * div[k] - rp)) * p["denom1"]
+        sm = (A(f[f"stressm_{k+1}"]) * relax + p["arlx1i"] * e * ten[k]) * p["denom1"]
+        s12 = (A(f[f"stress12_{k+1}"]) * relax + p["arlx1i"] * 0.5 * e * shr[k]) * p["denom1"]
+        P.append(np.where(mT, sp, A(f[f"stressp_{k+1}"])))
+        M.append(np.where(mT, sm, A(f[f"stressm_{k+1}"])))
+        S.append(np.where(mT, s12, A(f[f"stress12_{k+1}"])))
+    p111 = 1.0 / 9.0; p055 = p111 * 0.5; p027 = p055 * 0.5; p166 = 1.0 / 6.0; p222 = 2.0 / 9.0; p333 = 1.0 / 3.0
+    ssn = lambda X: X[0] + X[1]; sss = lambda X: X[2] + X[3]; sse = lambda X: X[0] + X[3]; ssw = lambda X: X[1] + X[2]
+    s1 = lambda X, w: (X[0] + X[2]) * w; s2 = lambda X, w: (X[1] + X[3]) * w
+    cs = lambda X, a, b: [a * X[0] + s2(X, b) + (b * 0.5 if a == p111 else p055) * X[2],
+                          a * X[1] + s1(X, b) + (b * 0.5 if a == p111 else p055) * X[3],
+                          a * X[2] + s2(X, b) + (b * 0.5 if a == p111 else p055) * X[0],
+                          a * X[3] + s1(X, b) + (b * 0.5 if a == p111 else p055) * X[1]]
+    cp, cm, c12 = cs(P, p111, p055), cs(M, p111, p055), cs(S, p222, p111)  # [ne, nw, sw, se]
+    str12ew = 0.5 * dxT * (p333 * sse(S) + p166 * ssw(S)); str12we = 0.5 * dxT * (p333 * ssw(S) + p166 * sse(S))
+    str12ns = 0.5 * dyT * (p333 * ssn(S) + p166 * sss(S)); str12sn = 0.5 * dyT * (p333 * sss(S) + p166 * ssn(S))
+    st = [None] * 8
+    a = 0.25 * dyT * (p333 * ssn(P) + p166 * sss(P)); b = 0.25 * dyT * (p333 * ssn(M) + p166 * sss(M))
+    st[0] = -a - b - str12ew + dxhy * (-cp[0] + cm[0]) + dyhx * c12[0]
+    st[1] = a + b - str12we + dxhy * (-cp[1] + cm[1]) + dyhx * c12[1]
+    a = 0.25 * dyT * (p333 * sss(P) + p166 * ssn(P)); b = 0.25 * dyT * (p333 * sss(M) + p166 * ssn(M))
+    st[2] = -a - b + str12ew + dxhy * (-cp[3] + cm[3]) + dyhx * c12[3]
+    st[3] = a + b + str12we + dxhy * (-cp[2] + cm[2]) + dyhx * c12[2]
+    a = 0.25 * dxT * (p333 * sse(P) + p166 * ssw(P)); b = 0.25 * dxT * (p333 * sse(M) + p166 * ssw(M))
+    st[4] = -a + b - str12ns - dyhx * (cp[0] + cm[0]) + dxhy * c12[0]
+    st[5] = a - b - str12sn - dyhx * (cp[3] + cm[3]) + dxhy * c12[3]
+    a = 0.25 * dxT * (p333 * ssw(P) + p166 * sse(P)); b = 0.25 * dxT * (p333 * ssw(M) + p166 * sse(M))
+    st[6] = -a + b + str12ns - dyhx * (cp[1] + cm[1]) + dxhy * c12[1]
+    st[7] = a - b + str12sn - dyhx * (cp[2] + cm[2]) + dxhy * c12[2]
+    st = [np.where(mT, x, 0.0) for x in st]
+    # momentum
+    mU = A(f["iceUmask"]).astype(bool)
+    F = lambda k: A(f[k])
+    vrel = F("aiU") * p["rhow"] * F("cdn_ocnU") * np.sqrt((F("uocnU") - u) * (F("uocnU") - u) + (F("vocnU") - v) * (F("vocnU") - v))
+    taux, tauy = vrel * F("waterxU"), vrel * F("wateryU")
+    Cb = F("TbU") / (np.sqrt(u * u + v * v) + p["u0"])
+    cca = (p["brlx"] + p["revp"]) * F("umassdti") + vrel * p["cosw"] + Cb
+    ccb = F("fmU") + np.copysign(1.0, F("fmU")) * vrel * p["sinw"]
+    ab2 = cca * cca + ccb * ccb
+    sx = A(g["uarear"]) * (st[0] + sh(st[1], 1, 0) + sh(st[2], 0, 1) + sh(st[3], 1, 1))
+    sy = A(g["uarear"]) * (st[4] + sh(st[5], 0, 1) + sh(st[6], 1, 0) + sh(st[7], 1, 1))
+    cc1 = sx + F("forcexU") + taux + F("umassdti") * (p["brlx"] * u + p["revp"] * u)
+    cc2 = sy + F("forceyU") + tauy + F("umassdti") * (p["brlx"] * v + p["revp"] * v)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        un = np.where(mU, (cca * cc1 + ccb * cc2) / ab2, u)
+        vn = np.where(mU, (cca * cc2 - ccb * cc1) / ab2, v)
+    out = {f"stressp_{k+1}": P[k] for k in range(4)}
+    out.update({f"stressm_{k+1}": M[k] for k in range(4)})
+    out.update({f"stress12_{k+1}": S[k] for k in range(4)})
+    out.update(uvel=un, vvel=vn, strintxU=np.where(mU, sx, 0), strintyU=np.where(mU, sy, 0),
+               taubxU=np.where(mU, -un * Cb, 0), taubyU=np.where(mU, -vn * Cb, 0))
+    return out
+
+
+@pytest.mark.parametrize("cfg,seed", [("tiny", 1), ("gx3", 20260101)])
+def test_one_subcycle_against_numpy(oracle_mod, cfg, seed):
+    """set S2 (random velocities / stresses / TbU): one subcycle of the C oracle equals an array-form
+    numpy evaluation of the same equations bit for bit on every interior cell."""
+    c = synth.make_case(cfg, seed=seed, ndte=1)
+    fo = run_oracle(oracle_mod, c, 1)
+    fn = numpy_subcycle(c, c.fields)
+    b = c.blocks
+    sl = (slice(b.jlo[0] - 1, b.jhi[0]), slice(b.ilo[0] - 1, b.ihi[0]))
+    for n in abi.FIELDS_INOUT:
+        assert np.array_equal(fo[n][0][sl], fn[n][sl]), n
+
+
+def test_zero_forcing_stays_at_rest(oracle_mod):
+    c = synth.make_case("tiny")
+    for n in ("uvel", "vvel", "uocnU", "vocnU", "waterxU", "wateryU", "forcexU", "forceyU"):
+        c.fields[n][:] = 0.0
+    f = run_oracle(oracle_mod, c, 1)
+    for n in ("uvel", "vvel") + abi.STRESS[4:]:
+        assert np.abs(f[n]).max() == 0.0, n
+
+
+def test_golden_checksums(oracle_mod):
+    """regression pin of the oracle itself (generated by tests/golden/make_golden.py from this oracle;
+    NOT reference output -- none can be produced in this image)."""
+    with open(GOLDEN) as fh:
+        gold = json.load(fh)
+    for name, spec in gold.items():
+        c = synth.make_case(**spec["case"])
+        f = run_oracle(oracle_mod, c, 1)
+        for n, want in spec["sums"].items():
+            got = hashlib.sha256(np.ascontiguousarray(synth.gather(f[n], c.blocks)).tobytes()).hexdigest()
+            assert got == want, (name, n)
