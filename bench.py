@@ -271,7 +271,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "split", "fused", "persistent"])
-    ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--mode", default="exact", choices=["fast", "exact"])
     ap.add_argument("--workload", default="gx1")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -109,6 +109,13 @@ struct Ctx {
   int gcur_end = 0;
 
   HaloPlan halo;
+
+  // KERNEL_PERSISTENT
+  PersistPlan pplan{};
+  bool persist_ok = false;
+  std::string persist_why;
+  unsigned *d_progress = nullptr;
+  int num_sms = 0;
 };
 static Ctx g;
 static CommState g_comm;
@@ -134,7 +141,7 @@ static int free_all() {
   for (auto &p : g.dstr) F(p);
   F(g.dmaskT); F(g.dmaskU);
   for (auto &p : g.stage) F(p);
-  F(g.stage_mask); F(g.d_gsrc);
+  F(g.stage_mask); F(g.d_gsrc); F(g.d_progress);
   F(g.d_uv_lin); F(g.d_uv_dom); F(g.d_sig_lin); F(g.d_sig_dom); F(g.d_int_lin); F(g.d_int_dom);
   g.halo.release();
   if (g.ev0) cudaEventDestroy(g.ev0);
@@ -149,6 +156,47 @@ static int upload_vec(T *&dptr, const std::vector<T> &h) {
   CK(cudaMalloc(&dptr, std::max<size_t>(h.size(), 1) * sizeof(T)));
   if (!h.empty()) CK(cudaMemcpy(dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
   return 0;
+}
+
+// choose the persistent tiling: at most one tile per SM, every tile's T cells fit 2 per thread, smallest
+// tile wins (it bounds the time of a subcycle); then keep as many static arrays in shared memory as fit
+static void plan_persist() {
+  const Dom &d = g.dom;
+  const int cap_cells = 2 * PERSIST_THREADS;
+  const size_t smem_max = 232448;  // 227 KB per CTA on sm_100
+  PersistPlan best{};
+  long best_cost = -1;
+  for (int ntx = 1; ntx <= g.num_sms; ++ntx) {
+    for (int nty = 1; ntx * nty <= g.num_sms; ++nty) {
+      const int bx = (d.nx + ntx - 1) / ntx, by = (d.ny + nty - 1) / nty;
+      const int tx2 = (d.nx + bx - 1) / bx, ty2 = (d.ny + by - 1) / by;  // drop empty tiles
+      if (tx2 != ntx || ty2 != nty) continue;
+      const int nT = (bx + 1) * (by + 1), nU = bx * by, nring = (bx + 2) * (by + 2);
+      if (nT > cap_cells) continue;
+      const size_t base = 8ull * (2 * nring + 8 * nT + nU) + nT + nU;  // u, v, str, cvrel + masks
+      if (base > smem_max) continue;
+      const long cost = (long)nT * 4096 - bx;  // smallest tile, then the widest rows
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best.ntx = ntx; best.nty = nty; best.bx = bx; best.by = by; best.nT = nT; best.nU = nU;
+      }
+    }
+  }
+  g.persist_ok = false;
+  if (best_cost < 0) { g.persist_why = "no tiling with <= 1 tile per SM fits the sub-domain on chip"; return; }
+  if (g.halo.n_dst != 0 || !g.halo.peers.empty()) { g.persist_why = "the halo needs an exchange between subcycles (neighbour ranks or tripole fold)"; return; }
+  PersistPlan &pp = best;
+  const int nring = (pp.bx + 2) * (pp.by + 2);
+  size_t used = 8ull * (2 * nring + 8 * pp.nT + pp.nU) + pp.nT + pp.nU;
+  pp.kT = 0; pp.kU = 1;
+  while (pp.kT < 10 && used + 8ull * pp.nT <= smem_max) { ++pp.kT; used += 8ull * pp.nT; }
+  while (pp.kU < 11 && used + 8ull * pp.nU <= smem_max) { ++pp.kU; used += 8ull * pp.nU; }
+  pp.off_u = 0; pp.off_v = nring; pp.off_str = 2 * nring; pp.off_T = pp.off_str + 8 * pp.nT;
+  pp.off_U = pp.off_T + pp.kT * pp.nT;
+  pp.off_mask = 8 * (pp.off_U + pp.kU * pp.nU);
+  pp.smem_bytes = (unsigned)(pp.off_mask + pp.nT + pp.nU);
+  g.pplan = pp;
+  g.persist_ok = true;
 }
 
 static int do_init(const evp_b200_grid_t *gr) {
@@ -273,11 +321,24 @@ static int do_init(const evp_b200_grid_t *gr) {
   if (g.halo.build(g_comm, gi0, gj0, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, g_err, sizeof g_err)) return 1;
   d.wrap_ew = g.halo.wrap_ew; d.wrap_ns = g.halo.wrap_ns;
 
+  // ---- persistent tiling ---------------------------------------------------------------------------
+  CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, g.device));
+  plan_persist();
+  if (g.persist_ok) {
+    CK(cudaMalloc(&g.d_progress, sizeof(unsigned) * g.pplan.ntx * g.pplan.nty));
+    g.pplan.progress = g.d_progress;
+  }
+
   CK(cudaStreamSynchronize(g.stream));
   g.inited = true;
-  char buf[256];
-  snprintf(buf, sizeof buf, "dom %dx%d (ld %d) at global (%d,%d) of %dx%d; %d block(s) %dx%d; rank %d/%d; halo: %s",
-           nx, ny, d.ld, gi0, gj0, g.nxg, g.nyg, g.nblocks, nxb, nyb, g_comm.rank, g_comm.nranks, g.halo.describe().c_str());
+  char buf[512], pbuf[200];
+  if (g.persist_ok)
+    snprintf(pbuf, sizeof pbuf, "persistent: %dx%d tiles of %dx%d on %d SMs, smem %u B, kT=%d kU=%d", g.pplan.ntx, g.pplan.nty,
+             g.pplan.bx, g.pplan.by, g.num_sms, g.pplan.smem_bytes, g.pplan.kT, g.pplan.kU);
+  else
+    snprintf(pbuf, sizeof pbuf, "persistent: unavailable (%s)", g.persist_why.c_str());
+  snprintf(buf, sizeof buf, "dom %dx%d (ld %d) at global (%d,%d) of %dx%d; %d block(s) %dx%d; rank %d/%d; halo: %s; %s",
+           nx, ny, d.ld, gi0, gj0, g.nxg, g.nyg, g.nblocks, nxb, nyb, g_comm.rank, g_comm.nranks, g.halo.describe().c_str(), pbuf);
   g.desc = buf;
   return 0;
 }
@@ -352,7 +413,7 @@ static KParams kparams(const evp_b200_params_t *p) {
 
 static int choose_kernel(const evp_b200_params_t *p) {
   int kern = p->kernel;
-  if (kern == EVP_B200_KERNEL_AUTO) kern = EVP_B200_KERNEL_FUSED;
+  if (kern == EVP_B200_KERNEL_AUTO) kern = g.persist_ok ? EVP_B200_KERNEL_PERSISTENT : EVP_B200_KERNEL_FUSED;
   return kern;
 }
 
@@ -363,6 +424,19 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
   const int kern = choose_kernel(p);
   int cur = 0;
   int64_t nl = 0;
+  if (kern == EVP_B200_KERNEL_PERSISTENT) {
+    if (!g.persist_ok) return fail("evp_b200_subcycle: persistent kernel unavailable: %s", g.persist_why.c_str());
+    if (p->ndte > 0) {
+      PersistPlan pp = g.pplan;
+      pp.ndte = p->ndte;
+      pp.use_init = (p->revp != 0.0);
+      CK(cudaMemsetAsync(g.d_progress, 0, sizeof(unsigned) * pp.ntx * pp.nty, g.stream));
+      CK(exact ? exact::launch_persist(g.dom, k, pp, g.stream) : fast::launch_persist(g.dom, k, pp, g.stream));
+    }
+    *cur_end = p->ndte & 1;
+    *launches = p->ndte > 0 ? 1 : 0;
+    return 0;
+  }
   for (int ksub = 0; ksub < p->ndte; ++ksub) {
     if (kern == EVP_B200_KERNEL_SPLIT) {
       CK(exact ? exact::launch_stress(g.dom, k, cur, g.stream) : fast::launch_stress(g.dom, k, cur, g.stream));

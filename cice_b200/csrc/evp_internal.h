@@ -43,12 +43,28 @@ struct KParams {
   double u0, cosw, sinw, rhow;
 };
 
+// KERNEL_PERSISTENT tiling (see evp_persist.cu)
+#define PERSIST_THREADS 512
+struct PersistPlan {
+  int ntx, nty;   // tile grid (one CTA per tile, all co-resident)
+  int bx, by;     // U points per tile
+  int nT, nU;     // (bx+1)*(by+1) T cells, bx*by U points
+  int ndte;
+  int kT, kU;     // how many static T / U arrays are kept in shared memory
+  int use_init;   // revised EVP reads uvel_init/vvel_init
+  unsigned *progress;  // [ntx*nty] subcycles published by each tile
+  int off_u, off_v, off_str, off_T, off_U;  // shared-memory offsets in doubles
+  int off_mask;                             // in bytes
+  unsigned smem_bytes;
+};
+
 // launchers implemented once per arithmetic mode (namespace exact / fast)
 #define EVP_DECLARE_LAUNCHERS(NS)                                                                   \
   namespace NS {                                                                                    \
   cudaError_t launch_stress(const Dom &d, const KParams &p, int cur, cudaStream_t s);               \
   cudaError_t launch_stepu(const Dom &d, const KParams &p, int cur, cudaStream_t s);                \
   cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s);                \
+  cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s); \
   }
 EVP_DECLARE_LAUNCHERS(exact)
 EVP_DECLARE_LAUNCHERS(fast)

@@ -1,0 +1,272 @@
+// evp_persist.cu -- KERNEL_PERSISTENT: all ndte subcycles of the EVP loop in ONE cooperative launch.
+//
+// One CTA per SM owns a bx x by tile of U points for the whole loop (ice_dyn_evp.F90:859-913):
+//   * the 12 stress components of its (bx+1) x (by+1) T cells live in REGISTERS (2 cells per thread),
+//   * u, v of the tile plus a one-cell ring, the 8 `str` terms, the ice masks and as many of the static
+//     per-cell coefficients as fit live in SHARED MEMORY (the rest is re-read through L1/L2),
+//   * per subcycle only the tile's edge velocities go through global memory (L2): the tile stores them
+//     into the ping-pong velocity arrays, publishes a per-tile progress counter with a release store,
+//     and its up-to-8 neighbours spin on that counter (acquire) before they refresh their ring.
+//     There is no grid-wide barrier; tiles drift by at most one subcycle (double buffering covers it).
+//   * T cells on a tile's E/N overlap edge are relaxed redundantly by both tiles (same inputs, same
+//     arithmetic -> identical bits), exactly like the reference evaluates N/E ghost T cells per block
+//     (ice_dyn_shared.F90:740-749).
+// Compiled twice like evp_kernels.cu (namespace exact: -fmad=false; namespace fast).
+#include "evp_math.cuh"
+
+#ifndef EVP_NS
+#error "compile with -DEVP_NS=exact or -DEVP_NS=fast"
+#endif
+
+namespace evp {
+namespace EVP_NS {
+
+constexpr int PNT = PERSIST_THREADS;  // threads per CTA
+constexpr int PCELLS = 2;             // T cells (and U points) per thread
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// static per-cell arrays, in smem-priority order
+enum { T_STRENGTH = 0, T_DXT, T_DYT, T_DXHY, T_DYHX, T_CXP, T_CYP, T_CXM, T_CYM, T_DMIN, T_COUNT };
+enum { U_CVREL = 0, U_UOCN, U_VOCN, U_WATERX, U_WATERY, U_FORCEX, U_FORCEY, U_UMASSDTI, U_FM, U_UAREAR, U_TBU, U_COUNT };
+
+__global__ void __launch_bounds__(PNT, 1)
+persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k, const __grid_constant__ PersistPlan pp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sm = reinterpret_cast<double *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int ttx = tile % pp.ntx, tty = tile / pp.ntx;
+  const int bx = pp.bx, by = pp.by;
+  const int i0 = 1 + ttx * bx, j0 = 1 + tty * by;  // first U point / T cell of the tile (dom coords)
+  const int tw = bx + 1, nT = pp.nT, nU = pp.nU;    // T pitch
+  const int uw = bx + 2;                            // u/v pitch (ring included)
+  const int nring = (bx + 2) * (by + 2);
+
+  double *su = sm + pp.off_u, *sv = sm + pp.off_v, *sstr = sm + pp.off_str;
+  double *sT = sm + pp.off_T, *sU = sm + pp.off_U;
+  unsigned char *smT = smem_raw + pp.off_mask, *smU = smT + nT;
+
+  const double *gT[T_COUNT] = {d.strength, d.dxT, d.dyT, d.dxhy, d.dyhx, d.cxp, d.cyp, d.cxm, d.cym, d.DminTarea};
+  const double *gU[U_COUNT] = {nullptr, d.uocn, d.vocn, d.waterx, d.watery, d.forcex, d.forcey, d.umassdti, d.fm, d.uarear, d.TbU};
+
+  // ---------------- prologue: make the tile resident ------------------------------------------------
+  Sigma sg[PCELLS];
+  size_t gcT[PCELLS];  // global index of my T cells
+  bool actT[PCELLS], ownT[PCELLS];
+#pragma unroll
+  for (int r = 0; r < PCELLS; ++r) {
+    const int t = tid + r * PNT;
+    const int li = t % tw, lj = t / tw;
+    const int i = i0 + li, j = j0 + lj;
+    const bool in = (t < nT) && (i <= d.nx + 1) && (j <= d.ny + 1);
+    gcT[r] = in ? (size_t)j * d.ld + i : (size_t)d.ld + 1;
+    actT[r] = in && d.maskT[gcT[r]];
+    ownT[r] = actT[r] && (li < bx || i == d.nx + 1) && (lj < by || j == d.ny + 1);
+    if (t < nT) {
+      smT[t] = actT[r];
+#pragma unroll
+      for (int q = 0; q < T_COUNT; ++q)
+        if (q < pp.kT) sT[q * nT + t] = in ? gT[q][gcT[r]] : 0.0;
+    }
+    if (actT[r]) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        sg[r].p[q] = d.sig[0][q][gcT[r]];
+        sg[r].m[q] = d.sig[0][4 + q][gcT[r]];
+        sg[r].s12[q] = d.sig[0][8 + q][gcT[r]];
+      }
+    }
+  }
+  size_t gcU[PCELLS];
+  bool actU[PCELLS];
+  int edgeU[PCELLS];
+#pragma unroll
+  for (int r = 0; r < PCELLS; ++r) {
+    const int uu = tid + r * PNT;
+    const int li = uu % bx, lj = uu / bx;
+    const int i = i0 + li, j = j0 + lj;
+    const bool in = (uu < nU) && (i <= d.nx) && (j <= d.ny);
+    gcU[r] = in ? (size_t)j * d.ld + i : (size_t)d.ld + 1;
+    actU[r] = in && d.maskU[gcU[r]];
+    // points whose value a neighbouring tile (or a wrapped ghost copy) needs
+    edgeU[r] = in && (li == 0 || li == bx - 1 || lj == 0 || lj == by - 1 || i == d.nx || j == d.ny);
+    if (uu < nU) {
+      smU[uu] = actU[r];
+      if (in) {
+        sU[U_CVREL * nU + uu] = d.aiu[gcU[r]] * k.rhow * d.cdn[gcU[r]];  // aiX*rhow*Cw, left to right
+#pragma unroll
+        for (int q = 1; q < U_COUNT; ++q)
+          if (q < pp.kU) sU[q * nU + uu] = gU[q][gcU[r]];
+      }
+    }
+  }
+  // u, v of the tile and its ring (copy 0 holds the state at entry)
+  for (int c = tid; c < nring; c += PNT) {
+    const int li = c % uw, lj = c / uw;
+    const int i = i0 - 1 + li, j = j0 - 1 + lj;
+    const bool in = (i <= d.nx + 1) && (j <= d.ny + 1);
+    const size_t g = in ? (size_t)j * d.ld + i : 0;
+    su[c] = in ? d.u[0][g] : 0.0;
+    sv[c] = in ? d.v[0][g] : 0.0;
+  }
+  // neighbour tiles whose edge values feed my ring (E-W / N-S wrap where the ghost ring aliases the interior)
+  int nb = -1;
+  if (tid < 8) {
+    const int dxs[8] = {-1, 1, 0, 0, -1, 1, -1, 1}, dys[8] = {0, 0, -1, 1, -1, -1, 1, 1};
+    int nx_ = ttx + dxs[tid], ny_ = tty + dys[tid];
+    if (d.wrap_ew) nx_ = (nx_ + pp.ntx) % pp.ntx;
+    if (d.wrap_ns) ny_ = (ny_ + pp.nty) % pp.nty;
+    if (nx_ >= 0 && nx_ < pp.ntx && ny_ >= 0 && ny_ < pp.nty) nb = ny_ * pp.ntx + nx_;
+    if (nb == tile) nb = -1;
+  }
+  __syncthreads();
+
+  // ---------------- the subcycle loop ----------------------------------------------------------------
+  for (int ksub = 0; ksub < pp.ndte; ++ksub) {
+    const int cur = ksub & 1, nxt = cur ^ 1;
+    if (ksub > 0) {
+      // wait until every neighbour has published subcycle ksub, then refresh the ring from copy `cur`
+      if (nb >= 0)
+        while (ld_acquire(pp.progress + nb) < (unsigned)ksub) {}
+      __syncthreads();
+      const double *__restrict__ U = d.u[cur];
+      const double *__restrict__ V = d.v[cur];
+      const int nedge = 2 * (bx + 2) + 2 * by;
+      for (int e = tid; e < nedge; e += PNT) {
+        int li, lj;
+        if (e < bx + 2) { li = e; lj = 0; }
+        else if (e < 2 * (bx + 2)) { li = e - (bx + 2); lj = by + 1; }
+        else if (e < 2 * (bx + 2) + by) { li = 0; lj = 1 + e - 2 * (bx + 2); }
+        else { li = bx + 1; lj = 1 + e - 2 * (bx + 2) - by; }
+        const int i = i0 - 1 + li, j = j0 - 1 + lj;
+        if (i <= d.nx + 1 && j <= d.ny + 1) {
+          const size_t g = (size_t)j * d.ld + i;
+          su[lj * uw + li] = __ldcg(U + g);  // written by another SM: bypass L1
+          sv[lj * uw + li] = __ldcg(V + g);
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- stress: relax my T cells, str -> shared -----------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < PCELLS; ++r) {
+      const int t = tid + r * PNT;
+      double str[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (actT[r]) {
+        const int li = t % tw, lj = t / tw;
+        const int c = (lj + 1) * uw + (li + 1);
+        double tv[T_COUNT];
+#pragma unroll
+        for (int q = 0; q < T_COUNT; ++q) tv[q] = (q < pp.kT) ? sT[q * nT + t] : __ldg(gT[q] + gcT[r]);
+        stress_point(su[c], sv[c], su[c - 1], sv[c - 1], su[c - uw], sv[c - uw], su[c - uw - 1], sv[c - uw - 1],
+                     tv[T_DXT], tv[T_DYT], tv[T_DXHY], tv[T_DYHX], tv[T_CXP], tv[T_CYP], tv[T_CXM], tv[T_CYM],
+                     tv[T_DMIN], tv[T_STRENGTH], k, sg[r], str);
+      }
+      if (t < nT) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sstr[q * nT + t] = str[q];
+      }
+    }
+    __syncthreads();
+
+    // ---- momentum: advance my U points ---------------------------------------------------------------
+    const bool last = (ksub == pp.ndte - 1);
+#pragma unroll
+    for (int r = 0; r < PCELLS; ++r) {
+      if (actU[r]) {
+        const int uu = tid + r * PNT;
+        const int li = uu % bx, lj = uu / bx;
+        const int c = (lj + 1) * uw + (li + 1);
+        const int t = lj * tw + li;
+        double uv_[U_COUNT];
+#pragma unroll
+        for (int q = 0; q < U_COUNT; ++q) uv_[q] = (q < pp.kU) ? sU[q * nU + uu] : __ldg(gU[q] + gcU[r]);
+        double ui = 0.0, vi = 0.0;
+        if (pp.use_init) { ui = __ldg(d.uinit + gcU[r]); vi = __ldg(d.vinit + gcU[r]); }
+        const double uold = su[c], vold = sv[c];
+        // stepu_point with aiX*rhow*Cw folded: pass Cw = 1-free form by giving aiX=cvrel, rhow*Cw via params is not
+        // bit-safe, so the product is formed here exactly as (aiX*rhow)*Cw was in the prologue.
+        const double du = uv_[U_UOCN] - uold, dv = uv_[U_VOCN] - vold;
+        const double vrel = uv_[U_CVREL] * sqrt(du * du + dv * dv);
+        const double taux = vrel * uv_[U_WATERX];
+        const double tauy = vrel * uv_[U_WATERY];
+        const double Cb = uv_[U_TBU] / (sqrt(uold * uold + vold * vold) + k.u0);
+        const double cca = (k.brlx + k.revp) * uv_[U_UMASSDTI] + vrel * k.cosw + Cb;
+        const double ccb = uv_[U_FM] + copysign(1.0, uv_[U_FM]) * vrel * k.sinw;
+        const double ab2 = cca * cca + ccb * ccb;
+        const double strintx = uv_[U_UAREAR] * (sstr[0 * nT + t] + sstr[1 * nT + t + 1] + sstr[2 * nT + t + tw] + sstr[3 * nT + t + tw + 1]);
+        const double strinty = uv_[U_UAREAR] * (sstr[4 * nT + t] + sstr[5 * nT + t + tw] + sstr[6 * nT + t + 1] + sstr[7 * nT + t + tw + 1]);
+        const double cc1 = strintx + uv_[U_FORCEX] + taux + uv_[U_UMASSDTI] * (k.brlx * uold + k.revp * ui);
+        const double cc2 = strinty + uv_[U_FORCEY] + tauy + uv_[U_UMASSDTI] * (k.brlx * vold + k.revp * vi);
+        const double un = (cca * cc1 + ccb * cc2) / ab2;
+        const double vn = (cca * cc2 - ccb * cc1) / ab2;
+        su[c] = un;
+        sv[c] = vn;
+        if (edgeU[r] || last) {
+          const int i = i0 + li, j = j0 + lj;
+          double *__restrict__ Un = d.u[nxt];
+          double *__restrict__ Vn = d.v[nxt];
+          const size_t g = gcU[r];
+          __stcg(Un + g, un);
+          __stcg(Vn + g, vn);
+          int ig = -1, jg = -1;
+          if (d.wrap_ew) ig = (i == 1) ? d.nx + 1 : (i == d.nx ? 0 : -1);
+          if (d.wrap_ns) jg = (j == 1) ? d.ny + 1 : (j == d.ny ? 0 : -1);
+          if (ig >= 0) { __stcg(Un + (size_t)j * d.ld + ig, un); __stcg(Vn + (size_t)j * d.ld + ig, vn); }
+          if (jg >= 0) { __stcg(Un + (size_t)jg * d.ld + i, un); __stcg(Vn + (size_t)jg * d.ld + i, vn); }
+          if (ig >= 0 && jg >= 0) { __stcg(Un + (size_t)jg * d.ld + ig, un); __stcg(Vn + (size_t)jg * d.ld + ig, vn); }
+        }
+        if (last) {
+          d.strintx[gcU[r]] = strintx;
+          d.strinty[gcU[r]] = strinty;
+          d.taubx[gcU[r]] = -un * Cb;
+          d.tauby[gcU[r]] = -vn * Cb;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      st_release(pp.progress + tile, (unsigned)(ksub + 1));
+    }
+  }
+
+  // ---------------- epilogue: the carried stress state goes back to copy (ndte & 1) -------------------
+  const int fin = pp.ndte & 1;
+#pragma unroll
+  for (int r = 0; r < PCELLS; ++r) {
+    if (ownT[r]) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        d.sig[fin][q][gcT[r]] = sg[r].p[q];
+        d.sig[fin][4 + q][gcT[r]] = sg[r].m[q];
+        d.sig[fin][8 + q][gcT[r]] = sg[r].s12[q];
+      }
+    }
+  }
+}
+
+size_t persist_smem_bytes(const PersistPlan &pp) { return pp.smem_bytes; }
+
+cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  void *args[] = {(void *)&d, (void *)&p, (void *)&pp};
+  return cudaLaunchCooperativeKernel((const void *)persist_kernel, dim3(pp.ntx * pp.nty), dim3(PNT), args, pp.smem_bytes, s);
+}
+
+}  // namespace EVP_NS
+}  // namespace evp
