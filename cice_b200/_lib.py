@@ -13,6 +13,7 @@ SYMBOLS = (
     "evp_b200_get_unique_id", "evp_b200_comm_init", "evp_b200_set_device", "evp_b200_init", "evp_b200_finalize",
     "evp_b200_last_error", "evp_b200_run_bgrid", "evp_b200_upload", "evp_b200_subcycle", "evp_b200_download",
     "evp_b200_last_loop_ms", "evp_b200_last_launches", "evp_b200_stream", "evp_b200_describe",
+    "evp_b200_halo_plan", "evp_b200_dom_pitch",
 )
 
 
@@ -58,6 +59,9 @@ def load():
     L.evp_b200_last_loop_ms.argtypes = [C.POINTER(C.c_double)]
     L.evp_b200_last_launches.argtypes = [C.POINTER(C.c_int64)]
     L.evp_b200_stream.argtypes = [C.POINTER(C.c_void_p)]
+    pi32 = C.POINTER(C.c_int32)
+    L.evp_b200_halo_plan.argtypes = [C.c_int32, pi32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, pi32, pi32, C.c_int32]
+    L.evp_b200_dom_pitch.argtypes = [C.c_int32]
     for n in SYMBOLS:
         getattr(L, n).restype = C.c_int
     L.evp_b200_last_error.restype = C.c_char_p

@@ -413,7 +413,7 @@ static KParams kparams(const evp_b200_params_t *p) {
 
 static int choose_kernel(const evp_b200_params_t *p) {
   int kern = p->kernel;
-  if (kern == EVP_B200_KERNEL_AUTO) kern = g.persist_ok ? EVP_B200_KERNEL_PERSISTENT : EVP_B200_KERNEL_FUSED;
+  if (kern == EVP_B200_KERNEL_AUTO) kern = EVP_B200_KERNEL_FUSED;  // measured faster than PERSISTENT at gx1 (profiles/)
   return kern;
 }
 
@@ -563,6 +563,13 @@ int evp_b200_run_bgrid(const evp_b200_params_t *p, evp_b200_fields_t *f) {
   if (do_subcycle(p)) return 1;
   return do_download(f);
 }
+
+int evp_b200_halo_plan(int32_t nranks, const int32_t *rects, int32_t rank, int32_t nxg, int32_t nyg, int32_t ew, int32_t ns,
+                       int32_t *n, int32_t *out, int32_t cap) {
+  if (!rects || !n || (!out && cap > 0) || nranks < 1 || rank < 0 || rank >= nranks) return fail("evp_b200_halo_plan: bad arguments");
+  return halo_plan_host(nranks, rects, rank, nxg, nyg, ew, ns, n, out, cap);
+}
+int32_t evp_b200_dom_pitch(int32_t nx) { return dom_pitch(nx); }
 
 int evp_b200_last_loop_ms(double *ms) { if (!ms) return fail("null"); *ms = g.last_ms; return 0; }
 int evp_b200_last_launches(int64_t *n) { if (!n) return fail("null"); *n = g.last_launches; return 0; }

@@ -131,18 +131,14 @@ static void enumerate(const std::vector<Rect> &R, int r, int nxg, int nyg, int e
       if (gj < 1) {
         if (ns != EVP_B200_BNDY_CYCLIC) continue;
         gj += nyg;
+      } else if (gj > nyg && ns == EVP_B200_BNDY_CYCLIC) {
+        gj -= nyg;
       }
       if (gj > nyg) {
-        if (ns == EVP_B200_BNDY_CYCLIC) {
-          gj -= nyg;
-          if (!owner(gi, gj, e.r1, e.c1)) continue;
-        } else if (tripole) {
-          const int it = wrapi(nxg - gi);
-          if (!owner(it, nyg - 1, e.r1, e.c1)) continue;
-          e.code = OP_NEG;
-        } else {
-          continue;
-        }
+        if (!tripole) continue;
+        const int it = wrapi(nxg - gi);
+        if (!owner(it, nyg - 1, e.r1, e.c1)) continue;
+        e.code = OP_NEG;
       } else if (toprow) {
         if (!owner(gi, nyg, e.r1, e.c1)) continue;
         if (gi == nxg / 2 || gi == nxg) {
@@ -161,6 +157,20 @@ static void enumerate(const std::vector<Rect> &R, int r, int nxg, int nyg, int e
       out.push_back(e);
     }
 }
+
+int halo_plan_host(int nranks, const int *rects, int rank, int nxg, int nyg, int ew, int ns, int *n, int *out, int cap) {
+  std::vector<Rect> R(nranks);
+  for (int q = 0; q < nranks; ++q) R[q] = Rect{rects[4 * q], rects[4 * q + 1], rects[4 * q + 2], rects[4 * q + 3]};
+  std::vector<Entry> es;
+  enumerate(R, rank, nxg, nyg, ew, ns, es);
+  *n = (int)es.size();
+  for (int k = 0; k < (int)es.size() && k < cap; ++k) {
+    int *o = out + 6 * k;
+    o[0] = es[k].dst; o[1] = es[k].r1; o[2] = es[k].c1; o[3] = es[k].r2; o[4] = es[k].c2; o[5] = es[k].code;
+  }
+  return 0;
+}
+int dom_pitch(int nx) { return ld_of(nx); }
 
 template <class T>
 static int up(T *&dptr, const std::vector<T> &h, char *err, size_t nerr) {

@@ -19,6 +19,9 @@ int comm_get_unique_id(void *id128, char *err, size_t nerr);
 int comm_init(CommState &cs, int rank, int nranks, const void *id128, char *err, size_t nerr);
 void comm_destroy(CommState &cs);
 
+int halo_plan_host(int nranks, const int *rects, int rank, int nxg, int nyg, int ew, int ns, int *n, int *out, int cap);
+int dom_pitch(int nx);
+
 // What one exchange does, for every destination cell e of this rank (ghost ring, plus the top interior
 // row on a tripole grid):  dst = op(code, s1, s2), where s1/s2 were staged from this rank's interior
 // (pack kernel) or received from a neighbour rank.

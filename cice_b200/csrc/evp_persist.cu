@@ -49,6 +49,9 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
   const int tw = bx + 1, nT = pp.nT, nU = pp.nU;    // T pitch
   const int uw = bx + 2;                            // u/v pitch (ring included)
   const int nring = (bx + 2) * (by + 2);
+  // a tile on the E/N edge of the sub-domain may be narrower than bx x by: its ring sits right
+  // after its last valid column/row
+  const int ebx = min(bx, d.nx - i0 + 1), eby = min(by, d.ny - j0 + 1);
 
   double *su = sm + pp.off_u, *sv = sm + pp.off_v, *sstr = sm + pp.off_str;
   double *sT = sm + pp.off_T, *sU = sm + pp.off_U;
@@ -139,13 +142,13 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
       __syncthreads();
       const double *__restrict__ U = d.u[cur];
       const double *__restrict__ V = d.v[cur];
-      const int nedge = 2 * (bx + 2) + 2 * by;
+      const int nedge = 2 * (ebx + 2) + 2 * eby;
       for (int e = tid; e < nedge; e += PNT) {
         int li, lj;
-        if (e < bx + 2) { li = e; lj = 0; }
-        else if (e < 2 * (bx + 2)) { li = e - (bx + 2); lj = by + 1; }
-        else if (e < 2 * (bx + 2) + by) { li = 0; lj = 1 + e - 2 * (bx + 2); }
-        else { li = bx + 1; lj = 1 + e - 2 * (bx + 2) - by; }
+        if (e < ebx + 2) { li = e; lj = 0; }
+        else if (e < 2 * (ebx + 2)) { li = e - (ebx + 2); lj = eby + 1; }
+        else if (e < 2 * (ebx + 2) + eby) { li = 0; lj = 1 + e - 2 * (ebx + 2); }
+        else { li = ebx + 1; lj = 1 + e - 2 * (ebx + 2) - eby; }
         const int i = i0 - 1 + li, j = j0 - 1 + lj;
         if (i <= d.nx + 1 && j <= d.ny + 1) {
           const size_t g = (size_t)j * d.ld + i;

@@ -97,6 +97,24 @@ def stream_handle():
     return v.value
 
 
+def halo_plan(rects, rank, nx_global, ny_global, ew, ns):
+    """host-only: the (uvel,vvel) halo plan of `rank` as an (n,6) int array
+    {dst, src1_rank, src1, src2_rank, src2, op}; rects is (nranks,4) {gi0, gj0, nx, ny}."""
+    L = load()
+    r = np.ascontiguousarray(rects, dtype=np.int32)
+    n = C.c_int32()
+    pi = C.POINTER(C.c_int32)
+    check(L.evp_b200_halo_plan(len(r), r.ctypes.data_as(pi), rank, nx_global, ny_global, ew, ns, C.byref(n), None, 0), "halo_plan")
+    out = np.zeros((max(n.value, 1), 6), np.int32)
+    check(L.evp_b200_halo_plan(len(r), r.ctypes.data_as(pi), rank, nx_global, ny_global, ew, ns, C.byref(n),
+                               out.ctypes.data_as(pi), n.value), "halo_plan")
+    return out[:n.value]
+
+
+def dom_pitch(nx):
+    return load().evp_b200_dom_pitch(int(nx))
+
+
 def describe():
     return load().evp_b200_describe().decode()
 

@@ -174,6 +174,18 @@ int evp_b200_stream(void **stream);
 /* report the chosen tiling/kernel as a short static string */
 const char *evp_b200_describe(void);
 
+
+/* ---- host-only planning hook (no GPU needed; used by the CPU tests of the multi-rank logic) ----
+ * The (uvel,vvel) halo plan of `rank` when rank r owns the rectangle rects[4r..4r+3] =
+ * {gi0, gj0, nx, ny} (global index of its first interior cell, interior extent).  Writes up to `cap`
+ * entries of 6 ints {dst, src1_rank, src1, src2_rank, src2, op} into `out` (dst/src are indices into
+ * the owning rank's (nx+2)-wide, pitch-padded sub-domain array: see evp_b200_dom_pitch; op 0 copy,
+ * 1 negate, 2 0.5*(src1 - src2)) and the total count into *n.  Ghost cells the compute kernels fill
+ * themselves (on-rank cyclic wrap) are not listed. */
+int evp_b200_halo_plan(int32_t nranks, const int32_t *rects, int32_t rank, int32_t nx_global, int32_t ny_global,
+                       int32_t ew_boundary_type, int32_t ns_boundary_type, int32_t *n, int32_t *out, int32_t cap);
+int32_t evp_b200_dom_pitch(int32_t nx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -157,6 +157,49 @@ def test_large_grid_properties(evp_lib):
     assert np.array_equal(o["vvel"][0][:, -1], o["vvel"][0][:, 1])
 
 
+@pytest.mark.parametrize("kernel", [abi.KERNEL_SPLIT, abi.KERNEL_FUSED], ids=KNAME.get)
+@pytest.mark.parametrize("bs", [None, (12, 10)], ids=["1block", "4blocks"])
+def test_tripole_fold_single_gpu(oracle_mod, evp_lib, kernel, bs):
+    """ns_boundary_type='tripole' (configs[3] geometry, small): the fold is part of the per-subcycle halo --
+    ghost row from the mirrored column with the sign flipped, top row symmetrised, pole points negated
+    (ice_boundary.F90:1630-1722)."""
+    c = synth.make_case("tiny", seed=41, ns="tripole", kmt="none", ndte=12, block_size=bs)
+    ref = run_oracle(oracle_mod, c)
+    got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=kernel)
+    assert_bitwise(got, ref)
+
+
+def test_tx1_tripole_full(oracle_mod, evp_lib):
+    """configs[3] grid on one GPU: tx1 360x240 tripole, ndte=240."""
+    c = synth.make_case("tx1")
+    ref = run_oracle(oracle_mod, c)
+    got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT)
+    assert_bitwise(got, ref)
+
+
+@pytest.mark.parametrize("args", [
+    ["gx3", "25", "29", "20", "fused"],
+    ["gx3", "50", "58", "15", "split"],
+    ["tiny", "12", "10", "16", "fused", "tripole"],
+], ids=["gx3-16blocks-fused", "gx3-4blocks-split", "tiny-tripole"])
+def test_multi_gpu_nccl_halo(args):
+    """N>1: one process per GPU, NCCL send/recv halo every subcycle, bit-identical to the oracle.
+    Runs when the box exposes at least 2 GPUs (gpurun --gpus 2); the 1-GPU round-end run skips it."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 4 if n >= 4 else 2
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", os.path.join(root, "tests", "mgpu_check.py")] + args
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "MGPU PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 def test_errors_are_reported_not_fatal(evp_lib):
     c = synth.make_case("tiny")
     bad = dict(c.grid, nghost=2)

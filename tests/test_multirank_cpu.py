@@ -1,0 +1,158 @@
+"""N>1 host-side logic on CPU: two real processes over gloo execute the library's halo plan (the
+host-only planning hook evp_b200_halo_plan, the very enumeration the GPU exchange is built from) on
+numpy sub-domains and must reproduce the oracle's halo update of the undecomposed domain -- cyclic,
+closed and tripole (fold, top-row symmetrisation, pole points).  Also covers the rank_view /
+cartesian_owner partition each rank derives its blocks from."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rects(case, owner, world):
+    rects = []
+    b = case.blocks
+    for r in range(world):
+        ids = np.nonzero(owner == r)[0]
+        gi0 = min(b.i_glob[n][b.ilo[n] - 1] for n in ids)
+        gi1 = max(b.i_glob[n][b.ihi[n] - 1] for n in ids)
+        gj0 = min(b.j_glob[n][b.jlo[n] - 1] for n in ids)
+        gj1 = max(b.j_glob[n][b.jhi[n] - 1] for n in ids)
+        rects.append([gi0, gj0, gi1 - gi0 + 1, gj1 - gj0 + 1])
+    return np.array(rects, np.int32)
+
+
+def _worker(rank, world, port, ew, ns, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from cice_b200 import abi, decomp, dyn_evp, synth
+    from oracle import oracle
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        case = synth.make_case("tiny", block_size=(12, 10), seed=21, ew=ew, ns=ns, kmt="none")
+        owner, _ = decomp.cartesian_owner(case.blocks, world)
+        rects = _rects(case, owner, world)
+        ewi, nsi = case.grid["ew_boundary_type"], case.grid["ns_boundary_type"]
+        nxg, nyg = case.grid["nx_global"], case.grid["ny_global"]
+
+        # truth: the oracle's halo update on the undecomposed domain
+        whole = synth.make_case("tiny", seed=21, ew=ew, ns=ns, kmt="none")
+        tu, tv = whole.fields["uvel"].copy(), whole.fields["vvel"].copy()
+        tu[0, 0, :] = tu[0, -1, :] = np.nan  # ghost rows/cols must come from the update, not from the input
+        tu[0, :, 0] = tu[0, :, -1] = np.nan
+        tv[0, 0, :] = tv[0, -1, :] = np.nan
+        tv[0, :, 0] = tv[0, :, -1] = np.nan
+        oracle.halo_update(whole.grid, [tu, tv], field_loc=1, field_type=1)
+
+        # my sub-domain (ny+2, ld), interior from the case, ring unknown
+        gi0, gj0, nx, ny = rects[rank]
+        ld = dyn_evp.dom_pitch(nx)
+        X = whole.X
+        dom = {}
+        for name in ("uvel", "vvel"):
+            a = np.full((ny + 2, ld), np.nan)
+            a[1:ny + 1, 1:nx + 1] = X[name][gj0:gj0 + ny, gi0:gi0 + nx]
+            dom[name] = a.reshape(-1)
+        wrap_ew = ewi == abi.BNDY_CYCLIC and nx == nxg
+        wrap_ns = nsi == abi.BNDY_CYCLIC and ny == nyg
+        for name in ("uvel", "vvel"):  # what the compute kernels' wrap stores do
+            a = dom[name].reshape(ny + 2, ld)
+            if wrap_ew:
+                a[1:ny + 1, 0], a[1:ny + 1, nx + 1] = a[1:ny + 1, nx].copy(), a[1:ny + 1, 1].copy()
+            if wrap_ns:
+                a[0, 1:nx + 1], a[ny + 1, 1:nx + 1] = a[ny, 1:nx + 1].copy(), a[1, 1:nx + 1].copy()
+            if wrap_ew and wrap_ns:
+                a[0, 0], a[0, nx + 1], a[ny + 1, 0], a[ny + 1, nx + 1] = a[ny, nx], a[ny, 1], a[1, nx], a[1, 1]
+
+        plans = [dyn_evp.halo_plan(rects, r, nxg, nyg, ewi, nsi) for r in range(world)]
+        # what every rank needs from me, in that rank's entry order (the send lists of the GPU plan)
+        outbox = {}
+        for r in range(world):
+            if r == rank:
+                continue
+            idx = []
+            for e in plans[r]:
+                if e[1] == rank:
+                    idx.append(e[2])
+                if e[3] == rank:
+                    idx.append(e[4])
+            outbox[r] = np.array([[dom["uvel"][c], dom["vvel"][c]] for c in idx], dtype=np.float64).reshape(-1, 2)
+        boxes = [None] * world
+        dist.all_gather_object(boxes, outbox)
+        cursor = {r: 0 for r in range(world)}
+
+        def take(r, c):
+            if r == rank:
+                return dom["uvel"][c], dom["vvel"][c]
+            v = boxes[r][rank][cursor[r]]
+            cursor[r] += 1
+            return v[0], v[1]
+
+        staged = []
+        for e in plans[rank]:  # all sources are read before any destination is written
+            a = take(e[1], e[2])
+            b = take(e[3], e[4]) if e[3] >= 0 else None
+            staged.append((e[0], e[5], a, b))
+        for dst, op, a, b in staged:
+            if op == 0:
+                u, v = a
+            elif op == 1:
+                u, v = -a[0], -a[1]
+            else:
+                u, v = 0.5 * (a[0] - b[0]), 0.5 * (a[1] - b[1])
+            dom["uvel"][dst], dom["vvel"][dst] = u, v
+
+        bad = 0
+        for name, truth in (("uvel", tu[0]), ("vvel", tv[0])):
+            a = dom[name].reshape(ny + 2, ld)
+            for dj in range(ny + 2):
+                for di in range(nx + 2):
+                    gi, gj = gi0 + di - 1, gj0 + dj - 1  # unwrapped global position
+                    if ewi == abi.BNDY_CYCLIC:
+                        gi = (gi - 1) % nxg + 1
+                    if nsi == abi.BNDY_CYCLIC:
+                        gj = (gj - 1) % nyg + 1
+                    if 0 <= gi <= nxg + 1 and 0 <= gj <= nyg + 1:
+                        want = truth[gj, gi]
+                        got = a[dj, di]
+                        if np.isnan(want):
+                            ok = np.isnan(got)  # outside a closed edge: untouched on both sides
+                        else:
+                            ok = (got == want)
+                        bad += 0 if ok else 1
+        q.put((rank, bad, len(plans[rank])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ew,ns", [("cyclic", "closed"), ("cyclic", "cyclic"), ("closed", "closed"), ("cyclic", "tripole")])
+@pytest.mark.parametrize("world", [2, 4])
+def test_halo_plan_two_processes_gloo(ew, ns, world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() * 7 + hash((ew, ns, world))) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ew, ns, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, bad, n in res:
+        assert bad == 0, f"rank {rank}: {bad} cells differ from the oracle halo ({n} plan entries)"
+
+
+def test_halo_plan_single_rank_is_empty_without_tripole():
+    from cice_b200 import abi, dyn_evp
+    for ew, ns in ((abi.BNDY_CYCLIC, abi.BNDY_CLOSED), (abi.BNDY_CYCLIC, abi.BNDY_CYCLIC), (abi.BNDY_CLOSED, abi.BNDY_OPEN)):
+        assert len(dyn_evp.halo_plan([[1, 1, 24, 20]], 0, 24, 20, ew, ns)) == 0
+    pl = dyn_evp.halo_plan([[1, 1, 24, 20]], 0, 24, 20, abi.BNDY_CYCLIC, abi.BNDY_TRIPOLE)
+    # ghost row (26 cells incl. corners, negated copies) + top row (24 interior + 2 ghost columns):
+    # two pole columns (i = 12, 24; the ghost column i=0 aliases 24) are negated, the rest symmetrised
+    assert len(pl) == 52
+    assert (pl[:, 5] == 1).sum() == 26 + 3 and (pl[:, 5] == 2).sum() == 23 and (pl[:, 5] == 0).sum() == 0
