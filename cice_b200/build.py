@@ -69,5 +69,34 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST_LIB = os.path.join(OUT, "libdyn_evp_b200.so")
+HOST_CALLER = os.path.join(OUT, "host_caller")
+
+
+def build_host(force=False):
+    """the C++ host mirror of the reference seam (host/dyn_evp_b200.cpp) and the test caller that
+    stands in for the Fortran driver (tests/host_caller.cpp); plain g++, linked against libevp_b200.so."""
+    build(force=False)
+    srcs = [os.path.join(HERE, "host", "dyn_evp_b200.cpp"), os.path.join(HERE, "host", "dyn_evp_b200.hpp"),
+            os.path.join(ROOT, "tests", "host_caller.cpp"), LIB]
+    if not force and os.path.exists(HOST_CALLER) and all(os.path.getmtime(s) <= os.path.getmtime(HOST_CALLER) for s in srcs):
+        return HOST_CALLER
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "host")]
+    cmds = [
+        ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared"] + inc + [srcs[0], "-o", HOST_LIB, "-L", OUT, "-levp_b200",
+                                                                        "-Wl,-rpath,$ORIGIN"],
+        ["/usr/bin/g++", "-O2", "-std=c++17"] + inc + [srcs[2], "-o", HOST_CALLER, "-L", OUT, "-ldyn_evp_b200", "-levp_b200",
+                                                       "-Wl,-rpath,$ORIGIN", "-Wl,-rpath-link," + OUT],
+    ]
+    for cmd in cmds:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            raise RuntimeError("host build failed: " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return HOST_CALLER
+
+
 if __name__ == "__main__":
+    if "--host" in sys.argv:
+        print(build_host(force="--force" in sys.argv))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -116,6 +117,8 @@ struct Ctx {
   std::string persist_why;
   unsigned *d_progress = nullptr;
   int num_sms = 0;
+  int fused_variant = 0;
+  bool fused_pdl = true;
 };
 static Ctx g;
 static CommState g_comm;
@@ -321,6 +324,8 @@ static int do_init(const evp_b200_grid_t *gr) {
   if (g.halo.build(g_comm, gi0, gj0, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, g_err, sizeof g_err)) return 1;
   d.wrap_ew = g.halo.wrap_ew; d.wrap_ns = g.halo.wrap_ns;
 
+  if (const char *e = getenv("EVP_B200_FUSED_VARIANT")) g.fused_variant = atoi(e);
+  if (const char *e = getenv("EVP_B200_PDL")) g.fused_pdl = (e[0] != '0');
   // ---- persistent tiling ---------------------------------------------------------------------------
   CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, g.device));
   plan_persist();
@@ -443,7 +448,8 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
       CK(exact ? exact::launch_stepu(g.dom, k, cur, g.stream) : fast::launch_stepu(g.dom, k, cur, g.stream));
       nl += 2;
     } else if (kern == EVP_B200_KERNEL_FUSED) {
-      CK(exact ? exact::launch_fused(g.dom, k, cur, g.stream) : fast::launch_fused(g.dom, k, cur, g.stream));
+      CK(exact ? exact::launch_fused(g.dom, k, cur, g.stream, g.fused_variant, g.fused_pdl)
+               : fast::launch_fused(g.dom, k, cur, g.stream, g.fused_variant, g.fused_pdl));
       cur ^= 1;
       nl += 1;
     } else {

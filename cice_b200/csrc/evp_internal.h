@@ -63,7 +63,7 @@ struct PersistPlan {
   namespace NS {                                                                                    \
   cudaError_t launch_stress(const Dom &d, const KParams &p, int cur, cudaStream_t s);               \
   cudaError_t launch_stepu(const Dom &d, const KParams &p, int cur, cudaStream_t s);                \
-  cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s);                \
+  cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl); \
   cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s); \
   }
 EVP_DECLARE_LAUNCHERS(exact)

@@ -14,6 +14,10 @@
 // Neither is GEMM shaped; both are bandwidth/latency bound fp64 stencils -> no tensor cores.
 #include "evp_math.cuh"
 
+#ifndef EVP_USE_PDL
+#define EVP_USE_PDL 1
+#endif
+
 #ifndef EVP_NS
 #error "compile with -DEVP_NS=exact or -DEVP_NS=fast"
 #endif
@@ -121,10 +125,11 @@ cudaError_t launch_stepu(const Dom &d, const KParams &p, int cur, cudaStream_t s
 // ---------------------------------------------------------------------------------------------
 // KERNEL_FUSED
 // ---------------------------------------------------------------------------------------------
-constexpr int FBX = 32, FBY = 8;
-
-__global__ void __launch_bounds__(FBX *FBY) fused_kernel(const __grid_constant__ Dom d,
-                                                          const __grid_constant__ KParams k, int cur) {
+// FBX x FBY threads relax an FBX x FBY patch of T cells and advance the (FBX-1) x (FBY-1) U points it closes.
+// MINB = CTAs per SM the register allocation is bounded for.
+template <int FBX, int FBY, int MINB>
+__global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_constant__ Dom d,
+                                                                const __grid_constant__ KParams k, int cur) {
   __shared__ double sstr[8][FBY][FBX];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i = 1 + blockIdx.x * (FBX - 1) + tx;  // T cell of this thread
@@ -132,6 +137,10 @@ __global__ void __launch_bounds__(FBX *FBY) fused_kernel(const __grid_constant__
   const int nxt = cur ^ 1;
   const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
   const size_t c = at(d, inT ? i : 1, inT ? j : 1);
+#if EVP_USE_PDL
+  // programmatic dependent launch: everything above overlaps the previous subcycle's tail
+  cudaGridDependencySynchronize();
+#endif
 
   double str[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (inT && d.maskT[c]) {
@@ -159,10 +168,28 @@ __global__ void __launch_bounds__(FBX *FBY) fused_kernel(const __grid_constant__
   }
 }
 
-cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s) {
+template <int FBX, int FBY, int MINB>
+static cudaError_t launch_fused_t(const Dom &d, const KParams &p, int cur, cudaStream_t s, bool pdl) {
   dim3 b(FBX, FBY), g((d.nx + FBX - 2) / (FBX - 1), (d.ny + FBY - 2) / (FBY - 1));
-  fused_kernel<<<g, b, 0, s>>>(d, p, cur);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, fused_kernel<FBX, FBY, MINB>, d, p, cur);
+}
+
+cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl) {
+  switch (variant) {
+    case 1: return launch_fused_t<32, 8, 3>(d, p, cur, s, pdl);
+    case 2: return launch_fused_t<32, 8, 4>(d, p, cur, s, pdl);
+    case 3: return launch_fused_t<32, 4, 4>(d, p, cur, s, pdl);
+    case 4: return launch_fused_t<32, 16, 1>(d, p, cur, s, pdl);
+    case 5: return launch_fused_t<64, 4, 2>(d, p, cur, s, pdl);
+    case 6: return launch_fused_t<32, 6, 3>(d, p, cur, s, pdl);
+    default: return launch_fused_t<32, 8, 2>(d, p, cur, s, pdl);
+  }
 }
 
 }  // namespace EVP_NS

@@ -1,0 +1,227 @@
+!=======================================================================
+! ice_dyn_evp_b200 -- Fortran side of the B200 EVP path (ISO_C_BINDING shim over include/evp_b200.h)
+!
+! NOT COMPILED OR TESTED IN THIS REPOSITORY'S IMAGE: there is no Fortran compiler here (gcc lacks
+! f951, no MPI).  tests/ exercise the same C ABI from a caller that reproduces this module's memory
+! layout byte for byte (Fortran a(nx_block,ny_block,max_blocks) == C-ordered (max_blocks,ny_block,nx_block)).
+!
+! It plugs into CICE at the seam the reference already has for its own 1-D solver:
+!   dyn_evp_b200_init      next to  dyn_evp1d_init      (ice_dyn_evp.F90:153-155)
+!   dyn_evp_b200_run       next to  dyn_evp1d_run       (ice_dyn_evp.F90:846-858), same 31 arrays
+!   dyn_evp_b200_finalize  next to  dyn_evp1d_finalize
+! and is selected with  evp_algorithm = 'gpu_b200'  in dynamics_nml (see INTEGRATION.md for the patch).
+!=======================================================================
+module ice_dyn_evp_b200
+
+  use, intrinsic :: iso_c_binding
+  use ice_kinds_mod
+  use ice_blocks,      only: block, get_block, nx_block, ny_block, nghost
+  use ice_domain,      only: nblocks, blocks_ice, ew_boundary_type, ns_boundary_type
+  use ice_domain_size, only: max_blocks, nx_global, ny_global
+  use ice_communicate, only: my_task, master_task, MPI_COMM_ICE, get_num_procs
+  use ice_exit,        only: abort_ice
+
+  implicit none
+  private
+  public :: dyn_evp_b200_init, dyn_evp_b200_run, dyn_evp_b200_finalize
+
+  integer(c_int32_t), parameter :: EVP_B200_ABI_VERSION = 1
+  integer(c_int32_t), parameter :: BNDY_OPEN = 0, BNDY_CLOSED = 1, BNDY_CYCLIC = 2, BNDY_TRIPOLE = 3
+
+  ! evp_b200_grid_t
+  type, bind(C) :: evp_b200_grid_t
+     integer(c_int32_t) :: abi_version, nx_block, ny_block, nblocks, max_blocks, nghost
+     integer(c_int32_t) :: nx_global, ny_global, ew_boundary_type, ns_boundary_type
+     type(c_ptr) :: ilo, ihi, jlo, jhi, i_glob, j_glob
+     type(c_ptr) :: dxT, dyT, dxhy, dyhx, cxp, cyp, cxm, cym, DminTarea, uarear
+  end type evp_b200_grid_t
+
+  ! evp_b200_params_t
+  type, bind(C) :: evp_b200_params_t
+     integer(c_int32_t) :: ndte, mode, kernel, reserved
+     real(c_double) :: arlx1i, denom1, revp, brlx, e_factor, epp2i, capping, Ktens, u0, cosw, sinw, rhow
+  end type evp_b200_params_t
+
+  ! evp_b200_fields_t: the argument list of dyn_evp1d_run, in order
+  type, bind(C) :: evp_b200_fields_t
+     type(c_ptr) :: stressp_1, stressp_2, stressp_3, stressp_4
+     type(c_ptr) :: stressm_1, stressm_2, stressm_3, stressm_4
+     type(c_ptr) :: stress12_1, stress12_2, stress12_3, stress12_4
+     type(c_ptr) :: strength, cdn_ocnU, aiU, uocnU, vocnU, waterxU, wateryU, forcexU, forceyU, umassdti, fmU
+     type(c_ptr) :: strintxU, strintyU, TbU, taubxU, taubyU, uvel, vvel
+     type(c_ptr) :: iceTmask, iceUmask
+  end type evp_b200_fields_t
+
+  interface
+     integer(c_int) function evp_b200_get_unique_id(id) bind(C, name='evp_b200_get_unique_id')
+       import :: c_int, c_char
+       character(kind=c_char) :: id(128)
+     end function
+     integer(c_int) function evp_b200_comm_init(rank, nranks, id) bind(C, name='evp_b200_comm_init')
+       import :: c_int, c_int32_t, c_char
+       integer(c_int32_t), value :: rank, nranks
+       character(kind=c_char) :: id(128)
+     end function
+     integer(c_int) function evp_b200_set_device(dev) bind(C, name='evp_b200_set_device')
+       import :: c_int, c_int32_t
+       integer(c_int32_t), value :: dev
+     end function
+     integer(c_int) function evp_b200_init(grid) bind(C, name='evp_b200_init')
+       import :: c_int, evp_b200_grid_t
+       type(evp_b200_grid_t), intent(in) :: grid
+     end function
+     integer(c_int) function evp_b200_run_bgrid(params, fields) bind(C, name='evp_b200_run_bgrid')
+       import :: c_int, evp_b200_params_t, evp_b200_fields_t
+       type(evp_b200_params_t), intent(in) :: params
+       type(evp_b200_fields_t), intent(inout) :: fields
+     end function
+     integer(c_int) function evp_b200_finalize() bind(C, name='evp_b200_finalize')
+       import :: c_int
+     end function
+     type(c_ptr) function evp_b200_last_error() bind(C, name='evp_b200_last_error')
+       import :: c_ptr
+     end function
+  end interface
+
+  ! C-interoperable copies of the block table and of the logical masks
+  integer(c_int32_t), allocatable, target, save :: b_ilo(:), b_ihi(:), b_jlo(:), b_jhi(:)
+  integer(c_int32_t), allocatable, target, save :: b_iglob(:,:), b_jglob(:,:)
+  integer(c_int32_t), allocatable, target, save :: imaskT(:,:,:), imaskU(:,:,:)
+
+contains
+
+  !---------------------------------------------------------------------
+  subroutine check(rc, where)
+    integer(c_int), intent(in) :: rc
+    character(len=*), intent(in) :: where
+    character(kind=c_char), pointer :: msg(:)
+    character(len=512) :: text
+    integer :: n
+    if (rc == 0) return
+    call c_f_pointer(evp_b200_last_error(), msg, [512])
+    text = ' '
+    do n = 1, 512
+       if (msg(n) == c_null_char) exit
+       text(n:n) = msg(n)
+    enddo
+    ! error convention of the reference: comm/mpi/ice_exit.F90
+    call abort_ice('(ice_dyn_evp_b200) ERROR in '//trim(where)//': '//trim(text), file=__FILE__, line=__LINE__)
+  end subroutine check
+
+  integer(c_int32_t) function bndy_code(name)
+    character(len=*), intent(in) :: name
+    select case (trim(name))
+    case ('cyclic');  bndy_code = BNDY_CYCLIC
+    case ('closed');  bndy_code = BNDY_CLOSED
+    case ('tripole'); bndy_code = BNDY_TRIPOLE
+    case default;     bndy_code = BNDY_OPEN
+    end select
+    if (trim(name) == 'tripoleT') call abort_ice('(ice_dyn_evp_b200) ERROR: tripoleT not supported', &
+         file=__FILE__, line=__LINE__)
+  end function bndy_code
+
+  !---------------------------------------------------------------------
+  ! once, after init_dyn_shared and the grid are set up (ice_dyn_evp.F90:153-155)
+  subroutine dyn_evp_b200_init
+    use mpi
+    use ice_grid,       only: dxT, dyT, uarear
+    use ice_dyn_shared, only: dxhy, dyhx, cxp, cyp, cxm, cym, DminTarea
+    type(evp_b200_grid_t) :: g
+    type(block) :: this_block
+    character(kind=c_char) :: id(128)
+    integer :: iblk, ierr, nprocs, ndev_local
+    integer :: local_comm, local_rank
+
+    ! one rank <-> one GPU of the node
+    call MPI_Comm_split_type(MPI_COMM_ICE, MPI_COMM_TYPE_SHARED, 0, MPI_INFO_NULL, local_comm, ierr)
+    call MPI_Comm_rank(local_comm, local_rank, ierr)
+    call check(evp_b200_set_device(int(local_rank, c_int32_t)), 'evp_b200_set_device')
+
+    ! NCCL bootstrap over the host's own transport (replaces the MPI halo of ice_boundary for the dyn fields)
+    nprocs = get_num_procs()
+    if (nprocs > 1) then
+       if (my_task == master_task) call check(evp_b200_get_unique_id(id), 'evp_b200_get_unique_id')
+       call MPI_Bcast(id, 128, MPI_CHARACTER, master_task, MPI_COMM_ICE, ierr)
+       call check(evp_b200_comm_init(int(my_task, c_int32_t), int(nprocs, c_int32_t), id), 'evp_b200_comm_init')
+    endif
+
+    allocate(b_ilo(nblocks), b_ihi(nblocks), b_jlo(nblocks), b_jhi(nblocks))
+    allocate(b_iglob(nx_block, nblocks), b_jglob(ny_block, nblocks))
+    allocate(imaskT(nx_block, ny_block, max_blocks), imaskU(nx_block, ny_block, max_blocks))
+    do iblk = 1, nblocks
+       this_block = get_block(blocks_ice(iblk), iblk)
+       b_ilo(iblk) = this_block%ilo;  b_ihi(iblk) = this_block%ihi
+       b_jlo(iblk) = this_block%jlo;  b_jhi(iblk) = this_block%jhi
+       b_iglob(:, iblk) = this_block%i_glob(:)
+       b_jglob(:, iblk) = this_block%j_glob(:)
+    enddo
+
+    g%abi_version = EVP_B200_ABI_VERSION
+    g%nx_block = nx_block;  g%ny_block = ny_block;  g%nblocks = nblocks;  g%max_blocks = max_blocks
+    g%nghost = nghost;      g%nx_global = nx_global; g%ny_global = ny_global
+    g%ew_boundary_type = bndy_code(ew_boundary_type)
+    g%ns_boundary_type = bndy_code(ns_boundary_type)
+    g%ilo = c_loc(b_ilo);  g%ihi = c_loc(b_ihi);  g%jlo = c_loc(b_jlo);  g%jhi = c_loc(b_jhi)
+    g%i_glob = c_loc(b_iglob);  g%j_glob = c_loc(b_jglob)
+    g%dxT = c_loc(dxT);    g%dyT = c_loc(dyT);    g%dxhy = c_loc(dxhy);  g%dyhx = c_loc(dyhx)
+    g%cxp = c_loc(cxp);    g%cyp = c_loc(cyp);    g%cxm = c_loc(cxm);    g%cym = c_loc(cym)
+    g%DminTarea = c_loc(DminTarea);  g%uarear = c_loc(uarear)
+    call check(evp_b200_init(g), 'evp_b200_init')
+  end subroutine dyn_evp_b200_init
+
+  !---------------------------------------------------------------------
+  ! one dynamics step: replaces the `do ksub = 1,ndte` loop of ice_dyn_evp.F90:859-913.
+  ! Same argument list and order as dyn_evp1d_run (ice_dyn_evp1d.F90:119-153).
+  subroutine dyn_evp_b200_run(stressp_1 , stressp_2 , stressp_3 , stressp_4 , &
+                              stressm_1 , stressm_2 , stressm_3 , stressm_4 , &
+                              stress12_1, stress12_2, stress12_3, stress12_4, &
+                              strength  ,                                     &
+                              cdn_ocnU  , aiU       , uocnU     , vocnU     , &
+                              waterxU   , wateryU   , forcexU   , forceyU   , &
+                              umassdti  , fmU       , strintxU  , strintyU  , &
+                              TbU       , taubxU    , taubyU    , uvel      , &
+                              vvel      , iceTmask  , iceUmask)
+    use ice_dyn_shared, only: ndte, arlx1i, denom1, revp, brlx, e_factor, epp2i, capping, Ktens, u0, cosw, sinw
+    use icepack_intfc,  only: icepack_query_parameters
+    real(kind=dbl_kind), dimension(:,:,:), intent(inout), target, contiguous :: &
+         stressp_1 , stressp_2 , stressp_3 , stressp_4 , stressm_1 , stressm_2 , stressm_3 , stressm_4 , &
+         stress12_1, stress12_2, stress12_3, stress12_4, strintxU  , strintyU  , uvel      , vvel      , &
+         taubxU    , taubyU
+    real(kind=dbl_kind), dimension(:,:,:), intent(in), target, contiguous :: &
+         strength, cdn_ocnU, aiU, uocnU, vocnU, waterxU, wateryU, forcexU, forceyU, umassdti, fmU, TbU
+    logical(kind=log_kind), dimension(:,:,:), intent(in) :: iceTmask, iceUmask
+    type(evp_b200_params_t) :: p
+    type(evp_b200_fields_t) :: f
+    real(kind=dbl_kind) :: rhow
+
+    call icepack_query_parameters(rhow_out=rhow)
+    p%ndte = ndte;  p%mode = 0;  p%kernel = 0;  p%reserved = 0      ! exact arithmetic, library picks the kernel
+    p%arlx1i = arlx1i;  p%denom1 = denom1;  p%revp = revp;  p%brlx = brlx
+    p%e_factor = e_factor;  p%epp2i = epp2i;  p%capping = capping;  p%Ktens = Ktens
+    p%u0 = u0;  p%cosw = cosw;  p%sinw = sinw;  p%rhow = rhow
+
+    ! Fortran logical is not C-interoperable: 0/1 integers cross the boundary
+    imaskT = merge(1_c_int32_t, 0_c_int32_t, iceTmask)
+    imaskU = merge(1_c_int32_t, 0_c_int32_t, iceUmask)
+
+    f%stressp_1 = c_loc(stressp_1);   f%stressp_2 = c_loc(stressp_2);   f%stressp_3 = c_loc(stressp_3);   f%stressp_4 = c_loc(stressp_4)
+    f%stressm_1 = c_loc(stressm_1);   f%stressm_2 = c_loc(stressm_2);   f%stressm_3 = c_loc(stressm_3);   f%stressm_4 = c_loc(stressm_4)
+    f%stress12_1 = c_loc(stress12_1); f%stress12_2 = c_loc(stress12_2); f%stress12_3 = c_loc(stress12_3); f%stress12_4 = c_loc(stress12_4)
+    f%strength = c_loc(strength);  f%cdn_ocnU = c_loc(cdn_ocnU);  f%aiU = c_loc(aiU)
+    f%uocnU = c_loc(uocnU);        f%vocnU = c_loc(vocnU)
+    f%waterxU = c_loc(waterxU);    f%wateryU = c_loc(wateryU);    f%forcexU = c_loc(forcexU);  f%forceyU = c_loc(forceyU)
+    f%umassdti = c_loc(umassdti);  f%fmU = c_loc(fmU)
+    f%strintxU = c_loc(strintxU);  f%strintyU = c_loc(strintyU);  f%TbU = c_loc(TbU)
+    f%taubxU = c_loc(taubxU);      f%taubyU = c_loc(taubyU);      f%uvel = c_loc(uvel);        f%vvel = c_loc(vvel)
+    f%iceTmask = c_loc(imaskT);    f%iceUmask = c_loc(imaskU)
+
+    call check(evp_b200_run_bgrid(p, f), 'evp_b200_run_bgrid')
+  end subroutine dyn_evp_b200_run
+
+  !---------------------------------------------------------------------
+  subroutine dyn_evp_b200_finalize
+    call check(evp_b200_finalize(), 'evp_b200_finalize')
+    if (allocated(b_ilo)) deallocate(b_ilo, b_ihi, b_jlo, b_jhi, b_iglob, b_jglob, imaskT, imaskU)
+  end subroutine dyn_evp_b200_finalize
+
+end module ice_dyn_evp_b200

@@ -144,7 +144,10 @@ def test_large_grid_properties(evp_lib):
     finish in seconds, so check size-independent properties: kernel strategies agree bit for bit, the
     state stays finite, cells off the ice are untouched, cyclic ghost columns equal their sources."""
     c = synth.make_case("p1deg", nx=900, ny=1200, ndte=6, seed=77)
-    outs = [run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=k) for k in KERNELS]
+    # the on-chip persistent kernel cannot hold 7300 cells per SM: it must refuse, not fall back silently
+    with pytest.raises(evp_lib.EvpB200Error, match="persistent kernel unavailable"):
+        run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_PERSISTENT)
+    outs = [run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=k) for k in (abi.KERNEL_SPLIT, abi.KERNEL_FUSED, abi.KERNEL_AUTO)]
     for o in outs[1:]:
         assert_bitwise(o, outs[0])
     o = outs[0]
