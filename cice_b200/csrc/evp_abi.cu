@@ -86,6 +86,8 @@ struct Ctx {
   // device memory
   double *dfield[NF_TOTAL] = {};  // dom-layout arrays (sig/u/v: copy 0)
   double *dsig1[12] = {}, *du1 = nullptr, *dv1 = nullptr;  // ping-pong copy 1
+  double *dshare = nullptr;  // [u0|u1|v0|v1] + 64 u64 flags in one allocation (CUDA-IPC shareable)
+  P2PState p2p;
   double *duinit = nullptr, *dvinit = nullptr;
   double *dstr[8] = {};
   unsigned char *dmaskT = nullptr, *dmaskU = nullptr;
@@ -138,6 +140,9 @@ static int free_all() {
     if (p) cudaFree(p);
     p = nullptr;
   };
+  g.p2p.release();
+  g.dfield[F_U] = g.dfield[F_V] = g.du1 = g.dv1 = nullptr;  // live inside dshare
+  F(g.dshare);
   for (auto &p : g.dfield) F(p);
   for (auto &p : g.dsig1) F(p);
   F(g.du1); F(g.dv1); F(g.duinit); F(g.dvinit);
@@ -285,10 +290,15 @@ static int do_init(const evp_b200_grid_t *gr) {
 
   // ---- device memory ----------------------------------------------------------------------------
   const size_t bdom = g.ndom * sizeof(double), bblk = g.nblk_elems * sizeof(double);
-  for (int f = 0; f < NF_TOTAL; ++f) { CK(cudaMalloc(&g.dfield[f], bdom)); CK(cudaMemsetAsync(g.dfield[f], 0, bdom, g.stream)); }
+  CK(cudaMalloc(&g.dshare, 4 * bdom + 64 * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(g.dshare, 0, 4 * bdom + 64 * sizeof(unsigned long long), g.stream));
+  for (int f = 0; f < NF_TOTAL; ++f) {
+    if (f == F_U || f == F_V) continue;
+    CK(cudaMalloc(&g.dfield[f], bdom)); CK(cudaMemsetAsync(g.dfield[f], 0, bdom, g.stream));
+  }
+  g.dfield[F_U] = g.dshare; g.du1 = g.dshare + g.ndom; g.dfield[F_V] = g.dshare + 2 * g.ndom; g.dv1 = g.dshare + 3 * g.ndom;
   for (int q = 0; q < 12; ++q) { CK(cudaMalloc(&g.dsig1[q], bdom)); CK(cudaMemsetAsync(g.dsig1[q], 0, bdom, g.stream)); }
-  CK(cudaMalloc(&g.du1, bdom)); CK(cudaMalloc(&g.dv1, bdom)); CK(cudaMalloc(&g.duinit, bdom)); CK(cudaMalloc(&g.dvinit, bdom));
-  CK(cudaMemsetAsync(g.du1, 0, bdom, g.stream)); CK(cudaMemsetAsync(g.dv1, 0, bdom, g.stream));
+  CK(cudaMalloc(&g.duinit, bdom)); CK(cudaMalloc(&g.dvinit, bdom));
   CK(cudaMemsetAsync(g.duinit, 0, bdom, g.stream)); CK(cudaMemsetAsync(g.dvinit, 0, bdom, g.stream));
   for (int q = 0; q < 8; ++q) { CK(cudaMalloc(&g.dstr[q], bdom)); CK(cudaMemsetAsync(g.dstr[q], 0, bdom, g.stream)); }
   CK(cudaMalloc(&g.dmaskT, g.ndom)); CK(cudaMalloc(&g.dmaskU, g.ndom));
@@ -323,6 +333,8 @@ static int do_init(const evp_b200_grid_t *gr) {
   // ---- halo plan ----------------------------------------------------------------------------------
   if (g.halo.build(g_comm, gi0, gj0, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, g_err, sizeof g_err)) return 1;
   d.wrap_ew = g.halo.wrap_ew; d.wrap_ns = g.halo.wrap_ns;
+  CK(cudaStreamSynchronize(g.stream));
+  if (g.p2p.setup(g_comm, g.halo, g.dshare, g.ndom, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, g_err, sizeof g_err)) return 1;
 
   if (const char *e = getenv("EVP_B200_FUSED_VARIANT")) g.fused_variant = atoi(e);
   if (const char *e = getenv("EVP_B200_PDL")) g.fused_pdl = (e[0] != '0');
@@ -345,6 +357,7 @@ static int do_init(const evp_b200_grid_t *gr) {
   snprintf(buf, sizeof buf, "dom %dx%d (ld %d) at global (%d,%d) of %dx%d; %d block(s) %dx%d; rank %d/%d; halo: %s; %s",
            nx, ny, d.ld, gi0, gj0, g.nxg, g.nyg, g.nblocks, nxb, nyb, g_comm.rank, g_comm.nranks, g.halo.describe().c_str(), pbuf);
   g.desc = buf;
+  g.desc += std::string("; p2p: ") + (g.p2p.enabled ? "" : "off (") + g.p2p.why + (g.p2p.enabled ? "" : ")");
   return 0;
 }
 
@@ -442,7 +455,20 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
     *launches = p->ndte > 0 ? 1 : 0;
     return 0;
   }
+  const bool p2p = g.p2p.enabled && kern == EVP_B200_KERNEL_FUSED;
+  if (p2p) {
+    CK(cudaMemsetAsync(g.p2p.d_done, 0, sizeof(unsigned long long), g.stream));
+    CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -1, g.stream) : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -1, g.stream));
+    ++nl;
+  }
   for (int ksub = 0; ksub < p->ndte; ++ksub) {
+    if (p2p) {
+      CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, g.stream)
+               : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, g.stream));
+      cur ^= 1;
+      ++nl;
+      continue;
+    }
     if (kern == EVP_B200_KERNEL_SPLIT) {
       CK(exact ? exact::launch_stress(g.dom, k, cur, g.stream) : fast::launch_stress(g.dom, k, cur, g.stream));
       CK(exact ? exact::launch_stepu(g.dom, k, cur, g.stream) : fast::launch_stepu(g.dom, k, cur, g.stream));
@@ -459,6 +485,11 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
     int hl = 0;
     if (g.halo.exchange(g_comm, g.dom.u[cur], g.dom.v[cur], g.stream, &hl, g_err, sizeof g_err)) return 1;
     nl += hl;
+  }
+  if (p2p) {
+    CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -2 - p->ndte, g.stream)
+             : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -2 - p->ndte, g.stream));
+    ++nl;
   }
   *cur_end = cur;
   *launches = nl;
@@ -479,6 +510,7 @@ static int do_subcycle(const evp_b200_params_t *p) {
     std::swap(g.dom.v[0], g.dom.v[1]);
     for (int q = 0; q < 12; ++q) std::swap(g.dom.sig[0][q], g.dom.sig[1][q]);
     g.cur = 0;
+    if (g.p2p.enabled) g.p2p.set_parity(g.p2p.swapped ^ 1);
     destroy_graph();  // pointers baked into the graph changed
   }
   // uvel_init = uvel at entry (ice_dyn_shared.F90:787-788; ice_dyn_evp1d.F90:939-940)
@@ -514,6 +546,33 @@ static int do_subcycle(const evp_b200_params_t *p) {
   g.last_launches = nl;
   CK(cudaStreamSynchronize(g.stream));
   CK(cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1));
+  if (g.p2p.enabled) {
+    int e = 0;
+    CK(cudaMemcpy(&e, g.p2p.d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (g.p2p.prm.dbg) {
+      static std::vector<unsigned long long> w(8 + 8 * 1024);
+      CK(cudaMemcpy(w.data(), g.p2p.d_dbg, w.size() * 8, cudaMemcpyDeviceToHost));
+      std::vector<unsigned long long> init(w.size(), 0);
+      for (int k = 0; k < 1024; ++k) init[8 + 8 * k] = ~0ULL;  // slot 0 is an atomicMin
+      CK(cudaMemcpy(g.p2p.d_dbg, init.data(), w.size() * 8, cudaMemcpyHostToDevice));
+      const int n = std::min(p->ndte, 1024);
+      double dur = 0, gap = 0, t_edge = 0, t_push = 0, t_flag = 0, t_rel = 0;
+      int cnt = 0;
+      for (int k = 1; k + 1 < n; ++k) {
+        const unsigned long long *a = &w[8 + 8 * k], *b = &w[8 + 8 * (k + 1)];
+        if (a[0] == ~0ULL || a[0] == 0 || b[0] == ~0ULL) continue;
+        dur += (double)(a[1] - a[0]); gap += (double)(b[0] - a[1]);
+        t_edge += (double)(a[2] - a[0]); t_push += (double)(a[3] - a[0]); t_flag += (double)(a[4] - a[0]); t_rel += (double)(a[5] - a[0]);
+        ++cnt;
+      }
+      if (cnt)
+        fprintf(stderr, "[evp_b200 p2p rank %d] loop %.3f ms | per kernel (us): duration %.2f, gap to next %.2f, last edge CTA released from wait at %.2f, "
+                        "last edge CTA done at %.2f, ring pushed+fenced at %.2f, flags written at %.2f | waits: mean %.0f cyc, max %llu\n",
+                g_comm.rank, g.last_ms, dur / cnt / 1e3, gap / cnt / 1e3, t_rel / cnt / 1e3, t_edge / cnt / 1e3, t_push / cnt / 1e3, t_flag / cnt / 1e3,
+                w[1] ? (double)w[0] / (double)w[1] : 0.0, w[2]);
+    }
+    if (e) return fail("evp_b200_subcycle: a neighbour GPU did not deliver its halo in time (in-kernel NVLink hand-over timed out)");
+  }
   return 0;
 }
 

@@ -204,9 +204,13 @@ int HaloPlan::build(CommState &cs, int gi0, int gj0, int nx, int ny, int ld, int
     HFAIL("halo: one rank but its blocks cover %dx%d of the %dx%d domain; call evp_b200_comm_init first", nx, ny, nxg, nyg);
   }
 
+  rects.assign(4 * (size_t)cs.nranks, 0);
+  for (int q = 0; q < cs.nranks; ++q) { rects[4 * q] = R[q].gi0; rects[4 * q + 1] = R[q].gj0; rects[4 * q + 2] = R[q].nx; rects[4 * q + 3] = R[q].ny; }
   const int me = cs.rank;
   std::vector<Entry> mine;
   enumerate(R, me, nxg, nyg, ew, ns, mine);
+  has_fold = false;
+  for (const Entry &e : mine) has_fold = has_fold || e.code != OP_COPY || e.r1 == me;
 
   // pack list: local sources first, then what each peer needs from me (in the peer's entry order)
   std::vector<int> pack_idx, h_dst, h_s1, h_s2;
@@ -287,6 +291,214 @@ int HaloPlan::exchange(CommState &cs, double *U, double *V, cudaStream_t s, int 
   }
   HCK(cudaGetLastError());
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// P2P: map the neighbours' velocity arrays, build the push table and the edge-first tile order
+// ------------------------------------------------------------------------------------------------
+int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t ndom, int nx, int ny, int ld, int nxg, int nyg,
+                    int ew, int ns, char *err, size_t nerr) {
+  release();
+  enabled = false;
+  const bool selftest = cs.nranks < 2 && getenv("EVP_B200_P2P_SELFTEST");
+  if (cs.nranks < 2 && !selftest) { why = "single rank"; return 0; }
+  if (selftest) {
+    // one rank, no peers: runs the edge-first tile order, the edge-CTA counter and the hand-shake kernels
+    // without any NVLink traffic (timing / parity of the kernel structure itself)
+    const int ntx = (nx + 30) / 31, nty = (ny + 6) / 7;
+    std::vector<int> order, start(2 * nx + 2 * (ny - 2) + 1, 0), none;
+    int n_edge = 0;
+    const bool rev = getenv("EVP_B200_P2P_SELFTEST")[0] == '2';
+    for (int pass = 0; pass < 2; ++pass)
+      for (int t = 0; t < ntx * nty; ++t) {
+        const int bx = t % ntx, by = t / ntx;
+        const bool edge = (bx == 0 || bx == ntx - 1 || by == 0 || by == nty - 1);
+        if (edge == (pass == 0)) { order.push_back(t); n_edge += edge; }
+      }
+    const char stm = getenv("EVP_B200_P2P_SELFTEST")[0];
+    if (rev) { order.clear(); for (int t = 0; t < ntx * nty; ++t) order.push_back(t); n_edge = 0; }
+    if (stm == '3') n_edge = 0;                                                     // edge-first order, no counter
+    if (stm == '4') { order.clear(); for (int t = 0; t < ntx * nty; ++t) order.push_back(t); }  // natural order, counter on the first n_edge tiles
+    if (up(d_tile_order, order, err, nerr) || up(d_push_start, start, err, nerr) || up(d_push_peer, none, err, nerr) || up(d_push_dst, none, err, nerr)) return 1;
+    HCK(cudaMalloc(&d_done, sizeof(unsigned long long))); HCK(cudaMalloc(&d_epoch, sizeof(unsigned long long))); HCK(cudaMalloc(&d_err, sizeof(int)));
+    HCK(cudaMemset(d_done, 0, 8)); HCK(cudaMemset(d_err, 0, 4)); HCK(cudaMemset(d_epoch, 0, 8));
+    prm = P2PParams{};
+    prm.enabled = 1; prm.npeers = 0; prm.n_edge_tiles = n_edge; prm.ntx = ntx; prm.nty = nty;
+    prm.tile_order = d_tile_order; prm.n_push = 0; prm.push_start = d_push_start; prm.push_peer = d_push_peer; prm.push_dst = d_push_dst;
+    prm.my_flags = (const unsigned long long *)(dshare + 4 * ndom);
+    prm.done_ctr = d_done; prm.epoch_base = d_epoch; prm.err = d_err;
+    enabled = true; why = "selftest (no peers)";
+    return 0;
+  }
+  const char *env = getenv("EVP_B200_P2P");
+  int want = !(env && env[0] == '0');
+  const int me = cs.rank;
+  std::vector<Rect> R(cs.nranks);
+  for (int q = 0; q < cs.nranks; ++q) R[q] = Rect{plan.rects[4 * q], plan.rects[4 * q + 1], plan.rects[4 * q + 2], plan.rects[4 * q + 3]};
+
+  // push table: every ghost cell of another rank whose source is one of my interior cells
+  struct Push { int src, rank, dst; };
+  std::vector<Push> pushes;
+  std::vector<int> peer_ranks;
+  bool fold = plan.has_fold;
+  auto slot_of = [&](int rk) {
+    for (size_t q = 0; q < peer_ranks.size(); ++q) if (peer_ranks[q] == rk) return (int)q;
+    peer_ranks.push_back(rk);
+    return (int)peer_ranks.size() - 1;
+  };
+  for (int q = 0; q < cs.nranks; ++q) {
+    if (q == me) continue;
+    std::vector<Entry> theirs;
+    enumerate(R, q, nxg, nyg, ew, ns, theirs);
+    for (const Entry &e : theirs) {
+      if (e.code != OP_COPY || e.r1 == q) fold = true;
+      if (e.r1 == me) { pushes.push_back(Push{e.c1, q, e.dst}); slot_of(q); }
+    }
+  }
+  {
+    std::vector<Entry> mine;
+    enumerate(R, me, nxg, nyg, ew, ns, mine);
+    for (const Entry &e : mine) if (e.r1 != me && e.r1 >= 0) slot_of(e.r1);
+  }
+  if (fold) { want = 0; why = "tripole fold / on-rank copies need the staged exchange"; }
+  if ((int)peer_ranks.size() > P2P_MAXPEER) { want = 0; why = "too many peers"; }
+  if (nx < 2 || ny < 3) { want = 0; why = "sub-domain too small"; }
+
+  // exchange IPC handles of the shared segment and try to map every peer
+  cudaIpcMemHandle_t myh;
+  memset(&myh, 0, sizeof myh);
+  if (want) {
+    cudaError_t e = cudaIpcGetMemHandle(&myh, dshare);
+    if (e != cudaSuccess) { want = 0; why = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); }
+  }
+  unsigned char *dbuf = nullptr;
+  const size_t hs = sizeof(cudaIpcMemHandle_t);
+  HCK(cudaMalloc(&dbuf, hs * cs.nranks));
+  HCK(cudaMemcpy(dbuf + hs * me, &myh, hs, cudaMemcpyHostToDevice));
+  NCK(ncclAllGather(dbuf + hs * me, dbuf, hs, ncclChar, cs.comm, 0));
+  HCK(cudaStreamSynchronize(0));
+  std::vector<cudaIpcMemHandle_t> hall(cs.nranks);
+  HCK(cudaMemcpy(hall.data(), dbuf, hs * cs.nranks, cudaMemcpyDeviceToHost));
+  HCK(cudaFree(dbuf));
+  npeers = (int)peer_ranks.size();
+  if (want) {
+    for (int q = 0; q < npeers; ++q) {
+      void *ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, hall[peer_ranks[q]], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        want = 0; why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); cudaGetLastError();
+        break;
+      }
+      peer_base[q] = (double *)ptr;
+      const Rect &A = R[peer_ranks[q]];
+      peer_ndom[q] = (size_t)ld_of(A.nx) * (A.ny + 2);
+    }
+  }
+  // every rank must take the same path
+  int *dflag = nullptr;
+  HCK(cudaMalloc(&dflag, sizeof(int)));
+  HCK(cudaMemcpy(dflag, &want, sizeof(int), cudaMemcpyHostToDevice));
+  NCK(ncclAllReduce(dflag, dflag, 1, ncclInt32, ncclMin, cs.comm, 0));
+  HCK(cudaStreamSynchronize(0));
+  int all = 0;
+  HCK(cudaMemcpy(&all, dflag, sizeof(int), cudaMemcpyDeviceToHost));
+  HCK(cudaFree(dflag));
+  if (!all) {
+    if (want) why = "a peer rank could not map the shared segment";
+    for (int q = 0; q < npeers; ++q) if (peer_base[q]) { cudaIpcCloseMemHandle(peer_base[q]); peer_base[q] = nullptr; }
+    npeers = 0;
+    return 0;
+  }
+
+  // CSR over the edge index of the source cell
+  const int nedge = 2 * nx + 2 * (ny - 2);
+  std::vector<int> start(nedge + 1, 0), ppeer(pushes.size()), pdst(pushes.size());
+  auto eidx = [&](int c) {
+    const int i = c % ld, j = c / ld;
+    if (j == 1) return i - 1;
+    if (j == ny) return nx + i - 1;
+    if (i == 1) return 2 * nx + (j - 2);
+    return 2 * nx + (ny - 2) + (j - 2);
+  };
+  for (const Push &p : pushes) {
+    const int i = p.src % ld, j = p.src / ld;
+    if (!(i == 1 || i == nx || j == 1 || j == ny)) HFAIL("p2p: a push source is not on the sub-domain edge");
+    start[eidx(p.src) + 1]++;
+  }
+  for (int e = 0; e < nedge; ++e) start[e + 1] += start[e];
+  {
+    std::vector<int> fill(start.begin(), start.end() - 1);
+    for (const Push &p : pushes) {
+      const int k = fill[eidx(p.src)]++;
+      ppeer[k] = slot_of(p.rank);
+      pdst[k] = p.dst;
+    }
+  }
+  // tile order of the 32x8 fused kernel, edge tiles first
+  const int ntx = (nx + 30) / 31, nty = (ny + 6) / 7;
+  std::vector<int> order;
+  int n_edge = 0;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int t = 0; t < ntx * nty; ++t) {
+      const int bx = t % ntx, by = t / ntx;
+      const bool edge = (bx == 0 || bx == ntx - 1 || by == 0 || by == nty - 1);
+      if (edge == (pass == 0)) { order.push_back(t); n_edge += edge; }
+    }
+  if (up(d_tile_order, order, err, nerr) || up(d_push_start, start, err, nerr) || up(d_push_peer, ppeer, err, nerr) ||
+      up(d_push_dst, pdst, err, nerr))
+    return 1;
+  HCK(cudaMalloc(&d_done, sizeof(unsigned long long)));
+  HCK(cudaMalloc(&d_epoch, sizeof(unsigned long long)));
+  HCK(cudaMalloc(&d_err, sizeof(int)));
+  HCK(cudaMalloc(&d_dbg, (8 + 8 * 1024) * sizeof(unsigned long long)));
+  HCK(cudaMemset(d_dbg, 0, (8 + 8 * 1024) * sizeof(unsigned long long)));
+  HCK(cudaMemset(d_done, 0, sizeof(unsigned long long)));
+  HCK(cudaMemset(d_err, 0, sizeof(int)));
+  const unsigned long long one = 1;  // flags start at 0: epoch 0 is "nothing yet"
+  HCK(cudaMemcpy(d_epoch, &one, sizeof one, cudaMemcpyHostToDevice));
+  HCK(cudaMemset(dshare + 4 * ndom, 0, 64 * sizeof(unsigned long long)));
+
+  prm = P2PParams{};
+  prm.enabled = 1; prm.npeers = npeers; prm.n_edge_tiles = n_edge; prm.ntx = ntx; prm.nty = nty;
+  prm.tile_order = d_tile_order; prm.n_push = (int)pushes.size(); prm.push_start = d_push_start; prm.push_peer = d_push_peer; prm.push_dst = d_push_dst;
+  prm.my_flags = (const unsigned long long *)(dshare + 4 * ndom);
+  for (int q = 0; q < npeers; ++q) {
+    prm.peer_rank[q] = peer_ranks[q];
+    prm.peer_flag[q] = (unsigned long long *)(peer_base[q] + 4 * peer_ndom[q]) + me;
+  }
+  prm.done_ctr = d_done; prm.epoch_base = d_epoch; prm.err = d_err;
+  prm.dbg = getenv("EVP_B200_P2P_DEBUG") ? d_dbg : nullptr;
+  set_parity(0);
+  // nobody may be written to before every rank has zeroed its flags
+  NCK(ncclAllReduce(d_err, d_err, 1, ncclInt32, ncclMax, cs.comm, 0));
+  HCK(cudaStreamSynchronize(0));
+  enabled = true;
+  char b[160];
+  snprintf(b, sizeof b, "in-kernel NVLink stores to %d peer(s), %zu pushed cells, %d edge tiles of %d", npeers, pushes.size(), n_edge, ntx * nty);
+  why = b;
+  return 0;
+}
+
+void P2PState::set_parity(int s) {
+  swapped = s;
+  for (int q = 0; q < npeers; ++q) {
+    for (int b = 0; b < 2; ++b) {
+      prm.peer_u[b][q] = peer_base[q] + (size_t)(b ^ s) * peer_ndom[q];
+      prm.peer_v[b][q] = peer_base[q] + (size_t)(2 + (b ^ s)) * peer_ndom[q];
+    }
+  }
+}
+
+void P2PState::release() {
+  for (int q = 0; q < P2P_MAXPEER; ++q) {
+    if (peer_base[q]) cudaIpcCloseMemHandle(peer_base[q]);
+    peer_base[q] = nullptr;
+  }
+  auto F = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
+  F(d_tile_order); F(d_push_start); F(d_push_peer); F(d_push_dst); F(d_done); F(d_epoch); F(d_err); F(d_dbg);
+  enabled = false;
+  npeers = 0;
+  prm = P2PParams{};
 }
 
 std::string HaloPlan::describe() const {

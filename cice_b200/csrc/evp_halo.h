@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 
+#include "evp_internal.h"
+
 #include <string>
 #include <vector>
 
@@ -41,10 +43,34 @@ struct HaloPlan {
   std::vector<Peer> peers;
   bool allow_graph = true;
 
+  std::vector<int> rects;  // 4 ints per rank {gi0, gj0, nx, ny}, filled by build
+  bool has_fold = false;   // some entry is not a plain copy (tripole)
+
   int build(CommState &cs, int gi0, int gj0, int nx, int ny, int ld, int nxg, int nyg, int ew, int ns, char *err, size_t nerr);
   int exchange(CommState &cs, double *U, double *V, cudaStream_t s, int *launches, char *err, size_t nerr);
   bool graph_safe() const { return allow_graph; }
   std::string describe() const;
+  void release();
+};
+
+// In-kernel NVLink halo: peers' velocity arrays and flags mapped through CUDA IPC (one process per GPU).
+struct P2PState {
+  bool enabled = false;
+  std::string why = "not set up";
+  P2PParams prm{};
+  int swapped = 0;
+  int npeers = 0;
+  double *peer_base[P2P_MAXPEER] = {};
+  size_t peer_ndom[P2P_MAXPEER] = {};
+  int *d_tile_order = nullptr, *d_push_start = nullptr, *d_push_peer = nullptr, *d_push_dst = nullptr;
+  unsigned long long *d_done = nullptr, *d_epoch = nullptr;
+  int *d_err = nullptr;
+  unsigned long long *d_dbg = nullptr;
+
+  // dshare = [u0 | u1 | v0 | v1] (ndom doubles each) followed by 64 u64 flags, one cudaMalloc
+  int setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t ndom, int nx, int ny, int ld, int nxg, int nyg,
+            int ew, int ns, char *err, size_t nerr);
+  void set_parity(int swapped_);
   void release();
 };
 

@@ -43,6 +43,29 @@ struct KParams {
   double u0, cosw, sinw, rhow;
 };
 
+// In-kernel NVLink halo (see evp_halo.cu, fused_kernel): edge CTAs store new edge velocities straight into the
+// neighbour GPUs' ghost cells (CUDA-IPC mapped peer memory) and hand over with per-peer epoch flags.
+#define P2P_MAXPEER 16
+struct P2PParams {
+  int enabled;
+  int npeers;
+  int n_edge_tiles;              // tiles touching the sub-domain boundary; they are scheduled first
+  int ntx, nty;                  // tile grid of the fused kernel
+  const int *tile_order;         // [ntx*nty] tile ids, edge tiles first
+  int n_push;                    // ghost cells of neighbour ranks that are fed from this rank
+  const int *push_start;         // CSR over the edge index of a boundary U point (see edge_index)
+  const int *push_peer;          // peer slot
+  const int *push_dst;           // cell index inside that peer's sub-domain array
+  double *peer_u[2][P2P_MAXPEER], *peer_v[2][P2P_MAXPEER];
+  unsigned long long *peer_flag[P2P_MAXPEER];  // the peer's flags[my rank]
+  const unsigned long long *my_flags;          // my flags[], indexed by peer rank
+  int peer_rank[P2P_MAXPEER];
+  unsigned long long *done_ctr;                // edge CTAs finished so far in this loop
+  unsigned long long *epoch_base;              // device-resident: epoch of the current loop
+  int *err;                                    // set when a wait times out
+  unsigned long long *dbg;                     // [0] sum of wait cycles of lane 0 of edge CTAs, [1] number of waits, [2] max wait
+};
+
 // KERNEL_PERSISTENT tiling (see evp_persist.cu)
 #define PERSIST_THREADS 512
 struct PersistPlan {
@@ -64,6 +87,7 @@ struct PersistPlan {
   cudaError_t launch_stress(const Dom &d, const KParams &p, int cur, cudaStream_t s);               \
   cudaError_t launch_stepu(const Dom &d, const KParams &p, int cur, cudaStream_t s);                \
   cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl); \
+  cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, cudaStream_t s); \
   cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s); \
   }
 EVP_DECLARE_LAUNCHERS(exact)

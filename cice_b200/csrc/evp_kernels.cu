@@ -127,20 +127,86 @@ cudaError_t launch_stepu(const Dom &d, const KParams &p, int cur, cudaStream_t s
 // ---------------------------------------------------------------------------------------------
 // FBX x FBY threads relax an FBX x FBY patch of T cells and advance the (FBX-1) x (FBY-1) U points it closes.
 // MINB = CTAs per SM the register allocation is bounded for.
-template <int FBX, int FBY, int MINB>
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// wait until flag >= want; bounded so that a lost peer cannot hang the GPU (sets *err instead)
+__device__ __forceinline__ void wait_flag(const unsigned long long *flag, unsigned long long want, int *err) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < want) {
+    if (clock64() - t0 > 6000000000LL) { atomicExch(err, 1); break; }
+  }
+}
+
+// edge index of a boundary U point (i==1 | i==nx | j==1 | j==ny), the row index of the push CSR
+__device__ __forceinline__ int edge_index(const Dom &d, int i, int j) {
+  if (j == 1) return i - 1;
+  if (j == d.ny) return d.nx + i - 1;
+  if (i == 1) return 2 * d.nx + (j - 2);
+  return 2 * d.nx + (d.ny - 2) + (j - 2);
+}
+
+template <int FBX, int FBY, int MINB, bool HOIST, bool P2P = false>
 __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_constant__ Dom d,
-                                                                const __grid_constant__ KParams k, int cur) {
+                                                                const __grid_constant__ KParams k, int cur,
+                                                                const __grid_constant__ P2PParams pp, int ksub) {
   __shared__ double sstr[8][FBY][FBX];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int i = 1 + blockIdx.x * (FBX - 1) + tx;  // T cell of this thread
-  const int j = 1 + blockIdx.y * (FBY - 1) + ty;
+  int tbx = blockIdx.x, tby = blockIdx.y;
+  bool edge_tile = false;
+  if (P2P) {
+    const int tile = pp.tile_order[blockIdx.x];
+    tbx = tile % pp.ntx;
+    tby = tile / pp.ntx;
+    edge_tile = (int)blockIdx.x < pp.n_edge_tiles;
+  }
+  const int i = 1 + tbx * (FBX - 1) + tx;  // T cell of this thread
+  const int j = 1 + tby * (FBY - 1) + ty;
   const int nxt = cur ^ 1;
+  unsigned long long base = 0;
+  unsigned long long *tl = (P2P && pp.dbg) ? pp.dbg + 8 + 8 * (size_t)ksub : nullptr;  // per-kernel timeline (ns)
+  if (tl && tx == 0 && ty == 0) atomicMin(tl + 0, gtime());
+  if (P2P && edge_tile) {
+    // the ghost ring of copy `cur` was written by the neighbour GPUs during their previous subcycle
+    base = *pp.epoch_base;
+    const int t = ty * FBX + tx;
+    const long long tw0 = clock64();
+    if (t < pp.npeers) wait_flag(pp.my_flags + pp.peer_rank[t], base + (unsigned long long)ksub, pp.err);
+    if (t == 0 && pp.dbg) {
+      const unsigned long long dt = (unsigned long long)(clock64() - tw0);
+      atomicAdd(pp.dbg, dt);
+      atomicAdd(pp.dbg + 1, 1ULL);
+      atomicMax(pp.dbg + 2, dt);
+      if (tl) atomicMax(tl + 5, gtime());  // last edge CTA released from its wait
+    }
+    __syncthreads();
+  }
   const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
   const size_t c = at(d, inT ? i : 1, inT ? j : 1);
 #if EVP_USE_PDL
   // programmatic dependent launch: everything above overlaps the previous subcycle's tail
   cudaGridDependencySynchronize();
 #endif
+
+  // the momentum step's operands are requested before the stress arithmetic so that their L2 latency
+  // hides under it (the U point of this thread is its own T cell index)
+  const bool doU = tx < FBX - 1 && ty < FBY - 1 && i <= d.nx && j <= d.ny && d.maskU[c];
+  double uin[16];
+  if (HOIST && doU) {
+    uin[0] = d.u[cur][c]; uin[1] = d.v[cur][c]; uin[2] = d.cdn[c]; uin[3] = d.aiu[c]; uin[4] = d.uocn[c]; uin[5] = d.vocn[c];
+    uin[6] = d.waterx[c]; uin[7] = d.watery[c]; uin[8] = d.forcex[c]; uin[9] = d.forcey[c]; uin[10] = d.umassdti[c];
+    uin[11] = d.fm[c]; uin[12] = d.uarear[c]; uin[13] = d.TbU[c]; uin[14] = d.uinit[c]; uin[15] = d.vinit[c];
+  }
 
   double str[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (inT && d.maskT[c]) {
@@ -154,10 +220,14 @@ __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_cons
   for (int q = 0; q < 8; ++q) sstr[q][ty][tx] = str[q];
   __syncthreads();
 
-  if (tx < FBX - 1 && ty < FBY - 1 && i <= d.nx && j <= d.ny && d.maskU[c]) {
-    const UOut o = stepu_point(d.u[cur][c], d.v[cur][c], d.cdn[c], d.aiu[c], d.uocn[c], d.vocn[c], d.waterx[c],
-                               d.watery[c], d.forcex[c], d.forcey[c], d.umassdti[c], d.fm[c], d.uarear[c],
-                               d.TbU[c], d.uinit[c], d.vinit[c], sstr[0][ty][tx], sstr[1][ty][tx + 1],
+  if (doU) {
+    if (!HOIST) {
+      uin[0] = d.u[cur][c]; uin[1] = d.v[cur][c]; uin[2] = d.cdn[c]; uin[3] = d.aiu[c]; uin[4] = d.uocn[c]; uin[5] = d.vocn[c];
+      uin[6] = d.waterx[c]; uin[7] = d.watery[c]; uin[8] = d.forcex[c]; uin[9] = d.forcey[c]; uin[10] = d.umassdti[c];
+      uin[11] = d.fm[c]; uin[12] = d.uarear[c]; uin[13] = d.TbU[c]; uin[14] = d.uinit[c]; uin[15] = d.vinit[c];
+    }
+    const UOut o = stepu_point(uin[0], uin[1], uin[2], uin[3], uin[4], uin[5], uin[6], uin[7], uin[8], uin[9], uin[10], uin[11],
+                               uin[12], uin[13], uin[14], uin[15], sstr[0][ty][tx], sstr[1][ty][tx + 1],
                                sstr[2][ty + 1][tx], sstr[3][ty + 1][tx + 1], sstr[4][ty][tx], sstr[5][ty + 1][tx],
                                sstr[6][ty][tx + 1], sstr[7][ty + 1][tx + 1], k);
     store_uv(d, d.u[nxt], d.v[nxt], i, j, o.u, o.v);
@@ -165,10 +235,56 @@ __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_cons
     d.strinty[c] = o.strinty;
     d.taubx[c] = o.taubx;
     d.tauby[c] = o.tauby;
+    if (P2P && (i == 1 || i == d.nx || j == 1 || j == d.ny)) {
+      // this point is a ghost cell of up to three neighbour GPUs: store it there over NVLink right away, so the
+      // traffic is spread over the kernel and long acknowledged when the hand-over fence below is issued
+      const int e = edge_index(d, i, j);
+      for (int q = pp.push_start[e]; q < pp.push_start[e + 1]; ++q) {
+        const int pr = pp.push_peer[q];
+        const int dst = pp.push_dst[q];
+        pp.peer_u[nxt][pr][dst] = o.u;
+        pp.peer_v[nxt][pr][dst] = o.v;
+      }
+    }
   }
+  if (P2P && edge_tile) {
+    // Hand-over.  Every edge CTA counts itself done with gpu-scope ordering (a system-scope fence per CTA costs
+    // ~3 us per kernel).  The CTA that arrives last issues the ONE system-scope fence -- cumulative over the NVLink
+    // stores of all edge CTAs it has synchronised with through the counter -- and then raises the peers' flags.
+    const int t = ty * FBX + tx;
+    __syncthreads();
+    if (t == 0) {
+      __threadfence();
+      const unsigned long long old = atomicAdd(pp.done_ctr, 1ULL);
+      if (old + 1 == (unsigned long long)pp.n_edge_tiles * (unsigned long long)(ksub + 1)) {
+        if (tl) tl[2] = gtime();  // last edge CTA done computing
+        __threadfence_system();
+        if (tl) tl[3] = gtime();  // fenced
+        for (int q = 0; q < pp.npeers; ++q)
+          asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(pp.peer_flag[q]), "l"(base + (unsigned long long)ksub + 1ULL) : "memory");
+        if (tl) tl[4] = gtime();  // flags written
+      }
+    }
+  }
+  if (tl && tx == 0 && ty == 0) atomicMax(tl + 1, gtime());
 }
 
-template <int FBX, int FBY, int MINB>
+// loop hand-shake: "I have entered loop `base`" (my buffers are ready to be written), and the closing wait
+__global__ void p2p_start_kernel(const __grid_constant__ P2PParams pp) {
+  if (threadIdx.x == 0) {
+    const unsigned long long base = *pp.epoch_base;
+    __threadfence_system();
+    for (int q = 0; q < pp.npeers; ++q) st_release_sys(pp.peer_flag[q], base);
+  }
+}
+__global__ void p2p_finish_kernel(const __grid_constant__ P2PParams pp, int ndte) {
+  const unsigned long long base = *pp.epoch_base;
+  if ((int)threadIdx.x < pp.npeers) wait_flag(pp.my_flags + pp.peer_rank[threadIdx.x], base + (unsigned long long)ndte, pp.err);
+  __syncthreads();
+  if (threadIdx.x == 0) *pp.epoch_base = base + (unsigned long long)ndte + 1ULL;
+}
+
+template <int FBX, int FBY, int MINB, bool HOIST = false>
 static cudaError_t launch_fused_t(const Dom &d, const KParams &p, int cur, cudaStream_t s, bool pdl) {
   dim3 b(FBX, FBY), g((d.nx + FBX - 2) / (FBX - 1), (d.ny + FBY - 2) / (FBY - 1));
   cudaLaunchConfig_t cfg{};
@@ -177,7 +293,8 @@ static cudaError_t launch_fused_t(const Dom &d, const KParams &p, int cur, cudaS
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, fused_kernel<FBX, FBY, MINB>, d, p, cur);
+  static const P2PParams nop2p{};
+  return cudaLaunchKernelEx(&cfg, fused_kernel<FBX, FBY, MINB, HOIST, false>, d, p, cur, nop2p, 0);
 }
 
 cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl) {
@@ -188,8 +305,26 @@ cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s
     case 4: return launch_fused_t<32, 16, 1>(d, p, cur, s, pdl);
     case 5: return launch_fused_t<64, 4, 2>(d, p, cur, s, pdl);
     case 6: return launch_fused_t<32, 6, 3>(d, p, cur, s, pdl);
+    case 7: return launch_fused_t<32, 8, 2, true>(d, p, cur, s, pdl);
+    case 8: return launch_fused_t<33, 8, 2, false>(d, p, cur, s, pdl);
+    case 9: return launch_fused_t<33, 8, 2, true>(d, p, cur, s, pdl);
+    case 10: return launch_fused_t<32, 4, 4, true>(d, p, cur, s, pdl);
     default: return launch_fused_t<32, 8, 2>(d, p, cur, s, pdl);
   }
+}
+
+// ksub = -1: loop start hand-shake; ksub = -2 - ndte ... no: see launch_p2p_aux
+cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, cudaStream_t s) {
+  if (ksub == -1) {
+    p2p_start_kernel<<<1, 32, 0, s>>>(pp);
+    return cudaGetLastError();
+  }
+  if (ksub <= -2) {  // closing wait after -2-ksub subcycles
+    p2p_finish_kernel<<<1, 32, 0, s>>>(pp, -2 - ksub);
+    return cudaGetLastError();
+  }
+  fused_kernel<32, 8, 2, false, true><<<dim3(pp.ntx * pp.nty), dim3(32, 8), 0, s>>>(d, p, cur, pp, ksub);
+  return cudaGetLastError();
 }
 
 }  // namespace EVP_NS

@@ -60,6 +60,8 @@ def main():
                     print(f"  differs: {n} on blocks {list(bids_r)}: {np.count_nonzero(a != b)} cells, max {np.nanmax(np.abs(a - b)):.3e}")
         ok = nbad == 0
         print(f"[{cfg} {bsx}x{bsy} ndte={ndte} kernel={kernel} ns={ns} procs={pg}] launches/rank={out[0][3]}  {out[0][2]}")
+        for o in out:
+            print("   ", o[2])
         print("MGPU PASS" if ok else "MGPU FAIL")
     dist.barrier()
     dist.destroy_process_group()

@@ -180,13 +180,16 @@ def test_tx1_tripole_full(oracle_mod, evp_lib):
     assert_bitwise(got, ref)
 
 
+@pytest.mark.parametrize("p2p", ["1", "0"], ids=["nvlink-stores", "nccl"])
 @pytest.mark.parametrize("args", [
-    ["gx3", "25", "29", "20", "fused"],
+    ["gx3", "25", "29", "40", "fused"],
     ["gx3", "50", "58", "15", "split"],
     ["tiny", "12", "10", "16", "fused", "tripole"],
 ], ids=["gx3-16blocks-fused", "gx3-4blocks-split", "tiny-tripole"])
-def test_multi_gpu_nccl_halo(args):
-    """N>1: one process per GPU, NCCL send/recv halo every subcycle, bit-identical to the oracle.
+def test_multi_gpu_halo(args, p2p):
+    """N>1: one process per GPU; the (uvel,vvel) halo goes either through in-kernel NVLink stores into the
+    neighbours' ghost cells (default for the fused kernel) or through the staged NCCL send/recv exchange
+    (split kernel, tripole fold, EVP_B200_P2P=0).  Bit-identical to the oracle either way.
     Runs when the box exposes at least 2 GPUs (gpurun --gpus 2); the 1-GPU round-end run skips it."""
     import subprocess
     import sys
@@ -199,8 +202,10 @@ def test_multi_gpu_nccl_halo(args):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(root, "tests", "mgpu_check.py")] + args
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, EVP_B200_P2P=p2p))
     assert "MGPU PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    if p2p == "1" and args[4] == "fused" and len(args) < 6:
+        assert "in-kernel NVLink stores" in r.stdout, r.stdout[-2000:]
 
 
 def test_errors_are_reported_not_fatal(evp_lib):
