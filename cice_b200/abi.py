@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 BNDY_OPEN, BNDY_CLOSED, BNDY_CYCLIC, BNDY_TRIPOLE = 0, 1, 2, 3
 BNDY_NAMES = {"open": BNDY_OPEN, "closed": BNDY_CLOSED, "cyclic": BNDY_CYCLIC, "tripole": BNDY_TRIPOLE}
@@ -35,9 +35,9 @@ class Grid(C.Structure):
 
 class Params(C.Structure):
     _fields_ = (
-        [(n, C.c_int32) for n in ("ndte", "mode", "kernel", "reserved")]
+        [(n, C.c_int32) for n in ("ndte", "mode", "kernel", "visc_method")]
         + [(n, C.c_double) for n in ("arlx1i", "denom1", "revp", "brlx", "e_factor", "epp2i", "capping",
-                                     "Ktens", "u0", "cosw", "sinw", "rhow")]
+                                     "Ktens", "u0", "cosw", "sinw", "rhow", "deltaminEVP")]
     )
 
 
@@ -54,6 +54,29 @@ FIELDS_ORDER = (STRESS + ("strength", "cdn_ocnU", "aiU", "uocnU", "vocnU", "wate
 
 class Fields(C.Structure):
     _fields_ = [(n, _pd) for n in FIELDS_ORDER] + [(n, _pi) for n in FIELDS_MASK]
+
+
+VISC_AVG_ZETA, VISC_AVG_STRENGTH = 0, 1
+
+CGRID_STATIC = ("dxN", "dyE", "dxE", "dyN", "dxU", "dyU", "tarea", "uarea", "earea", "narea", "earear", "narear",
+                "ratiodxN", "ratiodxNr", "ratiodyE", "ratiodyEr", "hm", "uvm", "epm", "npm")
+
+
+class CGrid(C.Structure):
+    _fields_ = [(n, _pd) for n in CGRID_STATIC]
+
+
+CFIELDS_INOUT = ("uvelE", "vvelE", "uvelN", "vvelN", "uvel", "vvel", "stresspT", "stressmT", "stress12T", "stress12U")
+CFIELDS_OUT = ("zetax2T", "etax2T", "etax2U", "strengthU", "divergU", "tensionU", "shearU", "deltaU",
+               "strintxE", "strintyN", "taubxE", "taubyN")
+CFIELDS_IN = ("strength", "cdn_ocnE", "cdn_ocnN", "aiE", "aiN", "uocnE", "vocnE", "uocnN", "vocnN", "waterxE", "wateryN",
+              "forcexE", "forceyN", "emassdti", "nmassdti", "fmE", "fmN", "TbE", "TbN", "rheofactE", "rheofactN")
+CFIELDS_ORDER = CFIELDS_INOUT + CFIELDS_OUT + CFIELDS_IN
+CFIELDS_MASK = ("iceTmask", "iceUmask", "iceEmask", "iceNmask")
+
+
+class CFields(C.Structure):
+    _fields_ = [(n, _pd) for n in CFIELDS_ORDER] + [(n, _pi) for n in CFIELDS_MASK]
 
 
 def _ptr(a, ctype):
@@ -80,6 +103,30 @@ def make_grid(g):
         keep[n] = as_f64(g[n])
         assert keep[n].size == s.nx_block * s.ny_block * s.max_blocks, n
         setattr(s, n, _ptr(keep[n], C.c_double))
+    return s, keep
+
+
+def make_cgrid(cg, npl_total):
+    s, keep = CGrid(), {}
+    for n in CGRID_STATIC:
+        keep[n] = as_f64(cg[n])
+        assert keep[n].size == npl_total, n
+        setattr(s, n, _ptr(keep[n], C.c_double))
+    return s, keep
+
+
+def make_cfields(f, npl_total):
+    s, keep = CFields(), {}
+    for n in CFIELDS_ORDER:
+        a = f[n]
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == npl_total, n
+        keep[n] = a
+        setattr(s, n, _ptr(a, C.c_double))
+    for n in CFIELDS_MASK:
+        a = f[n]
+        assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"] and a.size == npl_total, n
+        keep[n] = a
+        setattr(s, n, _ptr(a, C.c_int32))
     return s, keep
 
 

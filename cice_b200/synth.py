@@ -192,7 +192,7 @@ def make_kmt(kind, nx, ny, ew, ns):
 # ------------------------------------------------------------------------------------------
 def evp_params(ndte, revised_evp=False, elasticDamp=0.36, e_yieldcurve=2.0, e_plasticpot=2.0,
                Ktens=0.0, capping=1.0, arlx=300.0, brlx=300.0, mode=abi.MODE_EXACT, kernel=abi.KERNEL_AUTO):
-    p = dict(ndte=int(ndte), mode=mode, kernel=kernel, reserved=0)
+    p = dict(ndte=int(ndte), mode=mode, kernel=kernel)
     p["epp2i"] = 1.0 / e_plasticpot ** 2
     p["e_factor"] = e_yieldcurve ** 2 / e_plasticpot ** 4
     if revised_evp:
@@ -203,7 +203,7 @@ def evp_params(ndte, revised_evp=False, elasticDamp=0.36, e_yieldcurve=2.0, e_pl
         p["arlx1i"] = 1.0 / arlx
         p["brlx"] = float(ndte)
         p["denom1"] = 1.0 / (1.0 + p["arlx1i"])
-    p.update(capping=capping, Ktens=Ktens, u0=5.0e-5, cosw=1.0, sinw=0.0, rhow=RHOW)
+    p.update(capping=capping, Ktens=Ktens, u0=5.0e-5, cosw=1.0, sinw=0.0, rhow=RHOW, visc_method=0, deltaminEVP=1e-11)
     return p
 
 
@@ -342,12 +342,186 @@ def global_state(nx, ny, dx0, ew, ns, kmt="boxislands", dt=3600.0, deltaminEVP=1
     X["aiU"], X["cdn_ocnU"] = ext_u(aiU), ext_u(cdn_ocnU)
     X["uocnU"], X["vocnU"] = ext_u(uocnU), ext_u(vocnU)
     X["uvel"], X["vvel"] = ext_u(uvel_i, True), ext_u(vvel_i, True)
+    X["strax"], X["stray"], X["uocn"], X["vocn"], X["umass_i"] = strax, stray, uocn, vocn, umass
     X["TbU"] = np.zeros((ny + 2, nx + 2))
 
     # Hibler strength at ice T cells, then halo: ice_dyn_evp.F90:540-550, 727-728
     X["strength"] = np.where(iceT, PSTAR * vice * np.exp(-CSTAR * (1.0 - aice)), 0.0)
     X["aice"], X["vice"], X["tmass"] = aice, vice, tmass
     return X
+
+
+def cgrid_state(X, nx, ny, dx0, ew, ns, dt=3600.0, dyn_area_min=1e-11, dyn_mass_min=1e-10, rheo_area_min=1e-11):
+    """Extra geometry and per-step inputs of grid_ice='C' on the ghost-extended global arrays, added to X.
+
+    grid lengths at E/N points   ice_grid.F90:3100-3131 (dxE), :3243-3266 (dyN), dxN = HTN, dyE = HTE
+    areas, masks                 ice_grid.F90:681-715, :3370-3430 (epm, npm, uvmCD)
+    BC ratios                    ice_dyn_evp.F90:226-240
+    T -> E/N averages            ice_dyn_evp.F90:441-456 with grid_average_X2YS 'E','N' (ice_grid.F90:4289-4340)
+    dyn_prep2 at E, N, U         ice_dyn_evp.F90:564-680 (umaskCD for the U mask, rheofact)
+    initial uvelE.. = ocean current at new ice points (ice_dyn_shared.F90:772-775), then the re-interpolations
+    of ice_dyn_evp.F90:700-724."""
+    ig = np.arange(1, nx + 1, dtype=np.float64)[None, :]
+    jg = np.arange(1, ny + 1, dtype=np.float64)[:, None]
+    pi = np.pi
+    HTN = dx0 * (1.0 + 0.1 * np.sin(2 * pi * ig / nx) * np.cos(pi * jg / ny))
+    HTE = dx0 * (1.0 + 0.1 * np.cos(2 * pi * ig / nx) * np.sin(pi * jg / ny))
+    Hn1 = np.roll(HTN, -1, axis=1)  # (ip1, j)
+    dxE = np.empty_like(HTN)
+    dxE[1:, :] = 0.25 * (HTN[1:, :] + Hn1[1:, :] + HTN[:-1, :] + Hn1[:-1, :])
+    dxE[0, :] = 0.5 * (2.0 * HTN[1, :] - HTN[2, :] + 2.0 * Hn1[1, :] - Hn1[2, :])
+    Hem = np.roll(HTE, 1, axis=1)  # (im1, j)
+    dyN = np.empty_like(HTE)
+    dyN[:-1, :] = 0.25 * (HTE[:-1, :] + Hem[:-1, :] + HTE[1:, :] + Hem[1:, :])
+    dyN[-1, :] = 0.5 * (2.0 * HTE[-2, :] - HTE[-3, :] + 2.0 * Hem[-2, :] - Hem[-3, :])
+    X["dxN"], X["dyE"] = X["HTN"], X["HTE"]
+    X["dxE"] = extend(dxE, ew, ns, LOC_E, extrap=True)
+    X["dyN"] = extend(dyN, ew, ns, LOC_N, extrap=True)
+    X["earea"] = X["dxE"] * X["dyE"]
+    X["narea"] = X["dxN"] * X["dyN"]
+    for a, r in (("earea", "earear"), ("narea", "narear")):
+        X[r] = np.where(X[a] > 0.0, 1.0 / np.where(X[a] > 0.0, X[a], 1.0), 0.0)
+    hm = X["hm"]
+    npm = extend(np.minimum(_sl(hm, 0, 0), _sl(hm, 0, 1)), ew, ns, LOC_N)
+    epm = extend(np.minimum(_sl(hm, 0, 0), _sl(hm, 1, 0)), ew, ns, LOC_E)
+    uvmCD = extend(_sl(hm, 0, 0) + _sl(hm, 1, 0) + _sl(hm, 0, 1) + _sl(hm, 1, 1), ew, ns, LOC_NE)
+    X["npm"], X["epm"] = npm, epm
+    for nm in ("ratiodxN", "ratiodxNr", "ratiodyE", "ratiodyEr"):
+        X[nm] = np.zeros((ny + 2, nx + 2))
+    X["ratiodxN"][1:-1, 1:-1] = -_sl(X["dxN"], 1, 0) / _sl(X["dxN"], 0, 0)
+    X["ratiodyE"][1:-1, 1:-1] = -_sl(X["dyE"], 0, 1) / _sl(X["dyE"], 0, 0)
+    X["ratiodxNr"][1:-1, 1:-1] = 1.0 / X["ratiodxN"][1:-1, 1:-1]
+    X["ratiodyEr"][1:-1, 1:-1] = 1.0 / X["ratiodyE"][1:-1, 1:-1]
+
+    mw = hm * X["tarea"]
+
+    def t2x_S(w, di, dj):  # two-point masked average T -> E (di=1) or N (dj=1)
+        wt = _sl(mw, 0, 0) + _sl(mw, di, dj)
+        wm = w * mw
+        num = _sl(wm, 0, 0) + _sl(wm, di, dj)
+        return np.where(wt != 0.0, num / np.where(wt != 0.0, wt, 1.0), 0.0)
+
+    def t2x_F(w, di, dj, area):
+        wa = w * X["tarea"]
+        return 0.5 * (_sl(wa, 0, 0) + _sl(wa, di, dj)) / _sl(area, 0, 0)
+
+    aice, tmass = X["aice"], X["tmass"]
+    pts = {"E": (1, 0, epm, X["earea"], LOC_E), "N": (0, 1, npm, X["narea"], LOC_N)}
+    strax, stray = X["strax"], X["stray"]
+    uocn, vocn = X["uocn"], X["vocn"]
+    cosw, sinw = 1.0, 0.0
+    for P, (di, dj, pm, area, loc) in pts.items():
+        mass = t2x_S(tmass, di, dj)
+        ai = t2x_S(aice, di, dj)
+        cdn = t2x_S(np.full_like(aice, CDN_OCN), di, dj)
+        uo, vo = t2x_S(uocn, di, dj), t2x_S(vocn, di, dj)
+        sx, sy = t2x_F(strax, di, dj, area), t2x_F(stray, di, dj, area)
+        ice = (pm[1:-1, 1:-1] > 0.5) & (ai > dyn_area_min) & (mass > dyn_mass_min)
+        fm = np.where(ice, FCOR_CONST * mass, 0.0)
+        sgn = np.copysign(1.0, fm)
+        I = lambda a: np.where(ice, a, 0.0)
+        ext = lambda a, vector=False: extend(a, ew, ns, loc, vector=vector)
+        X["ice%smask" % P] = ext(ice.astype(np.float64)) > 0.5
+        X["%smassdti" % P.lower()] = ext(I(mass / dt))
+        X["fm" + P] = ext(fm)
+        X["ai" + P], X["cdn_ocn" + P] = ext(ai), ext(cdn)
+        X["uocn" + P], X["vocn" + P] = ext(uo), ext(vo)
+        X["waterx" + P] = ext(I(uo * cosw - vo * sinw * sgn))
+        X["watery" + P] = ext(I(vo * cosw + uo * sinw * sgn))
+        X["forcex" + P] = ext(I(sx + -fm * vo))
+        X["forcey" + P] = ext(I(sy + fm * uo))
+        X["rheofact" + P] = ext(np.where(ice, np.where(ai > rheo_area_min, 1.0, 0.0), 0.0))
+        X["Tb" + P] = np.zeros((ny + 2, nx + 2))
+        X["uvel" + P], X["vvel" + P] = ext(I(uo), True), ext(I(vo), True)
+    # the U mask of the C grid uses umaskCD (ice_dyn_evp.F90:572)
+    aiU, umass = X["aiU"][1:-1, 1:-1], None
+    iceU = (uvmCD[1:-1, 1:-1] > 1.5) & (X["aiU"][1:-1, 1:-1] > dyn_area_min) & (X["umass_i"] > dyn_mass_min)
+    X["iceUmaskC"] = extend(iceU.astype(np.float64), ew, ns, LOC_NE) > 0.5
+    # velocities as ice_dyn_evp.F90:700-724 leaves them: uvelN, vvelE and uvel, vvel re-interpolated from uvelE, vvelN
+    ea, na = X["earea"], X["narea"]
+
+    def avgA(w, wg, offs):
+        wt = sum(_sl(wg, di, dj) for di, dj in offs)
+        num = sum(_sl(w * wg, di, dj) for di, dj in offs)
+        return np.where(wt != 0.0, num / np.where(wt != 0.0, wt, 1.0), 0.0)
+
+    uE, vN = X["uvelE"], X["vvelN"]
+    X["uvelN"] = extend(avgA(uE, ea, [(-1, 0), (0, 0), (-1, 1), (0, 1)]) * npm[1:-1, 1:-1], ew, ns, LOC_N, vector=True)
+    X["vvelE"] = extend(avgA(vN, na, [(0, -1), (1, -1), (0, 0), (1, 0)]) * epm[1:-1, 1:-1], ew, ns, LOC_E, vector=True)
+    X["uvelC"] = extend(avgA(uE, ea, [(0, 0), (0, 1)]) * X["uvm"][1:-1, 1:-1], ew, ns, LOC_NE, vector=True)
+    X["vvelC"] = extend(avgA(vN, na, [(0, 0), (1, 0)]) * X["uvm"][1:-1, 1:-1], ew, ns, LOC_NE, vector=True)
+    return X
+
+
+class CCase:
+    """One synthetic C-grid EVP step in the reference's block layout."""
+
+    def __init__(self, blocks, grid, cgrid, params, fields, X):
+        self.blocks, self.grid, self.cgrid, self.params, self.fields, self.X = blocks, grid, cgrid, params, fields, X
+
+    def copy_fields(self):
+        return {k: v.copy() for k, v in self.fields.items()}
+
+
+def make_ccase(config="gx3", block_size=None, seed=None, ndte=None, mode=abi.MODE_EXACT, revised_evp=False,
+               visc_method=abi.VISC_AVG_ZETA, kmt=None, ew=None, ns=None, nx=None, ny=None, **kw):
+    """grid_ice='C' counterpart of make_case (configs[2]: gx1 C grid, ndte=600)."""
+    c = dict(CONFIGS[config])
+    if nx:
+        c["nx"] = nx
+    if ny:
+        c["ny"] = ny
+    ew_i = abi.BNDY_NAMES[ew or c["ew"]]
+    ns_i = abi.BNDY_NAMES[ns or c["ns"]]
+    if ns_i == abi.BNDY_TRIPOLE:
+        raise ValueError("C-grid cases are not generated for tripole grids")
+    nxg, nyg = c["nx"], c["ny"]
+    bsx, bsy = block_size or (nxg, nyg)
+    blocks = create_blocks(nxg, nyg, bsx, bsy, ew_i, ns_i)
+    X = global_state(nxg, nyg, c["dx0"], ew_i, ns_i, kmt or c["kmt"], **kw)
+    X = cgrid_state(X, nxg, nyg, c["dx0"], ew_i, ns_i)
+    shape = (nyg + 2, nxg + 2)
+    rng = np.random.Generator(np.random.PCG64(seed)) if seed is not None else None
+    iceT = X["iceTmask"]
+    for n in ("stresspT", "stressmT", "stress12T", "stress12U"):
+        if rng is None:
+            X[n] = np.zeros(shape)
+        else:
+            msk = X["iceUmaskC"] if n.endswith("U") else iceT
+            loc = LOC_NE if n.endswith("U") else LOC_CENTER
+            X[n] = np.where(msk, extend(rng.normal(0.0, 1.0, (nyg, nxg)), ew_i, ns_i, loc) * 0.2 * X["strength"].max() * 0.05, 0.0)
+    if rng is not None:
+        for P, loc in (("E", LOC_E), ("N", LOC_N)):
+            ice = X["ice%smask" % P][1:-1, 1:-1]
+            X["uvel" + P] = extend(np.where(ice, rng.uniform(-0.3, 0.3, (nyg, nxg)), 0.0), ew_i, ns_i, loc, vector=True)
+            X["vvel" + P] = extend(np.where(ice, rng.uniform(-0.3, 0.3, (nyg, nxg)), 0.0), ew_i, ns_i, loc, vector=True)
+            X["Tb" + P] = np.where(X["ice%smask" % P], extend(rng.uniform(0.0, 5.0, (nyg, nxg)), ew_i, ns_i, loc), 0.0)
+        iu = X["iceUmaskC"][1:-1, 1:-1]
+        X["uvelC"] = extend(np.where(iu, rng.uniform(-0.3, 0.3, (nyg, nxg)), 0.0), ew_i, ns_i, LOC_NE, vector=True)
+        X["vvelC"] = extend(np.where(iu, rng.uniform(-0.3, 0.3, (nyg, nxg)), 0.0), ew_i, ns_i, LOC_NE, vector=True)
+
+    mb = blocks.nblocks_tot
+    grid = dict(nx_block=blocks.nx_block, ny_block=blocks.ny_block, nblocks=blocks.nblocks_tot, max_blocks=mb,
+                nghost=1, nx_global=nxg, ny_global=nyg, ew_boundary_type=ew_i, ns_boundary_type=ns_i,
+                ilo=blocks.ilo, ihi=blocks.ihi, jlo=blocks.jlo, jhi=blocks.jhi, i_glob=blocks.i_glob, j_glob=blocks.j_glob)
+    for n in abi.GRID_STATIC:
+        grid[n] = scatter(X[n], blocks, mb)
+    cgrid = {n: scatter(X[n], blocks, mb) for n in abi.CGRID_STATIC}
+    src = {"uvel": "uvelC", "vvel": "vvelC", "emassdti": "emassdti", "nmassdti": "nmassdti"}
+    fields = {}
+    for n in abi.CFIELDS_ORDER:
+        if n in abi.CFIELDS_OUT:
+            fields[n] = np.zeros((mb, blocks.ny_block, blocks.nx_block))
+        else:
+            fields[n] = scatter(X[src.get(n, n)], blocks, mb)
+    fields["iceTmask"] = scatter(X["iceTmask"].astype(np.int32), blocks, mb)
+    fields["iceUmask"] = zero_ghosts(scatter(X["iceUmaskC"].astype(np.int32), blocks, mb), blocks)
+    fields["iceEmask"] = zero_ghosts(scatter(X["iceEmask"].astype(np.int32), blocks, mb), blocks)
+    fields["iceNmask"] = zero_ghosts(scatter(X["iceNmask"].astype(np.int32), blocks, mb), blocks)
+    params = evp_params(ndte or c["ndte"], revised_evp=revised_evp, mode=mode)
+    params["visc_method"] = visc_method
+    params["deltaminEVP"] = 1e-11
+    return CCase(blocks, grid, cgrid, params, fields, X)
 
 
 U_PREP = ("umassdti", "fmU", "waterxU", "wateryU", "forcexU", "forceyU", "TbU")  # interior-only after dyn_prep2

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define EVP_B200_ABI_VERSION 1
+#define EVP_B200_ABI_VERSION 2
 
 /* boundary types: domain_nml ew_boundary_type / ns_boundary_type
  * (cicecore/cicedyn/infrastructure/ice_domain.F90:186-240) */
@@ -103,12 +103,52 @@ typedef struct {
   int32_t ndte;               /* number of subcycles                         */
   int32_t mode;               /* EVP_B200_MODE_*                             */
   int32_t kernel;             /* EVP_B200_KERNEL_*                           */
-  int32_t reserved;
+  int32_t visc_method;        /* C grid only: EVP_B200_VISC_* (ice_init.F90:453) */
   double arlx1i, denom1, revp, brlx;
   double e_factor, epp2i, capping, Ktens;
   double u0, cosw, sinw;      /* ice_dyn_shared.F90:66-70                    */
   double rhow;                /* icepack_query_parameters(rhow_out=...)      */
+  double deltaminEVP;         /* C grid, avg_strength only (ice_dyn_evp.F90:1960) */
 } evp_b200_params_t;
+
+/* C grid: how viscosities reach the U point (dynamics_nml visc_method) */
+enum {
+  EVP_B200_VISC_AVG_ZETA     = 0,  /* Bouillon et al. 2013 / C1 of Kimmritz et al. 2016 (default) */
+  EVP_B200_VISC_AVG_STRENGTH = 1   /* C2 of Kimmritz et al. 2016 */
+};
+
+/*
+ * Extra static geometry of grid_ice = 'C' (ice_grid.F90 dx*, dy*, areas, masks;
+ * ice_dyn_evp.F90:218-240 ratio arrays).  Passed once with evp_b200_init_cgrid, after evp_b200_init.
+ * Each (nx_block,ny_block,max_blocks) f64.
+ */
+typedef struct {
+  const double *dxN, *dyE, *dxE, *dyN, *dxU, *dyU;
+  const double *tarea, *uarea, *earea, *narea, *earear, *narear;
+  const double *ratiodxN, *ratiodxNr, *ratiodyE, *ratiodyEr;
+  const double *hm, *uvm, *epm, *npm;   /* 0/1 land masks as the reference holds them (real) */
+} evp_b200_cgrid_t;
+
+/*
+ * Time-varying fields of one C-grid call: what the `grid_ice == "C"` branch of the subcycle loop
+ * reads and writes (ice_dyn_evp.F90:936-1101).  All (nx_block,ny_block,max_blocks).
+ */
+typedef struct {
+  /* inout: prognostic velocities at E and N points, their interpolants, the carried stresses */
+  double *uvelE, *vvelE, *uvelN, *vvelN, *uvel, *vvel;
+  double *stresspT, *stressmT, *stress12T, *stress12U;
+  /* out: work arrays the reference leaves behind after the last subcycle */
+  double *zetax2T, *etax2T, *etax2U, *strengthU;
+  double *divergU, *tensionU, *shearU, *deltaU;
+  double *strintxE, *strintyN, *taubxE, *taubyN;
+  /* in */
+  const double *strength;
+  const double *cdn_ocnE, *cdn_ocnN, *aiE, *aiN, *uocnE, *vocnE, *uocnN, *vocnN;
+  const double *waterxE, *wateryN, *forcexE, *forceyN, *emassdti, *nmassdti, *fmE, *fmN;
+  const double *TbE, *TbN, *rheofactE, *rheofactN;
+  /* in: 0/1 */
+  const int32_t *iceTmask, *iceUmask, *iceEmask, *iceNmask;
+} evp_b200_cfields_t;
 
 /*
  * Time-varying fields of one call, the argument list of dyn_evp1d_run
@@ -156,6 +196,12 @@ const char *evp_b200_last_error(void);
  * blocks, including the per-subcycle (uvel,vvel) halo update.  Host buffers in, host
  * buffers out: H2D of the fields, the device loop, D2H of the inout fields. */
 int evp_b200_run_bgrid(const evp_b200_params_t *params, evp_b200_fields_t *fields);
+
+/* C grid (configs[2]): one call = the whole `do ksub=1,ndte` loop of ice_dyn_evp.F90:938-1097
+ * (strain_rates_U, stressC_T, stressC_U, div_stress_Ex/Ny, stepu_C/stepv_C, the four velocity
+ * re-interpolations and the seven halo points), one GPU.  evp_b200_init_cgrid must have been called. */
+int evp_b200_init_cgrid(const evp_b200_cgrid_t *cgrid);
+int evp_b200_run_cgrid(const evp_b200_params_t *params, evp_b200_cfields_t *fields);
 
 /* The same call split in three so that a caller which keeps dynamics state on the device
  *  -- and bench.py's device-resident timing -- can run the loop alone.

@@ -38,6 +38,10 @@ int orc_evp_run_bgrid_1d(const evp_b200_grid_t *grid, const double *HTE, const d
                          double deltaminEVP, const evp_b200_params_t *params,
                          evp_b200_fields_t *fields, int nthreads);
 
+/* C grid (grid_ice='C'): ice_dyn_evp.F90:936-1101 and callees, see evp_oracle_cgrid.c.  Non-tripole only. */
+int orc_evp_run_cgrid(const evp_b200_grid_t *grid, const evp_b200_cgrid_t *cgrid, const evp_b200_params_t *params,
+                      evp_b200_cfields_t *fields, int nthreads);
+
 /* NE-corner / vector halo update of nfld fields, the dyn_haloUpdate call of
  * ice_dyn_evp.F90:908-910 (ice_boundary.F90:1066-1760; expectations halochk.F90:530-830).
  * field_loc: 0 center, 1 NE corner; field_type: 0 scalar, 1 vector. */

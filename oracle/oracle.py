@@ -21,7 +21,8 @@ def build(force=False):
     """compile the oracle with the committed Makefile (gcc only; no reference build system)."""
     need = force or not all(os.path.exists(os.path.join(_BUILD, f"liboracle_{v}.so")) for v in ("exact", "fast"))
     if not need:
-        src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("evp_oracle.c", "evp_oracle.h"))
+        src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("evp_oracle.c", "evp_oracle_cgrid.c", "evp_oracle.h"))
+        src_m = max(src_m, os.path.getmtime(os.path.join(os.path.dirname(_HERE), "include", "evp_b200.h")))
         need = any(os.path.getmtime(os.path.join(_BUILD, f"liboracle_{v}.so")) < src_m for v in ("exact", "fast"))
     if need:
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
@@ -50,6 +51,8 @@ def lib(variant="exact"):
         L.orc_evp_run_bgrid_1d.argtypes = [C.POINTER(abi.Grid), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                            C.c_double, C.POINTER(abi.Params), C.POINTER(abi.Fields), C.c_int]
         L.orc_evp_run_bgrid_1d.restype = C.c_int
+        L.orc_evp_run_cgrid.argtypes = [C.POINTER(abi.Grid), C.POINTER(abi.CGrid), C.POINTER(abi.Params), C.POINTER(abi.CFields), C.c_int]
+        L.orc_evp_run_cgrid.restype = C.c_int
         L.orc_halo_update.argtypes = [C.POINTER(abi.Grid), C.POINTER(C.POINTER(C.c_double)), C.c_int, C.c_int, C.c_int]
         L.orc_halo_update.restype = C.c_int
         L.orc_last_error.restype = C.c_char_p
@@ -91,6 +94,19 @@ def evp_run_bgrid_1d(grid, HTE, HTN, deltaminEVP, params, fields, nthreads=0, va
     if rc:
         raise RuntimeError("oracle1d: " + L.orc_last_error().decode())
     return fields
+
+
+def evp_run_cgrid(grid, cgrid, params, cfields, nthreads=0, variant="exact"):
+    """run the C-grid oracle IN PLACE on the arrays of `cfields`."""
+    L = lib(variant)
+    g, kg = abi.make_grid(grid)
+    cg, kcg = abi.make_cgrid(cgrid, _npl(grid))
+    p = abi.make_params(params)
+    f, kf = abi.make_cfields(cfields, _npl(grid))
+    rc = L.orc_evp_run_cgrid(C.byref(g), C.byref(cg), C.byref(p), C.byref(f), int(nthreads))
+    if rc:
+        raise RuntimeError("oracle cgrid failed")
+    return cfields
 
 
 def halo_update(grid, arrays, field_loc=1, field_type=1, variant="exact"):
