@@ -113,6 +113,13 @@ struct Ctx {
 
   HaloPlan halo;
 
+  // C grid
+  bool cinit = false;
+  CDom cdom{};
+  std::vector<double *> cbuf;      // every C-grid device array (freed together)
+  std::vector<double *> cstage;    // staging, one per C field
+  unsigned char *cmask[4] = {};
+
   // KERNEL_PERSISTENT
   PersistPlan pplan{};
   bool persist_ok = false;
@@ -136,11 +143,15 @@ static void destroy_graph() {
 
 static int free_all() {
   destroy_graph();
+  g.cinit = false;
   auto F = [](auto *&p) {
     if (p) cudaFree(p);
     p = nullptr;
   };
   g.p2p.release();
+  for (auto &p : g.cbuf) F(p);
+  for (auto &p : g.cstage) F(p);
+  for (auto &p : g.cmask) F(p);
   g.dfield[F_U] = g.dfield[F_V] = g.du1 = g.dv1 = nullptr;  // live inside dshare
   F(g.dshare);
   for (auto &p : g.dfield) F(p);
@@ -426,6 +437,7 @@ static KParams kparams(const evp_b200_params_t *p) {
   k.arlx1i = p->arlx1i; k.denom1 = p->denom1; k.revp = p->revp; k.brlx = p->brlx;
   k.e_factor = p->e_factor; k.epp2i = p->epp2i; k.capping = p->capping; k.Ktens = p->Ktens;
   k.u0 = p->u0; k.cosw = p->cosw; k.sinw = p->sinw; k.rhow = p->rhow;
+  k.deltaminEVP = p->deltaminEVP; k.visc_method = p->visc_method;
   return k;
 }
 
@@ -576,6 +588,156 @@ static int do_subcycle(const evp_b200_params_t *p) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// C grid
+// ------------------------------------------------------------------------------------------------
+static int calloc_dom(double *&p) {
+  CK(cudaMalloc(&p, g.ndom * sizeof(double)));
+  CK(cudaMemsetAsync(p, 0, g.ndom * sizeof(double), g.stream));
+  g.cbuf.push_back(p);
+  return 0;
+}
+
+static int do_init_cgrid(const evp_b200_cgrid_t *cg) {
+  if (!g.inited) return fail("evp_b200_init_cgrid: call evp_b200_init first");
+  if (!cg) return fail("evp_b200_init_cgrid: null grid");
+  if (g_comm.nranks > 1) return fail("evp_b200_init_cgrid: the C-grid path runs on one GPU in this version");
+  if (g.ns == EVP_B200_BNDY_TRIPOLE) return fail("evp_b200_init_cgrid: tripole grids are not supported on the C-grid path");
+  if (g.halo.n_dst != 0) return fail("evp_b200_init_cgrid: the halo of this decomposition is not an on-rank wrap");
+  if (g.cinit) return fail("evp_b200_init_cgrid: already initialised");
+  CK(cudaSetDevice(g.device));
+  CDom &c = g.cdom;
+  c.nx = g.dom.nx; c.ny = g.dom.ny; c.ld = g.dom.ld; c.nyd = g.dom.nyd; c.wrap_ew = g.dom.wrap_ew; c.wrap_ns = g.dom.wrap_ns;
+  const size_t bblk = g.nblk_elems * sizeof(double);
+  // static geometry: 20 arrays from the caller, 3 shared with the B-grid set
+  const double *src[20] = {cg->dxN, cg->dyE, cg->dxE, cg->dyN, cg->dxU, cg->dyU, cg->tarea, cg->uarea, cg->earea, cg->narea,
+                           cg->earear, cg->narear, cg->ratiodxN, cg->ratiodxNr, cg->ratiodyE, cg->ratiodyEr, cg->hm, cg->uvm, cg->epm, cg->npm};
+  const double **dst[20] = {&c.dxN, &c.dyE, &c.dxE, &c.dyN, &c.dxU, &c.dyU, &c.tarea, &c.uarea, &c.earea, &c.narea,
+                            &c.earear, &c.narear, &c.ratiodxN, &c.ratiodxNr, &c.ratiodyE, &c.ratiodyEr, &c.hm, &c.uvm, &c.epm, &c.npm};
+  for (int q = 0; q < 20; ++q) {
+    if (!src[q]) return fail("evp_b200_init_cgrid: null geometry array %d", q);
+    double *p = nullptr;
+    if (calloc_dom(p)) return 1;
+    CK(cudaMemcpyAsync(g.stage[q % NF_STEP], src[q], bblk, cudaMemcpyHostToDevice, g.stream));
+    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(p, g.stage[q % NF_STEP], g.d_gsrc, (int)g.ndom);
+    *dst[q] = p;
+  }
+  c.dxT = g.dom.dxT; c.dyT = g.dom.dyT; c.DminTarea = g.dom.DminTarea;
+  // 43 time-varying fields, each with a staging buffer in block layout
+  double **flds[43] = {&c.uvelE, &c.vvelE, &c.uvelN, &c.vvelN, &c.uvel, &c.vvel, &c.stresspT, &c.stressmT, &c.stress12T, &c.stress12U,
+                       &c.zetax2T, &c.etax2T, &c.etax2U, &c.strengthU, &c.divergU, &c.tensionU, &c.shearU, &c.deltaU,
+                       &c.strintxE, &c.strintyN, &c.taubxE, &c.taubyN,
+                       (double **)&c.strength, (double **)&c.cdnE, (double **)&c.cdnN, (double **)&c.aiE, (double **)&c.aiN,
+                       (double **)&c.uocnE, (double **)&c.vocnE, (double **)&c.uocnN, (double **)&c.vocnN, (double **)&c.waterxE,
+                       (double **)&c.wateryN, (double **)&c.forcexE, (double **)&c.forceyN, (double **)&c.emassdti, (double **)&c.nmassdti,
+                       (double **)&c.fmE, (double **)&c.fmN, (double **)&c.TbE, (double **)&c.TbN, (double **)&c.rheofactE, (double **)&c.rheofactN};
+  for (int q = 0; q < 43; ++q) {
+    if (calloc_dom(*flds[q])) return 1;
+    double *st = nullptr;
+    CK(cudaMalloc(&st, bblk));
+    g.cstage.push_back(st);
+  }
+  if (calloc_dom(c.uvelE_init) || calloc_dom(c.vvelN_init)) return 1;
+  for (int q = 0; q < 4; ++q) { CK(cudaMalloc(&g.cmask[q], g.ndom)); CK(cudaMemsetAsync(g.cmask[q], 0, g.ndom, g.stream)); }
+  c.maskT = g.cmask[0]; c.maskU = g.cmask[1]; c.maskE = g.cmask[2]; c.maskN = g.cmask[3];
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(g.stream));
+  g.cinit = true;
+  return 0;
+}
+
+static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
+  if (!g.cinit) return fail("evp_b200_run_cgrid: evp_b200_init_cgrid has not been called");
+  if (!p || !f) return fail("evp_b200_run_cgrid: null argument");
+  if (p->ndte < 0) return fail("evp_b200_run_cgrid: ndte < 0");
+  if (p->visc_method != EVP_B200_VISC_AVG_ZETA && p->visc_method != EVP_B200_VISC_AVG_STRENGTH) return fail("evp_b200_run_cgrid: unknown visc_method %d", p->visc_method);
+  CK(cudaSetDevice(g.device));
+  CDom &c = g.cdom;
+  const size_t bblk = g.nblk_elems * sizeof(double), bdom = g.ndom * sizeof(double);
+  // host pointer, device array, how it moves: 'i' in, 'r' inout ring, 's' inout T cells the loop owns (N/E ghost incl.),
+  // 'n' inout interior, 'z' out: the reference zero-fills the whole block then halo-updates / leaves it
+  struct Fld { const double *h; double *dv; char kind; };
+  const bool avgstr = (p->visc_method == EVP_B200_VISC_AVG_STRENGTH);
+  Fld tab[43] = {
+      {f->uvelE, c.uvelE, 'r'}, {f->vvelE, c.vvelE, 'r'}, {f->uvelN, c.uvelN, 'r'}, {f->vvelN, c.vvelN, 'r'}, {f->uvel, c.uvel, 'r'}, {f->vvel, c.vvel, 'r'},
+      {f->stresspT, c.stresspT, 'r'}, {f->stressmT, c.stressmT, 'r'}, {f->stress12T, c.stress12T, 's'}, {f->stress12U, c.stress12U, 'r'},
+      {f->zetax2T, c.zetax2T, 'r'}, {f->etax2T, c.etax2T, 'r'}, {f->etax2U, c.etax2U, avgstr ? '-' : 'z'}, {f->strengthU, c.strengthU, avgstr ? 'z' : '-'},
+      {f->divergU, c.divergU, 'z'}, {f->tensionU, c.tensionU, 'z'}, {f->shearU, c.shearU, 'z'}, {f->deltaU, c.deltaU, 'z'},
+      {f->strintxE, c.strintxE, 'n'}, {f->strintyN, c.strintyN, 'n'}, {f->taubxE, c.taubxE, 'n'}, {f->taubyN, c.taubyN, 'n'},
+      {f->strength, (double *)c.strength, 'i'}, {f->cdn_ocnE, (double *)c.cdnE, 'i'}, {f->cdn_ocnN, (double *)c.cdnN, 'i'}, {f->aiE, (double *)c.aiE, 'i'},
+      {f->aiN, (double *)c.aiN, 'i'}, {f->uocnE, (double *)c.uocnE, 'i'}, {f->vocnE, (double *)c.vocnE, 'i'}, {f->uocnN, (double *)c.uocnN, 'i'},
+      {f->vocnN, (double *)c.vocnN, 'i'}, {f->waterxE, (double *)c.waterxE, 'i'}, {f->wateryN, (double *)c.wateryN, 'i'}, {f->forcexE, (double *)c.forcexE, 'i'},
+      {f->forceyN, (double *)c.forceyN, 'i'}, {f->emassdti, (double *)c.emassdti, 'i'}, {f->nmassdti, (double *)c.nmassdti, 'i'}, {f->fmE, (double *)c.fmE, 'i'},
+      {f->fmN, (double *)c.fmN, 'i'}, {f->TbE, (double *)c.TbE, 'i'}, {f->TbN, (double *)c.TbN, 'i'}, {f->rheofactE, (double *)c.rheofactE, 'i'},
+      {f->rheofactN, (double *)c.rheofactN, 'i'}};
+  for (int q = 0; q < 43; ++q) {
+    const Fld &t = tab[q];
+    if (t.kind == '-') continue;
+    if (!t.h) return fail("evp_b200_run_cgrid: null field %d", q);
+    if (t.kind == 'z') {
+      CK(cudaMemsetAsync(t.dv, 0, bdom, g.stream));
+      CK(cudaMemsetAsync(g.cstage[q], 0, bblk, g.stream));
+      continue;
+    }
+    CK(cudaMemcpyAsync(g.cstage[q], t.h, bblk, cudaMemcpyHostToDevice, g.stream));
+    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(t.dv, g.cstage[q], g.d_gsrc, (int)g.ndom);
+  }
+  const int32_t *hm[4] = {f->iceTmask, f->iceUmask, f->iceEmask, f->iceNmask};
+  for (int q = 0; q < 4; ++q) {
+    if (!hm[q]) return fail("evp_b200_run_cgrid: null mask %d", q);
+    CK(cudaMemcpyAsync(g.stage_mask, hm[q], g.nblk_elems * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+    pack_mask<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(g.cmask[q], g.stage_mask, g.d_gsrc, (int)g.ndom);
+  }
+  // uvelE_init / vvelN_init = values at entry (dyn_prep2, shared.F90:787-788)
+  CK(cudaMemcpyAsync(c.uvelE_init, c.uvelE, bdom, cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaMemcpyAsync(c.vvelN_init, c.vvelN, bdom, cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaGetLastError());
+
+  // the loop: 5 kernels per subcycle, captured once per parameter set
+  const KParams k = kparams(p);
+  const bool exact = (p->mode == EVP_B200_MODE_EXACT);
+  static cudaGraphExec_t cexec = nullptr;
+  static evp_b200_params_t cparams{};
+  static const void *cowner = nullptr;
+  int nl = 0;
+  if (!cexec || cowner != (const void *)c.uvelE || memcmp(&cparams, p, sizeof *p) != 0) {
+    if (cexec) { cudaGraphExecDestroy(cexec); cexec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t le = cudaSuccess;
+    for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub)
+      le = exact ? exact::launch_cgrid_subcycle(c, k, g.stream, &nl) : fast::launch_cgrid_subcycle(c, k, g.stream, &nl);
+    cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
+    if (le != cudaSuccess || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail("evp_b200_run_cgrid: capture failed: %s", cudaGetErrorString(le != cudaSuccess ? le : ce)); }
+    CK(cudaGraphInstantiate(&cexec, graph, 0));
+    CK(cudaGraphDestroy(graph));
+    cparams = *p; cowner = (const void *)c.uvelE;
+  } else {
+    nl = 5 * p->ndte;
+  }
+  CK(cudaEventRecord(g.ev0, g.stream));
+  if (p->ndte > 0) CK(cudaGraphLaunch(cexec, g.stream));
+  CK(cudaEventRecord(g.ev1, g.stream));
+  g.last_launches = nl;
+
+  // back to the caller's block arrays
+  for (int q = 0; q < 22; ++q) {
+    const Fld &t = tab[q];
+    if (t.kind == '-') continue;
+    if (t.kind == 's')
+      unpack_f64<<<grid_blocks(g.n_sig), 256, 0, g.stream>>>(g.cstage[q], t.dv, g.d_sig_lin, g.d_sig_dom, g.n_sig);
+    else if (t.kind == 'n')
+      unpack_f64<<<grid_blocks(g.n_int), 256, 0, g.stream>>>(g.cstage[q], t.dv, g.d_int_lin, g.d_int_dom, g.n_int);
+    else
+      unpack_f64<<<grid_blocks(g.n_uv), 256, 0, g.stream>>>(g.cstage[q], t.dv, g.d_uv_lin, g.d_uv_dom, g.n_uv);
+    CK(cudaMemcpyAsync((void *)t.h, g.cstage[q], bblk, cudaMemcpyDeviceToHost, g.stream));
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1));
+  return 0;
+}
+
 }  // namespace evp
 
 // ------------------------------------------------------------------------------------------------
@@ -618,6 +780,9 @@ int evp_b200_finalize(void) {
   comm_destroy(g_comm);
   return 0;
 }
+
+int evp_b200_init_cgrid(const evp_b200_cgrid_t *cg) { return do_init_cgrid(cg); }
+int evp_b200_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) { return do_run_cgrid(p, f); }
 
 int evp_b200_upload(const evp_b200_fields_t *f) { return do_upload(f); }
 int evp_b200_subcycle(const evp_b200_params_t *p) { return do_subcycle(p); }

@@ -1,0 +1,234 @@
+// evp_cgrid.cu -- C-grid EVP subcycle (grid_ice = 'C', configs[2]) for sm_100a.
+//
+// One subcycle of ice_dyn_evp.F90:938-1097 is five kernels, cut exactly where a value is needed at a
+// neighbour cell (= where the reference has a halo point):
+//   k1  strain_rates_U                                  shared.F90:2319-2430      -> shearU halo
+//   k2  strain_rates_Tdt + stressC_T                    shared.F90:2250-2311, evp.F90:1758-1883
+//                                                                                 -> zetax2T, etax2T, stresspT, stressmT halo
+//   k3  grid_average_X2YS 'NE' (T->U) + stressC_U       grid.F90:4159-4211, evp.F90:1898-1970   -> stress12U halo
+//   k4  div_stress_Ex/Ny + stepu_C / stepv_C            evp.F90:2195-2248, 2364-2416, shared.F90:1090-1283
+//                                                                                 -> uvelE, vvelN halo
+//   k5  grid_average_X2YA E->N, N->E, E->U, N->U, masks grid.F90:4388-4606, evp.F90:1073-1090
+//                                                                                 -> uvelN, vvelE, uvel, vvel halo
+// The halo points themselves are the on-rank cyclic wrap: the producing thread also stores the ghost
+// copies (ring_store).  One GPU, non-tripole.  Compiled twice (exact: -fmad=false, fast) like the B-grid
+// kernels; every expression keeps the reference's operator order.
+#include "evp_internal.h"
+
+#ifndef EVP_NS
+#error "compile with -DEVP_NS=exact or -DEVP_NS=fast"
+#endif
+
+namespace evp {
+namespace EVP_NS {
+
+#define AT(i, j) ((size_t)(j)*d.ld + (size_t)(i))
+
+// store val at (i,j) and at the ghost cells that alias it under an on-rank cyclic wrap.
+// sides: 3 = both ghost sides (a halo update), 1 = only the E/N ghost (cells the reference computes redundantly).
+// zero_closed: additionally zero the ghost neighbours outside a non-cyclic edge (arrays the reference zero-fills
+// over the whole block every subcycle and whose outer ghosts no halo update touches).
+__device__ __forceinline__ void ring_store(const CDom &d, double *__restrict__ A, int i, int j, double val, int sides,
+                                           bool zero_closed) {
+  A[AT(i, j)] = val;
+  int ig = -1, jg = -1;
+  if (d.wrap_ew) ig = (i == 1) ? d.nx + 1 : ((i == d.nx && (sides & 2)) ? 0 : -1);
+  if (d.wrap_ns) jg = (j == 1) ? d.ny + 1 : ((j == d.ny && (sides & 2)) ? 0 : -1);
+  if (ig >= 0) A[AT(ig, j)] = val;
+  if (jg >= 0) A[AT(i, jg)] = val;
+  if (ig >= 0 && jg >= 0) A[AT(ig, jg)] = val;
+  if (zero_closed) {
+    const int zi = d.wrap_ew ? -1 : (i == 1 ? 0 : (i == d.nx ? d.nx + 1 : -1));
+    const int zj = d.wrap_ns ? -1 : (j == 1 ? 0 : (j == d.ny ? d.ny + 1 : -1));
+    if (zi >= 0) A[AT(zi, j)] = 0.0;
+    if (zj >= 0) A[AT(i, zj)] = 0.0;
+    if (zi >= 0 && zj >= 0) A[AT(zi, zj)] = 0.0;
+    if (zi >= 0 && jg >= 0) A[AT(zi, jg)] = 0.0;
+    if (ig >= 0 && zj >= 0) A[AT(ig, zj)] = 0.0;
+  }
+}
+
+__device__ __forceinline__ void visc_c(double strength, double dmin, double Delta, const KParams &k, double &zetax2,
+                                       double &etax2, double &rep_prs) {
+  const double tmp = k.capping * (strength / fmax(Delta, dmin)) + (1.0 - k.capping) * (strength / (Delta + dmin));
+  zetax2 = (1.0 + k.Ktens) * tmp;
+  rep_prs = (1.0 - k.Ktens) * tmp * Delta;
+  etax2 = k.epp2i * zetax2;
+}
+
+#define CELL_IJ(NXE, NYE)                                          \
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;         \
+  const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;         \
+  if (i > (NXE) || j > (NYE)) return;                              \
+  const size_t c = AT(i, j)
+
+// ---- k1 ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k1_strain_U(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  CELL_IJ(d.nx, d.ny);
+  double div = 0.0, ten = 0.0, shr = 0.0, del = 0.0;
+  if (d.maskU[c]) {
+    const size_t e = c + 1, n = c + d.ld;
+    const double npc = d.npm[c], npe = d.npm[e], epc = d.epm[c], epn = d.epm[n];
+    const double uNip1j = d.uvelN[e] * npe + (npc - npe) * npc * d.ratiodxN[c] * d.uvelN[c];
+    const double uNij = d.uvelN[c] * npc + (npe - npc) * npe * d.ratiodxNr[c] * d.uvelN[e];
+    const double vEijp1 = d.vvelE[n] * epn + (epc - epn) * epc * d.ratiodyE[c] * d.vvelE[c];
+    const double vEij = d.vvelE[c] * epc + (epn - epc) * epn * d.ratiodyEr[c] * d.vvelE[n];
+    const double dyU = d.dyU[c], dxU = d.dxU[c], uU = d.uvel[c], vU = d.vvel[c];
+    const double ddyN = d.dyN[e] - d.dyN[c], ddxE = d.dxE[n] - d.dxE[c];
+    div = dyU * (uNip1j - uNij) + uU * ddyN + dxU * (vEijp1 - vEij) + vU * ddxE;
+    ten = dyU * (uNip1j - uNij) - uU * ddyN - dxU * (vEijp1 - vEij) + vU * ddxE;
+    const double uEijp1 = d.uvelE[n] * epn + (epc - epn) * epc * d.ratiodyE[c] * d.uvelE[c];
+    const double uEij = d.uvelE[c] * epc + (epn - epc) * epn * d.ratiodyEr[c] * d.uvelE[n];
+    const double vNip1j = d.vvelN[e] * npe + (npc - npe) * npc * d.ratiodxN[c] * d.vvelN[c];
+    const double vNij = d.vvelN[c] * npc + (npe - npc) * npe * d.ratiodxNr[c] * d.vvelN[e];
+    shr = dxU * (uEijp1 - uEij) - uU * ddxE + dyU * (vNip1j - vNij) - vU * ddyN;
+    del = sqrt(div * div + k.e_factor * (ten * ten + shr * shr));
+  }
+  d.divergU[c] = div;
+  d.tensionU[c] = ten;
+  d.deltaU[c] = del;
+  ring_store(d, d.shearU, i, j, shr, 3, false);
+}
+
+// ---- k2 ------------------------------------------------------------------------------------------------
+// T cells 1..nx+1 x 1..ny+1 (N/E ghost cells are in the reference's list, shared.F90:740-749); a ghost row or
+// column that merely aliases the interior under the on-rank wrap is filled by ring_store instead.
+__global__ void __launch_bounds__(256) k2_stress_T(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  CELL_IJ(d.wrap_ew ? d.nx : d.nx + 1, d.wrap_ns ? d.ny : d.ny + 1);
+  if (!d.maskT[c]) return;
+  const size_t w = c - 1, s = c - d.ld, sw = s - 1;
+  const double dyEc = d.dyE[c], dyEw = d.dyE[w], dxNc = d.dxN[c], dxNs = d.dxN[s];
+  const double uEc = d.uvelE[c], uEw = d.uvelE[w], vNc = d.vvelN[c], vNs = d.vvelN[s];
+  const double dxT = d.dxT[c], dyT = d.dyT[c];
+  const double divT = dyEc * uEc - dyEw * uEw + dxNc * vNc - dxNs * vNs;
+  const double tensionT = (dyT * dyT) * (uEc / dyEc - uEw / dyEw) - (dxT * dxT) * (vNc / dxNc - vNs / dxNs);
+  const double uac = d.uarea[c], uas = d.uarea[s], uasw = d.uarea[sw], uaw = d.uarea[w];
+  const double shc = d.shearU[c], shs = d.shearU[s], shsw = d.shearU[sw], shw = d.shearU[w];
+  const double uareaavgr = 1.0 / (uac + uas + uasw + uaw);
+  const double shearTsqr = (shc * shc * uac + shs * shs * uas + shsw * shsw * uasw + shw * shw * uaw) * uareaavgr;
+  const double shearT = (shc * uac + shs * uas + shsw * uasw + shw * uaw) * uareaavgr;
+  const double DeltaT = sqrt(divT * divT + k.e_factor * (tensionT * tensionT + shearTsqr));
+  double zetax2, etax2, rep;
+  visc_c(d.strength[c], d.DminTarea[c], DeltaT, k, zetax2, etax2, rep);
+  const double relax = 1.0 - k.arlx1i * k.revp;
+  const double sp = (d.stresspT[c] * relax + k.arlx1i * (zetax2 * divT - rep)) * k.denom1;
+  const double sm = (d.stressmT[c] * relax + k.arlx1i * etax2 * tensionT) * k.denom1;
+  const double s12 = (d.stress12T[c] * relax + k.arlx1i * 0.5 * etax2 * shearT) * k.denom1;
+  ring_store(d, d.zetax2T, i, j, zetax2, 3, false);
+  ring_store(d, d.etax2T, i, j, etax2, 3, false);
+  ring_store(d, d.stresspT, i, j, sp, 3, false);
+  ring_store(d, d.stressmT, i, j, sm, 3, false);
+  ring_store(d, d.stress12T, i, j, s12, 1, false);  // not halo-updated: only the redundantly computed N/E ghost copy
+}
+
+// ---- k3 ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k3_stress_U(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  CELL_IJ(d.nx, d.ny);
+  const size_t e = c + 1, n = c + d.ld, ne = n + 1;
+  const double *__restrict__ src = (k.visc_method == 1) ? d.strength : d.etax2T;
+  const double mc = d.hm[c], me = d.hm[e], mn = d.hm[n], mne = d.hm[ne];
+  const double wc = d.tarea[c], we = d.tarea[e], wn = d.tarea[n], wne = d.tarea[ne];
+  const double wtmp = (mc * wc + me * we + mn * wn + mne * wne);
+  double avg = 0.0;
+  if (wtmp != 0.0) avg = (mc * src[c] * wc + me * src[e] * we + mn * src[n] * wn + mne * src[ne] * wne) / wtmp;
+  if (k.visc_method == 1) d.strengthU[c] = avg; else d.etax2U[c] = avg;
+  if (d.maskU[c]) {
+    const double relax = 1.0 - k.arlx1i * k.revp;
+    double etax2U = avg;
+    if (k.visc_method == 1) {
+      const double DminUarea = k.deltaminEVP * d.uarea[c];
+      double z, r;
+      visc_c(avg, DminUarea, d.deltaU[c], k, z, etax2U, r);
+    }
+    const double s12 = (d.stress12U[c] * relax + k.arlx1i * 0.5 * etax2U * d.shearU[c]) * k.denom1;
+    ring_store(d, d.stress12U, i, j, s12, 3, false);
+  }
+}
+
+// ---- k4 ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k4_momentum(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  CELL_IJ(d.nx, d.ny);
+  if (d.maskE[c]) {
+    const size_t e = c + 1, s = c - d.ld;
+    const double dyE = d.dyE[c], dyTe = d.dyT[e], dyTc = d.dyT[c], dxUc = d.dxU[c], dxUs = d.dxU[s];
+    const double strintx = d.rheofactE[c] * d.earear[c] *
+                           (0.5 * dyE * (d.stresspT[e] - d.stresspT[c]) +
+                            (0.5 / dyE) * ((dyTe * dyTe) * d.stressmT[e] - (dyTc * dyTc) * d.stressmT[c]) +
+                            (1.0 / d.dxE[c]) * ((dxUc * dxUc) * d.stress12U[c] - (dxUs * dxUs) * d.stress12U[s]));
+    d.strintxE[c] = strintx;
+    const double uold = d.uvelE[c], vold = d.vvelE[c];
+    const double du = d.uocnE[c] - uold, dv = d.vocnE[c] - vold;
+    const double vrel = d.aiE[c] * k.rhow * d.cdnE[c] * sqrt(du * du + dv * dv);
+    const double taux = vrel * d.waterxE[c];
+    const double ccc = sqrt(uold * uold + vold * vold) + k.u0;
+    const double Cb = d.TbE[c] / ccc;
+    const double m = d.emassdti[c], fm = d.fmE[c];
+    const double cca = (k.brlx + k.revp) * m + vrel * k.cosw + Cb;
+    const double ccb = fm + copysign(1.0, fm) * vrel * k.sinw;
+    const double cc1 = strintx + d.forcexE[c] + taux + m * (k.brlx * uold + k.revp * d.uvelE_init[c]);
+    const double un = (ccb * vold + cc1) / cca;
+    ring_store(d, d.uvelE, i, j, un, 3, false);
+    d.taubxE[c] = -un * Cb;
+  }
+  if (d.maskN[c]) {
+    const size_t n = c + d.ld, w = c - 1;
+    const double dxN = d.dxN[c], dxTn = d.dxT[n], dxTc = d.dxT[c], dyUc = d.dyU[c], dyUw = d.dyU[w];
+    const double strinty = d.rheofactN[c] * d.narear[c] *
+                           (0.5 * dxN * (d.stresspT[n] - d.stresspT[c]) -
+                            (0.5 / dxN) * ((dxTn * dxTn) * d.stressmT[n] - (dxTc * dxTc) * d.stressmT[c]) +
+                            (1.0 / d.dyN[c]) * ((dyUc * dyUc) * d.stress12U[c] - (dyUw * dyUw) * d.stress12U[w]));
+    d.strintyN[c] = strinty;
+    const double uold = d.uvelN[c], vold = d.vvelN[c];
+    const double du = d.uocnN[c] - uold, dv = d.vocnN[c] - vold;
+    const double vrel = d.aiN[c] * k.rhow * d.cdnN[c] * sqrt(du * du + dv * dv);
+    const double tauy = vrel * d.wateryN[c];
+    const double ccc = sqrt(uold * uold + vold * vold) + k.u0;
+    const double Cb = d.TbN[c] / ccc;
+    const double m = d.nmassdti[c], fm = d.fmN[c];
+    const double cca = (k.brlx + k.revp) * m + vrel * k.cosw + Cb;
+    const double ccb = fm + copysign(1.0, fm) * vrel * k.sinw;
+    const double cc2 = strinty + d.forceyN[c] + tauy + m * (k.brlx * vold + k.revp * d.vvelN_init[c]);
+    const double vn = (-ccb * uold + cc2) / cca;
+    ring_store(d, d.vvelN, i, j, vn, 3, false);
+    d.taubyN[c] = -vn * Cb;
+  }
+}
+
+// ---- k5 ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double avg4(const double *__restrict__ w1, const double *__restrict__ wg, size_t a, size_t b,
+                                       size_t c, size_t e) {
+  const double wa = wg[a], wb = wg[b], wc = wg[c], we = wg[e];
+  const double wtmp = (wa + wb + wc + we);
+  return (wtmp != 0.0) ? (w1[a] * wa + w1[b] * wb + w1[c] * wc + w1[e] * we) / wtmp : 0.0;
+}
+__device__ __forceinline__ double avg2(const double *__restrict__ w1, const double *__restrict__ wg, size_t a, size_t b) {
+  const double wa = wg[a], wb = wg[b];
+  const double wtmp = (wa + wb);
+  return (wtmp != 0.0) ? (w1[a] * wa + w1[b] * wb) / wtmp : 0.0;
+}
+__global__ void __launch_bounds__(256) k5_interp(const __grid_constant__ CDom d) {
+  CELL_IJ(d.nx, d.ny);
+  const size_t e = c + 1, w = c - 1, n = c + d.ld, s = c - d.ld;
+  const double uN = avg4(d.uvelE, d.earea, w, c, n - 1, n) * d.npm[c];      // E2NA 'NW'
+  const double vE = avg4(d.vvelN, d.narea, s, s + 1, c, e) * d.epm[c];      // N2EA 'SE'
+  const double uU = avg2(d.uvelE, d.earea, c, n) * d.uvm[c];                // E2UA 'N'
+  const double vU = avg2(d.vvelN, d.narea, c, e) * d.uvm[c];                // N2UA 'E'
+  ring_store(d, d.uvelN, i, j, uN, 3, true);
+  ring_store(d, d.vvelE, i, j, vE, 3, true);
+  ring_store(d, d.uvel, i, j, uU, 3, true);
+  ring_store(d, d.vvel, i, j, vU, 3, true);
+}
+
+cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches) {
+  dim3 b(32, 8), gU((d.nx + 31) / 32, (d.ny + 7) / 8), gT((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8);
+  k1_strain_U<<<gU, b, 0, s>>>(d, p);
+  k2_stress_T<<<gT, b, 0, s>>>(d, p);
+  k3_stress_U<<<gU, b, 0, s>>>(d, p);
+  k4_momentum<<<gU, b, 0, s>>>(d, p);
+  k5_interp<<<gU, b, 0, s>>>(d);
+  *launches += 5;
+  return cudaGetLastError();
+}
+
+}  // namespace EVP_NS
+}  // namespace evp

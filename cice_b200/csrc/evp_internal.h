@@ -36,11 +36,30 @@ struct Dom {
   const unsigned char *maskT, *maskU;
 };
 
+// C grid (grid_ice = 'C'): every array of the C-grid subcycle on the dom layout (see evp_cgrid.cu)
+struct CDom {
+  int nx, ny, ld, nyd, wrap_ew, wrap_ns;
+  // static geometry
+  const double *dxN, *dyE, *dxE, *dyN, *dxU, *dyU, *dxT, *dyT, *uarea, *DminTarea, *tarea, *hm, *earea, *narea, *earear, *narear;
+  const double *ratiodxN, *ratiodxNr, *ratiodyE, *ratiodyEr, *epm, *npm, *uvm;
+  // carried state
+  double *uvelE, *vvelE, *uvelN, *vvelN, *uvel, *vvel, *stresspT, *stressmT, *stress12T, *stress12U;
+  // work arrays the reference leaves behind
+  double *zetax2T, *etax2T, *etax2U, *strengthU, *divergU, *tensionU, *shearU, *deltaU, *strintxE, *strintyN, *taubxE, *taubyN;
+  // per-step inputs
+  const double *strength, *cdnE, *cdnN, *aiE, *aiN, *uocnE, *vocnE, *uocnN, *vocnN, *waterxE, *wateryN, *forcexE, *forceyN;
+  const double *emassdti, *nmassdti, *fmE, *fmN, *TbE, *TbN, *rheofactE, *rheofactN;
+  double *uvelE_init, *vvelN_init;
+  const unsigned char *maskT, *maskU, *maskE, *maskN;
+};
+
 // scalars of set_evp_parameters (ice_dyn_shared.F90:453-486) and friends
 struct KParams {
   double arlx1i, denom1, revp, brlx;
   double e_factor, epp2i, capping, Ktens;
   double u0, cosw, sinw, rhow;
+  double deltaminEVP;
+  int visc_method;
 };
 
 // In-kernel NVLink halo (see evp_halo.cu, fused_kernel): edge CTAs store new edge velocities straight into the
@@ -89,6 +108,7 @@ struct PersistPlan {
   cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl); \
   cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, cudaStream_t s); \
   cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s); \
+  cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \
   }
 EVP_DECLARE_LAUNCHERS(exact)
 EVP_DECLARE_LAUNCHERS(fast)

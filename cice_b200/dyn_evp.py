@@ -63,6 +63,21 @@ def dyn_evp_b200_run(params, fields):
     return fields
 
 
+def dyn_evp_b200_init_cgrid(cgrid):
+    """extra static geometry of grid_ice='C' (after dyn_evp_b200_init)."""
+    cg, keep = abi.make_cgrid(cgrid, _state["npl"])
+    check(load().evp_b200_init_cgrid(C.byref(cg)), "evp_b200_init_cgrid")
+    _state["ckeep"] = keep
+
+
+def dyn_evp_b200_run_cgrid(params, cfields):
+    """the C-grid subcycle loop (ice_dyn_evp.F90:936-1101): host arrays in, host arrays out."""
+    p = abi.make_params(params)
+    f, keep = abi.make_cfields(cfields, _state["npl"])
+    check(load().evp_b200_run_cgrid(C.byref(p), C.byref(f)), "evp_b200_run_cgrid")
+    return cfields
+
+
 def upload(fields):
     f, keep = _fields(fields)
     check(load().evp_b200_upload(C.byref(f)), "evp_b200_upload")

@@ -70,7 +70,7 @@ void dyn_evp_b200_run(double *stressp_1, double *stressp_2, double *stressp_3, d
   p.ndte = s.ndte; p.mode = s.mode; p.kernel = s.kernel;
   p.arlx1i = s.arlx1i; p.denom1 = s.denom1; p.revp = s.revp; p.brlx = s.brlx;
   p.e_factor = s.e_factor; p.epp2i = s.epp2i; p.capping = s.capping; p.Ktens = s.Ktens;
-  p.u0 = s.u0; p.cosw = s.cosw; p.sinw = s.sinw; p.rhow = s.rhow;
+  p.u0 = s.u0; p.cosw = s.cosw; p.sinw = s.sinw; p.rhow = s.rhow; p.deltaminEVP = s.deltaminEVP;
   evp_b200_fields_t f;
   f.stressp_1 = stressp_1; f.stressp_2 = stressp_2; f.stressp_3 = stressp_3; f.stressp_4 = stressp_4;
   f.stressm_1 = stressm_1; f.stressm_2 = stressm_2; f.stressm_3 = stressm_3; f.stressm_4 = stressm_4;

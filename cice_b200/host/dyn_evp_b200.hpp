@@ -44,7 +44,7 @@ struct Geometry {
 struct EvpScalars {
   int ndte = 120;
   double arlx1i = 0, denom1 = 0, revp = 0, brlx = 0, e_factor = 0, epp2i = 0, capping = 1, Ktens = 0;
-  double u0 = 5e-5, cosw = 1, sinw = 0, rhow = 1026;
+  double u0 = 5e-5, cosw = 1, sinw = 0, rhow = 1026, deltaminEVP = 1e-11;
   int mode = EVP_B200_MODE_EXACT, kernel = EVP_B200_KERNEL_AUTO;
 };
 

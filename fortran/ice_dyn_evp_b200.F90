@@ -25,7 +25,7 @@ module ice_dyn_evp_b200
   private
   public :: dyn_evp_b200_init, dyn_evp_b200_run, dyn_evp_b200_finalize
 
-  integer(c_int32_t), parameter :: EVP_B200_ABI_VERSION = 1
+  integer(c_int32_t), parameter :: EVP_B200_ABI_VERSION = 2
   integer(c_int32_t), parameter :: BNDY_OPEN = 0, BNDY_CLOSED = 1, BNDY_CYCLIC = 2, BNDY_TRIPOLE = 3
 
   ! evp_b200_grid_t
@@ -38,8 +38,8 @@ module ice_dyn_evp_b200
 
   ! evp_b200_params_t
   type, bind(C) :: evp_b200_params_t
-     integer(c_int32_t) :: ndte, mode, kernel, reserved
-     real(c_double) :: arlx1i, denom1, revp, brlx, e_factor, epp2i, capping, Ktens, u0, cosw, sinw, rhow
+     integer(c_int32_t) :: ndte, mode, kernel, visc_method
+     real(c_double) :: arlx1i, denom1, revp, brlx, e_factor, epp2i, capping, Ktens, u0, cosw, sinw, rhow, deltaminEVP
   end type evp_b200_params_t
 
   ! evp_b200_fields_t: the argument list of dyn_evp1d_run, in order
@@ -181,7 +181,7 @@ contains
                               umassdti  , fmU       , strintxU  , strintyU  , &
                               TbU       , taubxU    , taubyU    , uvel      , &
                               vvel      , iceTmask  , iceUmask)
-    use ice_dyn_shared, only: ndte, arlx1i, denom1, revp, brlx, e_factor, epp2i, capping, Ktens, u0, cosw, sinw
+    use ice_dyn_shared, only: ndte, arlx1i, denom1, revp, brlx, e_factor, epp2i, capping, Ktens, u0, cosw, sinw, deltaminEVP
     use icepack_intfc,  only: icepack_query_parameters
     real(kind=dbl_kind), dimension(:,:,:), intent(inout), target, contiguous :: &
          stressp_1 , stressp_2 , stressp_3 , stressp_4 , stressm_1 , stressm_2 , stressm_3 , stressm_4 , &
@@ -195,10 +195,10 @@ contains
     real(kind=dbl_kind) :: rhow
 
     call icepack_query_parameters(rhow_out=rhow)
-    p%ndte = ndte;  p%mode = 0;  p%kernel = 0;  p%reserved = 0      ! exact arithmetic, library picks the kernel
+    p%ndte = ndte;  p%mode = 0;  p%kernel = 0;  p%visc_method = 0   ! exact arithmetic, library picks the kernel
     p%arlx1i = arlx1i;  p%denom1 = denom1;  p%revp = revp;  p%brlx = brlx
     p%e_factor = e_factor;  p%epp2i = epp2i;  p%capping = capping;  p%Ktens = Ktens
-    p%u0 = u0;  p%cosw = cosw;  p%sinw = sinw;  p%rhow = rhow
+    p%u0 = u0;  p%cosw = cosw;  p%sinw = sinw;  p%rhow = rhow;  p%deltaminEVP = deltaminEVP
 
     ! Fortran logical is not C-interoperable: 0/1 integers cross the boundary
     imaskT = merge(1_c_int32_t, 0_c_int32_t, iceTmask)

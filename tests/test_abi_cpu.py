@@ -31,13 +31,20 @@ def test_library_exports_every_declared_symbol(evp_lib):
 def test_struct_layouts_match_header():
     """ctypes mirrors must have the C layout: 10 int32 + 6 + 10 pointers; 4 int32 + 12 doubles; 30 + 2 pointers."""
     assert C.sizeof(abi.Grid) == 10 * 4 + 16 * 8
-    assert C.sizeof(abi.Params) == 4 * 4 + 12 * 8
+    assert C.sizeof(abi.Params) == 4 * 4 + 13 * 8
     assert C.sizeof(abi.Fields) == 32 * 8
+    assert C.sizeof(abi.CGrid) == 20 * 8
+    assert C.sizeof(abi.CFields) == 47 * 8
     txt = open(os.path.join(ROOT, "include", "evp_b200.h")).read()
-    body = txt[txt.index("typedef struct {", txt.index("Time-varying fields")):txt.index("} evp_b200_fields_t;")]
+    body = txt[txt.index("typedef struct {", txt.index("Time-varying fields of one call")):txt.index("} evp_b200_fields_t;")]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = re.findall(r"\*\s*([A-Za-z_0-9]+)", body)
     assert tuple(names) == abi.FIELDS_ORDER + abi.FIELDS_MASK
+    for start, end, want in (("Extra static geometry of grid_ice", "} evp_b200_cgrid_t;", abi.CGRID_STATIC),
+                             ("Time-varying fields of one C-grid call", "} evp_b200_cfields_t;", abi.CFIELDS_ORDER + abi.CFIELDS_MASK)):
+        body = txt[txt.index("typedef struct {", txt.index(start)):txt.index(end)]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        assert tuple(re.findall(r"\*\s*([A-Za-z_0-9]+)", body)) == want, start
 
 
 def test_no_cpu_fallback_without_gpu(evp_lib):

@@ -1,0 +1,105 @@
+"""C grid (configs[2]: gx1 C-grid EVP, evp_algorithm=standard_2d, ndte=600, 1 GPU): oracle properties on the
+CPU, bit-exact parity of the CUDA path through the C ABI on the GPU."""
+import numpy as np
+import pytest
+
+from cice_b200 import abi, synth
+
+CF = abi.CFIELDS_INOUT + tuple(n for n in abi.CFIELDS_OUT if n != "strengthU")
+
+
+def run_oracle_c(oracle, c, nthreads=0):
+    f = c.copy_fields()
+    oracle.evp_run_cgrid(c.grid, c.cgrid, c.params, f, nthreads=nthreads)
+    return f
+
+
+def run_gpu_c(evp, c, **over):
+    f = c.copy_fields()
+    evp.dyn_evp_b200_init(c.grid)
+    try:
+        evp.dyn_evp_b200_init_cgrid(c.cgrid)
+        evp.dyn_evp_b200_run_cgrid(dict(c.params, **over), f)
+    finally:
+        evp.dyn_evp_b200_finalize()
+    return f
+
+
+@pytest.mark.parametrize("bs", [(12, 10), (7, 9), (24, 5)])
+@pytest.mark.parametrize("visc", [abi.VISC_AVG_ZETA, abi.VISC_AVG_STRENGTH], ids=["avg_zeta", "avg_strength"])
+def test_cgrid_oracle_decomposition_invariance(oracle_mod, bs, visc):
+    """the reference's decomp property (gridsys_suite runs every box case on the C grid too)"""
+    ref = synth.make_ccase("tiny", seed=5, visc_method=visc)
+    G = {n: synth.gather(v, ref.blocks) for n, v in run_oracle_c(oracle_mod, ref, 1).items() if n in abi.CFIELDS_INOUT}
+    c = synth.make_ccase("tiny", seed=5, visc_method=visc, block_size=bs)
+    f = run_oracle_c(oracle_mod, c)
+    for n in abi.CFIELDS_INOUT:
+        assert np.array_equal(synth.gather(f[n], c.blocks), G[n]), n
+
+
+def test_cgrid_oracle_zero_forcing_stays_at_rest(oracle_mod):
+    c = synth.make_ccase("tiny")
+    for n in ("uvelE", "vvelE", "uvelN", "vvelN", "uvel", "vvel", "uocnE", "vocnE", "uocnN", "vocnN", "waterxE", "wateryN", "forcexE", "forceyN"):
+        c.fields[n][:] = 0.0
+    f = run_oracle_c(oracle_mod, c, 1)
+    for n in ("uvelE", "vvelN", "uvel", "vvel", "stressmT", "stress12T", "stress12U"):
+        assert np.abs(f[n]).max() == 0.0, n
+
+
+def test_cgrid_oracle_interpolants_are_consistent(oracle_mod):
+    """after the loop uvel/vvel are exactly the masked area averages of uvelE/vvelN (ice_dyn_evp.F90:1081-1090)"""
+    c = synth.make_ccase("gx3", ndte=15)
+    f = run_oracle_c(oracle_mod, c, 1)
+    ea, uvm = c.cgrid["earea"][0], c.cgrid["uvm"][0]
+    uE = f["uvelE"][0]
+    num = uE[1:-1, 1:-1] * ea[1:-1, 1:-1] + uE[2:, 1:-1] * ea[2:, 1:-1]
+    want = num / (ea[1:-1, 1:-1] + ea[2:, 1:-1]) * uvm[1:-1, 1:-1]
+    assert np.array_equal(f["uvel"][0][1:-1, 1:-1], want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,kw", [
+    ("tiny", dict()), ("tiny", dict(seed=3)), ("tiny", dict(seed=4, revised_evp=True)),
+    ("tiny", dict(seed=5, visc_method=abi.VISC_AVG_STRENGTH)),
+    ("tiny", dict(seed=6, ew="closed", ns="closed")), ("tiny", dict(seed=7, ew="cyclic", ns="cyclic", kmt="none")),
+    ("gx3", dict(ndte=40)), ("gx3", dict(seed=20260103, ndte=9)),
+], ids=["tiny-s1", "tiny-s2", "tiny-revised", "tiny-avgstrength", "tiny-closed", "tiny-cyclic2", "gx3-s1", "gx3-s2"])
+def test_cgrid_exact_bitwise(oracle_mod, evp_lib, cfg, kw):
+    c = synth.make_ccase(cfg, **kw)
+    ref = run_oracle_c(oracle_mod, c)
+    got = run_gpu_c(evp_lib, c, mode=abi.MODE_EXACT)
+    skip = "etax2U" if c.params["visc_method"] == abi.VISC_AVG_STRENGTH else "strengthU"
+    for n in abi.CFIELDS_INOUT + abi.CFIELDS_OUT:
+        if n == skip:
+            continue
+        assert np.array_equal(got[n].view(np.int64), ref[n].view(np.int64)), \
+            f"{n}: {np.count_nonzero(got[n] != ref[n])} cells differ, max {np.nanmax(np.abs(got[n] - ref[n])):.3e}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bs", [(12, 10), (7, 9)])
+def test_cgrid_exact_bitwise_multi_block(oracle_mod, evp_lib, bs):
+    c = synth.make_ccase("tiny", seed=8, block_size=bs)
+    ref = run_oracle_c(oracle_mod, c)
+    got = run_gpu_c(evp_lib, c, mode=abi.MODE_EXACT)
+    for n in abi.CFIELDS_INOUT + abi.CFIELDS_OUT:
+        if n == "strengthU":
+            continue
+        assert np.array_equal(got[n].view(np.int64), ref[n].view(np.int64)), n
+
+
+@pytest.mark.gpu
+def test_cgrid_gx1_ndte600(oracle_mod, evp_lib):
+    """configs[2]: gx1 C grid, ndte = 600, one GPU."""
+    c = synth.make_ccase("gx1", ndte=600)
+    ref = run_oracle_c(oracle_mod, c)
+    got = run_gpu_c(evp_lib, c, mode=abi.MODE_EXACT)
+    for n in abi.CFIELDS_INOUT:
+        assert np.array_equal(got[n].view(np.int64), ref[n].view(np.int64)), n
+
+
+@pytest.mark.gpu
+def test_cgrid_refused_where_unsupported(evp_lib):
+    c = synth.make_ccase("tiny")
+    with pytest.raises(evp_lib.EvpB200Error, match="evp_b200_init first"):
+        evp_lib.dyn_evp_b200_init_cgrid(c.cgrid)
