@@ -119,6 +119,8 @@ struct Ctx {
   std::vector<double *> cbuf;      // every C-grid device array (freed together)
   std::vector<double *> cstage;    // staging, one per C field
   unsigned char *cmask[4] = {};
+  cudaGraphExec_t cexec = nullptr;  // cached graph of the C-grid loop (dies with the context: it bakes pointers and wrap flags)
+  evp_b200_params_t cparams{};
 
   // KERNEL_PERSISTENT
   PersistPlan pplan{};
@@ -138,6 +140,10 @@ static void destroy_graph() {
   if (g.gexec) {
     cudaGraphExecDestroy(g.gexec);
     g.gexec = nullptr;
+  }
+  if (g.cexec) {
+    cudaGraphExecDestroy(g.cexec);
+    g.cexec = nullptr;
   }
 }
 
@@ -696,11 +702,10 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
   // the loop: 5 kernels per subcycle, captured once per parameter set
   const KParams k = kparams(p);
   const bool exact = (p->mode == EVP_B200_MODE_EXACT);
-  static cudaGraphExec_t cexec = nullptr;
-  static evp_b200_params_t cparams{};
-  static const void *cowner = nullptr;
+  cudaGraphExec_t &cexec = g.cexec;
+  evp_b200_params_t &cparams = g.cparams;
   int nl = 0;
-  if (!cexec || cowner != (const void *)c.uvelE || memcmp(&cparams, p, sizeof *p) != 0) {
+  if (!cexec || memcmp(&cparams, p, sizeof *p) != 0) {
     if (cexec) { cudaGraphExecDestroy(cexec); cexec = nullptr; }
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
@@ -711,7 +716,7 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
     if (le != cudaSuccess || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail("evp_b200_run_cgrid: capture failed: %s", cudaGetErrorString(le != cudaSuccess ? le : ce)); }
     CK(cudaGraphInstantiate(&cexec, graph, 0));
     CK(cudaGraphDestroy(graph));
-    cparams = *p; cowner = (const void *)c.uvelE;
+    cparams = *p;
   } else {
     nl = 5 * p->ndte;
   }

@@ -284,6 +284,79 @@ __global__ void p2p_finish_kernel(const __grid_constant__ P2PParams pp, int ndte
   if (threadIdx.x == 0) *pp.epoch_base = base + (unsigned long long)ndte + 1ULL;
 }
 
+// ---------------------------------------------------------------------------------------------
+// KERNEL_FUSED, corner-parallel: 1024 threads = a 32 x 8 patch of T cells x 4 corner lanes (stress_lane).
+// Same patch geometry, ownership rule and ping-pong as fused_kernel; the momentum step runs on the first 256
+// threads, one per U point.
+// ---------------------------------------------------------------------------------------------
+constexpr int F4X = 32, F4Y = 8;
+__global__ void __launch_bounds__(F4X *F4Y * 4, 1) fused4_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k, int cur) {
+  __shared__ double sstr[8][F4Y][F4X];
+  __shared__ double su[F4Y + 1][F4X + 1], sv[F4Y + 1][F4X + 1];
+  const int t = threadIdx.x;
+  const int nxt = cur ^ 1;
+  const int i0 = 1 + blockIdx.x * (F4X - 1), j0 = 1 + blockIdx.y * (F4Y - 1);
+  {
+    const double *__restrict__ U = d.u[cur];
+    const double *__restrict__ V = d.v[cur];
+    for (int q = t; q < (F4X + 1) * (F4Y + 1); q += F4X * F4Y * 4) {
+      const int a = q % (F4X + 1), b = q / (F4X + 1);
+      const int gi = i0 - 1 + a, gj = j0 - 1 + b;
+      const bool in = (gi <= d.nx + 1) && (gj <= d.ny + 1);
+      su[b][a] = in ? U[at(d, gi, gj)] : 0.0;
+      sv[b][a] = in ? V[at(d, gi, gj)] : 0.0;
+    }
+  }
+  __syncthreads();
+  {
+    const int corner = t & 3, cell = t >> 2, cx = cell & (F4X - 1), cy = cell / F4X;
+    const int i = i0 + cx, j = j0 + cy;
+    const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
+    const size_t c = at(d, inT ? i : 1, inT ? j : 1);
+    double str_u = 0.0, str_v = 0.0;
+    if (inT && d.maskT[c]) {
+      const int a = cx + 1, b = cy + 1;
+      const int sa = a - ((corner == NW || corner == SW) ? 1 : 0), sb = b - ((corner >= SW) ? 1 : 0);
+      const int xa = 2 * a - 1 - sa, yb = 2 * b - 1 - sb;
+      double sp = d.sig[cur][corner][c], sm = d.sig[cur][4 + corner][c], s12 = d.sig[cur][8 + corner][c];
+      const unsigned gmask = 0xFu << ((t & 31) & ~3);
+      stress_lane(corner, su[sb][sa], sv[sb][sa], su[sb][xa], sv[sb][xa], su[yb][sa], sv[yb][sa], d.dxT[c], d.dyT[c], d.dxhy[c],
+                  d.dyhx[c], d.cxp[c], d.cyp[c], d.cxm[c], d.cym[c], d.DminTarea[c], d.strength[c], k, gmask, sp, sm, s12, str_u, str_v);
+      const bool own = (cx < F4X - 1 || i == d.nx + 1) && (cy < F4Y - 1 || j == d.ny + 1);
+      if (own) {
+        d.sig[nxt][corner][c] = sp;
+        d.sig[nxt][4 + corner][c] = sm;
+        d.sig[nxt][8 + corner][c] = s12;
+      }
+    }
+    // NE: str1,str5  NW: str2,str7  SW: str4,str8  SE: str3,str6
+    const int qu = (corner == NE) ? 0 : (corner == NW) ? 1 : (corner == SW) ? 3 : 2;
+    const int qv = (corner == NE) ? 4 : (corner == NW) ? 6 : (corner == SW) ? 7 : 5;
+    sstr[qu][cy][cx] = str_u;
+    sstr[qv][cy][cx] = str_v;
+  }
+  __syncthreads();
+  if (t < F4X * F4Y) {
+    const int tx = t & (F4X - 1), ty = t / F4X;
+    const int i = i0 + tx, j = j0 + ty;
+    if (tx < F4X - 1 && ty < F4Y - 1 && i <= d.nx && j <= d.ny) {
+      const size_t c = at(d, i, j);
+      if (d.maskU[c]) {
+        const UOut o = stepu_point(su[ty + 1][tx + 1], sv[ty + 1][tx + 1], d.cdn[c], d.aiu[c], d.uocn[c], d.vocn[c], d.waterx[c],
+                                   d.watery[c], d.forcex[c], d.forcey[c], d.umassdti[c], d.fm[c], d.uarear[c], d.TbU[c],
+                                   d.uinit[c], d.vinit[c], sstr[0][ty][tx], sstr[1][ty][tx + 1], sstr[2][ty + 1][tx],
+                                   sstr[3][ty + 1][tx + 1], sstr[4][ty][tx], sstr[5][ty + 1][tx], sstr[6][ty][tx + 1],
+                                   sstr[7][ty + 1][tx + 1], k);
+        store_uv(d, d.u[nxt], d.v[nxt], i, j, o.u, o.v);
+        d.strintx[c] = o.strintx;
+        d.strinty[c] = o.strinty;
+        d.taubx[c] = o.taubx;
+        d.tauby[c] = o.tauby;
+      }
+    }
+  }
+}
+
 template <int FBX, int FBY, int MINB, bool HOIST = false>
 static cudaError_t launch_fused_t(const Dom &d, const KParams &p, int cur, cudaStream_t s, bool pdl) {
   dim3 b(FBX, FBY), g((d.nx + FBX - 2) / (FBX - 1), (d.ny + FBY - 2) / (FBY - 1));
@@ -298,6 +371,11 @@ static cudaError_t launch_fused_t(const Dom &d, const KParams &p, int cur, cudaS
 }
 
 cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl) {
+  if (variant == 20) {
+    dim3 g4((d.nx + F4X - 2) / (F4X - 1), (d.ny + F4Y - 2) / (F4Y - 1));
+    fused4_kernel<<<g4, F4X * F4Y * 4, 0, s>>>(d, p, cur);
+    return cudaGetLastError();
+  }
   switch (variant) {
     case 1: return launch_fused_t<32, 8, 3>(d, p, cur, s, pdl);
     case 2: return launch_fused_t<32, 8, 4>(d, p, cur, s, pdl);
@@ -309,6 +387,11 @@ cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s
     case 8: return launch_fused_t<33, 8, 2, false>(d, p, cur, s, pdl);
     case 9: return launch_fused_t<33, 8, 2, true>(d, p, cur, s, pdl);
     case 10: return launch_fused_t<32, 4, 4, true>(d, p, cur, s, pdl);
+    case 11: return launch_fused_t<32, 9, 2>(d, p, cur, s, pdl);
+    case 12: return launch_fused_t<32, 10, 2>(d, p, cur, s, pdl);
+    case 13: return launch_fused_t<32, 7, 3>(d, p, cur, s, pdl);
+    case 14: return launch_fused_t<32, 5, 4>(d, p, cur, s, pdl);
+    case 15: return launch_fused_t<32, 11, 1>(d, p, cur, s, pdl);
     default: return launch_fused_t<32, 8, 2>(d, p, cur, s, pdl);
   }
 }
