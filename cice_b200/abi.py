@@ -79,6 +79,28 @@ class CFields(C.Structure):
     _fields_ = [(n, _pd) for n in CFIELDS_ORDER] + [(n, _pi) for n in CFIELDS_MASK]
 
 
+DEFORM_IN = ("dxU", "dyU", "tarear")
+DEFORM_OUT = ("divu", "shear", "vort", "rdg_conv", "rdg_shear")
+
+
+class Deform(C.Structure):
+    _fields_ = [(n, _pd) for n in DEFORM_IN + DEFORM_OUT] + [("e_factor", C.c_double)]
+
+
+def make_deform(d, npl_total, e_factor):
+    s, keep = Deform(), {}
+    for n in DEFORM_IN:
+        keep[n] = as_f64(d[n])
+        setattr(s, n, _ptr(keep[n], C.c_double))
+    for n in DEFORM_OUT:
+        a = d[n]
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == npl_total, n
+        keep[n] = a
+        setattr(s, n, _ptr(a, C.c_double))
+    s.e_factor = float(e_factor)
+    return s, keep
+
+
 def _ptr(a, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))
 

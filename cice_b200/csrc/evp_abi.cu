@@ -116,6 +116,7 @@ struct Ctx {
   // C grid
   bool cinit = false;
   CDom cdom{};
+  std::vector<double *> dbuf;      // deformations: dxU, dyU, tarear + 5 outputs
   std::vector<double *> cbuf;      // every C-grid device array (freed together)
   std::vector<double *> cstage;    // staging, one per C field
   unsigned char *cmask[4] = {};
@@ -156,6 +157,7 @@ static int free_all() {
   };
   g.p2p.release();
   for (auto &p : g.cbuf) F(p);
+  for (auto &p : g.dbuf) F(p);
   for (auto &p : g.cstage) F(p);
   for (auto &p : g.cmask) F(p);
   g.dfield[F_U] = g.dfield[F_V] = g.du1 = g.dv1 = nullptr;  // live inside dshare
@@ -604,6 +606,38 @@ static int calloc_dom(double *&p) {
   return 0;
 }
 
+// deformations on the device-resident final velocities
+static int do_deformations(evp_b200_deform_t *dd) {
+  if (!g.inited || !g.uploaded) return fail("evp_b200_deformations: no velocities on the device (run the loop first)");
+  if (!dd || !dd->dxU || !dd->dyU || !dd->tarear || !dd->divu || !dd->shear || !dd->vort || !dd->rdg_conv || !dd->rdg_shear)
+    return fail("evp_b200_deformations: null argument");
+  CK(cudaSetDevice(g.device));
+  const size_t bblk = g.nblk_elems * sizeof(double);
+  if (g.dbuf.empty()) {
+    for (int q = 0; q < 8; ++q) {
+      double *p = nullptr;
+      CK(cudaMalloc(&p, g.ndom * sizeof(double)));
+      g.dbuf.push_back(p);
+    }
+  }
+  const double *src[8] = {dd->dxU, dd->dyU, dd->tarear, dd->divu, dd->shear, dd->vort, dd->rdg_conv, dd->rdg_shear};
+  double *dst[5] = {dd->divu, dd->shear, dd->vort, dd->rdg_conv, dd->rdg_shear};
+  for (int q = 0; q < 8; ++q) {
+    CK(cudaMemcpyAsync(g.stage[q], src[q], bblk, cudaMemcpyHostToDevice, g.stream));
+    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(g.dbuf[q], g.stage[q], g.d_gsrc, (int)g.ndom);
+  }
+  // the exact build: the reference's `deformations` has no contraction-sensitive state, but keep one answer
+  CK(exact::launch_deform(g.dom, g.cur, g.dbuf[0], g.dbuf[1], g.dbuf[2], g.dbuf[3], g.dbuf[4], g.dbuf[5], g.dbuf[6], g.dbuf[7],
+                          dd->e_factor, g.stream));
+  for (int q = 0; q < 5; ++q) {
+    unpack_f64<<<grid_blocks(g.n_sig), 256, 0, g.stream>>>(g.stage[3 + q], g.dbuf[3 + q], g.d_sig_lin, g.d_sig_dom, g.n_sig);
+    CK(cudaMemcpyAsync(dst[q], g.stage[3 + q], bblk, cudaMemcpyDeviceToHost, g.stream));
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
 static int do_init_cgrid(const evp_b200_cgrid_t *cg) {
   if (!g.inited) return fail("evp_b200_init_cgrid: call evp_b200_init first");
   if (!cg) return fail("evp_b200_init_cgrid: null grid");
@@ -661,14 +695,15 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
   CDom &c = g.cdom;
   const size_t bblk = g.nblk_elems * sizeof(double), bdom = g.ndom * sizeof(double);
   // host pointer, device array, how it moves: 'i' in, 'r' inout ring, 's' inout T cells the loop owns (N/E ghost incl.),
-  // 'n' inout interior, 'z' out: the reference zero-fills the whole block then halo-updates / leaves it
+  // 'n' inout interior, 'z' out: the reference zero-fills the whole block, writes interiors, halo-updates;
+  // 'y' out: zero-filled whole block, interiors written, NOT halo-updated (block ghost cells stay 0)
   struct Fld { const double *h; double *dv; char kind; };
   const bool avgstr = (p->visc_method == EVP_B200_VISC_AVG_STRENGTH);
   Fld tab[43] = {
       {f->uvelE, c.uvelE, 'r'}, {f->vvelE, c.vvelE, 'r'}, {f->uvelN, c.uvelN, 'r'}, {f->vvelN, c.vvelN, 'r'}, {f->uvel, c.uvel, 'r'}, {f->vvel, c.vvel, 'r'},
       {f->stresspT, c.stresspT, 'r'}, {f->stressmT, c.stressmT, 'r'}, {f->stress12T, c.stress12T, 's'}, {f->stress12U, c.stress12U, 'r'},
-      {f->zetax2T, c.zetax2T, 'r'}, {f->etax2T, c.etax2T, 'r'}, {f->etax2U, c.etax2U, avgstr ? '-' : 'z'}, {f->strengthU, c.strengthU, avgstr ? 'z' : '-'},
-      {f->divergU, c.divergU, 'z'}, {f->tensionU, c.tensionU, 'z'}, {f->shearU, c.shearU, 'z'}, {f->deltaU, c.deltaU, 'z'},
+      {f->zetax2T, c.zetax2T, 'r'}, {f->etax2T, c.etax2T, 'r'}, {f->etax2U, c.etax2U, avgstr ? '-' : 'y'}, {f->strengthU, c.strengthU, avgstr ? 'y' : '-'},
+      {f->divergU, c.divergU, 'y'}, {f->tensionU, c.tensionU, 'y'}, {f->shearU, c.shearU, 'z'}, {f->deltaU, c.deltaU, 'y'},
       {f->strintxE, c.strintxE, 'n'}, {f->strintyN, c.strintyN, 'n'}, {f->taubxE, c.taubxE, 'n'}, {f->taubyN, c.taubyN, 'n'},
       {f->strength, (double *)c.strength, 'i'}, {f->cdn_ocnE, (double *)c.cdnE, 'i'}, {f->cdn_ocnN, (double *)c.cdnN, 'i'}, {f->aiE, (double *)c.aiE, 'i'},
       {f->aiN, (double *)c.aiN, 'i'}, {f->uocnE, (double *)c.uocnE, 'i'}, {f->vocnE, (double *)c.vocnE, 'i'}, {f->uocnN, (double *)c.uocnN, 'i'},
@@ -680,7 +715,7 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
     const Fld &t = tab[q];
     if (t.kind == '-') continue;
     if (!t.h) return fail("evp_b200_run_cgrid: null field %d", q);
-    if (t.kind == 'z') {
+    if (t.kind == 'z' || t.kind == 'y') {
       CK(cudaMemsetAsync(t.dv, 0, bdom, g.stream));
       CK(cudaMemsetAsync(g.cstage[q], 0, bblk, g.stream));
       continue;
@@ -731,7 +766,7 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
     if (t.kind == '-') continue;
     if (t.kind == 's')
       unpack_f64<<<grid_blocks(g.n_sig), 256, 0, g.stream>>>(g.cstage[q], t.dv, g.d_sig_lin, g.d_sig_dom, g.n_sig);
-    else if (t.kind == 'n')
+    else if (t.kind == 'n' || t.kind == 'y')
       unpack_f64<<<grid_blocks(g.n_int), 256, 0, g.stream>>>(g.cstage[q], t.dv, g.d_int_lin, g.d_int_dom, g.n_int);
     else
       unpack_f64<<<grid_blocks(g.n_uv), 256, 0, g.stream>>>(g.cstage[q], t.dv, g.d_uv_lin, g.d_uv_dom, g.n_uv);
@@ -786,6 +821,7 @@ int evp_b200_finalize(void) {
   return 0;
 }
 
+int evp_b200_deformations(evp_b200_deform_t *d) { return do_deformations(d); }
 int evp_b200_init_cgrid(const evp_b200_cgrid_t *cg) { return do_init_cgrid(cg); }
 int evp_b200_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) { return do_run_cgrid(p, f); }
 

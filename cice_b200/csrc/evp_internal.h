@@ -105,6 +105,7 @@ struct PersistPlan {
   namespace NS {                                                                                    \
   cudaError_t launch_stress(const Dom &d, const KParams &p, int cur, cudaStream_t s);               \
   cudaError_t launch_stepu(const Dom &d, const KParams &p, int cur, cudaStream_t s);                \
+  cudaError_t launch_deform(const Dom &d, int cur, const double *dxU, const double *dyU, const double *tarear, double *divu, double *shear, double *vort, double *rdg_conv, double *rdg_shear, double e_factor, cudaStream_t s); \
   cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl); \
   cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, cudaStream_t s); \
   cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s); \

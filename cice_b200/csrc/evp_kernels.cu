@@ -111,6 +111,59 @@ __global__ void __launch_bounds__(256) stepu_kernel(const __grid_constant__ Dom 
   d.tauby[c] = o.tauby;
 }
 
+// deformations (ice_dyn_shared.F90:1756-1860): the step right after the loop, from the resident velocities
+__global__ void __launch_bounds__(256) deform_kernel(const __grid_constant__ Dom d, const double *__restrict__ U,
+                                                     const double *__restrict__ V, const double *__restrict__ dxU,
+                                                     const double *__restrict__ dyU, const double *__restrict__ tarear,
+                                                     double *__restrict__ divu, double *__restrict__ shear,
+                                                     double *__restrict__ vort, double *__restrict__ rdg_conv,
+                                                     double *__restrict__ rdg_shear, double e_factor) {
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > d.nx + 1 || j > d.ny + 1) return;
+  const size_t c = at(d, i, j), w = c - 1, s = c - d.ld, sw = s - 1;
+  if (!d.maskT[c]) return;
+  const double ucc = U[c], vcc = V[c], uee = U[w], vee = V[w], use_ = U[s], vse = V[s], une = U[sw], vne = V[sw];
+  const double dxT = d.dxT[c], dyT = d.dyT[c], cxp = d.cxp[c], cyp = d.cyp[c], cxm = d.cxm[c], cym = d.cym[c];
+  double div[4], ten[4], shr[4];
+  div[NE] = cyp * ucc - dyT * uee + cxp * vcc - dxT * vse;
+  div[NW] = cym * uee + dyT * ucc + cxp * vee - dxT * vne;
+  div[SW] = cym * une + dyT * use_ + cxm * vne + dxT * vee;
+  div[SE] = cyp * use_ - dyT * une + cxm * vse + dxT * vcc;
+  ten[NE] = -cym * ucc - dyT * uee + cxm * vcc + dxT * vse;
+  ten[NW] = -cyp * uee + dyT * ucc + cxm * vee + dxT * vne;
+  ten[SW] = -cyp * une + dyT * use_ + cxp * vne - dxT * vee;
+  ten[SE] = -cym * use_ - dyT * une + cxp * vse - dxT * vcc;
+  shr[NE] = -cym * vcc - dyT * vee - cxm * ucc - dxT * use_;
+  shr[NW] = -cyp * vee + dyT * vcc - cxm * uee - dxT * une;
+  shr[SW] = -cyp * vne + dyT * vse - cxp * une + dxT * uee;
+  shr[SE] = -cym * vse - dyT * vne - cxp * use_ + dxT * ucc;
+  double Delta[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) Delta[q] = sqrt(div[q] * div[q] + e_factor * (ten[q] * ten[q] + shr[q] * shr[q]));
+  const double ta = tarear[c];
+  // reference order of the corner sums: ne + nw + se + sw
+  const double dv = 0.25 * (div[NE] + div[NW] + div[SE] + div[SW]) * ta;
+  const double tmp = 0.25 * (Delta[NE] + Delta[NW] + Delta[SE] + Delta[SW]) * ta;
+  divu[c] = dv;
+  rdg_conv[c] = -fmin(dv, 0.0);
+  rdg_shear[c] = 0.5 * (tmp - fabs(dv));
+  const double tsum = ten[NE] + ten[NW] + ten[SE] + ten[SW], ssum = shr[NE] + shr[NW] + shr[SE] + shr[SW];
+  shear[c] = 0.25 * ta * sqrt(tsum * tsum + ssum * ssum);
+  const double dvdxn = dyU[c] * vcc - dyU[w] * vee;
+  const double dvdxs = dyU[s] * vse - dyU[sw] * vne;
+  const double dudye = dxU[c] * ucc - dxU[s] * use_;
+  const double dudyw = dxU[w] * uee - dxU[sw] * une;
+  vort[c] = 0.5 * ta * (dvdxn + dvdxs - dudye - dudyw);
+}
+
+cudaError_t launch_deform(const Dom &d, int cur, const double *dxU, const double *dyU, const double *tarear, double *divu,
+                          double *shear, double *vort, double *rdg_conv, double *rdg_shear, double e_factor, cudaStream_t s) {
+  dim3 b(32, 8), g((d.nx + 1 + b.x - 1) / b.x, (d.ny + 1 + b.y - 1) / b.y);
+  deform_kernel<<<g, b, 0, s>>>(d, d.u[cur], d.v[cur], dxU, dyU, tarear, divu, shear, vort, rdg_conv, rdg_shear, e_factor);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_stress(const Dom &d, const KParams &p, int cur, cudaStream_t s) {
   dim3 b(32, 8), g((d.nx + 1 + b.x - 1) / b.x, (d.ny + 1 + b.y - 1) / b.y);
   stress_kernel<<<g, b, 0, s>>>(d, p, cur);

@@ -65,6 +65,8 @@ def dyn_evp_b200_run(params, fields):
 
 def dyn_evp_b200_init_cgrid(cgrid):
     """extra static geometry of grid_ice='C' (after dyn_evp_b200_init)."""
+    if _state["grid"] is None:
+        raise EvpB200Error("evp_b200_init_cgrid: call evp_b200_init first")
     cg, keep = abi.make_cgrid(cgrid, _state["npl"])
     check(load().evp_b200_init_cgrid(C.byref(cg)), "evp_b200_init_cgrid")
     _state["ckeep"] = keep
@@ -76,6 +78,14 @@ def dyn_evp_b200_run_cgrid(params, cfields):
     f, keep = abi.make_cfields(cfields, _state["npl"])
     check(load().evp_b200_run_cgrid(C.byref(p), C.byref(f)), "evp_b200_run_cgrid")
     return cfields
+
+
+def deformations(d, e_factor):
+    """`deformations` (ice_dyn_shared.F90:1756-1860) from the velocities the last loop left on the device;
+    d: dict with dxU, dyU, tarear (in) and divu, shear, vort, rdg_conv, rdg_shear (inout, in place)."""
+    s, keep = abi.make_deform(d, _state["npl"], e_factor)
+    check(load().evp_b200_deformations(C.byref(s)), "evp_b200_deformations")
+    return d
 
 
 def upload(fields):

@@ -203,6 +203,18 @@ int evp_b200_run_bgrid(const evp_b200_params_t *params, evp_b200_fields_t *field
 int evp_b200_init_cgrid(const evp_b200_cgrid_t *cgrid);
 int evp_b200_run_cgrid(const evp_b200_params_t *params, evp_b200_cfields_t *fields);
 
+/* ---- next row: deformations ------------------------------------------------
+ * `deformations` (ice_dyn_shared.F90:1756-1860), the step right after the subcycle loop in evp()
+ * (ice_dyn_evp.F90:920-934): divu, shear, vort, rdg_conv, rdg_shear at the ice T cells from the final
+ * (uvel,vvel), which are still resident on the device after evp_b200_run_bgrid / evp_b200_subcycle.
+ * The five arrays are inout: cells off the T list keep the caller's values (evp() zeroes them at :383-395). */
+typedef struct {
+  const double *dxU, *dyU, *tarear;                       /* static geometry, (nx_block,ny_block,max_blocks) */
+  double *divu, *shear, *vort, *rdg_conv, *rdg_shear;     /* inout */
+  double e_factor;                                        /* ice_dyn_shared.F90:465 */
+} evp_b200_deform_t;
+int evp_b200_deformations(evp_b200_deform_t *d);
+
 /* The same call split in three so that a caller which keeps dynamics state on the device
  *  -- and bench.py's device-resident timing -- can run the loop alone.
  * run_bgrid == upload + subcycle + download. */

@@ -630,3 +630,40 @@ int orc_evp_run_bgrid_1d(const evp_b200_grid_t *g, const double *HTE, const doub
   free(Cb); free(uinit); free(vinit); free(skipT); free(skipU);
   return 0;
 }
+
+/* ---------------------------------------------------------------------------------------
+ * deformations: shared.F90:1756-1860 (called from evp.F90:920-934 after the loop)
+ * ------------------------------------------------------------------------------------- */
+int orc_deformations(const evp_b200_grid_t *g, const int32_t *iceTmask, const double *uvel, const double *vvel,
+                     evp_b200_deform_t *d) {
+  if (check_grid(g)) return 1;
+  const int nx_block = g->nx_block;
+  const size_t npl = (size_t)g->nx_block * g->ny_block;
+  for (int b = 0; b < g->nblocks; ++b) {
+    const size_t o = (size_t)b * npl;
+    const double *u = uvel + o, *v = vvel + o, *dxU = d->dxU + o, *dyU = d->dyU + o, *tarear = d->tarear + o;
+    for (int j = g->jlo[b]; j <= g->jhi[b] + 1; ++j)
+      for (int i = g->ilo[b]; i <= g->ihi[b] + 1; ++i) {
+        const size_t c = IX(i, j), w = IX(i - 1, j), s = IX(i, j - 1), sw = IX(i - 1, j - 1);
+        if (!iceTmask[o + c]) continue;
+        strain_t st;
+        strain_rates_pt(u[c], v[c], u[w], v[w], u[s], v[s], u[sw], v[sw], g->dxT[o + c], g->dyT[o + c], g->cxp[o + c],
+                        g->cyp[o + c], g->cxm[o + c], g->cym[o + c], d->e_factor, &st);
+        /* shared.F90:1825-1848 */
+        const double divu = p25 * (st.divune + st.divunw + st.divuse + st.divusw) * tarear[c];
+        const double tmp = p25 * (st.Deltane + st.Deltanw + st.Deltase + st.Deltasw) * tarear[c];
+        d->divu[o + c] = divu;
+        d->rdg_conv[o + c] = -fmin(divu, c0);
+        d->rdg_shear[o + c] = p5 * (tmp - fabs(divu));
+        const double tsum = st.tensionne + st.tensionnw + st.tensionse + st.tensionsw;
+        const double ssum = st.shearne + st.shearnw + st.shearse + st.shearsw;
+        d->shear[o + c] = p25 * tarear[c] * sqrt(tsum * tsum + ssum * ssum);
+        const double dvdxn = dyU[c] * v[c] - dyU[w] * v[w];
+        const double dvdxs = dyU[s] * v[s] - dyU[sw] * v[sw];
+        const double dudye = dxU[c] * u[c] - dxU[s] * u[s];
+        const double dudyw = dxU[w] * u[w] - dxU[sw] * u[sw];
+        d->vort[o + c] = p5 * tarear[c] * (dvdxn + dvdxs - dudye - dudyw);
+      }
+  }
+  return 0;
+}

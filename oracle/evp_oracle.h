@@ -42,6 +42,10 @@ int orc_evp_run_bgrid_1d(const evp_b200_grid_t *grid, const double *HTE, const d
 int orc_evp_run_cgrid(const evp_b200_grid_t *grid, const evp_b200_cgrid_t *cgrid, const evp_b200_params_t *params,
                       evp_b200_cfields_t *fields, int nthreads);
 
+/* deformations: ice_dyn_shared.F90:1756-1860 over the T list (ilo:ihi+1, jlo:jhi+1 where iceTmask) */
+int orc_deformations(const evp_b200_grid_t *grid, const int32_t *iceTmask, const double *uvel, const double *vvel,
+                     evp_b200_deform_t *d);
+
 /* NE-corner / vector halo update of nfld fields, the dyn_haloUpdate call of
  * ice_dyn_evp.F90:908-910 (ice_boundary.F90:1066-1760; expectations halochk.F90:530-830).
  * field_loc: 0 center, 1 NE corner; field_type: 0 scalar, 1 vector. */

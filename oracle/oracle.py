@@ -53,6 +53,8 @@ def lib(variant="exact"):
         L.orc_evp_run_bgrid_1d.restype = C.c_int
         L.orc_evp_run_cgrid.argtypes = [C.POINTER(abi.Grid), C.POINTER(abi.CGrid), C.POINTER(abi.Params), C.POINTER(abi.CFields), C.c_int]
         L.orc_evp_run_cgrid.restype = C.c_int
+        L.orc_deformations.argtypes = [C.POINTER(abi.Grid), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(abi.Deform)]
+        L.orc_deformations.restype = C.c_int
         L.orc_halo_update.argtypes = [C.POINTER(abi.Grid), C.POINTER(C.POINTER(C.c_double)), C.c_int, C.c_int, C.c_int]
         L.orc_halo_update.restype = C.c_int
         L.orc_last_error.restype = C.c_char_p
@@ -107,6 +109,17 @@ def evp_run_cgrid(grid, cgrid, params, cfields, nthreads=0, variant="exact"):
     if rc:
         raise RuntimeError("oracle cgrid failed")
     return cfields
+
+
+def deformations(grid, iceTmask, uvel, vvel, d, e_factor, variant="exact"):
+    L = lib(variant)
+    g, kg = abi.make_grid(grid)
+    s, keep = abi.make_deform(d, _npl(grid), e_factor)
+    pd, pi = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    rc = L.orc_deformations(C.byref(g), iceTmask.ctypes.data_as(pi), uvel.ctypes.data_as(pd), vvel.ctypes.data_as(pd), C.byref(s))
+    if rc:
+        raise RuntimeError("oracle deformations: " + L.orc_last_error().decode())
+    return d
 
 
 def halo_update(grid, arrays, field_loc=1, field_type=1, variant="exact"):

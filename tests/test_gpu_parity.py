@@ -221,3 +221,26 @@ def test_errors_are_reported_not_fatal(evp_lib):
     g, f, ids = c4.rank_view(np.array([0, 0, 1, 1], np.int32), 0)
     with pytest.raises(evp_lib.EvpB200Error, match="comm_init"):
         evp_lib.dyn_evp_b200_init(g)
+
+
+@pytest.mark.parametrize("bs", [None, (25, 29)], ids=["1block", "16blocks"])
+def test_deformations_after_loop(oracle_mod, evp_lib, bs):
+    """next row: `deformations` (ice_dyn_shared.F90:1756-1860) from the velocities the loop
+    left on the device, bit-identical to the oracle; cells off the T list keep the caller's values."""
+    c = synth.make_case("gx3", ndte=25, block_size=bs, seed=4)
+    ref = run_oracle(oracle_mod, c)
+    X = c.X
+    tarear = np.where(X["tarea"] > 0, 1.0 / np.where(X["tarea"] > 0, X["tarea"], 1.0), 0.0)
+    mk = lambda: dict({n: synth.scatter(a, c.blocks) for n, a in (("dxU", X["dxU"]), ("dyU", X["dyU"]), ("tarear", tarear))},
+                      **{n: np.full(ref["uvel"].shape, -7.0) for n in abi.DEFORM_OUT})
+    want = oracle_mod.deformations(c.grid, ref["iceTmask"], ref["uvel"], ref["vvel"], mk(), c.params["e_factor"])
+    got, f = mk(), c.copy_fields()
+    evp_lib.dyn_evp_b200_init(c.grid)
+    try:
+        evp_lib.dyn_evp_b200_run(dict(c.params, mode=abi.MODE_EXACT), f)
+        evp_lib.deformations(got, c.params["e_factor"])
+    finally:
+        evp_lib.dyn_evp_b200_finalize()
+    for n in abi.DEFORM_OUT:
+        assert np.array_equal(got[n].view(np.int64), want[n].view(np.int64)), n
+        assert (got[n][ref["iceTmask"] == 0] == -7.0).all(), n
