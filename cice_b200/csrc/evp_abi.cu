@@ -696,11 +696,13 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
   const size_t bblk = g.nblk_elems * sizeof(double), bdom = g.ndom * sizeof(double);
   // host pointer, device array, how it moves: 'i' in, 'r' inout ring, 's' inout T cells the loop owns (N/E ghost incl.),
   // 'n' inout interior, 'z' out: the reference zero-fills the whole block, writes interiors, halo-updates;
-  // 'y' out: zero-filled whole block, interiors written, NOT halo-updated (block ghost cells stay 0)
+  // 'y' out: zero-filled whole block, interiors written, NOT halo-updated (block ghost cells stay 0);
+  // 'R' like 'r' but the reference zero-fills the whole block (padding included) every subcycle before it
+  //     re-interpolates and halo-updates (grid_average_X2YA, ice_grid.F90:4410)
   struct Fld { const double *h; double *dv; char kind; };
   const bool avgstr = (p->visc_method == EVP_B200_VISC_AVG_STRENGTH);
   Fld tab[43] = {
-      {f->uvelE, c.uvelE, 'r'}, {f->vvelE, c.vvelE, 'r'}, {f->uvelN, c.uvelN, 'r'}, {f->vvelN, c.vvelN, 'r'}, {f->uvel, c.uvel, 'r'}, {f->vvel, c.vvel, 'r'},
+      {f->uvelE, c.uvelE, 'r'}, {f->vvelE, c.vvelE, 'R'}, {f->uvelN, c.uvelN, 'R'}, {f->vvelN, c.vvelN, 'r'}, {f->uvel, c.uvel, 'R'}, {f->vvel, c.vvel, 'R'},
       {f->stresspT, c.stresspT, 'r'}, {f->stressmT, c.stressmT, 'r'}, {f->stress12T, c.stress12T, 's'}, {f->stress12U, c.stress12U, 'r'},
       {f->zetax2T, c.zetax2T, 'r'}, {f->etax2T, c.etax2T, 'r'}, {f->etax2U, c.etax2U, avgstr ? '-' : 'y'}, {f->strengthU, c.strengthU, avgstr ? 'y' : '-'},
       {f->divergU, c.divergU, 'y'}, {f->tensionU, c.tensionU, 'y'}, {f->shearU, c.shearU, 'z'}, {f->deltaU, c.deltaU, 'y'},
@@ -764,6 +766,7 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
   for (int q = 0; q < 22; ++q) {
     const Fld &t = tab[q];
     if (t.kind == '-') continue;
+    if (t.kind == 'R' && p->ndte > 0) CK(cudaMemsetAsync(g.cstage[q], 0, bblk, g.stream));
     if (t.kind == 's')
       unpack_f64<<<grid_blocks(g.n_sig), 256, 0, g.stream>>>(g.cstage[q], t.dv, g.d_sig_lin, g.d_sig_dom, g.n_sig);
     else if (t.kind == 'n' || t.kind == 'y')
