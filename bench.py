@@ -35,6 +35,17 @@ METRIC = "EVP grid-cells*subcycles/sec at gx1 (fp64)"
 UNIT = "cell-subcycles/s"
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)
+        e = t.get(kernel) or t.get("fused")
+        return e
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -122,26 +133,32 @@ def cpu_baseline(case, steps, warmup, nthreads=0):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (restated; see module docstring) on the host cores."""
+    """--impl reference: the reference's CPU path (restated; see module docstring) on the host cores, on the
+    same global grid as our arm at this GPU count (weak scaling: px*320 x py*384)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from cice_b200 import synth
+    from cice_b200 import decomp, synth
     wl = args.workload
     base = synth.CONFIGS[wl]
+    world = max(int(os.environ.get("WORLD_SIZE", "1")), args.gpus, 1)
+    px, py = decomp.proc_grid(world, world, world)
+    nx, ny = base["nx"] * px, base["ny"] * py
     # the reference's own block choice for <=16 PEs at gx1 is 40x48 (configuration/scripts/cice_decomp.csh:93-96)
     bs = (40, 48) if wl == "gx1" else (max(base["nx"] // 8, 8), max(base["ny"] // 8, 8))
-    case = synth.make_case(wl, block_size=bs)
+    case = synth.make_case(wl, nx=nx, ny=ny, block_size=bs)
     sec, nth = cpu_baseline(case, args.steps, max(args.warmup, 1))
-    cells = base["nx"] * base["ny"] * case.params["ndte"]
+    cells = nx * ny * case.params["ndte"]
     val = cells / sec
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{wl} {base['nx']}x{base['ny']} B-grid EVP ndte={case.params['ndte']}, blocks {bs[0]}x{bs[1]}, "
-                                   "CPU restatement of the reference loops (Fortran reference not buildable in this image)"},
+            "config": {"workload": f"{wl} {base['nx']}x{base['ny']} per GPU, B-grid EVP ndte={case.params['ndte']}, "
+                                   f"{px}x{py} GPUs, global {nx}x{ny}, box2001 synthetic",
+                       "cpu": f"CPU restatement of the reference loops (oracle port, -O3 AVX2/FMA, OpenMP over {bs[0]}x{bs[1]} blocks); "
+                              "the Fortran reference cannot be built in this image"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": nth, "kind": "port",
-                             "sample": f"{args.steps} full dynamics step(s) of {wl}, ndte={case.params['ndte']}"},
+                             "sample": f"{args.steps} full dynamics step(s) of the {nx}x{ny} grid, ndte={case.params['ndte']}"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -233,6 +250,7 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         per_gpu_cells = base["nx"] * base["ny"]
         nl_step = launches / args.steps
+        traffic = measured_traffic("fused" if args.kernel in ("auto", "fused") else args.kernel)
         # dominant kernel: the subcycle kernel; one launch advances the rank's sub-domain by ndte/launches subcycles
         sub_per_launch = ndte / max(nl_step, 1) if args.kernel != "split" else 0.5
         ach = per_gpu_cells * ndte * ALGO_BYTES_PER_CELL_SUBCYCLE / (kernel_ms * 1e-3) / 1e9
@@ -248,7 +266,8 @@ def run_ours(args):
                         "ms_per_step": e2e_s * 1e3},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                             "traffic": None, "peak_source": peak_src,
+                             "traffic": (traffic or {}).get("dram_bytes_per_launch_cold"), "traffic_detail": traffic,
+                             "peak_source": peak_src,
                              "algorithmic_bytes_per_cell_subcycle": ALGO_BYTES_PER_CELL_SUBCYCLE,
                              "kernel_ms_per_step": kernel_ms, "subcycles_per_launch": sub_per_launch},
                 "wall_s": t_wall}

@@ -244,3 +244,36 @@ def test_deformations_after_loop(oracle_mod, evp_lib, bs):
     for n in abi.DEFORM_OUT:
         assert np.array_equal(got[n].view(np.int64), want[n].view(np.int64)), n
         assert (got[n][ref["iceTmask"] == 0] == -7.0).all(), n
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
+def test_edge_cases_no_ice_and_odd_loops(oracle_mod, evp_lib, kernel):
+    """(a) no ice anywhere: every array comes back exactly as it went in; (b) ndte = 1 and ndte = 7 (odd loops end
+    on the other ping-pong copy) followed by a second loop without a new upload; (c) ndte = 0 is a no-op."""
+    c = synth.make_case("tiny", seed=17)
+    f = c.copy_fields()
+    f["iceTmask"][:] = 0
+    f["iceUmask"][:] = 0
+    before = {k: v.copy() for k, v in f.items()}
+    evp_lib.dyn_evp_b200_init(c.grid)
+    try:
+        evp_lib.dyn_evp_b200_run(dict(c.params, mode=abi.MODE_EXACT, kernel=kernel), f)
+        for n in abi.FIELDS_INOUT:
+            assert np.array_equal(f[n].view(np.int64), before[n].view(np.int64)), n
+        g0 = c.copy_fields()
+        evp_lib.dyn_evp_b200_run(dict(c.params, mode=abi.MODE_EXACT, kernel=kernel, ndte=0), g0)
+        for n in abi.FIELDS_INOUT:
+            assert np.array_equal(g0[n].view(np.int64), c.fields[n].view(np.int64)), n
+        # 1 + 7 subcycles in two loops on resident state == 8 subcycles in one (constants held)
+        p = dict(c.params, mode=abi.MODE_EXACT, kernel=kernel)
+        g1 = c.copy_fields()
+        evp_lib.upload(g1)
+        evp_lib.subcycle(dict(p, ndte=1))
+        evp_lib.subcycle(dict(p, ndte=7))
+        evp_lib.download(g1)
+    finally:
+        evp_lib.dyn_evp_b200_finalize()
+    ref = c.copy_fields()
+    oracle_mod.evp_run_bgrid(c.grid, dict(c.params, ndte=8), ref)
+    # uvel_init is re-taken at the start of each loop, which only matters for revised EVP (revp = 0 here)
+    assert_bitwise(g1, ref)
