@@ -9,6 +9,7 @@
 //   * tripole (u-fold): ghost row ny_global+1 <- -f(nx_global-i, ny_global-1); the top row
 //     ny_global is symmetrised, f <- 0.5*(f(i) - f(nx_global-i)), except the two pole points
 //     i = nx_global/2 and nx_global, which become -f(i)  (ice_boundary.F90:1630-1649, 1689-1722).
+//     (for i > nx_global/2 the reference forms -(0.5*(f(nx_global-i) - f(i))): same value, but a zero keeps that sign)
 // Every output is a function of the pre-update values only, so one staged exchange suffices.
 #include "evp_halo.h"
 
@@ -21,7 +22,7 @@
 
 namespace evp {
 
-enum { OP_COPY = 0, OP_NEG = 1, OP_AVGM = 2 };
+enum { OP_COPY = 0, OP_NEG = 1, OP_AVGM = 2, OP_AVGH = 3 };
 
 #define HFAIL(...) do { snprintf(err, nerr, __VA_ARGS__); return 1; } while (0)
 #define HCK(call)                                                                         \
@@ -86,10 +87,14 @@ __global__ void halo_apply(double *__restrict__ U, double *__restrict__ V, const
     const int op = code[k];
     if (op == OP_NEG) {
       u = -u; v = -v;
-    } else if (op == OP_AVGM) {
+    } else if (op == OP_AVGM || op == OP_AVGH) {
+      // xavg = 0.5*(x1 + isign*x2) with isign = -1, x1 the partner with the lower i (ice_boundary.F90:1641-1646).
+      // The lower partner receives isign*(isign*xavg) = xavg, the upper one isign*xavg: written exactly so, because
+      // -(0.5*(x1-x2)) and 0.5*(x2-x1) differ in the sign of a zero result.
       const double2 b = slot(packbuf, recvbuf, nloc, s2[k]);
-      u = 0.5 * (a.x - b.x);  // 0.5*(x1 + isign*x2), isign = -1   (ice_boundary.F90:1641-1646)
+      u = 0.5 * (a.x - b.x);
       v = 0.5 * (a.y - b.y);
+      if (op == OP_AVGH) { u = -u; v = -v; }
     }
     U[dst[k]] = u;
     V[dst[k]] = v;
@@ -143,9 +148,14 @@ static void enumerate(const std::vector<Rect> &R, int r, int nxg, int nyg, int e
         if (!owner(gi, nyg, e.r1, e.c1)) continue;
         if (gi == nxg / 2 || gi == nxg) {
           e.code = OP_NEG;
-        } else {
+        } else if (gi < nxg / 2) {
           if (!owner(wrapi(nxg - gi), nyg, e.r2, e.c2)) continue;
-          e.code = OP_AVGM;
+          e.code = OP_AVGM;  // s1 = own (lower partner), s2 = mirror
+        } else {
+          // upper partner: s1 = mirror (the lower partner), s2 = own, result negated
+          e.r2 = e.r1; e.c2 = e.c1;
+          if (!owner(wrapi(nxg - gi), nyg, e.r1, e.c1)) continue;
+          e.code = OP_AVGH;
         }
       } else {
         if (!owner(gi, gj, e.r1, e.c1)) continue;

@@ -238,7 +238,7 @@ const char *evp_b200_describe(void);
  * {gi0, gj0, nx, ny} (global index of its first interior cell, interior extent).  Writes up to `cap`
  * entries of 6 ints {dst, src1_rank, src1, src2_rank, src2, op} into `out` (dst/src are indices into
  * the owning rank's (nx+2)-wide, pitch-padded sub-domain array: see evp_b200_dom_pitch; op 0 copy,
- * 1 negate, 2 0.5*(src1 - src2)) and the total count into *n.  Ghost cells the compute kernels fill
+ * 1 negate, 2 0.5*(src1 - src2), 3 -(0.5*(src1 - src2))) and the total count into *n.  Ghost cells the compute kernels fill
  * themselves (on-rank cyclic wrap) are not listed. */
 int evp_b200_halo_plan(int32_t nranks, const int32_t *rects, int32_t rank, int32_t nx_global, int32_t ny_global,
                        int32_t ew_boundary_type, int32_t ns_boundary_type, int32_t *n, int32_t *out, int32_t cap);

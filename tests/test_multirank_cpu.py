@@ -33,14 +33,15 @@ def _worker(rank, world, port, ew, ns, q):
 
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
-        case = synth.make_case("tiny", block_size=(12, 10), seed=21, ew=ew, ns=ns, kmt="none")
+        kmt = "boxislands" if ns == "tripole" else "none"  # land on the fold: zeros whose sign the fold must keep
+        case = synth.make_case("tiny", block_size=(12, 10), seed=21, ew=ew, ns=ns, kmt=kmt)
         owner, _ = decomp.cartesian_owner(case.blocks, world)
         rects = _rects(case, owner, world)
         ewi, nsi = case.grid["ew_boundary_type"], case.grid["ns_boundary_type"]
         nxg, nyg = case.grid["nx_global"], case.grid["ny_global"]
 
         # truth: the oracle's halo update on the undecomposed domain
-        whole = synth.make_case("tiny", seed=21, ew=ew, ns=ns, kmt="none")
+        whole = synth.make_case("tiny", seed=21, ew=ew, ns=ns, kmt=kmt)
         tu, tv = whole.fields["uvel"].copy(), whole.fields["vvel"].copy()
         tu[0, 0, :] = tu[0, -1, :] = np.nan  # ghost rows/cols must come from the update, not from the input
         tu[0, :, 0] = tu[0, :, -1] = np.nan
@@ -102,8 +103,10 @@ def _worker(rank, world, port, ew, ns, q):
                 u, v = a
             elif op == 1:
                 u, v = -a[0], -a[1]
-            else:
+            elif op == 2:
                 u, v = 0.5 * (a[0] - b[0]), 0.5 * (a[1] - b[1])
+            else:
+                u, v = -(0.5 * (a[0] - b[0])), -(0.5 * (a[1] - b[1]))
             dom["uvel"][dst], dom["vvel"][dst] = u, v
 
         bad = 0
@@ -122,7 +125,7 @@ def _worker(rank, world, port, ew, ns, q):
                         if np.isnan(want):
                             ok = np.isnan(got)  # outside a closed edge: untouched on both sides
                         else:
-                            ok = (got == want)
+                            ok = (got == want) and (np.signbit(got) == np.signbit(want))
                         bad += 0 if ok else 1
         q.put((rank, bad, len(plans[rank])))
     finally:
@@ -155,4 +158,4 @@ def test_halo_plan_single_rank_is_empty_without_tripole():
     # ghost row (26 cells incl. corners, negated copies) + top row (24 interior + 2 ghost columns):
     # two pole columns (i = 12, 24; the ghost column i=0 aliases 24) are negated, the rest symmetrised
     assert len(pl) == 52
-    assert (pl[:, 5] == 1).sum() == 26 + 3 and (pl[:, 5] == 2).sum() == 23 and (pl[:, 5] == 0).sum() == 0
+    assert (pl[:, 5] == 1).sum() == 26 + 3 and ((pl[:, 5] == 2) | (pl[:, 5] == 3)).sum() == 23 and (pl[:, 5] == 0).sum() == 0
