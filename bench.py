@@ -29,6 +29,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line (the image sets NCCL_DEBUG=VERSION)
 
 ALGO_BYTES_PER_CELL_SUBCYCLE = 360.0  # 31 doubles read + 14 written
 METRIC = "EVP grid-cells*subcycles/sec at gx1 (fp64)"
@@ -283,18 +284,86 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+C_ALGO_BYTES = 504.0  # C grid: 53 doubles read (6 velocities, 4 stresses, strength, 22 geometry/mask, 20 momentum) + 10 written
+
+
+def run_cgrid(args):
+    """configs[2]: gx1 C-grid EVP (standard_2d), ndte = 600, one GPU; same JSON shape, metric at the C grid."""
+    import torch
+    from cice_b200 import abi, dyn_evp, synth
+    ndte = 600
+    base = synth.CONFIGS[args.workload]
+    cells = base["nx"] * base["ny"]
+    if args.impl == "reference":
+        from oracle import oracle
+        oracle.build()
+        c = synth.make_ccase(args.workload, ndte=ndte, block_size=(40, 48))  # OpenMP over blocks like ice_dyn_evp.F90:940
+        ts = []
+        for it in range(1 + args.steps):
+            f = c.copy_fields()
+            t0 = time.perf_counter()
+            oracle.evp_run_cgrid(c.grid, c.cgrid, c.params, f, nthreads=0, variant="fast")
+            if it:
+                ts.append(time.perf_counter() - t0)
+        sec = float(np.mean(ts))
+        val = cells * ndte / sec
+        print(json.dumps({"impl": "reference", "metric": METRIC.replace("gx1", "gx1 C-grid"), "value": val, "unit": UNIT, "n_gpus": 1,
+                          "steps": args.steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": f"{args.workload} C-grid EVP ndte={ndte}, 40x48 blocks, CPU restatement of the reference loops"},
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"{args.steps} full steps"},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    c = synth.make_ccase(args.workload, ndte=ndte)
+    torch.cuda.set_device(0)
+    dyn_evp.set_device(0)
+    dyn_evp.dyn_evp_b200_init(c.grid)
+    dyn_evp.dyn_evp_b200_init_cgrid(c.cgrid)
+    p = dict(c.params, mode=abi.MODE_FAST if args.mode == "fast" else abi.MODE_EXACT)
+    f = pin(c.copy_fields())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    loop, call = [], []
+    for it in range(max(args.warmup, 3) + args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dyn_evp.dyn_evp_b200_run_cgrid(p, f)
+        call.append(time.perf_counter() - t0)
+        loop.append(dyn_evp.last_loop_ms())
+    loop, call = loop[-args.steps:], call[-args.steps:]
+    ms = float(np.mean(loop))
+    peak, peak_src = measured_peak()
+    ach = cells * ndte * C_ALGO_BYTES / (ms * 1e-3) / 1e9
+    nblk = int(np.prod(c.fields["uvel"].shape))
+    print(json.dumps({"metric": METRIC.replace("gx1", "gx1 C-grid"), "value": cells * ndte / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+                      "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": f"{args.workload} {base['nx']}x{base['ny']} C-grid EVP (standard_2d) ndte={ndte}, 1 GPU, box2001 synthetic",
+                                 "mode": args.mode, "l2": "flushed between timed steps (256 MiB memset)", "layout": dyn_evp.describe()},
+                      "e2e": {"value": cells * ndte / float(np.mean(call)), "unit": UNIT, "h2d_bytes_per_step": 37 * nblk * 8 + 4 * nblk * 4,
+                              "d2h_bytes_per_step": 21 * nblk * 8, "ms_per_step": float(np.mean(call)) * 1e3},
+                      "gpu_launches": int(dyn_evp.last_launches()) * args.steps,
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                                   "peak_source": peak_src, "algorithmic_bytes_per_cell_subcycle": C_ALGO_BYTES,
+                                   "kernels_per_subcycle": 5}}))
+    dyn_evp.dyn_evp_b200_finalize()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "split", "fused", "persistent"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "split", "fused", "persistent", "queue"])
     ap.add_argument("--mode", default="exact", choices=["fast", "exact"])
     ap.add_argument("--workload", default="gx1")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--grid", default="B", choices=["B", "C"], help="C: configs[2], gx1 C-grid EVP, ndte=600 (one GPU)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.grid == "C":
+        run_cgrid(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

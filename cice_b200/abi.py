@@ -13,8 +13,8 @@ BNDY_OPEN, BNDY_CLOSED, BNDY_CYCLIC, BNDY_TRIPOLE = 0, 1, 2, 3
 BNDY_NAMES = {"open": BNDY_OPEN, "closed": BNDY_CLOSED, "cyclic": BNDY_CYCLIC, "tripole": BNDY_TRIPOLE}
 
 MODE_EXACT, MODE_FAST = 0, 1
-KERNEL_AUTO, KERNEL_SPLIT, KERNEL_FUSED, KERNEL_PERSISTENT = 0, 1, 2, 3
-KERNEL_NAMES = {"auto": 0, "split": 1, "fused": 2, "persistent": 3}
+KERNEL_AUTO, KERNEL_SPLIT, KERNEL_FUSED, KERNEL_PERSISTENT, KERNEL_QUEUE = 0, 1, 2, 3, 4
+KERNEL_NAMES = {"auto": 0, "split": 1, "fused": 2, "persistent": 3, "queue": 4}
 
 UNIQUE_ID_BYTES = 128
 

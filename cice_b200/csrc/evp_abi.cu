@@ -128,6 +128,8 @@ struct Ctx {
   bool persist_ok = false;
   std::string persist_why;
   unsigned *d_progress = nullptr;
+  unsigned *d_qprogress = nullptr, *d_qcounter = nullptr;  // KERNEL_QUEUE
+  int q_ntiles = 0, q_nctas = 0;
   int num_sms = 0;
   int fused_variant = 0;
   bool fused_pdl = true;
@@ -168,7 +170,7 @@ static int free_all() {
   for (auto &p : g.dstr) F(p);
   F(g.dmaskT); F(g.dmaskU);
   for (auto &p : g.stage) F(p);
-  F(g.stage_mask); F(g.d_gsrc); F(g.d_progress);
+  F(g.stage_mask); F(g.d_gsrc); F(g.d_progress); F(g.d_qprogress); F(g.d_qcounter);
   F(g.d_uv_lin); F(g.d_uv_dom); F(g.d_sig_lin); F(g.d_sig_dom); F(g.d_int_lin); F(g.d_int_dom);
   g.halo.release();
   if (g.ev0) cudaEventDestroy(g.ev0);
@@ -365,6 +367,12 @@ static int do_init(const evp_b200_grid_t *gr) {
     g.pplan.progress = g.d_progress;
   }
 
+  // KERNEL_QUEUE: progress counter per 31x7 patch, two resident CTAs per SM
+  g.q_ntiles = ((nx + 30) / 31) * ((ny + 6) / 7);
+  g.q_nctas = std::min(2 * g.num_sms, g.q_ntiles);
+  CK(cudaMalloc(&g.d_qprogress, sizeof(unsigned) * g.q_ntiles));
+  CK(cudaMalloc(&g.d_qcounter, sizeof(unsigned)));
+
   CK(cudaStreamSynchronize(g.stream));
   g.inited = true;
   char buf[512], pbuf[200];
@@ -480,6 +488,19 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
     CK(cudaMemsetAsync(g.p2p.d_done, 0, sizeof(unsigned long long), g.stream));
     CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -1, g.stream) : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -1, g.stream));
     ++nl;
+  }
+  if (kern == EVP_B200_KERNEL_QUEUE) {
+    if (g.halo.n_dst != 0 || !g.halo.peers.empty())
+      return fail("evp_b200_subcycle: the queue kernel needs a halo that is an on-rank wrap (one rank, no tripole fold)");
+    if (p->ndte > 0) {
+      CK(cudaMemsetAsync(g.d_qprogress, 0, sizeof(unsigned) * g.q_ntiles, g.stream));
+      CK(cudaMemsetAsync(g.d_qcounter, 0, sizeof(unsigned), g.stream));
+      CK(exact ? exact::launch_queue(g.dom, k, p->ndte, g.d_qprogress, g.d_qcounter, g.q_nctas, g.stream)
+               : fast::launch_queue(g.dom, k, p->ndte, g.d_qprogress, g.d_qcounter, g.q_nctas, g.stream));
+    }
+    *cur_end = p->ndte & 1;
+    *launches = p->ndte > 0 ? 1 : 0;
+    return 0;
   }
   for (int ksub = 0; ksub < p->ndte; ++ksub) {
     if (p2p) {

@@ -109,6 +109,7 @@ struct PersistPlan {
   cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl); \
   cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, cudaStream_t s); \
   cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s); \
+  cudaError_t launch_queue(const Dom &d, const KParams &p, int ndte, unsigned *progress, unsigned *counter, int nctas, cudaStream_t s); \
   cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \
   }
 EVP_DECLARE_LAUNCHERS(exact)

@@ -410,6 +410,112 @@ __global__ void __launch_bounds__(F4X *F4Y * 4, 1) fused4_kernel(const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// KERNEL_QUEUE: the fused patches of ALL subcycles as one work queue in a single launch.
+// Item w = (subcycle w / ntiles, patch w % ntiles).  A CTA claims the next item with an atomic counter, waits
+// until the patch itself and its (up to 8, cyclically wrapped) neighbour patches have published the previous
+// subcycle (per-patch progress counters, release/acquire through L2), then does exactly what fused_kernel does.
+// The same wait also covers the write-after-read hazard of the ping-pong copies.  Items are claimed in order,
+// so the oldest unfinished item always has its dependencies met: no deadlock as long as all CTAs are resident
+// (cooperative launch).  No kernel boundaries, no partial last wave, subcycles overlap at the patch level.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int QBX = 32, QBY = 8;
+__global__ void __launch_bounds__(QBX *QBY, 2) queue_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
+                                                            int ndte, int ntx, int nty, unsigned *__restrict__ progress,
+                                                            unsigned *__restrict__ counter) {
+  __shared__ double sstr[8][QBY][QBX];
+  __shared__ unsigned s_item;
+  const int tx = threadIdx.x, ty = threadIdx.y, t = ty * QBX + tx;
+  const unsigned ntiles = (unsigned)(ntx * nty), nitems = ntiles * (unsigned)ndte;
+  for (;;) {
+    if (t == 0) s_item = atomicAdd(counter, 1u);
+    __syncthreads();
+    const unsigned item = s_item;
+    if (item >= nitems) break;
+    const int ksub = (int)(item / ntiles), tile = (int)(item % ntiles);
+    const int tbx = tile % ntx, tby = tile / ntx;
+    const int cur = ksub & 1, nxt = cur ^ 1;
+    if (ksub > 0 && t < 9) {
+      int nx_ = tbx + (t % 3) - 1, ny_ = tby + (t / 3) - 1;
+      if (d.wrap_ew) nx_ = (nx_ + ntx) % ntx;
+      if (d.wrap_ns) ny_ = (ny_ + nty) % nty;
+      if (nx_ >= 0 && nx_ < ntx && ny_ >= 0 && ny_ < nty) {
+        const unsigned *f = progress + ny_ * ntx + nx_;
+        while (ld_acquire_gpu(f) < (unsigned)ksub) {}
+      }
+    }
+    __syncthreads();
+
+    const int i = 1 + tbx * (QBX - 1) + tx, j = 1 + tby * (QBY - 1) + ty;
+    const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
+    const size_t c = at(d, inT ? i : 1, inT ? j : 1);
+    double str[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double uc = 0.0, vc = 0.0;
+    if (inT && d.maskT[c]) {
+      const size_t w = c - 1, s = c - d.ld, sw = s - 1;
+      // state written by other CTAs inside this launch: read through L2 (ld.cg), never a stale L1 line
+      const double *__restrict__ U = d.u[cur];
+      const double *__restrict__ V = d.v[cur];
+      uc = __ldcg(U + c); vc = __ldcg(V + c);
+      Sigma sg;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        sg.p[q] = __ldcg(d.sig[cur][q] + c);
+        sg.m[q] = __ldcg(d.sig[cur][4 + q] + c);
+        sg.s12[q] = __ldcg(d.sig[cur][8 + q] + c);
+      }
+      stress_point(uc, vc, __ldcg(U + w), __ldcg(V + w), __ldcg(U + s), __ldcg(V + s), __ldcg(U + sw), __ldcg(V + sw), d.dxT[c],
+                   d.dyT[c], d.dxhy[c], d.dyhx[c], d.cxp[c], d.cyp[c], d.cxm[c], d.cym[c], d.DminTarea[c], d.strength[c], k, sg, str);
+      const bool own = (tx < QBX - 1 || i == d.nx + 1) && (ty < QBY - 1 || j == d.ny + 1);
+      if (own) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __stcg(d.sig[nxt][q] + c, sg.p[q]);
+          __stcg(d.sig[nxt][4 + q] + c, sg.m[q]);
+          __stcg(d.sig[nxt][8 + q] + c, sg.s12[q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sstr[q][ty][tx] = str[q];
+    __syncthreads();
+    if (tx < QBX - 1 && ty < QBY - 1 && i <= d.nx && j <= d.ny && d.maskU[c]) {
+      if (!d.maskT[c]) { uc = __ldcg(d.u[cur] + c); vc = __ldcg(d.v[cur] + c); }
+      const UOut o = stepu_point(uc, vc, d.cdn[c], d.aiu[c], d.uocn[c], d.vocn[c], d.waterx[c], d.watery[c], d.forcex[c],
+                                 d.forcey[c], d.umassdti[c], d.fm[c], d.uarear[c], d.TbU[c], d.uinit[c], d.vinit[c],
+                                 sstr[0][ty][tx], sstr[1][ty][tx + 1], sstr[2][ty + 1][tx], sstr[3][ty + 1][tx + 1],
+                                 sstr[4][ty][tx], sstr[5][ty + 1][tx], sstr[6][ty][tx + 1], sstr[7][ty + 1][tx + 1], k);
+      store_uv(d, d.u[nxt], d.v[nxt], i, j, o.u, o.v);
+      if (ksub == ndte - 1) {
+        d.strintx[c] = o.strintx;
+        d.strinty[c] = o.strinty;
+        d.taubx[c] = o.taubx;
+        d.tauby[c] = o.tauby;
+      }
+    }
+    __syncthreads();  // every store of the patch is issued; also protects sstr and s_item for the next item
+    if (t == 0) {
+      __threadfence();
+      st_release_gpu(progress + tile, (unsigned)(ksub + 1));
+    }
+  }
+}
+
+cudaError_t launch_queue(const Dom &d, const KParams &p, int ndte, unsigned *progress, unsigned *counter, int nctas, cudaStream_t s) {
+  int ntx = (d.nx + QBX - 2) / (QBX - 1), nty = (d.ny + QBY - 2) / (QBY - 1);
+  void *args[] = {(void *)&d, (void *)&p, (void *)&ndte, (void *)&ntx, (void *)&nty, (void *)&progress, (void *)&counter};
+  return cudaLaunchCooperativeKernel((const void *)queue_kernel, dim3(nctas), dim3(QBX, QBY), args, 0, s);
+}
+
 template <int FBX, int FBY, int MINB, bool HOIST = false>
 static cudaError_t launch_fused_t(const Dom &d, const KParams &p, int cur, cudaStream_t s, bool pdl) {
   dim3 b(FBX, FBY), g((d.nx + FBX - 2) / (FBX - 1), (d.ny + FBY - 2) / (FBY - 1));

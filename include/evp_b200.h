@@ -63,7 +63,9 @@ enum {
   EVP_B200_KERNEL_AUTO       = 0,
   EVP_B200_KERNEL_SPLIT      = 1,  /* stress kernel + stepu kernel per subcycle (first correct path) */
   EVP_B200_KERNEL_FUSED      = 2,  /* one fused stress+stepu kernel per subcycle, CUDA-graphed */
-  EVP_B200_KERNEL_PERSISTENT = 3   /* all ndte subcycles in one cooperative launch, state on chip */
+  EVP_B200_KERNEL_PERSISTENT = 3,  /* all ndte subcycles in one cooperative launch, state on chip */
+  EVP_B200_KERNEL_QUEUE      = 4   /* all ndte subcycles in one launch: the fused patches of every subcycle form one
+                                      work queue, ordered by per-patch progress counters instead of kernel boundaries */
 };
 
 /*

@@ -16,8 +16,8 @@ from tests.util import run_oracle, run_gpu, assert_bitwise, assert_close
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
-KERNELS = [abi.KERNEL_SPLIT, abi.KERNEL_FUSED, abi.KERNEL_PERSISTENT]
-KNAME = {abi.KERNEL_SPLIT: "split", abi.KERNEL_FUSED: "fused", abi.KERNEL_PERSISTENT: "persistent"}
+KERNELS = [abi.KERNEL_SPLIT, abi.KERNEL_FUSED, abi.KERNEL_PERSISTENT, abi.KERNEL_QUEUE]
+KNAME = {abi.KERNEL_SPLIT: "split", abi.KERNEL_FUSED: "fused", abi.KERNEL_PERSISTENT: "persistent", abi.KERNEL_QUEUE: "queue"}
 
 
 @pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
@@ -147,7 +147,7 @@ def test_large_grid_properties(evp_lib):
     # the on-chip persistent kernel cannot hold 7300 cells per SM: it must refuse, not fall back silently
     with pytest.raises(evp_lib.EvpB200Error, match="persistent kernel unavailable"):
         run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_PERSISTENT)
-    outs = [run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=k) for k in (abi.KERNEL_SPLIT, abi.KERNEL_FUSED, abi.KERNEL_AUTO)]
+    outs = [run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=k) for k in (abi.KERNEL_SPLIT, abi.KERNEL_FUSED, abi.KERNEL_QUEUE, abi.KERNEL_AUTO)]
     for o in outs[1:]:
         assert_bitwise(o, outs[0])
     o = outs[0]
