@@ -132,6 +132,7 @@ struct Ctx {
   int q_ntiles = 0, q_nctas = 0;
   int num_sms = 0;
   int fused_variant = 0;
+  int strip_m = 1;  // chunks per CTA of strip_kernel (fused_variant 30)
   bool fused_pdl = true;
 };
 static Ctx g;
@@ -357,10 +358,26 @@ static int do_init(const evp_b200_grid_t *gr) {
   CK(cudaStreamSynchronize(g.stream));
   if (g.p2p.setup(g_comm, g.halo, g.dshare, g.ndom, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, g_err, sizeof g_err)) return 1;
 
+  // fused kernel form.  Sub-domains whose arrays fit the 126 MB L2 run latency-bound: both masks requested at once and the
+  // IEEE division / square-root expansions of the four corners interleaved (variant 23).  Larger ones stream from HBM and
+  // want every operand in flight early: speculative T-cell loads + momentum operands through cp.async (variant 19).
+  // Measured on B200 (profiles/r1_fused_variants.txt): gx1 2.27 (v23) vs 2.39 (v19) ms per step; 3600x2400 164 (v19) vs 182 (v16).
+  g.fused_variant = (g.ndom * sizeof(double) * 50 > (size_t)96 << 20) ? 19 : 23;
   if (const char *e = getenv("EVP_B200_FUSED_VARIANT")) g.fused_variant = atoi(e);
   if (const char *e = getenv("EVP_B200_PDL")) g.fused_pdl = (e[0] != '0');
-  // ---- persistent tiling ---------------------------------------------------------------------------
   CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, g.device));
+  {
+    // strip_kernel: chunks per CTA.  cost = waves of co-resident CTAs (2 per SM) x work per CTA (m chunks + prologue)
+    const int slots = 2 * g.num_sms, ntx = (nx + 30) / 31;
+    double best = 0;
+    for (int m = 1; m <= 8; ++m) {
+      const long ctas = (long)ntx * ((ny + 8 * m - 2) / (8 * m - 1));
+      const double cost = (double)((ctas + slots - 1) / slots) * (m + 0.5);
+      if (m == 1 || cost < best) { best = cost; g.strip_m = m; }
+    }
+    if (const char *e = getenv("EVP_B200_STRIP_M")) g.strip_m = std::max(1, atoi(e));
+  }
+  // ---- persistent tiling ---------------------------------------------------------------------------
   plan_persist();
   if (g.persist_ok) {
     CK(cudaMalloc(&g.d_progress, sizeof(unsigned) * g.pplan.ntx * g.pplan.nty));
@@ -486,7 +503,7 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
   const bool p2p = g.p2p.enabled && kern == EVP_B200_KERNEL_FUSED;
   if (p2p) {
     CK(cudaMemsetAsync(g.p2p.d_done, 0, sizeof(unsigned long long), g.stream));
-    CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -1, g.stream) : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -1, g.stream));
+    CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -1, 0, 0, g.stream) : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -1, 0, 0, g.stream));
     ++nl;
   }
   if (kern == EVP_B200_KERNEL_QUEUE) {
@@ -503,9 +520,10 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
     return 0;
   }
   for (int ksub = 0; ksub < p->ndte; ++ksub) {
+    const int last = (ksub == p->ndte - 1);
     if (p2p) {
-      CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, g.stream)
-               : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, g.stream));
+      CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last, g.fused_variant, g.stream)
+               : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last, g.fused_variant, g.stream));
       cur ^= 1;
       ++nl;
       continue;
@@ -515,8 +533,12 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
       CK(exact ? exact::launch_stepu(g.dom, k, cur, g.stream) : fast::launch_stepu(g.dom, k, cur, g.stream));
       nl += 2;
     } else if (kern == EVP_B200_KERNEL_FUSED) {
-      CK(exact ? exact::launch_fused(g.dom, k, cur, g.stream, g.fused_variant, g.fused_pdl)
-               : fast::launch_fused(g.dom, k, cur, g.stream, g.fused_variant, g.fused_pdl));
+      if (g.fused_variant == 30)
+        CK(exact ? exact::launch_strip(g.dom, k, cur, g.strip_m, g.stream, g.fused_pdl, last)
+                 : fast::launch_strip(g.dom, k, cur, g.strip_m, g.stream, g.fused_pdl, last));
+      else
+        CK(exact ? exact::launch_fused(g.dom, k, cur, g.stream, g.fused_variant, g.fused_pdl, last)
+                 : fast::launch_fused(g.dom, k, cur, g.stream, g.fused_variant, g.fused_pdl, last));
       cur ^= 1;
       nl += 1;
     } else {
@@ -528,8 +550,8 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
     nl += hl;
   }
   if (p2p) {
-    CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -2 - p->ndte, g.stream)
-             : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -2 - p->ndte, g.stream));
+    CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -2 - p->ndte, 0, 0, g.stream)
+             : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -2 - p->ndte, 0, 0, g.stream));
     ++nl;
   }
   *cur_end = cur;

@@ -25,7 +25,9 @@
 namespace evp {
 namespace EVP_NS {
 
-__device__ __forceinline__ size_t at(const Dom &d, int i, int j) { return (size_t)j * d.ld + i; }
+// cell index inside a dom array; init refuses sub-domains of 2^31 cells or more, so 32 bits are enough and every
+// access costs one IMAD.WIDE instead of a 64-bit add pair
+__device__ __forceinline__ int at(const Dom &d, int i, int j) { return j * d.ld + i; }
 
 // store a new velocity and, where the ghost ring aliases the rank's own interior (cyclic direction
 // entirely local), the ghost copies too: the on-rank part of dyn_haloUpdate (ice_dyn_evp.F90:908-910)
@@ -44,7 +46,7 @@ __device__ __forceinline__ void store_uv(const Dom &d, double *__restrict__ U, d
   if (d.wrap_ns && d.ny == 1) { U[at(d, i, 0)] = un; V[at(d, i, 0)] = vn; }
 }
 
-__device__ __forceinline__ void load_sigma(const Dom &d, int b, size_t c, Sigma &s) {
+__device__ __forceinline__ void load_sigma(const Dom &d, int b, int c, Sigma &s) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     s.p[q] = d.sig[b][q][c];
@@ -52,7 +54,7 @@ __device__ __forceinline__ void load_sigma(const Dom &d, int b, size_t c, Sigma 
     s.s12[q] = d.sig[b][8 + q][c];
   }
 }
-__device__ __forceinline__ void store_sigma(const Dom &d, int b, size_t c, const Sigma &s) {
+__device__ __forceinline__ void store_sigma(const Dom &d, int b, int c, const Sigma &s) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     d.sig[b][q][c] = s.p[q];
@@ -63,7 +65,7 @@ __device__ __forceinline__ void store_sigma(const Dom &d, int b, size_t c, const
 
 __device__ __forceinline__ void stress_at(const Dom &d, const KParams &k, int cur, int i, int j, Sigma &sg,
                                           double (&str)[8]) {
-  const size_t c = at(d, i, j), w = c - 1, s = c - d.ld, sw = s - 1;
+  const int c = at(d, i, j), w = c - 1, s = c - d.ld, sw = s - 1;
   const double *__restrict__ U = d.u[cur];
   const double *__restrict__ V = d.v[cur];
   load_sigma(d, cur, c, sg);
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(256) stress_kernel(const __grid_constant__ Dom
   const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > d.nx + 1 || j > d.ny + 1) return;
-  const size_t c = at(d, i, j);
+  const int c = at(d, i, j);
   double str[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (d.maskT[c]) {
     Sigma sg;
@@ -97,9 +99,9 @@ __global__ void __launch_bounds__(256) stepu_kernel(const __grid_constant__ Dom 
   const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > d.nx || j > d.ny) return;
-  const size_t c = at(d, i, j);
+  const int c = at(d, i, j);
   if (!d.maskU[c]) return;
-  const size_t e = c + 1, n = c + d.ld, ne = n + 1;
+  const int e = c + 1, n = c + d.ld, ne = n + 1;
   const UOut o = stepu_point(d.u[cur][c], d.v[cur][c], d.cdn[c], d.aiu[c], d.uocn[c], d.vocn[c], d.waterx[c],
                              d.watery[c], d.forcex[c], d.forcey[c], d.umassdti[c], d.fm[c], d.uarear[c], d.TbU[c],
                              d.uinit[c], d.vinit[c], d.str[0][c], d.str[1][e], d.str[2][n], d.str[3][ne],
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(256) deform_kernel(const __grid_constant__ Dom
   const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > d.nx + 1 || j > d.ny + 1) return;
-  const size_t c = at(d, i, j), w = c - 1, s = c - d.ld, sw = s - 1;
+  const int c = at(d, i, j), w = c - 1, s = c - d.ld, sw = s - 1;
   if (!d.maskT[c]) return;
   const double ucc = U[c], vcc = V[c], uee = U[w], vee = V[w], use_ = U[s], vse = V[s], une = U[sw], vne = V[sw];
   const double dxT = d.dxT[c], dyT = d.dyT[c], cxp = d.cxp[c], cyp = d.cyp[c], cxm = d.cxm[c], cym = d.cym[c];
@@ -209,10 +211,148 @@ __device__ __forceinline__ int edge_index(const Dom &d, int i, int j) {
   return 2 * d.nx + (d.ny - 2) + (j - 2);
 }
 
-template <int FBX, int FBY, int MINB, bool HOIST, bool P2P = false>
+// operands of one U point.  uvel_init/vvel_init enter stepu only as revp * uvel_init (ice_dyn_shared.F90:957-958);
+// in classic EVP revp = 0 and the product is a zero that can change the sum brlx*uold + 0 only when that sum is
+// itself a zero, so the two arrays are read only then (or when revp != 0): same bits, 16 B per point less traffic.
+__device__ __forceinline__ void load_uin(const Dom &d, const KParams &k, int cur, int c, double (&uin)[16]) {
+  uin[0] = d.u[cur][c]; uin[1] = d.v[cur][c]; uin[2] = d.cdn[c]; uin[3] = d.aiu[c]; uin[4] = d.uocn[c]; uin[5] = d.vocn[c];
+  uin[6] = d.waterx[c]; uin[7] = d.watery[c]; uin[8] = d.forcex[c]; uin[9] = d.forcey[c]; uin[10] = d.umassdti[c];
+  uin[11] = d.fm[c]; uin[12] = d.uarear[c]; uin[13] = d.TbU[c];
+  uin[14] = 0.0; uin[15] = 0.0;
+  if (k.revp != 0.0 || uin[0] == 0.0 || uin[1] == 0.0) { uin[14] = d.uinit[c]; uin[15] = d.vinit[c]; }
+}
+
+// loads the compiler may not sink into the branch that consumes them (asm volatile): the speculative form of the
+// fused kernel issues every operand load of a cell at once, without waiting for the ice mask, so that a CTA pays
+// one L2 round trip instead of four (mask U -> mask T -> stress operands -> momentum operands)
+__device__ __forceinline__ double ld_f64(const double *p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_nc_f64(const double *p) {  // never written while the loop runs
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned ld_nc_u8(const unsigned char *p) {
+  unsigned v;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+// 8-byte asynchronous global -> shared copy (LDGSTS): the momentum operands travel while the stresses are relaxed
+__device__ __forceinline__ void cp_async8(double *smem, const double *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// The speculative body of fused_kernel (SPEC = true, the default): same arithmetic, same ownership rules, but
+//  * every operand of the T cell is requested before the ice masks are known (addresses are always inside the dom);
+//  * static operands (geometry, strength, masks) and the momentum operands are requested BEFORE the programmatic
+//    grid dependency is resolved, i.e. while the previous subcycle's kernel is still draining;
+//  * the 12 momentum operands go global -> shared with cp.async and are picked up after the CTA barrier.
+constexpr int NUOP = 12;
+// SPEC bit 0: speculative T-cell operand loads; bit 1: momentum operands through cp.async
+template <int FBX, int FBY, bool P2P, int SPEC>
+__device__ __forceinline__ void fused_spec_body(const Dom &d, const KParams &k, int cur, const P2PParams &pp, int last, int i, int j,
+                                                bool inT, int c, double (&sstr)[8][FBY][FBX]) {
+  constexpr bool SPT = (SPEC & 1) != 0, CPU = (SPEC & 2) != 0, IL = (SPEC & 4) != 0;  // bit 2: interleaved div/sqrt
+  __shared__ double sU[CPU ? NUOP : 1][FBY * FBX];
+  const int tx = threadIdx.x, ty = threadIdx.y, t = ty * FBX + tx;
+  const int nxt = cur ^ 1;
+  const bool uspot = tx < FBX - 1 && ty < FBY - 1 && i <= d.nx && j <= d.ny;
+  if (CPU) {
+    if (uspot) {
+      const double *src[NUOP] = {d.cdn, d.aiu, d.uocn, d.vocn, d.waterx, d.watery, d.forcex, d.forcey, d.umassdti, d.fm, d.uarear, d.TbU};
+#pragma unroll
+      for (int q = 0; q < NUOP; ++q) cp_async8(&sU[q][t], src[q] + c);
+    }
+    cp_async_commit();
+  }
+  const unsigned mT = ld_nc_u8(d.maskT + c), mU = ld_nc_u8(d.maskU + c);
+  double dxT, dyT, dxhy, dyhx, cxp, cyp, cxm, cym, dmin, strength;
+  if (SPT) {
+    dxT = ld_nc_f64(d.dxT + c); dyT = ld_nc_f64(d.dyT + c); dxhy = ld_nc_f64(d.dxhy + c); dyhx = ld_nc_f64(d.dyhx + c);
+    cxp = ld_nc_f64(d.cxp + c); cyp = ld_nc_f64(d.cyp + c); cxm = ld_nc_f64(d.cxm + c); cym = ld_nc_f64(d.cym + c);
+    dmin = ld_nc_f64(d.DminTarea + c); strength = ld_nc_f64(d.strength + c);
+  }
+#if EVP_USE_PDL
+  cudaGridDependencySynchronize();
+#endif
+  const int w = c - 1, s = c - d.ld, sw = s - 1;
+  const double *__restrict__ U = d.u[cur];
+  const double *__restrict__ V = d.v[cur];
+  double ucc, vcc;
+  double str[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (SPT) {
+    ucc = ld_f64(U + c); vcc = ld_f64(V + c);
+    const double uee = ld_f64(U + w), vee = ld_f64(V + w);
+    const double use_ = ld_f64(U + s), vse = ld_f64(V + s), une = ld_f64(U + sw), vne = ld_f64(V + sw);
+    Sigma sg;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      sg.p[q] = ld_f64(d.sig[cur][q] + c);
+      sg.m[q] = ld_f64(d.sig[cur][4 + q] + c);
+      sg.s12[q] = ld_f64(d.sig[cur][8 + q] + c);
+    }
+    if (inT && mT) {
+      stress_point<IL>(ucc, vcc, uee, vee, use_, vse, une, vne, dxT, dyT, dxhy, dyhx, cxp, cyp, cxm, cym, dmin, strength, k, sg, str);
+      const bool own = (tx < FBX - 1 || i == d.nx + 1) && (ty < FBY - 1 || j == d.ny + 1);
+      if (own) store_sigma(d, nxt, c, sg);
+    }
+  } else {
+    ucc = U[c]; vcc = V[c];
+    if (inT && mT) {
+      Sigma sg;
+      load_sigma(d, cur, c, sg);
+      stress_point<IL>(ucc, vcc, U[w], V[w], U[s], V[s], U[sw], V[sw], d.dxT[c], d.dyT[c], d.dxhy[c], d.dyhx[c],
+                       d.cxp[c], d.cyp[c], d.cxm[c], d.cym[c], d.DminTarea[c], d.strength[c], k, sg, str);
+      const bool own = (tx < FBX - 1 || i == d.nx + 1) && (ty < FBY - 1 || j == d.ny + 1);
+      if (own) store_sigma(d, nxt, c, sg);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) sstr[q][ty][tx] = str[q];
+  if (CPU) cp_async_wait_all();  // own copies only: each thread reads back what it requested itself
+  __syncthreads();
+  if (uspot && mU) {
+    double uo[NUOP];
+    if (CPU) {
+#pragma unroll
+      for (int q = 0; q < NUOP; ++q) uo[q] = sU[q][t];
+    } else {
+      uo[0] = d.cdn[c]; uo[1] = d.aiu[c]; uo[2] = d.uocn[c]; uo[3] = d.vocn[c]; uo[4] = d.waterx[c]; uo[5] = d.watery[c];
+      uo[6] = d.forcex[c]; uo[7] = d.forcey[c]; uo[8] = d.umassdti[c]; uo[9] = d.fm[c]; uo[10] = d.uarear[c]; uo[11] = d.TbU[c];
+    }
+    double ui = 0.0, vi = 0.0;
+    if (k.revp != 0.0 || ucc == 0.0 || vcc == 0.0) { ui = d.uinit[c]; vi = d.vinit[c]; }  // see load_uin
+    const UOut o = stepu_point<IL>(ucc, vcc, uo[0], uo[1], uo[2], uo[3], uo[4], uo[5], uo[6], uo[7], uo[8], uo[9], uo[10], uo[11], ui, vi,
+                               sstr[0][ty][tx], sstr[1][ty][tx + 1], sstr[2][ty + 1][tx], sstr[3][ty + 1][tx + 1], sstr[4][ty][tx],
+                               sstr[5][ty + 1][tx], sstr[6][ty][tx + 1], sstr[7][ty + 1][tx + 1], k);
+    store_uv(d, d.u[nxt], d.v[nxt], i, j, o.u, o.v);
+    if (last) {
+      d.strintx[c] = o.strintx;
+      d.strinty[c] = o.strinty;
+      d.taubx[c] = o.taubx;
+      d.tauby[c] = o.tauby;
+    }
+    if (P2P && (i == 1 || i == d.nx || j == 1 || j == d.ny)) {
+      const int e = edge_index(d, i, j);
+      for (int q = pp.push_start[e]; q < pp.push_start[e + 1]; ++q) {
+        const int pr = pp.push_peer[q];
+        const int dst = pp.push_dst[q];
+        pp.peer_u[nxt][pr][dst] = o.u;
+        pp.peer_v[nxt][pr][dst] = o.v;
+      }
+    }
+  }
+}
+
+template <int FBX, int FBY, int MINB, bool HOIST, bool P2P = false, int SPEC = 0>
 __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_constant__ Dom d,
                                                                 const __grid_constant__ KParams k, int cur,
-                                                                const __grid_constant__ P2PParams pp, int ksub) {
+                                                                const __grid_constant__ P2PParams pp, int ksub, int last) {
   __shared__ double sstr[8][FBY][FBX];
   const int tx = threadIdx.x, ty = threadIdx.y;
   int tbx = blockIdx.x, tby = blockIdx.y;
@@ -245,7 +385,10 @@ __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_cons
     __syncthreads();
   }
   const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
-  const size_t c = at(d, inT ? i : 1, inT ? j : 1);
+  const int c = at(d, inT ? i : 1, inT ? j : 1);
+  if (SPEC) {
+    fused_spec_body<FBX, FBY, P2P, SPEC>(d, k, cur, pp, last, i, j, inT, c, sstr);
+  } else {
 #if EVP_USE_PDL
   // programmatic dependent launch: everything above overlaps the previous subcycle's tail
   cudaGridDependencySynchronize();
@@ -256,9 +399,7 @@ __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_cons
   const bool doU = tx < FBX - 1 && ty < FBY - 1 && i <= d.nx && j <= d.ny && d.maskU[c];
   double uin[16];
   if (HOIST && doU) {
-    uin[0] = d.u[cur][c]; uin[1] = d.v[cur][c]; uin[2] = d.cdn[c]; uin[3] = d.aiu[c]; uin[4] = d.uocn[c]; uin[5] = d.vocn[c];
-    uin[6] = d.waterx[c]; uin[7] = d.watery[c]; uin[8] = d.forcex[c]; uin[9] = d.forcey[c]; uin[10] = d.umassdti[c];
-    uin[11] = d.fm[c]; uin[12] = d.uarear[c]; uin[13] = d.TbU[c]; uin[14] = d.uinit[c]; uin[15] = d.vinit[c];
+    load_uin(d, k, cur, c, uin);
   }
 
   double str[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -275,19 +416,21 @@ __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_cons
 
   if (doU) {
     if (!HOIST) {
-      uin[0] = d.u[cur][c]; uin[1] = d.v[cur][c]; uin[2] = d.cdn[c]; uin[3] = d.aiu[c]; uin[4] = d.uocn[c]; uin[5] = d.vocn[c];
-      uin[6] = d.waterx[c]; uin[7] = d.watery[c]; uin[8] = d.forcex[c]; uin[9] = d.forcey[c]; uin[10] = d.umassdti[c];
-      uin[11] = d.fm[c]; uin[12] = d.uarear[c]; uin[13] = d.TbU[c]; uin[14] = d.uinit[c]; uin[15] = d.vinit[c];
+      load_uin(d, k, cur, c, uin);
     }
     const UOut o = stepu_point(uin[0], uin[1], uin[2], uin[3], uin[4], uin[5], uin[6], uin[7], uin[8], uin[9], uin[10], uin[11],
                                uin[12], uin[13], uin[14], uin[15], sstr[0][ty][tx], sstr[1][ty][tx + 1],
                                sstr[2][ty + 1][tx], sstr[3][ty + 1][tx + 1], sstr[4][ty][tx], sstr[5][ty + 1][tx],
                                sstr[6][ty][tx + 1], sstr[7][ty + 1][tx + 1], k);
     store_uv(d, d.u[nxt], d.v[nxt], i, j, o.u, o.v);
-    d.strintx[c] = o.strintx;
-    d.strinty[c] = o.strinty;
-    d.taubx[c] = o.taubx;
-    d.tauby[c] = o.tauby;
+    if (last) {
+      // the loop overwrites these every subcycle and nothing reads them in between (ice_dyn_shared.F90:948-965);
+      // only the last subcycle's values survive, as in the reference's own 1-D solver (calc_diag_1d, ice_dyn_core1d.F90:607)
+      d.strintx[c] = o.strintx;
+      d.strinty[c] = o.strinty;
+      d.taubx[c] = o.taubx;
+      d.tauby[c] = o.tauby;
+    }
     if (P2P && (i == 1 || i == d.nx || j == 1 || j == d.ny)) {
       // this point is a ghost cell of up to three neighbour GPUs: store it there over NVLink right away, so the
       // traffic is spread over the kernel and long acknowledged when the hand-over fence below is issued
@@ -300,6 +443,7 @@ __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_cons
       }
     }
   }
+  }  // !SPEC
   if (P2P && edge_tile) {
     // Hand-over.  Every edge CTA counts itself done with gpu-scope ordering (a system-scope fence per CTA costs
     // ~3 us per kernel).  The CTA that arrives last issues the ONE system-scope fence -- cumulative over the NVLink
@@ -320,6 +464,85 @@ __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_cons
     }
   }
   if (tl && tx == 0 && ty == 0) atomicMax(tl + 1, gtime());
+}
+
+// ---------------------------------------------------------------------------------------------
+// KERNEL_FUSED, strip form (the default without in-kernel NVLink halo).
+// A CTA of 32 x 8 threads walks up a strip of 31 U columns in `m` chunks of 8 T rows.  The `str` terms of a chunk's
+// top T row stay in shared memory (row 0) for the next chunk, so inside a strip no T row is relaxed twice: a CTA
+// relaxes 8m T rows and advances 8m-1 U rows (fused_kernel: 8 and 7).  `m` is chosen on the host so that the whole
+// grid is one wave of co-resident CTAs when the sub-domain is small (gx1: m = 2, 286 CTAs on 296 slots instead of
+// 605 CTAs = 2.04 waves).  Ownership and ping-pong rules are those of fused_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int SBX = 32, SBY = 8;
+__global__ void __launch_bounds__(SBX *SBY, 2) strip_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
+                                                            int cur, int m, int last) {
+  __shared__ double sstr[8][SBY + 1][SBX];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int nxt = cur ^ 1;
+  const int i = 1 + blockIdx.x * (SBX - 1) + tx;
+  const int j0 = 1 + blockIdx.y * (SBY * m - 1);
+#if EVP_USE_PDL
+  cudaGridDependencySynchronize();
+#endif
+  for (int ch = 0; ch < m; ++ch) {
+    const int jT = j0 + SBY * ch + ty;
+    if (jT - ty > d.ny + 1) break;  // uniform: the strip has left the sub-domain
+    const bool inT = (i <= d.nx + 1) && (jT <= d.ny + 1);
+    const int c = at(d, inT ? i : 1, inT ? jT : 1);
+    double str[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (inT && d.maskT[c]) {
+      Sigma sg;
+      stress_at(d, k, cur, i, jT, sg, str);
+      // the strip's last T row is relaxed again by the strip above (as its first row), which stores it
+      const bool own = (tx < SBX - 1 || i == d.nx + 1) && (!(ch == m - 1 && ty == SBY - 1) || jT == d.ny + 1);
+      if (own) store_sigma(d, nxt, c, sg);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sstr[q][ty + 1][tx] = str[q];
+    __syncthreads();
+    // chunk 0 closes the U rows of its own first 7 T rows; later chunks close 8: the row carried in shared-memory
+    // row 0 plus their own first 7
+    const int jU = ch == 0 ? jT : jT - 1;
+    const int r = ch == 0 ? ty + 1 : ty;
+    const bool doU = (ch > 0 || ty < SBY - 1) && tx < SBX - 1 && i <= d.nx && jU <= d.ny;
+    if (doU) {
+      const int cu = at(d, i, jU);
+      if (d.maskU[cu]) {
+        double uin[16];
+        load_uin(d, k, cur, cu, uin);
+        const UOut o = stepu_point(uin[0], uin[1], uin[2], uin[3], uin[4], uin[5], uin[6], uin[7], uin[8], uin[9], uin[10], uin[11],
+                                   uin[12], uin[13], uin[14], uin[15], sstr[0][r][tx], sstr[1][r][tx + 1], sstr[2][r + 1][tx],
+                                   sstr[3][r + 1][tx + 1], sstr[4][r][tx], sstr[5][r + 1][tx], sstr[6][r][tx + 1],
+                                   sstr[7][r + 1][tx + 1], k);
+        store_uv(d, d.u[nxt], d.v[nxt], i, jU, o.u, o.v);
+        if (last) {
+          d.strintx[cu] = o.strintx;
+          d.strinty[cu] = o.strinty;
+          d.taubx[cu] = o.taubx;
+          d.tauby[cu] = o.tauby;
+        }
+      }
+    }
+    if (ch + 1 < m) {
+      __syncthreads();  // every read of this chunk's rows is done
+      if (ty == SBY - 1) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sstr[q][0][tx] = str[q];
+      }
+    }
+  }
+}
+
+cudaError_t launch_strip(const Dom &d, const KParams &p, int cur, int m, cudaStream_t s, bool pdl, int last) {
+  dim3 b(SBX, SBY), g((d.nx + SBX - 2) / (SBX - 1), (d.ny + SBY * m - 2) / (SBY * m - 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, strip_kernel, d, p, cur, m, last);
 }
 
 // loop hand-shake: "I have entered loop `base`" (my buffers are ready to be written), and the closing wait
@@ -365,7 +588,7 @@ __global__ void __launch_bounds__(F4X *F4Y * 4, 1) fused4_kernel(const __grid_co
     const int corner = t & 3, cell = t >> 2, cx = cell & (F4X - 1), cy = cell / F4X;
     const int i = i0 + cx, j = j0 + cy;
     const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
-    const size_t c = at(d, inT ? i : 1, inT ? j : 1);
+    const int c = at(d, inT ? i : 1, inT ? j : 1);
     double str_u = 0.0, str_v = 0.0;
     if (inT && d.maskT[c]) {
       const int a = cx + 1, b = cy + 1;
@@ -393,7 +616,7 @@ __global__ void __launch_bounds__(F4X *F4Y * 4, 1) fused4_kernel(const __grid_co
     const int tx = t & (F4X - 1), ty = t / F4X;
     const int i = i0 + tx, j = j0 + ty;
     if (tx < F4X - 1 && ty < F4Y - 1 && i <= d.nx && j <= d.ny) {
-      const size_t c = at(d, i, j);
+      const int c = at(d, i, j);
       if (d.maskU[c]) {
         const UOut o = stepu_point(su[ty + 1][tx + 1], sv[ty + 1][tx + 1], d.cdn[c], d.aiu[c], d.uocn[c], d.vocn[c], d.waterx[c],
                                    d.watery[c], d.forcex[c], d.forcey[c], d.umassdti[c], d.fm[c], d.uarear[c], d.TbU[c],
@@ -457,11 +680,11 @@ __global__ void __launch_bounds__(QBX *QBY, 2) queue_kernel(const __grid_constan
 
     const int i = 1 + tbx * (QBX - 1) + tx, j = 1 + tby * (QBY - 1) + ty;
     const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
-    const size_t c = at(d, inT ? i : 1, inT ? j : 1);
+    const int c = at(d, inT ? i : 1, inT ? j : 1);
     double str[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double uc = 0.0, vc = 0.0;
     if (inT && d.maskT[c]) {
-      const size_t w = c - 1, s = c - d.ld, sw = s - 1;
+      const int w = c - 1, s = c - d.ld, sw = s - 1;
       // state written by other CTAs inside this launch: read through L2 (ld.cg), never a stale L1 line
       const double *__restrict__ U = d.u[cur];
       const double *__restrict__ V = d.v[cur];
@@ -516,8 +739,8 @@ cudaError_t launch_queue(const Dom &d, const KParams &p, int ndte, unsigned *pro
   return cudaLaunchCooperativeKernel((const void *)queue_kernel, dim3(nctas), dim3(QBX, QBY), args, 0, s);
 }
 
-template <int FBX, int FBY, int MINB, bool HOIST = false>
-static cudaError_t launch_fused_t(const Dom &d, const KParams &p, int cur, cudaStream_t s, bool pdl) {
+template <int FBX, int FBY, int MINB, bool HOIST = false, int SPEC = 0>
+static cudaError_t launch_fused_t(const Dom &d, const KParams &p, int cur, cudaStream_t s, bool pdl, int last) {
   dim3 b(FBX, FBY), g((d.nx + FBX - 2) / (FBX - 1), (d.ny + FBY - 2) / (FBY - 1));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = 0; cfg.stream = s;
@@ -526,37 +749,44 @@ static cudaError_t launch_fused_t(const Dom &d, const KParams &p, int cur, cudaS
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
   static const P2PParams nop2p{};
-  return cudaLaunchKernelEx(&cfg, fused_kernel<FBX, FBY, MINB, HOIST, false>, d, p, cur, nop2p, 0);
+  return cudaLaunchKernelEx(&cfg, fused_kernel<FBX, FBY, MINB, HOIST, false, SPEC>, d, p, cur, nop2p, 0, last);
 }
 
-cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl) {
+cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl, int last) {
   if (variant == 20) {
     dim3 g4((d.nx + F4X - 2) / (F4X - 1), (d.ny + F4Y - 2) / (F4Y - 1));
     fused4_kernel<<<g4, F4X * F4Y * 4, 0, s>>>(d, p, cur);
     return cudaGetLastError();
   }
   switch (variant) {
-    case 1: return launch_fused_t<32, 8, 3>(d, p, cur, s, pdl);
-    case 2: return launch_fused_t<32, 8, 4>(d, p, cur, s, pdl);
-    case 3: return launch_fused_t<32, 4, 4>(d, p, cur, s, pdl);
-    case 4: return launch_fused_t<32, 16, 1>(d, p, cur, s, pdl);
-    case 5: return launch_fused_t<64, 4, 2>(d, p, cur, s, pdl);
-    case 6: return launch_fused_t<32, 6, 3>(d, p, cur, s, pdl);
-    case 7: return launch_fused_t<32, 8, 2, true>(d, p, cur, s, pdl);
-    case 8: return launch_fused_t<33, 8, 2, false>(d, p, cur, s, pdl);
-    case 9: return launch_fused_t<33, 8, 2, true>(d, p, cur, s, pdl);
-    case 10: return launch_fused_t<32, 4, 4, true>(d, p, cur, s, pdl);
-    case 11: return launch_fused_t<32, 9, 2>(d, p, cur, s, pdl);
-    case 12: return launch_fused_t<32, 10, 2>(d, p, cur, s, pdl);
-    case 13: return launch_fused_t<32, 7, 3>(d, p, cur, s, pdl);
-    case 14: return launch_fused_t<32, 5, 4>(d, p, cur, s, pdl);
-    case 15: return launch_fused_t<32, 11, 1>(d, p, cur, s, pdl);
-    default: return launch_fused_t<32, 8, 2>(d, p, cur, s, pdl);
+    case 1: return launch_fused_t<32, 8, 3>(d, p, cur, s, pdl, last);
+    case 2: return launch_fused_t<32, 8, 4>(d, p, cur, s, pdl, last);
+    case 3: return launch_fused_t<32, 4, 4>(d, p, cur, s, pdl, last);
+    case 4: return launch_fused_t<32, 16, 1>(d, p, cur, s, pdl, last);
+    case 5: return launch_fused_t<64, 4, 2>(d, p, cur, s, pdl, last);
+    case 6: return launch_fused_t<32, 6, 3>(d, p, cur, s, pdl, last);
+    case 7: return launch_fused_t<32, 8, 2, true>(d, p, cur, s, pdl, last);
+    case 8: return launch_fused_t<33, 8, 2, false>(d, p, cur, s, pdl, last);
+    case 9: return launch_fused_t<33, 8, 2, true>(d, p, cur, s, pdl, last);
+    case 10: return launch_fused_t<32, 4, 4, true>(d, p, cur, s, pdl, last);
+    case 11: return launch_fused_t<32, 9, 2>(d, p, cur, s, pdl, last);
+    case 12: return launch_fused_t<32, 10, 2>(d, p, cur, s, pdl, last);
+    case 13: return launch_fused_t<32, 7, 3>(d, p, cur, s, pdl, last);
+    case 14: return launch_fused_t<32, 5, 4>(d, p, cur, s, pdl, last);
+    case 15: return launch_fused_t<32, 11, 1>(d, p, cur, s, pdl, last);
+    case 16: return launch_fused_t<32, 8, 2>(d, p, cur, s, pdl, last);  // the non-speculative form (round-1 default)
+    case 17: return launch_fused_t<32, 8, 2, false, 1>(d, p, cur, s, pdl, last);  // speculative T loads only
+    case 18: return launch_fused_t<32, 8, 2, false, 2>(d, p, cur, s, pdl, last);  // cp.async momentum operands only
+    case 19: return launch_fused_t<32, 8, 2, false, 3>(d, p, cur, s, pdl, last);  // both
+    case 21: return launch_fused_t<32, 8, 2, false, 5>(d, p, cur, s, pdl, last);  // 17 + interleaved div/sqrt
+    case 22: return launch_fused_t<32, 8, 2, false, 7>(d, p, cur, s, pdl, last);  // 19 + interleaved div/sqrt
+    case 23: return launch_fused_t<32, 8, 2, false, 4>(d, p, cur, s, pdl, last);  // 16 + interleaved div/sqrt
+    default: return launch_fused_t<32, 8, 2, false, 4>(d, p, cur, s, pdl, last);
   }
 }
 
 // ksub = -1: loop start hand-shake; ksub = -2 - ndte ... no: see launch_p2p_aux
-cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, cudaStream_t s) {
+cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, int last, int variant, cudaStream_t s) {
   if (ksub == -1) {
     p2p_start_kernel<<<1, 32, 0, s>>>(pp);
     return cudaGetLastError();
@@ -565,7 +795,10 @@ cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp
     p2p_finish_kernel<<<1, 32, 0, s>>>(pp, -2 - ksub);
     return cudaGetLastError();
   }
-  fused_kernel<32, 8, 2, false, true><<<dim3(pp.ntx * pp.nty), dim3(32, 8), 0, s>>>(d, p, cur, pp, ksub);
+  if (variant == 19)
+    fused_kernel<32, 8, 2, false, true, 3><<<dim3(pp.ntx * pp.nty), dim3(32, 8), 0, s>>>(d, p, cur, pp, ksub, last);
+  else
+    fused_kernel<32, 8, 2, false, true, 4><<<dim3(pp.ntx * pp.nty), dim3(32, 8), 0, s>>>(d, p, cur, pp, ksub, last);
   return cudaGetLastError();
 }
 
