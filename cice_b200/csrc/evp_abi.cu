@@ -122,6 +122,9 @@ struct Ctx {
   unsigned char *cmask[4] = {};
   cudaGraphExec_t cexec = nullptr;  // cached graph of the C-grid loop (dies with the context: it bakes pointers and wrap flags)
   evp_b200_params_t cparams{};
+  unsigned *d_cbar = nullptr;       // grid-barrier counter of the cooperative C-grid kernel
+  int cgraph_launches = 0;
+  int c_max_ctas[2] = {0, 0};       // co-resident CTAs of that kernel (exact, fast); 0 = use the five-kernel form
 
   // KERNEL_PERSISTENT
   PersistPlan pplan{};
@@ -171,6 +174,7 @@ static int free_all() {
   for (auto &p : g.dstr) F(p);
   F(g.dmaskT); F(g.dmaskU);
   for (auto &p : g.stage) F(p);
+  F(g.d_cbar);
   F(g.stage_mask); F(g.d_gsrc); F(g.d_progress); F(g.d_qprogress); F(g.d_qcounter);
   F(g.d_uv_lin); F(g.d_uv_dom); F(g.d_sig_lin); F(g.d_sig_dom); F(g.d_int_lin); F(g.d_int_dom);
   g.halo.release();
@@ -723,6 +727,14 @@ static int do_init_cgrid(const evp_b200_cgrid_t *cg) {
   if (calloc_dom(c.uvelE_init) || calloc_dom(c.vvelN_init)) return 1;
   for (int q = 0; q < 4; ++q) { CK(cudaMalloc(&g.cmask[q], g.ndom)); CK(cudaMemsetAsync(g.cmask[q], 0, g.ndom, g.stream)); }
   c.maskT = g.cmask[0]; c.maskU = g.cmask[1]; c.maskE = g.cmask[2]; c.maskN = g.cmask[3];
+  CK(cudaMalloc(&g.d_cbar, sizeof(unsigned)));
+  // the single-launch cooperative form (EVP_B200_CGRID_COOP=1) is bit-identical but measured slower than five kernels per
+  // subcycle at gx1 (26.3 vs 23.3 us per subcycle): a grid barrier costs what a kernel boundary costs here
+  g.c_max_ctas[0] = g.c_max_ctas[1] = 0;
+  if (const char *e = getenv("EVP_B200_CGRID_COOP")) if (e[0] == '1') {
+    g.c_max_ctas[0] = exact::cgrid_coop_max_ctas(g.num_sms);
+    g.c_max_ctas[1] = fast::cgrid_coop_max_ctas(g.num_sms);
+  }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(g.stream));
   g.cinit = true;
@@ -790,15 +802,26 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t le = cudaSuccess;
-    for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub)
-      le = exact ? exact::launch_cgrid_subcycle(c, k, g.stream, &nl) : fast::launch_cgrid_subcycle(c, k, g.stream, &nl);
+    const int max_ctas = g.c_max_ctas[exact ? 0 : 1];
+    if (max_ctas > 0 && p->ndte > 0) {
+      // one cooperative launch for the whole loop, grid barriers where the five-kernel form has kernel boundaries
+      le = cudaMemsetAsync(g.d_cbar, 0, sizeof(unsigned), g.stream);
+      if (le == cudaSuccess)
+        le = exact ? exact::launch_cgrid_coop(c, k, p->ndte, g.d_cbar, max_ctas, g.stream)
+                   : fast::launch_cgrid_coop(c, k, p->ndte, g.d_cbar, max_ctas, g.stream);
+      nl = 1;
+    } else {
+      for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub)
+        le = exact ? exact::launch_cgrid_subcycle(c, k, g.stream, &nl) : fast::launch_cgrid_subcycle(c, k, g.stream, &nl);
+    }
+    g.cgraph_launches = nl;
     cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
     if (le != cudaSuccess || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail("evp_b200_run_cgrid: capture failed: %s", cudaGetErrorString(le != cudaSuccess ? le : ce)); }
     CK(cudaGraphInstantiate(&cexec, graph, 0));
     CK(cudaGraphDestroy(graph));
     cparams = *p;
   } else {
-    nl = 5 * p->ndte;
+    nl = g.cgraph_launches;
   }
   CK(cudaEventRecord(g.ev0, g.stream));
   if (p->ndte > 0) CK(cudaGraphLaunch(cexec, g.stream));

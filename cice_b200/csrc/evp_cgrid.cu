@@ -59,28 +59,35 @@ __device__ __forceinline__ void visc_c(double strength, double dmin, double Delt
 #define CELL_IJ(NXE, NYE)                                          \
   const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;         \
   const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;         \
-  if (i > (NXE) || j > (NYE)) return;                              \
-  const size_t c = AT(i, j)
+  if (i > (NXE) || j > (NYE)) return
+
+// Arrays the loop writes are read through M<CG>(): inside the single-launch cooperative kernel (CG = true) another SM
+// wrote them a phase ago, so the load must come from L2 (ld.global.cg), never from a stale L1 line; the five-kernel
+// form (CG = false) uses ordinary loads.  Static geometry and the per-step inputs stay L1-cacheable in both.
+template <bool CG>
+__device__ __forceinline__ double M(const double *p) { return CG ? __ldcg(p) : *p; }
 
 // ---- k1 ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k1_strain_U(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
-  CELL_IJ(d.nx, d.ny);
+template <bool CG>
+__device__ __forceinline__ void p1_strain_U(const CDom &d, const KParams &k, int i, int j) {
+  if (i > d.nx || j > d.ny) return;
+  const size_t c = AT(i, j);
   double div = 0.0, ten = 0.0, shr = 0.0, del = 0.0;
   if (d.maskU[c]) {
     const size_t e = c + 1, n = c + d.ld;
     const double npc = d.npm[c], npe = d.npm[e], epc = d.epm[c], epn = d.epm[n];
-    const double uNip1j = d.uvelN[e] * npe + (npc - npe) * npc * d.ratiodxN[c] * d.uvelN[c];
-    const double uNij = d.uvelN[c] * npc + (npe - npc) * npe * d.ratiodxNr[c] * d.uvelN[e];
-    const double vEijp1 = d.vvelE[n] * epn + (epc - epn) * epc * d.ratiodyE[c] * d.vvelE[c];
-    const double vEij = d.vvelE[c] * epc + (epn - epc) * epn * d.ratiodyEr[c] * d.vvelE[n];
-    const double dyU = d.dyU[c], dxU = d.dxU[c], uU = d.uvel[c], vU = d.vvel[c];
+    const double uNip1j = M<CG>(d.uvelN + e) * npe + (npc - npe) * npc * d.ratiodxN[c] * M<CG>(d.uvelN + c);
+    const double uNij = M<CG>(d.uvelN + c) * npc + (npe - npc) * npe * d.ratiodxNr[c] * M<CG>(d.uvelN + e);
+    const double vEijp1 = M<CG>(d.vvelE + n) * epn + (epc - epn) * epc * d.ratiodyE[c] * M<CG>(d.vvelE + c);
+    const double vEij = M<CG>(d.vvelE + c) * epc + (epn - epc) * epn * d.ratiodyEr[c] * M<CG>(d.vvelE + n);
+    const double dyU = d.dyU[c], dxU = d.dxU[c], uU = M<CG>(d.uvel + c), vU = M<CG>(d.vvel + c);
     const double ddyN = d.dyN[e] - d.dyN[c], ddxE = d.dxE[n] - d.dxE[c];
     div = dyU * (uNip1j - uNij) + uU * ddyN + dxU * (vEijp1 - vEij) + vU * ddxE;
     ten = dyU * (uNip1j - uNij) - uU * ddyN - dxU * (vEijp1 - vEij) + vU * ddxE;
-    const double uEijp1 = d.uvelE[n] * epn + (epc - epn) * epc * d.ratiodyE[c] * d.uvelE[c];
-    const double uEij = d.uvelE[c] * epc + (epn - epc) * epn * d.ratiodyEr[c] * d.uvelE[n];
-    const double vNip1j = d.vvelN[e] * npe + (npc - npe) * npc * d.ratiodxN[c] * d.vvelN[c];
-    const double vNij = d.vvelN[c] * npc + (npe - npc) * npe * d.ratiodxNr[c] * d.vvelN[e];
+    const double uEijp1 = M<CG>(d.uvelE + n) * epn + (epc - epn) * epc * d.ratiodyE[c] * M<CG>(d.uvelE + c);
+    const double uEij = M<CG>(d.uvelE + c) * epc + (epn - epc) * epn * d.ratiodyEr[c] * M<CG>(d.uvelE + n);
+    const double vNip1j = M<CG>(d.vvelN + e) * npe + (npc - npe) * npc * d.ratiodxN[c] * M<CG>(d.vvelN + c);
+    const double vNij = M<CG>(d.vvelN + c) * npc + (npe - npc) * npe * d.ratiodxNr[c] * M<CG>(d.vvelN + e);
     shr = dxU * (uEijp1 - uEij) - uU * ddxE + dyU * (vNip1j - vNij) - vU * ddyN;
     del = sqrt(div * div + k.e_factor * (ten * ten + shr * shr));
   }
@@ -90,20 +97,26 @@ __global__ void __launch_bounds__(256) k1_strain_U(const __grid_constant__ CDom 
   ring_store(d, d.shearU, i, j, shr, 3, false);
 }
 
+__global__ void __launch_bounds__(256) k1_strain_U(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  p1_strain_U<false>(d, k, 1 + blockIdx.x * blockDim.x + threadIdx.x, 1 + blockIdx.y * blockDim.y + threadIdx.y);
+}
+
 // ---- k2 ------------------------------------------------------------------------------------------------
 // T cells 1..nx+1 x 1..ny+1 (N/E ghost cells are in the reference's list, shared.F90:740-749); a ghost row or
 // column that merely aliases the interior under the on-rank wrap is filled by ring_store instead.
-__global__ void __launch_bounds__(256) k2_stress_T(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
-  CELL_IJ(d.wrap_ew ? d.nx : d.nx + 1, d.wrap_ns ? d.ny : d.ny + 1);
+template <bool CG>
+__device__ __forceinline__ void p2_stress_T(const CDom &d, const KParams &k, int i, int j) {
+  if (i > (d.wrap_ew ? d.nx : d.nx + 1) || j > (d.wrap_ns ? d.ny : d.ny + 1)) return;
+  const size_t c = AT(i, j);
   if (!d.maskT[c]) return;
   const size_t w = c - 1, s = c - d.ld, sw = s - 1;
   const double dyEc = d.dyE[c], dyEw = d.dyE[w], dxNc = d.dxN[c], dxNs = d.dxN[s];
-  const double uEc = d.uvelE[c], uEw = d.uvelE[w], vNc = d.vvelN[c], vNs = d.vvelN[s];
+  const double uEc = M<CG>(d.uvelE + c), uEw = M<CG>(d.uvelE + w), vNc = M<CG>(d.vvelN + c), vNs = M<CG>(d.vvelN + s);
   const double dxT = d.dxT[c], dyT = d.dyT[c];
   const double divT = dyEc * uEc - dyEw * uEw + dxNc * vNc - dxNs * vNs;
   const double tensionT = (dyT * dyT) * (uEc / dyEc - uEw / dyEw) - (dxT * dxT) * (vNc / dxNc - vNs / dxNs);
   const double uac = d.uarea[c], uas = d.uarea[s], uasw = d.uarea[sw], uaw = d.uarea[w];
-  const double shc = d.shearU[c], shs = d.shearU[s], shsw = d.shearU[sw], shw = d.shearU[w];
+  const double shc = M<CG>(d.shearU + c), shs = M<CG>(d.shearU + s), shsw = M<CG>(d.shearU + sw), shw = M<CG>(d.shearU + w);
   const double uareaavgr = 1.0 / (uac + uas + uasw + uaw);
   const double shearTsqr = (shc * shc * uac + shs * shs * uas + shsw * shsw * uasw + shw * shw * uaw) * uareaavgr;
   const double shearT = (shc * uac + shs * uas + shsw * uasw + shw * uaw) * uareaavgr;
@@ -111,9 +124,9 @@ __global__ void __launch_bounds__(256) k2_stress_T(const __grid_constant__ CDom 
   double zetax2, etax2, rep;
   visc_c(d.strength[c], d.DminTarea[c], DeltaT, k, zetax2, etax2, rep);
   const double relax = 1.0 - k.arlx1i * k.revp;
-  const double sp = (d.stresspT[c] * relax + k.arlx1i * (zetax2 * divT - rep)) * k.denom1;
-  const double sm = (d.stressmT[c] * relax + k.arlx1i * etax2 * tensionT) * k.denom1;
-  const double s12 = (d.stress12T[c] * relax + k.arlx1i * 0.5 * etax2 * shearT) * k.denom1;
+  const double sp = (M<CG>(d.stresspT + c) * relax + k.arlx1i * (zetax2 * divT - rep)) * k.denom1;
+  const double sm = (M<CG>(d.stressmT + c) * relax + k.arlx1i * etax2 * tensionT) * k.denom1;
+  const double s12 = (M<CG>(d.stress12T + c) * relax + k.arlx1i * 0.5 * etax2 * shearT) * k.denom1;
   ring_store(d, d.zetax2T, i, j, zetax2, 3, false);
   ring_store(d, d.etax2T, i, j, etax2, 3, false);
   ring_store(d, d.stresspT, i, j, sp, 3, false);
@@ -121,16 +134,22 @@ __global__ void __launch_bounds__(256) k2_stress_T(const __grid_constant__ CDom 
   ring_store(d, d.stress12T, i, j, s12, 1, false);  // not halo-updated: only the redundantly computed N/E ghost copy
 }
 
+__global__ void __launch_bounds__(256) k2_stress_T(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  p2_stress_T<false>(d, k, 1 + blockIdx.x * blockDim.x + threadIdx.x, 1 + blockIdx.y * blockDim.y + threadIdx.y);
+}
+
 // ---- k3 ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k3_stress_U(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
-  CELL_IJ(d.nx, d.ny);
+template <bool CG>
+__device__ __forceinline__ void p3_stress_U(const CDom &d, const KParams &k, int i, int j) {
+  if (i > d.nx || j > d.ny) return;
+  const size_t c = AT(i, j);
   const size_t e = c + 1, n = c + d.ld, ne = n + 1;
   const double *__restrict__ src = (k.visc_method == 1) ? d.strength : d.etax2T;
   const double mc = d.hm[c], me = d.hm[e], mn = d.hm[n], mne = d.hm[ne];
   const double wc = d.tarea[c], we = d.tarea[e], wn = d.tarea[n], wne = d.tarea[ne];
   const double wtmp = (mc * wc + me * we + mn * wn + mne * wne);
   double avg = 0.0;
-  if (wtmp != 0.0) avg = (mc * src[c] * wc + me * src[e] * we + mn * src[n] * wn + mne * src[ne] * wne) / wtmp;
+  if (wtmp != 0.0) avg = (mc * M<CG>(src + c) * wc + me * M<CG>(src + e) * we + mn * M<CG>(src + n) * wn + mne * M<CG>(src + ne) * wne) / wtmp;
   if (k.visc_method == 1) d.strengthU[c] = avg; else d.etax2U[c] = avg;
   if (d.maskU[c]) {
     const double relax = 1.0 - k.arlx1i * k.revp;
@@ -138,25 +157,31 @@ __global__ void __launch_bounds__(256) k3_stress_U(const __grid_constant__ CDom 
     if (k.visc_method == 1) {
       const double DminUarea = k.deltaminEVP * d.uarea[c];
       double z, r;
-      visc_c(avg, DminUarea, d.deltaU[c], k, z, etax2U, r);
+      visc_c(avg, DminUarea, M<CG>(d.deltaU + c), k, z, etax2U, r);
     }
-    const double s12 = (d.stress12U[c] * relax + k.arlx1i * 0.5 * etax2U * d.shearU[c]) * k.denom1;
+    const double s12 = (M<CG>(d.stress12U + c) * relax + k.arlx1i * 0.5 * etax2U * M<CG>(d.shearU + c)) * k.denom1;
     ring_store(d, d.stress12U, i, j, s12, 3, false);
   }
 }
 
+__global__ void __launch_bounds__(256) k3_stress_U(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  p3_stress_U<false>(d, k, 1 + blockIdx.x * blockDim.x + threadIdx.x, 1 + blockIdx.y * blockDim.y + threadIdx.y);
+}
+
 // ---- k4 ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k4_momentum(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
-  CELL_IJ(d.nx, d.ny);
+template <bool CG>
+__device__ __forceinline__ void p4_momentum(const CDom &d, const KParams &k, int i, int j) {
+  if (i > d.nx || j > d.ny) return;
+  const size_t c = AT(i, j);
   if (d.maskE[c]) {
     const size_t e = c + 1, s = c - d.ld;
     const double dyE = d.dyE[c], dyTe = d.dyT[e], dyTc = d.dyT[c], dxUc = d.dxU[c], dxUs = d.dxU[s];
     const double strintx = d.rheofactE[c] * d.earear[c] *
-                           (0.5 * dyE * (d.stresspT[e] - d.stresspT[c]) +
-                            (0.5 / dyE) * ((dyTe * dyTe) * d.stressmT[e] - (dyTc * dyTc) * d.stressmT[c]) +
-                            (1.0 / d.dxE[c]) * ((dxUc * dxUc) * d.stress12U[c] - (dxUs * dxUs) * d.stress12U[s]));
+                           (0.5 * dyE * (M<CG>(d.stresspT + e) - M<CG>(d.stresspT + c)) +
+                            (0.5 / dyE) * ((dyTe * dyTe) * M<CG>(d.stressmT + e) - (dyTc * dyTc) * M<CG>(d.stressmT + c)) +
+                            (1.0 / d.dxE[c]) * ((dxUc * dxUc) * M<CG>(d.stress12U + c) - (dxUs * dxUs) * M<CG>(d.stress12U + s)));
     d.strintxE[c] = strintx;
-    const double uold = d.uvelE[c], vold = d.vvelE[c];
+    const double uold = M<CG>(d.uvelE + c), vold = M<CG>(d.vvelE + c);
     const double du = d.uocnE[c] - uold, dv = d.vocnE[c] - vold;
     const double vrel = d.aiE[c] * k.rhow * d.cdnE[c] * sqrt(du * du + dv * dv);
     const double taux = vrel * d.waterxE[c];
@@ -174,11 +199,11 @@ __global__ void __launch_bounds__(256) k4_momentum(const __grid_constant__ CDom 
     const size_t n = c + d.ld, w = c - 1;
     const double dxN = d.dxN[c], dxTn = d.dxT[n], dxTc = d.dxT[c], dyUc = d.dyU[c], dyUw = d.dyU[w];
     const double strinty = d.rheofactN[c] * d.narear[c] *
-                           (0.5 * dxN * (d.stresspT[n] - d.stresspT[c]) -
-                            (0.5 / dxN) * ((dxTn * dxTn) * d.stressmT[n] - (dxTc * dxTc) * d.stressmT[c]) +
-                            (1.0 / d.dyN[c]) * ((dyUc * dyUc) * d.stress12U[c] - (dyUw * dyUw) * d.stress12U[w]));
+                           (0.5 * dxN * (M<CG>(d.stresspT + n) - M<CG>(d.stresspT + c)) -
+                            (0.5 / dxN) * ((dxTn * dxTn) * M<CG>(d.stressmT + n) - (dxTc * dxTc) * M<CG>(d.stressmT + c)) +
+                            (1.0 / d.dyN[c]) * ((dyUc * dyUc) * M<CG>(d.stress12U + c) - (dyUw * dyUw) * M<CG>(d.stress12U + w)));
     d.strintyN[c] = strinty;
-    const double uold = d.uvelN[c], vold = d.vvelN[c];
+    const double uold = M<CG>(d.uvelN + c), vold = M<CG>(d.vvelN + c);
     const double du = d.uocnN[c] - uold, dv = d.vocnN[c] - vold;
     const double vrel = d.aiN[c] * k.rhow * d.cdnN[c] * sqrt(du * du + dv * dv);
     const double tauy = vrel * d.wateryN[c];
@@ -194,29 +219,89 @@ __global__ void __launch_bounds__(256) k4_momentum(const __grid_constant__ CDom 
   }
 }
 
+__global__ void __launch_bounds__(256) k4_momentum(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  p4_momentum<false>(d, k, 1 + blockIdx.x * blockDim.x + threadIdx.x, 1 + blockIdx.y * blockDim.y + threadIdx.y);
+}
+
 // ---- k5 ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double avg4(const double *__restrict__ w1, const double *__restrict__ wg, size_t a, size_t b,
-                                       size_t c, size_t e) {
+template <bool CG>
+__device__ __forceinline__ double avg4(const double *w1, const double *__restrict__ wg, size_t a, size_t b, size_t c, size_t e) {
   const double wa = wg[a], wb = wg[b], wc = wg[c], we = wg[e];
   const double wtmp = (wa + wb + wc + we);
-  return (wtmp != 0.0) ? (w1[a] * wa + w1[b] * wb + w1[c] * wc + w1[e] * we) / wtmp : 0.0;
+  return (wtmp != 0.0) ? (M<CG>(w1 + a) * wa + M<CG>(w1 + b) * wb + M<CG>(w1 + c) * wc + M<CG>(w1 + e) * we) / wtmp : 0.0;
 }
-__device__ __forceinline__ double avg2(const double *__restrict__ w1, const double *__restrict__ wg, size_t a, size_t b) {
+template <bool CG>
+__device__ __forceinline__ double avg2(const double *w1, const double *__restrict__ wg, size_t a, size_t b) {
   const double wa = wg[a], wb = wg[b];
   const double wtmp = (wa + wb);
-  return (wtmp != 0.0) ? (w1[a] * wa + w1[b] * wb) / wtmp : 0.0;
+  return (wtmp != 0.0) ? (M<CG>(w1 + a) * wa + M<CG>(w1 + b) * wb) / wtmp : 0.0;
 }
-__global__ void __launch_bounds__(256) k5_interp(const __grid_constant__ CDom d) {
-  CELL_IJ(d.nx, d.ny);
+template <bool CG>
+__device__ __forceinline__ void p5_interp(const CDom &d, int i, int j) {
+  if (i > d.nx || j > d.ny) return;
+  const size_t c = AT(i, j);
   const size_t e = c + 1, w = c - 1, n = c + d.ld, s = c - d.ld;
-  const double uN = avg4(d.uvelE, d.earea, w, c, n - 1, n) * d.npm[c];      // E2NA 'NW'
-  const double vE = avg4(d.vvelN, d.narea, s, s + 1, c, e) * d.epm[c];      // N2EA 'SE'
-  const double uU = avg2(d.uvelE, d.earea, c, n) * d.uvm[c];                // E2UA 'N'
-  const double vU = avg2(d.vvelN, d.narea, c, e) * d.uvm[c];                // N2UA 'E'
+  const double uN = avg4<CG>(d.uvelE, d.earea, w, c, n - 1, n) * d.npm[c];      // E2NA 'NW'
+  const double vE = avg4<CG>(d.vvelN, d.narea, s, s + 1, c, e) * d.epm[c];      // N2EA 'SE'
+  const double uU = avg2<CG>(d.uvelE, d.earea, c, n) * d.uvm[c];                // E2UA 'N'
+  const double vU = avg2<CG>(d.vvelN, d.narea, c, e) * d.uvm[c];                // N2UA 'E'
   ring_store(d, d.uvelN, i, j, uN, 3, true);
   ring_store(d, d.vvelE, i, j, vE, 3, true);
   ring_store(d, d.uvel, i, j, uU, 3, true);
   ring_store(d, d.vvel, i, j, vU, 3, true);
+}
+__global__ void __launch_bounds__(256) k5_interp(const __grid_constant__ CDom d) {
+  p5_interp<false>(d, 1 + blockIdx.x * blockDim.x + threadIdx.x, 1 + blockIdx.y * blockDim.y + threadIdx.y);
+}
+
+// ---- all ndte subcycles in ONE cooperative launch -----------------------------------------------------------
+// 148 x 2 co-resident CTAs of 32 x 16 threads; every thread keeps the same cell for the whole loop (larger sub-domains:
+// a fixed list of tiles per CTA).  The five kernel boundaries of a subcycle become five grid barriers (one
+// red.release + ld.acquire spin on a monotonic counter, ~1 us instead of a ~2.5 us kernel boundary plus tail).
+constexpr int CBX = 32, CBY = 16;
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas) {
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    target += nctas;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(CBX *CBY, 2) cgrid_coop_kernel(const __grid_constant__ CDom d, const __grid_constant__ KParams k,
+                                                                  int ndte, int ntx, int ntiles, unsigned *bar) {
+  unsigned target = 0;
+  const unsigned nctas = gridDim.x;
+  for (int ksub = 0; ksub < ndte; ++ksub) {
+#define CG_PHASE(CALL)                                                        \
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {                      \
+    const int i = 1 + (t % ntx) * CBX + threadIdx.x, j = 1 + (t / ntx) * CBY + threadIdx.y; \
+    CALL;                                                                     \
+  }                                                                           \
+  grid_barrier(bar, target, nctas)
+    CG_PHASE(p1_strain_U<true>(d, k, i, j));
+    CG_PHASE(p2_stress_T<true>(d, k, i, j));
+    CG_PHASE(p3_stress_U<true>(d, k, i, j));
+    CG_PHASE(p4_momentum<true>(d, k, i, j));
+    CG_PHASE(p5_interp<true>(d, i, j));
+#undef CG_PHASE
+  }
+}
+
+cudaError_t launch_cgrid_coop(const CDom &d, const KParams &p, int ndte, unsigned *bar, int max_ctas, cudaStream_t s) {
+  int ntx = (d.nx + 1 + CBX - 1) / CBX, nty = (d.ny + 1 + CBY - 1) / CBY;
+  int ntiles = ntx * nty;
+  int nctas = ntiles < max_ctas ? ntiles : max_ctas;
+  void *args[] = {(void *)&d, (void *)&p, (void *)&ndte, (void *)&ntx, (void *)&ntiles, (void *)&bar};
+  return cudaLaunchCooperativeKernel((const void *)cgrid_coop_kernel, dim3(nctas), dim3(CBX, CBY), args, 0, s);
+}
+int cgrid_coop_max_ctas(int num_sms) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cgrid_coop_kernel, CBX * CBY, 0) != cudaSuccess) return 0;
+  return per_sm * num_sms;
 }
 
 cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches) {

@@ -112,6 +112,8 @@ struct PersistPlan {
   cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s); \
   cudaError_t launch_queue(const Dom &d, const KParams &p, int ndte, unsigned *progress, unsigned *counter, int nctas, cudaStream_t s); \
   cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \
+  cudaError_t launch_cgrid_coop(const CDom &d, const KParams &p, int ndte, unsigned *bar, int max_ctas, cudaStream_t s); \
+  int cgrid_coop_max_ctas(int num_sms); \
   }
 EVP_DECLARE_LAUNCHERS(exact)
 EVP_DECLARE_LAUNCHERS(fast)

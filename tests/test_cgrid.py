@@ -103,3 +103,20 @@ def test_cgrid_refused_where_unsupported(evp_lib):
     c = synth.make_ccase("tiny")
     with pytest.raises(evp_lib.EvpB200Error, match="evp_b200_init first"):
         evp_lib.dyn_evp_b200_init_cgrid(c.cgrid)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,kw", [("tiny", dict(seed=9)), ("tiny", dict(seed=10, ew="closed", ns="closed")),
+                                    ("tiny", dict(seed=11, visc_method=abi.VISC_AVG_STRENGTH)), ("gx3", dict(ndte=30))],
+                         ids=["tiny", "tiny-closed", "tiny-avgstrength", "gx3"])
+def test_cgrid_cooperative_single_launch(oracle_mod, evp_lib, monkeypatch, cfg, kw):
+    """EVP_B200_CGRID_COOP=1: the whole ndte loop as one cooperative launch with grid barriers."""
+    monkeypatch.setenv("EVP_B200_CGRID_COOP", "1")
+    c = synth.make_ccase(cfg, **kw)
+    ref = run_oracle_c(oracle_mod, c)
+    got = run_gpu_c(evp_lib, c, mode=abi.MODE_EXACT)
+    assert evp_lib.last_launches() == 1
+    skip = "etax2U" if c.params["visc_method"] == abi.VISC_AVG_STRENGTH else "strengthU"
+    for n in abi.CFIELDS_INOUT + abi.CFIELDS_OUT:
+        if n != skip:
+            assert np.array_equal(got[n].view(np.int64), ref[n].view(np.int64)), n

@@ -277,3 +277,38 @@ def test_edge_cases_no_ice_and_odd_loops(oracle_mod, evp_lib, kernel):
     oracle_mod.evp_run_bgrid(c.grid, dict(c.params, ndte=8), ref)
     # uvel_init is re-taken at the start of each loop, which only matters for revised EVP (revp = 0 here)
     assert_bitwise(g1, ref)
+
+
+# every form of the fused kernel that can be selected (EVP_B200_FUSED_VARIANT, read in evp_b200_init): 16 = round-1 form,
+# 17 = speculative T-cell loads, 19 = + cp.async momentum operands (default on sub-domains larger than L2),
+# 23 = interleaved IEEE division / square root (default on L2-resident sub-domains), 21/22 combinations, 30 = strip
+@pytest.mark.parametrize("variant,extra", [("16", {}), ("17", {}), ("18", {}), ("19", {}), ("21", {}), ("22", {}), ("23", {}),
+                                           ("30", {"EVP_B200_STRIP_M": "1"}), ("30", {"EVP_B200_STRIP_M": "2"}),
+                                           ("30", {"EVP_B200_STRIP_M": "3"})],
+                         ids=["v16", "v17", "v18", "v19", "v21", "v22", "v23", "strip1", "strip2", "strip3"])
+def test_fused_variants_bitwise(oracle_mod, evp_lib, monkeypatch, variant, extra):
+    monkeypatch.setenv("EVP_B200_FUSED_VARIANT", variant)
+    for k, v in extra.items():
+        monkeypatch.setenv(k, v)
+    cases = [synth.make_case("tiny", seed=11, block_size=(12, 10), ndte=9),
+             synth.make_case("tiny", seed=12, revised_evp=True),
+             synth.make_case("tiny", seed=13, ew="closed", ns="closed", kmt="boxislands"),
+             synth.make_case("gx3", seed=14, ndte=25),
+             synth.make_case("tiny", seed=15, ns="tripole", ew="cyclic", kmt="none", ndte=12)]
+    for c in cases:
+        ref = run_oracle(oracle_mod, c)
+        got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED)
+        assert_bitwise(got, ref)
+
+
+def test_interleaved_divsqrt_hits_the_fallback(oracle_mod, evp_lib, monkeypatch):
+    """operands outside the fast path of the hand-scheduled division / square root (zero and denormal-range
+    strain rates and numerators: ice at rest, zero forcing) must take the built-in operators and stay bit-identical."""
+    monkeypatch.setenv("EVP_B200_FUSED_VARIANT", "23")
+    c = synth.make_case("tiny", seed=21, ndte=6)
+    for n in ("uvel", "vvel", "uocnU", "vocnU", "forcexU", "forceyU", "waterxU", "wateryU"):
+        c.fields[n][...] = 0.0
+    c.fields["strength"][...] *= 1e-300  # Delta = 0 -> dmin branch; tiny numerators -> slow-path range test
+    ref = run_oracle(oracle_mod, c)
+    got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED)
+    assert_bitwise(got, ref)
