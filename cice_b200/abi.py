@@ -17,6 +17,7 @@ KERNEL_AUTO, KERNEL_SPLIT, KERNEL_FUSED, KERNEL_PERSISTENT, KERNEL_QUEUE = 0, 1,
 KERNEL_NAMES = {"auto": 0, "split": 1, "fused": 2, "persistent": 3, "queue": 4}
 
 UNIQUE_ID_BYTES = 128
+KEEP_STRESS, FETCH_STRESS = 1, 2  # evp_b200_run_bgrid_resident flags
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int32)

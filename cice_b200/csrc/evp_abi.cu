@@ -43,6 +43,37 @@ __global__ void pack_f64(double *__restrict__ dst, const double *__restrict__ sr
     dst[k] = (s >= 0) ? src[s] : 0.0;
   }
 }
+// same, into both ping-pong copies of a carried field (they must start identical: cells off the ice are never written)
+__global__ void pack2_f64(double *__restrict__ dst0, double *__restrict__ dst1, const double *__restrict__ src,
+                          const int *__restrict__ gsrc, int n) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int s = gsrc[k];
+    const double v = (s >= 0) ? src[s] : 0.0;
+    dst0[k] = v;
+    dst1[k] = v;
+  }
+}
+// device-resident stresses: what dyn_prep2 does to the carried stresses on the host before every
+// loop -- zero them where there is no ice (ice_dyn_shared.F90:717-730) -- applied to both ping-pong copies
+struct SigPtrs { double *p[24]; };
+__global__ void zero_stress_off_ice(const __grid_constant__ SigPtrs sp, const unsigned char *__restrict__ maskT, int n) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    if (!maskT[k]) {
+#pragma unroll
+      for (int q = 0; q < 24; ++q) sp.p[q][k] = 0.0;
+    }
+  }
+}
+// block-layout bookkeeping of that zeroing for the cells the device does not own (W/S ghost cells, padding): the host
+// zeroes the WHOLE block where iceTmask is false, so when resident stresses are fetched the same cells must read zero
+__global__ void note_off_ice(unsigned char *__restrict__ ever_off, const int *__restrict__ maskT_blk, int n) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    if (maskT_blk[k] == 0) ever_off[k] = 1;
+}
+__global__ void zero_where(double *__restrict__ a, const unsigned char *__restrict__ ever_off, int n) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    if (ever_off[k]) a[k] = 0.0;
+}
 __global__ void pack_mask(unsigned char *__restrict__ dst, const int *__restrict__ src, const int *__restrict__ gsrc,
                           int n) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -92,7 +123,12 @@ struct Ctx {
   double *dstr[8] = {};
   unsigned char *dmaskT = nullptr, *dmaskU = nullptr;
   double *stage[NF_STEP] = {};    // block-layout staging, one per time-varying field
-  int *stage_mask = nullptr;
+  int *stage_mask = nullptr, *stage_mask2 = nullptr;
+  cudaStream_t xfer = nullptr;          // copy-engine stream: H2D/D2H run beside the pack/unpack kernels
+  cudaEvent_t ev_field[34] = {};         // one per staged field
+  bool stress_resident = false;
+  bool stress_uploaded_this_call = false;
+  unsigned char *d_ever_off = nullptr;   // block layout: iceTmask was false in some step since the host last saw the stresses          // the device holds the current stresses (evp_b200_run_bgrid_resident)
   int *d_gsrc = nullptr;
   int *d_uv_lin = nullptr, *d_uv_dom = nullptr, n_uv = 0;
   int *d_sig_lin = nullptr, *d_sig_dom = nullptr, n_sig = 0;
@@ -137,6 +173,7 @@ struct Ctx {
   int fused_variant = 0;
   int strip_m = 1;  // chunks per CTA of strip_kernel (fused_variant 30)
   bool fused_pdl = true;
+  bool pdl_trigger = true;  // early programmatic-launch trigger in the fused kernel
 };
 static Ctx g;
 static CommState g_comm;
@@ -175,9 +212,11 @@ static int free_all() {
   F(g.dmaskT); F(g.dmaskU);
   for (auto &p : g.stage) F(p);
   F(g.d_cbar);
-  F(g.stage_mask); F(g.d_gsrc); F(g.d_progress); F(g.d_qprogress); F(g.d_qcounter);
+  F(g.stage_mask); F(g.stage_mask2); F(g.d_ever_off); F(g.d_gsrc); F(g.d_progress); F(g.d_qprogress); F(g.d_qcounter);
   F(g.d_uv_lin); F(g.d_uv_dom); F(g.d_sig_lin); F(g.d_sig_dom); F(g.d_int_lin); F(g.d_int_dom);
   g.halo.release();
+  for (auto &e : g.ev_field) if (e) cudaEventDestroy(e);
+  if (g.xfer) cudaStreamDestroy(g.xfer);
   if (g.ev0) cudaEventDestroy(g.ev0);
   if (g.ev1) cudaEventDestroy(g.ev1);
   if (g.stream) cudaStreamDestroy(g.stream);
@@ -248,6 +287,8 @@ static int do_init(const evp_b200_grid_t *gr) {
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&g.ev0));
   CK(cudaEventCreate(&g.ev1));
+  CK(cudaStreamCreateWithFlags(&g.xfer, cudaStreamNonBlocking));
+  for (auto &e : g.ev_field) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
   g.nx_block = gr->nx_block; g.ny_block = gr->ny_block; g.nblocks = gr->nblocks; g.max_blocks = gr->max_blocks;
   g.nxg = gr->nx_global; g.nyg = gr->ny_global; g.ew = gr->ew_boundary_type; g.ns = gr->ns_boundary_type;
@@ -331,6 +372,9 @@ static int do_init(const evp_b200_grid_t *gr) {
   CK(cudaMemsetAsync(g.dmaskT, 0, g.ndom, g.stream)); CK(cudaMemsetAsync(g.dmaskU, 0, g.ndom, g.stream));
   for (int f = 0; f < NF_STEP; ++f) CK(cudaMalloc(&g.stage[f], bblk));
   CK(cudaMalloc(&g.stage_mask, g.nblk_elems * sizeof(int)));
+  CK(cudaMalloc(&g.stage_mask2, g.nblk_elems * sizeof(int)));
+  CK(cudaMalloc(&g.d_ever_off, g.nblk_elems));
+  CK(cudaMemsetAsync(g.d_ever_off, 0, g.nblk_elems, g.stream));
 
   // ---- static geometry --------------------------------------------------------------------------
   const double *geo[10] = {gr->dxT, gr->dyT, gr->dxhy, gr->dyhx, gr->cxp, gr->cyp, gr->cxm, gr->cym, gr->DminTarea, gr->uarear};
@@ -369,6 +413,7 @@ static int do_init(const evp_b200_grid_t *gr) {
   g.fused_variant = (g.ndom * sizeof(double) * 50 > (size_t)96 << 20) ? 19 : 23;
   if (const char *e = getenv("EVP_B200_FUSED_VARIANT")) g.fused_variant = atoi(e);
   if (const char *e = getenv("EVP_B200_PDL")) g.fused_pdl = (e[0] != '0');
+  if (const char *e = getenv("EVP_B200_PDL_TRIGGER")) g.pdl_trigger = (e[0] != '0');
   CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, g.device));
   {
     // strip_kernel: chunks per CTA.  cost = waves of co-resident CTAs (2 per SM) x work per CTA (m chunks + prologue)
@@ -412,7 +457,7 @@ static int do_init(const evp_b200_grid_t *gr) {
 // ------------------------------------------------------------------------------------------------
 // upload / download
 // ------------------------------------------------------------------------------------------------
-static int do_upload(const evp_b200_fields_t *f) {
+static int do_upload(const evp_b200_fields_t *f, bool keep_stress = false) {
   if (!g.inited) return fail("evp_b200_upload: evp_b200_init has not been called");
   if (!f) return fail("evp_b200_upload: null fields");
   const double *src[NF_STEP] = {
@@ -420,30 +465,61 @@ static int do_upload(const evp_b200_fields_t *f) {
       f->stress12_1, f->stress12_2, f->stress12_3, f->stress12_4, f->strintxU, f->strintyU, f->taubxU, f->taubyU,
       f->uvel, f->vvel, f->strength, f->cdn_ocnU, f->aiU, f->uocnU, f->vocnU, f->waterxU, f->wateryU, f->forcexU,
       f->forceyU, f->umassdti, f->fmU, f->TbU};
-  const size_t bblk = g.nblk_elems * sizeof(double), bdom = g.ndom * sizeof(double);
+  const size_t bblk = g.nblk_elems * sizeof(double);
   CK(cudaSetDevice(g.device));
-  for (int q = 0; q < NF_STEP; ++q) {
+  keep_stress = keep_stress && g.stress_resident;
+  for (int q = keep_stress ? 12 : 0; q < NF_STEP; ++q)
     if (!src[q]) return fail("evp_b200_upload: null field %d", q);
-    CK(cudaMemcpyAsync(g.stage[q], src[q], bblk, cudaMemcpyHostToDevice, g.stream));
-    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(g.dfield[q], g.stage[q], g.d_gsrc, (int)g.ndom);
-  }
   if (!f->iceTmask || !f->iceUmask) return fail("evp_b200_upload: null mask");
-  CK(cudaMemcpyAsync(g.stage_mask, f->iceTmask, g.nblk_elems * sizeof(int), cudaMemcpyHostToDevice, g.stream));
-  pack_mask<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(g.dmaskT, g.stage_mask, g.d_gsrc, (int)g.ndom);
-  CK(cudaMemcpyAsync(g.stage_mask, f->iceUmask, g.nblk_elems * sizeof(int), cudaMemcpyHostToDevice, g.stream));
-  pack_mask<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(g.dmaskU, g.stage_mask, g.d_gsrc, (int)g.ndom);
-  CK(cudaGetLastError());
-  // both ping-pong copies start identical: cells off the ice are never written again
-  for (int q = 0; q < 12; ++q) CK(cudaMemcpyAsync(g.dsig1[q], g.dfield[F_SIG0 + q], bdom, cudaMemcpyDeviceToDevice, g.stream));
-  CK(cudaMemcpyAsync(g.du1, g.dfield[F_U], bdom, cudaMemcpyDeviceToDevice, g.stream));
-  CK(cudaMemcpyAsync(g.dv1, g.dfield[F_V], bdom, cudaMemcpyDeviceToDevice, g.stream));
+  // everything carried is packed into BOTH ping-pong copies below, so copy 0 can simply be declared current; resident
+  // stresses of a loop that ended on copy 1 are first brought over (no pointer swap: the cached graph bakes the pointers)
+  if (keep_stress && g.cur == 1)
+    for (int q = 0; q < 12; ++q)
+      CK(cudaMemcpyAsync(g.dom.sig[0][q], g.dom.sig[1][q], g.ndom * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
   g.cur = 0;
+  // the copy engine streams the block arrays in (g.xfer) while the pack kernels of earlier fields run (g.stream)
+  CK(cudaEventRecord(g.ev_field[33], g.stream));
+  CK(cudaStreamWaitEvent(g.xfer, g.ev_field[33], 0));  // staging buffers are free once earlier work on g.stream is done
+  const int nb = grid_blocks(g.ndom), nd = (int)g.ndom;
+  // masks first: the resident-stress path needs iceTmask early
+  CK(cudaMemcpyAsync(g.stage_mask, f->iceTmask, g.nblk_elems * sizeof(int), cudaMemcpyHostToDevice, g.xfer));
+  CK(cudaEventRecord(g.ev_field[30], g.xfer));
+  CK(cudaMemcpyAsync(g.stage_mask2, f->iceUmask, g.nblk_elems * sizeof(int), cudaMemcpyHostToDevice, g.xfer));
+  CK(cudaEventRecord(g.ev_field[31], g.xfer));
+  for (int q = keep_stress ? 12 : 0; q < NF_STEP; ++q) {
+    CK(cudaMemcpyAsync(g.stage[q], src[q], bblk, cudaMemcpyHostToDevice, g.xfer));
+    CK(cudaEventRecord(g.ev_field[q], g.xfer));
+  }
+  CK(cudaStreamWaitEvent(g.stream, g.ev_field[30], 0));
+  pack_mask<<<nb, 256, 0, g.stream>>>(g.dmaskT, g.stage_mask, g.d_gsrc, nd);
+  CK(cudaStreamWaitEvent(g.stream, g.ev_field[31], 0));
+  pack_mask<<<nb, 256, 0, g.stream>>>(g.dmaskU, g.stage_mask2, g.d_gsrc, nd);
+  g.stress_uploaded_this_call = !keep_stress;
+  if (!keep_stress) CK(cudaMemsetAsync(g.d_ever_off, 0, g.nblk_elems, g.stream));  // the host did its own zeroing
+  if (keep_stress) {
+    note_off_ice<<<grid_blocks(g.nblk_elems), 256, 0, g.stream>>>(g.d_ever_off, g.stage_mask, (int)g.nblk_elems);
+    SigPtrs sp;
+    for (int q = 0; q < 12; ++q) { sp.p[q] = g.dom.sig[0][q]; sp.p[12 + q] = g.dom.sig[1][q]; }
+    zero_stress_off_ice<<<nb, 256, 0, g.stream>>>(sp, g.dmaskT, nd);
+  }
+  for (int q = keep_stress ? 12 : 0; q < NF_STEP; ++q) {
+    CK(cudaStreamWaitEvent(g.stream, g.ev_field[q], 0));
+    // carried state goes into both ping-pong copies: cells off the ice are never written again
+    if (q < 12) pack2_f64<<<nb, 256, 0, g.stream>>>(g.dom.sig[0][q], g.dom.sig[1][q], g.stage[q], g.d_gsrc, nd);
+    else if (q == F_U) pack2_f64<<<nb, 256, 0, g.stream>>>(g.dom.u[0], g.dom.u[1], g.stage[q], g.d_gsrc, nd);
+    else if (q == F_V) pack2_f64<<<nb, 256, 0, g.stream>>>(g.dom.v[0], g.dom.v[1], g.stage[q], g.d_gsrc, nd);
+    else pack_f64<<<nb, 256, 0, g.stream>>>(g.dfield[q], g.stage[q], g.d_gsrc, nd);
+  }
+  CK(cudaGetLastError());
   g.uploaded = true;
+  g.stress_resident = true;
   return 0;
 }
 
-static int do_download(evp_b200_fields_t *f) {
+// what: bit 0 stresses, bit 1 everything else the loop writes (diagnostics, velocities)
+static int do_download(evp_b200_fields_t *f, int what = 3) {
   if (!g.inited || !g.uploaded) return fail("evp_b200_download: nothing uploaded");
+  if (!f) return fail("evp_b200_download: null fields");
   double *dst[18] = {f->stressp_1, f->stressp_2, f->stressp_3, f->stressp_4, f->stressm_1, f->stressm_2,
                      f->stressm_3, f->stressm_4, f->stress12_1, f->stress12_2, f->stress12_3, f->stress12_4,
                      f->strintxU, f->strintyU, f->taubxU, f->taubyU, f->uvel, f->vvel};
@@ -451,7 +527,14 @@ static int do_download(evp_b200_fields_t *f) {
   CK(cudaSetDevice(g.device));
   const Dom &d = g.dom;
   for (int q = 0; q < 18; ++q) {
+    if (!((q < 12) ? (what & 1) : (what & 2))) continue;
     if (!dst[q]) return fail("evp_b200_download: null field %d", q);
+    if (q < 12 && !g.stress_uploaded_this_call) {
+      // resident stresses are being fetched: the staging copy is stale, start from the caller's array and apply the zeroing
+      // the host would have applied to the cells the device does not own
+      CK(cudaMemcpyAsync(g.stage[q], dst[q], bblk, cudaMemcpyHostToDevice, g.stream));
+      zero_where<<<grid_blocks(g.nblk_elems), 256, 0, g.stream>>>(g.stage[q], g.d_ever_off, (int)g.nblk_elems);
+    }
     // the staging copy still holds the host array as uploaded: cells the loop does not own keep their values
     if (q < 12)
       unpack_f64<<<grid_blocks(g.n_sig), 256, 0, g.stream>>>(g.stage[q], d.sig[g.cur][q], g.d_sig_lin, g.d_sig_dom, g.n_sig);
@@ -459,10 +542,14 @@ static int do_download(evp_b200_fields_t *f) {
       unpack_f64<<<grid_blocks(g.n_int), 256, 0, g.stream>>>(g.stage[q], g.dfield[q], g.d_int_lin, g.d_int_dom, g.n_int);
     else
       unpack_f64<<<grid_blocks(g.n_uv), 256, 0, g.stream>>>(g.stage[q], q == 16 ? d.u[g.cur] : d.v[g.cur], g.d_uv_lin, g.d_uv_dom, g.n_uv);
-    CK(cudaMemcpyAsync(dst[q], g.stage[q], bblk, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaEventRecord(g.ev_field[q], g.stream));
+    CK(cudaStreamWaitEvent(g.xfer, g.ev_field[q], 0));
+    CK(cudaMemcpyAsync(dst[q], g.stage[q], bblk, cudaMemcpyDeviceToHost, g.xfer));
   }
+  if ((what & 1) && !g.stress_uploaded_this_call) CK(cudaMemsetAsync(g.d_ever_off, 0, g.nblk_elems, g.stream));  // host is current again
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(g.stream));
+  CK(cudaStreamSynchronize(g.xfer));
   return 0;
 }
 
@@ -523,6 +610,9 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
     *launches = p->ndte > 0 ? 1 : 0;
     return 0;
   }
+  // early programmatic-launch trigger: pays when the grid is more than one wave of co-resident CTAs (gx1 2.29 -> 2.21 ms), costs
+  // on grids far smaller than the machine (gx3 0.56 -> 0.64 ms)
+  const int pdl_trig = (g.fused_pdl && g.pdl_trigger && (long)((g.dom.nx + 30) / 31) * ((g.dom.ny + 6) / 7) > 2L * g.num_sms) ? 2 : 0;
   for (int ksub = 0; ksub < p->ndte; ++ksub) {
     const int last = (ksub == p->ndte - 1);
     if (p2p) {
@@ -541,8 +631,8 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
         CK(exact ? exact::launch_strip(g.dom, k, cur, g.strip_m, g.stream, g.fused_pdl, last)
                  : fast::launch_strip(g.dom, k, cur, g.strip_m, g.stream, g.fused_pdl, last));
       else
-        CK(exact ? exact::launch_fused(g.dom, k, cur, g.stream, g.fused_variant, g.fused_pdl, last)
-                 : fast::launch_fused(g.dom, k, cur, g.stream, g.fused_variant, g.fused_pdl, last));
+        CK(exact ? exact::launch_fused(g.dom, k, cur, g.stream, g.fused_variant, g.fused_pdl, last | (pdl_trig))
+                 : fast::launch_fused(g.dom, k, cur, g.stream, g.fused_variant, g.fused_pdl, last | (pdl_trig)));
       cur ^= 1;
       nl += 1;
     } else {
@@ -894,14 +984,25 @@ int evp_b200_deformations(evp_b200_deform_t *d) { return do_deformations(d); }
 int evp_b200_init_cgrid(const evp_b200_cgrid_t *cg) { return do_init_cgrid(cg); }
 int evp_b200_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) { return do_run_cgrid(p, f); }
 
-int evp_b200_upload(const evp_b200_fields_t *f) { return do_upload(f); }
+int evp_b200_upload(const evp_b200_fields_t *f) { return do_upload(f, false); }
 int evp_b200_subcycle(const evp_b200_params_t *p) { return do_subcycle(p); }
-int evp_b200_download(evp_b200_fields_t *f) { return do_download(f); }
+int evp_b200_download(evp_b200_fields_t *f) { return do_download(f, 3); }
+
+int evp_b200_run_bgrid_resident(const evp_b200_params_t *p, evp_b200_fields_t *f, int32_t flags) {
+  if ((flags & EVP_B200_KEEP_STRESS) && g.inited && g.ns == EVP_B200_BNDY_TRIPOLE)
+    return fail("evp_b200_run_bgrid_resident: EVP_B200_KEEP_STRESS is not available on tripole grids (the host symmetrises the "
+                "stresses across the fold after the loop, ice_dyn_evp.F90:1322-1389)");
+  if (do_upload(f, (flags & EVP_B200_KEEP_STRESS) != 0)) return 1;
+  if (do_subcycle(p)) return 1;
+  const bool stress_back = !(flags & EVP_B200_KEEP_STRESS) || (flags & EVP_B200_FETCH_STRESS);
+  return do_download(f, stress_back ? 3 : 2);
+}
+int evp_b200_download_stress(evp_b200_fields_t *f) { return do_download(f, 1); }
 
 int evp_b200_run_bgrid(const evp_b200_params_t *p, evp_b200_fields_t *f) {
-  if (do_upload(f)) return 1;
+  if (do_upload(f, false)) return 1;
   if (do_subcycle(p)) return 1;
-  return do_download(f);
+  return do_download(f, 3);
 }
 
 int evp_b200_halo_plan(int32_t nranks, const int32_t *rects, int32_t rank, int32_t nxg, int32_t nyg, int32_t ew, int32_t ns,

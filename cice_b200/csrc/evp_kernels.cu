@@ -352,11 +352,18 @@ __device__ __forceinline__ void fused_spec_body(const Dom &d, const KParams &k, 
 template <int FBX, int FBY, int MINB, bool HOIST, bool P2P = false, int SPEC = 0>
 __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_constant__ Dom d,
                                                                 const __grid_constant__ KParams k, int cur,
-                                                                const __grid_constant__ P2PParams pp, int ksub, int last) {
+                                                                const __grid_constant__ P2PParams pp, int ksub, int flags) {
   __shared__ double sstr[8][FBY][FBX];
   const int tx = threadIdx.x, ty = threadIdx.y;
   int tbx = blockIdx.x, tby = blockIdx.y;
   bool edge_tile = false;
+  const int last = flags & 1;
+#if EVP_USE_PDL
+  // programmatic dependent launch, early trigger: once every CTA of this grid has started, the next subcycle's CTAs may
+  // be scheduled onto SMs this grid no longer fills (its last, partial wave); they fetch masks and static operands and
+  // then block in cudaGridDependencySynchronize() until this grid has completed and flushed
+  if (flags & 2) cudaTriggerProgrammaticLaunchCompletion();
+#endif
   if (P2P) {
     const int tile = pp.tile_order[blockIdx.x];
     tbx = tile % pp.ntx;
@@ -749,7 +756,7 @@ static cudaError_t launch_fused_t(const Dom &d, const KParams &p, int cur, cudaS
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
   static const P2PParams nop2p{};
-  return cudaLaunchKernelEx(&cfg, fused_kernel<FBX, FBY, MINB, HOIST, false, SPEC>, d, p, cur, nop2p, 0, last);
+  return cudaLaunchKernelEx(&cfg, fused_kernel<FBX, FBY, MINB, HOIST, false, SPEC>, d, p, cur, nop2p, 0, last);  // last: bit 0 = last subcycle, bit 1 = early PDL trigger
 }
 
 cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl, int last) {
@@ -781,6 +788,12 @@ cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s
     case 21: return launch_fused_t<32, 8, 2, false, 5>(d, p, cur, s, pdl, last);  // 17 + interleaved div/sqrt
     case 22: return launch_fused_t<32, 8, 2, false, 7>(d, p, cur, s, pdl, last);  // 19 + interleaved div/sqrt
     case 23: return launch_fused_t<32, 8, 2, false, 4>(d, p, cur, s, pdl, last);  // 16 + interleaved div/sqrt
+    case 24: return launch_fused_t<32, 8, 3, false, 4>(d, p, cur, s, pdl, last);  // 23 with other CTA shapes / residency
+    case 25: return launch_fused_t<32, 6, 3, false, 4>(d, p, cur, s, pdl, last);
+    case 26: return launch_fused_t<32, 5, 4, false, 4>(d, p, cur, s, pdl, last);
+    case 27: return launch_fused_t<32, 4, 4, false, 4>(d, p, cur, s, pdl, last);
+    case 28: return launch_fused_t<32, 16, 1, false, 4>(d, p, cur, s, pdl, last);
+    case 29: return launch_fused_t<32, 12, 1, false, 4>(d, p, cur, s, pdl, last);
     default: return launch_fused_t<32, 8, 2, false, 4>(d, p, cur, s, pdl, last);
   }
 }

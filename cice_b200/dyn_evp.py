@@ -63,6 +63,23 @@ def dyn_evp_b200_run(params, fields):
     return fields
 
 
+def dyn_evp_b200_run_resident(params, fields, keep_stress=True, fetch_stress=False):
+    """one dynamics step with the stresses resident on the device: the host's 12 stress arrays are
+    neither read nor written (unless fetch_stress), dyn_prep2's zeroing off the ice is applied on the device."""
+    p = abi.make_params(params)
+    f, keep = _fields(fields)
+    flags = (abi.KEEP_STRESS if keep_stress else 0) | (abi.FETCH_STRESS if fetch_stress else 0)
+    check(load().evp_b200_run_bgrid_resident(C.byref(p), C.byref(f), flags), "evp_b200_run_bgrid_resident")
+    return fields
+
+
+def download_stress(fields):
+    """fetch the device-resident stresses into the host arrays (restart / history)."""
+    f, keep = _fields(fields)
+    check(load().evp_b200_download_stress(C.byref(f)), "evp_b200_download_stress")
+    return fields
+
+
 def dyn_evp_b200_init_cgrid(cgrid):
     """extra static geometry of grid_ice='C' (after dyn_evp_b200_init)."""
     if _state["grid"] is None:

@@ -80,7 +80,10 @@ void dyn_evp_b200_run(double *stressp_1, double *stressp_2, double *stressp_3, d
   f.umassdti = umassdti; f.fmU = fmU; f.strintxU = strintxU; f.strintyU = strintyU; f.TbU = TbU;
   f.taubxU = taubxU; f.taubyU = taubyU; f.uvel = uvel; f.vvel = vvel;
   f.iceTmask = g_maskT.data(); f.iceUmask = g_maskU.data();
-  check(evp_b200_run_bgrid(&p, &f), "dyn_evp_b200_run");
+  if (s.resident_flags)
+    check(evp_b200_run_bgrid_resident(&p, &f, s.resident_flags), "dyn_evp_b200_run");
+  else
+    check(evp_b200_run_bgrid(&p, &f), "dyn_evp_b200_run");
 }
 
 void dyn_evp_b200_finalize() {

@@ -46,6 +46,9 @@ struct EvpScalars {
   double arlx1i = 0, denom1 = 0, revp = 0, brlx = 0, e_factor = 0, epp2i = 0, capping = 1, Ktens = 0;
   double u0 = 5e-5, cosw = 1, sinw = 0, rhow = 1026, deltaminEVP = 1e-11;
   int mode = EVP_B200_MODE_EXACT, kernel = EVP_B200_KERNEL_AUTO;
+  // EVP_B200_KEEP_STRESS / EVP_B200_FETCH_STRESS: leave the stresses on the device between steps;
+  // the driver sets FETCH on steps that write a restart or history file (ice_restart_driver.F90:150-231)
+  int resident_flags = 0;
 };
 
 // optional: before init, for more than one rank (the host broadcasts the id itself, e.g. MPI_Bcast)

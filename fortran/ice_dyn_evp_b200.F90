@@ -75,6 +75,16 @@ module ice_dyn_evp_b200
        type(evp_b200_params_t), intent(in) :: params
        type(evp_b200_fields_t), intent(inout) :: fields
      end function
+     integer(c_int) function evp_b200_run_bgrid_resident(params, fields, flags) bind(C, name='evp_b200_run_bgrid_resident')
+       import :: c_int, c_int32_t, evp_b200_params_t, evp_b200_fields_t
+       type(evp_b200_params_t), intent(in) :: params
+       type(evp_b200_fields_t), intent(inout) :: fields
+       integer(c_int32_t), value :: flags
+     end function
+     integer(c_int) function evp_b200_download_stress(fields) bind(C, name='evp_b200_download_stress')
+       import :: c_int, evp_b200_fields_t
+       type(evp_b200_fields_t), intent(inout) :: fields
+     end function
      integer(c_int) function evp_b200_finalize() bind(C, name='evp_b200_finalize')
        import :: c_int
      end function
@@ -180,7 +190,7 @@ contains
                               waterxU   , wateryU   , forcexU   , forceyU   , &
                               umassdti  , fmU       , strintxU  , strintyU  , &
                               TbU       , taubxU    , taubyU    , uvel      , &
-                              vvel      , iceTmask  , iceUmask)
+                              vvel      , iceTmask  , iceUmask  , stress_on_host)
     use ice_dyn_shared, only: ndte, arlx1i, denom1, revp, brlx, e_factor, epp2i, capping, Ktens, u0, cosw, sinw, deltaminEVP
     use icepack_intfc,  only: icepack_query_parameters
     real(kind=dbl_kind), dimension(:,:,:), intent(inout), target, contiguous :: &
@@ -190,6 +200,11 @@ contains
     real(kind=dbl_kind), dimension(:,:,:), intent(in), target, contiguous :: &
          strength, cdn_ocnU, aiU, uocnU, vocnU, waterxU, wateryU, forcexU, forceyU, umassdti, fmU, TbU
     logical(kind=log_kind), dimension(:,:,:), intent(in) :: iceTmask, iceUmask
+    ! optional: .false. keeps the 12 stress arrays on the device between steps (EVP_B200_KEEP_STRESS, include/evp_b200.h);
+    ! the caller passes .true. on steps that write a restart or history file (ice_restart_driver.F90:150-231).
+    ! Absent = the host arrays are read and written every step, exactly like dyn_evp1d_run.
+    logical(kind=log_kind), intent(in), optional :: stress_on_host
+    integer(c_int32_t) :: flags
     type(evp_b200_params_t) :: p
     type(evp_b200_fields_t) :: f
     real(kind=dbl_kind) :: rhow
@@ -215,7 +230,16 @@ contains
     f%taubxU = c_loc(taubxU);      f%taubyU = c_loc(taubyU);      f%uvel = c_loc(uvel);        f%vvel = c_loc(vvel)
     f%iceTmask = c_loc(imaskT);    f%iceUmask = c_loc(imaskU)
 
-    call check(evp_b200_run_bgrid(p, f), 'evp_b200_run_bgrid')
+    flags = 0
+    if (present(stress_on_host)) then
+       flags = 1                               ! EVP_B200_KEEP_STRESS
+       if (stress_on_host) flags = 3           ! ... | EVP_B200_FETCH_STRESS
+    endif
+    if (flags /= 0) then
+       call check(evp_b200_run_bgrid_resident(p, f, flags), 'evp_b200_run_bgrid_resident')
+    else
+       call check(evp_b200_run_bgrid(p, f), 'evp_b200_run_bgrid')
+    endif
   end subroutine dyn_evp_b200_run
 
   !---------------------------------------------------------------------

@@ -224,6 +224,22 @@ int evp_b200_upload(const evp_b200_fields_t *fields);
 int evp_b200_subcycle(const evp_b200_params_t *params);
 int evp_b200_download(evp_b200_fields_t *fields);
 
+/* ---- next row: stresses resident on the device across dynamics steps ----------------
+ * The 12 stress arrays and the velocities are the whole carried dynamics state (ice_restart_driver.F90:150-231).
+ * Between two calls of evp() the reference touches the stresses in exactly one place: dyn_prep2 zeroes them where
+ * iceTmask is false (ice_dyn_shared.F90:717-730).  With EVP_B200_KEEP_STRESS the library keeps them on the device,
+ * applies that zeroing itself from the iceTmask of the call, and neither reads nor writes the host's stress arrays
+ * (24 of the 48 field transfers of a step).  The first call after evp_b200_init uploads them regardless.
+ * EVP_B200_FETCH_STRESS additionally copies them back in this call (restart / history steps);
+ * evp_b200_download_stress does the same outside a step.  Not for tripole grids, where the host symmetrises the
+ * stresses across the fold after the loop (ice_dyn_evp.F90:1322-1389). */
+enum {
+  EVP_B200_KEEP_STRESS  = 1,
+  EVP_B200_FETCH_STRESS = 2
+};
+int evp_b200_run_bgrid_resident(const evp_b200_params_t *params, evp_b200_fields_t *fields, int32_t flags);
+int evp_b200_download_stress(evp_b200_fields_t *fields);
+
 /* ---- measurement hooks (not part of the reference seam) ---------------------------------- */
 /* device time of the most recent evp_b200_subcycle in ms (CUDA events on the library's stream) */
 int evp_b200_last_loop_ms(double *ms);

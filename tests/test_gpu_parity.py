@@ -312,3 +312,68 @@ def test_interleaved_divsqrt_hits_the_fallback(oracle_mod, evp_lib, monkeypatch)
     ref = run_oracle(oracle_mod, c)
     got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED)
     assert_bitwise(got, ref)
+
+
+def _host_zero_stress_off_ice(fields):
+    """what dyn_prep2 does to the carried stresses before every loop (ice_dyn_shared.F90:717-730)."""
+    off = fields["iceTmask"] == 0
+    for n in abi.STRESS:
+        fields[n][off] = 0.0
+
+
+@pytest.mark.parametrize("ndte", [6, 7], ids=["even", "odd"])
+@pytest.mark.parametrize("bs", [None, (12, 10)], ids=["1block", "4blocks"])
+def test_resident_stress_equals_host_round_trip(oracle_mod, evp_lib, ndte, bs):
+    """consecutive dynamics steps with the stresses kept on the device (the ice edge moves between
+    steps, so dyn_prep2's zeroing matters) give the same bits as the oracle stepping with the stresses on the host."""
+    c = synth.make_case("tiny", seed=31, ndte=ndte, block_size=bs)
+    rng = np.random.Generator(np.random.PCG64(7))
+    ref = c.copy_fields()
+    got = c.copy_fields()
+    not_stress = [n for n in abi.FIELDS_INOUT if n not in abi.STRESS]
+    host_view = {n: got[n].copy() for n in abi.STRESS}   # what the host's stress arrays should hold
+    evp_lib.dyn_evp_b200_init(c.grid)
+    try:
+        for step in range(4):
+            if step:
+                # move the ice edge: drop ice from a different set of T cells every step
+                # (one decision per GLOBAL cell, so that every block copy of a cell agrees, as the reference's halo'd mask does)
+                keep = (rng.random(c.X["iceTmask"].shape) >= 0.15) & (c.X["iceTmask"] != 0)
+                # ghost ring of the extended global array must mirror the interior under the cyclic E-W boundary
+                keep[:, 0], keep[:, -1] = keep[:, -2], keep[:, 1]
+                newmask = synth.scatter(keep.astype(np.int32), c.blocks, c.grid["max_blocks"])
+                for f in (ref, got):
+                    f["iceTmask"] = newmask.copy()
+                    f["strength"] = f["strength"] * (1.0 + 0.01 * step)
+                _host_zero_stress_off_ice(ref)          # the host does this only where it still owns the stresses
+            oracle_mod.evp_run_bgrid(c.grid, c.params, ref)
+            fetch = (step == 2)
+            evp_lib.dyn_evp_b200_run_resident(dict(c.params, mode=abi.MODE_EXACT), got, keep_stress=True, fetch_stress=fetch)
+            assert_bitwise(got, ref, names=not_stress)   # velocities and diagnostics come back every step
+            if fetch:
+                assert_bitwise(got, ref)                 # ... the stresses when asked for
+                host_view = {n: got[n].copy() for n in abi.STRESS}
+            else:
+                for n in abi.STRESS:                     # ... and are otherwise not touched
+                    assert np.array_equal(got[n], host_view[n]), n
+        evp_lib.download_stress(got)
+        assert_bitwise(got, ref)
+        # back to the plain call: the host owns the stresses again
+        _host_zero_stress_off_ice(ref)
+        _host_zero_stress_off_ice(got)
+        oracle_mod.evp_run_bgrid(c.grid, c.params, ref)
+        evp_lib.dyn_evp_b200_run(dict(c.params, mode=abi.MODE_EXACT), got)
+        assert_bitwise(got, ref)
+    finally:
+        evp_lib.dyn_evp_b200_finalize()
+
+
+def test_resident_stress_refused_on_tripole(evp_lib):
+    c = synth.make_case("tiny", seed=41, ns="tripole", kmt="none", ndte=2)
+    f = c.copy_fields()
+    evp_lib.dyn_evp_b200_init(c.grid)
+    try:
+        with pytest.raises(evp_lib.EvpB200Error, match="tripole"):
+            evp_lib.dyn_evp_b200_run_resident(dict(c.params, mode=abi.MODE_EXACT), f)
+    finally:
+        evp_lib.dyn_evp_b200_finalize()
