@@ -160,6 +160,7 @@ struct Ctx {
   evp_b200_params_t cparams{};
   unsigned *d_cbar = nullptr;       // grid-barrier counter of the cooperative C-grid kernel
   int cgraph_launches = 0;
+  bool c_fused = true;               // three kernels per subcycle (kA, kB, k5) instead of five
   int c_max_ctas[2] = {0, 0};       // co-resident CTAs of that kernel (exact, fast); 0 = use the five-kernel form
 
   // KERNEL_PERSISTENT
@@ -800,6 +801,12 @@ static int do_init_cgrid(const evp_b200_cgrid_t *cg) {
     *dst[q] = p;
   }
   c.dxT = g.dom.dxT; c.dyT = g.dom.dyT; c.DminTarea = g.dom.DminTarea;
+  {
+    double *q[5] = {};
+    for (auto &p : q) if (calloc_dom(p)) return 1;
+    CK(exact::launch_cgrid_static(c, q[0], q[1], q[2], q[3], q[4], g.stream));
+    c.rhalf_dyE = q[0]; c.r_dxE = q[1]; c.rhalf_dxN = q[2]; c.r_dyN = q[3]; c.uareaavgr = q[4];
+  }
   // 43 time-varying fields, each with a staging buffer in block layout
   double **flds[43] = {&c.uvelE, &c.vvelE, &c.uvelN, &c.vvelN, &c.uvel, &c.vvel, &c.stresspT, &c.stressmT, &c.stress12T, &c.stress12U,
                        &c.zetax2T, &c.etax2T, &c.etax2U, &c.strengthU, &c.divergU, &c.tensionU, &c.shearU, &c.deltaU,
@@ -814,7 +821,9 @@ static int do_init_cgrid(const evp_b200_cgrid_t *cg) {
     CK(cudaMalloc(&st, bblk));
     g.cstage.push_back(st);
   }
-  if (calloc_dom(c.uvelE_init) || calloc_dom(c.vvelN_init)) return 1;
+  if (calloc_dom(c.uvelE_init) || calloc_dom(c.vvelN_init) || calloc_dom(c.stress12Ub)) return 1;
+  g.c_fused = true;
+  if (const char *e = getenv("EVP_B200_CGRID_FUSED")) g.c_fused = (e[0] != '0');
   for (int q = 0; q < 4; ++q) { CK(cudaMalloc(&g.cmask[q], g.ndom)); CK(cudaMemsetAsync(g.cmask[q], 0, g.ndom, g.stream)); }
   c.maskT = g.cmask[0]; c.maskU = g.cmask[1]; c.maskE = g.cmask[2]; c.maskN = g.cmask[3];
   CK(cudaMalloc(&g.d_cbar, sizeof(unsigned)));
@@ -868,7 +877,10 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
       continue;
     }
     CK(cudaMemcpyAsync(g.cstage[q], t.h, bblk, cudaMemcpyHostToDevice, g.stream));
-    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(t.dv, g.cstage[q], g.d_gsrc, (int)g.ndom);
+    if (t.dv == c.stress12U)  // ping-ponged by the fused form: both copies start identical
+      pack2_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(c.stress12U, c.stress12Ub, g.cstage[q], g.d_gsrc, (int)g.ndom);
+    else
+      pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(t.dv, g.cstage[q], g.d_gsrc, (int)g.ndom);
   }
   const int32_t *hm[4] = {f->iceTmask, f->iceUmask, f->iceEmask, f->iceNmask};
   for (int q = 0; q < 4; ++q) {
@@ -900,6 +912,9 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
         le = exact ? exact::launch_cgrid_coop(c, k, p->ndte, g.d_cbar, max_ctas, g.stream)
                    : fast::launch_cgrid_coop(c, k, p->ndte, g.d_cbar, max_ctas, g.stream);
       nl = 1;
+    } else if (g.c_fused) {
+      for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub)
+        le = exact ? exact::launch_cgrid_subcycle_fused(c, k, ksub & 1, g.stream, &nl) : fast::launch_cgrid_subcycle_fused(c, k, ksub & 1, g.stream, &nl);
     } else {
       for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub)
         le = exact ? exact::launch_cgrid_subcycle(c, k, g.stream, &nl) : fast::launch_cgrid_subcycle(c, k, g.stream, &nl);
@@ -927,8 +942,10 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
       unpack_f64<<<grid_blocks(g.n_sig), 256, 0, g.stream>>>(g.cstage[q], t.dv, g.d_sig_lin, g.d_sig_dom, g.n_sig);
     else if (t.kind == 'n' || t.kind == 'y')
       unpack_f64<<<grid_blocks(g.n_int), 256, 0, g.stream>>>(g.cstage[q], t.dv, g.d_int_lin, g.d_int_dom, g.n_int);
-    else
-      unpack_f64<<<grid_blocks(g.n_uv), 256, 0, g.stream>>>(g.cstage[q], t.dv, g.d_uv_lin, g.d_uv_dom, g.n_uv);
+    else {
+      const bool in_b = (t.dv == c.stress12U) && g.c_fused && g.c_max_ctas[exact ? 0 : 1] == 0 && (p->ndte & 1);
+      unpack_f64<<<grid_blocks(g.n_uv), 256, 0, g.stream>>>(g.cstage[q], in_b ? c.stress12Ub : t.dv, g.d_uv_lin, g.d_uv_dom, g.n_uv);
+    }
     CK(cudaMemcpyAsync((void *)t.h, g.cstage[q], bblk, cudaMemcpyDeviceToHost, g.stream));
   }
   CK(cudaGetLastError());

@@ -13,7 +13,7 @@
 // The halo points themselves are the on-rank cyclic wrap: the producing thread also stores the ghost
 // copies (ring_store).  One GPU, non-tripole.  Compiled twice (exact: -fmad=false, fast) like the B-grid
 // kernels; every expression keeps the reference's operator order.
-#include "evp_internal.h"
+#include "evp_math.cuh"  // div_fast: the IEEE division fast path as straight-line code
 
 #ifndef EVP_NS
 #error "compile with -DEVP_NS=exact or -DEVP_NS=fast"
@@ -22,7 +22,8 @@
 namespace evp {
 namespace EVP_NS {
 
-#define AT(i, j) ((size_t)(j)*d.ld + (size_t)(i))
+// sub-domains are refused at 2^31 cells (evp_b200_init), so 32-bit cell indices are enough
+#define AT(i, j) ((j)*d.ld + (i))
 
 // store val at (i,j) and at the ghost cells that alias it under an on-rank cyclic wrap.
 // sides: 3 = both ghost sides (a halo update), 1 = only the E/N ghost (cells the reference computes redundantly).
@@ -31,6 +32,7 @@ namespace EVP_NS {
 __device__ __forceinline__ void ring_store(const CDom &d, double *__restrict__ A, int i, int j, double val, int sides,
                                            bool zero_closed) {
   A[AT(i, j)] = val;
+  if (!(i == 1 || i == d.nx || j == 1 || j == d.ny)) return;  // only the outermost interior ring has ghost aliases
   int ig = -1, jg = -1;
   if (d.wrap_ew) ig = (i == 1) ? d.nx + 1 : ((i == d.nx && (sides & 2)) ? 0 : -1);
   if (d.wrap_ns) jg = (j == 1) ? d.ny + 1 : ((j == d.ny && (sides & 2)) ? 0 : -1);
@@ -50,7 +52,10 @@ __device__ __forceinline__ void ring_store(const CDom &d, double *__restrict__ A
 
 __device__ __forceinline__ void visc_c(double strength, double dmin, double Delta, const KParams &k, double &zetax2,
                                        double &etax2, double &rep_prs) {
-  const double tmp = k.capping * (strength / fmax(Delta, dmin)) + (1.0 - k.capping) * (strength / (Delta + dmin));
+  // capping == 1: the second term is (1-1)*(finite, >= 0) = +0 and x + 0 == x bit for bit (strength >= 0, dmin > 0), so the
+  // second division is skipped -- same shortcut as the B-grid stress_point
+  const double tmp = (k.capping == 1.0) ? strength / fmax(Delta, dmin)
+                                        : k.capping * (strength / fmax(Delta, dmin)) + (1.0 - k.capping) * (strength / (Delta + dmin));
   zetax2 = (1.0 + k.Ktens) * tmp;
   rep_prs = (1.0 - k.Ktens) * tmp * Delta;
   etax2 = k.epp2i * zetax2;
@@ -68,13 +73,12 @@ template <bool CG>
 __device__ __forceinline__ double M(const double *p) { return CG ? __ldcg(p) : *p; }
 
 // ---- k1 ------------------------------------------------------------------------------------------------
-template <bool CG>
-__device__ __forceinline__ void p1_strain_U(const CDom &d, const KParams &k, int i, int j) {
-  if (i > d.nx || j > d.ny) return;
-  const size_t c = AT(i, j);
-  double div = 0.0, ten = 0.0, shr = 0.0, del = 0.0;
+// strain rates at one U point (shared.F90:2319-2430); zero where there is no ice (the reference zero-fills)
+template <bool CG = false>
+__device__ __forceinline__ void strain_U_at(const CDom &d, const KParams &k, int c, double &div, double &ten, double &shr, double &del) {
+  div = 0.0; ten = 0.0; shr = 0.0; del = 0.0;
   if (d.maskU[c]) {
-    const size_t e = c + 1, n = c + d.ld;
+    const int e = c + 1, n = c + d.ld;
     const double npc = d.npm[c], npe = d.npm[e], epc = d.epm[c], epn = d.epm[n];
     const double uNip1j = M<CG>(d.uvelN + e) * npe + (npc - npe) * npc * d.ratiodxN[c] * M<CG>(d.uvelN + c);
     const double uNij = M<CG>(d.uvelN + c) * npc + (npe - npc) * npe * d.ratiodxNr[c] * M<CG>(d.uvelN + e);
@@ -91,6 +95,13 @@ __device__ __forceinline__ void p1_strain_U(const CDom &d, const KParams &k, int
     shr = dxU * (uEijp1 - uEij) - uU * ddxE + dyU * (vNip1j - vNij) - vU * ddyN;
     del = sqrt(div * div + k.e_factor * (ten * ten + shr * shr));
   }
+}
+template <bool CG>
+__device__ __forceinline__ void p1_strain_U(const CDom &d, const KParams &k, int i, int j) {
+  if (i > d.nx || j > d.ny) return;
+  const int c = AT(i, j);
+  double div, ten, shr, del;
+  strain_U_at<CG>(d, k, c, div, ten, shr, del);
   d.divergU[c] = div;
   d.tensionU[c] = ten;
   d.deltaU[c] = del;
@@ -104,20 +115,26 @@ __global__ void __launch_bounds__(256) k1_strain_U(const __grid_constant__ CDom 
 // ---- k2 ------------------------------------------------------------------------------------------------
 // T cells 1..nx+1 x 1..ny+1 (N/E ghost cells are in the reference's list, shared.F90:740-749); a ghost row or
 // column that merely aliases the interior under the on-rank wrap is filled by ring_store instead.
-template <bool CG>
-__device__ __forceinline__ void p2_stress_T(const CDom &d, const KParams &k, int i, int j) {
-  if (i > (d.wrap_ew ? d.nx : d.nx + 1) || j > (d.wrap_ns ? d.ny : d.ny + 1)) return;
-  const size_t c = AT(i, j);
-  if (!d.maskT[c]) return;
-  const size_t w = c - 1, s = c - d.ld, sw = s - 1;
+template <bool CG = false>
+__device__ __forceinline__ void stress_T_at(const CDom &d, const KParams &k, int i, int j, int c, double shc, double shs, double shsw,
+                                            double shw) {
+  const int w = c - 1, s = c - d.ld, sw = s - 1;
   const double dyEc = d.dyE[c], dyEw = d.dyE[w], dxNc = d.dxN[c], dxNs = d.dxN[s];
   const double uEc = M<CG>(d.uvelE + c), uEw = M<CG>(d.uvelE + w), vNc = M<CG>(d.vvelN + c), vNs = M<CG>(d.vvelN + s);
   const double dxT = d.dxT[c], dyT = d.dyT[c];
   const double divT = dyEc * uEc - dyEw * uEw + dxNc * vNc - dxNs * vNs;
-  const double tensionT = (dyT * dyT) * (uEc / dyEc - uEw / dyEw) - (dxT * dxT) * (vNc / dxNc - vNs / dxNs);
+  // four independent quotients: fast paths first (interleaved by the scheduler), the rare out-of-range operand afterwards
+  bool ok0, ok1, ok2, ok3;
+  double q0 = div_fast(uEc, dyEc, ok0), q1 = div_fast(uEw, dyEw, ok1), q2 = div_fast(vNc, dxNc, ok2), q3 = div_fast(vNs, dxNs, ok3);
+  if (!(ok0 && ok1 && ok2 && ok3)) {
+    if (!ok0) q0 = uEc / dyEc;
+    if (!ok1) q1 = uEw / dyEw;
+    if (!ok2) q2 = vNc / dxNc;
+    if (!ok3) q3 = vNs / dxNs;
+  }
+  const double tensionT = (dyT * dyT) * (q0 - q1) - (dxT * dxT) * (q2 - q3);
   const double uac = d.uarea[c], uas = d.uarea[s], uasw = d.uarea[sw], uaw = d.uarea[w];
-  const double shc = M<CG>(d.shearU + c), shs = M<CG>(d.shearU + s), shsw = M<CG>(d.shearU + sw), shw = M<CG>(d.shearU + w);
-  const double uareaavgr = 1.0 / (uac + uas + uasw + uaw);
+  const double uareaavgr = d.uareaavgr[c];  // 1.0 / (uac + uas + uasw + uaw), static: divided once in evp_b200_init_cgrid
   const double shearTsqr = (shc * shc * uac + shs * shs * uas + shsw * shsw * uasw + shw * shw * uaw) * uareaavgr;
   const double shearT = (shc * uac + shs * uas + shsw * uasw + shw * uaw) * uareaavgr;
   const double DeltaT = sqrt(divT * divT + k.e_factor * (tensionT * tensionT + shearTsqr));
@@ -133,35 +150,50 @@ __device__ __forceinline__ void p2_stress_T(const CDom &d, const KParams &k, int
   ring_store(d, d.stressmT, i, j, sm, 3, false);
   ring_store(d, d.stress12T, i, j, s12, 1, false);  // not halo-updated: only the redundantly computed N/E ghost copy
 }
+template <bool CG>
+__device__ __forceinline__ void p2_stress_T(const CDom &d, const KParams &k, int i, int j) {
+  if (i > (d.wrap_ew ? d.nx : d.nx + 1) || j > (d.wrap_ns ? d.ny : d.ny + 1)) return;
+  const int c = AT(i, j);
+  if (!d.maskT[c]) return;
+  const int w = c - 1, s = c - d.ld, sw = s - 1;
+  stress_T_at<CG>(d, k, i, j, c, M<CG>(d.shearU + c), M<CG>(d.shearU + s), M<CG>(d.shearU + sw), M<CG>(d.shearU + w));
+}
 
 __global__ void __launch_bounds__(256) k2_stress_T(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
   p2_stress_T<false>(d, k, 1 + blockIdx.x * blockDim.x + threadIdx.x, 1 + blockIdx.y * blockDim.y + threadIdx.y);
 }
 
 // ---- k3 ------------------------------------------------------------------------------------------------
-template <bool CG>
-__device__ __forceinline__ void p3_stress_U(const CDom &d, const KParams &k, int i, int j) {
-  if (i > d.nx || j > d.ny) return;
-  const size_t c = AT(i, j);
-  const size_t e = c + 1, n = c + d.ld, ne = n + 1;
+// stress12U at one U point: returns whether the point is updated (ice), `avg` = the T->U average it stores either way
+template <bool CG = false>
+__device__ __forceinline__ bool stress_U_at(const CDom &d, const KParams &k, int c, const double *s12old, double &avg, double &s12) {
+  const int e = c + 1, n = c + d.ld, ne = n + 1;
   const double *__restrict__ src = (k.visc_method == 1) ? d.strength : d.etax2T;
   const double mc = d.hm[c], me = d.hm[e], mn = d.hm[n], mne = d.hm[ne];
   const double wc = d.tarea[c], we = d.tarea[e], wn = d.tarea[n], wne = d.tarea[ne];
   const double wtmp = (mc * wc + me * we + mn * wn + mne * wne);
-  double avg = 0.0;
+  avg = 0.0;
   if (wtmp != 0.0) avg = (mc * M<CG>(src + c) * wc + me * M<CG>(src + e) * we + mn * M<CG>(src + n) * wn + mne * M<CG>(src + ne) * wne) / wtmp;
-  if (k.visc_method == 1) d.strengthU[c] = avg; else d.etax2U[c] = avg;
-  if (d.maskU[c]) {
-    const double relax = 1.0 - k.arlx1i * k.revp;
-    double etax2U = avg;
-    if (k.visc_method == 1) {
-      const double DminUarea = k.deltaminEVP * d.uarea[c];
-      double z, r;
-      visc_c(avg, DminUarea, M<CG>(d.deltaU + c), k, z, etax2U, r);
-    }
-    const double s12 = (M<CG>(d.stress12U + c) * relax + k.arlx1i * 0.5 * etax2U * M<CG>(d.shearU + c)) * k.denom1;
-    ring_store(d, d.stress12U, i, j, s12, 3, false);
+  s12 = M<CG>(s12old + c);
+  if (!d.maskU[c]) return false;
+  const double relax = 1.0 - k.arlx1i * k.revp;
+  double etax2U = avg;
+  if (k.visc_method == 1) {
+    const double DminUarea = k.deltaminEVP * d.uarea[c];
+    double z, r;
+    visc_c(avg, DminUarea, M<CG>(d.deltaU + c), k, z, etax2U, r);
   }
+  s12 = (s12 * relax + k.arlx1i * 0.5 * etax2U * M<CG>(d.shearU + c)) * k.denom1;
+  return true;
+}
+template <bool CG>
+__device__ __forceinline__ void p3_stress_U(const CDom &d, const KParams &k, int i, int j) {
+  if (i > d.nx || j > d.ny) return;
+  const int c = AT(i, j);
+  double avg, s12;
+  const bool upd = stress_U_at<CG>(d, k, c, d.stress12U, avg, s12);
+  if (k.visc_method == 1) d.strengthU[c] = avg; else d.etax2U[c] = avg;
+  if (upd) ring_store(d, d.stress12U, i, j, s12, 3, false);
 }
 
 __global__ void __launch_bounds__(256) k3_stress_U(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
@@ -169,24 +201,23 @@ __global__ void __launch_bounds__(256) k3_stress_U(const __grid_constant__ CDom 
 }
 
 // ---- k4 ------------------------------------------------------------------------------------------------
-template <bool CG>
-__device__ __forceinline__ void p4_momentum(const CDom &d, const KParams &k, int i, int j) {
-  if (i > d.nx || j > d.ny) return;
-  const size_t c = AT(i, j);
+template <bool CG = false>
+__device__ __forceinline__ void momentum_at(const CDom &d, const KParams &k, int i, int j, int c, double s12c, double s12s, double s12w) {
   if (d.maskE[c]) {
-    const size_t e = c + 1, s = c - d.ld;
+    const int e = c + 1, s = c - d.ld;
     const double dyE = d.dyE[c], dyTe = d.dyT[e], dyTc = d.dyT[c], dxUc = d.dxU[c], dxUs = d.dxU[s];
     const double strintx = d.rheofactE[c] * d.earear[c] *
                            (0.5 * dyE * (M<CG>(d.stresspT + e) - M<CG>(d.stresspT + c)) +
-                            (0.5 / dyE) * ((dyTe * dyTe) * M<CG>(d.stressmT + e) - (dyTc * dyTc) * M<CG>(d.stressmT + c)) +
-                            (1.0 / d.dxE[c]) * ((dxUc * dxUc) * M<CG>(d.stress12U + c) - (dxUs * dxUs) * M<CG>(d.stress12U + s)));
+                            d.rhalf_dyE[c] * ((dyTe * dyTe) * M<CG>(d.stressmT + e) - (dyTc * dyTc) * M<CG>(d.stressmT + c)) +
+                            d.r_dxE[c] * ((dxUc * dxUc) * s12c - (dxUs * dxUs) * s12s));
     d.strintxE[c] = strintx;
     const double uold = M<CG>(d.uvelE + c), vold = M<CG>(d.vvelE + c);
     const double du = d.uocnE[c] - uold, dv = d.vocnE[c] - vold;
     const double vrel = d.aiE[c] * k.rhow * d.cdnE[c] * sqrt(du * du + dv * dv);
     const double taux = vrel * d.waterxE[c];
-    const double ccc = sqrt(uold * uold + vold * vold) + k.u0;
-    const double Cb = d.TbE[c] / ccc;
+    // no grounded ice: Tb is (+-)0 and (+-)0 / (finite positive) is that same zero (see stepu_point)
+    const double Tb = d.TbE[c];
+    const double Cb = (Tb == 0.0 && k.u0 > 0.0) ? Tb : Tb / (sqrt(uold * uold + vold * vold) + k.u0);
     const double m = d.emassdti[c], fm = d.fmE[c];
     const double cca = (k.brlx + k.revp) * m + vrel * k.cosw + Cb;
     const double ccb = fm + copysign(1.0, fm) * vrel * k.sinw;
@@ -196,19 +227,20 @@ __device__ __forceinline__ void p4_momentum(const CDom &d, const KParams &k, int
     d.taubxE[c] = -un * Cb;
   }
   if (d.maskN[c]) {
-    const size_t n = c + d.ld, w = c - 1;
+    const int n = c + d.ld, w = c - 1;
     const double dxN = d.dxN[c], dxTn = d.dxT[n], dxTc = d.dxT[c], dyUc = d.dyU[c], dyUw = d.dyU[w];
     const double strinty = d.rheofactN[c] * d.narear[c] *
                            (0.5 * dxN * (M<CG>(d.stresspT + n) - M<CG>(d.stresspT + c)) -
-                            (0.5 / dxN) * ((dxTn * dxTn) * M<CG>(d.stressmT + n) - (dxTc * dxTc) * M<CG>(d.stressmT + c)) +
-                            (1.0 / d.dyN[c]) * ((dyUc * dyUc) * M<CG>(d.stress12U + c) - (dyUw * dyUw) * M<CG>(d.stress12U + w)));
+                            d.rhalf_dxN[c] * ((dxTn * dxTn) * M<CG>(d.stressmT + n) - (dxTc * dxTc) * M<CG>(d.stressmT + c)) +
+                            d.r_dyN[c] * ((dyUc * dyUc) * s12c - (dyUw * dyUw) * s12w));
     d.strintyN[c] = strinty;
     const double uold = M<CG>(d.uvelN + c), vold = M<CG>(d.vvelN + c);
     const double du = d.uocnN[c] - uold, dv = d.vocnN[c] - vold;
     const double vrel = d.aiN[c] * k.rhow * d.cdnN[c] * sqrt(du * du + dv * dv);
     const double tauy = vrel * d.wateryN[c];
-    const double ccc = sqrt(uold * uold + vold * vold) + k.u0;
-    const double Cb = d.TbN[c] / ccc;
+    // no grounded ice: Tb is (+-)0 and (+-)0 / (finite positive) is that same zero (see stepu_point)
+    const double Tb = d.TbN[c];
+    const double Cb = (Tb == 0.0 && k.u0 > 0.0) ? Tb : Tb / (sqrt(uold * uold + vold * vold) + k.u0);
     const double m = d.nmassdti[c], fm = d.fmN[c];
     const double cca = (k.brlx + k.revp) * m + vrel * k.cosw + Cb;
     const double ccb = fm + copysign(1.0, fm) * vrel * k.sinw;
@@ -219,32 +251,54 @@ __device__ __forceinline__ void p4_momentum(const CDom &d, const KParams &k, int
   }
 }
 
+template <bool CG>
+__device__ __forceinline__ void p4_momentum(const CDom &d, const KParams &k, int i, int j) {
+  if (i > d.nx || j > d.ny) return;
+  const int c = AT(i, j);
+  momentum_at<CG>(d, k, i, j, c, M<CG>(d.stress12U + c), M<CG>(d.stress12U + c - d.ld), M<CG>(d.stress12U + c - 1));
+}
+
 __global__ void __launch_bounds__(256) k4_momentum(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
   p4_momentum<false>(d, k, 1 + blockIdx.x * blockDim.x + threadIdx.x, 1 + blockIdx.y * blockDim.y + threadIdx.y);
 }
 
 // ---- k5 ------------------------------------------------------------------------------------------------
+// grid_average_X2YA (ice_grid.F90:4388-4606): area-weighted average, zero where the weights vanish.  The numerator and
+// the denominator are formed here, the four quotients of a point are then taken together (div_fast) in p5_interp.
 template <bool CG>
-__device__ __forceinline__ double avg4(const double *w1, const double *__restrict__ wg, size_t a, size_t b, size_t c, size_t e) {
+__device__ __forceinline__ void avg4_terms(const double *w1, const double *__restrict__ wg, int a, int b, int c, int e, double &num,
+                                           double &den) {
   const double wa = wg[a], wb = wg[b], wc = wg[c], we = wg[e];
-  const double wtmp = (wa + wb + wc + we);
-  return (wtmp != 0.0) ? (M<CG>(w1 + a) * wa + M<CG>(w1 + b) * wb + M<CG>(w1 + c) * wc + M<CG>(w1 + e) * we) / wtmp : 0.0;
+  den = (wa + wb + wc + we);
+  num = (M<CG>(w1 + a) * wa + M<CG>(w1 + b) * wb + M<CG>(w1 + c) * wc + M<CG>(w1 + e) * we);
 }
 template <bool CG>
-__device__ __forceinline__ double avg2(const double *w1, const double *__restrict__ wg, size_t a, size_t b) {
+__device__ __forceinline__ void avg2_terms(const double *w1, const double *__restrict__ wg, int a, int b, double &num, double &den) {
   const double wa = wg[a], wb = wg[b];
-  const double wtmp = (wa + wb);
-  return (wtmp != 0.0) ? (M<CG>(w1 + a) * wa + M<CG>(w1 + b) * wb) / wtmp : 0.0;
+  den = (wa + wb);
+  num = (M<CG>(w1 + a) * wa + M<CG>(w1 + b) * wb);
 }
 template <bool CG>
 __device__ __forceinline__ void p5_interp(const CDom &d, int i, int j) {
   if (i > d.nx || j > d.ny) return;
-  const size_t c = AT(i, j);
-  const size_t e = c + 1, w = c - 1, n = c + d.ld, s = c - d.ld;
-  const double uN = avg4<CG>(d.uvelE, d.earea, w, c, n - 1, n) * d.npm[c];      // E2NA 'NW'
-  const double vE = avg4<CG>(d.vvelN, d.narea, s, s + 1, c, e) * d.epm[c];      // N2EA 'SE'
-  const double uU = avg2<CG>(d.uvelE, d.earea, c, n) * d.uvm[c];                // E2UA 'N'
-  const double vU = avg2<CG>(d.vvelN, d.narea, c, e) * d.uvm[c];                // N2UA 'E'
+  const int c = AT(i, j);
+  const int e = c + 1, w = c - 1, n = c + d.ld, s = c - d.ld;
+  double num[4], den[4], q[4];
+  bool ok[4];
+  avg4_terms<CG>(d.uvelE, d.earea, w, c, n - 1, n, num[0], den[0]);      // E2NA 'NW'
+  avg4_terms<CG>(d.vvelN, d.narea, s, s + 1, c, e, num[1], den[1]);      // N2EA 'SE'
+  avg2_terms<CG>(d.uvelE, d.earea, c, n, num[2], den[2]);                // E2UA 'N'
+  avg2_terms<CG>(d.vvelN, d.narea, c, e, num[3], den[3]);                // N2UA 'E'
+#pragma unroll
+  for (int r = 0; r < 4; ++r) q[r] = div_fast(num[r], den[r], ok[r]);
+  if (!(ok[0] && ok[1] && ok[2] && ok[3])) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) if (!ok[r]) q[r] = num[r] / den[r];
+  }
+  const double uN = ((den[0] != 0.0) ? q[0] : 0.0) * d.npm[c];
+  const double vE = ((den[1] != 0.0) ? q[1] : 0.0) * d.epm[c];
+  const double uU = ((den[2] != 0.0) ? q[2] : 0.0) * d.uvm[c];
+  const double vU = ((den[3] != 0.0) ? q[3] : 0.0) * d.uvm[c];
   ring_store(d, d.uvelN, i, j, uN, 3, true);
   ring_store(d, d.vvelE, i, j, vE, 3, true);
   ring_store(d, d.uvel, i, j, uU, 3, true);
@@ -252,6 +306,117 @@ __device__ __forceinline__ void p5_interp(const CDom &d, int i, int j) {
 }
 __global__ void __launch_bounds__(256) k5_interp(const __grid_constant__ CDom d) {
   p5_interp<false>(d, 1 + blockIdx.x * blockDim.x + threadIdx.x, 1 + blockIdx.y * blockDim.y + threadIdx.y);
+}
+
+// ---- fused forms: three kernels per subcycle instead of five ------------------------------------------------
+// kA = k1 + k2 and kB = k3 + k4 on overlapping 32 x 8 tiles, the way the B-grid fused kernel joins stress and stepu:
+// thread (tx,ty) of a tile holds point (i,j) = (ti-1+tx, tj-1+ty); the first phase runs on all 32 x 8 points (the
+// west column and south row belong to the neighbouring tiles and are recomputed, not stored), hands its result to the
+// second phase through shared memory, and the second phase runs on the 31 x 7 points with tx,ty >= 1, which are the
+// points the tile owns.  A ghost point that aliases the interior under an on-rank cyclic wrap is recomputed at the
+// interior point it aliases; a ghost point outside a closed/open edge is never written by the loop and is read back.
+// kB's first phase updates stress12U in place (new = f(old)), so the recomputed copies would race with the owner's
+// store: stress12U is ping-ponged between two arrays (both start identical; cells off the ice are never written).
+constexpr int GBX = 32, GBY = 8;
+
+// index of the interior point a ring point aliases (wrap), or -1 when the point is a constant ghost / outside
+__device__ __forceinline__ bool alias_point(const CDom &d, int &i, int &j) {
+  if (i < 1) { if (!d.wrap_ew) return false; i += d.nx; }
+  if (j < 1) { if (!d.wrap_ns) return false; j += d.ny; }
+  if (i > d.nx) { if (!d.wrap_ew) return false; i -= d.nx; }
+  if (j > d.ny) { if (!d.wrap_ns) return false; j -= d.ny; }
+  return i >= 1 && i <= d.nx && j >= 1 && j <= d.ny;
+}
+
+__global__ void __launch_bounds__(GBX *GBY) kA_strainU_stressT(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  __shared__ double sh[GBY][GBX];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = blockIdx.x * (GBX - 1) + tx, j = blockIdx.y * (GBY - 1) + ty;  // ti = 1 + bx*(GBX-1), point ti-1+tx
+  const int nxT = d.wrap_ew ? d.nx : d.nx + 1, nyT = d.wrap_ns ? d.ny : d.ny + 1;
+  // phase 1: shearU (and divergU, tensionU, deltaU) at the U point (i,j)
+  double shr = 0.0;
+  if (i <= d.nx + 1 && j <= d.ny + 1) {
+    int ia = i, ja = j;
+    if (alias_point(d, ia, ja)) {
+      double div, ten, del;
+      strain_U_at(d, k, AT(ia, ja), div, ten, shr, del);
+      if (tx >= 1 && ty >= 1 && ia == i && ja == j) {  // an interior point this tile owns
+        const int c = AT(i, j);
+        d.divergU[c] = div;
+        d.tensionU[c] = ten;
+        d.deltaU[c] = del;
+        ring_store(d, d.shearU, i, j, shr, 3, false);
+      }
+    } else {
+      shr = d.shearU[AT(i, j)];  // ghost outside a non-cyclic edge: the loop never writes it
+    }
+  }
+  sh[ty][tx] = shr;
+  __syncthreads();
+  // phase 2: the T cell (i,j); its corners are the U points (i,j) (i-1,j) (i,j-1) (i-1,j-1)
+  if (tx >= 1 && ty >= 1 && i <= nxT && j <= nyT) {
+    const int c = AT(i, j);
+    if (d.maskT[c]) stress_T_at(d, k, i, j, c, sh[ty][tx], sh[ty - 1][tx], sh[ty - 1][tx - 1], sh[ty][tx - 1]);
+  }
+}
+
+__global__ void __launch_bounds__(GBX *GBY) kB_stressU_momentum(const __grid_constant__ CDom d, const __grid_constant__ KParams k, int cur) {
+  __shared__ double sh[GBY][GBX];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = blockIdx.x * (GBX - 1) + tx, j = blockIdx.y * (GBY - 1) + ty;
+  const double *__restrict__ s12old = cur ? d.stress12Ub : d.stress12U;
+  double *__restrict__ s12new = cur ? d.stress12U : d.stress12Ub;
+  // phase 1: stress12U (and etax2U / strengthU) at the U point (i,j)
+  double s12 = 0.0;
+  if (i <= d.nx + 1 && j <= d.ny + 1) {
+    int ia = i, ja = j;
+    if (alias_point(d, ia, ja)) {
+      const int ca = AT(ia, ja);
+      double avg;
+      const bool upd = stress_U_at(d, k, ca, s12old, avg, s12);
+      if (tx >= 1 && ty >= 1 && ia == i && ja == j) {
+        if (k.visc_method == 1) d.strengthU[ca] = avg; else d.etax2U[ca] = avg;
+        if (upd) ring_store(d, s12new, i, j, s12, 3, false);
+      }
+    } else {
+      s12 = s12old[AT(i, j)];
+    }
+  }
+  sh[ty][tx] = s12;
+  __syncthreads();
+  // phase 2: the E and N points (i,j)
+  if (tx >= 1 && ty >= 1 && i <= d.nx && j <= d.ny) momentum_at(d, k, i, j, AT(i, j), sh[ty][tx], sh[ty - 1][tx], sh[ty][tx - 1]);
+}
+
+// quotients of static geometry that the reference re-divides every subcycle (ice_dyn_evp.F90:2230-2240, 2398-2408,
+// ice_dyn_shared.F90:2296): an IEEE division of the same operands gives the same bits whenever it is done, so they are
+// divided once here
+__global__ void cgrid_static_quotients(const __grid_constant__ CDom d, double *rhalf_dyE, double *r_dxE, double *rhalf_dxN, double *r_dyN,
+                                       double *uareaavgr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > d.nx + 1 || j > d.ny + 1) return;
+  const int c = AT(i, j);
+  rhalf_dyE[c] = 0.5 / d.dyE[c];
+  r_dxE[c] = 1.0 / d.dxE[c];
+  rhalf_dxN[c] = 0.5 / d.dxN[c];
+  r_dyN[c] = 1.0 / d.dyN[c];
+  if (i >= 1 && j >= 1) uareaavgr[c] = 1.0 / (d.uarea[c] + d.uarea[c - d.ld] + d.uarea[c - d.ld - 1] + d.uarea[c - 1]);
+}
+cudaError_t launch_cgrid_static(const CDom &d, double *rhalf_dyE, double *r_dxE, double *rhalf_dxN, double *r_dyN, double *uareaavgr,
+                                cudaStream_t s) {
+  dim3 b(32, 8), g((d.nx + 2 + 31) / 32, (d.ny + 2 + 7) / 8);
+  cgrid_static_quotients<<<g, b, 0, s>>>(d, rhalf_dyE, r_dxE, rhalf_dxN, r_dyN, uareaavgr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur, cudaStream_t s, int *launches) {
+  dim3 b(GBX, GBY), g((d.nx + 1 + GBX - 2) / (GBX - 1), (d.ny + 1 + GBY - 2) / (GBY - 1));
+  dim3 b5(32, 8), g5((d.nx + 31) / 32, (d.ny + 7) / 8);
+  kA_strainU_stressT<<<g, b, 0, s>>>(d, p);
+  kB_stressU_momentum<<<g, b, 0, s>>>(d, p, cur);
+  k5_interp<<<g5, b5, 0, s>>>(d);
+  *launches += 3;
+  return cudaGetLastError();
 }
 
 // ---- all ndte subcycles in ONE cooperative launch -----------------------------------------------------------

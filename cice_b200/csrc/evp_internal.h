@@ -42,8 +42,10 @@ struct CDom {
   // static geometry
   const double *dxN, *dyE, *dxE, *dyN, *dxU, *dyU, *dxT, *dyT, *uarea, *DminTarea, *tarea, *hm, *earea, *narea, *earear, *narear;
   const double *ratiodxN, *ratiodxNr, *ratiodyE, *ratiodyEr, *epm, *npm, *uvm;
+  const double *rhalf_dyE, *r_dxE, *rhalf_dxN, *r_dyN, *uareaavgr;  // static quotients, divided once at init (evp_cgrid.cu)
   // carried state
   double *uvelE, *vvelE, *uvelN, *vvelN, *uvel, *vvel, *stresspT, *stressmT, *stress12T, *stress12U;
+  double *stress12Ub;  // second copy of stress12U for the fused three-kernel form (ping-pong, see evp_cgrid.cu)
   // work arrays the reference leaves behind
   double *zetax2T, *etax2T, *etax2U, *strengthU, *divergU, *tensionU, *shearU, *deltaU, *strintxE, *strintyN, *taubxE, *taubyN;
   // per-step inputs
@@ -112,6 +114,8 @@ struct PersistPlan {
   cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s); \
   cudaError_t launch_queue(const Dom &d, const KParams &p, int ndte, unsigned *progress, unsigned *counter, int nctas, cudaStream_t s); \
   cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \
+  cudaError_t launch_cgrid_static(const CDom &d, double *rhalf_dyE, double *r_dxE, double *rhalf_dxN, double *r_dyN, double *uareaavgr, cudaStream_t s); \
+  cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur, cudaStream_t s, int *launches);  \
   cudaError_t launch_cgrid_coop(const CDom &d, const KParams &p, int ndte, unsigned *bar, int max_ctas, cudaStream_t s); \
   int cgrid_coop_max_ctas(int num_sms); \
   }

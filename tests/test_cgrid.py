@@ -119,3 +119,39 @@ def test_cgrid_cooperative_single_launch(oracle_mod, evp_lib, monkeypatch, cfg, 
     for n in abi.CFIELDS_INOUT + abi.CFIELDS_OUT:
         if n != skip:
             assert np.array_equal(got[n].view(np.int64), ref[n].view(np.int64)), n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,kw", [("tiny", dict(seed=12)), ("tiny", dict(seed=13, ew="closed", ns="closed")),
+                                    ("tiny", dict(seed=14, ew="cyclic", ns="cyclic", kmt="none")),
+                                    ("tiny", dict(seed=15, visc_method=abi.VISC_AVG_STRENGTH, block_size=(12, 10))),
+                                    ("gx3", dict(ndte=31))],
+                         ids=["tiny", "tiny-closed", "tiny-cyclic2", "tiny-avgstrength-4blocks", "gx3-odd"])
+def test_cgrid_five_kernel_form(oracle_mod, evp_lib, monkeypatch, cfg, kw):
+    """EVP_B200_CGRID_FUSED=0: the first correct form, five kernels per subcycle (the default is three: kA, kB, k5)."""
+    monkeypatch.setenv("EVP_B200_CGRID_FUSED", "0")
+    c = synth.make_ccase(cfg, **kw)
+    ref = run_oracle_c(oracle_mod, c)
+    got = run_gpu_c(evp_lib, c, mode=abi.MODE_EXACT)
+    skip = "etax2U" if c.params["visc_method"] == abi.VISC_AVG_STRENGTH else "strengthU"
+    for n in abi.CFIELDS_INOUT + abi.CFIELDS_OUT:
+        if n != skip:
+            assert np.array_equal(got[n].view(np.int64), ref[n].view(np.int64)), n
+
+
+@pytest.mark.gpu
+def test_cgrid_fused_odd_loop_and_repeat(oracle_mod, evp_lib):
+    """the fused form ping-pongs stress12U: an odd ndte ends on the second copy, and a second call must start from it."""
+    c = synth.make_ccase("tiny", seed=16, ndte=7)
+    ref = c.copy_fields()
+    got = c.copy_fields()
+    evp_lib.dyn_evp_b200_init(c.grid)
+    evp_lib.dyn_evp_b200_init_cgrid(c.cgrid)
+    try:
+        for _ in range(2):
+            oracle_mod.evp_run_cgrid(c.grid, c.cgrid, c.params, ref)
+            evp_lib.dyn_evp_b200_run_cgrid(dict(c.params, mode=abi.MODE_EXACT), got)
+            for n in abi.CFIELDS_INOUT:
+                assert np.array_equal(got[n].view(np.int64), ref[n].view(np.int64)), n
+    finally:
+        evp_lib.dyn_evp_b200_finalize()
