@@ -160,6 +160,7 @@ struct Ctx {
   evp_b200_params_t cparams{};
   unsigned *d_cbar = nullptr;       // grid-barrier counter of the cooperative C-grid kernel
   int cgraph_launches = 0;
+  int c_shape = 0;                   // tile shape / residency of kA, kB (EVP_B200_CGRID_SHAPE)
   bool c_fused = true;               // three kernels per subcycle (kA, kB, k5) instead of five
   int c_max_ctas[2] = {0, 0};       // co-resident CTAs of that kernel (exact, fast); 0 = use the five-kernel form
 
@@ -824,6 +825,7 @@ static int do_init_cgrid(const evp_b200_cgrid_t *cg) {
   if (calloc_dom(c.uvelE_init) || calloc_dom(c.vvelN_init) || calloc_dom(c.stress12Ub)) return 1;
   g.c_fused = true;
   if (const char *e = getenv("EVP_B200_CGRID_FUSED")) g.c_fused = (e[0] != '0');
+  if (const char *e = getenv("EVP_B200_CGRID_SHAPE")) g.c_shape = atoi(e);
   for (int q = 0; q < 4; ++q) { CK(cudaMalloc(&g.cmask[q], g.ndom)); CK(cudaMemsetAsync(g.cmask[q], 0, g.ndom, g.stream)); }
   c.maskT = g.cmask[0]; c.maskU = g.cmask[1]; c.maskE = g.cmask[2]; c.maskN = g.cmask[3];
   CK(cudaMalloc(&g.d_cbar, sizeof(unsigned)));
@@ -914,7 +916,7 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
       nl = 1;
     } else if (g.c_fused) {
       for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub)
-        le = exact ? exact::launch_cgrid_subcycle_fused(c, k, ksub & 1, g.stream, &nl) : fast::launch_cgrid_subcycle_fused(c, k, ksub & 1, g.stream, &nl);
+        le = exact ? exact::launch_cgrid_subcycle_fused(c, k, ksub & 1, g.c_shape, g.stream, &nl) : fast::launch_cgrid_subcycle_fused(c, k, ksub & 1, g.c_shape, g.stream, &nl);
     } else {
       for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub)
         le = exact ? exact::launch_cgrid_subcycle(c, k, g.stream, &nl) : fast::launch_cgrid_subcycle(c, k, g.stream, &nl);

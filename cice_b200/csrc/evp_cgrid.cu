@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256) k5_interp(const __grid_constant__ CDom d)
 // interior point it aliases; a ghost point outside a closed/open edge is never written by the loop and is read back.
 // kB's first phase updates stress12U in place (new = f(old)), so the recomputed copies would race with the owner's
 // store: stress12U is ping-ponged between two arrays (both start identical; cells off the ice are never written).
-constexpr int GBX = 32, GBY = 8;
+constexpr int GBX = 32;
 
 // index of the interior point a ring point aliases (wrap), or -1 when the point is a constant ghost / outside
 __device__ __forceinline__ bool alias_point(const CDom &d, int &i, int &j) {
@@ -328,7 +328,8 @@ __device__ __forceinline__ bool alias_point(const CDom &d, int &i, int &j) {
   return i >= 1 && i <= d.nx && j >= 1 && j <= d.ny;
 }
 
-__global__ void __launch_bounds__(GBX *GBY) kA_strainU_stressT(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+template <int GBY, int MINB>
+__global__ void __launch_bounds__(GBX *GBY, MINB) kA_strainU_stressT(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
   __shared__ double sh[GBY][GBX];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i = blockIdx.x * (GBX - 1) + tx, j = blockIdx.y * (GBY - 1) + ty;  // ti = 1 + bx*(GBX-1), point ti-1+tx
@@ -360,7 +361,8 @@ __global__ void __launch_bounds__(GBX *GBY) kA_strainU_stressT(const __grid_cons
   }
 }
 
-__global__ void __launch_bounds__(GBX *GBY) kB_stressU_momentum(const __grid_constant__ CDom d, const __grid_constant__ KParams k, int cur) {
+template <int GBY, int MINB>
+__global__ void __launch_bounds__(GBX *GBY, MINB) kB_stressU_momentum(const __grid_constant__ CDom d, const __grid_constant__ KParams k, int cur) {
   __shared__ double sh[GBY][GBX];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i = blockIdx.x * (GBX - 1) + tx, j = blockIdx.y * (GBY - 1) + ty;
@@ -409,11 +411,21 @@ cudaError_t launch_cgrid_static(const CDom &d, double *rhalf_dyE, double *r_dxE,
   return cudaGetLastError();
 }
 
-cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur, cudaStream_t s, int *launches) {
+template <int GBY, int MINB>
+static void launch_AB(const CDom &d, const KParams &p, int cur, cudaStream_t s) {
   dim3 b(GBX, GBY), g((d.nx + 1 + GBX - 2) / (GBX - 1), (d.ny + 1 + GBY - 2) / (GBY - 1));
+  kA_strainU_stressT<GBY, MINB><<<g, b, 0, s>>>(d, p);
+  kB_stressU_momentum<GBY, MINB><<<g, b, 0, s>>>(d, p, cur);
+}
+cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur, int shape, cudaStream_t s, int *launches) {
   dim3 b5(32, 8), g5((d.nx + 31) / 32, (d.ny + 7) / 8);
-  kA_strainU_stressT<<<g, b, 0, s>>>(d, p);
-  kB_stressU_momentum<<<g, b, 0, s>>>(d, p, cur);
+  switch (shape) {
+    case 1: launch_AB<8, 5>(d, p, cur, s); break;
+    case 2: launch_AB<16, 2>(d, p, cur, s); break;
+    case 3: launch_AB<12, 3>(d, p, cur, s); break;
+    case 4: launch_AB<4, 8>(d, p, cur, s); break;
+    default: launch_AB<8, 4>(d, p, cur, s); break;  // 62 registers, 4 CTAs per SM; the other shapes measure within 4 % (profiles/)
+  }
   k5_interp<<<g5, b5, 0, s>>>(d);
   *launches += 3;
   return cudaGetLastError();
