@@ -14,7 +14,7 @@ SYMBOLS = (
     "evp_b200_last_error", "evp_b200_run_bgrid", "evp_b200_upload", "evp_b200_subcycle", "evp_b200_download",
     "evp_b200_last_loop_ms", "evp_b200_last_launches", "evp_b200_stream", "evp_b200_describe",
     "evp_b200_halo_plan", "evp_b200_dom_pitch", "evp_b200_init_cgrid", "evp_b200_run_cgrid", "evp_b200_deformations",
-    "evp_b200_run_bgrid_resident", "evp_b200_download_stress",
+    "evp_b200_run_bgrid_resident", "evp_b200_download_stress", "evp_b200_allow_partial_domain",
 )
 
 
@@ -51,6 +51,7 @@ def load():
     L.evp_b200_get_unique_id.argtypes = [C.c_void_p]
     L.evp_b200_comm_init.argtypes = [C.c_int32, C.c_int32, C.c_void_p]
     L.evp_b200_set_device.argtypes = [C.c_int32]
+    L.evp_b200_allow_partial_domain.argtypes = [C.c_int32]
     L.evp_b200_init.argtypes = [pg]
     L.evp_b200_finalize.argtypes = []
     L.evp_b200_run_bgrid.argtypes = [pp, pf]

@@ -179,6 +179,7 @@ struct Ctx {
 };
 static Ctx g;
 static CommState g_comm;
+static bool g_allow_partial = false;  // evp_b200_allow_partial_domain
 
 static int grid_blocks(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 16); }
 
@@ -314,9 +315,12 @@ static int do_init(const evp_b200_grid_t *gr) {
     ncell += (size_t)(ihi - ilo + 1) * (jhi - jlo + 1);
   }
   const int nx = gi1 - gi0 + 1, ny = gj1 - gj0 + 1;
-  if (ncell != (size_t)nx * ny)
-    return fail("evp_b200_init: the rank's blocks do not tile a rectangle (%zu cells vs %dx%d); use a cartesian "
-                "distribution without land-block elimination", ncell, nx, ny);
+  // Land-block elimination (ice_domain.F90: blocks without ocean are not distributed) leaves holes in the rectangle:
+  // allowed.  A hole cell is land for every purpose -- masks 0, fields 0, exactly what the reference's halo update puts
+  // into the ghost cells that face an eliminated block (ice_boundary.F90:1398-1408) -- unless a neighbouring block holds
+  // it as a ghost cell, whose (halo-filled) value is then used.
+  if (ncell > (size_t)nx * ny) return fail("evp_b200_init: the rank's blocks overlap (%zu cells in a %dx%d rectangle)", ncell, nx, ny);
+  const size_t nholes = (size_t)nx * ny - ncell;
   g.gi0 = gi0; g.gj0 = gj0;
   Dom &d = g.dom;
   d.nx = nx; d.ny = ny; d.nyd = ny + 2;
@@ -344,8 +348,8 @@ static int do_init(const evp_b200_grid_t *gr) {
           owned[dm] = 1;
           gsrc[dm] = lin;
           int_lin.push_back(lin); int_dom.push_back(dm);
-        } else if (ring && gsrc[dm] < 0) {
-          gsrc[dm] = lin;
+        } else if (!owned[dm] && gsrc[dm] < 0) {
+          gsrc[dm] = lin;  // ghost ring of the rectangle, or a hole cell next to a block: some block's ghost copy of it
         }
         uv_lin.push_back(lin); uv_dom.push_back(dm);
         if (li >= ilo && lj >= jlo) { sig_lin.push_back(lin); sig_dom.push_back(dm); }
@@ -403,7 +407,7 @@ static int do_init(const evp_b200_grid_t *gr) {
   d.maskT = g.dmaskT; d.maskU = g.dmaskU;
 
   // ---- halo plan ----------------------------------------------------------------------------------
-  if (g.halo.build(g_comm, gi0, gj0, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, g_err, sizeof g_err)) return 1;
+  if (g.halo.build(g_comm, gi0, gj0, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, g_allow_partial, g_err, sizeof g_err)) return 1;
   d.wrap_ew = g.halo.wrap_ew; d.wrap_ns = g.halo.wrap_ns;
   CK(cudaStreamSynchronize(g.stream));
   if (g.p2p.setup(g_comm, g.halo, g.dshare, g.ndom, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, g_err, sizeof g_err)) return 1;
@@ -449,8 +453,8 @@ static int do_init(const evp_b200_grid_t *gr) {
              g.pplan.bx, g.pplan.by, g.num_sms, g.pplan.smem_bytes, g.pplan.kT, g.pplan.kU);
   else
     snprintf(pbuf, sizeof pbuf, "persistent: unavailable (%s)", g.persist_why.c_str());
-  snprintf(buf, sizeof buf, "dom %dx%d (ld %d) at global (%d,%d) of %dx%d; %d block(s) %dx%d; rank %d/%d; halo: %s; %s",
-           nx, ny, d.ld, gi0, gj0, g.nxg, g.nyg, g.nblocks, nxb, nyb, g_comm.rank, g_comm.nranks, g.halo.describe().c_str(), pbuf);
+  snprintf(buf, sizeof buf, "dom %dx%d (ld %d) at global (%d,%d) of %dx%d; %d block(s) %dx%d, %zu hole cell(s); rank %d/%d; halo: %s; %s",
+           nx, ny, d.ld, gi0, gj0, g.nxg, g.nyg, g.nblocks, nxb, nyb, nholes, g_comm.rank, g_comm.nranks, g.halo.describe().c_str(), pbuf);
   g.desc = buf;
   g.desc += std::string("; p2p: ") + (g.p2p.enabled ? "" : "off (") + g.p2p.why + (g.p2p.enabled ? "" : ")");
   return 0;
@@ -977,6 +981,8 @@ int evp_b200_set_device(int32_t dev) {
   CK(cudaSetDevice(dev));
   return 0;
 }
+
+int evp_b200_allow_partial_domain(int32_t yes) { g_allow_partial = (yes != 0); return 0; }
 
 int evp_b200_get_unique_id(void *id128) { return comm_get_unique_id(id128, g_err, sizeof g_err); }
 

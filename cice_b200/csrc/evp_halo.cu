@@ -189,8 +189,8 @@ static int up(T *&dptr, const std::vector<T> &h, char *err, size_t nerr) {
   return 0;
 }
 
-int HaloPlan::build(CommState &cs, int gi0, int gj0, int nx, int ny, int ld, int nxg, int nyg, int ew, int ns, char *err,
-                    size_t nerr) {
+int HaloPlan::build(CommState &cs, int gi0, int gj0, int nx, int ny, int ld, int nxg, int nyg, int ew, int ns, bool allow_partial,
+                    char *err, size_t nerr) {
   release();
   wrap_ew = (ew == EVP_B200_BNDY_CYCLIC && nx == nxg);
   wrap_ns = (ns == EVP_B200_BNDY_CYCLIC && ny == nyg);
@@ -207,11 +207,17 @@ int HaloPlan::build(CommState &cs, int gi0, int gj0, int nx, int ny, int ld, int
     HCK(cudaStreamSynchronize(0));
     HCK(cudaMemcpy(R.data(), dbuf, sizeof(Rect) * cs.nranks, cudaMemcpyDeviceToHost));
     HCK(cudaFree(dbuf));
-    size_t cells = 0;
-    for (auto &q : R) cells += (size_t)q.nx * q.ny;
-    if (cells != (size_t)nxg * nyg) HFAIL("halo: the ranks' rectangles cover %zu of %zu cells (land-block elimination is not supported)", cells, (size_t)nxg * nyg);
-  } else if (nx != nxg || ny != nyg) {
-    HFAIL("halo: one rank but its blocks cover %dx%d of the %dx%d domain; call evp_b200_comm_init first", nx, ny, nxg, nyg);
+    // the bounding rectangles must be disjoint (cartesian distribution); they need not cover the domain: ghost cells that
+    // face eliminated land blocks have no source and keep the zeros the host's halo update put there
+    for (int a = 0; a < cs.nranks; ++a)
+      for (int b = a + 1; b < cs.nranks; ++b) {
+        const bool sep = R[a].gi0 + R[a].nx <= R[b].gi0 || R[b].gi0 + R[b].nx <= R[a].gi0 || R[a].gj0 + R[a].ny <= R[b].gj0 ||
+                         R[b].gj0 + R[b].ny <= R[a].gj0;
+        if (!sep) HFAIL("halo: the blocks of ranks %d and %d interleave (bounding rectangles overlap); use distribution_type = 'cartesian'", a, b);
+      }
+  } else if ((nx != nxg || ny != nyg) && !allow_partial) {
+    HFAIL("halo: one rank but its blocks span %dx%d of the %dx%d domain: call evp_b200_comm_init first, or -- if the rest of the "
+          "domain is eliminated land blocks -- evp_b200_allow_partial_domain(1)", nx, ny, nxg, nyg);
   }
 
   rects.assign(4 * (size_t)cs.nranks, 0);

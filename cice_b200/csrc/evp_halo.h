@@ -46,7 +46,8 @@ struct HaloPlan {
   std::vector<int> rects;  // 4 ints per rank {gi0, gj0, nx, ny}, filled by build
   bool has_fold = false;   // some entry is not a plain copy (tripole)
 
-  int build(CommState &cs, int gi0, int gj0, int nx, int ny, int ld, int nxg, int nyg, int ew, int ns, char *err, size_t nerr);
+  int build(CommState &cs, int gi0, int gj0, int nx, int ny, int ld, int nxg, int nyg, int ew, int ns, bool allow_partial, char *err,
+            size_t nerr);
   int exchange(CommState &cs, double *U, double *V, cudaStream_t s, int *launches, char *err, size_t nerr);
   bool graph_safe() const { return allow_graph; }
   std::string describe() const;

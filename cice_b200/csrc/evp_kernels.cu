@@ -258,6 +258,7 @@ template <int FBX, int FBY, bool P2P, int SPEC>
 __device__ __forceinline__ void fused_spec_body(const Dom &d, const KParams &k, int cur, const P2PParams &pp, int last, int i, int j,
                                                 bool inT, int c, double (&sstr)[8][FBY][FBX]) {
   constexpr bool SPT = (SPEC & 1) != 0, CPU = (SPEC & 2) != 0, IL = (SPEC & 4) != 0;  // bit 2: interleaved div/sqrt
+  constexpr bool PAIR = (SPEC & 8) != 0;                                                 // bit 3: pairwise named barriers
   __shared__ double sU[CPU ? NUOP : 1][FBY * FBX];
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * FBX + tx;
   const int nxt = cur ^ 1;
@@ -315,7 +316,15 @@ __device__ __forceinline__ void fused_spec_body(const Dom &d, const KParams &k, 
 #pragma unroll
   for (int q = 0; q < 8; ++q) sstr[q][ty][tx] = str[q];
   if (CPU) cp_async_wait_all();  // own copies only: each thread reads back what it requested itself
-  __syncthreads();
+  if (PAIR && FBX == 32) {
+    // U row ty needs the str terms of T rows ty and ty+1 only, and a row is one warp: instead of a CTA-wide barrier, warp
+    // ty+1 arrives on named barrier ty+1 once its terms are in shared memory and warp ty waits there (64 threads each,
+    // every barrier used once per launch), so a warp is held up by one neighbour, not by the slowest of eight
+    if (ty >= 1) asm volatile("bar.arrive %0, 64;" ::"r"(ty) : "memory");
+    if (ty < FBY - 1) asm volatile("bar.sync %0, 64;" ::"r"(ty + 1) : "memory");
+  } else {
+    __syncthreads();
+  }
   if (uspot && mU) {
     double uo[NUOP];
     if (CPU) {
@@ -788,6 +797,8 @@ cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s
     case 21: return launch_fused_t<32, 8, 2, false, 5>(d, p, cur, s, pdl, last);  // 17 + interleaved div/sqrt
     case 22: return launch_fused_t<32, 8, 2, false, 7>(d, p, cur, s, pdl, last);  // 19 + interleaved div/sqrt
     case 23: return launch_fused_t<32, 8, 2, false, 4>(d, p, cur, s, pdl, last);  // 16 + interleaved div/sqrt
+    case 31: return launch_fused_t<32, 8, 2, false, 12>(d, p, cur, s, pdl, last);  // 23 + pairwise named barriers
+    case 32: return launch_fused_t<32, 8, 2, false, 11>(d, p, cur, s, pdl, last);  // 19 + pairwise named barriers
     case 24: return launch_fused_t<32, 8, 3, false, 4>(d, p, cur, s, pdl, last);  // 23 with other CTA shapes / residency
     case 25: return launch_fused_t<32, 6, 3, false, 4>(d, p, cur, s, pdl, last);
     case 26: return launch_fused_t<32, 5, 4, false, 4>(d, p, cur, s, pdl, last);

@@ -31,6 +31,11 @@ def set_device(ordinal):
     check(load().evp_b200_set_device(int(ordinal)), "evp_b200_set_device")
 
 
+def allow_partial_domain(yes=True):
+    """a single rank whose blocks span less than the domain because land blocks were eliminated (see include/evp_b200.h)."""
+    check(load().evp_b200_allow_partial_domain(1 if yes else 0), "evp_b200_allow_partial_domain")
+
+
 def get_unique_id():
     buf = C.create_string_buffer(abi.UNIQUE_ID_BYTES)
     check(load().evp_b200_get_unique_id(buf), "evp_b200_get_unique_id")

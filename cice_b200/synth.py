@@ -176,6 +176,12 @@ def make_kmt(kind, nx, ny, ew, ns):
     elif kind == "channel":
         hm = np.zeros((ny, nx))
         hm[2:ny - 2, :] = 1.0
+    elif kind == "continents":
+        # not a reference option: boxislands plus two solid land masses (a block in the interior, a cap along the southern
+        # edge) so that small blocks come out all-land and land-block elimination (ice_domain.F90) can be exercised
+        hm = kmt_boxislands(nx, ny) if min(nx, ny) >= 20 else np.ones((ny, nx))
+        hm[int(0.35 * ny):int(0.75 * ny), int(0.40 * nx):int(0.80 * nx)] = 0.0
+        hm[:int(0.22 * ny), :] = 0.0
     else:
         raise ValueError(kind)
     if ew == abi.BNDY_CLOSED:

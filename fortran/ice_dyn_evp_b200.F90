@@ -66,6 +66,10 @@ module ice_dyn_evp_b200
        import :: c_int, c_int32_t
        integer(c_int32_t), value :: dev
      end function
+     integer(c_int) function evp_b200_allow_partial_domain(yes) bind(C, name='evp_b200_allow_partial_domain')
+       import :: c_int, c_int32_t
+       integer(c_int32_t), value :: yes
+     end function
      integer(c_int) function evp_b200_init(grid) bind(C, name='evp_b200_init')
        import :: c_int, evp_b200_grid_t
        type(evp_b200_grid_t), intent(in) :: grid
@@ -153,6 +157,9 @@ contains
        if (my_task == master_task) call check(evp_b200_get_unique_id(id), 'evp_b200_get_unique_id')
        call MPI_Bcast(id, 128, MPI_CHARACTER, master_task, MPI_COMM_ICE, ierr)
        call check(evp_b200_comm_init(int(my_task, c_int32_t), int(nprocs, c_int32_t), id), 'evp_b200_comm_init')
+    else
+       ! one task holds every distributed block: if they span less than the domain, land blocks were eliminated (ice_domain.F90)
+       call check(evp_b200_allow_partial_domain(1_c_int32_t), 'evp_b200_allow_partial_domain')
     endif
 
     allocate(b_ilo(nblocks), b_ihi(nblocks), b_jlo(nblocks), b_jhi(nblocks))

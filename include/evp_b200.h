@@ -192,6 +192,12 @@ int evp_b200_set_device(int32_t device_ordinal);           /* default: current d
 int evp_b200_init(const evp_b200_grid_t *grid);
 int evp_b200_finalize(void);
 const char *evp_b200_last_error(void);
+/* Land-block elimination (ice_domain.F90: blocks without an ocean cell are not distributed): the blocks of a rank may
+ * leave holes in the rectangle they span -- accepted as is; hole cells are land -- and several ranks' rectangles need
+ * not cover the domain.  The one case that cannot be told from a forgotten evp_b200_comm_init is a SINGLE rank whose
+ * blocks span less than the global domain; the caller, who knows that blocks were eliminated
+ * (nblocks_tot vs. the distributed count), states it with this call before evp_b200_init. */
+int evp_b200_allow_partial_domain(int32_t yes);
 
 /* ---- the hot path ------------------------------------------------------------------------
  * One call = the whole `do ksub=1,ndte` loop of ice_dyn_evp.F90:859-913 on this rank's

@@ -185,7 +185,8 @@ def test_tx1_tripole_full(oracle_mod, evp_lib):
     ["gx3", "25", "29", "40", "fused"],
     ["gx3", "50", "58", "15", "split"],
     ["tiny", "12", "10", "16", "fused", "tripole"],
-], ids=["gx3-16blocks-fused", "gx3-4blocks-split", "tiny-tripole"])
+    ["gx3", "10", "10", "20", "fused", "-", "elim"],
+], ids=["gx3-16blocks-fused", "gx3-4blocks-split", "tiny-tripole", "gx3-land-blocks-eliminated"])
 def test_multi_gpu_halo(args, p2p):
     """N>1: one process per GPU; the (uvel,vvel) halo goes either through in-kernel NVLink stores into the
     neighbours' ghost cells (default for the fused kernel) or through the staged NCCL send/recv exchange
@@ -204,7 +205,7 @@ def test_multi_gpu_halo(args, p2p):
            "--master-port", "29611", os.path.join(root, "tests", "mgpu_check.py")] + args
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, EVP_B200_P2P=p2p))
     assert "MGPU PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
-    if p2p == "1" and args[4] == "fused" and len(args) < 6:
+    if p2p == "1" and args[4] == "fused" and (len(args) < 6 or args[5] == "-"):
         assert "in-kernel NVLink stores" in r.stdout, r.stdout[-2000:]
 
 
@@ -377,3 +378,35 @@ def test_resident_stress_refused_on_tripole(evp_lib):
             evp_lib.dyn_evp_b200_run_resident(dict(c.params, mode=abi.MODE_EXACT), f)
     finally:
         evp_lib.dyn_evp_b200_finalize()
+
+
+def _eliminate_land_blocks(c):
+    """what ice_domain.F90 does before distributing blocks: a block without a single ocean cell is dropped."""
+    nb = c.blocks.nblocks_tot
+    land = [n for n in range(nb) if not c.fields["iceTmask"][n][1:-1, 1:-1].any() and not c.fields["iceUmask"][n].any()]
+    owner = np.zeros(nb, int)
+    owner[land] = -1
+    g, f, ids = c.rank_view(owner, 0)
+    return g, f, ids, land
+
+
+@pytest.mark.parametrize("kernel", [abi.KERNEL_SPLIT, abi.KERNEL_FUSED], ids=KNAME.get)
+@pytest.mark.parametrize("cfg,bs", [("gx3", (10, 10)), ("gx3", (20, 16)), ("tiny", (4, 4))])
+def test_land_block_elimination(oracle_mod, evp_lib, kernel, cfg, bs):
+    """the rank's blocks no longer tile a rectangle (holes where all-land blocks were dropped, and a bounding box that
+    stops short of the domain's southern edge): hole cells are land, ghost cells facing them keep the halo's zeros."""
+    c = synth.make_case(cfg, block_size=bs, seed=51, ndte=9, kmt="continents")
+    g, f, ids, land = _eliminate_land_blocks(c)
+    assert len(land) >= 5
+    ref = {k: v.copy() for k, v in f.items()}
+    oracle_mod.evp_run_bgrid(g, c.params, ref)
+    got = {k: v.copy() for k, v in f.items()}
+    evp_lib.allow_partial_domain(True)   # the southern cap is gone: the rank's rectangle is smaller than the domain
+    try:
+        evp_lib.dyn_evp_b200_init(g)
+        assert "hole cell" in evp_lib.describe() and " 0 hole cell" not in evp_lib.describe()
+        evp_lib.dyn_evp_b200_run(dict(c.params, mode=abi.MODE_EXACT, kernel=kernel), got)
+    finally:
+        evp_lib.dyn_evp_b200_finalize()
+        evp_lib.allow_partial_domain(False)
+    assert_bitwise(got, ref)

@@ -159,3 +159,22 @@ def test_halo_plan_single_rank_is_empty_without_tripole():
     # two pole columns (i = 12, 24; the ghost column i=0 aliases 24) are negated, the rest symmetrised
     assert len(pl) == 52
     assert (pl[:, 5] == 1).sum() == 26 + 3 and ((pl[:, 5] == 2) | (pl[:, 5] == 3)).sum() == 23 and (pl[:, 5] == 0).sum() == 0
+
+
+def test_halo_plan_with_eliminated_land_blocks():
+    """rectangles that do not cover the domain (land-block elimination): a ghost cell whose source no rank owns has no
+    plan entry (it keeps the zeros of the host's halo fill), every other ghost cell is still served."""
+    from cice_b200 import abi, dyn_evp
+    nxg, nyg = 24, 20
+    # rank 0 owns the west half above row 5 (rows 1..4 were an all-land cap), rank 1 the east half in full
+    rects = [[1, 5, 12, 16], [13, 1, 12, 20]]
+    p0 = dyn_evp.halo_plan(rects, 0, nxg, nyg, abi.BNDY_CYCLIC, abi.BNDY_CLOSED)
+    p1 = dyn_evp.halo_plan(rects, 1, nxg, nyg, abi.BNDY_CYCLIC, abi.BNDY_CLOSED)
+    ld = dyn_evp.dom_pitch(12)
+    # rank 0 (global rows 5..20): E ghost column (global i = 13) and, cyclically, W ghost column (global i = 24) come from
+    # rank 1 for its 16 interior rows plus the S ghost row (global row 4, which rank 1 owns); the N ghost row is outside
+    assert all(e[1] == 1 and e[5] == 0 for e in p0)
+    assert sorted(set(int(e[0]) // ld for e in p0)) == list(range(0, 17)) and len(p0) == 2 * 17
+    # rank 1 (global rows 1..20): its ghost columns have a source only where rank 0 exists, global rows 5..20
+    assert all(e[1] == 0 and e[5] == 0 for e in p1)
+    assert sorted(set(int(e[0]) // ld for e in p1)) == list(range(5, 21)) and len(p1) == 2 * 16
