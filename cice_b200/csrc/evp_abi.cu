@@ -619,11 +619,14 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
   // early programmatic-launch trigger: pays when the grid is more than one wave of co-resident CTAs (gx1 2.29 -> 2.21 ms), costs
   // on grids far smaller than the machine (gx3 0.56 -> 0.64 ms)
   const int pdl_trig = (g.fused_pdl && g.pdl_trigger && (long)((g.dom.nx + 30) / 31) * ((g.dom.ny + 6) / 7) > 2L * g.num_sms) ? 2 : 0;
+  // in-kernel NVLink halo: programmatic dependent launch between the subcycle kernels (EVP_B200_P2P_PDL=0: off, 1: attribute only, 2: + early trigger)
+  int p2p_pdl = 6;  // default: attribute + early trigger (no-peer self test on one GPU: 2.74 -> 2.60 ms per step)
+  if (const char *e = getenv("EVP_B200_P2P_PDL")) p2p_pdl = (e[0] == '1') ? 4 : (e[0] == '2') ? 6 : 0;
   for (int ksub = 0; ksub < p->ndte; ++ksub) {
     const int last = (ksub == p->ndte - 1);
     if (p2p) {
-      CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last, g.fused_variant, g.stream)
-               : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last, g.fused_variant, g.stream));
+      CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, g.fused_variant, g.stream)
+               : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, g.fused_variant, g.stream));
       cur ^= 1;
       ++nl;
       continue;

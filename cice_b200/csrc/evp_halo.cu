@@ -335,6 +335,8 @@ int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t 
     if (rev) { order.clear(); for (int t = 0; t < ntx * nty; ++t) order.push_back(t); n_edge = 0; }
     if (stm == '3') n_edge = 0;                                                     // edge-first order, no counter
     if (stm == '4') { order.clear(); for (int t = 0; t < ntx * nty; ++t) order.push_back(t); }  // natural order, counter on the first n_edge tiles
+    if (ntx > 0xffff || nty > 0x7fff) HFAIL("p2p: tile grid too large");
+    for (int &t : order) t = ((t / ntx) << 16) | (t % ntx);  // packed (tby, tbx): see fused_kernel
     if (up(d_tile_order, order, err, nerr) || up(d_push_start, start, err, nerr) || up(d_push_peer, none, err, nerr) || up(d_push_dst, none, err, nerr)) return 1;
     HCK(cudaMalloc(&d_done, sizeof(unsigned long long))); HCK(cudaMalloc(&d_epoch, sizeof(unsigned long long))); HCK(cudaMalloc(&d_err, sizeof(int)));
     HCK(cudaMemset(d_done, 0, 8)); HCK(cudaMemset(d_err, 0, 4)); HCK(cudaMemset(d_epoch, 0, 8));
@@ -460,6 +462,8 @@ int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t 
       const bool edge = (bx == 0 || bx == ntx - 1 || by == 0 || by == nty - 1);
       if (edge == (pass == 0)) { order.push_back(t); n_edge += edge; }
     }
+  if (ntx > 0xffff || nty > 0x7fff) { why = "tile grid too large"; }
+  for (int &t : order) t = ((t / ntx) << 16) | (t % ntx);  // packed (tby, tbx): see fused_kernel
   if (up(d_tile_order, order, err, nerr) || up(d_push_start, start, err, nerr) || up(d_push_peer, ppeer, err, nerr) ||
       up(d_push_dst, pdst, err, nerr))
     return 1;
@@ -476,7 +480,8 @@ int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t 
 
   prm = P2PParams{};
   prm.enabled = 1; prm.npeers = npeers; prm.n_edge_tiles = n_edge; prm.ntx = ntx; prm.nty = nty;
-  prm.tile_order = d_tile_order; prm.n_push = (int)pushes.size(); prm.push_start = d_push_start; prm.push_peer = d_push_peer; prm.push_dst = d_push_dst;
+  prm.tile_order = d_tile_order;
+  prm.n_push = (int)pushes.size(); prm.push_start = d_push_start; prm.push_peer = d_push_peer; prm.push_dst = d_push_dst;
   prm.my_flags = (const unsigned long long *)(dshare + 4 * ndom);
   for (int q = 0; q < npeers; ++q) {
     prm.peer_rank[q] = peer_ranks[q];

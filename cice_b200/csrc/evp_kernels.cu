@@ -374,10 +374,13 @@ __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_cons
   if (flags & 2) cudaTriggerProgrammaticLaunchCompletion();
 #endif
   if (P2P) {
-    const int tile = pp.tile_order[blockIdx.x];
-    tbx = tile % pp.ntx;
-    tby = tile / pp.ntx;
-    edge_tile = (int)blockIdx.x < pp.n_edge_tiles;
+    const int b = blockIdx.x;
+    // edge tiles first; the table holds (tby << 16 | tbx) so that no runtime integer division (~80 instructions and a MUFU
+    // round trip at the top of every CTA) is needed to decode it
+    const int tile = pp.tile_order[b];
+    tbx = tile & 0xffff;
+    tby = tile >> 16;
+    edge_tile = b < pp.n_edge_tiles;
   }
   const int i = 1 + tbx * (FBX - 1) + tx;  // T cell of this thread
   const int j = 1 + tby * (FBY - 1) + ty;
@@ -819,10 +822,16 @@ cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp
     p2p_finish_kernel<<<1, 32, 0, s>>>(pp, -2 - ksub);
     return cudaGetLastError();
   }
-  if (variant == 19)
-    fused_kernel<32, 8, 2, false, true, 3><<<dim3(pp.ntx * pp.nty), dim3(32, 8), 0, s>>>(d, p, cur, pp, ksub, last);
-  else
-    fused_kernel<32, 8, 2, false, true, 4><<<dim3(pp.ntx * pp.nty), dim3(32, 8), 0, s>>>(d, p, cur, pp, ksub, last);
+  // `last`: bit 0 = last subcycle, bit 1 = early programmatic-launch trigger, bit 2 = launch with the PDL attribute
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(pp.ntx * pp.nty); cfg.blockDim = dim3(32, 8); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (last & 4) ? 1 : 0;
+  const int flags = last & 3;
+  if (variant == 19) return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 3>, d, p, cur, pp, ksub, flags);
+  return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 4>, d, p, cur, pp, ksub, flags);
   return cudaGetLastError();
 }
 
