@@ -1,0 +1,525 @@
+"""Pin the CPU oracle to the reference's own SOURCE TEXT.
+
+The reference is Fortran 90 and cannot be compiled in this image (no f951), and it stores no golden vectors
+for the EVP path.  Its hot-path subroutines, however, are straight-line fp64 arithmetic:
+
+    stress          cicecore/cicedyn/dynamics/ice_dyn_evp.F90      
+    stepu           cicecore/cicedyn/dynamics/ice_dyn_shared.F90   (a3)
+    strain_rates    .../ice_dyn_shared.F90                         (a4)
+    visc_replpress  .../ice_dyn_shared.F90                         (a5)
+    constants       cicecore/shared/ice_constants.F90              (p111 = c1/c9 ...)
+
+This script READS those subroutines from /root/reference at generation time, transliterates them statement
+by statement into Python -- same operators, same operand order, same parentheses; a Python float is an IEEE
+double and `a op b` is rounded once, exactly like Fortran without FMA contraction -- executes the result on
+a synthetic case (the subcycle loop of ice_dyn_evp.F90:859-913 with the reference's own index lists), and
+writes the outputs as golden vectors.  Nothing of the arithmetic is restated by hand here: the translator
+knows Fortran syntax (continuations, do/if, call with intent(out) scalars, array references, `x**2`), not
+the formulas.  tests/test_oracle.py::test_oracle_matches_vectors_from_reference_source then compares the C
+oracle with the committed vectors bit for bit (runs anywhere), and ::test_reference_source_vectors_regenerate
+re-derives them from /root/reference when it is present.
+
+usage:  python tests/golden/ref_translit.py [--write]      (run from the repo root, in the container that has /root/reference)
+"""
+import math
+import os
+import re
+import sys
+
+import numpy as np
+
+REF = os.environ.get("CICE_REFERENCE", "/root/reference")
+F_EVP = "cicecore/cicedyn/dynamics/ice_dyn_evp.F90"
+F_SHARED = "cicecore/cicedyn/dynamics/ice_dyn_shared.F90"
+F_CONST = "cicecore/shared/ice_constants.F90"
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "ref_source_vectors.npz")
+
+
+# ------------------------------------------------------------------------------------------
+# Fortran source -> logical lines
+# ------------------------------------------------------------------------------------------
+def _strip_comment(line):
+    out, q = [], None
+    for ch in line:
+        if q:
+            out.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            out.append(ch)
+        elif ch == "!":
+            break
+        else:
+            out.append(ch)
+    return "".join(out).rstrip()
+
+
+def logical_lines(text):
+    """join `&` continuations, drop comments and blank lines, keep original case."""
+    res, cur = [], ""
+    for raw in text.splitlines():
+        if raw.lstrip().startswith("#"):  # cpp
+            continue
+        s = _strip_comment(raw).strip()
+        if not s:
+            continue
+        if s.startswith("&"):
+            s = s[1:].lstrip()
+        if s.endswith("&"):
+            cur += s[:-1] + " "
+            continue
+        res.append(cur + s)
+        cur = ""
+    return res
+
+
+def subroutine_lines(path, name):
+    lines = logical_lines(open(os.path.join(REF, path)).read())
+    start = None
+    for n, ln in enumerate(lines):
+        if re.match(rf"^\s*subroutine\s+{name}\b", ln, re.I):
+            start = n
+        if start is not None and re.match(rf"^\s*end\s+subroutine\s+{name}\b", ln, re.I):
+            return lines[start:n + 1]
+    raise RuntimeError(f"subroutine {name} not found in {path}")
+
+
+# ------------------------------------------------------------------------------------------
+# expression translator (precedence of Fortran 90: ** > * / > unary +- > binary +- > relational > .not. > .and. > .or.)
+# ------------------------------------------------------------------------------------------
+TOK = re.compile(r"""\s*(?:
+    (?P<num>(?:\d+\.\d*|\.\d+|\d+)(?:[eEdD][+-]?\d+)?(?:_\w+)?)
+  | (?P<dot>\.(?:and|or|not|true|false|eq|ne|lt|le|gt|ge)\.)
+  | (?P<id>[A-Za-z_]\w*)
+  | (?P<str>'[^']*'|"[^"]*")
+  | (?P<op>\*\*|==|/=|<=|>=|[-+*/(),<>=:])
+)""", re.X | re.I)
+
+INTRINSICS = {"sqrt": "math.sqrt", "max": "max", "min": "min", "abs": "abs", "sign": "_sign", "trim": "_trim", "real": "float"}
+REL = {"==": "==", "/=": "!=", "<": "<", ">": ">", "<=": "<=", ">=": ">=",
+       ".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">="}
+
+
+def tokenize(s):
+    pos, toks = 0, []
+    s = s.rstrip()
+    while pos < len(s):
+        m = TOK.match(s, pos)
+        if not m or m.end() == pos:
+            raise SyntaxError(f"cannot tokenize {s[pos:]!r} in {s!r}")
+        pos = m.end()
+        kind = m.lastgroup
+        toks.append((kind, m.group(kind)))
+    return toks
+
+
+class Expr:
+    def __init__(self, toks, arrays):
+        self.t, self.p, self.arrays = toks, 0, arrays
+
+    def peek(self):
+        return self.t[self.p] if self.p < len(self.t) else (None, None)
+
+    def next(self):
+        tok = self.peek()
+        self.p += 1
+        return tok
+
+    def expect(self, v):
+        k, x = self.next()
+        if x != v:
+            raise SyntaxError(f"expected {v!r}, got {x!r}")
+
+    def parse(self):
+        return self.p_or()
+
+    def p_or(self):
+        a = self.p_and()
+        while self.peek()[1] and self.peek()[1].lower() == ".or.":
+            self.next()
+            a = f"({a} or {self.p_and()})"
+        return a
+
+    def p_and(self):
+        a = self.p_not()
+        while self.peek()[1] and self.peek()[1].lower() == ".and.":
+            self.next()
+            a = f"({a} and {self.p_not()})"
+        return a
+
+    def p_not(self):
+        if self.peek()[1] and self.peek()[1].lower() == ".not.":
+            self.next()
+            return f"(not {self.p_not()})"
+        return self.p_rel()
+
+    def p_rel(self):
+        a = self.p_add()
+        v = self.peek()[1]
+        if v and v.lower() in REL:
+            self.next()
+            return f"({a} {REL[v.lower()]} {self.p_add()})"
+        return a
+
+    def p_add(self):
+        v = self.peek()[1]
+        if v in ("+", "-"):           # leading sign applies to the first TERM: -a*b == -(a*b)
+            self.next()
+            a = f"({v}{self.p_mul()})"
+        else:
+            a = self.p_mul()
+        while self.peek()[1] in ("+", "-"):
+            op = self.next()[1]
+            a = f"({a} {op} {self.p_mul()})"
+        return a
+
+    def p_mul(self):
+        a = self.p_pow()
+        while self.peek()[1] in ("*", "/"):
+            op = self.next()[1]
+            a = f"({a} {op} {self.p_pow()})"
+        return a
+
+    def p_pow(self):
+        a = self.p_primary()
+        if self.peek()[1] == "**":
+            self.next()
+            b = self.p_pow() if self.peek()[1] != "-" else None
+            if b is None:
+                raise SyntaxError("negative exponent not supported")
+            if b in ("2", "2.0"):
+                return f"_sq({a})"     # x**2 is x*x in every Fortran compiler; Python's pow() is not guaranteed to be
+            raise SyntaxError(f"exponent {b} not supported")
+        return a
+
+    def p_primary(self):
+        k, v = self.next()
+        if k == "num":
+            v = re.sub(r"_\w+$", "", v)
+            v = re.sub(r"[dD]", "e", v)
+            return v if ("." in v or "e" in v.lower()) else v  # integers stay integers (indices, exponents)
+        if k == "dot":
+            return {".true.": "True", ".false.": "False"}[v.lower()]
+        if k == "str":
+            return repr(v[1:-1])
+        if k == "op" and v == "(":
+            e = self.parse()
+            self.expect(")")
+            return f"({e})"
+        if k == "id":
+            if self.peek()[1] == "(":
+                self.next()
+                args = []
+                if self.peek()[1] != ")":
+                    args.append(self.parse())
+                    while self.peek()[1] == ",":
+                        self.next()
+                        args.append(self.parse())
+                self.expect(")")
+                if v.lower() in INTRINSICS and v.lower() not in self.arrays:
+                    return f"{INTRINSICS[v.lower()]}({', '.join(args)})"
+                return f"{v}[{', '.join(args)}]"      # array element
+            return v
+        raise SyntaxError(f"unexpected token {v!r}")
+
+
+def tr_expr(s, arrays=()):
+    e = Expr(tokenize(s), {a.lower() for a in arrays})
+    out = e.parse()
+    if e.p != len(e.t):
+        raise SyntaxError(f"trailing tokens in {s!r}")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# subroutine translator
+# ------------------------------------------------------------------------------------------
+DECL = re.compile(r"^\s*(integer|real|logical|character|type)\b", re.I)
+
+
+def split_top(s, sep=","):
+    parts, depth, cur = [], 0, ""
+    for ch in s:
+        if ch == "(":
+            depth += 1
+        elif ch == ")":
+            depth -= 1
+        if ch == sep and depth == 0:
+            parts.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        parts.append(cur.strip())
+    return parts
+
+
+class Sub:
+    """one reference subroutine: its interface (from the declarations) and its body as Python source."""
+
+    def __init__(self, path, name, registry):
+        self.name, self.registry = name, registry
+        L = subroutine_lines(path, name)
+        m = re.match(r"^\s*subroutine\s+\w+\s*\((.*)\)\s*$", L[0], re.I)
+        self.args = [a.strip() for a in m.group(1).split(",")]
+        self.arrays, self.out_scalars, self.locals_ = set(), [], set()
+        body = []
+        for ln in L[1:-1]:
+            if re.match(r"^\s*(use|implicit)\b", ln, re.I):
+                continue
+            if DECL.match(ln) and "::" in ln:
+                attrs, names = ln.split("::", 1)
+                is_arr = re.search(r"dimension\s*\(", attrs, re.I) is not None
+                intent = re.search(r"intent\s*\(\s*(\w+)\s*\)", attrs, re.I)
+                if re.search(r"\bparameter\b", attrs, re.I):
+                    continue
+                for nm in split_top(names):
+                    base = re.match(r"\s*(\w+)", nm).group(1)
+                    if is_arr or "(" in nm:
+                        self.arrays.add(base)
+                    elif intent and intent.group(1).lower() in ("out", "inout") and base in self.args:
+                        self.out_scalars.append(base)
+                continue
+            body.append(ln)
+        self.out_scalars.sort(key=self.args.index)
+        self.body = body
+
+    def python(self):
+        src = [f"def {self.name}({', '.join(self.args)}):"]
+        ind = 1
+
+        def emit(s):
+            src.append("    " * ind + s)
+
+        for ln in self.body:
+            low = ln.lower().strip()
+            if "icepack_warnings" in low:
+                continue                                   # diagnostics plumbing, not arithmetic
+            m = re.match(r"^call\s+icepack_query_parameters\s*\(\s*(\w+)_out\s*=\s*(\w+)\s*\)$", ln.strip(), re.I)
+            if m:
+                emit(f"{m.group(2)} = ICEPACK[{m.group(1).lower()!r}]")
+                continue
+            m = re.match(r"^do\s+(\w+)\s*=\s*(.+)$", ln.strip(), re.I)
+            if m:
+                lo, hi = split_top(m.group(2))[:2]
+                emit(f"for {m.group(1)} in range({tr_expr(lo, self.arrays)}, ({tr_expr(hi, self.arrays)}) + 1):")
+                ind += 1
+                continue
+            if re.match(r"^end\s*do\b", low):
+                ind -= 1
+                continue
+            m = re.match(r"^if\s*\((.*)\)\s*then$", ln.strip(), re.I)
+            if m:
+                emit(f"if {tr_expr(m.group(1), self.arrays)}:")
+                ind += 1
+                continue
+            m = re.match(r"^else\s*if\s*\((.*)\)\s*then$", ln.strip(), re.I)
+            if m:
+                ind -= 1
+                emit(f"elif {tr_expr(m.group(1), self.arrays)}:")
+                ind += 1
+                continue
+            if low == "else":
+                ind -= 1
+                emit("else:")
+                ind += 1
+                continue
+            if re.match(r"^end\s*if\b", low):
+                ind -= 1
+                continue
+            m = re.match(r"^call\s+(\w+)\s*\((.*)\)$", ln.strip(), re.I)
+            if m:
+                callee = self.registry[m.group(1)]
+                actual = split_top(m.group(2))
+                if len(actual) != len(callee.args):
+                    raise SyntaxError(f"{self.name}: call {m.group(1)} with {len(actual)} args, expected {len(callee.args)}")
+                outs = [actual[callee.args.index(o)] for o in callee.out_scalars]
+                pyargs = ["None" if callee.args[k] in callee.out_scalars and re.fullmatch(r"\w+", a) else tr_expr(a, self.arrays)
+                          for k, a in enumerate(actual)]
+                emit(f"{', '.join(outs)}{',' if len(outs) == 1 else ''} = {callee.name}({', '.join(pyargs)})")
+                continue
+            m = re.match(r"^(\w+)\s*\(\s*:(\s*,\s*:)*\s*\)\s*=\s*(.+)$", ln.strip())
+            if m:                                          # whole-array assignment  a(:,:,:) = c0
+                emit(f"{m.group(1)}.fill({tr_expr(m.group(3), self.arrays)})")
+                continue
+            # assignment: split at the first top-level '=' that is not part of a relational operator
+            depth, eq = 0, None
+            for k, ch in enumerate(ln):
+                if ch == "(":
+                    depth += 1
+                elif ch == ")":
+                    depth -= 1
+                elif ch == "=" and depth == 0 and ln[k + 1:k + 2] != "=" and ln[k - 1:k] not in ("=", "/", "<", ">"):
+                    eq = k
+                    break
+            if eq is None:
+                raise SyntaxError(f"{self.name}: cannot translate statement {ln!r}")
+            emit(f"{tr_expr(ln[:eq], self.arrays)} = {tr_expr(ln[eq + 1:], self.arrays)}")
+        ret = ", ".join(self.out_scalars)
+        src.append(f"    return ({ret}{',' if len(self.out_scalars) == 1 else ''})" if self.out_scalars else "    return None")
+        return "\n".join(src)
+
+
+def reference_constants():
+    """evaluate the `real (kind=dbl_kind), parameter` definitions of ice_constants.F90 in source order."""
+    env = {}
+    for ln in logical_lines(open(os.path.join(REF, F_CONST)).read()):
+        if not (re.match(r"^\s*real\b", ln, re.I) and re.search(r"\bparameter\b", ln, re.I) and "::" in ln):
+            continue
+        for item in split_top(ln.split("::", 1)[1]):
+            if "=" not in item:
+                continue
+            nm, ex = item.split("=", 1)
+            try:
+                env[nm.strip()] = float(eval(tr_expr(ex), {"math": math, "_sq": lambda x: x * x}, dict(env)))
+            except Exception:
+                pass  # parameters built from names defined elsewhere (not needed by the dynamics)
+    return env
+
+
+# ------------------------------------------------------------------------------------------
+# Fortran arrays: 1-based, first index fastest, over numpy arrays stored (..., ny, nx)
+# ------------------------------------------------------------------------------------------
+class FArr:
+    def __init__(self, a):
+        self.a = a
+
+    def __getitem__(self, idx):
+        if not isinstance(idx, tuple):
+            return self.a[idx - 1].item()
+        return self.a[tuple(k - 1 for k in reversed(idx))].item()
+
+    def __setitem__(self, idx, v):
+        if not isinstance(idx, tuple):
+            self.a[idx - 1] = v
+        else:
+            self.a[tuple(k - 1 for k in reversed(idx))] = v
+
+    def fill(self, v):
+        self.a[...] = v
+
+
+def build_reference_functions(params):
+    reg = {}
+    reg["strain_rates"] = Sub(F_SHARED, "strain_rates", reg)
+    reg["visc_replpress"] = Sub(F_SHARED, "visc_replpress", reg)
+    reg["stress"] = Sub(F_EVP, "stress", reg)
+    reg["stepu"] = Sub(F_SHARED, "stepu", reg)
+    env = {"math": math, "_sq": lambda x: x * x, "_sign": lambda a, b: math.copysign(abs(a), b), "_trim": lambda s: s.strip(),
+           "ICEPACK": {"rhow": params["rhow"]}}
+    env.update(reference_constants())
+    # module variables of ice_dyn_shared the routines read (set_evp_parameters, ice_dyn_shared.F90:453-486)
+    for k in ("arlx1i", "denom1", "revp", "brlx", "e_factor", "epp2i", "capping", "Ktens", "u0", "cosw", "sinw"):
+        env[k] = float(params[k])
+    srcs = {}
+    for nm in ("strain_rates", "visc_replpress", "stress", "stepu"):
+        srcs[nm] = reg[nm].python()
+        exec(compile(srcs[nm], f"<{nm} transliterated from {REF}>", "exec"), env)
+    return env, srcs
+
+
+# ------------------------------------------------------------------------------------------
+# the subcycle loop of ice_dyn_evp.F90:859-913 on ONE block, driven with the reference's index lists
+# ------------------------------------------------------------------------------------------
+def run_reference_loop(case, ndte):
+    """case: cice_b200.synth.Case with a single block (E-W cyclic, N-S closed/open).  Returns the inout fields."""
+    g, p = case.grid, dict(case.params)
+    assert g["nblocks"] == 1
+    nxb, nyb = g["nx_block"], g["ny_block"]
+    ilo, ihi, jlo, jhi = (int(g[k][0]) for k in ("ilo", "ihi", "jlo", "jhi"))
+    env, _ = build_reference_functions(p)
+    f = {k: v[0].copy() for k, v in case.fields.items()}       # (ny_block, nx_block)
+    geo = {k: np.asarray(g[k][0]) for k in ("dxT", "dyT", "dxhy", "dyhx", "cxp", "cyp", "cxm", "cym", "DminTarea", "uarear")}
+    A = {k: FArr(v) for k, v in {**f, **geo}.items()}
+    # index lists exactly as dyn_prep2 builds them (ice_dyn_shared.F90:740-749, 759-770)
+    Ti, Tj, Ui, Uj = [], [], [], []
+    for j in range(jlo, jhi + 2):
+        for i in range(ilo, ihi + 2):
+            if f["iceTmask"][j - 1, i - 1]:
+                Ti.append(i); Tj.append(j)
+    for j in range(jlo, jhi + 1):
+        for i in range(ilo, ihi + 1):
+            if f["iceUmask"][j - 1, i - 1]:
+                Ui.append(i); Uj.append(j)
+    indxTi, indxTj = FArr(np.array(Ti or [0])), FArr(np.array(Tj or [0]))
+    indxUi, indxUj = FArr(np.array(Ui or [0])), FArr(np.array(Uj or [0]))
+    strtmp = FArr(np.zeros((8, nyb, nxb)))
+    uinit, vinit = FArr(f["uvel"].copy()), FArr(f["vvel"].copy())
+    cyclic = g["ew_boundary_type"] == 2
+    for _ in range(ndte):
+        env["stress"](nxb, nyb, len(Ti), indxTi, indxTj, A["uvel"], A["vvel"], A["dxT"], A["dyT"], A["dxhy"], A["dyhx"],
+                      A["cxp"], A["cyp"], A["cxm"], A["cym"], A["DminTarea"], A["strength"],
+                      A["stressp_1"], A["stressp_2"], A["stressp_3"], A["stressp_4"], A["stressm_1"], A["stressm_2"],
+                      A["stressm_3"], A["stressm_4"], A["stress12_1"], A["stress12_2"], A["stress12_3"], A["stress12_4"], strtmp)
+        env["stepu"](nxb, nyb, len(Ui), A["cdn_ocnU"], indxUi, indxUj, A["aiU"], strtmp, A["uocnU"], A["vocnU"],
+                     A["waterxU"], A["wateryU"], A["forcexU"], A["forceyU"], A["umassdti"], A["fmU"], A["uarear"],
+                     A["strintxU"], A["strintyU"], A["taubxU"], A["taubyU"], uinit, vinit, A["uvel"], A["vvel"], A["TbU"])
+        # dyn_haloUpdate(uvel, vvel) for one block that spans the domain: E-W cyclic wrap, N-S closed (ghost rows untouched)
+        if cyclic:
+            for a in (f["uvel"], f["vvel"]):
+                a[:, ilo - 2] = a[:, ihi - 1]
+                a[:, ihi] = a[:, ilo - 1]
+    return f
+
+
+# synth.make_case keywords (+ "params": overrides of the EVP scalars) -- seeds give random velocities, stresses and TbU (set S2)
+CASES = [dict(config="tiny", seed=61, ndte=6),
+         dict(config="tiny", seed=62, ndte=4, revised_evp=True),
+         dict(config="tiny", seed=63, ndte=5, kmt="continents"),
+         dict(config="tiny", seed=64, ndte=5, params=dict(capping=0.0, Ktens=0.2)),          # the general visc_replpress branch
+         dict(config="tiny", seed=65, ndte=3, params=dict(cosw=0.9, sinw=0.4358898943540674)),  # turning angle in stepu
+         dict(config="tiny", ndte=8),                                                          # set S1: box2001 start from rest
+         dict(config="gx3", seed=66, ndte=3)]
+FIELDS = ("stressp_1", "stressp_2", "stressp_3", "stressp_4", "stressm_1", "stressm_2", "stressm_3", "stressm_4",
+          "stress12_1", "stress12_2", "stress12_3", "stress12_4", "strintxU", "strintyU", "taubxU", "taubyU", "uvel", "vvel")
+
+
+def make(synth, kw):
+    kw = dict(kw)
+    over = kw.pop("params", {})
+    c = synth.make_case(**kw)
+    c.params.update(over)
+    return c
+
+
+def generate(only=None):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from cice_b200 import synth
+    out = {}
+    for n, kw in enumerate(CASES):
+        if only is not None and n not in only:
+            continue
+        c = make(synth, kw)
+        f = run_reference_loop(c, c.params["ndte"])
+        for k in FIELDS:
+            out[f"case{n}_{k}"] = f[k]
+    return out
+
+
+FULL_VECTORS = (0, 1, 3)   # cases whose arrays are committed in full; every case is committed as sha256 per field
+SHA = os.path.join(HERE, "ref_source_vectors.json")
+
+
+def sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a, dtype=np.float64).tobytes()).hexdigest()
+
+
+if __name__ == "__main__":
+    import json
+    vec = generate()
+    if "--write" in sys.argv:
+        np.savez_compressed(OUT, **{k: v for k, v in vec.items() if int(k[4:k.index("_")]) in FULL_VECTORS})
+        meta = {"_how": "python tests/golden/ref_translit.py --write  (transliterates stress/stepu/strain_rates/visc_replpress of the reference "
+                        "source under /root/reference and runs them; see the module docstring)",
+                "cases": [dict(kw) for kw in CASES], "sha256": {k: sha(v) for k, v in vec.items()}}
+        json.dump(meta, open(SHA, "w"), indent=1)
+        print("wrote", OUT, os.path.getsize(OUT), "bytes;", SHA)
+    if "--show" in sys.argv:
+        _, srcs = build_reference_functions(dict(arlx1i=0, denom1=0, revp=0, brlx=0, e_factor=0, epp2i=0, capping=1, Ktens=0, u0=0, cosw=1,
+                                                 sinw=0, rhow=1026))
+        for k, v in srcs.items():
+            print(v, "\n")
+    print({k: float(np.abs(v).max()) for k, v in vec.items() if k.startswith("case0_") and k.endswith(("uvel", "stressp_1"))})

@@ -410,3 +410,11 @@ def test_land_block_elimination(oracle_mod, evp_lib, kernel, cfg, bs):
         evp_lib.dyn_evp_b200_finalize()
         evp_lib.allow_partial_domain(False)
     assert_bitwise(got, ref)
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
+def test_gpu_matches_vectors_from_reference_source(evp_lib, kernel):
+    """the CUDA path against vectors produced from the reference's own Fortran text (tests/golden/ref_translit.py), without
+    the C oracle in between: bit for bit, every kernel strategy."""
+    from tests.test_oracle import check_against_ref_source_vectors
+    check_against_ref_source_vectors(lambda c: run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=kernel))
