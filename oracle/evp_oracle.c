@@ -11,9 +11,9 @@
  *   boundary.F90 = cicecore/cicedyn/infrastructure/comm/mpi/ice_boundary.F90
  *   halochk.F90  = cicecore/drivers/unittest/halochk/halochk.F90
  *
- * PARITY UNPINNED BY VECTORS (see evp_oracle.h): no Fortran compiler exists in this image and
- * the reference stores no golden vectors for this path; the restatement is pinned by the
- * properties the reference asserts (decomposition invariance, 2-D == 1-D, halochk values).
+ * PINNING (see evp_oracle.h): no Fortran compiler exists in this image; the restatement reproduces, bit for bit, vectors
+ * generated from the reference's own source text (tests/golden/ref_translit.py) and satisfies the properties the
+ * reference asserts (decomposition invariance, 2-D == 1-D, halochk values).  Not pinned by a compiled reference binary.
  *
  * Arithmetic contract: expressions keep the Fortran source's operator order (left to right
  * at equal precedence, `x**2` as x*x).  Built with -O2 -ffp-contract=off this file defines the

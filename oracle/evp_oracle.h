@@ -5,11 +5,18 @@
  * may load this library, and only as the checker or the timed CPU baseline.  The product
  * (cice_b200/) never links, imports or calls it.
  *
- * PARITY UNPINNED BY VECTORS: the reference (Fortran) cannot be compiled in this image
- * (no f951 / MPI / csh) and ships no golden vectors for this path, so this
- * restatement is pinned by the properties the reference itself asserts (bit-for-bit under
- * any block decomposition, 2-D == 1-D formulation, halochk closed-form halo values), not
- * by outputs of the reference binary.
+ * PINNING: the reference (Fortran) cannot be compiled in this image (no f951 / MPI / csh) and ships no
+ * golden vectors for this path.  The restatement is pinned
+ *   (1) by vectors generated FROM THE REFERENCE'S SOURCE TEXT: tests/golden/ref_translit.py reads the Fortran
+ *       subroutines under /root/reference, transliterates them statement by statement into Python (same operators,
+ *       operand order and parentheses; IEEE doubles, no contraction) and executes them; this oracle reproduces those
+ *       vectors bit for bit (tests/golden/ref_source_vectors.{npz,json}; B grid: stress, stepu, strain_rates,
+ *       visc_replpress; C grid: strain_rates_U/Tdt, stressC_T/U, div_stress_Ex/Ny, stepu_C, stepv_C, grid_average_X2Y*;
+ *       deformations; ice_constants).  Not covered that way: the MPI halo (ice_boundary.F90) and the 1-D solver;
+ *   (2) by the properties the reference itself asserts (bit-for-bit under any block decomposition and with eliminated
+ *       land blocks, 2-D == 1-D formulation, halochk closed-form halo values).
+ * It is still not pinned by outputs of a COMPILED reference binary: compiler-specific reassociation or FMA contraction
+ * in a real Fortran build is outside what a source-level transliteration can show.
  *
  * The entry points take the SAME structs as the product's C ABI (include/evp_b200.h) so a
  * test feeds both sides from one set of buffers.

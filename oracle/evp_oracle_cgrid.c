@@ -1,6 +1,7 @@
 /*
  * evp_oracle_cgrid.c -- CPU oracle for the C-grid branch of CICE's EVP subcycling loop.
- * TEST INFRASTRUCTURE ONLY (see evp_oracle.h).  PARITY UNPINNED BY VECTORS (no Fortran compiler here).
+ * TEST INFRASTRUCTURE ONLY (see evp_oracle.h).  Pinned bit for bit to vectors generated from the reference's source text
+ * (tests/golden/ref_translit.py, ccase*); not pinned by a compiled reference binary (no Fortran compiler here).
  *
  * Restates, with the Fortran operator order, the `grid_ice == "C"` loop of
  *   evp.F90:936-1101 (cicecore/cicedyn/dynamics/ice_dyn_evp.F90) and the routines it calls:

@@ -1,8 +1,8 @@
 """ctypes binding of the C oracle (oracle/evp_oracle.c).  TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module;
-the product package (cice_b200) never does.  Parity is unpinned by reference vectors -- see the
-header of evp_oracle.h.
+the product package (cice_b200) never does.  Pinned to vectors generated from the reference's source text
+(tests/golden/ref_translit.py), not to a compiled reference binary -- see the header of evp_oracle.h.
 """
 import ctypes as C
 import os

@@ -1,25 +1,33 @@
-"""Pin the CPU oracle to the reference's own SOURCE TEXT.
+"""Pin the CPU oracle (and, through tests/, the CUDA path) to the reference's own SOURCE TEXT.
 
 The reference is Fortran 90 and cannot be compiled in this image (no f951), and it stores no golden vectors
 for the EVP path.  Its hot-path subroutines, however, are straight-line fp64 arithmetic:
 
-    stress          cicecore/cicedyn/dynamics/ice_dyn_evp.F90      
-    stepu           cicecore/cicedyn/dynamics/ice_dyn_shared.F90   (a3)
-    strain_rates    .../ice_dyn_shared.F90                         (a4)
-    visc_replpress  .../ice_dyn_shared.F90                         (a5)
-    constants       cicecore/shared/ice_constants.F90              (p111 = c1/c9 ...)
+  B grid   stress            cicecore/cicedyn/dynamics/ice_dyn_evp.F90      
+           stepu             cicecore/cicedyn/dynamics/ice_dyn_shared.F90   (a3)
+           strain_rates      .../ice_dyn_shared.F90                         (a4)
+           visc_replpress    .../ice_dyn_shared.F90                         (a5)
+  C grid   strain_rates_U, strain_rates_Tdt, stepu_C, stepv_C   ice_dyn_shared.F90          (a12)
+           stressC_T, stressC_U, div_stress_Ex, div_stress_Ny   ice_dyn_evp.F90
+           grid_average_X2Y_1 / X2YS / X2YA                     cicecore/cicedyn/infrastructure/ice_grid.F90
+  next     deformations      .../ice_dyn_shared.F90                         (8f rank 2)
+  constants                  cicecore/shared/ice_constants.F90              (p111 = c1/c9 ...)
 
 This script READS those subroutines from /root/reference at generation time, transliterates them statement
 by statement into Python -- same operators, same operand order, same parentheses; a Python float is an IEEE
-double and `a op b` is rounded once, exactly like Fortran without FMA contraction -- executes the result on
-a synthetic case (the subcycle loop of ice_dyn_evp.F90:859-913 with the reference's own index lists), and
-writes the outputs as golden vectors.  Nothing of the arithmetic is restated by hand here: the translator
-knows Fortran syntax (continuations, do/if, call with intent(out) scalars, array references, `x**2`), not
-the formulas.  tests/test_oracle.py::test_oracle_matches_vectors_from_reference_source then compares the C
-oracle with the committed vectors bit for bit (runs anywhere), and ::test_reference_source_vectors_regenerate
-re-derives them from /root/reference when it is present.
+double and `a op b` is rounded once, exactly like Fortran without reassociation or FMA contraction -- executes
+the result on synthetic cases inside a driver that repeats the reference's loop (ice_dyn_evp.F90:859-913 and
+:936-1101: call order, index lists, halo points), and writes the outputs as golden vectors.  Nothing of the
+arithmetic is restated by hand here: the translator knows Fortran syntax (continuations, do / if / select case,
+call with intent(out) scalars, generic interfaces, array references and sections, derived-type members, `x**2`),
+not the formulas.  The halo between the calls is not transliterated (ice_boundary.F90 is MPI code): the B-grid
+driver applies the single-block cyclic wrap directly, the C-grid driver is handed the oracle's halo routine.
 
-usage:  python tests/golden/ref_translit.py [--write]      (run from the repo root, in the container that has /root/reference)
+Consumers: tests/test_oracle.py, tests/test_cgrid.py (the C oracle against the committed vectors, bit for bit,
+anywhere; re-derivation from /root/reference where it exists) and tests/test_gpu_parity.py, tests/test_cgrid.py
+-m gpu (the CUDA path against the same vectors).
+
+usage:  python tests/golden/ref_translit.py [--write] [--show]     (repo root, in the container that has /root/reference)
 """
 import math
 import os
@@ -94,7 +102,7 @@ TOK = re.compile(r"""\s*(?:
   | (?P<dot>\.(?:and|or|not|true|false|eq|ne|lt|le|gt|ge)\.)
   | (?P<id>[A-Za-z_]\w*)
   | (?P<str>'[^']*'|"[^"]*")
-  | (?P<op>\*\*|==|/=|<=|>=|[-+*/(),<>=:])
+  | (?P<op>\*\*|==|/=|<=|>=|[-+*/(),<>=:%])
 )""", re.X | re.I)
 
 INTRINSICS = {"sqrt": "math.sqrt", "max": "max", "min": "min", "abs": "abs", "sign": "_sign", "trim": "_trim", "real": "float"}
@@ -209,7 +217,22 @@ class Expr:
             self.expect(")")
             return f"({e})"
         if k == "id":
+            v = v.lower()                         # Fortran is case-insensitive (deltaU / DeltaU)
+            while self.peek()[1] == "%":          # derived-type member: this_block%ilo
+                self.next()
+                v = f"{v}.{self.next()[1].lower()}"
             if self.peek()[1] == "(":
+                # array section name(:,:) / name(:) -> the whole array
+                q = self.p + 1
+                sec = True
+                while q < len(self.t) and self.t[q][1] != ")":
+                    if self.t[q][1] not in (":", ","):
+                        sec = False
+                        break
+                    q += 1
+                if sec and q < len(self.t) and q > self.p + 1:
+                    self.p = q + 1
+                    return v
                 self.next()
                 args = []
                 if self.peek()[1] != ")":
@@ -218,8 +241,8 @@ class Expr:
                         self.next()
                         args.append(self.parse())
                 self.expect(")")
-                if v.lower() in INTRINSICS and v.lower() not in self.arrays:
-                    return f"{INTRINSICS[v.lower()]}({', '.join(args)})"
+                if v in INTRINSICS and v not in self.arrays:
+                    return f"{INTRINSICS[v]}({', '.join(args)})"
                 return f"{v}[{', '.join(args)}]"      # array element
             return v
         raise SyntaxError(f"unexpected token {v!r}")
@@ -263,8 +286,9 @@ class Sub:
         self.name, self.registry = name, registry
         L = subroutine_lines(path, name)
         m = re.match(r"^\s*subroutine\s+\w+\s*\((.*)\)\s*$", L[0], re.I)
-        self.args = [a.strip() for a in m.group(1).split(",")]
+        self.args = [a.strip().lower() for a in m.group(1).split(",")]
         self.arrays, self.out_scalars, self.locals_ = set(), [], set()
+        self.local_arrays = []   # (name, [dims]) declared in the body, not dummy arguments
         body = []
         for ln in L[1:-1]:
             if re.match(r"^\s*(use|implicit)\b", ln, re.I):
@@ -272,13 +296,17 @@ class Sub:
             if DECL.match(ln) and "::" in ln:
                 attrs, names = ln.split("::", 1)
                 is_arr = re.search(r"dimension\s*\(", attrs, re.I) is not None
+                mdim = re.search(r"dimension\s*\(([^)]*)\)", attrs, re.I)
                 intent = re.search(r"intent\s*\(\s*(\w+)\s*\)", attrs, re.I)
                 if re.search(r"\bparameter\b", attrs, re.I):
                     continue
                 for nm in split_top(names):
-                    base = re.match(r"\s*(\w+)", nm).group(1)
+                    base = re.match(r"\s*(\w+)", nm).group(1).lower()
                     if is_arr or "(" in nm:
                         self.arrays.add(base)
+                        if base not in self.args:
+                            dims = mdim.group(1) if mdim else nm[nm.index("(") + 1:nm.rindex(")")]
+                            self.local_arrays.append((base, split_top(dims)))
                     elif intent and intent.group(1).lower() in ("out", "inout") and base in self.args:
                         self.out_scalars.append(base)
                 continue
@@ -287,11 +315,15 @@ class Sub:
         self.body = body
 
     def python(self):
-        src = [f"def {self.name}({', '.join(self.args)}):"]
+        src = [f"def {self.name.lower()}({', '.join(self.args)}):"]
         ind = 1
+        sel = []   # stack of (selector expression, first case seen) for select case
 
         def emit(s):
             src.append("    " * ind + s)
+
+        for nm, dims in self.local_arrays:
+            emit(f"{nm} = _alloc({', '.join(tr_expr(d, self.arrays) for d in dims)})")
 
         for ln in self.body:
             low = ln.lower().strip()
@@ -299,16 +331,49 @@ class Sub:
                 continue                                   # diagnostics plumbing, not arithmetic
             m = re.match(r"^call\s+icepack_query_parameters\s*\(\s*(\w+)_out\s*=\s*(\w+)\s*\)$", ln.strip(), re.I)
             if m:
-                emit(f"{m.group(2)} = ICEPACK[{m.group(1).lower()!r}]")
+                emit(f"{m.group(2).lower()} = ICEPACK[{m.group(1).lower()!r}]")
                 continue
             m = re.match(r"^do\s+(\w+)\s*=\s*(.+)$", ln.strip(), re.I)
             if m:
                 lo, hi = split_top(m.group(2))[:2]
-                emit(f"for {m.group(1)} in range({tr_expr(lo, self.arrays)}, ({tr_expr(hi, self.arrays)}) + 1):")
+                emit(f"for {m.group(1).lower()} in range({tr_expr(lo, self.arrays)}, ({tr_expr(hi, self.arrays)}) + 1):")
                 ind += 1
                 continue
             if re.match(r"^end\s*do\b", low):
                 ind -= 1
+                continue
+            if re.match(r"^call\s+abort_ice\b", low):
+                emit(f"raise RuntimeError({ln.strip()!r})")
+                continue
+            m = re.match(r"^this_block\s*=\s*get_block\s*\(", ln.strip(), re.I)
+            if m:
+                emit("this_block = get_block(iblk)")      # ice_blocks.F90 get_block: the block table entry
+                continue
+            m = re.match(r"^select\s+case\s*\((.*)\)$", ln.strip(), re.I)
+            if m:
+                sel.append([tr_expr(m.group(1), self.arrays), False])
+                continue
+            m = re.match(r"^case\s*\((.*)\)$", ln.strip(), re.I)
+            if m:
+                vals = ", ".join(tr_expr(v, self.arrays) for v in split_top(m.group(1)))
+                if sel[-1][1]:
+                    ind -= 1
+                emit(f"{'elif' if sel[-1][1] else 'if'} {sel[-1][0]} in ({vals},):")
+                sel[-1][1] = True
+                ind += 1
+                continue
+            if re.match(r"^case\s+default$", low):
+                if sel[-1][1]:
+                    ind -= 1
+                    emit("else:")
+                else:
+                    emit("if True:")
+                sel[-1][1] = True
+                ind += 1
+                continue
+            if re.match(r"^end\s*select\b", low):
+                if sel.pop()[1]:
+                    ind -= 1
                 continue
             m = re.match(r"^if\s*\((.*)\)\s*then$", ln.strip(), re.I)
             if m:
@@ -329,20 +394,44 @@ class Sub:
             if re.match(r"^end\s*if\b", low):
                 ind -= 1
                 continue
+            if re.match(r"^if\s*\(", ln.strip(), re.I):       # one-line  if (cond) statement
+                st = ln.strip()
+                depth, k = 0, st.index("(")
+                for k in range(st.index("("), len(st)):
+                    depth += st[k] == "("
+                    depth -= st[k] == ")"
+                    if depth == 0:
+                        break
+                emit(f"if {tr_expr(st[st.index('(') + 1:k], self.arrays)}:")
+                ind += 1
+                ln = st[k + 1:].strip()
+                one_line = True
+            else:
+                one_line = False
             m = re.match(r"^call\s+(\w+)\s*\((.*)\)$", ln.strip(), re.I)
             if m:
-                callee = self.registry[m.group(1)]
                 actual = split_top(m.group(2))
+                if m.group(1) not in self.registry:   # a routine this script does not transliterate (never reached by the driver)
+                    emit(f"raise RuntimeError('{m.group(1)} is not transliterated')")
+                    if one_line:
+                        ind -= 1
+                    continue
+                callee = self.registry[m.group(1)]
+                if isinstance(callee, list):      # generic interface: resolved by the number of arguments
+                    callee = [c for c in callee if len(c.args) == len(actual)][0]
                 if len(actual) != len(callee.args):
                     raise SyntaxError(f"{self.name}: call {m.group(1)} with {len(actual)} args, expected {len(callee.args)}")
-                outs = [actual[callee.args.index(o)] for o in callee.out_scalars]
+                outs = [tr_expr(actual[callee.args.index(o)], self.arrays) for o in callee.out_scalars]
                 pyargs = ["None" if callee.args[k] in callee.out_scalars and re.fullmatch(r"\w+", a) else tr_expr(a, self.arrays)
                           for k, a in enumerate(actual)]
-                emit(f"{', '.join(outs)}{',' if len(outs) == 1 else ''} = {callee.name}({', '.join(pyargs)})")
+                lhs = f"{', '.join(outs)}{',' if len(outs) == 1 else ''} = " if outs else ""
+                emit(f"{lhs}{callee.name.lower()}({', '.join(pyargs)})")
+                if one_line:
+                    ind -= 1
                 continue
             m = re.match(r"^(\w+)\s*\(\s*:(\s*,\s*:)*\s*\)\s*=\s*(.+)$", ln.strip())
             if m:                                          # whole-array assignment  a(:,:,:) = c0
-                emit(f"{m.group(1)}.fill({tr_expr(m.group(3), self.arrays)})")
+                emit(f"{m.group(1).lower()}.fill({tr_expr(m.group(3), self.arrays)})")
                 continue
             # assignment: split at the first top-level '=' that is not part of a relational operator
             depth, eq = 0, None
@@ -357,6 +446,8 @@ class Sub:
             if eq is None:
                 raise SyntaxError(f"{self.name}: cannot translate statement {ln!r}")
             emit(f"{tr_expr(ln[:eq], self.arrays)} = {tr_expr(ln[eq + 1:], self.arrays)}")
+            if one_line:
+                ind -= 1
         ret = ", ".join(self.out_scalars)
         src.append(f"    return ({ret}{',' if len(self.out_scalars) == 1 else ''})" if self.out_scalars else "    return None")
         return "\n".join(src)
@@ -373,7 +464,7 @@ def reference_constants():
                 continue
             nm, ex = item.split("=", 1)
             try:
-                env[nm.strip()] = float(eval(tr_expr(ex), {"math": math, "_sq": lambda x: x * x}, dict(env)))
+                env[nm.strip().lower()] = float(eval(tr_expr(ex), {"math": math, "_sq": lambda x: x * x}, dict(env)))
             except Exception:
                 pass  # parameters built from names defined elsewhere (not needed by the dynamics)
     return env
@@ -413,6 +504,7 @@ def build_reference_functions(params):
     # module variables of ice_dyn_shared the routines read (set_evp_parameters, ice_dyn_shared.F90:453-486)
     for k in ("arlx1i", "denom1", "revp", "brlx", "e_factor", "epp2i", "capping", "Ktens", "u0", "cosw", "sinw"):
         env[k] = float(params[k])
+    env = {k.lower() if k not in ("ICEPACK",) else k: v for k, v in env.items()}
     srcs = {}
     for nm in ("strain_rates", "visc_replpress", "stress", "stepu"):
         srcs[nm] = reg[nm].python()
@@ -464,6 +556,134 @@ def run_reference_loop(case, ndte):
     return f
 
 
+# ------------------------------------------------------------------------------------------
+# C grid: the subcycle loop of ice_dyn_evp.F90:936-1101 on ONE block
+# ------------------------------------------------------------------------------------------
+F_GRID = "cicecore/cicedyn/infrastructure/ice_grid.F90"
+
+
+class _Block:
+    pass
+
+
+def build_reference_cfunctions(params, case):
+    reg = {}
+    for path, name in ((F_SHARED, "visc_replpress"), (F_SHARED, "strain_rates_Tdt"), (F_SHARED, "strain_rates_Tdtsd"),
+                       (F_SHARED, "strain_rates_U"), (F_EVP, "stressC_T"), (F_EVP, "stressC_U"), (F_EVP, "div_stress_Ex"),
+                       (F_EVP, "div_stress_Ny"), (F_SHARED, "stepu_C"), (F_SHARED, "stepv_C"), (F_GRID, "grid_average_X2YS"),
+                       (F_GRID, "grid_average_X2YA"), (F_GRID, "grid_average_X2Y_1")):
+        reg[name] = Sub(path, name, reg)
+    reg["strain_rates_T"] = [reg["strain_rates_Tdt"], reg["strain_rates_Tdtsd"]]   # interface, ice_dyn_shared.F90:146
+    g, cg = case.grid, case.cgrid
+    blk = _Block()
+    blk.ilo, blk.ihi, blk.jlo, blk.jhi = (int(g[k][0]) for k in ("ilo", "ihi", "jlo", "jhi"))
+    env = {"math": math, "_sq": lambda x: x * x, "_sign": lambda a, b: math.copysign(abs(a), b), "_trim": lambda s: s.strip(),
+           "_alloc": lambda nx, ny: FArr(np.zeros((ny, nx))), "ICEPACK": {"rhow": params["rhow"]},
+           "nblocks": 1, "get_block": lambda iblk: blk}
+    env.update(reference_constants())
+    for k in ("arlx1i", "denom1", "revp", "brlx", "e_factor", "epp2i", "capping", "Ktens", "u0", "cosw", "sinw", "deltaminEVP"):
+        env[k] = float(params[k])
+    env["visc_method"] = "avg_strength" if params["visc_method"] == 1 else "avg_zeta"   # dynamics_nml visc_method (ice_init.F90:453)
+    for k in ("tarea", "hm", "uvm", "earea", "narea", "epm", "npm", "uarea"):            # ice_grid module arrays of grid_average_X2Y_1
+        env[k] = FArr(np.asarray(cg[k]))
+    env = {k.lower() if k not in ("ICEPACK",) else k: v for k, v in env.items()}
+    for nm in ("visc_replpress", "strain_rates_Tdt", "strain_rates_Tdtsd", "strain_rates_U", "stressC_T", "stressC_U", "div_stress_Ex",
+               "div_stress_Ny", "stepu_C", "stepv_C", "grid_average_X2YS", "grid_average_X2YA", "grid_average_X2Y_1"):
+        exec(compile(reg[nm].python(), f"<{nm} transliterated from {REF}>", "exec"), env)
+    return env
+
+
+def run_reference_cloop(case, ndte, halo_update):
+    """case: cice_b200.synth.CCase with a single block.  halo_update(arrays, field_loc, field_type): the ghost-cell refresh
+    (the halo is not what is being pinned here; the oracle's own halo, pinned by halochk's closed form, is passed in)."""
+    g, cg, p = case.grid, case.cgrid, dict(case.params)
+    assert g["nblocks"] == 1
+    nxb, nyb = g["nx_block"], g["ny_block"]
+    ilo, ihi, jlo, jhi = (int(g[k][0]) for k in ("ilo", "ihi", "jlo", "jhi"))
+    env = build_reference_cfunctions(p, case)
+    f = {k: np.ascontiguousarray(v.copy()) for k, v in case.fields.items()}     # (1, ny_block, nx_block)
+    A3 = {k: FArr(v) for k, v in f.items()}                                     # (i,j,iblk) views for grid_average
+    A = {k: FArr(v[0]) for k, v in f.items()}
+    G = {k: FArr(np.asarray(cg[k])[0]) for k in cg}
+    for k in ("dxT", "dyT", "DminTarea"):
+        G[k] = FArr(np.asarray(g[k])[0])
+
+    def index_list(mask, j1, i1):
+        I, J = [], []
+        for j in range(jlo, j1 + 1):
+            for i in range(ilo, i1 + 1):
+                if mask[0, j - 1, i - 1]:
+                    I.append(i); J.append(j)
+        return len(I), FArr(np.array(I or [0])), FArr(np.array(J or [0]))
+
+    nT, Ti, Tj = index_list(f["iceTmask"], jhi + 1, ihi + 1)     # T list includes the N/E ghost cells (shared.F90:740-749)
+    nU, Ui, Uj = index_list(f["iceUmask"], jhi, ihi)
+    nE, Ei, Ej = index_list(f["iceEmask"], jhi, ihi)
+    nN, Ni, Nj = index_list(f["iceNmask"], jhi, ihi)
+    uE0, vN0 = FArr(f["uvelE"][0].copy()), FArr(f["vvelN"][0].copy())
+    CENTER, NE, SCALAR, VECTOR = 0, 1, 0, 1
+    X2Y = env["grid_average_x2y_1"]       # grid_average_X2Y_base builds X2Y = grid1//'2'//grid2//type (ice_grid.F90:3817-3841)
+    for _ in range(ndte):                 # ice_dyn_evp.F90:938
+        env["strain_rates_u"](nxb, nyb, nU, Ui, Uj, A["uvelE"], A["vvelE"], A["uvelN"], A["vvelN"], A["uvel"], A["vvel"], G["dxE"], G["dyN"],
+                              G["dxU"], G["dyU"], G["ratiodxN"], G["ratiodxNr"], G["ratiodyE"], G["ratiodyEr"], G["epm"], G["npm"],
+                              A["divergU"], A["tensionU"], A["shearU"], A["deltaU"])
+        halo_update([f["shearU"]], NE, SCALAR)
+        env["stressc_t"](nxb, nyb, nT, Ti, Tj, A["uvelE"], A["vvelE"], A["uvelN"], A["vvelN"], G["dxN"], G["dyE"], G["dxT"], G["dyT"],
+                         G["uarea"], G["DminTarea"], A["strength"], A["shearU"], A["zetax2T"], A["etax2T"], A["stresspT"], A["stressmT"],
+                         A["stress12T"])
+        halo_update([f["zetax2T"], f["etax2T"], f["stresspT"], f["stressmT"]], CENTER, SCALAR)
+        if env["visc_method"] == "avg_strength":
+            X2Y("T2US", A3["strength"], A3["strengthU"])
+        else:
+            X2Y("T2US", A3["etax2T"], A3["etax2U"])
+        env["stressc_u"](nxb, nyb, nU, Ui, Uj, G["uarea"], A["etax2U"], A["deltaU"], A["strengthU"], A["shearU"], A["stress12U"])
+        halo_update([f["stress12U"]], NE, SCALAR)
+        env["div_stress_ex"](nxb, nyb, nE, Ei, Ej, G["dxE"], G["dyE"], G["dxU"], G["dyT"], G["earear"], A["rheofactE"], A["stresspT"],
+                             A["stressmT"], A["stress12U"], A["strintxE"])
+        env["div_stress_ny"](nxb, nyb, nN, Ni, Nj, G["dxN"], G["dyN"], G["dxT"], G["dyU"], G["narear"], A["rheofactN"], A["stresspT"],
+                             A["stressmT"], A["stress12U"], A["strintyN"])
+        env["stepu_c"](nxb, nyb, nE, A["cdn_ocnE"], Ei, Ej, A["aiE"], A["uocnE"], A["vocnE"], A["waterxE"], A["forcexE"], A["emassdti"],
+                       A["fmE"], A["strintxE"], A["taubxE"], uE0, A["uvelE"], A["vvelE"], A["TbE"])
+        env["stepv_c"](nxb, nyb, nN, A["cdn_ocnN"], Ni, Nj, A["aiN"], A["uocnN"], A["vocnN"], A["wateryN"], A["forceyN"], A["nmassdti"],
+                       A["fmN"], A["strintyN"], A["taubyN"], vN0, A["uvelN"], A["vvelN"], A["TbN"])
+        halo_update([f["uvelE"]], NE, VECTOR)
+        halo_update([f["vvelN"]], NE, VECTOR)
+        X2Y("E2NA", A3["uvelE"], A3["uvelN"])
+        X2Y("N2EA", A3["vvelN"], A3["vvelE"])
+        f["uvelN"][...] = f["uvelN"] * np.asarray(cg["npm"])      # uvelN(:,:,:) = uvelN(:,:,:)*npm(:,:,:)   evp.F90:1075
+        f["vvelE"][...] = f["vvelE"] * np.asarray(cg["epm"])
+        halo_update([f["uvelN"]], NE, VECTOR)
+        halo_update([f["vvelE"]], NE, VECTOR)
+        X2Y("E2UA", A3["uvelE"], A3["uvel"])
+        X2Y("N2UA", A3["vvelN"], A3["vvel"])
+        f["uvel"][...] = f["uvel"] * np.asarray(cg["uvm"])
+        f["vvel"][...] = f["vvel"] * np.asarray(cg["uvm"])
+        halo_update([f["uvel"], f["vvel"]], NE, VECTOR)
+    return f
+
+
+CCASES = [dict(config="tiny", seed=71, ndte=4), dict(config="tiny", seed=72, ndte=3, revised_evp=True),
+          dict(config="tiny", seed=73, ndte=3, visc_method=1), dict(config="tiny", ndte=5),
+          dict(config="tiny", seed=74, ndte=3, ew="closed", ns="closed"), dict(config="gx3", seed=75, ndte=2)]
+CFIELDS = ("uvelE", "vvelE", "uvelN", "vvelN", "uvel", "vvel", "stresspT", "stressmT", "stress12T", "stress12U", "zetax2T", "etax2T",
+           "divergU", "tensionU", "shearU", "deltaU", "strintxE", "strintyN", "taubxE", "taubyN")
+
+
+def generate_c(only=None):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from cice_b200 import synth
+    from oracle import oracle
+    out = {}
+    for n, kw in enumerate(CCASES):
+        if only is not None and n not in only:
+            continue
+        c = synth.make_ccase(**kw)
+        f = run_reference_cloop(c, c.params["ndte"], lambda arrs, loc, typ: oracle.halo_update(c.grid, arrs, loc, typ))
+        for k in CFIELDS:
+            out[f"ccase{n}_{k}"] = f[k]
+    return out
+
+
 # synth.make_case keywords (+ "params": overrides of the EVP scalars) -- seeds give random velocities, stresses and TbU (set S2)
 CASES = [dict(config="tiny", seed=61, ndte=6),
          dict(config="tiny", seed=62, ndte=4, revised_evp=True),
@@ -498,7 +718,50 @@ def generate(only=None):
     return out
 
 
+# ------------------------------------------------------------------------------------------
+# deformations (ice_dyn_shared.F90:1756-1860) on the random velocities of a set-S2 case
+# ------------------------------------------------------------------------------------------
+DFIELDS = ("divu", "shear", "vort", "rdg_conv", "rdg_shear")
+
+
+def deform_inputs(synth, seed=81):
+    c = synth.make_case("tiny", seed=seed, ndte=1)
+    X = c.X
+    tarear = np.where(X["tarea"] > 0, 1.0 / np.where(X["tarea"] > 0, X["tarea"], 1.0), 0.0)
+    d = {n: synth.scatter(a, c.blocks) for n, a in (("dxU", X["dxU"]), ("dyU", X["dyU"]), ("tarear", tarear))}
+    for n in DFIELDS:
+        d[n] = np.full(c.fields["uvel"].shape, -7.0)
+    return c, d
+
+
+def generate_d():
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from cice_b200 import synth
+    c, d = deform_inputs(synth)
+    g, p = c.grid, c.params
+    reg = {}
+    reg["strain_rates"] = Sub(F_SHARED, "strain_rates", reg)
+    reg["deformations"] = Sub(F_SHARED, "deformations", reg)
+    env = {"math": math, "_sq": lambda x: x * x, "_sign": lambda a, b: math.copysign(abs(a), b), "e_factor": float(p["e_factor"])}
+    env.update(reference_constants())
+    for nm in ("strain_rates", "deformations"):
+        exec(compile(reg[nm].python(), f"<{nm} transliterated from {REF}>", "exec"), env)
+    ilo, ihi, jlo, jhi = (int(g[k][0]) for k in ("ilo", "ihi", "jlo", "jhi"))
+    Ti, Tj = [], []
+    for j in range(jlo, jhi + 2):
+        for i in range(ilo, ihi + 2):
+            if c.fields["iceTmask"][0, j - 1, i - 1]:
+                Ti.append(i); Tj.append(j)
+    A = lambda a: FArr(np.asarray(a)[0])
+    out = {k: d[k].copy() for k in DFIELDS}
+    env["deformations"](g["nx_block"], g["ny_block"], len(Ti), FArr(np.array(Ti)), FArr(np.array(Tj)), A(c.fields["uvel"]), A(c.fields["vvel"]),
+                        A(g["dxT"]), A(g["dyT"]), A(d["dxU"]), A(d["dyU"]), A(g["cxp"]), A(g["cyp"]), A(g["cxm"]), A(g["cym"]), A(d["tarear"]),
+                        FArr(out["vort"][0]), FArr(out["shear"][0]), FArr(out["divu"][0]), FArr(out["rdg_conv"][0]), FArr(out["rdg_shear"][0]))
+    return {f"dcase0_{k}": v for k, v in out.items()}
+
+
 FULL_VECTORS = (0, 1, 3)   # cases whose arrays are committed in full; every case is committed as sha256 per field
+FULL_CVECTORS = (0, 2)
 SHA = os.path.join(HERE, "ref_source_vectors.json")
 
 
@@ -510,11 +773,18 @@ def sha(a):
 if __name__ == "__main__":
     import json
     vec = generate()
+    cvec = generate_c()
+    dvec = generate_d()
     if "--write" in sys.argv:
-        np.savez_compressed(OUT, **{k: v for k, v in vec.items() if int(k[4:k.index("_")]) in FULL_VECTORS})
-        meta = {"_how": "python tests/golden/ref_translit.py --write  (transliterates stress/stepu/strain_rates/visc_replpress of the reference "
-                        "source under /root/reference and runs them; see the module docstring)",
-                "cases": [dict(kw) for kw in CASES], "sha256": {k: sha(v) for k, v in vec.items()}}
+        full = {k: v for k, v in vec.items() if int(k[4:k.index("_")]) in FULL_VECTORS}
+        full.update({k: v for k, v in cvec.items() if int(k[5:k.index("_")]) in FULL_CVECTORS})
+        full.update(dvec)
+        np.savez_compressed(OUT, **full)
+        meta = {"_how": "python tests/golden/ref_translit.py --write  (transliterates the reference's Fortran subroutines under /root/reference "
+                        "-- B grid: stress, stepu, strain_rates, visc_replpress; C grid: strain_rates_U, strain_rates_Tdt, stressC_T, stressC_U, "
+                        "div_stress_Ex/Ny, stepu_C, stepv_C, grid_average_X2Y_1/X2YS/X2YA; ice_constants -- and runs them; see the module docstring)",
+                "cases": [dict(kw) for kw in CASES], "ccases": [dict(kw) for kw in CCASES],
+                "sha256": {k: sha(v) for k, v in {**vec, **cvec, **dvec}.items()}}
         json.dump(meta, open(SHA, "w"), indent=1)
         print("wrote", OUT, os.path.getsize(OUT), "bytes;", SHA)
     if "--show" in sys.argv:

@@ -155,3 +155,41 @@ def test_cgrid_fused_odd_loop_and_repeat(oracle_mod, evp_lib):
                 assert np.array_equal(got[n].view(np.int64), ref[n].view(np.int64)), n
     finally:
         evp_lib.dyn_evp_b200_finalize()
+
+
+# ---- C grid against vectors generated from the reference's own source text (tests/golden/ref_translit.py) ----
+def check_cgrid_against_ref_source_vectors(run):
+    import hashlib
+    import json
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import ref_translit as rt
+    meta = json.load(open(os.path.join(here, "ref_source_vectors.json")))
+    full = np.load(os.path.join(here, "ref_source_vectors.npz"))
+    assert meta["ccases"] == [dict(kw) for kw in rt.CCASES], "tests/golden/ref_source_vectors.json is stale: regenerate"
+    for n, kw in enumerate(rt.CCASES):
+        c = synth.make_ccase(**kw)
+        f = run(c)
+        for k in rt.CFIELDS:
+            key = f"ccase{n}_{k}"
+            if key in full.files:
+                assert np.array_equal(f[k].view(np.int64), full[key].view(np.int64)), \
+                    f"{key}: {np.count_nonzero(f[k] != full[key])} cells differ from the reference-source vector"
+            h = hashlib.sha256(np.ascontiguousarray(f[k], dtype=np.float64).tobytes()).hexdigest()
+            assert h == meta["sha256"][key], f"{key}: differs from the reference-source vector (sha256)"
+
+
+def test_cgrid_oracle_matches_vectors_from_reference_source(oracle_mod):
+    """the C-grid oracle against the output of the reference's own Fortran text, transliterated statement by statement and
+    executed (strain_rates_U, strain_rates_Tdt, stressC_T, stressC_U, div_stress_Ex/Ny, stepu_C, stepv_C,
+    grid_average_X2Y_1/X2YS/X2YA, visc_replpress): bit for bit, both visc_method settings, classic and revised EVP."""
+    check_cgrid_against_ref_source_vectors(lambda c: run_oracle_c(oracle_mod, c))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", ["1", "0"], ids=["three-kernel", "five-kernel"])
+def test_cgrid_gpu_matches_vectors_from_reference_source(evp_lib, monkeypatch, fused):
+    monkeypatch.setenv("EVP_B200_CGRID_FUSED", fused)
+    check_cgrid_against_ref_source_vectors(lambda c: run_gpu_c(evp_lib, c, mode=abi.MODE_EXACT))

@@ -1,9 +1,10 @@
 """CPU tests of the oracle (the checker must be trusted before it checks anything).
 
-The reference stores no golden vectors for this path, so the oracle is pinned by
-the properties the reference asserts: bit-for-bit results under any block decomposition
-(decomp_suite / perf_suite BFB columns), 2-D == 1-D formulation (core1d.F90:196), the halochk
-closed-form halo values, plus an independent numpy restatement of one subcycle.
+The reference stores no golden vectors for this path and cannot be compiled here.  The oracle is pinned
+(1) to vectors generated from the reference's own Fortran text by tests/golden/ref_translit.py (statement-by-statement
+transliteration, executed; bit for bit), and (2) by the properties the reference asserts: bit-for-bit results under any
+block decomposition (decomp_suite / perf_suite BFB columns) and with eliminated land blocks, 2-D == 1-D formulation
+(core1d.F90:196), the halochk closed-form halo values, plus an independent numpy restatement of one subcycle.
 """
 import hashlib
 import json
@@ -252,3 +253,16 @@ def test_reference_source_vectors_regenerate():
     assert len(vec) == 2 * len(rt.FIELDS)
     for k, v in vec.items():
         assert _sha(v) == meta["sha256"][k], k
+
+
+def test_deformations_oracle_matches_vectors_from_reference_source(oracle_mod):
+    """`deformations` (ice_dyn_shared.F90:1756-1860): the oracle against the transliterated reference text."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ref_translit as rt
+    meta, full = _ref_source_vectors()
+    c, d = rt.deform_inputs(synth)
+    got = oracle_mod.deformations(c.grid, c.fields["iceTmask"], c.fields["uvel"], c.fields["vvel"], d, c.params["e_factor"])
+    for k in rt.DFIELDS:
+        assert np.array_equal(got[k].view(np.int64), full[f"dcase0_{k}"].view(np.int64)), k
+        assert _sha(got[k]) == meta["sha256"][f"dcase0_{k}"], k
