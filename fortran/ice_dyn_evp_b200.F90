@@ -24,6 +24,7 @@ module ice_dyn_evp_b200
   implicit none
   private
   public :: dyn_evp_b200_init, dyn_evp_b200_run, dyn_evp_b200_finalize
+  public :: dyn_evp_b200_init_cgrid, dyn_evp_b200_run_cgrid   ! grid_ice = 'C' (ice_dyn_evp.F90:936-1101)
 
   integer(c_int32_t), parameter :: EVP_B200_ABI_VERSION = 2
   integer(c_int32_t), parameter :: BNDY_OPEN = 0, BNDY_CLOSED = 1, BNDY_CYCLIC = 2, BNDY_TRIPOLE = 3
@@ -52,7 +53,38 @@ module ice_dyn_evp_b200
      type(c_ptr) :: iceTmask, iceUmask
   end type evp_b200_fields_t
 
+  ! evp_b200_cgrid_t: extra static geometry of grid_ice = 'C'
+  type, bind(C) :: evp_b200_cgrid_t
+     type(c_ptr) :: dxN, dyE, dxE, dyN, dxU, dyU
+     type(c_ptr) :: tarea, uarea, earea, narea, earear, narear
+     type(c_ptr) :: ratiodxN, ratiodxNr, ratiodyE, ratiodyEr
+     type(c_ptr) :: hm, uvm, epm, npm
+  end type evp_b200_cgrid_t
+
+  ! evp_b200_cfields_t: what the C-grid subcycle loop reads and writes, in the order of include/evp_b200.h
+  type, bind(C) :: evp_b200_cfields_t
+     type(c_ptr) :: uvelE, vvelE, uvelN, vvelN, uvel, vvel
+     type(c_ptr) :: stresspT, stressmT, stress12T, stress12U
+     type(c_ptr) :: zetax2T, etax2T, etax2U, strengthU
+     type(c_ptr) :: divergU, tensionU, shearU, deltaU
+     type(c_ptr) :: strintxE, strintyN, taubxE, taubyN
+     type(c_ptr) :: strength
+     type(c_ptr) :: cdn_ocnE, cdn_ocnN, aiE, aiN, uocnE, vocnE, uocnN, vocnN
+     type(c_ptr) :: waterxE, wateryN, forcexE, forceyN, emassdti, nmassdti, fmE, fmN
+     type(c_ptr) :: TbE, TbN, rheofactE, rheofactN
+     type(c_ptr) :: iceTmask, iceUmask, iceEmask, iceNmask
+  end type evp_b200_cfields_t
+
   interface
+     integer(c_int) function evp_b200_init_cgrid(cgrid) bind(C, name='evp_b200_init_cgrid')
+       import :: c_int, evp_b200_cgrid_t
+       type(evp_b200_cgrid_t), intent(in) :: cgrid
+     end function
+     integer(c_int) function evp_b200_run_cgrid(params, fields) bind(C, name='evp_b200_run_cgrid')
+       import :: c_int, evp_b200_params_t, evp_b200_cfields_t
+       type(evp_b200_params_t), intent(in) :: params
+       type(evp_b200_cfields_t), intent(inout) :: fields
+     end function
      integer(c_int) function evp_b200_get_unique_id(id) bind(C, name='evp_b200_get_unique_id')
        import :: c_int, c_char
        character(kind=c_char) :: id(128)
@@ -101,6 +133,7 @@ module ice_dyn_evp_b200
   integer(c_int32_t), allocatable, target, save :: b_ilo(:), b_ihi(:), b_jlo(:), b_jhi(:)
   integer(c_int32_t), allocatable, target, save :: b_iglob(:,:), b_jglob(:,:)
   integer(c_int32_t), allocatable, target, save :: imaskT(:,:,:), imaskU(:,:,:)
+  integer(c_int32_t), allocatable, target, save :: imaskE(:,:,:), imaskN(:,:,:)   ! C grid
 
 contains
 
@@ -248,6 +281,75 @@ contains
        call check(evp_b200_run_bgrid(p, f), 'evp_b200_run_bgrid')
     endif
   end subroutine dyn_evp_b200_run
+
+  !---------------------------------------------------------------------
+  ! grid_ice = 'C': once, after dyn_evp_b200_init (the ratio arrays exist after init_evp, ice_dyn_evp.F90:218-240)
+  subroutine dyn_evp_b200_init_cgrid
+    use ice_grid,    only: dxN, dyE, dxE, dyN, dxU, dyU, tarea, uarea, earea, narea, earear, narear, hm, uvm, epm, npm
+    use ice_dyn_evp, only: ratiodxN, ratiodxNr, ratiodyE, ratiodyEr
+    type(evp_b200_cgrid_t) :: cg
+    cg%dxN = c_loc(dxN);  cg%dyE = c_loc(dyE);  cg%dxE = c_loc(dxE);  cg%dyN = c_loc(dyN);  cg%dxU = c_loc(dxU);  cg%dyU = c_loc(dyU)
+    cg%tarea = c_loc(tarea);  cg%uarea = c_loc(uarea);  cg%earea = c_loc(earea);  cg%narea = c_loc(narea)
+    cg%earear = c_loc(earear);  cg%narear = c_loc(narear)
+    cg%ratiodxN = c_loc(ratiodxN);  cg%ratiodxNr = c_loc(ratiodxNr);  cg%ratiodyE = c_loc(ratiodyE);  cg%ratiodyEr = c_loc(ratiodyEr)
+    cg%hm = c_loc(hm);  cg%uvm = c_loc(uvm);  cg%epm = c_loc(epm);  cg%npm = c_loc(npm)
+    allocate(imaskE(nx_block, ny_block, max_blocks), imaskN(nx_block, ny_block, max_blocks))
+    call check(evp_b200_init_cgrid(cg), 'evp_b200_init_cgrid')
+  end subroutine dyn_evp_b200_init_cgrid
+
+  !---------------------------------------------------------------------
+  ! grid_ice = 'C': one dynamics step, replaces the `do ksub = 1,ndte` loop of ice_dyn_evp.F90:938-1097 (one more
+  ! elseif in front of it).  The arguments are the module / local arrays that loop reads and writes.
+  subroutine dyn_evp_b200_run_cgrid(uvelE, vvelE, uvelN, vvelN, uvel, vvel,                          &
+                                    stresspT, stressmT, stress12T, stress12U,                        &
+                                    zetax2T, etax2T, etax2U, strengthU,                              &
+                                    divergU, tensionU, shearU, deltaU,                               &
+                                    strintxE, strintyN, taubxE, taubyN,                              &
+                                    strength,                                                        &
+                                    cdn_ocnE, cdn_ocnN, aiE, aiN, uocnE, vocnE, uocnN, vocnN,        &
+                                    waterxE, wateryN, forcexE, forceyN, emassdti, nmassdti, fmE, fmN,&
+                                    TbE, TbN, rheofactE, rheofactN,                                  &
+                                    iceTmask, iceUmask, iceEmask, iceNmask)
+    use ice_dyn_shared, only: ndte, arlx1i, denom1, revp, brlx, e_factor, epp2i, capping, Ktens, u0, cosw, sinw, deltaminEVP, &
+                              visc_method
+    use icepack_intfc,  only: icepack_query_parameters
+    real(kind=dbl_kind), dimension(:,:,:), intent(inout), target, contiguous :: &
+         uvelE, vvelE, uvelN, vvelN, uvel, vvel, stresspT, stressmT, stress12T, stress12U, &
+         zetax2T, etax2T, etax2U, strengthU, divergU, tensionU, shearU, deltaU, strintxE, strintyN, taubxE, taubyN
+    real(kind=dbl_kind), dimension(:,:,:), intent(in), target, contiguous :: &
+         strength, cdn_ocnE, cdn_ocnN, aiE, aiN, uocnE, vocnE, uocnN, vocnN, waterxE, wateryN, forcexE, forceyN, &
+         emassdti, nmassdti, fmE, fmN, TbE, TbN, rheofactE, rheofactN
+    logical(kind=log_kind), dimension(:,:,:), intent(in) :: iceTmask, iceUmask, iceEmask, iceNmask
+    type(evp_b200_params_t) :: p
+    type(evp_b200_cfields_t) :: f
+    real(kind=dbl_kind) :: rhow
+
+    call icepack_query_parameters(rhow_out=rhow)
+    p%ndte = ndte;  p%mode = 0;  p%kernel = 0
+    p%visc_method = merge(1_c_int32_t, 0_c_int32_t, trim(visc_method) == 'avg_strength')
+    p%arlx1i = arlx1i;  p%denom1 = denom1;  p%revp = revp;  p%brlx = brlx
+    p%e_factor = e_factor;  p%epp2i = epp2i;  p%capping = capping;  p%Ktens = Ktens
+    p%u0 = u0;  p%cosw = cosw;  p%sinw = sinw;  p%rhow = rhow;  p%deltaminEVP = deltaminEVP
+
+    imaskT = merge(1_c_int32_t, 0_c_int32_t, iceTmask);  imaskU = merge(1_c_int32_t, 0_c_int32_t, iceUmask)
+    imaskE = merge(1_c_int32_t, 0_c_int32_t, iceEmask);  imaskN = merge(1_c_int32_t, 0_c_int32_t, iceNmask)
+
+    f%uvelE = c_loc(uvelE);  f%vvelE = c_loc(vvelE);  f%uvelN = c_loc(uvelN);  f%vvelN = c_loc(vvelN)
+    f%uvel = c_loc(uvel);    f%vvel = c_loc(vvel)
+    f%stresspT = c_loc(stresspT);  f%stressmT = c_loc(stressmT);  f%stress12T = c_loc(stress12T);  f%stress12U = c_loc(stress12U)
+    f%zetax2T = c_loc(zetax2T);  f%etax2T = c_loc(etax2T);  f%etax2U = c_loc(etax2U);  f%strengthU = c_loc(strengthU)
+    f%divergU = c_loc(divergU);  f%tensionU = c_loc(tensionU);  f%shearU = c_loc(shearU);  f%deltaU = c_loc(deltaU)
+    f%strintxE = c_loc(strintxE);  f%strintyN = c_loc(strintyN);  f%taubxE = c_loc(taubxE);  f%taubyN = c_loc(taubyN)
+    f%strength = c_loc(strength)
+    f%cdn_ocnE = c_loc(cdn_ocnE);  f%cdn_ocnN = c_loc(cdn_ocnN);  f%aiE = c_loc(aiE);  f%aiN = c_loc(aiN)
+    f%uocnE = c_loc(uocnE);  f%vocnE = c_loc(vocnE);  f%uocnN = c_loc(uocnN);  f%vocnN = c_loc(vocnN)
+    f%waterxE = c_loc(waterxE);  f%wateryN = c_loc(wateryN);  f%forcexE = c_loc(forcexE);  f%forceyN = c_loc(forceyN)
+    f%emassdti = c_loc(emassdti);  f%nmassdti = c_loc(nmassdti);  f%fmE = c_loc(fmE);  f%fmN = c_loc(fmN)
+    f%TbE = c_loc(TbE);  f%TbN = c_loc(TbN);  f%rheofactE = c_loc(rheofactE);  f%rheofactN = c_loc(rheofactN)
+    f%iceTmask = c_loc(imaskT);  f%iceUmask = c_loc(imaskU);  f%iceEmask = c_loc(imaskE);  f%iceNmask = c_loc(imaskN)
+
+    call check(evp_b200_run_cgrid(p, f), 'evp_b200_run_cgrid')
+  end subroutine dyn_evp_b200_run_cgrid
 
   !---------------------------------------------------------------------
   subroutine dyn_evp_b200_finalize
