@@ -81,6 +81,36 @@ class CFields(C.Structure):
 
 
 DEFORM_IN = ("dxU", "dyU", "tarear")
+# grid_ice = 'CD' (ice_dyn_evp.F90:1123-1293): both velocity components at E and at N, the full stress tensor at T and at U
+CDFIELDS_INOUT = ("uvelE", "vvelE", "uvelN", "vvelN", "uvel", "vvel", "stresspT", "stressmT", "stress12T", "stresspU", "stressmU",
+                  "stress12U")
+CDFIELDS_OUT = ("zetax2T", "etax2T", "zetax2U", "etax2U", "strengthU", "divergU", "tensionU", "shearU", "deltaU",
+                "strintxE", "strintyE", "strintxN", "strintyN", "taubxE", "taubyE", "taubxN", "taubyN")
+CDFIELDS_IN = ("strength", "cdn_ocnE", "cdn_ocnN", "aiE", "aiN", "uocnE", "vocnE", "uocnN", "vocnN", "waterxE", "wateryE", "waterxN",
+               "wateryN", "forcexE", "forceyE", "forcexN", "forceyN", "emassdti", "nmassdti", "fmE", "fmN", "TbE", "TbN", "rheofactE",
+               "rheofactN")
+CDFIELDS_ORDER = CDFIELDS_INOUT + CDFIELDS_OUT + CDFIELDS_IN
+
+
+class CDFields(C.Structure):
+    _fields_ = [(n, _pd) for n in CDFIELDS_ORDER] + [(n, _pi) for n in CFIELDS_MASK]
+
+
+def make_cdfields(f, npl_total):
+    s, keep = CDFields(), {}
+    for n in CDFIELDS_ORDER:
+        a = f[n]
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == npl_total, n
+        keep[n] = a
+        setattr(s, n, _ptr(a, C.c_double))
+    for n in CFIELDS_MASK:
+        a = f[n]
+        assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"] and a.size == npl_total, n
+        keep[n] = a
+        setattr(s, n, _ptr(a, C.c_int32))
+    return s, keep
+
+
 DEFORM_OUT = ("divu", "shear", "vort", "rdg_conv", "rdg_shear")
 
 

@@ -530,6 +530,35 @@ def make_ccase(config="gx3", block_size=None, seed=None, ndte=None, mode=abi.MOD
     return CCase(blocks, grid, cgrid, params, fields, X)
 
 
+def make_cdcase(config="gx3", block_size=None, seed=None, ndte=None, mode=abi.MODE_EXACT, revised_evp=False,
+                visc_method=abi.VISC_AVG_ZETA, kmt=None, ew=None, ns=None, **kw):
+    """grid_ice='CD' counterpart of make_ccase (ice_dyn_evp.F90:1123-1293): same geometry and E/N-point coefficients (dyn_prep2
+    at E and N yields both components of water*, force*), all four of uvelE, vvelE, uvelN, vvelN prognostic, the stress
+    tensor carried at T and at U."""
+    cc = make_ccase(config, block_size=block_size, seed=seed, ndte=ndte, mode=mode, revised_evp=revised_evp, visc_method=visc_method,
+                    kmt=kmt, ew=ew, ns=ns, **kw)
+    X, blocks = cc.X, cc.blocks
+    mb = blocks.nblocks_tot
+    nyg, nxg = X["aice"].shape[0] - 2, X["aice"].shape[1] - 2
+    ew_i, ns_i = cc.grid["ew_boundary_type"], cc.grid["ns_boundary_type"]
+    rng = np.random.Generator(np.random.PCG64(seed + 1000)) if seed is not None else None
+    for n in ("stresspU", "stressmU"):
+        X[n] = (np.zeros((nyg + 2, nxg + 2)) if rng is None else
+                np.where(X["iceUmaskC"], extend(rng.normal(0.0, 1.0, (nyg, nxg)), ew_i, ns_i, LOC_NE) * 0.01 * X["strength"].max(), 0.0))
+    src = {"uvel": "uvelC", "vvel": "vvelC"}
+    fields = {}
+    for n in abi.CDFIELDS_ORDER:
+        if n in abi.CDFIELDS_OUT:
+            fields[n] = np.zeros((mb, blocks.ny_block, blocks.nx_block))
+        elif n in cc.fields:
+            fields[n] = cc.fields[n].copy()
+        else:
+            fields[n] = scatter(X[src.get(n, n)], blocks, mb)
+    for n in abi.CFIELDS_MASK:
+        fields[n] = cc.fields[n].copy()
+    return CCase(blocks, cc.grid, cc.cgrid, cc.params, fields, X)
+
+
 U_PREP = ("umassdti", "fmU", "waterxU", "wateryU", "forcexU", "forceyU", "TbU")  # interior-only after dyn_prep2
 
 

@@ -211,6 +211,29 @@ int evp_b200_run_bgrid(const evp_b200_params_t *params, evp_b200_fields_t *field
 int evp_b200_init_cgrid(const evp_b200_cgrid_t *cgrid);
 int evp_b200_run_cgrid(const evp_b200_params_t *params, evp_b200_cfields_t *fields);
 
+/* ---- CD grid (grid_ice = 'CD', ice_dyn_evp.F90:1123-1293) --------------------------------------------
+ * Both velocity components are prognostic at E and at N (stepuv_CD, ice_dyn_shared.F90:973-1085), the full stress tensor is
+ * carried at T (stressCD_T, ice_dyn_evp.F90:1978-2080) and at U (stressCD_U, :2088-2178), the stress divergence has four parts
+ * (div_stress_Ex/Ey/Nx/Ny, :2195-2416).  Same static geometry as the C grid (evp_b200_init_cgrid), one GPU, non-tripole.
+ * All arrays (nx_block,ny_block,max_blocks). */
+typedef struct {
+  /* inout */
+  double *uvelE, *vvelE, *uvelN, *vvelN, *uvel, *vvel;
+  double *stresspT, *stressmT, *stress12T, *stresspU, *stressmU, *stress12U;
+  /* out: work arrays the reference leaves behind after the last subcycle */
+  double *zetax2T, *etax2T, *zetax2U, *etax2U, *strengthU;
+  double *divergU, *tensionU, *shearU, *deltaU;
+  double *strintxE, *strintyE, *strintxN, *strintyN, *taubxE, *taubyE, *taubxN, *taubyN;
+  /* in */
+  const double *strength;
+  const double *cdn_ocnE, *cdn_ocnN, *aiE, *aiN, *uocnE, *vocnE, *uocnN, *vocnN;
+  const double *waterxE, *wateryE, *waterxN, *wateryN, *forcexE, *forceyE, *forcexN, *forceyN;
+  const double *emassdti, *nmassdti, *fmE, *fmN, *TbE, *TbN, *rheofactE, *rheofactN;
+  /* in: 0/1 */
+  const int32_t *iceTmask, *iceUmask, *iceEmask, *iceNmask;
+} evp_b200_cdfields_t;
+int evp_b200_run_cdgrid(const evp_b200_params_t *params, evp_b200_cdfields_t *fields);
+
 /* ---- next row: deformations ------------------------------------------------
  * `deformations` (ice_dyn_shared.F90:1756-1860), the step right after the subcycle loop in evp()
  * (ice_dyn_evp.F90:920-934): divu, shear, vort, rdg_conv, rdg_shear at the ice T cells from the final

@@ -48,6 +48,9 @@ int orc_evp_run_bgrid_1d(const evp_b200_grid_t *grid, const double *HTE, const d
 /* C grid (grid_ice='C'): ice_dyn_evp.F90:936-1101 and callees, see evp_oracle_cgrid.c.  Non-tripole only. */
 int orc_evp_run_cgrid(const evp_b200_grid_t *grid, const evp_b200_cgrid_t *cgrid, const evp_b200_params_t *params,
                       evp_b200_cfields_t *fields, int nthreads);
+/* grid_ice = 'CD': evp.F90:1123-1275 */
+int orc_evp_run_cdgrid(const evp_b200_grid_t *grid, const evp_b200_cgrid_t *cgrid, const evp_b200_params_t *params,
+                        evp_b200_cdfields_t *fields, int nthreads);
 
 /* deformations: ice_dyn_shared.F90:1756-1860 over the T list (ilo:ihi+1, jlo:jhi+1 where iceTmask) */
 int orc_deformations(const evp_b200_grid_t *grid, const int32_t *iceTmask, const double *uvel, const double *vvel,

@@ -342,3 +342,197 @@ done:
   free(uvelE_init); free(vvelN_init);
   return rc;
 }
+
+/* =============================================================================================
+ * grid_ice = 'CD': evp.F90:1123-1275 and the routines it calls
+ *   strain_rates_Tdtsd  shared.F90:2171-2243     stressCD_T   evp.F90:1978-2080     stressCD_U  evp.F90:2088-2178
+ *   div_stress_Ey       evp.F90:2252-2304        div_stress_Nx evp.F90:2308-2360    stepuv_CD   shared.F90:973-1085
+ * (strain_rates_U, div_stress_Ex/Ny, the T->U and E/N->U averages are shared with the C grid above).
+ * Pinned bit for bit to the transliterated reference source (tests/golden/ref_translit.py, cdcase*).
+ * ============================================================================================= */
+static void stressCD_T(int nx_block, int ny_block, int icellT, const int *indxTi, const int *indxTj, const double *uvelE,
+                       const double *vvelE, const double *uvelN, const double *vvelN, const double *dxN, const double *dyE,
+                       const double *dxT, const double *dyT, const double *DminTarea, const double *strength, double *zetax2T,
+                       double *etax2T, double *stresspT, double *stressmT, double *stress12T, const evp_b200_params_t *p) {
+  (void)ny_block;
+  const double arlx1i = p->arlx1i, revp = p->revp, denom1 = p->denom1;
+  for (int ij = 0; ij < icellT; ++ij) {
+    const int i = indxTi[ij], j = indxTj[ij];
+    const size_t c = IX(i, j), w = IX(i - 1, j), s = IX(i, j - 1);
+    /* strain_rates_Tdt: shared.F90:2299-2307 */
+    double divT = dyE[c] * uvelE[c] - dyE[w] * uvelE[w] + dxN[c] * vvelN[c] - dxN[s] * vvelN[s];
+    double tensionT = (dyT[c] * dyT[c]) * (uvelE[c] / dyE[c] - uvelE[w] / dyE[w]) -
+                      (dxT[c] * dxT[c]) * (vvelN[c] / dxN[c] - vvelN[s] / dxN[s]);
+    /* strain_rates_Tdtsd: shared.F90:2232-2239 */
+    double shearT = (dxT[c] * dxT[c]) * (uvelN[c] / dxN[c] - uvelN[s] / dxN[s]) +
+                    (dyT[c] * dyT[c]) * (vvelE[c] / dyE[c] - vvelE[w] / dyE[w]);
+    double DeltaT = sqrt(divT * divT + p->e_factor * (tensionT * tensionT + shearT * shearT));
+    double rep_prsT;
+    visc_replpress_c(strength[c], DminTarea[c], DeltaT, p, &zetax2T[c], &etax2T[c], &rep_prsT);
+    stresspT[c] = (stresspT[c] * (c1 - arlx1i * revp) + arlx1i * (zetax2T[c] * divT - rep_prsT)) * denom1;
+    stressmT[c] = (stressmT[c] * (c1 - arlx1i * revp) + arlx1i * etax2T[c] * tensionT) * denom1;
+    stress12T[c] = (stress12T[c] * (c1 - arlx1i * revp) + arlx1i * p5 * etax2T[c] * shearT) * denom1;
+  }
+}
+
+static void stressCD_U(int nx_block, int icellU, const int *indxUi, const int *indxUj, const double *uarea, const double *zetax2U,
+                       const double *etax2U, const double *strengthU, const double *divergU, const double *tensionU,
+                       const double *shearU, const double *deltaU, double *stresspU, double *stressmU, double *stress12U,
+                       const evp_b200_params_t *p) {
+  const double arlx1i = p->arlx1i, revp = p->revp, denom1 = p->denom1;
+  for (int ij = 0; ij < icellU; ++ij) {
+    const size_t c = IX(indxUi[ij], indxUj[ij]);
+    double lzetax2U, letax2U, lrep_prsU;
+    if (p->visc_method == EVP_B200_VISC_AVG_ZETA) {
+      lzetax2U = zetax2U[c];
+      letax2U = etax2U[c];
+      lrep_prsU = (c1 - p->Ktens) / (c1 + p->Ktens) * lzetax2U * deltaU[c];
+    } else {
+      double DminUarea = p->deltaminEVP * uarea[c];
+      visc_replpress_c(strengthU[c], DminUarea, deltaU[c], p, &lzetax2U, &letax2U, &lrep_prsU);
+    }
+    stresspU[c] = (stresspU[c] * (c1 - arlx1i * revp) + arlx1i * (lzetax2U * divergU[c] - lrep_prsU)) * denom1;
+    stressmU[c] = (stressmU[c] * (c1 - arlx1i * revp) + arlx1i * letax2U * tensionU[c]) * denom1;
+    stress12U[c] = (stress12U[c] * (c1 - arlx1i * revp) + arlx1i * p5 * letax2U * shearU[c]) * denom1;
+  }
+}
+
+static void div_stress_Ey(int nx_block, int icell, const int *indxi, const int *indxj, const double *dxE, const double *dyE,
+                          const double *dxU, const double *dyT, const double *arear, const double *rheofactE,
+                          const double *stressp, const double *stressm, const double *stress12, double *strinty) {
+  for (int ij = 0; ij < icell; ++ij) {
+    const int i = indxi[ij], j = indxj[ij];
+    const size_t c = IX(i, j), e = IX(i + 1, j), s = IX(i, j - 1);
+    strinty[c] = rheofactE[c] * arear[c] *
+                 (p5 * dxE[c] * (stressp[c] - stressp[s]) -
+                  (p5 / dxE[c]) * ((dxU[c] * dxU[c]) * stressm[c] - (dxU[s] * dxU[s]) * stressm[s]) +
+                  (c1 / dyE[c]) * ((dyT[e] * dyT[e]) * stress12[e] - (dyT[c] * dyT[c]) * stress12[c]));
+  }
+}
+static void div_stress_Nx(int nx_block, int icell, const int *indxi, const int *indxj, const double *dxN, const double *dyN,
+                          const double *dxT, const double *dyU, const double *arear, const double *rheofactN,
+                          const double *stressp, const double *stressm, const double *stress12, double *strintx) {
+  for (int ij = 0; ij < icell; ++ij) {
+    const int i = indxi[ij], j = indxj[ij];
+    const size_t c = IX(i, j), n = IX(i, j + 1), w = IX(i - 1, j);
+    strintx[c] = rheofactN[c] * arear[c] *
+                 (p5 * dyN[c] * (stressp[c] - stressp[w]) +
+                  (p5 / dyN[c]) * ((dyU[c] * dyU[c]) * stressm[c] - (dyU[w] * dyU[w]) * stressm[w]) +
+                  (c1 / dxN[c]) * ((dxT[n] * dxT[n]) * stress12[n] - (dxT[c] * dxT[c]) * stress12[c]));
+  }
+}
+
+static void stepuv_CD(int nx_block, int icell, const int *indxi, const int *indxj, const double *Cw, const double *aiX,
+                      const double *uocn, const double *vocn, const double *waterx, const double *watery, const double *forcex,
+                      const double *forcey, const double *massdti, const double *fm, const double *strintx, const double *strinty,
+                      double *taubx, double *tauby, const double *uvel_init, const double *vvel_init, double *uvel, double *vvel,
+                      const double *Tb, const evp_b200_params_t *p) {
+  const double rhow = p->rhow, brlx = p->brlx, revp = p->revp, u0 = p->u0, cosw = p->cosw, sinw = p->sinw;
+  for (int ij = 0; ij < icell; ++ij) {
+    const size_t c = IX(indxi[ij], indxj[ij]);
+    double uold = uvel[c], vold = vvel[c];
+    double vrel = aiX[c] * rhow * Cw[c] * sqrt((uocn[c] - uold) * (uocn[c] - uold) + (vocn[c] - vold) * (vocn[c] - vold));
+    double taux = vrel * waterx[c];
+    double tauy = vrel * watery[c];
+    double ccc = sqrt(uold * uold + vold * vold) + u0;
+    double Cb = Tb[c] / ccc;
+    double cca = (brlx + revp) * massdti[c] + vrel * cosw + Cb;
+    double ccb = fm[c] + copysign(c1, fm[c]) * vrel * sinw;
+    double ab2 = cca * cca + ccb * ccb;
+    double cc1 = strintx[c] + forcex[c] + taux + massdti[c] * (brlx * uold + revp * uvel_init[c]);
+    double cc2 = strinty[c] + forcey[c] + tauy + massdti[c] * (brlx * vold + revp * vvel_init[c]);
+    uvel[c] = (cca * cc1 + ccb * cc2) / ab2;
+    vvel[c] = (cca * cc2 - ccb * cc1) / ab2;
+    taubx[c] = -uvel[c] * Cb;
+    tauby[c] = -vvel[c] * Cb;
+  }
+}
+
+int orc_evp_run_cdgrid(const evp_b200_grid_t *g, const evp_b200_cgrid_t *cg, const evp_b200_params_t *p,
+                       evp_b200_cdfields_t *f, int nthreads) {
+  if (!g || !cg || !p || !f) return 1;
+  if (g->ns_boundary_type == EVP_B200_BNDY_TRIPOLE) return 1;
+  const int nx_block = g->nx_block, ny_block = g->ny_block, nb = g->nblocks;
+  const size_t npl = (size_t)nx_block * ny_block;
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+  nthreads = 1;
+#endif
+  int *nT = calloc(nb, sizeof(int)), *nU = calloc(nb, sizeof(int)), *nE = calloc(nb, sizeof(int)), *nN = calloc(nb, sizeof(int));
+  int *Ti = malloc(sizeof(int) * npl * nb), *Tj = malloc(sizeof(int) * npl * nb), *Ui = malloc(sizeof(int) * npl * nb),
+      *Uj = malloc(sizeof(int) * npl * nb), *Ei = malloc(sizeof(int) * npl * nb), *Ej = malloc(sizeof(int) * npl * nb),
+      *Ni = malloc(sizeof(int) * npl * nb), *Nj = malloc(sizeof(int) * npl * nb);
+  double *init[4];
+  double *cur[4] = {f->uvelE, f->vvelE, f->uvelN, f->vvelN};
+  for (int q = 0; q < 4; ++q) init[q] = malloc(sizeof(double) * npl * nb);
+  if (!nT || !nU || !nE || !nN || !Ti || !Tj || !Ui || !Uj || !Ei || !Ej || !Ni || !Nj || !init[0] || !init[1] || !init[2] || !init[3]) return 1;
+  for (int b = 0; b < nb; ++b) {
+    const size_t o = (size_t)b * npl;
+    nT[b] = build_list(g, b, f->iceTmask + o, 1, Ti + o, Tj + o);
+    nU[b] = build_list(g, b, f->iceUmask + o, 0, Ui + o, Uj + o);
+    nE[b] = build_list(g, b, f->iceEmask + o, 0, Ei + o, Ej + o);
+    nN[b] = build_list(g, b, f->iceNmask + o, 0, Ni + o, Nj + o);
+  }
+  for (int q = 0; q < 4; ++q) memcpy(init[q], cur[q], sizeof(double) * npl * nb);
+  int rc = 0;
+  for (int ksub = 1; ksub <= p->ndte; ++ksub) { /* evp.F90:1125 */
+    PARFOR for (int b = 0; b < nb; ++b) {
+      const size_t o = (size_t)b * npl;
+      stressCD_T(nx_block, ny_block, nT[b], Ti + o, Tj + o, f->uvelE + o, f->vvelE + o, f->uvelN + o, f->vvelN + o, cg->dxN + o,
+                 cg->dyE + o, g->dxT + o, g->dyT + o, g->DminTarea + o, f->strength + o, f->zetax2T + o, f->etax2T + o,
+                 f->stresspT + o, f->stressmT + o, f->stress12T + o, p);
+    }
+    HALO(2, 0, 0, f->zetax2T, f->etax2T); /* evp.F90:1143-1145 */
+    PARFOR for (int b = 0; b < nb; ++b) {
+      const size_t o = (size_t)b * npl;
+      if (p->visc_method == EVP_B200_VISC_AVG_STRENGTH) {
+        avg_S_NE(nx_block, ny_block, g->ilo[b], g->ihi[b], g->jlo[b], g->jhi[b], f->strength + o, cg->tarea + o, cg->hm + o, f->strengthU + o);
+      } else {
+        avg_S_NE(nx_block, ny_block, g->ilo[b], g->ihi[b], g->jlo[b], g->jhi[b], f->zetax2T + o, cg->tarea + o, cg->hm + o, f->zetax2U + o);
+        avg_S_NE(nx_block, ny_block, g->ilo[b], g->ihi[b], g->jlo[b], g->jhi[b], f->etax2T + o, cg->tarea + o, cg->hm + o, f->etax2U + o);
+      }
+      strain_rates_U(nx_block, ny_block, nU[b], Ui + o, Uj + o, f->uvelE + o, f->vvelE + o, f->uvelN + o, f->vvelN + o,
+                     f->uvel + o, f->vvel + o, cg->dxE + o, cg->dyN + o, cg->dxU + o, cg->dyU + o, cg->ratiodxN + o,
+                     cg->ratiodxNr + o, cg->ratiodyE + o, cg->ratiodyEr + o, cg->epm + o, cg->npm + o, f->divergU + o,
+                     f->tensionU + o, f->shearU + o, f->deltaU + o, p->e_factor);
+      stressCD_U(nx_block, nU[b], Ui + o, Uj + o, cg->uarea + o, f->zetax2U + o, f->etax2U + o, f->strengthU + o, f->divergU + o,
+                 f->tensionU + o, f->shearU + o, f->deltaU + o, f->stresspU + o, f->stressmU + o, f->stress12U + o, p);
+    }
+    HALO(3, 0, 0, f->stresspT, f->stressmT, f->stress12T); /* evp.F90:1181-1186 */
+    HALO(3, 1, 0, f->stresspU, f->stressmU, f->stress12U);
+    PARFOR for (int b = 0; b < nb; ++b) {
+      const size_t o = (size_t)b * npl;
+      div_stress_Ex(nx_block, nE[b], Ei + o, Ej + o, cg->dxE + o, cg->dyE + o, cg->dxU + o, g->dyT + o, cg->earear + o,
+                    f->rheofactE + o, f->stresspT + o, f->stressmT + o, f->stress12U + o, f->strintxE + o);
+      div_stress_Ey(nx_block, nE[b], Ei + o, Ej + o, cg->dxE + o, cg->dyE + o, cg->dxU + o, g->dyT + o, cg->earear + o,
+                    f->rheofactE + o, f->stresspU + o, f->stressmU + o, f->stress12T + o, f->strintyE + o);
+      div_stress_Nx(nx_block, nN[b], Ni + o, Nj + o, cg->dxN + o, cg->dyN + o, g->dxT + o, cg->dyU + o, cg->narear + o,
+                    f->rheofactN + o, f->stresspU + o, f->stressmU + o, f->stress12T + o, f->strintxN + o);
+      div_stress_Ny(nx_block, nN[b], Ni + o, Nj + o, cg->dxN + o, cg->dyN + o, g->dxT + o, cg->dyU + o, cg->narear + o,
+                    f->rheofactN + o, f->stresspT + o, f->stressmT + o, f->stress12U + o, f->strintyN + o);
+      stepuv_CD(nx_block, nE[b], Ei + o, Ej + o, f->cdn_ocnE + o, f->aiE + o, f->uocnE + o, f->vocnE + o, f->waterxE + o,
+                f->wateryE + o, f->forcexE + o, f->forceyE + o, f->emassdti + o, f->fmE + o, f->strintxE + o, f->strintyE + o,
+                f->taubxE + o, f->taubyE + o, init[0] + o, init[1] + o, f->uvelE + o, f->vvelE + o, f->TbE + o, p);
+      stepuv_CD(nx_block, nN[b], Ni + o, Nj + o, f->cdn_ocnN + o, f->aiN + o, f->uocnN + o, f->vocnN + o, f->waterxN + o,
+                f->wateryN + o, f->forcexN + o, f->forceyN + o, f->nmassdti + o, f->fmN + o, f->strintxN + o, f->strintyN + o,
+                f->taubxN + o, f->taubyN + o, init[2] + o, init[3] + o, f->uvelN + o, f->vvelN + o, f->TbN + o, p);
+    }
+    HALO(2, 1, 1, f->uvelE, f->vvelE); /* evp.F90:1247-1252 */
+    HALO(2, 1, 1, f->uvelN, f->vvelN);
+    PARFOR for (int b = 0; b < nb; ++b) {
+      const size_t o = (size_t)b * npl;
+      avg_A(2, nx_block, ny_block, g->ilo[b], g->ihi[b], g->jlo[b], g->jhi[b], f->uvelE + o, cg->earea + o, f->uvel + o); /* E2UA 'N' */
+      avg_A(3, nx_block, ny_block, g->ilo[b], g->ihi[b], g->jlo[b], g->jhi[b], f->vvelN + o, cg->narea + o, f->vvel + o); /* N2UA 'E' */
+      for (size_t k = 0; k < npl; ++k) {
+        f->uvel[o + k] = f->uvel[o + k] * cg->uvm[o + k];
+        f->vvel[o + k] = f->vvel[o + k] * cg->uvm[o + k];
+      }
+    }
+    HALO(2, 1, 1, f->uvel, f->vvel); /* evp.F90:1262-1264 */
+  }
+done:
+  free(nT); free(nU); free(nE); free(nN); free(Ti); free(Tj); free(Ui); free(Uj); free(Ei); free(Ej); free(Ni); free(Nj);
+  for (int q = 0; q < 4; ++q) free(init[q]);
+  return rc;
+}

@@ -52,6 +52,7 @@ def lib(variant="exact"):
                                            C.c_double, C.POINTER(abi.Params), C.POINTER(abi.Fields), C.c_int]
         L.orc_evp_run_bgrid_1d.restype = C.c_int
         L.orc_evp_run_cgrid.argtypes = [C.POINTER(abi.Grid), C.POINTER(abi.CGrid), C.POINTER(abi.Params), C.POINTER(abi.CFields), C.c_int]
+        L.orc_evp_run_cdgrid.argtypes = [C.POINTER(abi.Grid), C.POINTER(abi.CGrid), C.POINTER(abi.Params), C.POINTER(abi.CDFields), C.c_int]
         L.orc_evp_run_cgrid.restype = C.c_int
         L.orc_deformations.argtypes = [C.POINTER(abi.Grid), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(abi.Deform)]
         L.orc_deformations.restype = C.c_int
@@ -109,6 +110,19 @@ def evp_run_cgrid(grid, cgrid, params, cfields, nthreads=0, variant="exact"):
     if rc:
         raise RuntimeError("oracle cgrid failed")
     return cfields
+
+
+def evp_run_cdgrid(grid, cgrid, params, cdfields, nthreads=0, variant="exact"):
+    """grid_ice = 'CD' (ice_dyn_evp.F90:1123-1275), in place."""
+    L = lib(variant)
+    g, kg = abi.make_grid(grid)
+    cg, kc = abi.make_cgrid(cgrid, _npl(grid))
+    p = abi.make_params(params)
+    f, kf = abi.make_cdfields(cdfields, _npl(grid))
+    rc = L.orc_evp_run_cdgrid(C.byref(g), C.byref(cg), C.byref(p), C.byref(f), nthreads)
+    if rc:
+        raise RuntimeError("oracle cd grid failed")
+    return cdfields
 
 
 def deformations(grid, iceTmask, uvel, vvel, d, e_factor, variant="exact"):

@@ -10,6 +10,8 @@ for the EVP path.  Its hot-path subroutines, however, are straight-line fp64 ari
   C grid   strain_rates_U, strain_rates_Tdt, stepu_C, stepv_C   ice_dyn_shared.F90          (a12)
            stressC_T, stressC_U, div_stress_Ex, div_stress_Ny   ice_dyn_evp.F90
            grid_average_X2Y_1 / X2YS / X2YA                     cicecore/cicedyn/infrastructure/ice_grid.F90
+  CD grid  stressCD_T, stressCD_U, div_stress_Ey, div_stress_Nx  ice_dyn_evp.F90           (a13)
+           strain_rates_Tdtsd, stepuv_CD                         ice_dyn_shared.F90
   next     deformations      .../ice_dyn_shared.F90                         (8f rank 2)
   constants                  cicecore/shared/ice_constants.F90              (p111 = c1/c9 ...)
 
@@ -662,6 +664,118 @@ def run_reference_cloop(case, ndte, halo_update):
     return f
 
 
+def run_reference_cdloop(case, ndte, halo_update):
+    """grid_ice = 'CD': the subcycle loop of ice_dyn_evp.F90:1123-1275 on ONE block (same conventions as run_reference_cloop)."""
+    g, cg, p = case.grid, case.cgrid, dict(case.params)
+    assert g["nblocks"] == 1
+    nxb, nyb = g["nx_block"], g["ny_block"]
+    ilo, ihi, jlo, jhi = (int(g[k][0]) for k in ("ilo", "ihi", "jlo", "jhi"))
+    reg = {}
+    names = ((F_SHARED, "visc_replpress"), (F_SHARED, "strain_rates_Tdt"), (F_SHARED, "strain_rates_Tdtsd"), (F_SHARED, "strain_rates_U"),
+             (F_EVP, "stressCD_T"), (F_EVP, "stressCD_U"), (F_EVP, "div_stress_Ex"), (F_EVP, "div_stress_Ey"), (F_EVP, "div_stress_Nx"),
+             (F_EVP, "div_stress_Ny"), (F_SHARED, "stepuv_CD"), (F_GRID, "grid_average_X2YS"), (F_GRID, "grid_average_X2YA"),
+             (F_GRID, "grid_average_X2Y_1"))
+    for path, name in names:
+        reg[name] = Sub(path, name, reg)
+    reg["strain_rates_T"] = [reg["strain_rates_Tdt"], reg["strain_rates_Tdtsd"]]
+    blk = _Block()
+    blk.ilo, blk.ihi, blk.jlo, blk.jhi = ilo, ihi, jlo, jhi
+    env = {"math": math, "_sq": lambda x: x * x, "_sign": lambda a, b: math.copysign(abs(a), b), "_trim": lambda s: s.strip(),
+           "_alloc": lambda nx, ny: FArr(np.zeros((ny, nx))), "ICEPACK": {"rhow": p["rhow"]}, "nblocks": 1, "get_block": lambda iblk: blk}
+    env.update(reference_constants())
+    for k in ("arlx1i", "denom1", "revp", "brlx", "e_factor", "epp2i", "capping", "Ktens", "u0", "cosw", "sinw", "deltaminEVP"):
+        env[k] = float(p[k])
+    env["visc_method"] = "avg_strength" if p["visc_method"] == 1 else "avg_zeta"
+    for k in ("tarea", "hm", "uvm", "earea", "narea", "epm", "npm", "uarea"):
+        env[k] = FArr(np.asarray(cg[k]))
+    env = {k.lower() if k != "ICEPACK" else k: v for k, v in env.items()}
+    for _, nm in names:
+        exec(compile(reg[nm].python(), f"<{nm} transliterated from {REF}>", "exec"), env)
+    f = {k: np.ascontiguousarray(v.copy()) for k, v in case.fields.items()}
+    A3 = {k: FArr(v) for k, v in f.items()}
+    A = {k: FArr(v[0]) for k, v in f.items()}
+    G = {k: FArr(np.asarray(cg[k])[0]) for k in cg}
+    for k in ("dxT", "dyT", "DminTarea"):
+        G[k] = FArr(np.asarray(g[k])[0])
+
+    def index_list(mask, j1, i1):
+        I, J = [], []
+        for j in range(jlo, j1 + 1):
+            for i in range(ilo, i1 + 1):
+                if mask[0, j - 1, i - 1]:
+                    I.append(i); J.append(j)
+        return len(I), FArr(np.array(I or [0])), FArr(np.array(J or [0]))
+
+    nT, Ti, Tj = index_list(f["iceTmask"], jhi + 1, ihi + 1)
+    nU, Ui, Uj = index_list(f["iceUmask"], jhi, ihi)
+    nE, Ei, Ej = index_list(f["iceEmask"], jhi, ihi)
+    nN, Ni, Nj = index_list(f["iceNmask"], jhi, ihi)
+    init = {k: FArr(f[k][0].copy()) for k in ("uvelE", "vvelE", "uvelN", "vvelN")}
+    CENTER, NE, SCALAR, VECTOR = 0, 1, 0, 1
+    X2Y = env["grid_average_x2y_1"]
+    for _ in range(ndte):                 # ice_dyn_evp.F90:1125
+        env["stresscd_t"](nxb, nyb, nT, Ti, Tj, A["uvelE"], A["vvelE"], A["uvelN"], A["vvelN"], G["dxN"], G["dyE"], G["dxT"], G["dyT"],
+                          G["DminTarea"], A["strength"], A["zetax2T"], A["etax2T"], A["stresspT"], A["stressmT"], A["stress12T"])
+        halo_update([f["zetax2T"], f["etax2T"]], CENTER, SCALAR)
+        if env["visc_method"] == "avg_strength":
+            X2Y("T2US", A3["strength"], A3["strengthU"])
+        else:
+            X2Y("T2US", A3["zetax2T"], A3["zetax2U"])
+            X2Y("T2US", A3["etax2T"], A3["etax2U"])
+        env["strain_rates_u"](nxb, nyb, nU, Ui, Uj, A["uvelE"], A["vvelE"], A["uvelN"], A["vvelN"], A["uvel"], A["vvel"], G["dxE"], G["dyN"],
+                              G["dxU"], G["dyU"], G["ratiodxN"], G["ratiodxNr"], G["ratiodyE"], G["ratiodyEr"], G["epm"], G["npm"],
+                              A["divergU"], A["tensionU"], A["shearU"], A["deltaU"])
+        env["stresscd_u"](nxb, nyb, nU, Ui, Uj, G["uarea"], A["zetax2U"], A["etax2U"], A["strengthU"], A["divergU"], A["tensionU"],
+                          A["shearU"], A["deltaU"], A["stresspU"], A["stressmU"], A["stress12U"])
+        halo_update([f["stresspT"], f["stressmT"], f["stress12T"]], CENTER, SCALAR)
+        halo_update([f["stresspU"], f["stressmU"], f["stress12U"]], NE, SCALAR)
+        env["div_stress_ex"](nxb, nyb, nE, Ei, Ej, G["dxE"], G["dyE"], G["dxU"], G["dyT"], G["earear"], A["rheofactE"], A["stresspT"],
+                             A["stressmT"], A["stress12U"], A["strintxE"])
+        env["div_stress_ey"](nxb, nyb, nE, Ei, Ej, G["dxE"], G["dyE"], G["dxU"], G["dyT"], G["earear"], A["rheofactE"], A["stresspU"],
+                             A["stressmU"], A["stress12T"], A["strintyE"])
+        env["div_stress_nx"](nxb, nyb, nN, Ni, Nj, G["dxN"], G["dyN"], G["dxT"], G["dyU"], G["narear"], A["rheofactN"], A["stresspU"],
+                             A["stressmU"], A["stress12T"], A["strintxN"])
+        env["div_stress_ny"](nxb, nyb, nN, Ni, Nj, G["dxN"], G["dyN"], G["dxT"], G["dyU"], G["narear"], A["rheofactN"], A["stresspT"],
+                             A["stressmT"], A["stress12U"], A["strintyN"])
+        env["stepuv_cd"](nxb, nyb, nE, A["cdn_ocnE"], Ei, Ej, A["aiE"], A["uocnE"], A["vocnE"], A["waterxE"], A["wateryE"], A["forcexE"],
+                         A["forceyE"], A["emassdti"], A["fmE"], A["strintxE"], A["strintyE"], A["taubxE"], A["taubyE"], init["uvelE"],
+                         init["vvelE"], A["uvelE"], A["vvelE"], A["TbE"])
+        env["stepuv_cd"](nxb, nyb, nN, A["cdn_ocnN"], Ni, Nj, A["aiN"], A["uocnN"], A["vocnN"], A["waterxN"], A["wateryN"], A["forcexN"],
+                         A["forceyN"], A["nmassdti"], A["fmN"], A["strintxN"], A["strintyN"], A["taubxN"], A["taubyN"], init["uvelN"],
+                         init["vvelN"], A["uvelN"], A["vvelN"], A["TbN"])
+        halo_update([f["uvelE"], f["vvelE"]], NE, VECTOR)
+        halo_update([f["uvelN"], f["vvelN"]], NE, VECTOR)
+        X2Y("E2UA", A3["uvelE"], A3["uvel"])
+        X2Y("N2UA", A3["vvelN"], A3["vvel"])
+        f["uvel"][...] = f["uvel"] * np.asarray(cg["uvm"])
+        f["vvel"][...] = f["vvel"] * np.asarray(cg["uvm"])
+        halo_update([f["uvel"], f["vvel"]], NE, VECTOR)
+    return f
+
+
+CDCASES = [dict(config="tiny", seed=91, ndte=4), dict(config="tiny", seed=92, ndte=3, revised_evp=True),
+           dict(config="tiny", seed=93, ndte=3, visc_method=1), dict(config="tiny", ndte=5),
+           dict(config="tiny", seed=94, ndte=3, ew="closed", ns="closed"), dict(config="gx3", seed=95, ndte=2)]
+CDFIELDS = ("uvelE", "vvelE", "uvelN", "vvelN", "uvel", "vvel", "stresspT", "stressmT", "stress12T", "stresspU", "stressmU", "stress12U",
+            "zetax2T", "etax2T", "divergU", "tensionU", "shearU", "deltaU", "strintxE", "strintyE", "strintxN", "strintyN",
+            "taubxE", "taubyE", "taubxN", "taubyN")
+
+
+def generate_cd(only=None):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from cice_b200 import synth
+    from oracle import oracle
+    out = {}
+    for n, kw in enumerate(CDCASES):
+        if only is not None and n not in only:
+            continue
+        c = synth.make_cdcase(**kw)
+        f = run_reference_cdloop(c, c.params["ndte"], lambda arrs, loc, typ: oracle.halo_update(c.grid, arrs, loc, typ))
+        for k in CDFIELDS:
+            out[f"cdcase{n}_{k}"] = f[k]
+    return out
+
+
 CCASES = [dict(config="tiny", seed=71, ndte=4), dict(config="tiny", seed=72, ndte=3, revised_evp=True),
           dict(config="tiny", seed=73, ndte=3, visc_method=1), dict(config="tiny", ndte=5),
           dict(config="tiny", seed=74, ndte=3, ew="closed", ns="closed"), dict(config="gx3", seed=75, ndte=2)]
@@ -762,6 +876,7 @@ def generate_d():
 
 FULL_VECTORS = (0, 1, 3)   # cases whose arrays are committed in full; every case is committed as sha256 per field
 FULL_CVECTORS = (0, 2)
+FULL_CDVECTORS = (0, 2)
 SHA = os.path.join(HERE, "ref_source_vectors.json")
 
 
@@ -775,16 +890,20 @@ if __name__ == "__main__":
     vec = generate()
     cvec = generate_c()
     dvec = generate_d()
+    cdvec = generate_cd()
     if "--write" in sys.argv:
         full = {k: v for k, v in vec.items() if int(k[4:k.index("_")]) in FULL_VECTORS}
         full.update({k: v for k, v in cvec.items() if int(k[5:k.index("_")]) in FULL_CVECTORS})
         full.update(dvec)
+        full.update({k: v for k, v in cdvec.items() if int(k[6:k.index("_")]) in FULL_CDVECTORS})
         np.savez_compressed(OUT, **full)
         meta = {"_how": "python tests/golden/ref_translit.py --write  (transliterates the reference's Fortran subroutines under /root/reference "
                         "-- B grid: stress, stepu, strain_rates, visc_replpress; C grid: strain_rates_U, strain_rates_Tdt, stressC_T, stressC_U, "
-                        "div_stress_Ex/Ny, stepu_C, stepv_C, grid_average_X2Y_1/X2YS/X2YA; ice_constants -- and runs them; see the module docstring)",
+                        "div_stress_Ex/Ny, stepu_C, stepv_C, grid_average_X2Y_1/X2YS/X2YA; CD grid: stressCD_T, stressCD_U, strain_rates_Tdtsd, "
+                        "div_stress_Ey/Nx, stepuv_CD; deformations; ice_constants -- and runs them; see the module docstring)",
                 "cases": [dict(kw) for kw in CASES], "ccases": [dict(kw) for kw in CCASES],
-                "sha256": {k: sha(v) for k, v in {**vec, **cvec, **dvec}.items()}}
+                "cdcases": [dict(kw) for kw in CDCASES],
+                "sha256": {k: sha(v) for k, v in {**vec, **cvec, **dvec, **cdvec}.items()}}
         json.dump(meta, open(SHA, "w"), indent=1)
         print("wrote", OUT, os.path.getsize(OUT), "bytes;", SHA)
     if "--show" in sys.argv:

@@ -193,3 +193,48 @@ def test_cgrid_oracle_matches_vectors_from_reference_source(oracle_mod):
 def test_cgrid_gpu_matches_vectors_from_reference_source(evp_lib, monkeypatch, fused):
     monkeypatch.setenv("EVP_B200_CGRID_FUSED", fused)
     check_cgrid_against_ref_source_vectors(lambda c: run_gpu_c(evp_lib, c, mode=abi.MODE_EXACT))
+
+
+# ---- CD grid ----
+def run_oracle_cd(oracle, c, nthreads=0):
+    f = c.copy_fields()
+    oracle.evp_run_cdgrid(c.grid, c.cgrid, c.params, f, nthreads=nthreads)
+    return f
+
+
+def check_cdgrid_against_ref_source_vectors(run):
+    import hashlib
+    import json
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    import ref_translit as rt
+    meta = json.load(open(os.path.join(here, "ref_source_vectors.json")))
+    full = np.load(os.path.join(here, "ref_source_vectors.npz"))
+    assert meta["cdcases"] == [dict(kw) for kw in rt.CDCASES], "tests/golden/ref_source_vectors.json is stale: regenerate"
+    for n, kw in enumerate(rt.CDCASES):
+        c = synth.make_cdcase(**kw)
+        f = run(c)
+        for k in rt.CDFIELDS:
+            key = f"cdcase{n}_{k}"
+            if key in full.files:
+                assert np.array_equal(f[k].view(np.int64), full[key].view(np.int64)), \
+                    f"{key}: {np.count_nonzero(f[k] != full[key])} cells differ from the reference-source vector"
+            h = hashlib.sha256(np.ascontiguousarray(f[k], dtype=np.float64).tobytes()).hexdigest()
+            assert h == meta["sha256"][key], f"{key}: differs from the reference-source vector (sha256)"
+
+
+def test_cdgrid_oracle_matches_vectors_from_reference_source(oracle_mod):
+    """grid_ice = 'CD' (ice_dyn_evp.F90:1123-1275): the oracle against the transliterated reference source (stressCD_T, stressCD_U,
+    strain_rates_Tdtsd, strain_rates_U, div_stress_Ex/Ey/Nx/Ny, stepuv_CD, grid averages), bit for bit."""
+    check_cdgrid_against_ref_source_vectors(lambda c: run_oracle_cd(oracle_mod, c))
+
+
+@pytest.mark.parametrize("bs", [(12, 10), (7, 9)])
+def test_cdgrid_oracle_decomposition_invariance(oracle_mod, bs):
+    c1 = synth.make_cdcase("tiny", seed=96, ndte=5)
+    cb = synth.make_cdcase("tiny", seed=96, ndte=5, block_size=bs)
+    f1, fb = run_oracle_cd(oracle_mod, c1), run_oracle_cd(oracle_mod, cb)
+    for n in abi.CDFIELDS_INOUT:
+        assert np.array_equal(synth.gather(fb[n], cb.blocks), synth.gather(f1[n], c1.blocks)), n
