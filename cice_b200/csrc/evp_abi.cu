@@ -155,6 +155,10 @@ struct Ctx {
   std::vector<double *> dbuf;      // deformations: dxU, dyU, tarear + 5 outputs
   std::vector<double *> cbuf;      // every C-grid device array (freed together)
   std::vector<double *> cstage;    // staging, one per C field
+  std::vector<double *> cdstage;   // staging, one per CD field
+  bool cdinit = false;             // CD-only device arrays allocated
+  cudaGraphExec_t cdexec = nullptr;
+  evp_b200_params_t cdparams{};
   unsigned char *cmask[4] = {};
   cudaGraphExec_t cexec = nullptr;  // cached graph of the C-grid loop (dies with the context: it bakes pointers and wrap flags)
   evp_b200_params_t cparams{};
@@ -192,11 +196,16 @@ static void destroy_graph() {
     cudaGraphExecDestroy(g.cexec);
     g.cexec = nullptr;
   }
+  if (g.cdexec) {
+    cudaGraphExecDestroy(g.cdexec);
+    g.cdexec = nullptr;
+  }
 }
 
 static int free_all() {
   destroy_graph();
   g.cinit = false;
+  g.cdinit = false;
   auto F = [](auto *&p) {
     if (p) cudaFree(p);
     p = nullptr;
@@ -205,6 +214,7 @@ static int free_all() {
   for (auto &p : g.cbuf) F(p);
   for (auto &p : g.dbuf) F(p);
   for (auto &p : g.cstage) F(p);
+  for (auto &p : g.cdstage) F(p);
   for (auto &p : g.cmask) F(p);
   g.dfield[F_U] = g.dfield[F_V] = g.du1 = g.dv1 = nullptr;  // live inside dshare
   F(g.dshare);
@@ -963,6 +973,114 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// CD grid: same life cycle as the C grid, four kernels per subcycle
+// ------------------------------------------------------------------------------------------------
+static int do_run_cdgrid(const evp_b200_params_t *p, evp_b200_cdfields_t *f) {
+  if (!g.cinit) return fail("evp_b200_run_cdgrid: evp_b200_init_cgrid has not been called (the CD grid uses the C grid's geometry)");
+  if (!p || !f) return fail("evp_b200_run_cdgrid: null argument");
+  if (p->ndte < 0) return fail("evp_b200_run_cdgrid: ndte < 0");
+  if (p->visc_method != EVP_B200_VISC_AVG_ZETA && p->visc_method != EVP_B200_VISC_AVG_STRENGTH) return fail("evp_b200_run_cdgrid: unknown visc_method %d", p->visc_method);
+  if (p->mode != EVP_B200_MODE_EXACT && p->mode != EVP_B200_MODE_FAST) return fail("evp_b200_run_cdgrid: unknown mode %d", p->mode);
+  CK(cudaSetDevice(g.device));
+  CDom &c = g.cdom;
+  const size_t bblk = g.nblk_elems * sizeof(double), bdom = g.ndom * sizeof(double);
+  constexpr int NCD = 54;
+  if (!g.cdinit) {
+    double **extra[13] = {&c.stresspU, &c.stressmU, &c.zetax2U, &c.strintyE, &c.strintxN, &c.taubyE, &c.taubxN, &c.vvelE_init, &c.uvelN_init,
+                          (double **)&c.wateryE, (double **)&c.waterxN, (double **)&c.forceyE, (double **)&c.forcexN};
+    for (auto pp : extra) if (calloc_dom(*pp)) return 1;
+    for (int q = 0; q < NCD; ++q) {
+      double *st = nullptr;
+      CK(cudaMalloc(&st, bblk));
+      g.cdstage.push_back(st);
+    }
+    g.cdinit = true;
+  }
+  // kinds as in do_run_cgrid: 'i' in; 'r' inout, ring refreshed by the loop; 'R' like 'r' but zero-filled whole block every subcycle
+  // (grid_average output); 'n' inout interior; 'y' out: zero-filled, interiors written, not halo-updated; '-' untouched
+  struct Fld { const double *h; double *dv; char kind; };
+  const bool avgstr = (p->visc_method == EVP_B200_VISC_AVG_STRENGTH);
+  Fld tab[NCD] = {
+      {f->uvelE, c.uvelE, 'r'}, {f->vvelE, c.vvelE, 'r'}, {f->uvelN, c.uvelN, 'r'}, {f->vvelN, c.vvelN, 'r'}, {f->uvel, c.uvel, 'R'}, {f->vvel, c.vvel, 'R'},
+      {f->stresspT, c.stresspT, 'r'}, {f->stressmT, c.stressmT, 'r'}, {f->stress12T, c.stress12T, 'r'},
+      {f->stresspU, c.stresspU, 'r'}, {f->stressmU, c.stressmU, 'r'}, {f->stress12U, c.stress12U, 'r'},
+      {f->zetax2T, c.zetax2T, 'r'}, {f->etax2T, c.etax2T, 'r'}, {f->zetax2U, c.zetax2U, avgstr ? '-' : 'y'}, {f->etax2U, c.etax2U, avgstr ? '-' : 'y'},
+      {f->strengthU, c.strengthU, avgstr ? 'y' : '-'},
+      {f->divergU, c.divergU, 'y'}, {f->tensionU, c.tensionU, 'y'}, {f->shearU, c.shearU, 'y'}, {f->deltaU, c.deltaU, 'y'},
+      {f->strintxE, c.strintxE, 'n'}, {f->strintyE, c.strintyE, 'n'}, {f->strintxN, c.strintxN, 'n'}, {f->strintyN, c.strintyN, 'n'},
+      {f->taubxE, c.taubxE, 'n'}, {f->taubyE, c.taubyE, 'n'}, {f->taubxN, c.taubxN, 'n'}, {f->taubyN, c.taubyN, 'n'},
+      {f->strength, (double *)c.strength, 'i'}, {f->cdn_ocnE, (double *)c.cdnE, 'i'}, {f->cdn_ocnN, (double *)c.cdnN, 'i'}, {f->aiE, (double *)c.aiE, 'i'},
+      {f->aiN, (double *)c.aiN, 'i'}, {f->uocnE, (double *)c.uocnE, 'i'}, {f->vocnE, (double *)c.vocnE, 'i'}, {f->uocnN, (double *)c.uocnN, 'i'},
+      {f->vocnN, (double *)c.vocnN, 'i'}, {f->waterxE, (double *)c.waterxE, 'i'}, {f->wateryE, (double *)c.wateryE, 'i'},
+      {f->waterxN, (double *)c.waterxN, 'i'}, {f->wateryN, (double *)c.wateryN, 'i'}, {f->forcexE, (double *)c.forcexE, 'i'},
+      {f->forceyE, (double *)c.forceyE, 'i'}, {f->forcexN, (double *)c.forcexN, 'i'}, {f->forceyN, (double *)c.forceyN, 'i'},
+      {f->emassdti, (double *)c.emassdti, 'i'}, {f->nmassdti, (double *)c.nmassdti, 'i'}, {f->fmE, (double *)c.fmE, 'i'}, {f->fmN, (double *)c.fmN, 'i'},
+      {f->TbE, (double *)c.TbE, 'i'}, {f->TbN, (double *)c.TbN, 'i'}, {f->rheofactE, (double *)c.rheofactE, 'i'}, {f->rheofactN, (double *)c.rheofactN, 'i'}};
+  for (int q = 0; q < NCD; ++q) {
+    const Fld &t = tab[q];
+    if (t.kind == '-') continue;
+    if (!t.h) return fail("evp_b200_run_cdgrid: null field %d", q);
+    if (t.kind == 'y') {
+      CK(cudaMemsetAsync(t.dv, 0, bdom, g.stream));
+      CK(cudaMemsetAsync(g.cdstage[q], 0, bblk, g.stream));
+      continue;
+    }
+    CK(cudaMemcpyAsync(g.cdstage[q], t.h, bblk, cudaMemcpyHostToDevice, g.stream));
+    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(t.dv, g.cdstage[q], g.d_gsrc, (int)g.ndom);
+  }
+  const int32_t *hm[4] = {f->iceTmask, f->iceUmask, f->iceEmask, f->iceNmask};
+  for (int q = 0; q < 4; ++q) {
+    if (!hm[q]) return fail("evp_b200_run_cdgrid: null mask %d", q);
+    CK(cudaMemcpyAsync(g.stage_mask, hm[q], g.nblk_elems * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+    pack_mask<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(g.cmask[q], g.stage_mask, g.d_gsrc, (int)g.ndom);
+  }
+  // velocities at entry (dyn_prep2 at E and N, shared.F90:787-788)
+  CK(cudaMemcpyAsync(c.uvelE_init, c.uvelE, bdom, cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaMemcpyAsync(c.vvelE_init, c.vvelE, bdom, cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaMemcpyAsync(c.uvelN_init, c.uvelN, bdom, cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaMemcpyAsync(c.vvelN_init, c.vvelN, bdom, cudaMemcpyDeviceToDevice, g.stream));
+  CK(cudaGetLastError());
+
+  const KParams k = kparams(p);
+  const bool exact = (p->mode == EVP_B200_MODE_EXACT);
+  int nl = 0;
+  if (!g.cdexec || memcmp(&g.cdparams, p, sizeof *p) != 0) {
+    if (g.cdexec) { cudaGraphExecDestroy(g.cdexec); g.cdexec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t le = cudaSuccess;
+    for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub)
+      le = exact ? exact::launch_cdgrid_subcycle(c, k, g.stream, &nl) : fast::launch_cdgrid_subcycle(c, k, g.stream, &nl);
+    cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
+    if (le != cudaSuccess || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail("evp_b200_run_cdgrid: capture failed: %s", cudaGetErrorString(le != cudaSuccess ? le : ce)); }
+    CK(cudaGraphInstantiate(&g.cdexec, graph, 0));
+    CK(cudaGraphDestroy(graph));
+    g.cdparams = *p;
+  } else {
+    nl = 4 * p->ndte;
+  }
+  CK(cudaEventRecord(g.ev0, g.stream));
+  if (p->ndte > 0) CK(cudaGraphLaunch(g.cdexec, g.stream));
+  CK(cudaEventRecord(g.ev1, g.stream));
+  g.last_launches = nl;
+
+  for (int q = 0; q < 29; ++q) {   // everything that is not 'i'
+    const Fld &t = tab[q];
+    if (t.kind == '-') continue;
+    if (t.kind == 'R' && p->ndte > 0) CK(cudaMemsetAsync(g.cdstage[q], 0, bblk, g.stream));
+    if (t.kind == 'n' || t.kind == 'y')
+      unpack_f64<<<grid_blocks(g.n_int), 256, 0, g.stream>>>(g.cdstage[q], t.dv, g.d_int_lin, g.d_int_dom, g.n_int);
+    else
+      unpack_f64<<<grid_blocks(g.n_uv), 256, 0, g.stream>>>(g.cdstage[q], t.dv, g.d_uv_lin, g.d_uv_dom, g.n_uv);
+    CK(cudaMemcpyAsync((void *)t.h, g.cdstage[q], bblk, cudaMemcpyDeviceToHost, g.stream));
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1));
+  return 0;
+}
+
 }  // namespace evp
 
 // ------------------------------------------------------------------------------------------------
@@ -1011,6 +1129,7 @@ int evp_b200_finalize(void) {
 int evp_b200_deformations(evp_b200_deform_t *d) { return do_deformations(d); }
 int evp_b200_init_cgrid(const evp_b200_cgrid_t *cg) { return do_init_cgrid(cg); }
 int evp_b200_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) { return do_run_cgrid(p, f); }
+int evp_b200_run_cdgrid(const evp_b200_params_t *p, evp_b200_cdfields_t *f) { return do_run_cdgrid(p, f); }
 
 int evp_b200_upload(const evp_b200_fields_t *f) { return do_upload(f, false); }
 int evp_b200_subcycle(const evp_b200_params_t *p) { return do_subcycle(p); }

@@ -431,6 +431,174 @@ cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur
   return cudaGetLastError();
 }
 
+// =============================================================================================================
+// CD grid (grid_ice = 'CD'): one subcycle of ice_dyn_evp.F90:1125-1267 as four kernels, cut where a value
+// is needed at a neighbour point:
+//   kcd1  strain_rates_Tdtsd + stressCD_T                         shared.F90:2171-2243, evp.F90:1978-2080
+//   kcd2  T->U averages (zetax2U, etax2U | strengthU), strain_rates_U, stressCD_U     grid.F90:4159-4211, evp.F90:2088-2178
+//   kcd3  div_stress_Ex/Ey/Nx/Ny + stepuv_CD at E and at N        evp.F90:2195-2416, shared.F90:973-1085
+//   kcd4  grid_average_X2YA E->U, N->U, times uvm                  grid.F90:4388-4606, evp.F90:1254-1259
+// Halo points are the producing thread's wrap stores (ring_store), as on the C grid.  First correct form: one thread per
+// point, plain IEEE division and square root, no fusion.  Bit-identical to the oracle and to the reference-source vectors.
+// =============================================================================================================
+__device__ __forceinline__ double t2u_S(const CDom &d, const double *__restrict__ src, int c) {   // grid_average_X2YS 'NE'
+  const int e = c + 1, n = c + d.ld, ne = n + 1;
+  const double mc = d.hm[c], me = d.hm[e], mn = d.hm[n], mne = d.hm[ne];
+  const double wc = d.tarea[c], we = d.tarea[e], wn = d.tarea[n], wne = d.tarea[ne];
+  const double wtmp = (mc * wc + me * we + mn * wn + mne * wne);
+  if (wtmp == 0.0) return 0.0;
+  return (mc * src[c] * wc + me * src[e] * we + mn * src[n] * wn + mne * src[ne] * wne) / wtmp;
+}
+
+__global__ void __launch_bounds__(256) kcd1_stress_T(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  CELL_IJ(d.wrap_ew ? d.nx : d.nx + 1, d.wrap_ns ? d.ny : d.ny + 1);
+  const int c = AT(i, j);
+  if (!d.maskT[c]) return;
+  const int w = c - 1, s = c - d.ld;
+  const double dyEc = d.dyE[c], dyEw = d.dyE[w], dxNc = d.dxN[c], dxNs = d.dxN[s], dxT = d.dxT[c], dyT = d.dyT[c];
+  const double uEc = d.uvelE[c], uEw = d.uvelE[w], vNc = d.vvelN[c], vNs = d.vvelN[s];
+  const double divT = dyEc * uEc - dyEw * uEw + dxNc * vNc - dxNs * vNs;
+  const double tensionT = (dyT * dyT) * (uEc / dyEc - uEw / dyEw) - (dxT * dxT) * (vNc / dxNc - vNs / dxNs);
+  const double shearT = (dxT * dxT) * (d.uvelN[c] / dxNc - d.uvelN[s] / dxNs) + (dyT * dyT) * (d.vvelE[c] / dyEc - d.vvelE[w] / dyEw);
+  const double DeltaT = sqrt(divT * divT + k.e_factor * (tensionT * tensionT + shearT * shearT));
+  double zetax2, etax2, rep;
+  visc_c(d.strength[c], d.DminTarea[c], DeltaT, k, zetax2, etax2, rep);
+  const double relax = 1.0 - k.arlx1i * k.revp;
+  const double sp = (d.stresspT[c] * relax + k.arlx1i * (zetax2 * divT - rep)) * k.denom1;
+  const double sm = (d.stressmT[c] * relax + k.arlx1i * etax2 * tensionT) * k.denom1;
+  const double s12 = (d.stress12T[c] * relax + k.arlx1i * 0.5 * etax2 * shearT) * k.denom1;
+  ring_store(d, d.zetax2T, i, j, zetax2, 3, false);
+  ring_store(d, d.etax2T, i, j, etax2, 3, false);
+  ring_store(d, d.stresspT, i, j, sp, 3, false);
+  ring_store(d, d.stressmT, i, j, sm, 3, false);
+  ring_store(d, d.stress12T, i, j, s12, 3, false);
+}
+
+__global__ void __launch_bounds__(256) kcd2_stress_U(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  CELL_IJ(d.nx, d.ny);
+  const int c = AT(i, j);
+  double zetax2U = 0.0, etax2U = 0.0, strengthU = 0.0;
+  if (k.visc_method == 1) {
+    strengthU = t2u_S(d, d.strength, c);
+    d.strengthU[c] = strengthU;
+  } else {
+    zetax2U = t2u_S(d, d.zetax2T, c);
+    etax2U = t2u_S(d, d.etax2T, c);
+    d.zetax2U[c] = zetax2U;
+    d.etax2U[c] = etax2U;
+  }
+  double div, ten, shr, del;
+  strain_U_at(d, k, c, div, ten, shr, del);
+  d.divergU[c] = div;
+  d.tensionU[c] = ten;
+  d.shearU[c] = shr;
+  d.deltaU[c] = del;
+  if (!d.maskU[c]) return;
+  double lzetax2U, letax2U, lrep_prsU;
+  if (k.visc_method == 1) {
+    const double DminUarea = k.deltaminEVP * d.uarea[c];
+    visc_c(strengthU, DminUarea, del, k, lzetax2U, letax2U, lrep_prsU);
+  } else {
+    lzetax2U = zetax2U;
+    letax2U = etax2U;
+    lrep_prsU = (1.0 - k.Ktens) / (1.0 + k.Ktens) * lzetax2U * del;
+  }
+  const double relax = 1.0 - k.arlx1i * k.revp;
+  const double sp = (d.stresspU[c] * relax + k.arlx1i * (lzetax2U * div - lrep_prsU)) * k.denom1;
+  const double sm = (d.stressmU[c] * relax + k.arlx1i * letax2U * ten) * k.denom1;
+  const double s12 = (d.stress12U[c] * relax + k.arlx1i * 0.5 * letax2U * shr) * k.denom1;
+  ring_store(d, d.stresspU, i, j, sp, 3, false);
+  ring_store(d, d.stressmU, i, j, sm, 3, false);
+  ring_store(d, d.stress12U, i, j, s12, 3, false);
+}
+
+// stepuv_CD at one point (shared.F90:1040-1078); returns the new velocity, stores the seabed stress components
+__device__ __forceinline__ void stepuv_cd_at(const KParams &k, double uold, double vold, double ai, double Cw, double uocn, double vocn,
+                                             double waterx, double watery, double forcex, double forcey, double massdti, double fm,
+                                             double strintx, double strinty, double uinit, double vinit, double Tb, double &un,
+                                             double &vn, double &taubx, double &tauby) {
+  const double du = uocn - uold, dv = vocn - vold;
+  const double vrel = ai * k.rhow * Cw * sqrt(du * du + dv * dv);
+  const double taux = vrel * waterx;
+  const double tauy = vrel * watery;
+  const double ccc = sqrt(uold * uold + vold * vold) + k.u0;
+  const double Cb = Tb / ccc;
+  const double cca = (k.brlx + k.revp) * massdti + vrel * k.cosw + Cb;
+  const double ccb = fm + copysign(1.0, fm) * vrel * k.sinw;
+  const double ab2 = cca * cca + ccb * ccb;
+  const double cc1 = strintx + forcex + taux + massdti * (k.brlx * uold + k.revp * uinit);
+  const double cc2 = strinty + forcey + tauy + massdti * (k.brlx * vold + k.revp * vinit);
+  un = (cca * cc1 + ccb * cc2) / ab2;
+  vn = (cca * cc2 - ccb * cc1) / ab2;
+  taubx = -un * Cb;
+  tauby = -vn * Cb;
+}
+
+__global__ void __launch_bounds__(256) kcd3_momentum(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  CELL_IJ(d.nx, d.ny);
+  const int c = AT(i, j), e = c + 1, n = c + d.ld, s = c - d.ld, w = c - 1;
+  if (d.maskE[c]) {
+    const double dyE = d.dyE[c], dxE = d.dxE[c], dyTe = d.dyT[e], dyTc = d.dyT[c], dxUc = d.dxU[c], dxUs = d.dxU[s];
+    const double fac = d.rheofactE[c] * d.earear[c];
+    const double strintx = fac * (0.5 * dyE * (d.stresspT[e] - d.stresspT[c]) +
+                                  (0.5 / dyE) * ((dyTe * dyTe) * d.stressmT[e] - (dyTc * dyTc) * d.stressmT[c]) +
+                                  (1.0 / dxE) * ((dxUc * dxUc) * d.stress12U[c] - (dxUs * dxUs) * d.stress12U[s]));
+    const double strinty = fac * (0.5 * dxE * (d.stresspU[c] - d.stresspU[s]) -
+                                  (0.5 / dxE) * ((dxUc * dxUc) * d.stressmU[c] - (dxUs * dxUs) * d.stressmU[s]) +
+                                  (1.0 / dyE) * ((dyTe * dyTe) * d.stress12T[e] - (dyTc * dyTc) * d.stress12T[c]));
+    d.strintxE[c] = strintx;
+    d.strintyE[c] = strinty;
+    double un, vn, tbx, tby;
+    stepuv_cd_at(k, d.uvelE[c], d.vvelE[c], d.aiE[c], d.cdnE[c], d.uocnE[c], d.vocnE[c], d.waterxE[c], d.wateryE[c], d.forcexE[c],
+                 d.forceyE[c], d.emassdti[c], d.fmE[c], strintx, strinty, d.uvelE_init[c], d.vvelE_init[c], d.TbE[c], un, vn, tbx, tby);
+    ring_store(d, d.uvelE, i, j, un, 3, false);
+    ring_store(d, d.vvelE, i, j, vn, 3, false);
+    d.taubxE[c] = tbx;
+    d.taubyE[c] = tby;
+  }
+  if (d.maskN[c]) {
+    const double dxN = d.dxN[c], dyN = d.dyN[c], dxTn = d.dxT[n], dxTc = d.dxT[c], dyUc = d.dyU[c], dyUw = d.dyU[w];
+    const double fac = d.rheofactN[c] * d.narear[c];
+    const double strintx = fac * (0.5 * dyN * (d.stresspU[c] - d.stresspU[w]) +
+                                  (0.5 / dyN) * ((dyUc * dyUc) * d.stressmU[c] - (dyUw * dyUw) * d.stressmU[w]) +
+                                  (1.0 / dxN) * ((dxTn * dxTn) * d.stress12T[n] - (dxTc * dxTc) * d.stress12T[c]));
+    const double strinty = fac * (0.5 * dxN * (d.stresspT[n] - d.stresspT[c]) -
+                                  (0.5 / dxN) * ((dxTn * dxTn) * d.stressmT[n] - (dxTc * dxTc) * d.stressmT[c]) +
+                                  (1.0 / dyN) * ((dyUc * dyUc) * d.stress12U[c] - (dyUw * dyUw) * d.stress12U[w]));
+    d.strintxN[c] = strintx;
+    d.strintyN[c] = strinty;
+    double un, vn, tbx, tby;
+    stepuv_cd_at(k, d.uvelN[c], d.vvelN[c], d.aiN[c], d.cdnN[c], d.uocnN[c], d.vocnN[c], d.waterxN[c], d.wateryN[c], d.forcexN[c],
+                 d.forceyN[c], d.nmassdti[c], d.fmN[c], strintx, strinty, d.uvelN_init[c], d.vvelN_init[c], d.TbN[c], un, vn, tbx, tby);
+    ring_store(d, d.uvelN, i, j, un, 3, false);
+    ring_store(d, d.vvelN, i, j, vn, 3, false);
+    d.taubxN[c] = tbx;
+    d.taubyN[c] = tby;
+  }
+}
+
+__global__ void __launch_bounds__(256) kcd4_interp(const __grid_constant__ CDom d) {
+  CELL_IJ(d.nx, d.ny);
+  const int c = AT(i, j), e = c + 1, n = c + d.ld;
+  double num, den;
+  avg2_terms<false>(d.uvelE, d.earea, c, n, num, den);                // E2UA 'N'
+  const double uU = ((den != 0.0) ? num / den : 0.0) * d.uvm[c];
+  avg2_terms<false>(d.vvelN, d.narea, c, e, num, den);                // N2UA 'E'
+  const double vU = ((den != 0.0) ? num / den : 0.0) * d.uvm[c];
+  ring_store(d, d.uvel, i, j, uU, 3, true);
+  ring_store(d, d.vvel, i, j, vU, 3, true);
+}
+
+cudaError_t launch_cdgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches) {
+  dim3 b(32, 8), gU((d.nx + 31) / 32, (d.ny + 7) / 8), gT((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8);
+  kcd1_stress_T<<<gT, b, 0, s>>>(d, p);
+  kcd2_stress_U<<<gU, b, 0, s>>>(d, p);
+  kcd3_momentum<<<gU, b, 0, s>>>(d, p);
+  kcd4_interp<<<gU, b, 0, s>>>(d);
+  *launches += 4;
+  return cudaGetLastError();
+}
+
 // ---- all ndte subcycles in ONE cooperative launch -----------------------------------------------------------
 // 148 x 2 co-resident CTAs of 32 x 16 threads; every thread keeps the same cell for the whole loop (larger sub-domains:
 // a fixed list of tiles per CTA).  The five kernel boundaries of a subcycle become five grid barriers (one

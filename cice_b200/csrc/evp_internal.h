@@ -53,6 +53,9 @@ struct CDom {
   const double *emassdti, *nmassdti, *fmE, *fmN, *TbE, *TbN, *rheofactE, *rheofactN;
   double *uvelE_init, *vvelN_init;
   const unsigned char *maskT, *maskU, *maskE, *maskN;
+  // CD grid only (grid_ice = 'CD', evp_b200_run_cdgrid): the rest of the stress tensor, the other momentum component at E and N
+  double *stresspU, *stressmU, *zetax2U, *strintyE, *strintxN, *taubyE, *taubxN, *vvelE_init, *uvelN_init;
+  const double *wateryE, *waterxN, *forceyE, *forcexN;
 };
 
 // scalars of set_evp_parameters (ice_dyn_shared.F90:453-486) and friends
@@ -116,6 +119,7 @@ struct PersistPlan {
   cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \
   cudaError_t launch_cgrid_static(const CDom &d, double *rhalf_dyE, double *r_dxE, double *rhalf_dxN, double *r_dyN, double *uareaavgr, cudaStream_t s); \
   cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur, int shape, cudaStream_t s, int *launches);  \
+  cudaError_t launch_cdgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \
   cudaError_t launch_cgrid_coop(const CDom &d, const KParams &p, int ndte, unsigned *bar, int max_ctas, cudaStream_t s); \
   int cgrid_coop_max_ctas(int num_sms); \
   }

@@ -102,6 +102,14 @@ def dyn_evp_b200_run_cgrid(params, cfields):
     return cfields
 
 
+def dyn_evp_b200_run_cdgrid(params, cdfields):
+    """the CD-grid subcycle loop (ice_dyn_evp.F90:1123-1275): host arrays in, host arrays out (after dyn_evp_b200_init_cgrid)."""
+    p = abi.make_params(params)
+    f, keep = abi.make_cdfields(cdfields, _state["npl"])
+    check(load().evp_b200_run_cdgrid(C.byref(p), C.byref(f)), "evp_b200_run_cdgrid")
+    return cdfields
+
+
 def deformations(d, e_factor):
     """`deformations` (ice_dyn_shared.F90:1756-1860) from the velocities the last loop left on the device;
     d: dict with dxU, dyU, tarear (in) and divu, shear, vort, rdg_conv, rdg_shear (inout, in place)."""

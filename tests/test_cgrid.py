@@ -238,3 +238,70 @@ def test_cdgrid_oracle_decomposition_invariance(oracle_mod, bs):
     f1, fb = run_oracle_cd(oracle_mod, c1), run_oracle_cd(oracle_mod, cb)
     for n in abi.CDFIELDS_INOUT:
         assert np.array_equal(synth.gather(fb[n], cb.blocks), synth.gather(f1[n], c1.blocks)), n
+
+
+def run_gpu_cd(evp, c, **over):
+    f = c.copy_fields()
+    evp.dyn_evp_b200_init(c.grid)
+    try:
+        evp.dyn_evp_b200_init_cgrid(c.cgrid)
+        evp.dyn_evp_b200_run_cdgrid(dict(c.params, **over), f)
+    finally:
+        evp.dyn_evp_b200_finalize()
+    return f
+
+
+def _cd_compare(got, ref, params):
+    skip = ("zetax2U", "etax2U") if params["visc_method"] == abi.VISC_AVG_STRENGTH else ("strengthU",)
+    bad = []
+    for n in abi.CDFIELDS_INOUT + abi.CDFIELDS_OUT:
+        if n in skip:
+            continue
+        if not np.array_equal(got[n].view(np.int64), ref[n].view(np.int64)):
+            bad.append(f"{n}: {np.count_nonzero(got[n] != ref[n])} cells differ, max {np.nanmax(np.abs(got[n] - ref[n])):.3e}")
+    assert not bad, "CD grid not bit-identical:\n  " + "\n  ".join(bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,kw", [
+    ("tiny", dict(seed=101)), ("tiny", dict(seed=102, revised_evp=True)), ("tiny", dict(seed=103, visc_method=abi.VISC_AVG_STRENGTH)),
+    ("tiny", dict(seed=104, ew="closed", ns="closed")), ("tiny", dict(seed=105, ew="cyclic", ns="cyclic", kmt="none")),
+    ("tiny", dict(seed=106, block_size=(12, 10))), ("tiny", dict(seed=107, block_size=(7, 9), visc_method=abi.VISC_AVG_STRENGTH)),
+    ("tiny", dict(ndte=9)), ("gx3", dict(seed=108, ndte=12)),
+], ids=["tiny", "tiny-revised", "tiny-avgstrength", "tiny-closed", "tiny-cyclic2", "tiny-4blocks", "tiny-12blocks-avgstrength", "tiny-S1",
+        "gx3"])
+def test_cdgrid_exact_bitwise(oracle_mod, evp_lib, cfg, kw):
+    """grid_ice = 'CD' (SURVEY 8a row a13): the CUDA path (four kernels per subcycle) against the oracle, every inout and work
+    array, every cell of every block."""
+    c = synth.make_cdcase(cfg, **kw)
+    ref = run_oracle_cd(oracle_mod, c)
+    got = run_gpu_cd(evp_lib, c, mode=abi.MODE_EXACT)
+    _cd_compare(got, ref, c.params)
+
+
+@pytest.mark.gpu
+def test_cdgrid_gpu_matches_vectors_from_reference_source(evp_lib):
+    check_cdgrid_against_ref_source_vectors(lambda c: run_gpu_cd(evp_lib, c, mode=abi.MODE_EXACT))
+
+
+@pytest.mark.gpu
+def test_cdgrid_repeat_and_fast_mode(oracle_mod, evp_lib):
+    """two consecutive calls carry the state; FMA mode stays within 1e-10 on a short loop."""
+    c = synth.make_cdcase("tiny", seed=109, ndte=5)
+    ref, got = c.copy_fields(), c.copy_fields()
+    evp_lib.dyn_evp_b200_init(c.grid)
+    evp_lib.dyn_evp_b200_init_cgrid(c.cgrid)
+    try:
+        for _ in range(2):
+            oracle_mod.evp_run_cdgrid(c.grid, c.cgrid, c.params, ref)
+            evp_lib.dyn_evp_b200_run_cdgrid(dict(c.params, mode=abi.MODE_EXACT), got)
+            _cd_compare(got, ref, c.params)
+        fast = c.copy_fields()
+        evp_lib.dyn_evp_b200_run_cdgrid(dict(c.params, mode=abi.MODE_FAST), fast)
+        one = c.copy_fields()
+        oracle_mod.evp_run_cdgrid(c.grid, c.cgrid, c.params, one)
+        for n in abi.CDFIELDS_INOUT:
+            den = max(np.abs(one[n]).max(), 1e-300)
+            assert np.abs(fast[n] - one[n]).max() / den <= 1e-10, n
+    finally:
+        evp_lib.dyn_evp_b200_finalize()
