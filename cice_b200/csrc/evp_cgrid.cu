@@ -521,8 +521,8 @@ __device__ __forceinline__ void stepuv_cd_at(const KParams &k, double uold, doub
   const double vrel = ai * k.rhow * Cw * sqrt(du * du + dv * dv);
   const double taux = vrel * waterx;
   const double tauy = vrel * watery;
-  const double ccc = sqrt(uold * uold + vold * vold) + k.u0;
-  const double Cb = Tb / ccc;
+  // no grounded ice: Tb is (+-)0 and (+-)0 / (finite positive) is that same zero (see stepu_point)
+  const double Cb = (Tb == 0.0 && k.u0 > 0.0) ? Tb : Tb / (sqrt(uold * uold + vold * vold) + k.u0);
   const double cca = (k.brlx + k.revp) * massdti + vrel * k.cosw + Cb;
   const double ccb = fm + copysign(1.0, fm) * vrel * k.sinw;
   const double ab2 = cca * cca + ccb * ccb;
@@ -541,8 +541,8 @@ __global__ void __launch_bounds__(256) kcd3_momentum(const __grid_constant__ CDo
     const double dyE = d.dyE[c], dxE = d.dxE[c], dyTe = d.dyT[e], dyTc = d.dyT[c], dxUc = d.dxU[c], dxUs = d.dxU[s];
     const double fac = d.rheofactE[c] * d.earear[c];
     const double strintx = fac * (0.5 * dyE * (d.stresspT[e] - d.stresspT[c]) +
-                                  (0.5 / dyE) * ((dyTe * dyTe) * d.stressmT[e] - (dyTc * dyTc) * d.stressmT[c]) +
-                                  (1.0 / dxE) * ((dxUc * dxUc) * d.stress12U[c] - (dxUs * dxUs) * d.stress12U[s]));
+                                  d.rhalf_dyE[c] * ((dyTe * dyTe) * d.stressmT[e] - (dyTc * dyTc) * d.stressmT[c]) +
+                                  d.r_dxE[c] * ((dxUc * dxUc) * d.stress12U[c] - (dxUs * dxUs) * d.stress12U[s]));
     const double strinty = fac * (0.5 * dxE * (d.stresspU[c] - d.stresspU[s]) -
                                   (0.5 / dxE) * ((dxUc * dxUc) * d.stressmU[c] - (dxUs * dxUs) * d.stressmU[s]) +
                                   (1.0 / dyE) * ((dyTe * dyTe) * d.stress12T[e] - (dyTc * dyTc) * d.stress12T[c]));
@@ -563,8 +563,8 @@ __global__ void __launch_bounds__(256) kcd3_momentum(const __grid_constant__ CDo
                                   (0.5 / dyN) * ((dyUc * dyUc) * d.stressmU[c] - (dyUw * dyUw) * d.stressmU[w]) +
                                   (1.0 / dxN) * ((dxTn * dxTn) * d.stress12T[n] - (dxTc * dxTc) * d.stress12T[c]));
     const double strinty = fac * (0.5 * dxN * (d.stresspT[n] - d.stresspT[c]) -
-                                  (0.5 / dxN) * ((dxTn * dxTn) * d.stressmT[n] - (dxTc * dxTc) * d.stressmT[c]) +
-                                  (1.0 / dyN) * ((dyUc * dyUc) * d.stress12U[c] - (dyUw * dyUw) * d.stress12U[w]));
+                                  d.rhalf_dxN[c] * ((dxTn * dxTn) * d.stressmT[n] - (dxTc * dxTc) * d.stressmT[c]) +
+                                  d.r_dyN[c] * ((dyUc * dyUc) * d.stress12U[c] - (dyUw * dyUw) * d.stress12U[w]));
     d.strintxN[c] = strintx;
     d.strintyN[c] = strinty;
     double un, vn, tbx, tby;
