@@ -153,6 +153,8 @@ struct Ctx {
   bool cinit = false;
   CDom cdom{};
   std::vector<double *> dbuf;      // deformations: dxU, dyU, tarear + 5 outputs
+  std::vector<double *> dstage;    // their own block-layout staging (g.stage still holds the fields of an upload that a later
+                                   // evp_b200_download builds on)
   std::vector<double *> cbuf;      // every C-grid device array (freed together)
   std::vector<double *> cstage;    // staging, one per C field
   std::vector<double *> cdstage;   // staging, one per CD field
@@ -213,6 +215,7 @@ static int free_all() {
   g.p2p.release();
   for (auto &p : g.cbuf) F(p);
   for (auto &p : g.dbuf) F(p);
+  for (auto &p : g.dstage) F(p);
   for (auto &p : g.cstage) F(p);
   for (auto &p : g.cdstage) F(p);
   for (auto &p : g.cmask) F(p);
@@ -774,20 +777,23 @@ static int do_deformations(evp_b200_deform_t *dd) {
       double *p = nullptr;
       CK(cudaMalloc(&p, g.ndom * sizeof(double)));
       g.dbuf.push_back(p);
+      double *st = nullptr;
+      CK(cudaMalloc(&st, bblk));
+      g.dstage.push_back(st);
     }
   }
   const double *src[8] = {dd->dxU, dd->dyU, dd->tarear, dd->divu, dd->shear, dd->vort, dd->rdg_conv, dd->rdg_shear};
   double *dst[5] = {dd->divu, dd->shear, dd->vort, dd->rdg_conv, dd->rdg_shear};
   for (int q = 0; q < 8; ++q) {
-    CK(cudaMemcpyAsync(g.stage[q], src[q], bblk, cudaMemcpyHostToDevice, g.stream));
-    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(g.dbuf[q], g.stage[q], g.d_gsrc, (int)g.ndom);
+    CK(cudaMemcpyAsync(g.dstage[q], src[q], bblk, cudaMemcpyHostToDevice, g.stream));
+    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(g.dbuf[q], g.dstage[q], g.d_gsrc, (int)g.ndom);
   }
   // the exact build: the reference's `deformations` has no contraction-sensitive state, but keep one answer
   CK(exact::launch_deform(g.dom, g.cur, g.dbuf[0], g.dbuf[1], g.dbuf[2], g.dbuf[3], g.dbuf[4], g.dbuf[5], g.dbuf[6], g.dbuf[7],
                           dd->e_factor, g.stream));
   for (int q = 0; q < 5; ++q) {
-    unpack_f64<<<grid_blocks(g.n_sig), 256, 0, g.stream>>>(g.stage[3 + q], g.dbuf[3 + q], g.d_sig_lin, g.d_sig_dom, g.n_sig);
-    CK(cudaMemcpyAsync(dst[q], g.stage[3 + q], bblk, cudaMemcpyDeviceToHost, g.stream));
+    unpack_f64<<<grid_blocks(g.n_sig), 256, 0, g.stream>>>(g.dstage[3 + q], g.dbuf[3 + q], g.d_sig_lin, g.d_sig_dom, g.n_sig);
+    CK(cudaMemcpyAsync(dst[q], g.dstage[3 + q], bblk, cudaMemcpyDeviceToHost, g.stream));
   }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(g.stream));
@@ -810,14 +816,19 @@ static int do_init_cgrid(const evp_b200_cgrid_t *cg) {
                            cg->earear, cg->narear, cg->ratiodxN, cg->ratiodxNr, cg->ratiodyE, cg->ratiodyEr, cg->hm, cg->uvm, cg->epm, cg->npm};
   const double **dst[20] = {&c.dxN, &c.dyE, &c.dxE, &c.dyN, &c.dxU, &c.dyU, &c.tarea, &c.uarea, &c.earea, &c.narea,
                             &c.earear, &c.narear, &c.ratiodxN, &c.ratiodxNr, &c.ratiodyE, &c.ratiodyEr, &c.hm, &c.uvm, &c.epm, &c.npm};
+  double *scratch = nullptr;
+  CK(cudaMalloc(&scratch, bblk));
   for (int q = 0; q < 20; ++q) {
-    if (!src[q]) return fail("evp_b200_init_cgrid: null geometry array %d", q);
+    if (!src[q]) { cudaFree(scratch); return fail("evp_b200_init_cgrid: null geometry array %d", q); }
     double *p = nullptr;
     if (calloc_dom(p)) return 1;
-    CK(cudaMemcpyAsync(g.stage[q % NF_STEP], src[q], bblk, cudaMemcpyHostToDevice, g.stream));
-    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(p, g.stage[q % NF_STEP], g.d_gsrc, (int)g.ndom);
+    // scratch staging of its own (freed below): g.stage may hold an upload that a later evp_b200_download builds on
+    CK(cudaMemcpyAsync(scratch, src[q], bblk, cudaMemcpyHostToDevice, g.stream));
+    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(p, scratch, g.d_gsrc, (int)g.ndom);
     *dst[q] = p;
   }
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaFree(scratch));
   c.dxT = g.dom.dxT; c.dyT = g.dom.dyT; c.DminTarea = g.dom.DminTarea;
   {
     double *q[5] = {};

@@ -418,3 +418,24 @@ def test_gpu_matches_vectors_from_reference_source(evp_lib, kernel):
     the C oracle in between: bit for bit, every kernel strategy."""
     from tests.test_oracle import check_against_ref_source_vectors
     check_against_ref_source_vectors(lambda c: run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=kernel))
+
+
+def test_deformations_between_subcycle_and_download(oracle_mod, evp_lib):
+    """the split API in the order a device-resident caller uses it: upload, subcycle, deformations, THEN download -- the
+    deformations call must not disturb what the download builds on (cells the loop does not own keep the uploaded values)."""
+    c = synth.make_case("tiny", seed=111, ndte=7, block_size=(12, 10))
+    ref = run_oracle(oracle_mod, c)
+    X = c.X
+    tarear = np.where(X["tarea"] > 0, 1.0 / np.where(X["tarea"] > 0, X["tarea"], 1.0), 0.0)
+    d = dict({n: synth.scatter(a, c.blocks) for n, a in (("dxU", X["dxU"]), ("dyU", X["dyU"]), ("tarear", tarear))},
+             **{n: np.full(ref["uvel"].shape, -7.0) for n in abi.DEFORM_OUT})
+    f = c.copy_fields()
+    evp_lib.dyn_evp_b200_init(c.grid)
+    try:
+        evp_lib.upload(f)
+        evp_lib.subcycle(dict(c.params, mode=abi.MODE_EXACT))
+        evp_lib.deformations(d, c.params["e_factor"])
+        evp_lib.download(f)
+    finally:
+        evp_lib.dyn_evp_b200_finalize()
+    assert_bitwise(f, ref)
