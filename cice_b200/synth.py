@@ -349,6 +349,7 @@ def global_state(nx, ny, dx0, ew, ns, kmt="boxislands", dt=3600.0, deltaminEVP=1
     X["uocnU"], X["vocnU"] = ext_u(uocnU), ext_u(vocnU)
     X["uvel"], X["vvel"] = ext_u(uvel_i, True), ext_u(vvel_i, True)
     X["strax"], X["stray"], X["uocn"], X["vocn"], X["umass_i"] = strax, stray, uocn, vocn, umass
+    X["strairxU_i"], X["strairyU_i"] = strairxU, strairyU   # interior arrays: dyn_prep2 inputs (tests/golden/ref_translit.py)
     X["TbU"] = np.zeros((ny + 2, nx + 2))
 
     # Hibler strength at ice T cells, then halo: ice_dyn_evp.F90:540-550, 727-728

@@ -107,7 +107,8 @@ TOK = re.compile(r"""\s*(?:
   | (?P<op>\*\*|==|/=|<=|>=|[-+*/(),<>=:%])
 )""", re.X | re.I)
 
-INTRINSICS = {"sqrt": "math.sqrt", "max": "max", "min": "min", "abs": "abs", "sign": "_sign", "trim": "_trim", "real": "float"}
+INTRINSICS = {"sqrt": "math.sqrt", "max": "max", "min": "min", "abs": "abs", "sign": "_sign", "trim": "_trim", "real": "float",
+              "present": "_present"}
 REL = {"==": "==", "/=": "!=", "<": "<", ">": ">", "<=": "<=", ">=": ">=",
        ".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">="}
 
@@ -874,6 +875,56 @@ def generate_d():
     return {f"dcase0_{k}": v for k, v in out.items()}
 
 
+# ------------------------------------------------------------------------------------------
+# dyn_prep2 (ice_dyn_shared.F90:593-839): the routine that builds every time-varying input of the loop.  Run on the
+# synthetic state, it must reproduce what cice_b200/synth.py feeds the kernels and the bench (SURVEY 8d inputs).
+# ------------------------------------------------------------------------------------------
+PFIELDS = ("umassdti", "fmU", "waterxU", "wateryU", "forcexU", "forceyU", "uvel", "vvel", "iceUmask")
+
+
+def generate_prep2(config="tiny"):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from cice_b200 import synth
+    c = synth.make_case(config)           # set S1: the box2001 start, exactly what bench.py uses
+    X, g = c.X, c.grid
+    nxb, nyb = g["nx_block"], g["ny_block"]
+    ilo, ihi, jlo, jhi = (int(g[k][0]) for k in ("ilo", "ihi", "jlo", "jhi"))
+    reg = {}
+    reg["dyn_prep2"] = Sub(F_SHARED, "dyn_prep2", reg)
+    env = {"math": math, "_sq": lambda x: x * x, "_sign": lambda a, b: math.copysign(abs(a), b), "_trim": lambda s: s.strip(),
+           "_present": lambda x: x is not None, "_alloc": lambda nx, ny: FArr(np.zeros((ny, nx))), "ICEPACK": {"gravit": 9.80616},
+           "ssh_stress": "geostrophic", "dyn_area_min": 1e-11, "dyn_mass_min": 1e-10, "rheo_area_min": 1e-11, "cosw": 1.0, "sinw": 0.0}
+    env.update(reference_constants())
+    exec(compile(reg["dyn_prep2"].python(), f"<dyn_prep2 transliterated from {REF}>", "exec"), env)
+
+    def ext(a):   # interior (ny,nx) array -> block array with zero ghosts
+        out = np.zeros((nyb, nxb))
+        out[jlo - 1:jhi, ilo - 1:ihi] = a
+        return out
+
+    Z = lambda: np.zeros((nyb, nxb))
+    aiX, Xmass = X["aiU"].copy(), ext(X["umass_i"])
+    fcor = np.full((nyb, nxb), synth.FCOR_CONST)
+    Xmask = (X["uvm"] > 0.5).astype(np.float64)
+    out = {k: Z() for k in ("Xmassdti", "fm", "strtltx", "strtlty", "strocnx", "strocny", "strintx", "strinty", "taubx", "tauby",
+                            "waterx", "watery", "forcex", "forcey", "uvel_init", "vvel_init", "uvel", "vvel", "TbU", "iceXmask")}
+    sig = [Z() for _ in range(12)]
+    A = FArr
+    n = nxb * nyb
+    env["dyn_prep2"](nxb, nyb, ilo, ihi, jlo, jhi, None, None, A(np.zeros(n, int)), A(np.zeros(n, int)), A(np.zeros(n, int)), A(np.zeros(n, int)),
+                     A(aiX), A(Xmass), A(out["Xmassdti"]), A(fcor), A(Xmask), A(X["uocnU"].copy()), A(X["vocnU"].copy()),
+                     A(ext(X["strairxU_i"])), A(ext(X["strairyU_i"])), A(Z()), A(Z()), A(X["iceTmask"].astype(np.float64)), A(out["iceXmask"]),
+                     A(out["fm"]), 3600.0, A(out["strtltx"]), A(out["strtlty"]), A(out["strocnx"]), A(out["strocny"]), A(out["strintx"]),
+                     A(out["strinty"]), A(out["taubx"]), A(out["tauby"]), A(out["waterx"]), A(out["watery"]), A(out["forcex"]), A(out["forcey"]),
+                     *[A(a) for a in sig], A(out["uvel_init"]), A(out["vvel_init"]), A(out["uvel"]), A(out["vvel"]), A(out["TbU"]), None)
+    names = {"umassdti": "Xmassdti", "fmU": "fm", "waterxU": "waterx", "wateryU": "watery", "forcexU": "forcex", "forceyU": "forcey",
+             "uvel": "uvel", "vvel": "vvel", "iceUmask": "iceXmask"}
+    inner = (slice(jlo - 1, jhi), slice(ilo - 1, ihi))
+    ref = {k: out[v][inner].copy() for k, v in names.items()}
+    mine = {k: np.asarray(X[k], dtype=np.float64)[inner] for k in names}
+    return ref, mine
+
+
 FULL_VECTORS = (0, 1, 3)   # cases whose arrays are committed in full; every case is committed as sha256 per field
 FULL_CVECTORS = (0, 2)
 FULL_CDVECTORS = (0, 2)
@@ -891,6 +942,10 @@ if __name__ == "__main__":
     cvec = generate_c()
     dvec = generate_d()
     cdvec = generate_cd()
+    pvec = {}
+    for cfg in ("tiny", "gx3", "gx1"):
+        pref, _ = generate_prep2(cfg)
+        pvec.update({f"prep2_{cfg}_{k}": v for k, v in pref.items()})
     if "--write" in sys.argv:
         full = {k: v for k, v in vec.items() if int(k[4:k.index("_")]) in FULL_VECTORS}
         full.update({k: v for k, v in cvec.items() if int(k[5:k.index("_")]) in FULL_CVECTORS})
@@ -903,7 +958,7 @@ if __name__ == "__main__":
                         "div_stress_Ey/Nx, stepuv_CD; deformations; ice_constants -- and runs them; see the module docstring)",
                 "cases": [dict(kw) for kw in CASES], "ccases": [dict(kw) for kw in CCASES],
                 "cdcases": [dict(kw) for kw in CDCASES],
-                "sha256": {k: sha(v) for k, v in {**vec, **cvec, **dvec, **cdvec}.items()}}
+                "sha256": {k: sha(v) for k, v in {**vec, **cvec, **dvec, **cdvec, **pvec}.items()}}
         json.dump(meta, open(SHA, "w"), indent=1)
         print("wrote", OUT, os.path.getsize(OUT), "bytes;", SHA)
     if "--show" in sys.argv:

@@ -266,3 +266,20 @@ def test_deformations_oracle_matches_vectors_from_reference_source(oracle_mod):
     for k in rt.DFIELDS:
         assert np.array_equal(got[k].view(np.int64), full[f"dcase0_{k}"].view(np.int64)), k
         assert _sha(got[k]) == meta["sha256"][f"dcase0_{k}"], k
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "gx3", "gx1"])
+def test_synthetic_inputs_follow_reference_dyn_prep2(cfg):
+    """the loop's time-varying inputs (umassdti, fmU, waterx/y, forcex/y, the U ice mask, new-ice velocities) that
+    cice_b200/synth.py produces for tests and bench are, bit for bit, what the reference's own dyn_prep2
+    (ice_dyn_shared.F90:593-839, transliterated and executed by tests/golden/ref_translit.py) makes of the same box2001 state."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ref_translit as rt
+    meta, _ = _ref_source_vectors()
+    c = synth.make_case(cfg)
+    g = c.grid
+    inner = (slice(int(g["jlo"][0]) - 1, int(g["jhi"][0])), slice(int(g["ilo"][0]) - 1, int(g["ihi"][0])))
+    for k in rt.PFIELDS:
+        mine = np.asarray(c.X[k], dtype=np.float64)[inner]
+        assert _sha(mine) == meta["sha256"][f"prep2_{cfg}_{k}"], k
