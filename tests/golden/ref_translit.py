@@ -332,9 +332,11 @@ class Sub:
             low = ln.lower().strip()
             if "icepack_warnings" in low:
                 continue                                   # diagnostics plumbing, not arithmetic
-            m = re.match(r"^call\s+icepack_query_parameters\s*\(\s*(\w+)_out\s*=\s*(\w+)\s*\)$", ln.strip(), re.I)
+            m = re.match(r"^call\s+icepack_query_parameters\s*\((.*)\)$", ln.strip(), re.I)
             if m:
-                emit(f"{m.group(2).lower()} = ICEPACK[{m.group(1).lower()!r}]")
+                for kw in split_top(m.group(1)):
+                    mm = re.match(r"^(\w+)_out\s*=\s*(\w+)$", kw.strip(), re.I)
+                    emit(f"{mm.group(2).lower()} = ICEPACK[{mm.group(1).lower()!r}]")
                 continue
             m = re.match(r"^do\s+(\w+)\s*=\s*(.+)$", ln.strip(), re.I)
             if m:
@@ -925,6 +927,46 @@ def generate_prep2(config="tiny"):
     return ref, mine
 
 
+def generate_prep1_and_averages(config="tiny"):
+    """dyn_prep1 (ice_dyn_shared.F90:496-592) and the T->U averages evp() takes before dyn_prep2 (ice_dyn_evp.F90:433-456:
+    grid_average_X2Y 'S' for aice, tmass, uocn, vocn; 'F' for the wind stress), run on the synthetic box2001 state."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from cice_b200 import synth
+    c = synth.make_case(config)
+    X, g = c.X, c.grid
+    nxb, nyb = g["nx_block"], g["ny_block"]
+    blk = _Block()
+    blk.ilo, blk.ihi, blk.jlo, blk.jhi = (int(g[k][0]) for k in ("ilo", "ihi", "jlo", "jhi"))
+    reg = {}
+    for path, name in ((F_SHARED, "dyn_prep1"), (F_GRID, "grid_average_X2YS"), (F_GRID, "grid_average_X2YF")):
+        reg[name] = Sub(path, name, reg)
+    env = {"math": math, "_sq": lambda x: x * x, "_trim": lambda s: s.strip(), "_alloc": lambda nx, ny: FArr(np.zeros((ny, nx))),
+           "ICEPACK": {"rhoi": synth.RHOI, "rhos": synth.RHOS}, "dyn_area_min": 1e-11, "dyn_mass_min": 1e-10, "nblocks": 1,
+           "get_block": lambda iblk: blk}
+    env.update(reference_constants())
+    env = {k.lower() if k != "ICEPACK" else k: v for k, v in env.items()}
+    for nm in ("dyn_prep1", "grid_average_X2YS", "grid_average_X2YF"):
+        exec(compile(reg[nm].python(), f"<{nm} transliterated from {REF}>", "exec"), env)
+    tmass, iceT = np.zeros((nyb, nxb)), np.zeros((nyb, nxb))
+    env["dyn_prep1"](nxb, nyb, blk.ilo, blk.ihi, blk.jlo, blk.jhi, FArr(X["aice"].copy()), FArr(X["vice"].copy()), FArr(np.zeros((nyb, nxb))),
+                     FArr((X["hm"] > 0.5).astype(np.float64)), FArr(tmass), FArr(iceT))
+    inner = (slice(blk.jlo - 1, blk.jhi), slice(blk.ilo - 1, blk.ihi))
+    ref = {"tmass": tmass, "iceTmask_interior": iceT[inner].copy()}
+    mine = {"tmass": X["tmass"], "iceTmask_interior": X["iceTmask"].astype(np.float64)[inner]}
+    A3 = lambda a: FArr(np.ascontiguousarray(np.asarray(a, dtype=np.float64))[None, :, :])
+    for out, src in (("aiU", "aice"), ("umass_i", "tmass"), ("uocnU", "uocn"), ("vocnU", "vocn")):
+        w2 = np.zeros((1, nyb, nxb))
+        env["grid_average_x2ys"]("NE", A3(X[src]), A3(X["tarea"]), A3(X["hm"]), FArr(w2))        # T2US, ice_grid.F90:3984
+        ref[out] = w2[0][inner].copy()
+        mine[out] = np.asarray(X[out], dtype=np.float64)[inner] if X[out].shape == (nyb, nxb) else np.asarray(X[out])
+    for out, src in (("strairxU_i", "strax"), ("strairyU_i", "stray")):
+        w2 = np.zeros((1, nyb, nxb))
+        env["grid_average_x2yf"]("NE", A3(X[src]), A3(X["tarea"]), FArr(w2), A3(X["uarea"]))       # T2UF, ice_grid.F90:3958
+        ref[out] = w2[0][inner].copy()
+        mine[out] = np.asarray(X[out])
+    return ref, mine
+
+
 FULL_VECTORS = (0, 1, 3)   # cases whose arrays are committed in full; every case is committed as sha256 per field
 FULL_CVECTORS = (0, 2)
 FULL_CDVECTORS = (0, 2)
@@ -946,6 +988,8 @@ if __name__ == "__main__":
     for cfg in ("tiny", "gx3", "gx1"):
         pref, _ = generate_prep2(cfg)
         pvec.update({f"prep2_{cfg}_{k}": v for k, v in pref.items()})
+        qref, _ = generate_prep1_and_averages(cfg)
+        pvec.update({f"prep1_{cfg}_{k}": np.asarray(v, dtype=np.float64) for k, v in qref.items()})
     if "--write" in sys.argv:
         full = {k: v for k, v in vec.items() if int(k[4:k.index("_")]) in FULL_VECTORS}
         full.update({k: v for k, v in cvec.items() if int(k[5:k.index("_")]) in FULL_CVECTORS})

@@ -283,3 +283,19 @@ def test_synthetic_inputs_follow_reference_dyn_prep2(cfg):
     for k in rt.PFIELDS:
         mine = np.asarray(c.X[k], dtype=np.float64)[inner]
         assert _sha(mine) == meta["sha256"][f"prep2_{cfg}_{k}"], k
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "gx3", "gx1"])
+def test_synthetic_inputs_follow_reference_prep1_and_averages(cfg):
+    """the stage before dyn_prep2: dyn_prep1 (tmass, iceTmask; ice_dyn_shared.F90:496-592) and evp()'s T->U averages
+    (grid_average_X2YS 'NE' of aice, tmass, uocn, vocn; grid_average_X2YF 'NE' of the wind stress; ice_dyn_evp.F90:433-456) as
+    cice_b200/synth.py computes them == the transliterated reference routines on the same box2001 state, bit for bit."""
+    meta, _ = _ref_source_vectors()
+    c = synth.make_case(cfg)
+    g, X = c.grid, c.X
+    inner = (slice(int(g["jlo"][0]) - 1, int(g["jhi"][0])), slice(int(g["ilo"][0]) - 1, int(g["ihi"][0])))
+    mine = {"tmass": X["tmass"], "iceTmask_interior": X["iceTmask"].astype(np.float64)[inner], "aiU": X["aiU"][inner],
+            "umass_i": X["umass_i"], "uocnU": X["uocnU"][inner], "vocnU": X["vocnU"][inner], "strairxU_i": X["strairxU_i"],
+            "strairyU_i": X["strairyU_i"]}
+    for k, v in mine.items():
+        assert _sha(v) == meta["sha256"][f"prep1_{cfg}_{k}"], k
