@@ -35,13 +35,15 @@ def test_struct_layouts_match_header():
     assert C.sizeof(abi.Fields) == 32 * 8
     assert C.sizeof(abi.CGrid) == 20 * 8
     assert C.sizeof(abi.CFields) == 47 * 8
+    assert C.sizeof(abi.CDFields) == 58 * 8
     txt = open(os.path.join(ROOT, "include", "evp_b200.h")).read()
     body = txt[txt.index("typedef struct {", txt.index("Time-varying fields of one call")):txt.index("} evp_b200_fields_t;")]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = re.findall(r"\*\s*([A-Za-z_0-9]+)", body)
     assert tuple(names) == abi.FIELDS_ORDER + abi.FIELDS_MASK
     for start, end, want in (("Extra static geometry of grid_ice", "} evp_b200_cgrid_t;", abi.CGRID_STATIC),
-                             ("Time-varying fields of one C-grid call", "} evp_b200_cfields_t;", abi.CFIELDS_ORDER + abi.CFIELDS_MASK)):
+                             ("Time-varying fields of one C-grid call", "} evp_b200_cfields_t;", abi.CFIELDS_ORDER + abi.CFIELDS_MASK),
+                             ("CD grid (SURVEY 8a row a13", "} evp_b200_cdfields_t;", abi.CDFIELDS_ORDER + abi.CFIELDS_MASK)):
         body = txt[txt.index("typedef struct {", txt.index(start)):txt.index(end)]
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         assert tuple(re.findall(r"\*\s*([A-Za-z_0-9]+)", body)) == want, start
