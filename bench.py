@@ -295,9 +295,10 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             bs = (40, 48) if args.workload == "gx1" else (max(base["nx"] // 8, 8), max(base["ny"] // 8, 8))
             ccase = synth.make_case(args.workload, block_size=bs)
-            sec, nth = cpu_baseline(ccase, 2, 1)
+            ncpu = 12 if args.workload in ("gx1", "gx3", "tx1") else 2   # ~3 s of wall time on 16 threads at gx1 (~50 core-seconds)
+            sec, nth = cpu_baseline(ccase, ncpu, 1)
             line["cpu_baseline"] = {"value": per_gpu_cells * ndte / sec, "unit": UNIT, "cores": nth, "kind": "port",
-                                    "sample": f"2 full dynamics steps of {args.workload} (ndte={ndte}), blocks {bs[0]}x{bs[1]}, "
+                                    "sample": f"{ncpu} full dynamics steps of {args.workload} (ndte={ndte}), blocks {bs[0]}x{bs[1]}, "
                                               f"{sec:.3f} s each"}
         print(json.dumps(line))
     if world > 1:
