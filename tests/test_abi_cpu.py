@@ -115,3 +115,29 @@ def test_rank_view_partitions_blocks():
         seen[ids] += 1
         assert g["nblocks"] == 4 and f["uvel"].shape[0] == 4
     assert (seen == 1).all()
+
+
+def test_fortran_shim_types_match_the_header():
+    """fortran/ice_dyn_evp_b200.F90 cannot be compiled here (no Fortran compiler), so at least its bind(C) derived types must
+    list the members of the C structs in include/evp_b200.h in the same order (a swapped pair would be silent corruption)."""
+    txt = open(os.path.join(ROOT, "fortran", "ice_dyn_evp_b200.F90")).read()
+
+    def members(tname):
+        m = re.search(rf"type,\s*bind\(C\)\s*::\s*{tname}\b(.*?)end type {tname}", txt, flags=re.S | re.I)
+        assert m, tname
+        names = []
+        for line in m.group(1).splitlines():
+            line = line.split("!")[0]
+            if "::" in line:
+                names += [n.strip() for n in line.split("::", 1)[1].split(",") if n.strip()]
+        return tuple(names)
+
+    assert members("evp_b200_fields_t") == abi.FIELDS_ORDER + abi.FIELDS_MASK
+    assert members("evp_b200_cgrid_t") == abi.CGRID_STATIC
+    assert members("evp_b200_cfields_t") == abi.CFIELDS_ORDER + abi.CFIELDS_MASK
+    assert members("evp_b200_grid_t") == tuple(n for n, _ in abi.Grid._fields_)
+    assert members("evp_b200_params_t") == tuple(n for n, _ in abi.Params._fields_)
+    # every C entry point the shim binds exists in the header
+    hdr = open(os.path.join(ROOT, "include", "evp_b200.h")).read()
+    for name in re.findall(r"bind\(C,\s*name='(\w+)'\)", txt):
+        assert re.search(rf"\b{name}\s*\(", hdr), name
