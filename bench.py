@@ -292,6 +292,11 @@ def run_ours(args):
                              "algorithmic_bytes_per_cell_subcycle": ALGO_BYTES_PER_CELL_SUBCYCLE,
                              "kernel_ms_per_step": kernel_ms, "subcycles_per_launch": sub_per_launch},
                 "wall_s": t_wall}
+        # the active-cell rate beside R (T cells that carry ice; rank 0's sub-domain, the same on every rank up to the
+        # synthetic ice edge)
+        act = int(np.count_nonzero(np.asarray(fields["iceTmask"])[:, 1:-1, 1:-1]))
+        line["active_cells"] = {"icellT_rank0": act, "fraction_rank0": act / float(per_gpu_cells),
+                                "active_cell_subcycles_per_s": value * act / float(per_gpu_cells)}
         if world == 1 and not args.no_cpu:
             bs = (40, 48) if args.workload == "gx1" else (max(base["nx"] // 8, 8), max(base["ny"] // 8, 8))
             ccase = synth.make_case(args.workload, block_size=bs)
