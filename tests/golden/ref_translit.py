@@ -262,6 +262,7 @@ def tr_expr(s, arrays=()):
 # ------------------------------------------------------------------------------------------
 # subroutine translator
 # ------------------------------------------------------------------------------------------
+STUBS = {"ice_haloupdate"}
 DECL = re.compile(r"^\s*(integer|real|logical|character|type)\b", re.I)
 
 
@@ -416,6 +417,11 @@ class Sub:
             m = re.match(r"^call\s+(\w+)\s*\((.*)\)$", ln.strip(), re.I)
             if m:
                 actual = split_top(m.group(2))
+                if m.group(1).lower() in STUBS:       # e.g. the MPI halo: done by the driver, not by the transliterated text
+                    emit("pass")
+                    if one_line:
+                        ind -= 1
+                    continue
                 if m.group(1) not in self.registry:   # a routine this script does not transliterate (never reached by the driver)
                     emit(f"raise RuntimeError('{m.group(1)} is not transliterated')")
                     if one_line:
@@ -967,6 +973,49 @@ def generate_prep1_and_averages(config="tiny"):
     return ref, mine
 
 
+# ------------------------------------------------------------------------------------------
+# static geometry of the B-grid loop: the tail of init_dyn_shared (ice_dyn_shared.F90), from the
+# `grid_ice == 'B'` block that fills dxhy, dyhx to the loops that fill cyp, cxp, cym, cxm
+# ------------------------------------------------------------------------------------------
+def generate_geometry(config="tiny"):
+    import tempfile
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from cice_b200 import synth
+    global REF
+    lines = open(os.path.join(REF, F_SHARED)).read().splitlines()
+    a = next(n for n, ln in enumerate(lines) if "grid_ice == 'B' .and. evp_algorithm" in ln and "if" in ln.lower()
+             and n > next(k for k, l2 in enumerate(lines) if re.match(r"^\s*subroutine\s+init_dyn_shared\b", l2, re.I)))
+    b = next(n for n, ln in enumerate(lines) if re.match(r"^\s*end\s+subroutine\s+init_dyn_shared\b", ln, re.I))
+    text = "      subroutine geom_tail ()\n" + "\n".join(lines[a:b]) + "\n      end subroutine geom_tail\n"
+    c = synth.make_case(config)
+    X, g = c.X, c.grid
+    blk = _Block()
+    blk.ilo, blk.ihi, blk.jlo, blk.jhi = (int(g[k][0]) for k in ("ilo", "ihi", "jlo", "jhi"))
+    shape = (1,) + X["HTE"].shape
+    out = {k: np.zeros(shape) for k in ("dxhy", "dyhx", "cyp", "cxp", "cym", "cxm")}
+    env = {"grid_ice": "B", "evp_algorithm": "standard_2d", "nblocks": 1, "get_block": lambda iblk: blk,
+           "hte": FArr(X["HTE"][None].copy()), "htn": FArr(X["HTN"][None].copy()), **{k: FArr(v) for k, v in out.items()}}
+    env.update(reference_constants())
+    env = {k.lower(): v for k, v in env.items()}
+    with tempfile.TemporaryDirectory() as tmp:
+        open(os.path.join(tmp, "g.F90"), "w").write(text)
+        keep, REF = REF, tmp
+        try:
+            sub = Sub("g.F90", "geom_tail", {})
+        finally:
+            REF = keep
+    sub.arrays |= {"hte", "htn", "dxhy", "dyhx", "cyp", "cxp", "cym", "cxm"}
+    exec(compile(sub.python(), "<tail of init_dyn_shared transliterated>", "exec"), env)
+    env["geom_tail"]()
+    i0_, i1_, j0_, j1_ = blk.ilo - 1, blk.ihi, blk.jlo - 1, blk.jhi
+    ref = {"dxhy": out["dxhy"][0][j0_:j1_, i0_:i1_], "dyhx": out["dyhx"][0][j0_:j1_, i0_:i1_]}
+    mine = {"dxhy": X["dxhy"][j0_:j1_, i0_:i1_], "dyhx": X["dyhx"][j0_:j1_, i0_:i1_]}
+    for k in ("cyp", "cxp", "cym", "cxm"):          # filled on ilo:ihi+1, jlo:jhi+1
+        ref[k] = out[k][0][j0_:j1_ + 1, i0_:i1_ + 1]
+        mine[k] = X[k][j0_:j1_ + 1, i0_:i1_ + 1]
+    return ref, mine
+
+
 FULL_VECTORS = (0, 1, 3)   # cases whose arrays are committed in full; every case is committed as sha256 per field
 FULL_CVECTORS = (0, 2)
 FULL_CDVECTORS = (0, 2)
@@ -990,6 +1039,8 @@ if __name__ == "__main__":
         pvec.update({f"prep2_{cfg}_{k}": v for k, v in pref.items()})
         qref, _ = generate_prep1_and_averages(cfg)
         pvec.update({f"prep1_{cfg}_{k}": np.asarray(v, dtype=np.float64) for k, v in qref.items()})
+        gref, _ = generate_geometry(cfg)
+        pvec.update({f"geom_{cfg}_{k}": np.ascontiguousarray(v) for k, v in gref.items()})
     if "--write" in sys.argv:
         full = {k: v for k, v in vec.items() if int(k[4:k.index("_")]) in FULL_VECTORS}
         full.update({k: v for k, v in cvec.items() if int(k[5:k.index("_")]) in FULL_CVECTORS})

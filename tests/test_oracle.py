@@ -299,3 +299,17 @@ def test_synthetic_inputs_follow_reference_prep1_and_averages(cfg):
             "strairyU_i": X["strairyU_i"]}
     for k, v in mine.items():
         assert _sha(v) == meta["sha256"][f"prep1_{cfg}_{k}"], k
+
+
+@pytest.mark.parametrize("cfg", ["tiny", "gx3", "gx1"])
+def test_synthetic_geometry_follows_reference_init_dyn_shared(cfg):
+    """dxhy, dyhx, cyp, cxp, cym, cxm as cice_b200/synth.py derives them from HTE/HTN == the tail of the reference's
+    init_dyn_shared (ice_dyn_shared.F90:401-441), transliterated and executed on the same HTE/HTN, bit for bit."""
+    meta, _ = _ref_source_vectors()
+    c = synth.make_case(cfg)
+    g, X = c.grid, c.X
+    i0, i1, j0, j1 = int(g["ilo"][0]) - 1, int(g["ihi"][0]), int(g["jlo"][0]) - 1, int(g["jhi"][0])
+    for k in ("dxhy", "dyhx"):
+        assert _sha(X[k][j0:j1, i0:i1]) == meta["sha256"][f"geom_{cfg}_{k}"], k
+    for k in ("cyp", "cxp", "cym", "cxm"):
+        assert _sha(X[k][j0:j1 + 1, i0:i1 + 1]) == meta["sha256"][f"geom_{cfg}_{k}"], k
