@@ -202,6 +202,8 @@ class Expr:
                 raise SyntaxError("negative exponent not supported")
             if b in ("2", "2.0"):
                 return f"_sq({a})"     # x**2 is x*x in every Fortran compiler; Python's pow() is not guaranteed to be
+            if b in ("4", "4.0"):
+                return f"_sq(_sq({a}))"  # x**4 = (x*x)*(x*x) by repeated squaring
             raise SyntaxError(f"exponent {b} not supported")
         return a
 
@@ -325,14 +327,19 @@ class Sub:
 
         def emit(s):
             src.append("    " * ind + s)
+            if s.endswith(":"):                      # a block whose statements are all skipped must not be empty
+                src.append("    " * (ind + 1) + "pass")
 
+        if getattr(self, "module_vars", None):
+            emit("global " + ", ".join(self.module_vars))     # module variables the routine assigns
         for nm, dims in self.local_arrays:
             emit(f"{nm} = _alloc({', '.join(tr_expr(d, self.arrays) for d in dims)})")
 
         for ln in self.body:
             low = ln.lower().strip()
-            if "icepack_warnings" in low:
+            if "icepack_warnings" in low or re.match(r"^write\s*\(", low):
                 continue                                   # diagnostics plumbing, not arithmetic
+            ln = re.sub(r",\s*kind\s*=\s*\w+\s*\)", ")", ln)   # real(ndte,kind=dbl_kind) -> real(ndte)
             m = re.match(r"^call\s+icepack_query_parameters\s*\((.*)\)$", ln.strip(), re.I)
             if m:
                 for kw in split_top(m.group(1)):
@@ -1014,6 +1021,21 @@ def generate_geometry(config="tiny"):
         ref[k] = out[k][0][j0_:j1_ + 1, i0_:i1_ + 1]
         mine[k] = X[k][j0_:j1_ + 1, i0_:i1_ + 1]
     return ref, mine
+
+
+# ------------------------------------------------------------------------------------------
+# EVP constants: set_evp_parameters (ice_dyn_shared.F90:453-486)
+# ------------------------------------------------------------------------------------------
+def generate_params(ndte, revised_evp, elasticDamp=0.36, e_yieldcurve=2.0, e_plasticpot=2.0, arlx=300.0, brlx=300.0):
+    reg = {}
+    sub = Sub(F_SHARED, "set_evp_parameters", reg)
+    sub.module_vars = ["dtei", "epp2i", "e_factor", "ecci", "revp", "denom1", "arlx1i", "arlx", "brlx"]
+    env = {"ndte": int(ndte), "revised_evp": bool(revised_evp), "elasticdamp": elasticDamp, "e_yieldcurve": e_yieldcurve,
+           "e_plasticpot": e_plasticpot, "arlx": arlx, "brlx": brlx, "my_task": 1, "master_task": 0, "_sq": lambda x: x * x}
+    env.update({k.lower(): v for k, v in reference_constants().items()})
+    exec(compile(sub.python(), "<set_evp_parameters transliterated>", "exec"), env)
+    env["set_evp_parameters"](3600.0)
+    return {k: float(env[k]) for k in ("epp2i", "e_factor", "revp", "denom1", "arlx1i", "brlx")}
 
 
 FULL_VECTORS = (0, 1, 3)   # cases whose arrays are committed in full; every case is committed as sha256 per field

@@ -313,3 +313,17 @@ def test_synthetic_geometry_follows_reference_init_dyn_shared(cfg):
         assert _sha(X[k][j0:j1, i0:i1]) == meta["sha256"][f"geom_{cfg}_{k}"], k
     for k in ("cyp", "cxp", "cym", "cxm"):
         assert _sha(X[k][j0:j1 + 1, i0:i1 + 1]) == meta["sha256"][f"geom_{cfg}_{k}"], k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cicecore"), reason="the reference source tree is not on this machine")
+@pytest.mark.parametrize("ndte,revised", [(120, False), (240, False), (600, False), (240, True)])
+def test_evp_constants_follow_reference_set_evp_parameters(ndte, revised):
+    """arlx1i, denom1, revp, brlx, epp2i, e_factor as synth.evp_params computes them == set_evp_parameters
+    (ice_dyn_shared.F90:453-486), transliterated and executed."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ref_translit as rt
+    ref = rt.generate_params(ndte, revised)
+    mine = synth.evp_params(ndte, revised_evp=revised)
+    for k, v in ref.items():
+        assert mine[k] == v, k
