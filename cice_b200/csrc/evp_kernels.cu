@@ -13,6 +13,7 @@
 //                                  patches never race (KERNEL_FUSED)
 // Neither is GEMM shaped; both are bandwidth/latency bound fp64 stencils -> no tensor cores.
 #include "evp_math.cuh"
+#include "evp_dom.cuh"
 
 #ifndef EVP_USE_PDL
 #define EVP_USE_PDL 1
@@ -24,27 +25,6 @@
 
 namespace evp {
 namespace EVP_NS {
-
-// cell index inside a dom array; init refuses sub-domains of 2^31 cells or more, so 32 bits are enough and every
-// access costs one IMAD.WIDE instead of a 64-bit add pair
-__device__ __forceinline__ int at(const Dom &d, int i, int j) { return j * d.ld + i; }
-
-// store a new velocity and, where the ghost ring aliases the rank's own interior (cyclic direction
-// entirely local), the ghost copies too: the on-rank part of dyn_haloUpdate (ice_dyn_evp.F90:908-910)
-__device__ __forceinline__ void store_uv(const Dom &d, double *__restrict__ U, double *__restrict__ V, int i, int j,
-                                         double un, double vn) {
-  U[at(d, i, j)] = un;
-  V[at(d, i, j)] = vn;
-  int ig = -1, jg = -1;
-  if (d.wrap_ew) ig = (i == 1) ? d.nx + 1 : (i == d.nx ? 0 : -1);
-  if (d.wrap_ns) jg = (j == 1) ? d.ny + 1 : (j == d.ny ? 0 : -1);
-  if (ig >= 0) { U[at(d, ig, j)] = un; V[at(d, ig, j)] = vn; }
-  if (jg >= 0) { U[at(d, i, jg)] = un; V[at(d, i, jg)] = vn; }
-  if (ig >= 0 && jg >= 0) { U[at(d, ig, jg)] = un; V[at(d, ig, jg)] = vn; }
-  // a 1-wide interior aliases both ghosts
-  if (d.wrap_ew && d.nx == 1) { U[at(d, 0, j)] = un; V[at(d, 0, j)] = vn; }
-  if (d.wrap_ns && d.ny == 1) { U[at(d, i, 0)] = un; V[at(d, i, 0)] = vn; }
-}
 
 __device__ __forceinline__ void load_sigma(const Dom &d, int b, int c, Sigma &s) {
 #pragma unroll
@@ -209,17 +189,6 @@ __device__ __forceinline__ int edge_index(const Dom &d, int i, int j) {
   if (j == d.ny) return d.nx + i - 1;
   if (i == 1) return 2 * d.nx + (j - 2);
   return 2 * d.nx + (d.ny - 2) + (j - 2);
-}
-
-// operands of one U point.  uvel_init/vvel_init enter stepu only as revp * uvel_init (ice_dyn_shared.F90:957-958);
-// in classic EVP revp = 0 and the product is a zero that can change the sum brlx*uold + 0 only when that sum is
-// itself a zero, so the two arrays are read only then (or when revp != 0): same bits, 16 B per point less traffic.
-__device__ __forceinline__ void load_uin(const Dom &d, const KParams &k, int cur, int c, double (&uin)[16]) {
-  uin[0] = d.u[cur][c]; uin[1] = d.v[cur][c]; uin[2] = d.cdn[c]; uin[3] = d.aiu[c]; uin[4] = d.uocn[c]; uin[5] = d.vocn[c];
-  uin[6] = d.waterx[c]; uin[7] = d.watery[c]; uin[8] = d.forcex[c]; uin[9] = d.forcey[c]; uin[10] = d.umassdti[c];
-  uin[11] = d.fm[c]; uin[12] = d.uarear[c]; uin[13] = d.TbU[c];
-  uin[14] = 0.0; uin[15] = 0.0;
-  if (k.revp != 0.0 || uin[0] == 0.0 || uin[1] == 0.0) { uin[14] = d.uinit[c]; uin[15] = d.vinit[c]; }
 }
 
 // loads the compiler may not sink into the branch that consumes them (asm volatile): the speculative form of the
@@ -758,6 +727,20 @@ cudaError_t launch_queue(const Dom &d, const KParams &p, int ndte, unsigned *pro
   return cudaLaunchCooperativeKernel((const void *)queue_kernel, dim3(nctas), dim3(QBX, QBY), args, 0, s);
 }
 
+#include "evp_lane2.cuh"
+
+template <int PX, int PY, int MINB, bool IL, int MAP>
+static cudaError_t launch_fused2_t(const Dom &d, const KParams &p, int cur, cudaStream_t s, bool pdl, int last) {
+  dim3 b(2 * PX * PY), g((d.nx + PX - 2) / (PX - 1), (d.ny + PY - 2) / (PY - 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, fused2_kernel<PX, PY, MINB, IL, MAP>, d, p, cur, last);
+}
+
 template <int FBX, int FBY, int MINB, bool HOIST = false, int SPEC = 0>
 static cudaError_t launch_fused_t(const Dom &d, const KParams &p, int cur, cudaStream_t s, bool pdl, int last) {
   dim3 b(FBX, FBY), g((d.nx + FBX - 2) / (FBX - 1), (d.ny + FBY - 2) / (FBY - 1));
@@ -808,6 +791,18 @@ cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s
     case 27: return launch_fused_t<32, 4, 4, false, 4>(d, p, cur, s, pdl, last);
     case 28: return launch_fused_t<32, 16, 1, false, 4>(d, p, cur, s, pdl, last);
     case 29: return launch_fused_t<32, 12, 1, false, 4>(d, p, cur, s, pdl, last);
+    // two lanes per T cell (evp_lane2.cuh): <patch x, patch y, CTAs per SM, interleaved div/sqrt, lane mapping>
+    case 40: return launch_fused2_t<32, 8, 2, true, 0>(d, p, cur, s, pdl, last);   // 512 threads, 64 registers
+    case 41: return launch_fused2_t<32, 8, 1, true, 0>(d, p, cur, s, pdl, last);   // 512 threads, 128 registers
+    case 42: return launch_fused2_t<16, 8, 3, true, 0>(d, p, cur, s, pdl, last);   // 256 threads, 80 registers
+    case 43: return launch_fused2_t<16, 8, 4, true, 0>(d, p, cur, s, pdl, last);   // 256 threads, 64 registers
+    case 44: return launch_fused2_t<32, 4, 3, true, 0>(d, p, cur, s, pdl, last);   // 256 threads, 80 registers
+    case 45: return launch_fused2_t<16, 16, 2, true, 0>(d, p, cur, s, pdl, last);  // 512 threads, 64 registers
+    case 46: return launch_fused2_t<32, 8, 2, false, 0>(d, p, cur, s, pdl, last);  // 40 with the built-in / and sqrt
+    case 50: return launch_fused2_t<32, 8, 2, true, 1>(d, p, cur, s, pdl, last);   // warp-uniform roles, shared-memory swap
+    case 51: return launch_fused2_t<32, 8, 1, true, 1>(d, p, cur, s, pdl, last);
+    case 52: return launch_fused2_t<32, 4, 3, true, 1>(d, p, cur, s, pdl, last);
+    case 53: return launch_fused2_t<32, 4, 4, true, 1>(d, p, cur, s, pdl, last);
     default: return launch_fused_t<32, 8, 2, false, 4>(d, p, cur, s, pdl, last);
   }
 }

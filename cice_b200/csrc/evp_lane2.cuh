@@ -1,0 +1,117 @@
+// evp_lane2.cuh -- KERNEL_FUSED with TWO LANES PER T CELL (lane2_relax / lane2_str of evp_math.cuh).
+//
+// Why: at gx1 the fused kernel is bound by the length of the dependent fp64 chain of a T cell (~5.7 k cycles at 14 resident
+// warps per SM), not by a pipe or by memory.  Here the chain of a cell is cut in two: the north lane
+// relaxes the corners NE and NW, the south lane SE and SW, the lanes swap their six stresses, and each forms the four
+// `str` terms of the U points on its own row.  Patch geometry, ownership rule, ping-pong copies, on-rank wrap stores and
+// the programmatic-dependent-launch protocol are those of fused_kernel; the momentum step runs on the first PX*PY
+// threads, one per U point.  Bit-identical to the one-thread-per-cell form (tests/test_host_math.py, tests/test_emu_lane2.py).
+//
+// Included by evp_kernels.cu inside namespace evp::EVP_NS.  Everything CUDA-specific it touches is a qualifier,
+// __syncthreads, one warp shuffle, one named barrier and the two PDL calls, so the same text also compiles for the
+// host emulation in tests/emu_lane2.cpp.
+//
+//   MAP 0: lanes 2q and 2q+1 of a warp share T cell q; stresses swapped with __shfl_xor_sync
+//   MAP 1: threads [0, PX*PY) are the north lanes, [PX*PY, 2*PX*PY) the south lanes of the same cells (`north` is
+//          warp-uniform, loads fully coalesced); stresses swapped through shared memory behind a 64-thread named
+//          barrier per row (needs PX == 32: one warp per row and role)
+#pragma once
+
+#ifndef EVP_LANE2_BAR64
+// named barrier `id` (1..15) over the two warps of one patch row
+#define EVP_LANE2_BAR64(id) asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory")
+#endif
+
+template <int PX, int PY, int MINB, bool IL, int MAP>
+__global__ void __launch_bounds__(2 * PX *PY, MINB) fused2_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
+                                                                  int cur, int flags) {
+  static_assert(MAP == 0 || (PX == 32 && PY <= 15), "MAP 1 pairs one north warp with one south warp per row");
+  static_assert(MAP != 0 || PX % 16 == 0, "MAP 0 keeps the 16 cells of a warp on one row");
+  __shared__ double sstr[8][PY][PX];
+  __shared__ double sx[MAP == 1 ? 12 : 1][PY][PX];  // MAP 1: [0..5] the north lanes' stresses, [6..11] the south lanes'
+  const int t = threadIdx.x;
+  const int last = flags & 1;
+#if EVP_USE_PDL
+  if (flags & 2) cudaTriggerProgrammaticLaunchCompletion();  // see fused_kernel
+#endif
+  const bool north = MAP == 0 ? !(t & 1) : t < PX * PY;
+  const int cell = MAP == 0 ? (t >> 1) : (north ? t : t - PX * PY);
+  const int cx = cell % PX, cy = cell / PX;
+  const int i = 1 + blockIdx.x * (PX - 1) + cx;  // T cell of this lane pair
+  const int j = 1 + blockIdx.y * (PY - 1) + cy;
+  const int nxt = cur ^ 1;
+  const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
+  const int c = at(d, inT ? i : 1, inT ? j : 1);
+#if EVP_USE_PDL
+  cudaGridDependencySynchronize();
+#endif
+  const bool active = inT && d.maskT[c];
+  Half own = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double dxT = 0.0, dyT = 0.0;
+  if (active) {
+    // the lane's own velocity row a and the other row b (evp_math.cuh: lane2_relax)
+    const int ca = north ? c : c - d.ld, cb = north ? c - d.ld : c;
+    const double *__restrict__ U = d.u[cur];
+    const double *__restrict__ V = d.v[cur];
+    // corner numbering 0 NE, 1 NW, 2 SW, 3 SE: the lane's E corner is NE or SE, its W corner NW or SW
+    const int qE = north ? NE : SE, qW = north ? NW : SW;
+    own.pE = d.sig[cur][qE][c]; own.pW = d.sig[cur][qW][c];
+    own.mE = d.sig[cur][4 + qE][c]; own.mW = d.sig[cur][4 + qW][c];
+    own.sE = d.sig[cur][8 + qE][c]; own.sW = d.sig[cur][8 + qW][c];
+    dxT = d.dxT[c]; dyT = d.dyT[c];
+    lane2_relax<IL>(north, U[ca], V[ca], U[ca - 1], V[ca - 1], U[cb], V[cb], U[cb - 1], V[cb - 1], dxT, dyT, d.cxp[c], d.cyp[c],
+                    d.cxm[c], d.cym[c], d.DminTarea[c], d.strength[c], k, own);
+    // each T cell is stored by exactly one CTA: the one that holds it off its E/N overlap edge
+    const bool ownT = (cx < PX - 1 || i == d.nx + 1) && (cy < PY - 1 || j == d.ny + 1);
+    if (ownT) {
+      d.sig[nxt][qE][c] = own.pE; d.sig[nxt][qW][c] = own.pW;
+      d.sig[nxt][4 + qE][c] = own.mE; d.sig[nxt][4 + qW][c] = own.mW;
+      d.sig[nxt][8 + qE][c] = own.sE; d.sig[nxt][8 + qW][c] = own.sW;
+    }
+  }
+  // the swap is unconditional (every lane of the warp / both warps of the row take part); off the ice the lanes swap zeros
+  Half oth;
+  if (MAP == 0) {
+    oth.pE = __shfl_xor_sync(0xffffffffu, own.pE, 1); oth.pW = __shfl_xor_sync(0xffffffffu, own.pW, 1);
+    oth.mE = __shfl_xor_sync(0xffffffffu, own.mE, 1); oth.mW = __shfl_xor_sync(0xffffffffu, own.mW, 1);
+    oth.sE = __shfl_xor_sync(0xffffffffu, own.sE, 1); oth.sW = __shfl_xor_sync(0xffffffffu, own.sW, 1);
+  } else {
+    const int mine = north ? 0 : 6, theirs = north ? 6 : 0;
+    sx[mine + 0][cy][cx] = own.pE; sx[mine + 1][cy][cx] = own.pW; sx[mine + 2][cy][cx] = own.mE;
+    sx[mine + 3][cy][cx] = own.mW; sx[mine + 4][cy][cx] = own.sE; sx[mine + 5][cy][cx] = own.sW;
+    EVP_LANE2_BAR64(cy + 1);
+    oth.pE = sx[theirs + 0][cy][cx]; oth.pW = sx[theirs + 1][cy][cx]; oth.mE = sx[theirs + 2][cy][cx];
+    oth.mW = sx[theirs + 3][cy][cx]; oth.sE = sx[theirs + 4][cy][cx]; oth.sW = sx[theirs + 5][cy][cx];
+  }
+  double out[4] = {0.0, 0.0, 0.0, 0.0};
+  if (active) lane2_str(north, own, oth, dxT, dyT, d.dxhy[c], d.dyhx[c], out);
+  // north: str1 str2 str5 str7, south: str3 str4 str6 str8 (0-based rows of sstr as fused_kernel uses them)
+  sstr[north ? 0 : 2][cy][cx] = out[0];
+  sstr[north ? 1 : 3][cy][cx] = out[1];
+  sstr[north ? 4 : 5][cy][cx] = out[2];
+  sstr[north ? 6 : 7][cy][cx] = out[3];
+  __syncthreads();
+
+  if (t < PX * PY) {
+    const int tx = t % PX, ty = t / PX;
+    const int iu = 1 + blockIdx.x * (PX - 1) + tx, ju = 1 + blockIdx.y * (PY - 1) + ty;
+    if (tx < PX - 1 && ty < PY - 1 && iu <= d.nx && ju <= d.ny) {
+      const int cu = at(d, iu, ju);
+      if (d.maskU[cu]) {
+        double uin[16];
+        load_uin(d, k, cur, cu, uin);
+        const UOut o = stepu_point<IL>(uin[0], uin[1], uin[2], uin[3], uin[4], uin[5], uin[6], uin[7], uin[8], uin[9], uin[10], uin[11],
+                                       uin[12], uin[13], uin[14], uin[15], sstr[0][ty][tx], sstr[1][ty][tx + 1], sstr[2][ty + 1][tx],
+                                       sstr[3][ty + 1][tx + 1], sstr[4][ty][tx], sstr[5][ty + 1][tx], sstr[6][ty][tx + 1],
+                                       sstr[7][ty + 1][tx + 1], k);
+        store_uv(d, d.u[nxt], d.v[nxt], iu, ju, o.u, o.v);
+        if (last) {  // see fused_kernel
+          d.strintx[cu] = o.strintx;
+          d.strinty[cu] = o.strinty;
+          d.taubx[cu] = o.taubx;
+          d.tauby[cu] = o.tauby;
+        }
+      }
+    }
+  }
+}

@@ -7,6 +7,8 @@ Bars (BASELINE.md section 3 / SURVEY.md 8d):
   * MODE_FAST (FMA contraction): maxabs(gpu-ref) <= 1e-10 * maxabs(ref) per field after the
     full ndte loop (TOL below).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -300,6 +302,38 @@ def test_fused_variants_bitwise(oracle_mod, evp_lib, monkeypatch, variant, extra
         ref = run_oracle(oracle_mod, c)
         got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED)
         assert_bitwise(got, ref)
+
+
+# Two lanes per T cell (cice_b200/csrc/evp_lane2.cuh): written at the end of round 1 after the GPU budget was spent.  The kernel text
+# is checked bit for bit against the oracle on the host (tests/test_emu_lane2.py) but has not run on a GPU yet, so this test is
+# opt-in until it has (EVP_B200_TEST_CANDIDATES=1; scripts/job_r2_candidates.sh runs it first thing in round 2).
+CANDIDATES = pytest.mark.skipif(os.environ.get("EVP_B200_TEST_CANDIDATES", "0") != "1",
+                                reason="round-2 candidate kernels: host-emulated only so far; set EVP_B200_TEST_CANDIDATES=1")
+
+
+@CANDIDATES
+@pytest.mark.parametrize("variant", ["40", "41", "42", "43", "44", "45", "46", "50", "51", "52", "53"])
+def test_two_lane_variants(oracle_mod, evp_lib, monkeypatch, variant):
+    monkeypatch.setenv("EVP_B200_FUSED_VARIANT", variant)
+    cases = [synth.make_case("tiny", seed=11, block_size=(12, 10), ndte=9),
+             synth.make_case("tiny", seed=12, revised_evp=True),
+             synth.make_case("tiny", seed=13, ew="closed", ns="closed", kmt="boxislands"),
+             synth.make_case("tiny", nx=62, ny=30, seed=136, ns="cyclic", ndte=5),
+             synth.make_case("gx3", seed=14, ndte=25),
+             synth.make_case("tiny", seed=15, ns="tripole", ew="cyclic", kmt="none", ndte=12)]
+    for c in cases:
+        ref = run_oracle(oracle_mod, c)
+        got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED)
+        assert_bitwise(got, ref)
+    # zero and denormal-range operands: the fast paths of the interleaved division / square root must fall back
+    c = synth.make_case("tiny", seed=21, ndte=6)
+    for n in ("uvel", "vvel", "uocnU", "vocnU", "forcexU", "forceyU", "waterxU", "wateryU"):
+        c.fields[n][...] = 0.0
+    c.fields["strength"][...] *= 1e-300
+    assert_bitwise(run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED), run_oracle(oracle_mod, c))
+    # fast mode: within the floating-point tolerance of the other fast kernels
+    c = synth.make_case("gx3")
+    assert_close(run_gpu(evp_lib, c, mode=abi.MODE_FAST, kernel=abi.KERNEL_FUSED), run_oracle(oracle_mod, c), TOL)
 
 
 def test_interleaved_divsqrt_hits_the_fallback(oracle_mod, evp_lib, monkeypatch):
