@@ -179,6 +179,7 @@ struct Ctx {
   int q_ntiles = 0, q_nctas = 0;
   int num_sms = 0;
   int fused_variant = 0;
+  int p2p_variant_bits = 0;  // 0x100: the in-kernel-halo kernel reads its tile table from constant memory (EVP_B200_P2P_CONST_TILES=1)
   int strip_m = 1;  // chunks per CTA of strip_kernel (fused_variant 30)
   bool fused_pdl = true;
   bool pdl_trigger = true;  // early programmatic-launch trigger in the fused kernel
@@ -424,6 +425,17 @@ static int do_init(const evp_b200_grid_t *gr) {
   d.wrap_ew = g.halo.wrap_ew; d.wrap_ns = g.halo.wrap_ns;
   CK(cudaStreamSynchronize(g.stream));
   if (g.p2p.setup(g_comm, g.halo, g.dshare, g.ndom, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, g_err, sizeof g_err)) return 1;
+  g.p2p_variant_bits = 0;
+  if (const char *e = getenv("EVP_B200_P2P_CONST_TILES")) {
+    const int nt = g.p2p.prm.ntx * g.p2p.prm.nty;
+    if (e[0] == '1' && g.p2p.enabled && nt <= P2P_CONST_TILES) {
+      std::vector<int> tiles(nt);
+      CK(cudaMemcpy(tiles.data(), g.p2p.d_tile_order, sizeof(int) * nt, cudaMemcpyDeviceToHost));
+      CK(exact::set_p2p_tiles(tiles.data(), nt));
+      CK(fast::set_p2p_tiles(tiles.data(), nt));
+      g.p2p_variant_bits = 0x100;
+    }
+  }
 
   // fused kernel form.  Sub-domains whose arrays fit the 126 MB L2 run latency-bound: both masks requested at once and the
   // IEEE division / square-root expansions of the four corners interleaved (variant 23).  Larger ones stream from HBM and
@@ -638,8 +650,8 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
   for (int ksub = 0; ksub < p->ndte; ++ksub) {
     const int last = (ksub == p->ndte - 1);
     if (p2p) {
-      CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, g.fused_variant, g.stream)
-               : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, g.fused_variant, g.stream));
+      CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, g.fused_variant | g.p2p_variant_bits, g.stream)
+               : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, g.fused_variant | g.p2p_variant_bits, g.stream));
       cur ^= 1;
       ++nl;
       continue;

@@ -70,6 +70,7 @@ struct KParams {
 // In-kernel NVLink halo (see evp_halo.cu, fused_kernel): edge CTAs store new edge velocities straight into the
 // neighbour GPUs' ghost cells (CUDA-IPC mapped peer memory) and hand over with per-peer epoch flags.
 #define P2P_MAXPEER 16
+#define P2P_CONST_TILES 8192  // capacity of the constant-memory copy of tile_order (evp_kernels.cu)
 struct P2PParams {
   int enabled;
   int npeers;
@@ -114,6 +115,7 @@ struct PersistPlan {
   cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl, int last); \
   cudaError_t launch_strip(const Dom &d, const KParams &p, int cur, int m, cudaStream_t s, bool pdl, int last); \
   cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, int last, int variant, cudaStream_t s); \
+  cudaError_t set_p2p_tiles(const int *host_tiles, int n); \
   cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s); \
   cudaError_t launch_queue(const Dom &d, const KParams &p, int ndte, unsigned *progress, unsigned *counter, int nctas, cudaStream_t s); \
   cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \

@@ -221,6 +221,15 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //  * static operands (geometry, strength, masks) and the momentum operands are requested BEFORE the programmatic
 //    grid dependency is resolved, i.e. while the previous subcycle's kernel is still draining;
 //  * the 12 momentum operands go global -> shared with cp.async and are picked up after the CTA barrier.
+// the in-kernel-halo form's edge-first tile table in CONSTANT memory (SPEC bit 4, EVP_B200_P2P_CONST_TILES=1): the table
+// lookup is the first thing a CTA does and every address depends on it; from global memory that is one more serialised L2
+// round trip per CTA, from the constant cache it is a few cycles.  Round-2 candidate, not yet measured.
+__constant__ int c_tile_order[P2P_CONST_TILES];
+cudaError_t set_p2p_tiles(const int *host_tiles, int n) {
+  if (n > P2P_CONST_TILES) return cudaErrorInvalidValue;
+  return cudaMemcpyToSymbol(c_tile_order, host_tiles, sizeof(int) * (size_t)n);
+}
+
 constexpr int NUOP = 12;
 // SPEC bit 0: speculative T-cell operand loads; bit 1: momentum operands through cp.async
 template <int FBX, int FBY, bool P2P, int SPEC>
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_cons
     const int b = blockIdx.x;
     // edge tiles first; the table holds (tby << 16 | tbx) so that no runtime integer division (~80 instructions and a MUFU
     // round trip at the top of every CTA) is needed to decode it
-    const int tile = pp.tile_order[b];
+    const int tile = (SPEC & 16) ? c_tile_order[b] : pp.tile_order[b];
     tbx = tile & 0xffff;
     tby = tile >> 16;
     edge_tile = b < pp.n_edge_tiles;
@@ -825,6 +834,10 @@ cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = (last & 4) ? 1 : 0;
   const int flags = last & 3;
+  if (variant & 0x100) {  // tile table in constant memory (set_p2p_tiles)
+    if ((variant & 0xff) == 19) return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 3 | 16>, d, p, cur, pp, ksub, flags);
+    return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 4 | 16>, d, p, cur, pp, ksub, flags);
+  }
   if (variant == 19) return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 3>, d, p, cur, pp, ksub, flags);
   return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 4>, d, p, cur, pp, ksub, flags);
   return cudaGetLastError();

@@ -1,0 +1,21 @@
+#!/bin/bash
+# round 2, first GPU job (one GPU): the candidates written at the end of round 1 without a GPU.
+#   1. parity of the two-lanes-per-cell kernel variants (host-emulated so far: tests/test_emu_lane2.py)
+#   2. gx1 bench line per variant (ms per step, roofline fraction) next to the default
+#   3. the in-kernel-halo kernel with its tile table in constant memory, in the one-GPU no-peer self test
+# Output: gpurun_out/r2_candidates.txt.   /usr/local/graft/bin/gpurun --timeout 1500 -- bash scripts/job_r2_candidates.sh
+mkdir -p gpurun_out
+{
+echo "== parity of variants 40-53"
+EVP_B200_TEST_CANDIDATES=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k two_lane 2>&1 | tail -15
+b() { timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu "$@" 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], round(d['roofline']['frac'],4))"; }
+echo "== gx1, ms per step and roofline fraction"
+echo "default: $(b)"
+for v in 40 41 42 43 44 45 46 50 51 52 53; do echo "variant $v: $(EVP_B200_FUSED_VARIANT=$v b)"; done
+echo "== gx1 fast mode"
+echo "default fast: $(b --mode fast)"
+for v in 40 43 50; do echo "variant $v fast: $(EVP_B200_FUSED_VARIANT=$v b --mode fast)"; done
+echo "== in-kernel-halo kernel, no-peer self test: tile table in global vs constant memory"
+for st in 1 3; do for ct in 0 1; do echo "selftest $st const_tiles $ct: $(EVP_B200_P2P_SELFTEST=$st EVP_B200_P2P_CONST_TILES=$ct b)"; done; done
+echo "parity selftest 1 + constant tiles: $(EVP_B200_P2P_SELFTEST=1 EVP_B200_P2P_CONST_TILES=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k 'exact_mode_bitwise and fused or gx1_ndte240_every_kernel_exact and fused or boundary_types' 2>&1 | tail -1)"
+} 2>&1 | tee gpurun_out/r2_candidates.txt
