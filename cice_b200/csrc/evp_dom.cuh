@@ -1,6 +1,6 @@
 // evp_dom.cuh -- index and store helpers on the device sub-domain layout (struct Dom, evp_internal.h), shared by the B-grid
 // kernels of evp_kernels.cu and evp_lane2.cuh.  Plain C++ apart from the CUDA function qualifiers, so that the kernels built
-// on them can also be run thread by thread on the host (tests/emu_lane2.cpp).
+// on them can also be run thread by thread on the host (tests/emu_bgrid.cpp).
 #pragma once
 #include "evp_internal.h"
 

@@ -14,6 +14,7 @@
 // Neither is GEMM shaped; both are bandwidth/latency bound fp64 stencils -> no tensor cores.
 #include "evp_math.cuh"
 #include "evp_dom.cuh"
+#include "evp_ptx.cuh"
 
 #ifndef EVP_USE_PDL
 #define EVP_USE_PDL 1
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(256) deform_kernel(const __grid_constant__ Dom
   vort[c] = 0.5 * ta * (dvdxn + dvdxs - dudye - dudyw);
 }
 
+#ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
 cudaError_t launch_deform(const Dom &d, int cur, const double *dxU, const double *dyU, const double *tarear, double *divu,
                           double *shear, double *vort, double *rdg_conv, double *rdg_shear, double e_factor, cudaStream_t s) {
   dim3 b(32, 8), g((d.nx + 1 + b.x - 1) / b.x, (d.ny + 1 + b.y - 1) / b.y);
@@ -157,32 +159,13 @@ cudaError_t launch_stepu(const Dom &d, const KParams &p, int cur, cudaStream_t s
   return cudaGetLastError();
 }
 
+#endif  // EVP_HOST_EMU
+
 // ---------------------------------------------------------------------------------------------
 // KERNEL_FUSED
 // ---------------------------------------------------------------------------------------------
 // FBX x FBY threads relax an FBX x FBY patch of T cells and advance the (FBX-1) x (FBY-1) U points it closes.
 // MINB = CTAs per SM the register allocation is bounded for.
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// wait until flag >= want; bounded so that a lost peer cannot hang the GPU (sets *err instead)
-__device__ __forceinline__ void wait_flag(const unsigned long long *flag, unsigned long long want, int *err) {
-  const long long t0 = clock64();
-  while (ld_acquire_sys(flag) < want) {
-    if (clock64() - t0 > 6000000000LL) { atomicExch(err, 1); break; }
-  }
-}
-
 // edge index of a boundary U point (i==1 | i==nx | j==1 | j==ny), the row index of the push CSR
 __device__ __forceinline__ int edge_index(const Dom &d, int i, int j) {
   if (j == 1) return i - 1;
@@ -190,31 +173,6 @@ __device__ __forceinline__ int edge_index(const Dom &d, int i, int j) {
   if (i == 1) return 2 * d.nx + (j - 2);
   return 2 * d.nx + (d.ny - 2) + (j - 2);
 }
-
-// loads the compiler may not sink into the branch that consumes them (asm volatile): the speculative form of the
-// fused kernel issues every operand load of a cell at once, without waiting for the ice mask, so that a CTA pays
-// one L2 round trip instead of four (mask U -> mask T -> stress operands -> momentum operands)
-__device__ __forceinline__ double ld_f64(const double *p) {
-  double v;
-  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ double ld_nc_f64(const double *p) {  // never written while the loop runs
-  double v;
-  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ unsigned ld_nc_u8(const unsigned char *p) {
-  unsigned v;
-  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-// 8-byte asynchronous global -> shared copy (LDGSTS): the momentum operands travel while the stresses are relaxed
-__device__ __forceinline__ void cp_async8(double *smem, const double *g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // The speculative body of fused_kernel (SPEC = true, the default): same arithmetic, same ownership rules, but
 //  * every operand of the T cell is requested before the ice masks are known (addresses are always inside the dom);
@@ -225,10 +183,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // lookup is the first thing a CTA does and every address depends on it; from global memory that is one more serialised L2
 // round trip per CTA, from the constant cache it is a few cycles.  Round-2 candidate, not yet measured.
 __constant__ int c_tile_order[P2P_CONST_TILES];
+#ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
 cudaError_t set_p2p_tiles(const int *host_tiles, int n) {
   if (n > P2P_CONST_TILES) return cudaErrorInvalidValue;
   return cudaMemcpyToSymbol(c_tile_order, host_tiles, sizeof(int) * (size_t)n);
 }
+#endif  // EVP_HOST_EMU
 
 constexpr int NUOP = 12;
 // SPEC bit 0: speculative T-cell operand loads; bit 1: momentum operands through cp.async
@@ -298,8 +258,8 @@ __device__ __forceinline__ void fused_spec_body(const Dom &d, const KParams &k, 
     // U row ty needs the str terms of T rows ty and ty+1 only, and a row is one warp: instead of a CTA-wide barrier, warp
     // ty+1 arrives on named barrier ty+1 once its terms are in shared memory and warp ty waits there (64 threads each,
     // every barrier used once per launch), so a warp is held up by one neighbour, not by the slowest of eight
-    if (ty >= 1) asm volatile("bar.arrive %0, 64;" ::"r"(ty) : "memory");
-    if (ty < FBY - 1) asm volatile("bar.sync %0, 64;" ::"r"(ty + 1) : "memory");
+    if (ty >= 1) bar_arrive64(ty);
+    if (ty < FBY - 1) bar_sync64(ty + 1);
   } else {
     __syncthreads();
   }
@@ -455,7 +415,7 @@ __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_cons
         __threadfence_system();
         if (tl) tl[3] = gtime();  // fenced
         for (int q = 0; q < pp.npeers; ++q)
-          asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(pp.peer_flag[q]), "l"(base + (unsigned long long)ksub + 1ULL) : "memory");
+          st_relaxed_sys(pp.peer_flag[q], base + (unsigned long long)ksub + 1ULL);
         if (tl) tl[4] = gtime();  // flags written
       }
     }
@@ -531,6 +491,7 @@ __global__ void __launch_bounds__(SBX *SBY, 2) strip_kernel(const __grid_constan
   }
 }
 
+#ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
 cudaError_t launch_strip(const Dom &d, const KParams &p, int cur, int m, cudaStream_t s, bool pdl, int last) {
   dim3 b(SBX, SBY), g((d.nx + SBX - 2) / (SBX - 1), (d.ny + SBY * m - 2) / (SBY * m - 1));
   cudaLaunchConfig_t cfg{};
@@ -541,6 +502,8 @@ cudaError_t launch_strip(const Dom &d, const KParams &p, int cur, int m, cudaStr
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, strip_kernel, d, p, cur, m, last);
 }
+
+#endif  // EVP_HOST_EMU
 
 // loop hand-shake: "I have entered loop `base`" (my buffers are ready to be written), and the closing wait
 __global__ void p2p_start_kernel(const __grid_constant__ P2PParams pp) {
@@ -639,15 +602,6 @@ __global__ void __launch_bounds__(F4X *F4Y * 4, 1) fused4_kernel(const __grid_co
 // so the oldest unfinished item always has its dependencies met: no deadlock as long as all CTAs are resident
 // (cooperative launch).  No kernel boundaries, no partial last wave, subcycles overlap at the patch level.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 constexpr int QBX = 32, QBY = 8;
 __global__ void __launch_bounds__(QBX *QBY, 2) queue_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
                                                             int ndte, int ntx, int nty, unsigned *__restrict__ progress,
@@ -730,14 +684,18 @@ __global__ void __launch_bounds__(QBX *QBY, 2) queue_kernel(const __grid_constan
   }
 }
 
+#ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
 cudaError_t launch_queue(const Dom &d, const KParams &p, int ndte, unsigned *progress, unsigned *counter, int nctas, cudaStream_t s) {
   int ntx = (d.nx + QBX - 2) / (QBX - 1), nty = (d.ny + QBY - 2) / (QBY - 1);
   void *args[] = {(void *)&d, (void *)&p, (void *)&ndte, (void *)&ntx, (void *)&nty, (void *)&progress, (void *)&counter};
   return cudaLaunchCooperativeKernel((const void *)queue_kernel, dim3(nctas), dim3(QBX, QBY), args, 0, s);
 }
 
+#endif  // EVP_HOST_EMU
+
 #include "evp_lane2.cuh"
 
+#ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
 template <int PX, int PY, int MINB, bool IL, int MAP>
 static cudaError_t launch_fused2_t(const Dom &d, const KParams &p, int cur, cudaStream_t s, bool pdl, int last) {
   dim3 b(2 * PX * PY), g((d.nx + PX - 2) / (PX - 1), (d.ny + PY - 2) / (PY - 1));
@@ -842,6 +800,7 @@ cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp
   return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 4>, d, p, cur, pp, ksub, flags);
   return cudaGetLastError();
 }
+#endif  // EVP_HOST_EMU
 
 }  // namespace EVP_NS
 }  // namespace evp

@@ -5,22 +5,17 @@
 // relaxes the corners NE and NW, the south lane SE and SW, the lanes swap their six stresses, and each forms the four
 // `str` terms of the U points on its own row.  Patch geometry, ownership rule, ping-pong copies, on-rank wrap stores and
 // the programmatic-dependent-launch protocol are those of fused_kernel; the momentum step runs on the first PX*PY
-// threads, one per U point.  Bit-identical to the one-thread-per-cell form (tests/test_host_math.py, tests/test_emu_lane2.py).
+// threads, one per U point.  Bit-identical to the one-thread-per-cell form (tests/test_host_math.py, tests/test_emu_bgrid.py).
 //
 // Included by evp_kernels.cu inside namespace evp::EVP_NS.  Everything CUDA-specific it touches is a qualifier,
 // __syncthreads, one warp shuffle, one named barrier and the two PDL calls, so the same text also compiles for the
-// host emulation in tests/emu_lane2.cpp.
+// host emulation in tests/emu_bgrid.cpp.
 //
 //   MAP 0: lanes 2q and 2q+1 of a warp share T cell q; stresses swapped with __shfl_xor_sync
 //   MAP 1: threads [0, PX*PY) are the north lanes, [PX*PY, 2*PX*PY) the south lanes of the same cells (`north` is
 //          warp-uniform, loads fully coalesced); stresses swapped through shared memory behind a 64-thread named
 //          barrier per row (needs PX == 32: one warp per row and role)
 #pragma once
-
-#ifndef EVP_LANE2_BAR64
-// named barrier `id` (1..15) over the two warps of one patch row
-#define EVP_LANE2_BAR64(id) asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory")
-#endif
 
 template <int PX, int PY, int MINB, bool IL, int MAP>
 __global__ void __launch_bounds__(2 * PX *PY, MINB) fused2_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
@@ -79,7 +74,7 @@ __global__ void __launch_bounds__(2 * PX *PY, MINB) fused2_kernel(const __grid_c
     const int mine = north ? 0 : 6, theirs = north ? 6 : 0;
     sx[mine + 0][cy][cx] = own.pE; sx[mine + 1][cy][cx] = own.pW; sx[mine + 2][cy][cx] = own.mE;
     sx[mine + 3][cy][cx] = own.mW; sx[mine + 4][cy][cx] = own.sE; sx[mine + 5][cy][cx] = own.sW;
-    EVP_LANE2_BAR64(cy + 1);
+    bar_sync64(cy + 1);  // named barrier over the two warps of this patch row (evp_ptx.cuh)
     oth.pE = sx[theirs + 0][cy][cx]; oth.pW = sx[theirs + 1][cy][cx]; oth.mE = sx[theirs + 2][cy][cx];
     oth.mW = sx[theirs + 3][cy][cx]; oth.sE = sx[theirs + 4][cy][cx]; oth.sW = sx[theirs + 5][cy][cx];
   }

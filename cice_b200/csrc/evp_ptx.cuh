@@ -1,0 +1,100 @@
+// evp_ptx.cuh -- the inline-PTX helpers of the B-grid kernels (evp_kernels.cu), in one place.
+//
+// With EVP_HOST_EMU defined (tests/emu_bgrid.cpp: the kernels run thread by thread on the host as a CPU-side check of their
+// index logic) every helper has a plain C++ stand-in with the same meaning minus the timing: a volatile load is a load, an
+// asynchronous copy is a copy, fences and acquire/release accesses are C++ atomics' business.  The product never defines it.
+#pragma once
+#include "evp_internal.h"
+
+namespace evp {
+
+#ifndef EVP_HOST_EMU
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// wait until flag >= want; bounded so that a lost peer cannot hang the GPU (sets *err instead)
+__device__ __forceinline__ void wait_flag(const unsigned long long *flag, unsigned long long want, int *err) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < want) {
+    if (clock64() - t0 > 6000000000LL) { atomicExch(err, 1); break; }
+  }
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// loads the compiler may not sink into the branch that consumes them (asm volatile): the speculative form of the
+// fused kernel issues every operand load of a cell at once, without waiting for the ice mask, so that a CTA pays
+// one L2 round trip instead of four (mask U -> mask T -> stress operands -> momentum operands)
+__device__ __forceinline__ double ld_f64(const double *p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_nc_f64(const double *p) {  // never written while the loop runs
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned ld_nc_u8(const unsigned char *p) {
+  unsigned v;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+// 8-byte asynchronous global -> shared copy (LDGSTS): the momentum operands travel while the stresses are relaxed
+__device__ __forceinline__ void cp_async8(double *smem, const double *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// named barriers 1..15 over 64 threads (two warps): arrive without waiting / wait for both
+__device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+#else  // EVP_HOST_EMU: see the header comment; emu:: is provided by tests/cuda_emu.h
+
+inline unsigned long long gtime() { return 0; }
+inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline void st_relaxed_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+inline void wait_flag(const unsigned long long *flag, unsigned long long want, int *err) {
+  for (long spins = 0; ld_acquire_sys(flag) < want; ++spins) {
+    if (spins > 200000000L) { *err = 1; break; }
+    emu::yield();
+  }
+}
+inline double ld_f64(const double *p) { return *(const volatile double *)p; }
+inline double ld_nc_f64(const double *p) { return *p; }
+inline unsigned ld_nc_u8(const unsigned char *p) { return *p; }
+inline void cp_async8(double *smem, const double *g) { *smem = *g; }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
+inline void bar_arrive64(int id) { emu::bar_arrive(id, 64); }
+inline void bar_sync64(int id) { emu::bar_sync(id, 64); }
+inline unsigned ld_acquire_gpu(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release_gpu(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+
+#endif
+
+}  // namespace evp

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, first GPU job (one GPU): the candidates written at the end of round 1 without a GPU.
-#   1. parity of the two-lanes-per-cell kernel variants (host-emulated so far: tests/test_emu_lane2.py)
+#   1. parity of the two-lanes-per-cell kernel variants (host-emulated so far: tests/test_emu_bgrid.py)
 #   2. gx1 bench line per variant (ms per step, roofline fraction) next to the default
 #   3. the in-kernel-halo kernel with its tile table in constant memory, in the one-GPU no-peer self test
 # Output: gpurun_out/r2_candidates.txt.   /usr/local/graft/bin/gpurun --timeout 1500 -- bash scripts/job_r2_candidates.sh

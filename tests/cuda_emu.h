@@ -1,0 +1,121 @@
+// cuda_emu.h -- just enough of the CUDA execution model on host threads to run the repo's kernels THREAD BY THREAD on a CPU.
+//
+// Test infrastructure only (tests/emu_bgrid.cpp); nothing in the product includes this.  A kernel is compiled unchanged
+// by g++ (-ffp-contract=off for the `exact` arithmetic): every CUDA thread of a CTA is a host thread, CTAs of a grid run one
+// after the other (their __shared__ arrays are function statics), __syncthreads is a pthread barrier, named barriers are
+// arrive/wait counters, warp shuffles are mailboxes, device atomics are GCC atomics, the PDL calls are compiled out.
+// What this checks without a GPU: index decoding, ownership rules, shared-memory hand-over, lane exchanges, wrap stores,
+// ping-pong parity -- the logic of the kernel text.  What it cannot check: timing, memory-model races between CTAs
+// (CTAs are sequential here), and the hardware's MUFU seeds (evp_math.cuh substitutes host seeds under EVP_HOST_EMU).
+#pragma once
+#include <math.h>
+#include <pthread.h>
+#include <sched.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>  // host mode: the CUDA function/memory-space qualifiers expand to nothing
+
+#undef __shared__
+#define __shared__ static
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+#ifndef __grid_constant__
+#define __grid_constant__
+#endif
+
+namespace emu {
+constexpr int MAXT = 1024, RING = 64;
+struct Idx { int x, y, z; };
+thread_local Idx tid, bid, bdim, gdim;
+thread_local int lin;            // linear thread id inside the CTA
+thread_local unsigned shfl_seq;  // shuffles executed by this thread (every lane of a warp executes the same sequence)
+struct Mail { std::atomic<unsigned> seq; double val[RING]; };
+static Mail mail[MAXT];
+static pthread_barrier_t cta_barrier;
+struct NamedBar { std::atomic<int> count; std::atomic<unsigned> gen; };
+static NamedBar named[16];
+
+inline void yield() { sched_yield(); }
+inline void syncthreads() { pthread_barrier_wait(&cta_barrier); }
+inline void bar_arrive(int id, int n) {
+  NamedBar &b = named[id];
+  if (b.count.fetch_add(1) + 1 == n) { b.count.store(0); b.gen.fetch_add(1); }
+}
+inline void bar_sync(int id, int n) {
+  NamedBar &b = named[id];
+  const unsigned g = b.gen.load();
+  if (b.count.fetch_add(1) + 1 == n) { b.count.store(0); b.gen.fetch_add(1); }
+  else while (b.gen.load() == g) yield();
+}
+// publish v, then read the value lane `src` (linear id inside the CTA) published in the same shuffle.  A lane may run up to
+// RING shuffles ahead of a reader before it overwrites a slot; CTA barriers bound the lead (kernels here: <= 12).
+inline double shfl_from(double v, int src) {
+  const unsigned n = ++shfl_seq;
+  mail[lin].val[n % RING] = v;
+  mail[lin].seq.store(n, std::memory_order_release);
+  while (mail[src].seq.load(std::memory_order_acquire) < n) yield();
+  return mail[src].val[n % RING];
+}
+
+// run `kernel()` for every thread of every CTA of the grid
+template <class F>
+inline void launch(Idx grid, Idx block, F kernel) {
+  const int nthreads = block.x * block.y;
+  pthread_barrier_init(&cta_barrier, nullptr, nthreads);
+  for (auto &b : named) { b.count.store(0); b.gen.store(0); }
+  for (int t = 0; t < nthreads; ++t) mail[t].seq.store(0);
+  std::vector<std::thread> th;
+  th.reserve(nthreads);
+  for (int t = 0; t < nthreads; ++t)
+    th.emplace_back([=] {
+      lin = t;
+      tid = {t % block.x, t / block.x, 0};
+      bdim = block;
+      gdim = grid;
+      shfl_seq = 0;
+      for (int by = 0; by < grid.y; ++by)
+        for (int bx = 0; bx < grid.x; ++bx) {
+          bid = {bx, by, 0};
+          kernel();
+          syncthreads();  // the next CTA reuses the static "shared" arrays
+        }
+    });
+  for (auto &x : th) x.join();
+  pthread_barrier_destroy(&cta_barrier);
+}
+}  // namespace emu
+
+#define threadIdx (emu::tid)
+#define blockIdx (emu::bid)
+#define blockDim (emu::bdim)
+#define gridDim (emu::gdim)
+#define __syncthreads() emu::syncthreads()
+#define __shfl_xor_sync(mask, v, lanemask) emu::shfl_from((v), emu::lin ^ (lanemask))
+#define __shfl_sync(mask, v, src, width) emu::shfl_from((v), (emu::lin & ~((width) - 1)) + (src))
+
+// device intrinsics and atomics the kernels mention
+static inline int __double2hiint(double x) { int64_t b; memcpy(&b, &x, 8); return (int)(b >> 32); }
+static inline int __double2loint(double x) { int64_t b; memcpy(&b, &x, 8); return (int)(b & 0xffffffff); }
+static inline double __hiloint2double(int hi, int lo) { int64_t b = ((int64_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &b, 8); return x; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline long long clock64() { return 0; }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicExch(T *p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicMin(T *p, T v) { T o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+template <class T> static inline T atomicMax(T *p, T v) { T o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
+template <class T> static inline T __ldcg(const T *p) { return *(const volatile T *)p; }
+template <class T> static inline void __stcg(T *p, T v) { *(volatile T *)p = v; }

@@ -1,0 +1,117 @@
+"""The B-grid CUDA kernels run thread by thread ON THE HOST.
+
+tests/emu_bgrid.cpp includes the kernel translation unit cice_b200/csrc/evp_kernels.cu unchanged (EVP_HOST_EMU: launchers compiled
+out, the inline-PTX helpers of evp_ptx.cuh replaced by their plain C++ meaning) on top of tests/cuda_emu.h, which makes every CUDA
+thread of a CTA a host thread (pthread barriers for __syncthreads, counters for named barriers, mailboxes for warp shuffles, GCC
+atomics).  Several subcycles of the ping-pong on one block must equal the oracle bit for bit -- stresses, velocities including the
+on-rank cyclic ghost copies, the last subcycle's diagnostics -- for the split kernels, every selectable form of the fused kernel
+(the default one included), the strip kernel, the four- and two-lanes-per-cell kernels and the in-kernel-halo instantiation
+without peers.  This is the CPU-side check of the kernels' index logic, ownership rules and hand-overs; the hardware's own
+division / square-root seeds, timing and inter-CTA memory ordering are what the -m gpu tests add."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cice_b200 import abi, synth
+
+
+
+class KParams(C.Structure):   # cice_b200/csrc/evp_internal.h
+    _fields_ = [(n, C.c_double) for n in ("arlx1i", "denom1", "revp", "brlx", "e_factor", "epp2i", "capping", "Ktens", "u0", "cosw",
+                                          "sinw", "rhow", "deltaminEVP")] + [("visc_method", C.c_int)]
+
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# (kind, sub) of emu_bgrid_run
+KERNELS = {
+    "split": (0, 0),
+    "fused-v16": (1, 0), "fused-v17-spec-loads": (1, 1), "fused-v18-cp-async": (1, 2), "fused-v19-both": (1, 3),
+    "fused-v23-default": (1, 4), "fused-v21": (1, 5), "fused-v22": (1, 7), "fused-v31-pair-barriers": (1, 12), "fused-spec-body-plain": (1, 16),
+    "strip-m1": (2, 1), "strip-m2": (2, 2), "strip-m3": (2, 3),
+    "four-lanes": (3, 0),
+    "two-lanes-32x8-shuffle": (4, 0), "two-lanes-16x8-shuffle": (4, 1), "two-lanes-32x4-shuffle": (4, 2), "two-lanes-16x16-shuffle": (4, 3),
+    "two-lanes-32x8-warp-pairs": (4, 4), "two-lanes-32x4-warp-pairs": (4, 5),
+    "two-lanes-32x8-shuffle-IL": (4, 8), "two-lanes-16x8-shuffle-IL": (4, 9), "two-lanes-32x4-shuffle-IL": (4, 10),
+    "two-lanes-16x16-shuffle-IL": (4, 11), "two-lanes-32x8-warp-pairs-IL": (4, 12), "two-lanes-32x4-warp-pairs-IL": (4, 13),
+    "p2p-no-peers-edge-first": (5, 0), "p2p-no-peers-no-counter": (5, 1),
+}
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emu") / "libemu_bgrid.so")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    cmd = ["/usr/bin/g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", cuda_inc,
+           "-I", os.path.join(ROOT, "cice_b200", "csrc"), "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emu_bgrid.cpp"), "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return C.CDLL(out)
+
+
+def run_emulated(emu, c, kind, sub):
+    g, f = c.grid, c.copy_fields()
+    assert g["nblocks"] == 1
+    nxb, nyb = g["nx_block"], g["ny_block"]
+    k = KParams(**{nm: float(c.params.get(nm, 0.0)) for nm, _ in KParams._fields_[:-1]})
+    sig = np.ascontiguousarray(np.stack([f[nm][0] for nm in abi.STRESS]))
+    geo = np.ascontiguousarray(np.stack([np.asarray(g[nm][0]) for nm in abi.GRID_STATIC]))
+    inp = np.ascontiguousarray(np.stack([f[nm][0] for nm in ("cdn_ocnU", "aiU", "uocnU", "vocnU", "waterxU", "wateryU", "forcexU", "forceyU",
+                                                             "umassdti", "fmU", "TbU")]))
+    diag = np.zeros((4, nyb, nxb))
+    u, v = f["uvel"][0].copy(), f["vvel"][0].copy()
+    strength = np.ascontiguousarray(f["strength"][0])
+    pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    pi = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    mT, mU = np.ascontiguousarray(f["iceTmask"][0]), np.ascontiguousarray(f["iceUmask"][0])
+    cyc = abi.BNDY_NAMES["cyclic"]
+    rc = emu.emu_bgrid_run(kind, sub, nxb, nyb, int(g["ew_boundary_type"] == cyc), int(g["ns_boundary_type"] == cyc), C.byref(k),
+                           int(c.params["ndte"]), pi(mT), pi(mU), pd(sig), pd(u), pd(v), pd(geo), pd(strength), pd(inp), pd(diag))
+    assert rc == 0
+    out = {nm: sig[q] for q, nm in enumerate(abi.STRESS)}
+    out.update(uvel=u, vvel=v, strintxU=diag[0], strintyU=diag[1], taubxU=diag[2], taubyU=diag[3])
+    return out
+
+
+CASES = {
+    "tiny-4sub": dict(config="tiny", ndte=4, seed=131),
+    "tiny-5sub-revised": dict(config="tiny", ndte=5, seed=132, revised_evp=True),
+    "wide-3sub": dict(config="tiny", nx=70, ny=17, ndte=3, seed=133, kmt="continents"),
+    "doubly-cyclic-3sub": dict(config="tiny", nx=33, ny=22, ndte=3, seed=134, ns="cyclic"),
+    "S1-2sub": dict(config="tiny", ndte=2),
+    # the N/E ghost T cells fall on the overlap row/column of the last patch (the `own` exception): 30 = 2*15, 21 = 3*7 = 7*3
+    "aligned-16x8-32x4": dict(config="tiny", nx=30, ny=21, ndte=2, seed=135),
+    "aligned-32x8-16x16": dict(config="tiny", nx=62, ny=30, ndte=2, seed=136, ns="cyclic"),   # 62 = 2*31, 30 = 2*15
+}
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_kernel_text_on_the_host_equals_the_oracle(oracle_mod, emu, case, kernel):
+    c = synth.make_case(**CASES[case])
+    if case == "tiny-4sub":
+        c.params.update(capping=0.0, Ktens=0.2, cosw=0.9, sinw=0.4358898943540674)   # general branches too
+    ref = c.copy_fields()
+    oracle_mod.evp_run_bgrid(c.grid, c.params, ref)
+    got = run_emulated(emu, c, *KERNELS[kernel])
+    for nm in abi.STRESS + ("uvel", "vvel", "strintxU", "strintyU", "taubxU", "taubyU"):
+        assert np.array_equal(got[nm].view(np.int64), ref[nm][0].view(np.int64)), (nm, int((got[nm] != ref[nm][0]).sum()))
+
+
+def test_fast_path_fallbacks_on_the_host(oracle_mod, emu):
+    """zero and denormal-range operands: the hand-scheduled division / square root must report out-of-range and the built-in
+    operators take over (the wiring of the fallbacks; the hardware seeds themselves are covered by the -m gpu twin of this test)."""
+    c = synth.make_case("tiny", seed=21, ndte=3)
+    for n in ("uvel", "vvel", "uocnU", "vocnU", "forcexU", "forceyU", "waterxU", "wateryU"):
+        c.fields[n][...] = 0.0
+    c.fields["strength"][...] *= 1e-300
+    ref = c.copy_fields()
+    oracle_mod.evp_run_bgrid(c.grid, c.params, ref)
+    for kernel in ("fused-v23-default", "two-lanes-32x8-shuffle-IL"):
+        got = run_emulated(emu, c, *KERNELS[kernel])
+        for nm in abi.STRESS + ("uvel", "vvel", "strintxU", "strintyU", "taubxU", "taubyU"):
+            assert np.array_equal(got[nm].view(np.int64), ref[nm][0].view(np.int64)), (kernel, nm)

@@ -305,7 +305,7 @@ def test_fused_variants_bitwise(oracle_mod, evp_lib, monkeypatch, variant, extra
 
 
 # Two lanes per T cell (cice_b200/csrc/evp_lane2.cuh): written at the end of round 1 after the GPU budget was spent.  The kernel text
-# is checked bit for bit against the oracle on the host (tests/test_emu_lane2.py) but has not run on a GPU yet, so this test is
+# is checked bit for bit against the oracle on the host (tests/test_emu_bgrid.py) but has not run on a GPU yet, so this test is
 # opt-in until it has (EVP_B200_TEST_CANDIDATES=1; scripts/job_r2_candidates.sh runs it first thing in round 2).
 CANDIDATES = pytest.mark.skipif(os.environ.get("EVP_B200_TEST_CANDIDATES", "0") != "1",
                                 reason="round-2 candidate kernels: host-emulated only so far; set EVP_B200_TEST_CANDIDATES=1")
