@@ -132,6 +132,21 @@ def make_deform(d, npl_total, e_factor):
     return s, keep
 
 
+class Finish(C.Structure):   # evp_b200_finish_t
+    _fields_ = [("strocnxU", _pd), ("strocnyU", _pd), ("rhow", C.c_double), ("cosw", C.c_double), ("sinw", C.c_double)]
+
+
+def make_finish(d, npl_total, rhow, cosw, sinw):
+    s, keep = Finish(), {}
+    for n in ("strocnxU", "strocnyU"):
+        a = d[n]
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == npl_total, n
+        keep[n] = a
+        setattr(s, n, _ptr(a, C.c_double))
+    s.rhow, s.cosw, s.sinw = float(rhow), float(cosw), float(sinw)
+    return s, keep
+
+
 def _ptr(a, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))
 

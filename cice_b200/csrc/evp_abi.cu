@@ -778,22 +778,48 @@ static int calloc_dom(double *&p) {
 }
 
 // deformations on the device-resident final velocities
+// dom arrays + block-layout staging of their own for the post-loop entry points (deformations, dyn_finish)
+static int ensure_aux_buffers() {
+  if (!g.dbuf.empty()) return 0;
+  for (int q = 0; q < 8; ++q) {
+    double *p = nullptr;
+    CK(cudaMalloc(&p, g.ndom * sizeof(double)));
+    g.dbuf.push_back(p);
+    double *st = nullptr;
+    CK(cudaMalloc(&st, g.nblk_elems * sizeof(double)));
+    g.dstage.push_back(st);
+  }
+  return 0;
+}
+
+static int do_dyn_finish(evp_b200_finish_t *ff) {
+  if (!g.inited || !g.uploaded) return fail("evp_b200_dyn_finish: no velocities on the device (run the loop first)");
+  if (!ff || !ff->strocnxU || !ff->strocnyU) return fail("evp_b200_dyn_finish: null argument");
+  CK(cudaSetDevice(g.device));
+  if (ensure_aux_buffers()) return 1;
+  const size_t bblk = g.nblk_elems * sizeof(double);
+  double *host[2] = {ff->strocnxU, ff->strocnyU};
+  for (int q = 0; q < 2; ++q) {  // inout: points off the U list keep the caller's values
+    CK(cudaMemcpyAsync(g.dstage[q], host[q], bblk, cudaMemcpyHostToDevice, g.stream));
+    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(g.dbuf[q], g.dstage[q], g.d_gsrc, (int)g.ndom);
+  }
+  CK(exact::launch_finish(g.dom, g.cur, g.dbuf[0], g.dbuf[1], ff->rhow, ff->cosw, ff->sinw, g.stream));
+  for (int q = 0; q < 2; ++q) {
+    unpack_f64<<<grid_blocks(g.n_int), 256, 0, g.stream>>>(g.dstage[q], g.dbuf[q], g.d_int_lin, g.d_int_dom, g.n_int);
+    CK(cudaMemcpyAsync(host[q], g.dstage[q], bblk, cudaMemcpyDeviceToHost, g.stream));
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
 static int do_deformations(evp_b200_deform_t *dd) {
   if (!g.inited || !g.uploaded) return fail("evp_b200_deformations: no velocities on the device (run the loop first)");
   if (!dd || !dd->dxU || !dd->dyU || !dd->tarear || !dd->divu || !dd->shear || !dd->vort || !dd->rdg_conv || !dd->rdg_shear)
     return fail("evp_b200_deformations: null argument");
   CK(cudaSetDevice(g.device));
   const size_t bblk = g.nblk_elems * sizeof(double);
-  if (g.dbuf.empty()) {
-    for (int q = 0; q < 8; ++q) {
-      double *p = nullptr;
-      CK(cudaMalloc(&p, g.ndom * sizeof(double)));
-      g.dbuf.push_back(p);
-      double *st = nullptr;
-      CK(cudaMalloc(&st, bblk));
-      g.dstage.push_back(st);
-    }
-  }
+  if (ensure_aux_buffers()) return 1;
   const double *src[8] = {dd->dxU, dd->dyU, dd->tarear, dd->divu, dd->shear, dd->vort, dd->rdg_conv, dd->rdg_shear};
   double *dst[5] = {dd->divu, dd->shear, dd->vort, dd->rdg_conv, dd->rdg_shear};
   for (int q = 0; q < 8; ++q) {
@@ -1150,6 +1176,7 @@ int evp_b200_finalize(void) {
 }
 
 int evp_b200_deformations(evp_b200_deform_t *d) { return do_deformations(d); }
+int evp_b200_dyn_finish(evp_b200_finish_t *f) { return do_dyn_finish(f); }
 int evp_b200_init_cgrid(const evp_b200_cgrid_t *cg) { return do_init_cgrid(cg); }
 int evp_b200_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) { return do_run_cgrid(p, f); }
 int evp_b200_run_cdgrid(const evp_b200_params_t *p, evp_b200_cdfields_t *f) { return do_run_cdgrid(p, f); }

@@ -140,7 +140,30 @@ __global__ void __launch_bounds__(256) deform_kernel(const __grid_constant__ Dom
   vort[c] = 0.5 * ta * (dvdxn + dvdxs - dudye - dudyw);
 }
 
+// dyn_finish (ice_dyn_shared.F90:1291-1365): the ice-ocean stress at the ice U points, from the resident velocities and the
+// U-point inputs of the last upload; points off the U list keep what the arrays held
+__global__ void __launch_bounds__(256) finish_kernel(const __grid_constant__ Dom d, const double *__restrict__ U,
+                                                     const double *__restrict__ V, double *__restrict__ strocnx,
+                                                     double *__restrict__ strocny, double rhow, double cosw, double sinw) {
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > d.nx || j > d.ny) return;
+  const int c = at(d, i, j);
+  if (!d.maskU[c]) return;
+  const double du = d.uocn[c] - U[c], dv = d.vocn[c] - V[c];
+  double vrel = rhow * d.cdn[c] * sqrt(du * du + dv * dv);
+  vrel = vrel * d.aiu[c];
+  const double sg = copysign(1.0, d.fm[c]);
+  strocnx[c] = vrel * (du * cosw - dv * sinw * sg);
+  strocny[c] = vrel * (dv * cosw + du * sinw * sg);
+}
+
 #ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
+cudaError_t launch_finish(const Dom &d, int cur, double *strocnx, double *strocny, double rhow, double cosw, double sinw, cudaStream_t s) {
+  dim3 b(32, 8), g((d.nx + b.x - 1) / b.x, (d.ny + b.y - 1) / b.y);
+  finish_kernel<<<g, b, 0, s>>>(d, d.u[cur], d.v[cur], strocnx, strocny, rhow, cosw, sinw);
+  return cudaGetLastError();
+}
 cudaError_t launch_deform(const Dom &d, int cur, const double *dxU, const double *dyU, const double *tarear, double *divu,
                           double *shear, double *vort, double *rdg_conv, double *rdg_shear, double e_factor, cudaStream_t s) {
   dim3 b(32, 8), g((d.nx + 1 + b.x - 1) / b.x, (d.ny + 1 + b.y - 1) / b.y);

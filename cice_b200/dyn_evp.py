@@ -118,6 +118,14 @@ def deformations(d, e_factor):
     return d
 
 
+def dyn_finish(d, rhow, cosw=1.0, sinw=0.0):
+    """`dyn_finish` (ice_dyn_shared.F90:1291-1365) from the velocities and U-point inputs the last loop left on the device;
+    d["strocnxU"], d["strocnyU"] are inout block arrays (points off the U list keep their values)."""
+    s, keep = abi.make_finish(d, _state["npl"], rhow, cosw, sinw)
+    check(load().evp_b200_dyn_finish(C.byref(s)), "evp_b200_dyn_finish")
+    return d
+
+
 def upload(fields):
     f, keep = _fields(fields)
     check(load().evp_b200_upload(C.byref(f)), "evp_b200_upload")

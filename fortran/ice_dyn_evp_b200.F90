@@ -25,6 +25,7 @@ module ice_dyn_evp_b200
   private
   public :: dyn_evp_b200_init, dyn_evp_b200_run, dyn_evp_b200_finalize
   public :: dyn_evp_b200_init_cgrid, dyn_evp_b200_run_cgrid   ! grid_ice = 'C' (ice_dyn_evp.F90:936-1101)
+  public :: dyn_evp_b200_deformations, dyn_evp_b200_finish    ! the two steps right after the loop, from the device-resident velocities
 
   integer(c_int32_t), parameter :: EVP_B200_ABI_VERSION = 2
   integer(c_int32_t), parameter :: BNDY_OPEN = 0, BNDY_CLOSED = 1, BNDY_CYCLIC = 2, BNDY_TRIPOLE = 3
@@ -75,7 +76,28 @@ module ice_dyn_evp_b200
      type(c_ptr) :: iceTmask, iceUmask, iceEmask, iceNmask
   end type evp_b200_cfields_t
 
+  ! evp_b200_deform_t
+  type, bind(C) :: evp_b200_deform_t
+     type(c_ptr) :: dxU, dyU, tarear
+     type(c_ptr) :: divu, shear, vort, rdg_conv, rdg_shear
+     real(c_double) :: e_factor
+  end type evp_b200_deform_t
+
+  ! evp_b200_finish_t
+  type, bind(C) :: evp_b200_finish_t
+     type(c_ptr) :: strocnxU, strocnyU
+     real(c_double) :: rhow, cosw, sinw
+  end type evp_b200_finish_t
+
   interface
+     integer(c_int) function evp_b200_deformations(d) bind(C, name='evp_b200_deformations')
+       import :: c_int, evp_b200_deform_t
+       type(evp_b200_deform_t), intent(inout) :: d
+     end function evp_b200_deformations
+     integer(c_int) function evp_b200_dyn_finish(f) bind(C, name='evp_b200_dyn_finish')
+       import :: c_int, evp_b200_finish_t
+       type(evp_b200_finish_t), intent(inout) :: f
+     end function evp_b200_dyn_finish
      integer(c_int) function evp_b200_init_cgrid(cgrid) bind(C, name='evp_b200_init_cgrid')
        import :: c_int, evp_b200_cgrid_t
        type(evp_b200_cgrid_t), intent(in) :: cgrid
@@ -281,6 +303,35 @@ contains
        call check(evp_b200_run_bgrid(p, f), 'evp_b200_run_bgrid')
     endif
   end subroutine dyn_evp_b200_run
+
+  !---------------------------------------------------------------------
+  ! `deformations` (ice_dyn_shared.F90:1756-1860; the per-block call at ice_dyn_evp.F90:920-934) for all blocks at once, from
+  ! the velocities dyn_evp_b200_run left on the device.  The five arrays keep their values off the ice T cells.
+  subroutine dyn_evp_b200_deformations(divu, shear, vort, rdg_conv, rdg_shear)
+    use ice_grid,       only: dxU, dyU, tarear
+    use ice_dyn_shared, only: e_factor
+    real(kind=dbl_kind), dimension(:,:,:), intent(inout), target, contiguous :: divu, shear, vort, rdg_conv, rdg_shear
+    type(evp_b200_deform_t) :: d
+    d%dxU = c_loc(dxU);  d%dyU = c_loc(dyU);  d%tarear = c_loc(tarear)
+    d%divu = c_loc(divu);  d%shear = c_loc(shear);  d%vort = c_loc(vort);  d%rdg_conv = c_loc(rdg_conv);  d%rdg_shear = c_loc(rdg_shear)
+    d%e_factor = e_factor
+    call check(evp_b200_deformations(d), 'evp_b200_deformations')
+  end subroutine dyn_evp_b200_deformations
+
+  !---------------------------------------------------------------------
+  ! `dyn_finish` (ice_dyn_shared.F90:1291-1365; the per-block call at ice_dyn_evp.F90:1392-1405) for all blocks at once: the
+  ! velocities, cdn_ocnU, uocnU, vocnU, aiU, fmU and iceUmask of the last dyn_evp_b200_run are still on the device.
+  subroutine dyn_evp_b200_finish(strocnxU, strocnyU)
+    use ice_dyn_shared, only: cosw, sinw
+    use icepack_intfc,  only: icepack_query_parameters
+    real(kind=dbl_kind), dimension(:,:,:), intent(inout), target, contiguous :: strocnxU, strocnyU
+    type(evp_b200_finish_t) :: f
+    real(kind=dbl_kind) :: rhow
+    call icepack_query_parameters(rhow_out=rhow)
+    f%strocnxU = c_loc(strocnxU);  f%strocnyU = c_loc(strocnyU)
+    f%rhow = rhow;  f%cosw = cosw;  f%sinw = sinw
+    call check(evp_b200_dyn_finish(f), 'evp_b200_dyn_finish')
+  end subroutine dyn_evp_b200_finish
 
   !---------------------------------------------------------------------
   ! grid_ice = 'C': once, after dyn_evp_b200_init (the ratio arrays exist after init_evp, ice_dyn_evp.F90:218-240)

@@ -246,6 +246,17 @@ typedef struct {
 } evp_b200_deform_t;
 int evp_b200_deformations(evp_b200_deform_t *d);
 
+/* ---- next row (second half): dyn_finish ------------------------------------------
+ * `dyn_finish` (ice_dyn_shared.F90:1291-1365), called by evp() after the loop (ice_dyn_evp.F90:1392-1405): the ice-ocean stress
+ * strocnxU, strocnyU at the ice U points from the final (uvel,vvel) and from cdn_ocnU, uocnU, vocnU, aiU, fmU, iceUmask of the
+ * last upload -- all still resident on the device, so only the two results cross the boundary.
+ * The two arrays are inout: points off the U list keep the caller's values, as in the reference. */
+typedef struct {
+  double *strocnxU, *strocnyU;   /* inout, (nx_block,ny_block,max_blocks) */
+  double rhow, cosw, sinw;       /* icepack rhow; ice_dyn_shared.F90:66-70 */
+} evp_b200_finish_t;
+int evp_b200_dyn_finish(evp_b200_finish_t *f);
+
 /* The same call split in three so that a caller which keeps dynamics state on the device
  *  -- and bench.py's device-resident timing -- can run the loop alone.
  * run_bgrid == upload + subcycle + download. */

@@ -667,3 +667,29 @@ int orc_deformations(const evp_b200_grid_t *g, const int32_t *iceTmask, const do
   }
   return 0;
 }
+
+/* ---------------------------------------------------------------------------------------
+ * dyn_finish: shared.F90:1291-1365 (called from evp.F90:1392-1405 after the loop), over the U list
+ * (ilo:ihi, jlo:jhi where iceUmask)
+ * ------------------------------------------------------------------------------------- */
+int orc_dyn_finish(const evp_b200_grid_t *g, const int32_t *iceUmask, const double *uvel, const double *vvel, const double *Cw,
+                   const double *uocn, const double *vocn, const double *aiX, const double *fm, evp_b200_finish_t *f) {
+  if (check_grid(g)) return 1;
+  const int nx_block = g->nx_block;
+  const size_t npl = (size_t)g->nx_block * g->ny_block;
+  for (int b = 0; b < g->nblocks; ++b) {
+    const size_t o = (size_t)b * npl;
+    for (int j = g->jlo[b]; j <= g->jhi[b]; ++j)
+      for (int i = g->ilo[b]; i <= g->ihi[b]; ++i) {
+        const size_t c = o + IX(i, j);
+        if (!iceUmask[c]) continue;
+        /* shared.F90:1343-1353 */
+        const double du = uocn[c] - uvel[c], dv = vocn[c] - vvel[c];
+        double vrel = f->rhow * Cw[c] * sqrt(du * du + dv * dv);
+        vrel = vrel * aiX[c];
+        f->strocnxU[c] = vrel * (du * f->cosw - dv * f->sinw * copysign(c1, fm[c]));
+        f->strocnyU[c] = vrel * (dv * f->cosw + du * f->sinw * copysign(c1, fm[c]));
+      }
+  }
+  return 0;
+}

@@ -55,6 +55,9 @@ int orc_evp_run_cdgrid(const evp_b200_grid_t *grid, const evp_b200_cgrid_t *cgri
 /* deformations: ice_dyn_shared.F90:1756-1860 over the T list (ilo:ihi+1, jlo:jhi+1 where iceTmask) */
 int orc_deformations(const evp_b200_grid_t *grid, const int32_t *iceTmask, const double *uvel, const double *vvel,
                      evp_b200_deform_t *d);
+/* dyn_finish: ice_dyn_shared.F90:1291-1365 over the U list (ilo:ihi, jlo:jhi where iceUmask) */
+int orc_dyn_finish(const evp_b200_grid_t *grid, const int32_t *iceUmask, const double *uvel, const double *vvel, const double *Cw,
+                   const double *uocn, const double *vocn, const double *aiX, const double *fm, evp_b200_finish_t *f);
 
 /* NE-corner / vector halo update of nfld fields, the dyn_haloUpdate call of
  * ice_dyn_evp.F90:908-910 (ice_boundary.F90:1066-1760; expectations halochk.F90:530-830).

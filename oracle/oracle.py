@@ -56,6 +56,8 @@ def lib(variant="exact"):
         L.orc_evp_run_cgrid.restype = C.c_int
         L.orc_deformations.argtypes = [C.POINTER(abi.Grid), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(abi.Deform)]
         L.orc_deformations.restype = C.c_int
+        L.orc_dyn_finish.argtypes = [C.POINTER(abi.Grid), C.POINTER(C.c_int32)] + [C.POINTER(C.c_double)] * 7 + [C.POINTER(abi.Finish)]
+        L.orc_dyn_finish.restype = C.c_int
         L.orc_halo_update.argtypes = [C.POINTER(abi.Grid), C.POINTER(C.POINTER(C.c_double)), C.c_int, C.c_int, C.c_int]
         L.orc_halo_update.restype = C.c_int
         L.orc_last_error.restype = C.c_char_p
@@ -133,6 +135,21 @@ def deformations(grid, iceTmask, uvel, vvel, d, e_factor, variant="exact"):
     rc = L.orc_deformations(C.byref(g), iceTmask.ctypes.data_as(pi), uvel.ctypes.data_as(pd), vvel.ctypes.data_as(pd), C.byref(s))
     if rc:
         raise RuntimeError("oracle deformations: " + L.orc_last_error().decode())
+    return d
+
+
+def dyn_finish(grid, fields, d, rhow, cosw, sinw, variant="exact"):
+    """dyn_finish (ice_dyn_shared.F90:1291-1365) from the loop's final velocities and U-point inputs in `fields`;
+    d["strocnxU"], d["strocnyU"] are inout."""
+    L = lib(variant)
+    g, kg = abi.make_grid(grid)
+    s, keep = abi.make_finish(d, _npl(grid), rhow, cosw, sinw)
+    pd, pi = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    arr = [np.ascontiguousarray(fields[n], dtype=np.float64) for n in ("uvel", "vvel", "cdn_ocnU", "uocnU", "vocnU", "aiU", "fmU")]
+    mask = np.ascontiguousarray(fields["iceUmask"], dtype=np.int32)
+    rc = L.orc_dyn_finish(C.byref(g), mask.ctypes.data_as(pi), *[a.ctypes.data_as(pd) for a in arr], C.byref(s))
+    if rc:
+        raise RuntimeError("oracle dyn_finish: " + L.orc_last_error().decode())
     return d
 
 

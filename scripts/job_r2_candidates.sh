@@ -1,13 +1,13 @@
 #!/bin/bash
 # round 2, first GPU job (one GPU): the candidates written at the end of round 1 without a GPU.
-#   1. parity of the two-lanes-per-cell kernel variants (host-emulated so far: tests/test_emu_bgrid.py)
+#   1. parity of the two-lanes-per-cell kernel variants and of evp_b200_dyn_finish (host-emulated so far: tests/test_emu_bgrid.py)
 #   2. gx1 bench line per variant (ms per step, roofline fraction) next to the default
 #   3. the in-kernel-halo kernel with its tile table in constant memory, in the one-GPU no-peer self test
 # Output: gpurun_out/r2_candidates.txt.   /usr/local/graft/bin/gpurun --timeout 1500 -- bash scripts/job_r2_candidates.sh
 mkdir -p gpurun_out
 {
 echo "== parity of variants 40-53"
-EVP_B200_TEST_CANDIDATES=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k two_lane 2>&1 | tail -15
+EVP_B200_TEST_CANDIDATES=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "two_lane or dyn_finish" 2>&1 | tail -15
 b() { timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu "$@" 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], round(d['roofline']['frac'],4))"; }
 echo "== gx1, ms per step and roofline fraction"
 echo "default: $(b)"

@@ -138,3 +138,31 @@ extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, i
   }
   return 0;
 }
+
+// the two post-loop kernels on one block: deform_kernel (T cells 1..nx+1, 1..ny+1) and finish_kernel (U points 1..nx, 1..ny)
+extern "C" int emu_deform_run(int nxb, int nyb, const int32_t *maskT, const double *u, const double *v, const double *geo /*[10][n]*/,
+                              const double *dxU, const double *dyU, const double *tarear, double *out /*[5][n]: divu shear vort rdg_conv
+                              rdg_shear*/, double e_factor) {
+  const size_t n = (size_t)nxb * nyb;
+  std::vector<unsigned char> mT(n);
+  for (size_t q = 0; q < n; ++q) mT[q] = maskT[q] != 0;
+  Dom d{};
+  d.nx = nxb - 2; d.ny = nyb - 2; d.ld = nxb; d.nyd = nyb;
+  d.dxT = geo; d.dyT = geo + n; d.cxp = geo + 4 * n; d.cyp = geo + 5 * n; d.cxm = geo + 6 * n; d.cym = geo + 7 * n;
+  d.maskT = mT.data();
+  emu::launch({(d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8, 1}, {32, 8, 1},
+              [&] { deform_kernel(d, u, v, dxU, dyU, tarear, out, out + n, out + 2 * n, out + 3 * n, out + 4 * n, e_factor); });
+  return 0;
+}
+extern "C" int emu_finish_run(int nxb, int nyb, const int32_t *maskU, const double *u, const double *v, const double *in /*[11][n]*/,
+                              double *strocnx, double *strocny, double rhow, double cosw, double sinw) {
+  const size_t n = (size_t)nxb * nyb;
+  std::vector<unsigned char> mU(n);
+  for (size_t q = 0; q < n; ++q) mU[q] = maskU[q] != 0;
+  Dom d{};
+  d.nx = nxb - 2; d.ny = nyb - 2; d.ld = nxb; d.nyd = nyb;
+  d.cdn = in; d.aiu = in + n; d.uocn = in + 2 * n; d.vocn = in + 3 * n; d.fm = in + 9 * n;
+  d.maskU = mU.data();
+  emu::launch({(d.nx + 31) / 32, (d.ny + 7) / 8, 1}, {32, 8, 1}, [&] { finish_kernel(d, u, v, strocnx, strocny, rhow, cosw, sinw); });
+  return 0;
+}

@@ -891,6 +891,49 @@ def generate_d():
 
 
 # ------------------------------------------------------------------------------------------
+# dyn_finish (ice_dyn_shared.F90:1291-1365): the ice-ocean stress after the loop, on the state a set-S2
+# case reaches after 3 subcycles, with a turning angle so that the sinw*sign(fm) terms are exercised
+# ------------------------------------------------------------------------------------------
+FFIELDS = ("strocnxU", "strocnyU")
+FINISH_ANGLE = dict(cosw=0.9, sinw=0.4358898943540674)
+
+
+def finish_inputs(synth, oracle_mod, seed=82):
+    c = synth.make_case("tiny", seed=seed, ndte=3)
+    c.params.update(FINISH_ANGLE)
+    f = c.copy_fields()
+    oracle_mod.evp_run_bgrid(c.grid, c.params, f)           # the velocities dyn_finish sees are the loop's final ones
+    d = {n: np.full(f["uvel"].shape, -7.0) for n in FFIELDS}
+    return c, f, d
+
+
+def generate_f():
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from cice_b200 import synth
+    from oracle import oracle as oracle_mod
+    c, f, d = finish_inputs(synth, oracle_mod)
+    g, p = c.grid, c.params
+    reg = {}
+    reg["dyn_finish"] = Sub(F_SHARED, "dyn_finish", reg)
+    env = {"math": math, "_sq": lambda x: x * x, "_sign": lambda a, b: math.copysign(abs(a), b), "ICEPACK": {"rhow": float(p["rhow"])},
+           "cosw": float(p["cosw"]), "sinw": float(p["sinw"])}
+    env.update(reference_constants())
+    env = {k.lower() if k != "ICEPACK" else k: v for k, v in env.items()}
+    exec(compile(reg["dyn_finish"].python(), f"<dyn_finish transliterated from {REF}>", "exec"), env)
+    ilo, ihi, jlo, jhi = (int(g[k][0]) for k in ("ilo", "ihi", "jlo", "jhi"))
+    Ui, Uj = [], []
+    for j in range(jlo, jhi + 1):
+        for i in range(ilo, ihi + 1):
+            if f["iceUmask"][0, j - 1, i - 1]:
+                Ui.append(i); Uj.append(j)
+    A = lambda a: FArr(np.asarray(a, dtype=np.float64)[0])
+    out = {k: d[k].copy() for k in FFIELDS}
+    env["dyn_finish"](g["nx_block"], g["ny_block"], len(Ui), A(f["cdn_ocnU"]), FArr(np.array(Ui)), FArr(np.array(Uj)), A(f["uvel"]), A(f["vvel"]),
+                      A(f["uocnU"]), A(f["vocnU"]), A(f["aiU"]), A(f["fmU"]), FArr(out["strocnxU"][0]), FArr(out["strocnyU"][0]))
+    return {f"fcase0_{k}": v for k, v in out.items()}
+
+
+# ------------------------------------------------------------------------------------------
 # dyn_prep2 (ice_dyn_shared.F90:593-839): the routine that builds every time-varying input of the loop.  Run on the
 # synthetic state, it must reproduce what cice_b200/synth.py feeds the kernels and the bench (SURVEY 8d inputs).
 # ------------------------------------------------------------------------------------------
@@ -1054,6 +1097,7 @@ if __name__ == "__main__":
     vec = generate()
     cvec = generate_c()
     dvec = generate_d()
+    dvec.update(generate_f())
     cdvec = generate_cd()
     pvec = {}
     for cfg in ("tiny", "gx3", "gx1"):
@@ -1072,7 +1116,7 @@ if __name__ == "__main__":
         meta = {"_how": "python tests/golden/ref_translit.py --write  (transliterates the reference's Fortran subroutines under /root/reference "
                         "-- B grid: stress, stepu, strain_rates, visc_replpress; C grid: strain_rates_U, strain_rates_Tdt, stressC_T, stressC_U, "
                         "div_stress_Ex/Ny, stepu_C, stepv_C, grid_average_X2Y_1/X2YS/X2YA; CD grid: stressCD_T, stressCD_U, strain_rates_Tdtsd, "
-                        "div_stress_Ey/Nx, stepuv_CD; deformations; ice_constants -- and runs them; see the module docstring)",
+                        "div_stress_Ey/Nx, stepuv_CD; deformations; dyn_finish; ice_constants -- and runs them; see the module docstring)",
                 "cases": [dict(kw) for kw in CASES], "ccases": [dict(kw) for kw in CCASES],
                 "cdcases": [dict(kw) for kw in CDCASES],
                 "sha256": {k: sha(v) for k, v in {**vec, **cvec, **dvec, **cdvec, **pvec}.items()}}

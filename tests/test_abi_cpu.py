@@ -36,6 +36,8 @@ def test_struct_layouts_match_header():
     assert C.sizeof(abi.CGrid) == 20 * 8
     assert C.sizeof(abi.CFields) == 47 * 8
     assert C.sizeof(abi.CDFields) == 58 * 8
+    assert C.sizeof(abi.Deform) == 9 * 8
+    assert C.sizeof(abi.Finish) == 5 * 8
     txt = open(os.path.join(ROOT, "include", "evp_b200.h")).read()
     body = txt[txt.index("typedef struct {", txt.index("Time-varying fields of one call")):txt.index("} evp_b200_fields_t;")]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
@@ -137,6 +139,8 @@ def test_fortran_shim_types_match_the_header():
     assert members("evp_b200_cfields_t") == abi.CFIELDS_ORDER + abi.CFIELDS_MASK
     assert members("evp_b200_grid_t") == tuple(n for n, _ in abi.Grid._fields_)
     assert members("evp_b200_params_t") == tuple(n for n, _ in abi.Params._fields_)
+    assert members("evp_b200_deform_t") == tuple(n for n, _ in abi.Deform._fields_)
+    assert members("evp_b200_finish_t") == tuple(n for n, _ in abi.Finish._fields_)
     # every C entry point the shim binds exists in the header
     hdr = open(os.path.join(ROOT, "include", "evp_b200.h")).read()
     for name in re.findall(r"bind\(C,\s*name='(\w+)'\)", txt):

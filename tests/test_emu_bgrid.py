@@ -115,3 +115,42 @@ def test_fast_path_fallbacks_on_the_host(oracle_mod, emu):
         got = run_emulated(emu, c, *KERNELS[kernel])
         for nm in abi.STRESS + ("uvel", "vvel", "strintxU", "strintyU", "taubxU", "taubyU"):
             assert np.array_equal(got[nm].view(np.int64), ref[nm][0].view(np.int64)), (kernel, nm)
+
+
+def test_post_loop_kernels_on_the_host(oracle_mod, emu):
+    """deform_kernel and finish_kernel (`deformations`, `dyn_finish`) against the oracle, which is itself pinned to
+    the reference source for both (tests/test_oracle.py)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_translit as rt
+    pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    pi = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    emu.emu_deform_run.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32)] + [C.POINTER(C.c_double)] * 7 + [C.c_double]
+    emu.emu_finish_run.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32)] + [C.POINTER(C.c_double)] * 5 + [C.c_double] * 3
+    # deformations
+    c, d = rt.deform_inputs(synth)
+    g = c.grid
+    nxb, nyb = g["nx_block"], g["ny_block"]
+    ref = oracle_mod.deformations(g, c.fields["iceTmask"], c.fields["uvel"], c.fields["vvel"], {k: v.copy() for k, v in d.items()},
+                                  c.params["e_factor"])
+    geo = np.ascontiguousarray(np.stack([np.asarray(g[nm][0]) for nm in abi.GRID_STATIC]))
+    out = np.ascontiguousarray(np.stack([d[k][0] for k in rt.DFIELDS]))
+    A = lambda a: np.ascontiguousarray(a[0], dtype=np.float64)
+    mT = np.ascontiguousarray(c.fields["iceTmask"][0], dtype=np.int32)
+    u, v, dxU, dyU, tar = A(c.fields["uvel"]), A(c.fields["vvel"]), A(d["dxU"]), A(d["dyU"]), A(d["tarear"])
+    assert emu.emu_deform_run(nxb, nyb, pi(mT), pd(u), pd(v), pd(geo), pd(dxU), pd(dyU), pd(tar), pd(out), float(c.params["e_factor"])) == 0
+    for q, k in enumerate(rt.DFIELDS):
+        assert np.array_equal(out[q].view(np.int64), ref[k][0].view(np.int64)), k
+    # dyn_finish
+    c, f, d = rt.finish_inputs(synth, oracle_mod)
+    g = c.grid
+    nxb, nyb = g["nx_block"], g["ny_block"]
+    ref = oracle_mod.dyn_finish(g, f, {k: v.copy() for k, v in d.items()}, c.params["rhow"], c.params["cosw"], c.params["sinw"])
+    inp = np.ascontiguousarray(np.stack([f[nm][0] for nm in ("cdn_ocnU", "aiU", "uocnU", "vocnU", "waterxU", "wateryU", "forcexU", "forceyU",
+                                                             "umassdti", "fmU", "TbU")]))
+    mU = np.ascontiguousarray(f["iceUmask"][0], dtype=np.int32)
+    u, v, sx, sy = A(f["uvel"]), A(f["vvel"]), A(d["strocnxU"]), A(d["strocnyU"])
+    assert emu.emu_finish_run(nxb, nyb, pi(mU), pd(u), pd(v), pd(inp), pd(sx), pd(sy), float(c.params["rhow"]), float(c.params["cosw"]),
+                              float(c.params["sinw"])) == 0
+    assert np.array_equal(sx.view(np.int64), ref["strocnxU"][0].view(np.int64))
+    assert np.array_equal(sy.view(np.int64), ref["strocnyU"][0].view(np.int64))

@@ -18,6 +18,12 @@ from tests.util import run_oracle, run_gpu, assert_bitwise, assert_close
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
+# Two lanes per T cell (cice_b200/csrc/evp_lane2.cuh): written at the end of round 1 after the GPU budget was spent.  The kernel text
+# is checked bit for bit against the oracle on the host (tests/test_emu_bgrid.py) but has not run on a GPU yet, so this test is
+# opt-in until it has (EVP_B200_TEST_CANDIDATES=1; scripts/job_r2_candidates.sh runs it first thing in round 2).
+CANDIDATES = pytest.mark.skipif(os.environ.get("EVP_B200_TEST_CANDIDATES", "0") != "1",
+                                reason="round-2 candidate kernels: host-emulated only so far; set EVP_B200_TEST_CANDIDATES=1")
+
 KERNELS = [abi.KERNEL_SPLIT, abi.KERNEL_FUSED, abi.KERNEL_PERSISTENT, abi.KERNEL_QUEUE]
 KNAME = {abi.KERNEL_SPLIT: "split", abi.KERNEL_FUSED: "fused", abi.KERNEL_PERSISTENT: "persistent", abi.KERNEL_QUEUE: "queue"}
 
@@ -249,6 +255,32 @@ def test_deformations_after_loop(oracle_mod, evp_lib, bs):
         assert (got[n][ref["iceTmask"] == 0] == -7.0).all(), n
 
 
+@CANDIDATES
+@pytest.mark.parametrize("bs", [None, (25, 29)], ids=["1block", "16blocks"])
+def test_dyn_finish_after_loop(oracle_mod, evp_lib, bs):
+    """next row: `dyn_finish` (ice_dyn_shared.F90:1291-1365) from the velocities and U-point inputs the loop left
+    on the device, bit-identical to the oracle; points off the U list keep the caller's values.  (The kernel text equals the oracle
+    on the host, tests/test_emu_bgrid.py; this entry point was written after the round-1 GPU budget was spent.)"""
+    c = synth.make_case("gx3", ndte=25, block_size=bs, seed=5)
+    c.params.update(cosw=0.9, sinw=0.4358898943540674)
+    ref = run_oracle(oracle_mod, c)
+    mk = lambda: {n: np.full(ref["uvel"].shape, -7.0) for n in ("strocnxU", "strocnyU")}
+    want = oracle_mod.dyn_finish(c.grid, ref, mk(), c.params["rhow"], c.params["cosw"], c.params["sinw"])
+    got, f = mk(), c.copy_fields()
+    evp_lib.dyn_evp_b200_init(c.grid)
+    try:
+        evp_lib.dyn_evp_b200_run(dict(c.params, mode=abi.MODE_EXACT), f)
+        evp_lib.dyn_finish(got, c.params["rhow"], c.params["cosw"], c.params["sinw"])
+        again = mk()
+        evp_lib.dyn_finish(again, c.params["rhow"], c.params["cosw"], c.params["sinw"])
+    finally:
+        evp_lib.dyn_evp_b200_finalize()
+    for n in ("strocnxU", "strocnyU"):
+        assert np.array_equal(got[n].view(np.int64), want[n].view(np.int64)), n
+        assert np.array_equal(again[n].view(np.int64), want[n].view(np.int64)), n
+        assert (got[n][ref["iceUmask"] == 0] == -7.0).all(), n
+
+
 @pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
 def test_edge_cases_no_ice_and_odd_loops(oracle_mod, evp_lib, kernel):
     """(a) no ice anywhere: every array comes back exactly as it went in; (b) ndte = 1 and ndte = 7 (odd loops end
@@ -302,13 +334,6 @@ def test_fused_variants_bitwise(oracle_mod, evp_lib, monkeypatch, variant, extra
         ref = run_oracle(oracle_mod, c)
         got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED)
         assert_bitwise(got, ref)
-
-
-# Two lanes per T cell (cice_b200/csrc/evp_lane2.cuh): written at the end of round 1 after the GPU budget was spent.  The kernel text
-# is checked bit for bit against the oracle on the host (tests/test_emu_bgrid.py) but has not run on a GPU yet, so this test is
-# opt-in until it has (EVP_B200_TEST_CANDIDATES=1; scripts/job_r2_candidates.sh runs it first thing in round 2).
-CANDIDATES = pytest.mark.skipif(os.environ.get("EVP_B200_TEST_CANDIDATES", "0") != "1",
-                                reason="round-2 candidate kernels: host-emulated only so far; set EVP_B200_TEST_CANDIDATES=1")
 
 
 @CANDIDATES

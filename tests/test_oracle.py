@@ -268,6 +268,21 @@ def test_deformations_oracle_matches_vectors_from_reference_source(oracle_mod):
         assert _sha(got[k]) == meta["sha256"][f"dcase0_{k}"], k
 
 
+def test_dyn_finish_oracle_matches_vectors_from_reference_source(oracle_mod):
+    """`dyn_finish` (ice_dyn_shared.F90:1291-1365): the oracle against the transliterated reference text, on the
+    velocities a three-subcycle loop leaves, with a turning angle (the sinw * sign(fm) terms)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ref_translit as rt
+    meta, full = _ref_source_vectors()
+    c, f, d = rt.finish_inputs(synth, oracle_mod)
+    got = oracle_mod.dyn_finish(c.grid, f, d, c.params["rhow"], c.params["cosw"], c.params["sinw"])
+    for k in rt.FFIELDS:
+        assert np.array_equal(got[k].view(np.int64), full[f"fcase0_{k}"].view(np.int64)), k
+        assert _sha(got[k]) == meta["sha256"][f"fcase0_{k}"], k
+        assert (got[k] != -7.0).sum() == (f["iceUmask"] != 0).sum()      # exactly the U list is written
+
+
 @pytest.mark.parametrize("cfg", ["tiny", "gx3", "gx1"])
 def test_synthetic_inputs_follow_reference_dyn_prep2(cfg):
     """the loop's time-varying inputs (umassdti, fmU, waterx/y, forcex/y, the U ice mask, new-ice velocities) that
