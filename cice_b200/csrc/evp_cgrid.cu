@@ -404,13 +404,16 @@ __global__ void cgrid_static_quotients(const __grid_constant__ CDom d, double *r
   r_dyN[c] = 1.0 / d.dyN[c];
   if (i >= 1 && j >= 1) uareaavgr[c] = 1.0 / (d.uarea[c] + d.uarea[c - d.ld] + d.uarea[c - d.ld - 1] + d.uarea[c - 1]);
 }
+#ifndef EVP_HOST_EMU  // launchers (and the cooperative kernel): not part of the host emulation (tests/emu_cgrid.cpp)
 cudaError_t launch_cgrid_static(const CDom &d, double *rhalf_dyE, double *r_dxE, double *rhalf_dxN, double *r_dyN, double *uareaavgr,
                                 cudaStream_t s) {
   dim3 b(32, 8), g((d.nx + 2 + 31) / 32, (d.ny + 2 + 7) / 8);
   cgrid_static_quotients<<<g, b, 0, s>>>(d, rhalf_dyE, r_dxE, rhalf_dxN, r_dyN, uareaavgr);
   return cudaGetLastError();
 }
+#endif  // EVP_HOST_EMU
 
+#ifndef EVP_HOST_EMU  // launchers (and the cooperative kernel): not part of the host emulation (tests/emu_cgrid.cpp)
 template <int GBY, int MINB>
 static void launch_AB(const CDom &d, const KParams &p, int cur, cudaStream_t s) {
   dim3 b(GBX, GBY), g((d.nx + 1 + GBX - 2) / (GBX - 1), (d.ny + 1 + GBY - 2) / (GBY - 1));
@@ -430,6 +433,7 @@ cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur
   *launches += 3;
   return cudaGetLastError();
 }
+#endif  // EVP_HOST_EMU
 
 // =============================================================================================================
 // CD grid (grid_ice = 'CD'): one subcycle of ice_dyn_evp.F90:1125-1267 as four kernels, cut where a value
@@ -589,6 +593,7 @@ __global__ void __launch_bounds__(256) kcd4_interp(const __grid_constant__ CDom 
   ring_store(d, d.vvel, i, j, vU, 3, true);
 }
 
+#ifndef EVP_HOST_EMU  // launchers (and the cooperative kernel): not part of the host emulation (tests/emu_cgrid.cpp)
 cudaError_t launch_cdgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches) {
   dim3 b(32, 8), gU((d.nx + 31) / 32, (d.ny + 7) / 8), gT((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8);
   kcd1_stress_T<<<gT, b, 0, s>>>(d, p);
@@ -598,7 +603,9 @@ cudaError_t launch_cdgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t
   *launches += 4;
   return cudaGetLastError();
 }
+#endif  // EVP_HOST_EMU
 
+#ifndef EVP_HOST_EMU  // launchers (and the cooperative kernel): not part of the host emulation (tests/emu_cgrid.cpp)
 // ---- all ndte subcycles in ONE cooperative launch -----------------------------------------------------------
 // 148 x 2 co-resident CTAs of 32 x 16 threads; every thread keeps the same cell for the whole loop (larger sub-domains:
 // a fixed list of tiles per CTA).  The five kernel boundaries of a subcycle become five grid barriers (one
@@ -659,6 +666,7 @@ cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t 
   *launches += 5;
   return cudaGetLastError();
 }
+#endif  // EVP_HOST_EMU
 
 }  // namespace EVP_NS
 }  // namespace evp
