@@ -328,8 +328,20 @@ __device__ __forceinline__ bool alias_point(const CDom &d, int &i, int &j) {
   return i >= 1 && i <= d.nx && j >= 1 && j <= d.ny;
 }
 
-template <int GBY, int MINB>
+// programmatic dependent launch (EVP_B200_CGRID_SHAPE >= 16; round-2 candidate, not yet measured): the kernel lets its
+// successor be scheduled as soon as all of its own CTAs have started, and itself waits for its predecessor's completion and
+// memory flush before it touches anything -- the kernel-boundary gap of the three launches per subcycle overlaps with the
+// predecessor's tail, as on the B grid
+__device__ __forceinline__ void pdl_enter() {
+#ifndef EVP_HOST_EMU
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+#endif
+}
+
+template <int GBY, int MINB, bool PDL = false>
 __global__ void __launch_bounds__(GBX *GBY, MINB) kA_strainU_stressT(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  if (PDL) pdl_enter();
   __shared__ double sh[GBY][GBX];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i = blockIdx.x * (GBX - 1) + tx, j = blockIdx.y * (GBY - 1) + ty;  // ti = 1 + bx*(GBX-1), point ti-1+tx
@@ -361,8 +373,9 @@ __global__ void __launch_bounds__(GBX *GBY, MINB) kA_strainU_stressT(const __gri
   }
 }
 
-template <int GBY, int MINB>
+template <int GBY, int MINB, bool PDL = false>
 __global__ void __launch_bounds__(GBX *GBY, MINB) kB_stressU_momentum(const __grid_constant__ CDom d, const __grid_constant__ KParams k, int cur) {
+  if (PDL) pdl_enter();
   __shared__ double sh[GBY][GBX];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i = blockIdx.x * (GBX - 1) + tx, j = blockIdx.y * (GBY - 1) + ty;
@@ -388,6 +401,11 @@ __global__ void __launch_bounds__(GBX *GBY, MINB) kB_stressU_momentum(const __gr
   __syncthreads();
   // phase 2: the E and N points (i,j)
   if (tx >= 1 && ty >= 1 && i <= d.nx && j <= d.ny) momentum_at(d, k, i, j, AT(i, j), sh[ty][tx], sh[ty - 1][tx], sh[ty][tx - 1]);
+}
+
+__global__ void __launch_bounds__(256) k5_pdl(const __grid_constant__ CDom d) {
+  pdl_enter();
+  p5_interp<false>(d, 1 + blockIdx.x * blockDim.x + threadIdx.x, 1 + blockIdx.y * blockDim.y + threadIdx.y);
 }
 
 // quotients of static geometry that the reference re-divides every subcycle (ice_dyn_evp.F90:2230-2240, 2398-2408,
@@ -420,6 +438,26 @@ static void launch_AB(const CDom &d, const KParams &p, int cur, cudaStream_t s) 
   kA_strainU_stressT<GBY, MINB><<<g, b, 0, s>>>(d, p);
   kB_stressU_momentum<GBY, MINB><<<g, b, 0, s>>>(d, p, cur);
 }
+template <class K, class... A>
+static cudaError_t launch_pdl(K kern, dim3 g, dim3 b, cudaStream_t s, A... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+template <int GBY, int MINB>
+static cudaError_t launch_AB5_pdl(const CDom &d, const KParams &p, int cur, cudaStream_t s, int *launches) {
+  dim3 b(GBX, GBY), g((d.nx + 1 + GBX - 2) / (GBX - 1), (d.ny + 1 + GBY - 2) / (GBY - 1));
+  dim3 b5(32, 8), g5((d.nx + 31) / 32, (d.ny + 7) / 8);
+  cudaError_t e = launch_pdl(kA_strainU_stressT<GBY, MINB, true>, g, b, s, d, p);
+  if (e == cudaSuccess) e = launch_pdl(kB_stressU_momentum<GBY, MINB, true>, g, b, s, d, p, cur);
+  if (e == cudaSuccess) e = launch_pdl(k5_pdl, g5, b5, s, d);
+  *launches += 3;
+  return e;
+}
 cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur, int shape, cudaStream_t s, int *launches) {
   dim3 b5(32, 8), g5((d.nx + 31) / 32, (d.ny + 7) / 8);
   switch (shape) {
@@ -427,6 +465,8 @@ cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur
     case 2: launch_AB<16, 2>(d, p, cur, s); break;
     case 3: launch_AB<12, 3>(d, p, cur, s); break;
     case 4: launch_AB<4, 8>(d, p, cur, s); break;
+    case 16: return launch_AB5_pdl<8, 4>(d, p, cur, s, launches);    // the default shape with programmatic dependent launch
+    case 18: return launch_AB5_pdl<16, 2>(d, p, cur, s, launches);
     default: launch_AB<8, 4>(d, p, cur, s); break;  // 62 registers, 4 CTAs per SM; the other shapes measure within 4 % (profiles/)
   }
   k5_interp<<<g5, b5, 0, s>>>(d);

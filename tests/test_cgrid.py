@@ -1,5 +1,7 @@
 """C grid (configs[2]: gx1 C-grid EVP, evp_algorithm=standard_2d, ndte=600, 1 GPU): oracle properties on the
 CPU, bit-exact parity of the CUDA path through the C ABI on the GPU."""
+import os
+
 import numpy as np
 import pytest
 
@@ -137,6 +139,24 @@ def test_cgrid_five_kernel_form(oracle_mod, evp_lib, monkeypatch, cfg, kw):
     for n in abi.CFIELDS_INOUT + abi.CFIELDS_OUT:
         if n != skip:
             assert np.array_equal(got[n].view(np.int64), ref[n].view(np.int64)), n
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("EVP_B200_TEST_CANDIDATES", "0") != "1",
+                    reason="round-2 candidate: written after the round-1 GPU budget was spent; set EVP_B200_TEST_CANDIDATES=1")
+@pytest.mark.parametrize("shape", ["16", "18"])
+def test_cgrid_fused_with_programmatic_dependent_launch(oracle_mod, evp_lib, monkeypatch, shape):
+    """EVP_B200_CGRID_SHAPE=16/18: kA, kB, k5 chained by programmatic dependent launch (same arithmetic, same tiles)."""
+    monkeypatch.setenv("EVP_B200_CGRID_SHAPE", shape)
+    for cfg, kw in (("tiny", dict(seed=12, ndte=7)), ("tiny", dict(seed=14, ew="cyclic", ns="cyclic", kmt="none")),
+                    ("tiny", dict(seed=15, visc_method=abi.VISC_AVG_STRENGTH, block_size=(12, 10))), ("gx3", dict(ndte=31))):
+        c = synth.make_ccase(cfg, **kw)
+        ref = run_oracle_c(oracle_mod, c)
+        got = run_gpu_c(evp_lib, c, mode=abi.MODE_EXACT)
+        skip = "etax2U" if c.params["visc_method"] == abi.VISC_AVG_STRENGTH else "strengthU"
+        for n in abi.CFIELDS_INOUT + abi.CFIELDS_OUT:
+            if n != skip:
+                assert np.array_equal(got[n].view(np.int64), ref[n].view(np.int64)), (cfg, kw, n)
 
 
 @pytest.mark.gpu
