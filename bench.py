@@ -188,6 +188,16 @@ def run_ours(args):
     ndte = params["ndte"]
     cells_global = base["nx"] * px * base["ny"] * py
     dyn_evp.dyn_evp_b200_init(grid)
+    if os.environ.get("EVP_B200_FUSED_VARIANT") in ("59", "63"):
+        # derived-geometry kernels (round-2 candidate): hand over HTN, HTE; the library checks them bit for bit on the device
+        from cice_b200 import decomp
+        sel = slice(None)
+        if world > 1:
+            owner, _ = decomp.cartesian_owner(case.blocks, world)
+            sel = case.rank_view(owner, rank)[2]
+        bad = dyn_evp.set_metric(synth.scatter(case.X["HTN"], case.blocks)[sel], synth.scatter(case.X["HTE"], case.blocks)[sel], 1e-11)
+        if rank == 0:
+            print(f"# set_metric: {bad} cells differ", file=sys.stderr)
     desc = dyn_evp.describe()
 
     hf = pin(fields)

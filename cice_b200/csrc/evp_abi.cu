@@ -179,6 +179,8 @@ struct Ctx {
   int q_ntiles = 0, q_nctas = 0;
   int num_sms = 0;
   int fused_variant = 0;
+  bool derived_ok = false;   // evp_b200_set_metric: HTN/HTE reproduce the seven derived geometry arrays bit for bit (variants 59/63 usable)
+  int metric_mismatches = -1;
   int p2p_variant_bits = 0;  // 0x100: the in-kernel-halo kernel reads its tile table from constant memory (EVP_B200_P2P_CONST_TILES=1)
   int strip_m = 1;  // chunks per CTA of strip_kernel (fused_variant 30)
   bool fused_pdl = true;
@@ -596,6 +598,12 @@ static KParams kparams(const evp_b200_params_t *p) {
   return k;
 }
 
+// variants 59 / 63 (derived geometry) need the metric arrays of evp_b200_set_metric and its bitwise check; otherwise 19 / 23
+static int fused_variant_now() {
+  if ((g.fused_variant == 59 || g.fused_variant == 63) && !g.derived_ok) return g.fused_variant == 59 ? 19 : 23;
+  return g.fused_variant;
+}
+
 static int choose_kernel(const evp_b200_params_t *p) {
   int kern = p->kernel;
   if (kern == EVP_B200_KERNEL_AUTO) kern = EVP_B200_KERNEL_FUSED;  // measured faster than PERSISTENT at gx1 (profiles/)
@@ -650,8 +658,8 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
   for (int ksub = 0; ksub < p->ndte; ++ksub) {
     const int last = (ksub == p->ndte - 1);
     if (p2p) {
-      CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, g.fused_variant | g.p2p_variant_bits, g.stream)
-               : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, g.fused_variant | g.p2p_variant_bits, g.stream));
+      CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, fused_variant_now() | g.p2p_variant_bits, g.stream)
+               : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, fused_variant_now() | g.p2p_variant_bits, g.stream));
       cur ^= 1;
       ++nl;
       continue;
@@ -665,8 +673,8 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
         CK(exact ? exact::launch_strip(g.dom, k, cur, g.strip_m, g.stream, g.fused_pdl, last)
                  : fast::launch_strip(g.dom, k, cur, g.strip_m, g.stream, g.fused_pdl, last));
       else
-        CK(exact ? exact::launch_fused(g.dom, k, cur, g.stream, g.fused_variant, g.fused_pdl, last | (pdl_trig))
-                 : fast::launch_fused(g.dom, k, cur, g.stream, g.fused_variant, g.fused_pdl, last | (pdl_trig)));
+        CK(exact ? exact::launch_fused(g.dom, k, cur, g.stream, fused_variant_now(), g.fused_pdl, last | (pdl_trig))
+                 : fast::launch_fused(g.dom, k, cur, g.stream, fused_variant_now(), g.fused_pdl, last | (pdl_trig)));
       cur ^= 1;
       nl += 1;
     } else {
@@ -810,6 +818,49 @@ static int do_dyn_finish(evp_b200_finish_t *ff) {
   }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+// metric arrays for the derived-geometry kernels (variants 59 / 63): upload, check on the device that they reproduce the seven
+// derived arrays of evp_b200_init bit for bit on every T cell the loop can touch, publish them to both kernel units
+static int do_set_metric(const double *HTN, const double *HTE, double deltaminEVP, int32_t *mismatches) {
+  if (!g.inited) return fail("evp_b200_set_metric: call evp_b200_init first");
+  if (!HTN || !HTE) return fail("evp_b200_set_metric: null argument");
+  CK(cudaSetDevice(g.device));
+  const size_t bblk = g.nblk_elems * sizeof(double);
+  double *dm[2] = {nullptr, nullptr}, *scratch = nullptr;
+  int *dcount = nullptr;
+  CK(cudaMalloc(&scratch, bblk));
+  CK(cudaMalloc(&dcount, sizeof(int)));
+  CK(cudaMemsetAsync(dcount, 0, sizeof(int), g.stream));
+  const double *src[2] = {HTN, HTE};
+  for (int q = 0; q < 2; ++q) {
+    if (calloc_dom(dm[q])) return 1;
+    CK(cudaMemcpyAsync(scratch, src[q], bblk, cudaMemcpyHostToDevice, g.stream));
+    pack_f64<<<grid_blocks(g.ndom), 256, 0, g.stream>>>(dm[q], scratch, g.d_gsrc, (int)g.ndom);
+  }
+  // ghost T cells outside a closed or open domain edge are never ice (tmask is false there) and hold fill values: not checked.
+  // A tripole top row is checked like any other; its sign-flipped dxhy/dyhx make the check fail and the arrays stay in use.
+  const bool e_edge = (g.gi0 + g.dom.nx - 1 == g.nxg), n_edge = (g.gj0 + g.dom.ny - 1 == g.nyg);
+  const int skip_e = (e_edge && g.ew != EVP_B200_BNDY_CYCLIC) ? 1 : 0;
+  const int skip_n = (n_edge && g.ns != EVP_B200_BNDY_CYCLIC && g.ns != EVP_B200_BNDY_TRIPOLE) ? 1 : 0;
+  CK(exact::launch_metric_verify(g.dom, dm[0], dm[1], deltaminEVP, skip_e, skip_n, dcount, g.stream));
+  int bad = -1;
+  CK(cudaMemcpyAsync(&bad, dcount, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaFree(scratch));
+  CK(cudaFree(dcount));
+  g.metric_mismatches = bad;
+  g.derived_ok = (bad == 0);   // (cells next to an eliminated land block fail the check by themselves: the hole holds zeros)
+  if (g.derived_ok) {
+    CK(exact::set_metric(dm[0], dm[1], deltaminEVP));
+    CK(fast::set_metric(dm[0], dm[1], deltaminEVP));
+    destroy_graph();  // a cached graph may hold the array-reading form
+  }
+  if (mismatches) *mismatches = bad;
+  char b[160];
+  snprintf(b, sizeof b, "; metric: %s (%d cells differ)", g.derived_ok ? "derived geometry available" : "arrays kept", bad);
+  g.desc += b;
   return 0;
 }
 
@@ -1177,6 +1228,9 @@ int evp_b200_finalize(void) {
 
 int evp_b200_deformations(evp_b200_deform_t *d) { return do_deformations(d); }
 int evp_b200_dyn_finish(evp_b200_finish_t *f) { return do_dyn_finish(f); }
+int evp_b200_set_metric(const double *HTN, const double *HTE, double deltaminEVP, int32_t *mismatches) {
+  return do_set_metric(HTN, HTE, deltaminEVP, mismatches);
+}
 int evp_b200_init_cgrid(const evp_b200_cgrid_t *cg) { return do_init_cgrid(cg); }
 int evp_b200_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) { return do_run_cgrid(p, f); }
 int evp_b200_run_cdgrid(const evp_b200_params_t *p, evp_b200_cdfields_t *f) { return do_run_cdgrid(p, f); }

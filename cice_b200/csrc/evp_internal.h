@@ -117,6 +117,8 @@ struct PersistPlan {
   cudaError_t launch_strip(const Dom &d, const KParams &p, int cur, int m, cudaStream_t s, bool pdl, int last); \
   cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, int last, int variant, cudaStream_t s); \
   cudaError_t set_p2p_tiles(const int *host_tiles, int n); \
+  cudaError_t set_metric(const double *HTN, const double *HTE, double deltamin); \
+  cudaError_t launch_metric_verify(const Dom &d, const double *HTN, const double *HTE, double deltamin, int skip_e, int skip_n, int *mismatches, cudaStream_t s); \
   cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s); \
   cudaError_t launch_queue(const Dom &d, const KParams &p, int ndte, unsigned *progress, unsigned *counter, int nctas, cudaStream_t s); \
   cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \

@@ -213,6 +213,57 @@ cudaError_t set_p2p_tiles(const int *host_tiles, int n) {
 }
 #endif  // EVP_HOST_EMU
 
+// Derived geometry (SPEC bit 5, EVP_B200_FUSED_VARIANT=59/63 after evp_b200_set_metric; round-2 candidate, not yet measured).
+// Seven of the ten static T-cell arrays are functions of the two metric arrays HTN, HTE and of dxT, dyT
+// (ice_dyn_shared.F90:384-388, 401-441): on sub-domains that stream from HBM, reading HTN/HTE (their i-1 / j-1 neighbours come
+// from the same cache lines) instead of dxhy, dyhx, cxp, cyp, cxm, cym, DminTarea moves 360 instead of 400 B per cell and
+// subcycle -- the algorithmic figure of SURVEY 8d.  The expressions are the reference's, operation for operation; whether they
+// reproduce the host's arrays bit for bit on every cell the loop can touch is CHECKED on the device when the metric arrays are
+// handed over (metric_verify_kernel); if a single cell differs the library keeps reading the arrays.
+__constant__ const double *c_HTN, *c_HTE;
+__constant__ double c_deltamin;
+__device__ __forceinline__ void derive_geometry(double hn, double hs, double he, double hw, double dxT, double dyT, double deltamin,
+                                                double &dxhy, double &dyhx, double &cxp, double &cyp, double &cxm, double &cym,
+                                                double &dmin) {
+  dxhy = 0.5 * (he - hw);            // p5*(HTE(i,j) - HTE(i-1,j))
+  dyhx = 0.5 * (hn - hs);            // p5*(HTN(i,j) - HTN(i,j-1))
+  cyp = (1.5 * he - 0.5 * hw);       // c1p5*HTE(i,j) - p5*HTE(i-1,j)
+  cxp = (1.5 * hn - 0.5 * hs);
+  cym = -(1.5 * hw - 0.5 * he);
+  cxm = -(1.5 * hs - 0.5 * hn);
+  dmin = deltamin * (dxT * dyT);     // deltaminEVP*tarea, tarea = dxT*dyT (ice_grid.F90:681-715)
+}
+// counts the T cells (1..nx+1-skip_e, 1..ny+1-skip_n) on which the derived values differ from the arrays in any bit
+__global__ void __launch_bounds__(256) metric_verify_kernel(const __grid_constant__ Dom d, const double *__restrict__ HTN,
+                                                            const double *__restrict__ HTE, double deltamin, int skip_e, int skip_n,
+                                                            int *__restrict__ mismatches) {
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > d.nx + 1 - skip_e || j > d.ny + 1 - skip_n) return;
+  const int c = at(d, i, j);
+  double dxhy, dyhx, cxp, cyp, cxm, cym, dmin;
+  derive_geometry(HTN[c], HTN[c - d.ld], HTE[c], HTE[c - 1], d.dxT[c], d.dyT[c], deltamin, dxhy, dyhx, cxp, cyp, cxm, cym, dmin);
+  const bool same = __double_as_longlong(dxhy) == __double_as_longlong(d.dxhy[c]) && __double_as_longlong(dyhx) == __double_as_longlong(d.dyhx[c]) &&
+                    __double_as_longlong(cxp) == __double_as_longlong(d.cxp[c]) && __double_as_longlong(cyp) == __double_as_longlong(d.cyp[c]) &&
+                    __double_as_longlong(cxm) == __double_as_longlong(d.cxm[c]) && __double_as_longlong(cym) == __double_as_longlong(d.cym[c]) &&
+                    __double_as_longlong(dmin) == __double_as_longlong(d.DminTarea[c]);
+  if (!same) atomicAdd(mismatches, 1);
+}
+#ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
+cudaError_t set_metric(const double *HTN, const double *HTE, double deltamin) {
+  cudaError_t e = cudaMemcpyToSymbol(c_HTN, &HTN, sizeof HTN);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_HTE, &HTE, sizeof HTE);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_deltamin, &deltamin, sizeof deltamin);
+  return e;
+}
+cudaError_t launch_metric_verify(const Dom &d, const double *HTN, const double *HTE, double deltamin, int skip_e, int skip_n,
+                                 int *mismatches, cudaStream_t s) {
+  dim3 b(32, 8), g((d.nx + 1 + b.x - 1) / b.x, (d.ny + 1 + b.y - 1) / b.y);
+  metric_verify_kernel<<<g, b, 0, s>>>(d, HTN, HTE, deltamin, skip_e, skip_n, mismatches);
+  return cudaGetLastError();
+}
+#endif  // EVP_HOST_EMU
+
 constexpr int NUOP = 12;
 // SPEC bit 0: speculative T-cell operand loads; bit 1: momentum operands through cp.async
 template <int FBX, int FBY, bool P2P, int SPEC>
@@ -220,6 +271,7 @@ __device__ __forceinline__ void fused_spec_body(const Dom &d, const KParams &k, 
                                                 bool inT, int c, double (&sstr)[8][FBY][FBX]) {
   constexpr bool SPT = (SPEC & 1) != 0, CPU = (SPEC & 2) != 0, IL = (SPEC & 4) != 0;  // bit 2: interleaved div/sqrt
   constexpr bool PAIR = (SPEC & 8) != 0;                                                 // bit 3: pairwise named barriers
+  constexpr bool DER = (SPEC & 32) != 0;                                                 // bit 5: derived geometry (see above)
   __shared__ double sU[CPU ? NUOP : 1][FBY * FBX];
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * FBX + tx;
   const int nxt = cur ^ 1;
@@ -235,9 +287,16 @@ __device__ __forceinline__ void fused_spec_body(const Dom &d, const KParams &k, 
   const unsigned mT = ld_nc_u8(d.maskT + c), mU = ld_nc_u8(d.maskU + c);
   double dxT, dyT, dxhy, dyhx, cxp, cyp, cxm, cym, dmin, strength;
   if (SPT) {
-    dxT = ld_nc_f64(d.dxT + c); dyT = ld_nc_f64(d.dyT + c); dxhy = ld_nc_f64(d.dxhy + c); dyhx = ld_nc_f64(d.dyhx + c);
-    cxp = ld_nc_f64(d.cxp + c); cyp = ld_nc_f64(d.cyp + c); cxm = ld_nc_f64(d.cxm + c); cym = ld_nc_f64(d.cym + c);
-    dmin = ld_nc_f64(d.DminTarea + c); strength = ld_nc_f64(d.strength + c);
+    dxT = ld_nc_f64(d.dxT + c); dyT = ld_nc_f64(d.dyT + c);
+    if (DER) {
+      const double hn = ld_nc_f64(c_HTN + c), hs = ld_nc_f64(c_HTN + c - d.ld), he = ld_nc_f64(c_HTE + c), hw = ld_nc_f64(c_HTE + c - 1);
+      derive_geometry(hn, hs, he, hw, dxT, dyT, c_deltamin, dxhy, dyhx, cxp, cyp, cxm, cym, dmin);
+    } else {
+      dxhy = ld_nc_f64(d.dxhy + c); dyhx = ld_nc_f64(d.dyhx + c);
+      cxp = ld_nc_f64(d.cxp + c); cyp = ld_nc_f64(d.cyp + c); cxm = ld_nc_f64(d.cxm + c); cym = ld_nc_f64(d.cym + c);
+      dmin = ld_nc_f64(d.DminTarea + c);
+    }
+    strength = ld_nc_f64(d.strength + c);
   }
 #if EVP_USE_PDL
   cudaGridDependencySynchronize();
@@ -268,6 +327,11 @@ __device__ __forceinline__ void fused_spec_body(const Dom &d, const KParams &k, 
     if (inT && mT) {
       Sigma sg;
       load_sigma(d, cur, c, sg);
+      if (DER) {
+        const double dxT_ = d.dxT[c], dyT_ = d.dyT[c];
+        derive_geometry(c_HTN[c], c_HTN[s], c_HTE[c], c_HTE[w], dxT_, dyT_, c_deltamin, dxhy, dyhx, cxp, cyp, cxm, cym, dmin);
+        stress_point<IL>(ucc, vcc, U[w], V[w], U[s], V[s], U[sw], V[sw], dxT_, dyT_, dxhy, dyhx, cxp, cyp, cxm, cym, dmin, d.strength[c], k, sg, str);
+      } else
       stress_point<IL>(ucc, vcc, U[w], V[w], U[s], V[s], U[sw], V[sw], d.dxT[c], d.dyT[c], d.dxhy[c], d.dyhx[c],
                        d.cxp[c], d.cyp[c], d.cxm[c], d.cym[c], d.DminTarea[c], d.strength[c], k, sg, str);
       const bool own = (tx < FBX - 1 || i == d.nx + 1) && (ty < FBY - 1 || j == d.ny + 1);
@@ -781,6 +845,8 @@ cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s
     case 27: return launch_fused_t<32, 4, 4, false, 4>(d, p, cur, s, pdl, last);
     case 28: return launch_fused_t<32, 16, 1, false, 4>(d, p, cur, s, pdl, last);
     case 29: return launch_fused_t<32, 12, 1, false, 4>(d, p, cur, s, pdl, last);
+    case 59: return launch_fused_t<32, 8, 2, false, 3 | 32>(d, p, cur, s, pdl, last);  // 19 + derived geometry (after set_metric)
+    case 63: return launch_fused_t<32, 8, 2, false, 4 | 32>(d, p, cur, s, pdl, last);  // 23 + derived geometry
     // two lanes per T cell (evp_lane2.cuh): <patch x, patch y, CTAs per SM, interleaved div/sqrt, lane mapping>
     case 40: return launch_fused2_t<32, 8, 2, true, 0>(d, p, cur, s, pdl, last);   // 512 threads, 64 registers
     case 41: return launch_fused2_t<32, 8, 1, true, 0>(d, p, cur, s, pdl, last);   // 512 threads, 128 registers
@@ -815,6 +881,8 @@ cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = (last & 4) ? 1 : 0;
   const int flags = last & 3;
+  if ((variant & 0xff) == 59) return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 3 | 32>, d, p, cur, pp, ksub, flags);
+  if ((variant & 0xff) == 63) return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 4 | 32>, d, p, cur, pp, ksub, flags);
   if (variant & 0x100) {  // tile table in constant memory (set_p2p_tiles)
     if ((variant & 0xff) == 19) return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 3 | 16>, d, p, cur, pp, ksub, flags);
     return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 4 | 16>, d, p, cur, pp, ksub, flags);

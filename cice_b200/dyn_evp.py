@@ -126,6 +126,18 @@ def dyn_finish(d, rhow, cosw=1.0, sinw=0.0):
     return d
 
 
+def set_metric(HTN, HTE, deltaminEVP):
+    """hand HTN, HTE (block arrays) to the library; returns the number of T cells on which the reference's expressions do NOT
+    reproduce dxhy, dyhx, cxp, cyp, cxm, cym, DminTarea bit for bit (0 = the derived-geometry kernels, variants 59/63, may be used)."""
+    a = np.ascontiguousarray(HTN, dtype=np.float64)
+    b = np.ascontiguousarray(HTE, dtype=np.float64)
+    assert a.size == _state["npl"] and b.size == _state["npl"]
+    bad = C.c_int32(-1)
+    pd = C.POINTER(C.c_double)
+    check(load().evp_b200_set_metric(a.ctypes.data_as(pd), b.ctypes.data_as(pd), float(deltaminEVP), C.byref(bad)), "evp_b200_set_metric")
+    return int(bad.value)
+
+
 def upload(fields):
     f, keep = _fields(fields)
     check(load().evp_b200_upload(C.byref(f)), "evp_b200_upload")

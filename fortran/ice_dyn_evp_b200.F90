@@ -90,6 +90,12 @@ module ice_dyn_evp_b200
   end type evp_b200_finish_t
 
   interface
+     integer(c_int) function evp_b200_set_metric(HTN, HTE, deltaminEVP, mismatches) bind(C, name='evp_b200_set_metric')
+       import :: c_int, c_int32_t, c_double, c_ptr
+       type(c_ptr), value :: HTN, HTE
+       real(c_double), value :: deltaminEVP
+       integer(c_int32_t), intent(out) :: mismatches
+     end function evp_b200_set_metric
      integer(c_int) function evp_b200_deformations(d) bind(C, name='evp_b200_deformations')
        import :: c_int, evp_b200_deform_t
        type(evp_b200_deform_t), intent(inout) :: d
@@ -193,11 +199,12 @@ contains
   ! once, after init_dyn_shared and the grid are set up (ice_dyn_evp.F90:153-155)
   subroutine dyn_evp_b200_init
     use mpi
-    use ice_grid,       only: dxT, dyT, uarear
-    use ice_dyn_shared, only: dxhy, dyhx, cxp, cyp, cxm, cym, DminTarea
+    use ice_grid,       only: dxT, dyT, uarear, HTN, HTE
+    use ice_dyn_shared, only: dxhy, dyhx, cxp, cyp, cxm, cym, DminTarea, deltaminEVP
     type(evp_b200_grid_t) :: g
     type(block) :: this_block
     character(kind=c_char) :: id(128)
+    integer(c_int32_t) :: nbad
     integer :: iblk, ierr, nprocs, ndev_local
     integer :: local_comm, local_rank
 
@@ -239,6 +246,9 @@ contains
     g%cxp = c_loc(cxp);    g%cyp = c_loc(cyp);    g%cxm = c_loc(cxm);    g%cym = c_loc(cym)
     g%DminTarea = c_loc(DminTarea);  g%uarear = c_loc(uarear)
     call check(evp_b200_init(g), 'evp_b200_init')
+    ! optional: the metric arrays behind dxhy, dyhx, cxp, cyp, cxm, cym, DminTarea; the library checks on the device that they
+    ! reproduce those arrays bit for bit before any kernel may derive them (include/evp_b200.h); a non-zero count is not an error
+    call check(evp_b200_set_metric(c_loc(HTN), c_loc(HTE), deltaminEVP, nbad), 'evp_b200_set_metric')
   end subroutine dyn_evp_b200_init
 
   !---------------------------------------------------------------------

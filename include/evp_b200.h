@@ -257,6 +257,16 @@ typedef struct {
 } evp_b200_finish_t;
 int evp_b200_dyn_finish(evp_b200_finish_t *f);
 
+/* ---- optional: metric arrays for the derived-geometry kernels ---------------------------------------------
+ * dxhy, dyhx, cxp, cyp, cxm, cym and DminTarea of evp_b200_grid_t are functions of HTN, HTE, dxT, dyT and deltaminEVP
+ * (ice_dyn_shared.F90:384-388, 401-441; the reference's own 1-D solver recomputes them from HTE, HTN every subcycle,
+ * ice_dyn_core1d.F90:191-199).  Given HTN and HTE (ice_grid.F90, (nx_block,ny_block,max_blocks)), the library checks ON THE
+ * DEVICE that the reference's expressions reproduce the seven arrays bit for bit on every T cell the loop can touch; only then
+ * may the kernels that read two arrays instead of seven be selected (EVP_B200_FUSED_VARIANT=59|63: 360 instead of 400 B per cell
+ * and subcycle on sub-domains that stream from HBM).  *mismatches (may be NULL) receives the number of cells that differ;
+ * a non-zero count is not an error, the arrays simply stay in use.  Call after evp_b200_init. */
+int evp_b200_set_metric(const double *HTN, const double *HTE, double deltaminEVP, int32_t *mismatches);
+
 /* The same call split in three so that a caller which keeps dynamics state on the device
  *  -- and bench.py's device-resident timing -- can run the loop alone.
  * run_bgrid == upload + subcycle + download. */

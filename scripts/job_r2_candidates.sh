@@ -7,7 +7,7 @@
 mkdir -p gpurun_out
 {
 echo "== parity of variants 40-53"
-EVP_B200_TEST_CANDIDATES=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "two_lane or dyn_finish" 2>&1 | tail -15
+EVP_B200_TEST_CANDIDATES=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "two_lane or dyn_finish or derived_geometry" 2>&1 | tail -15
 b() { timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu "$@" 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], round(d['roofline']['frac'],4))"; }
 EVP_B200_TEST_CANDIDATES=1 timeout 600 python -m pytest tests/test_cgrid.py -m gpu -q -k programmatic 2>&1 | tail -3
 echo "== gx1 C grid (ndte=600): default vs programmatic dependent launch"
@@ -15,6 +15,10 @@ for sh in 0 16 18; do echo "cgrid shape $sh: $(EVP_B200_CGRID_SHAPE=$sh b --grid
 echo "== gx1, ms per step and roofline fraction"
 echo "default: $(b)"
 for v in 40 41 42 43 44 45 46 50 51 52 53; do echo "variant $v: $(EVP_B200_FUSED_VARIANT=$v b)"; done
+echo "== derived geometry (two metric arrays instead of seven): gx1 variant 63 vs 23, 3600x2400 variant 59 vs 19"
+echo "gx1 v63: $(EVP_B200_FUSED_VARIANT=63 b)"
+echo "p1deg v19 (default): $(b --workload p1deg --steps 3 --warmup 2)"
+echo "p1deg v59: $(EVP_B200_FUSED_VARIANT=59 b --workload p1deg --steps 3 --warmup 2)"
 echo "== gx1 fast mode"
 echo "default fast: $(b --mode fast)"
 for v in 40 43 50; do echo "variant $v fast: $(EVP_B200_FUSED_VARIANT=$v b --mode fast)"; done

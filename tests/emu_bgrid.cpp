@@ -32,7 +32,7 @@ void lane2_step(const Dom &d, const KParams &k, int cur, int flags) {
 }  // namespace
 
 // kind 0: stress_kernel + stepu_kernel (in place)            sub: unused
-// kind 1: fused_kernel<32,8,2,false,false,SPEC>               sub: SPEC (0 1 2 3 4 5 7 12 16; 4 is the default form)
+// kind 1: fused_kernel<32,8,2,false,false,SPEC>               sub: SPEC (0 1 2 3 4 5 7 12 16 35 36; 4 is the default form)
 // kind 2: strip_kernel                                        sub: chunks per CTA
 // kind 3: fused4_kernel (four lanes per cell)                 sub: unused
 // kind 4: fused2_kernel (two lanes per cell)                  sub: shape/mapping 0..5, +8 for IL = true
@@ -99,6 +99,8 @@ extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, i
         case 7: fused_step<7>(d, k, cur, flags); break;
         case 12: fused_step<12>(d, k, cur, flags); break;
         case 16: fused_step<16>(d, k, cur, flags); break;
+        case 35: fused_step<3 | 32>(d, k, cur, flags); break;   // variant 59: 19 + derived geometry (emu_set_metric first)
+        case 36: fused_step<4 | 32>(d, k, cur, flags); break;   // variant 63: 23 + derived geometry
         default: return 1;
       }
     } else if (kind == 2) {
@@ -165,4 +167,18 @@ extern "C" int emu_finish_run(int nxb, int nyb, const int32_t *maskU, const doub
   d.maskU = mU.data();
   emu::launch({(d.nx + 31) / 32, (d.ny + 7) / 8, 1}, {32, 8, 1}, [&] { finish_kernel(d, u, v, strocnx, strocny, rhow, cosw, sinw); });
   return 0;
+}
+
+// derived geometry: publish the metric arrays to the kernels (what set_metric does on the device) and run the bitwise check
+extern "C" int emu_set_metric(int nxb, int nyb, const double *geo /*[10][n]*/, const double *HTN, const double *HTE, double deltamin,
+                              int skip_e, int skip_n) {
+  const size_t n = (size_t)nxb * nyb;
+  Dom d{};
+  d.nx = nxb - 2; d.ny = nyb - 2; d.ld = nxb; d.nyd = nyb;
+  d.dxT = geo; d.dyT = geo + n; d.dxhy = geo + 2 * n; d.dyhx = geo + 3 * n; d.cxp = geo + 4 * n; d.cyp = geo + 5 * n;
+  d.cxm = geo + 6 * n; d.cym = geo + 7 * n; d.DminTarea = geo + 8 * n;
+  int bad = 0;
+  emu::launch({(d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8, 1}, {32, 8, 1}, [&] { metric_verify_kernel(d, HTN, HTE, deltamin, skip_e, skip_n, &bad); });
+  c_HTN = HTN; c_HTE = HTE; c_deltamin = deltamin;
+  return bad;
 }

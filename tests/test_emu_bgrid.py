@@ -154,3 +154,31 @@ def test_post_loop_kernels_on_the_host(oracle_mod, emu):
                               float(c.params["sinw"])) == 0
     assert np.array_equal(sx.view(np.int64), ref["strocnxU"][0].view(np.int64))
     assert np.array_equal(sy.view(np.int64), ref["strocnyU"][0].view(np.int64))
+
+
+@pytest.mark.parametrize("case", ["tiny-4sub", "tiny-5sub-revised", "wide-3sub", "doubly-cyclic-3sub", "aligned-32x8-16x16"])
+def test_derived_geometry_kernels_on_the_host(oracle_mod, emu, case):
+    """variants 59 / 63: dxhy, dyhx, cxp, cyp, cxm, cym, DminTarea derived in the kernel from HTN, HTE, dxT, dyT with the reference's
+    expressions (ice_dyn_shared.F90:384-441).  The device-side check must find no differing cell on the synthetic grids (ghost cells
+    outside a closed edge excluded), must notice a perturbed metric array, and the kernels must equal the oracle bit for bit."""
+    c = synth.make_case(**CASES[case])
+    g = c.grid
+    nxb, nyb = g["nx_block"], g["ny_block"]
+    geo = np.ascontiguousarray(np.stack([np.asarray(g[nm][0]) for nm in abi.GRID_STATIC]))
+    HTN = np.ascontiguousarray(synth.scatter(c.X["HTN"], c.blocks)[0])
+    HTE = np.ascontiguousarray(synth.scatter(c.X["HTE"], c.blocks)[0])
+    pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    emu.emu_set_metric.argtypes = [C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 3 + [C.c_double, C.c_int, C.c_int]
+    cyc = abi.BNDY_NAMES["cyclic"]
+    skip_e, skip_n = int(g["ew_boundary_type"] != cyc), int(g["ns_boundary_type"] != cyc)
+    dmin = 1e-11                                      # deltaminEVP of synth.global_state
+    wrong = HTN.copy()
+    wrong[nyb // 2, nxb // 2] *= 1.0 + 2.0 ** -40
+    assert emu.emu_set_metric(nxb, nyb, pd(geo), pd(wrong), pd(HTE), dmin, skip_e, skip_n) > 0
+    assert emu.emu_set_metric(nxb, nyb, pd(geo), pd(HTN), pd(HTE), dmin, skip_e, skip_n) == 0
+    ref = c.copy_fields()
+    oracle_mod.evp_run_bgrid(c.grid, c.params, ref)
+    for sub in (35, 36):
+        got = run_emulated(emu, c, 1, sub)
+        for nm in abi.STRESS + ("uvel", "vvel", "strintxU", "strintyU", "taubxU", "taubyU"):
+            assert np.array_equal(got[nm].view(np.int64), ref[nm][0].view(np.int64)), (sub, nm)

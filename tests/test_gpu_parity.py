@@ -361,6 +361,35 @@ def test_two_lane_variants(oracle_mod, evp_lib, monkeypatch, variant):
     assert_close(run_gpu(evp_lib, c, mode=abi.MODE_FAST, kernel=abi.KERNEL_FUSED), run_oracle(oracle_mod, c), TOL)
 
 
+@CANDIDATES
+@pytest.mark.parametrize("variant", ["59", "63"])
+def test_derived_geometry_variants(oracle_mod, evp_lib, monkeypatch, variant):
+    """EVP_B200_FUSED_VARIANT=59|63 after evp_b200_set_metric: seven geometry arrays derived in the kernel from HTN, HTE (two arrays
+    read instead of seven).  The device-side check must accept the synthetic metric arrays, reject a perturbed one (the kernels then
+    keep reading the arrays), and the results stay bit-identical either way.  Host-emulated in tests/test_emu_bgrid.py."""
+    monkeypatch.setenv("EVP_B200_FUSED_VARIANT", variant)
+    cases = [synth.make_case("tiny", seed=11, block_size=(12, 10), ndte=9), synth.make_case("tiny", seed=12, revised_evp=True),
+             synth.make_case("tiny", seed=13, ew="closed", ns="closed", kmt="boxislands"), synth.make_case("gx3", seed=14, ndte=25),
+             synth.make_case("tiny", seed=15, ns="tripole", ew="cyclic", kmt="none", ndte=12)]
+    for n, c in enumerate(cases):
+        ref = run_oracle(oracle_mod, c)
+        HTN, HTE = synth.scatter(c.X["HTN"], c.blocks), synth.scatter(c.X["HTE"], c.blocks)
+        for perturb in (False, True):
+            f = c.copy_fields()
+            evp_lib.dyn_evp_b200_init(c.grid)
+            try:
+                h = HTN.copy()
+                if perturb:
+                    h[0, h.shape[1] // 2, h.shape[2] // 2] *= 1.0 + 2.0 ** -40
+                bad = evp_lib.set_metric(h, HTE, 1e-11)
+                tripole = c.grid["ns_boundary_type"] == abi.BNDY_NAMES["tripole"]
+                assert (bad > 0) == (perturb or tripole), (n, perturb, bad)     # the tripole ghost row holds sign-flipped dxhy, dyhx
+                evp_lib.dyn_evp_b200_run(dict(c.params, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED), f)
+            finally:
+                evp_lib.dyn_evp_b200_finalize()
+            assert_bitwise(f, ref)
+
+
 def test_interleaved_divsqrt_hits_the_fallback(oracle_mod, evp_lib, monkeypatch):
     """operands outside the fast path of the hand-scheduled division / square root (zero and denormal-range
     strain rates and numerators: ice at rest, zero forcing) must take the built-in operators and stay bit-identical."""
