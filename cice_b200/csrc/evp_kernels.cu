@@ -783,7 +783,7 @@ cudaError_t launch_queue(const Dom &d, const KParams &p, int ndte, unsigned *pro
 #include "evp_lane2.cuh"
 
 #ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
-template <int PX, int PY, int MINB, bool IL, int MAP>
+template <int PX, int PY, int MINB, bool IL, int MAP, bool SPT = false>
 static cudaError_t launch_fused2_t(const Dom &d, const KParams &p, int cur, cudaStream_t s, bool pdl, int last) {
   dim3 b(2 * PX * PY), g((d.nx + PX - 2) / (PX - 1), (d.ny + PY - 2) / (PY - 1));
   cudaLaunchConfig_t cfg{};
@@ -792,7 +792,7 @@ static cudaError_t launch_fused2_t(const Dom &d, const KParams &p, int cur, cuda
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, fused2_kernel<PX, PY, MINB, IL, MAP>, d, p, cur, last);
+  return cudaLaunchKernelEx(&cfg, fused2_kernel<PX, PY, MINB, IL, MAP, SPT>, d, p, cur, last);
 }
 
 template <int FBX, int FBY, int MINB, bool HOIST = false, int SPEC = 0>
@@ -855,6 +855,9 @@ cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s
     case 44: return launch_fused2_t<32, 4, 3, true, 0>(d, p, cur, s, pdl, last);   // 256 threads, 80 registers
     case 45: return launch_fused2_t<16, 16, 2, true, 0>(d, p, cur, s, pdl, last);  // 512 threads, 64 registers
     case 46: return launch_fused2_t<32, 8, 2, false, 0>(d, p, cur, s, pdl, last);  // 40 with the built-in / and sqrt
+    case 47: return launch_fused2_t<32, 8, 2, true, 0, true>(d, p, cur, s, pdl, last);   // 40 with speculative operand loads
+    case 48: return launch_fused2_t<16, 8, 3, true, 0, true>(d, p, cur, s, pdl, last);   // 42 with speculative operand loads
+    case 49: return launch_fused2_t<32, 8, 2, true, 1, true>(d, p, cur, s, pdl, last);   // 50 with speculative operand loads
     case 50: return launch_fused2_t<32, 8, 2, true, 1>(d, p, cur, s, pdl, last);   // warp-uniform roles, shared-memory swap
     case 51: return launch_fused2_t<32, 8, 1, true, 1>(d, p, cur, s, pdl, last);
     case 52: return launch_fused2_t<32, 4, 3, true, 1>(d, p, cur, s, pdl, last);

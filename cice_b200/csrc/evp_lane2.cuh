@@ -17,7 +17,9 @@
 //          barrier per row (needs PX == 32: one warp per row and role)
 #pragma once
 
-template <int PX, int PY, int MINB, bool IL, int MAP>
+//   SPT:   every operand of the lane requested before the ice mask is known (the speculative form of fused_kernel: one L2
+//          round trip instead of mask -> operands), static ones even before the grid dependency resolves
+template <int PX, int PY, int MINB, bool IL, int MAP, bool SPT = false>
 __global__ void __launch_bounds__(2 * PX *PY, MINB) fused2_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
                                                                   int cur, int flags) {
   static_assert(MAP == 0 || (PX == 32 && PY <= 15), "MAP 1 pairs one north warp with one south warp per row");
@@ -37,6 +39,54 @@ __global__ void __launch_bounds__(2 * PX *PY, MINB) fused2_kernel(const __grid_c
   const int nxt = cur ^ 1;
   const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
   const int c = at(d, inT ? i : 1, inT ? j : 1);
+  if (SPT) {
+    // corner numbering 0 NE, 1 NW, 2 SW, 3 SE: the lane's E corner is NE or SE, its W corner NW or SW
+    const int qE = north ? NE : SE, qW = north ? NW : SW;
+    const unsigned mT = ld_nc_u8(d.maskT + c);
+    const double dxT_ = ld_nc_f64(d.dxT + c), dyT_ = ld_nc_f64(d.dyT + c), dxhy = ld_nc_f64(d.dxhy + c), dyhx = ld_nc_f64(d.dyhx + c);
+    const double cxp = ld_nc_f64(d.cxp + c), cyp = ld_nc_f64(d.cyp + c), cxm = ld_nc_f64(d.cxm + c), cym = ld_nc_f64(d.cym + c);
+    const double dmin = ld_nc_f64(d.DminTarea + c), strength = ld_nc_f64(d.strength + c);
+#if EVP_USE_PDL
+    cudaGridDependencySynchronize();
+#endif
+    const int ca = north ? c : c - d.ld, cb = north ? c - d.ld : c;
+    const double *U = d.u[cur], *V = d.v[cur];
+    const double ua_c = ld_f64(U + ca), va_c = ld_f64(V + ca), ua_e = ld_f64(U + ca - 1), va_e = ld_f64(V + ca - 1);
+    const double ub_c = ld_f64(U + cb), vb_c = ld_f64(V + cb), ub_e = ld_f64(U + cb - 1), vb_e = ld_f64(V + cb - 1);
+    Half own = {ld_f64(d.sig[cur][qE] + c), ld_f64(d.sig[cur][qW] + c), ld_f64(d.sig[cur][4 + qE] + c), ld_f64(d.sig[cur][4 + qW] + c),
+                ld_f64(d.sig[cur][8 + qE] + c), ld_f64(d.sig[cur][8 + qW] + c)};
+    const bool active = inT && mT;
+    if (active) {
+      lane2_relax<IL>(north, ua_c, va_c, ua_e, va_e, ub_c, vb_c, ub_e, vb_e, dxT_, dyT_, cxp, cyp, cxm, cym, dmin, strength, k, own);
+      const bool ownT = (cx < PX - 1 || i == d.nx + 1) && (cy < PY - 1 || j == d.ny + 1);
+      if (ownT) {
+        d.sig[nxt][qE][c] = own.pE; d.sig[nxt][qW][c] = own.pW;
+        d.sig[nxt][4 + qE][c] = own.mE; d.sig[nxt][4 + qW][c] = own.mW;
+        d.sig[nxt][8 + qE][c] = own.sE; d.sig[nxt][8 + qW][c] = own.sW;
+      }
+    } else {
+      own = Half{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    }
+    Half oth;
+    if (MAP == 0) {
+      oth.pE = __shfl_xor_sync(0xffffffffu, own.pE, 1); oth.pW = __shfl_xor_sync(0xffffffffu, own.pW, 1);
+      oth.mE = __shfl_xor_sync(0xffffffffu, own.mE, 1); oth.mW = __shfl_xor_sync(0xffffffffu, own.mW, 1);
+      oth.sE = __shfl_xor_sync(0xffffffffu, own.sE, 1); oth.sW = __shfl_xor_sync(0xffffffffu, own.sW, 1);
+    } else {
+      const int mine = north ? 0 : 6, theirs = north ? 6 : 0;
+      sx[mine + 0][cy][cx] = own.pE; sx[mine + 1][cy][cx] = own.pW; sx[mine + 2][cy][cx] = own.mE;
+      sx[mine + 3][cy][cx] = own.mW; sx[mine + 4][cy][cx] = own.sE; sx[mine + 5][cy][cx] = own.sW;
+      bar_sync64(cy + 1);
+      oth.pE = sx[theirs + 0][cy][cx]; oth.pW = sx[theirs + 1][cy][cx]; oth.mE = sx[theirs + 2][cy][cx];
+      oth.mW = sx[theirs + 3][cy][cx]; oth.sE = sx[theirs + 4][cy][cx]; oth.sW = sx[theirs + 5][cy][cx];
+    }
+    double out[4] = {0.0, 0.0, 0.0, 0.0};
+    if (active) lane2_str(north, own, oth, dxT_, dyT_, dxhy, dyhx, out);
+    sstr[north ? 0 : 2][cy][cx] = out[0];
+    sstr[north ? 1 : 3][cy][cx] = out[1];
+    sstr[north ? 4 : 5][cy][cx] = out[2];
+    sstr[north ? 6 : 7][cy][cx] = out[3];
+  } else {
 #if EVP_USE_PDL
   cudaGridDependencySynchronize();
 #endif
@@ -85,6 +135,7 @@ __global__ void __launch_bounds__(2 * PX *PY, MINB) fused2_kernel(const __grid_c
   sstr[north ? 1 : 3][cy][cx] = out[1];
   sstr[north ? 4 : 5][cy][cx] = out[2];
   sstr[north ? 6 : 7][cy][cx] = out[3];
+  }  // !SPT
   __syncthreads();
 
   if (t < PX * PY) {

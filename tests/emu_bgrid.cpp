@@ -25,9 +25,9 @@ void fused_step(const Dom &d, const KParams &k, int cur, int flags) {
   static const P2PParams nop2p{};
   emu::launch({(d.nx + 30) / 31, (d.ny + 6) / 7, 1}, {32, 8, 1}, [&] { fused_kernel<32, 8, 2, false, false, SPEC>(d, k, cur, nop2p, 0, flags); });
 }
-template <int PX, int PY, bool IL, int MAP>
+template <int PX, int PY, bool IL, int MAP, bool SPT = false>
 void lane2_step(const Dom &d, const KParams &k, int cur, int flags) {
-  emu::launch({(d.nx + PX - 2) / (PX - 1), (d.ny + PY - 2) / (PY - 1), 1}, {2 * PX * PY, 1, 1}, [&] { fused2_kernel<PX, PY, 1, IL, MAP>(d, k, cur, flags); });
+  emu::launch({(d.nx + PX - 2) / (PX - 1), (d.ny + PY - 2) / (PY - 1), 1}, {2 * PX * PY, 1, 1}, [&] { fused2_kernel<PX, PY, 1, IL, MAP, SPT>(d, k, cur, flags); });
 }
 }  // namespace
 
@@ -35,7 +35,7 @@ void lane2_step(const Dom &d, const KParams &k, int cur, int flags) {
 // kind 1: fused_kernel<32,8,2,false,false,SPEC>               sub: SPEC (0 1 2 3 4 5 7 12 16 35 36; 4 is the default form)
 // kind 2: strip_kernel                                        sub: chunks per CTA
 // kind 3: fused4_kernel (four lanes per cell)                 sub: unused
-// kind 4: fused2_kernel (two lanes per cell)                  sub: shape/mapping 0..5, +8 for IL = true
+// kind 4: fused2_kernel (two lanes per cell)                  sub: shape/mapping 0..5, +8 for IL = true, 16..18 speculative loads
 // kind 5: fused_kernel<32,8,2,false,true,4> without peers     sub: 0 = all tiles counted as edge tiles first, 1 = none
 // One block in the reference's layout (nghost = 1) IS a dom: ld = nx_block, interior 1..nx_block-2.
 extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, int wrap_ns, const KParams *kp, int ndte,
@@ -123,6 +123,9 @@ extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, i
         case 11: lane2_step<16, 16, true, 0>(d, k, cur, flags); break;
         case 12: lane2_step<32, 8, true, 1>(d, k, cur, flags); break;
         case 13: lane2_step<32, 4, true, 1>(d, k, cur, flags); break;
+        case 16: lane2_step<32, 8, true, 0, true>(d, k, cur, flags); break;   // speculative operand loads
+        case 17: lane2_step<16, 8, true, 0, true>(d, k, cur, flags); break;
+        case 18: lane2_step<32, 8, true, 1, true>(d, k, cur, flags); break;
         default: return 1;
       }
     } else if (kind == 5) {

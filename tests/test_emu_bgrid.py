@@ -36,6 +36,7 @@ KERNELS = {
     "two-lanes-32x8-warp-pairs": (4, 4), "two-lanes-32x4-warp-pairs": (4, 5),
     "two-lanes-32x8-shuffle-IL": (4, 8), "two-lanes-16x8-shuffle-IL": (4, 9), "two-lanes-32x4-shuffle-IL": (4, 10),
     "two-lanes-16x16-shuffle-IL": (4, 11), "two-lanes-32x8-warp-pairs-IL": (4, 12), "two-lanes-32x4-warp-pairs-IL": (4, 13),
+    "two-lanes-32x8-shuffle-IL-spec": (4, 16), "two-lanes-16x8-shuffle-IL-spec": (4, 17), "two-lanes-32x8-warp-pairs-IL-spec": (4, 18),
     "p2p-no-peers-edge-first": (5, 0), "p2p-no-peers-no-counter": (5, 1),
 }
 
