@@ -19,23 +19,20 @@
 
 //   SPT:   every operand of the lane requested before the ice mask is known (the speculative form of fused_kernel: one L2
 //          round trip instead of mask -> operands), static ones even before the grid dependency resolves
-template <int PX, int PY, int MINB, bool IL, int MAP, bool SPT = false>
-__global__ void __launch_bounds__(2 * PX *PY, MINB) fused2_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
-                                                                  int cur, int flags) {
+//   P2P:   the in-kernel NVLink halo of fused_kernel<..., P2P = true>: (tbx, tby) come from the edge-first tile
+//          table, boundary U points are also stored into the neighbour GPUs' ghost cells
+template <int PX, int PY, bool IL, int MAP, bool SPT, bool P2P>
+__device__ __forceinline__ void lane2_body(const Dom &d, const KParams &k, int cur, int last, int tbx, int tby, const P2PParams *pp) {
   static_assert(MAP == 0 || (PX == 32 && PY <= 15), "MAP 1 pairs one north warp with one south warp per row");
   static_assert(MAP != 0 || PX % 16 == 0, "MAP 0 keeps the 16 cells of a warp on one row");
   __shared__ double sstr[8][PY][PX];
   __shared__ double sx[MAP == 1 ? 12 : 1][PY][PX];  // MAP 1: [0..5] the north lanes' stresses, [6..11] the south lanes'
   const int t = threadIdx.x;
-  const int last = flags & 1;
-#if EVP_USE_PDL
-  if (flags & 2) cudaTriggerProgrammaticLaunchCompletion();  // see fused_kernel
-#endif
   const bool north = MAP == 0 ? !(t & 1) : t < PX * PY;
   const int cell = MAP == 0 ? (t >> 1) : (north ? t : t - PX * PY);
   const int cx = cell % PX, cy = cell / PX;
-  const int i = 1 + blockIdx.x * (PX - 1) + cx;  // T cell of this lane pair
-  const int j = 1 + blockIdx.y * (PY - 1) + cy;
+  const int i = 1 + tbx * (PX - 1) + cx;  // T cell of this lane pair
+  const int j = 1 + tby * (PY - 1) + cy;
   const int nxt = cur ^ 1;
   const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
   const int c = at(d, inT ? i : 1, inT ? j : 1);
@@ -140,7 +137,7 @@ __global__ void __launch_bounds__(2 * PX *PY, MINB) fused2_kernel(const __grid_c
 
   if (t < PX * PY) {
     const int tx = t % PX, ty = t / PX;
-    const int iu = 1 + blockIdx.x * (PX - 1) + tx, ju = 1 + blockIdx.y * (PY - 1) + ty;
+    const int iu = 1 + tbx * (PX - 1) + tx, ju = 1 + tby * (PY - 1) + ty;
     if (tx < PX - 1 && ty < PY - 1 && iu <= d.nx && ju <= d.ny) {
       const int cu = at(d, iu, ju);
       if (d.maskU[cu]) {
@@ -157,6 +154,58 @@ __global__ void __launch_bounds__(2 * PX *PY, MINB) fused2_kernel(const __grid_c
           d.taubx[cu] = o.taubx;
           d.tauby[cu] = o.tauby;
         }
+        if (P2P && (iu == 1 || iu == d.nx || ju == 1 || ju == d.ny)) {  // a ghost cell of up to three neighbour GPUs
+          const int e = edge_index(d, iu, ju);
+          for (int q = pp->push_start[e]; q < pp->push_start[e + 1]; ++q) {
+            const int pr = pp->push_peer[q];
+            const int dst = pp->push_dst[q];
+            pp->peer_u[nxt][pr][dst] = o.u;
+            pp->peer_v[nxt][pr][dst] = o.v;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int PX, int PY, int MINB, bool IL, int MAP, bool SPT = false>
+__global__ void __launch_bounds__(2 * PX *PY, MINB) fused2_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
+                                                                  int cur, int flags) {
+#if EVP_USE_PDL
+  if (flags & 2) cudaTriggerProgrammaticLaunchCompletion();  // see fused_kernel
+#endif
+  lane2_body<PX, PY, IL, MAP, SPT, false>(d, k, cur, flags & 1, blockIdx.x, blockIdx.y, nullptr);
+}
+
+// The in-kernel-halo form: the protocol of fused_kernel<..., P2P = true> around lane2_body (edge tiles first, wait for the
+// neighbours' epoch flags before touching ghost cells, count the edge CTAs, the last one fences at system scope and raises
+// the peers' flags).  The tile table is read from constant memory when `ctiles` is set (evp_b200 P2P_CONST_TILES).
+template <int PX, int PY, int MINB, bool IL, int MAP>
+__global__ void __launch_bounds__(2 * PX *PY, MINB) fused2_p2p_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
+                                                                      int cur, const __grid_constant__ P2PParams pp, int ksub, int flags,
+                                                                      int ctiles) {
+#if EVP_USE_PDL
+  if (flags & 2) cudaTriggerProgrammaticLaunchCompletion();
+#endif
+  const int t = threadIdx.x, b = blockIdx.x;
+  const int tile = ctiles ? c_tile_order[b] : pp.tile_order[b];
+  const bool edge_tile = b < pp.n_edge_tiles;
+  unsigned long long base = 0;
+  if (edge_tile) {
+    // the ghost ring of copy `cur` was written by the neighbour GPUs during their previous subcycle
+    base = *pp.epoch_base;
+    if (t < pp.npeers) wait_flag(pp.my_flags + pp.peer_rank[t], base + (unsigned long long)ksub, pp.err);
+    __syncthreads();
+  }
+  lane2_body<PX, PY, IL, MAP, false, true>(d, k, cur, flags & 1, tile & 0xffff, tile >> 16, &pp);
+  if (edge_tile) {
+    __syncthreads();
+    if (t == 0) {
+      __threadfence();
+      const unsigned long long old = atomicAdd(pp.done_ctr, 1ULL);
+      if (old + 1 == (unsigned long long)pp.n_edge_tiles * (unsigned long long)(ksub + 1)) {
+        __threadfence_system();
+        for (int q = 0; q < pp.npeers; ++q) st_relaxed_sys(pp.peer_flag[q], base + (unsigned long long)ksub + 1ULL);
       }
     }
   }

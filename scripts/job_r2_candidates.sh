@@ -24,5 +24,7 @@ echo "default fast: $(b --mode fast)"
 for v in 40 43 50; do echo "variant $v fast: $(EVP_B200_FUSED_VARIANT=$v b --mode fast)"; done
 echo "== in-kernel-halo kernel, no-peer self test: tile table in global vs constant memory"
 for st in 1 3; do for ct in 0 1; do echo "selftest $st const_tiles $ct: $(EVP_B200_P2P_SELFTEST=$st EVP_B200_P2P_CONST_TILES=$ct b)"; done; done
+echo "selftest 1, two-lane kernel (variant 40): $(EVP_B200_P2P_SELFTEST=1 EVP_B200_FUSED_VARIANT=40 b)"
+echo "parity selftest 1 + two-lane kernel: $(EVP_B200_P2P_SELFTEST=1 EVP_B200_FUSED_VARIANT=40 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k 'exact_mode_bitwise and fused or gx1_ndte240_every_kernel_exact and fused or boundary_types' 2>&1 | tail -1)"
 echo "parity selftest 1 + constant tiles: $(EVP_B200_P2P_SELFTEST=1 EVP_B200_P2P_CONST_TILES=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k 'exact_mode_bitwise and fused or gx1_ndte240_every_kernel_exact and fused or boundary_types' 2>&1 | tail -1)"
 } 2>&1 | tee gpurun_out/r2_candidates.txt

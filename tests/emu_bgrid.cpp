@@ -36,7 +36,8 @@ void lane2_step(const Dom &d, const KParams &k, int cur, int flags) {
 // kind 2: strip_kernel                                        sub: chunks per CTA
 // kind 3: fused4_kernel (four lanes per cell)                 sub: unused
 // kind 4: fused2_kernel (two lanes per cell)                  sub: shape/mapping 0..5, +8 for IL = true, 16..18 speculative loads
-// kind 5: fused_kernel<32,8,2,false,true,4> without peers     sub: 0 = all tiles counted as edge tiles first, 1 = none
+// kind 5: fused_kernel<32,8,2,false,true,4> without peers     sub: 0 = edge tiles first and counted, 1 = none counted
+// kind 6: fused2_p2p_kernel (two lanes + in-kernel halo form)  sub: bit 0 none counted, bit 1 warp-pair mapping, bit 2 constant tile table
 // One block in the reference's layout (nghost = 1) IS a dom: ld = nx_block, interior 1..nx_block-2.
 extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, int wrap_ns, const KParams *kp, int ndte,
                              const int32_t *maskT, const int32_t *maskU, double *sig /*[12][n]*/, double *u, double *v,
@@ -67,7 +68,7 @@ extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, i
   std::vector<int> order, push_start(2 * d.nx + 2 * d.ny + 8, 0);
   unsigned long long done = 0, epoch = 1, flags_mem[64] = {};
   int err = 0;
-  if (kind == 5) {
+  if (kind == 5 || kind == 6) {
     const int ntx = (d.nx + 30) / 31, nty = (d.ny + 6) / 7;
     int n_edge = 0;
     for (int pass = 0; pass < 2; ++pass)
@@ -76,7 +77,7 @@ extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, i
         const bool edge = (bx == 0 || bx == ntx - 1 || by == 0 || by == nty - 1);
         if (edge == (pass == 0)) { order.push_back(((t / ntx) << 16) | (t % ntx)); n_edge += edge; }
       }
-    pp.enabled = 1; pp.npeers = 0; pp.n_edge_tiles = sub == 0 ? n_edge : 0; pp.ntx = ntx; pp.nty = nty;
+    pp.enabled = 1; pp.npeers = 0; pp.n_edge_tiles = (sub & 1) ? 0 : n_edge; pp.ntx = ntx; pp.nty = nty;
     pp.tile_order = order.data(); pp.push_start = push_start.data(); pp.push_peer = push_start.data(); pp.push_dst = push_start.data();
     pp.my_flags = flags_mem; pp.done_ctr = &done; pp.epoch_base = &epoch; pp.err = &err;
   }
@@ -130,6 +131,13 @@ extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, i
       }
     } else if (kind == 5) {
       emu::launch({pp.ntx * pp.nty, 1, 1}, {32, 8, 1}, [&] { fused_kernel<32, 8, 2, false, true, 4>(d, k, cur, pp, ks, flags); });
+      if (err) return 2;
+    } else if (kind == 6) {   // sub bit 0: no edge counter, bit 1: warp-pair mapping, bit 2: tile table from the "constant" array
+      if (sub & 4) memcpy(c_tile_order, order.data(), order.size() * sizeof(int));
+      if (sub & 2)
+        emu::launch({pp.ntx * pp.nty, 1, 1}, {512, 1, 1}, [&] { fused2_p2p_kernel<32, 8, 2, true, 1>(d, k, cur, pp, ks, flags, (sub & 4) ? 1 : 0); });
+      else
+        emu::launch({pp.ntx * pp.nty, 1, 1}, {512, 1, 1}, [&] { fused2_p2p_kernel<32, 8, 2, true, 0>(d, k, cur, pp, ks, flags, (sub & 4) ? 1 : 0); });
       if (err) return 2;
     } else {
       return 1;
