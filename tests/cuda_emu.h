@@ -43,6 +43,7 @@ static Mail mail[MAXT];
 static pthread_barrier_t cta_barrier;
 struct NamedBar { std::atomic<int> count; std::atomic<unsigned> gen; };
 static NamedBar named[16];
+static int cta_order = 0;  // 0 forwards, 1 backwards, 2 alternating from both ends
 
 inline void yield() { sched_yield(); }
 inline void syncthreads() { pthread_barrier_wait(&cta_barrier); }
@@ -82,12 +83,17 @@ inline void launch(Idx grid, Idx block, F kernel) {
       bdim = block;
       gdim = grid;
       shfl_seq = 0;
-      for (int by = 0; by < grid.y; ++by)
-        for (int bx = 0; bx < grid.x; ++bx) {
-          bid = {bx, by, 0};
-          kernel();
-          syncthreads();  // the next CTA reuses the static "shared" arrays
-        }
+      const int nctas = grid.x * grid.y;
+      for (int l = 0; l < nctas; ++l) {
+        // CTAs run one after the other; the ORDER is a test parameter: a kernel whose CTAs are independent within a launch (no CTA
+        // reads what another one writes) gives the same bits forwards, backwards and interleaved
+        int q = l;
+        if (cta_order == 1) q = nctas - 1 - l;
+        else if (cta_order == 2) q = (l % 2 == 0) ? l / 2 : nctas - 1 - l / 2;
+        bid = {q % grid.x, q / grid.x, 0};
+        kernel();
+        syncthreads();  // the next CTA reuses the static "shared" arrays
+      }
     });
   for (auto &x : th) x.join();
   pthread_barrier_destroy(&cta_barrier);
@@ -120,3 +126,5 @@ template <class T> static inline T atomicMin(T *p, T v) { T o = __atomic_load_n(
 template <class T> static inline T atomicMax(T *p, T v) { T o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
 template <class T> static inline T __ldcg(const T *p) { return *(const volatile T *)p; }
 template <class T> static inline void __stcg(T *p, T v) { *(volatile T *)p = v; }
+
+extern "C" void emu_set_cta_order(int order) { emu::cta_order = order; }

@@ -185,3 +185,21 @@ def test_derived_geometry_kernels_on_the_host(oracle_mod, emu, case):
         got = run_emulated(emu, c, 1, sub)
         for nm in abi.STRESS + ("uvel", "vvel", "strintxU", "strintyU", "taubxU", "taubyU"):
             assert np.array_equal(got[nm].view(np.int64), ref[nm][0].view(np.int64)), (sub, nm)
+
+
+@pytest.mark.parametrize("order", [1, 2], ids=["backwards", "alternating"])
+@pytest.mark.parametrize("kernel", ["fused-v23-default", "fused-v19-both", "strip-m2", "two-lanes-32x8-shuffle-IL", "two-lanes-32x8-warp-pairs-IL-spec",
+                                    "p2p-no-peers-edge-first", "two-lanes-p2p-no-peers"])
+def test_cta_order_does_not_matter(oracle_mod, emu, kernel, order):
+    """the emulation runs the CTAs of a launch one after the other, so a hazard BETWEEN CTAs (one reading what another writes in the
+    same launch) would show as a dependence on their order: run them backwards and interleaved from both ends."""
+    c = synth.make_case(**CASES["wide-3sub"])
+    ref = c.copy_fields()
+    oracle_mod.evp_run_bgrid(c.grid, c.params, ref)
+    emu.emu_set_cta_order(order)
+    try:
+        got = run_emulated(emu, c, *KERNELS[kernel])
+    finally:
+        emu.emu_set_cta_order(0)
+    for nm in abi.STRESS + ("uvel", "vvel", "strintxU", "strintyU", "taubxU", "taubyU"):
+        assert np.array_equal(got[nm].view(np.int64), ref[nm][0].view(np.int64)), nm

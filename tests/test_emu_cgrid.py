@@ -92,3 +92,24 @@ def test_cdgrid_kernel_text_on_the_host_equals_the_oracle(oracle_mod, emu, case)
     assert emu.emu_cdgrid_run(C.byref(g), C.byref(cg), C.byref(p), C.byref(s)) == 0
     skip = ("zetax2U", "etax2U") if c.params["visc_method"] == abi.VISC_AVG_STRENGTH else ("strengthU",)
     block_equal(f, ref, abi.CDFIELDS_INOUT + abi.CDFIELDS_OUT, skip)
+
+
+@pytest.mark.parametrize("order", [1, 2], ids=["backwards", "alternating"])
+@pytest.mark.parametrize("form", [0, 1], ids=["five-kernels", "fused-32x8"])
+def test_cgrid_cta_order_does_not_matter(oracle_mod, emu, form, order):
+    """as tests/test_emu_bgrid.py::test_cta_order_does_not_matter: the fused C-grid kernels recompute ring points of neighbouring
+    tiles and ping-pong stress12U exactly so that no CTA depends on another one of the same launch."""
+    c = synth.make_ccase(**CCASES["tiny-cyclic2"])
+    ref = c.copy_fields()
+    oracle_mod.evp_run_cgrid(c.grid, c.cgrid, c.params, ref)
+    f = c.copy_fields()
+    g, kg = abi.make_grid(c.grid)
+    cg, kcg = abi.make_cgrid(c.cgrid, _npl(c.grid))
+    p = abi.make_params(c.params)
+    s, ks = abi.make_cfields(f, _npl(c.grid))
+    emu.emu_set_cta_order(order)
+    try:
+        assert emu.emu_cgrid_run(form, C.byref(g), C.byref(cg), C.byref(p), C.byref(s)) == 0
+    finally:
+        emu.emu_set_cta_order(0)
+    block_equal(f, ref, abi.CFIELDS_INOUT + abi.CFIELDS_OUT, ("strengthU",))
