@@ -19,6 +19,7 @@
 #include <cstring>
 
 #include "evp_b200.h"
+#include "evp_halo_local.cuh"
 
 namespace evp {
 
@@ -282,12 +283,42 @@ int HaloPlan::build(CommState &cs, int gi0, int gj0, int nx, int ny, int ld, int
   HCK(cudaMalloc(&d_recvbuf, sizeof(double) * 2 * std::max(n_recv, 1)));
   const char *eg = getenv("EVP_B200_GRAPH");
   allow_graph = !(eg && eg[0] == '0');
+  // opt-in: one kernel instead of pack + apply when every source is on this rank
+  local_fused = false;
+  if (const char *ef = getenv("EVP_B200_HALO_FUSED")) {
+    if (ef[0] != '0' && cs.nranks == 1 && n_dst > 0 && n_dst <= HALO_LOCAL_MAX) {
+      std::vector<int> h_c1, h_c2;
+      bool all_local = true;
+      for (const Entry &e : mine) {
+        all_local = all_local && e.r1 == me && (e.r2 < 0 || e.r2 == me);
+        h_c1.push_back(e.c1);
+        h_c2.push_back(e.r2 < 0 ? e.c1 : e.c2);
+      }
+      if (all_local) {
+        if (up(d_c1, h_c1, err, nerr) || up(d_c2, h_c2, err, nerr)) return 1;
+        local_fused = true;
+      }
+      local_pdl = (ef[0] == '2') ? 1 : 0;   // 2: also chained by programmatic dependent launch
+    }
+  }
   return 0;
 }
 
 int HaloPlan::exchange(CommState &cs, double *U, double *V, cudaStream_t s, int *launches, char *err, size_t nerr) {
   *launches = 0;
   if (n_dst == 0 && n_pack == 0) return 0;
+  if (local_fused) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(HALO_LOCAL_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = local_pdl ? 1 : 0;
+    HCK(cudaLaunchKernelEx(&cfg, halo_local_kernel, U, V, (const int *)d_dst, (const int *)d_c1, (const int *)d_c2,
+                           (const signed char *)d_code, n_dst, local_pdl));
+    ++*launches;
+    return 0;
+  }
   if (n_pack) {
     halo_pack<<<std::min((n_pack + 127) / 128, 296), 128, 0, s>>>(U, V, d_pack_idx, n_pack, d_packbuf);
     ++*launches;
@@ -530,7 +561,8 @@ std::string HaloPlan::describe() const {
 
 void HaloPlan::release() {
   auto F = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
-  F(d_pack_idx); F(d_dst); F(d_s1); F(d_s2); F(d_code); F(d_packbuf); F(d_recvbuf);
+  F(d_pack_idx); F(d_dst); F(d_s1); F(d_s2); F(d_code); F(d_packbuf); F(d_recvbuf); F(d_c1); F(d_c2);
+  local_fused = false;
   peers.clear();
   n_dst = n_pack = n_loc = n_recv = 0;
   wrap_ew = wrap_ns = 0;

@@ -38,6 +38,10 @@ struct HaloPlan {
   int *d_dst = nullptr, *d_s1 = nullptr, *d_s2 = nullptr;  // [n_dst] dom index to write, slot refs
   signed char *d_code = nullptr;             // [n_dst]
   double *d_packbuf = nullptr, *d_recvbuf = nullptr;       // 2 doubles (u,v) per slot
+  // one rank, every source local (tripole fold on one GPU): pack + apply as one kernel (evp_halo_local.cuh, EVP_B200_HALO_FUSED=1)
+  bool local_fused = false;
+  int local_pdl = 0;
+  int *d_c1 = nullptr, *d_c2 = nullptr;                    // [n_dst] dom index of the sources
 
   struct Peer { int rank, send_off, nsend, recv_off, nrecv; };
   std::vector<Peer> peers;

@@ -7,7 +7,7 @@
 mkdir -p gpurun_out
 {
 echo "== parity of variants 40-53"
-EVP_B200_TEST_CANDIDATES=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "two_lane or dyn_finish or derived_geometry" 2>&1 | tail -15
+EVP_B200_TEST_CANDIDATES=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "two_lane or dyn_finish or derived_geometry or tripole_fold_as_one" 2>&1 | tail -15
 b() { timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu "$@" 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], round(d['roofline']['frac'],4))"; }
 EVP_B200_TEST_CANDIDATES=1 timeout 600 python -m pytest tests/test_cgrid.py -m gpu -q -k programmatic 2>&1 | tail -3
 echo "== gx1 C grid (ndte=600): default vs programmatic dependent launch"
@@ -19,6 +19,8 @@ echo "== derived geometry (two metric arrays instead of seven): gx1 variant 63 v
 echo "gx1 v63: $(EVP_B200_FUSED_VARIANT=63 b)"
 echo "p1deg v19 (default): $(b --workload p1deg --steps 3 --warmup 2)"
 echo "p1deg v59: $(EVP_B200_FUSED_VARIANT=59 b --workload p1deg --steps 3 --warmup 2)"
+echo "== tx1 tripole on one GPU: fold as pack + apply (default) vs one kernel vs one kernel in the PDL chain"
+for hf in 0 1 2; do echo "tx1 halo_fused $hf: $(EVP_B200_HALO_FUSED=$hf b --workload tx1)"; done
 echo "== gx1 fast mode"
 echo "default fast: $(b --mode fast)"
 for v in 40 43 50; do echo "variant $v fast: $(EVP_B200_FUSED_VARIANT=$v b --mode fast)"; done

@@ -193,3 +193,11 @@ extern "C" int emu_set_metric(int nxb, int nyb, const double *geo /*[10][n]*/, c
   c_HTN = HTN; c_HTE = HTE; c_deltamin = deltamin;
   return bad;
 }
+
+// the one-kernel halo update of a single rank (tripole fold): evp_halo_local.cuh on the host-exported plan
+#include "evp_halo_local.cuh"
+extern "C" int emu_halo_local(double *U, double *V, const int *dst, const int *c1, const int *c2, const signed char *code, int n) {
+  if (n > HALO_LOCAL_MAX) return 1;
+  emu::launch({1, 1, 1}, {HALO_LOCAL_THREADS, 1, 1}, [&] { halo_local_kernel(U, V, dst, c1, c2, code, n, 0); });
+  return 0;
+}

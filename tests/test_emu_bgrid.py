@@ -203,3 +203,38 @@ def test_cta_order_does_not_matter(oracle_mod, emu, kernel, order):
         emu.emu_set_cta_order(0)
     for nm in abi.STRESS + ("uvel", "vvel", "strintxU", "strintyU", "taubxU", "taubyU"):
         assert np.array_equal(got[nm].view(np.int64), ref[nm][0].view(np.int64)), nm
+
+
+@pytest.mark.parametrize("nx,ny", [(24, 20), (62, 21)])
+def test_local_halo_kernel_on_the_host_equals_the_oracle_halo(oracle_mod, emu, evp_lib, nx, ny):
+    """EVP_B200_HALO_FUSED: pack + apply of the (uvel,vvel) halo as one kernel when every source is on the rank (tripole fold on one
+    GPU).  The kernel text runs on the host-exported plan (evp_b200_halo_plan, the enumeration the GPU exchange is built from) and
+    must reproduce the oracle's halo update -- ghost row, symmetrised top row with its signed zeros, pole points."""
+    from cice_b200 import dyn_evp
+    c = synth.make_case("tiny", nx=nx, ny=ny, seed=141, ew="cyclic", ns="tripole", kmt="none")
+    g = c.grid
+    tu, tv = c.fields["uvel"].copy(), c.fields["vvel"].copy()
+    for a in (tu, tv):      # ghost cells must come from the update, not from the input
+        a[0, 0, :] = a[0, -1, :] = np.nan
+        a[0, :, 0] = a[0, :, -1] = np.nan
+    oracle_mod.halo_update(g, [tu, tv], field_loc=1, field_type=1)
+    ld = dyn_evp.dom_pitch(nx)
+    plan = np.asarray(dyn_evp.halo_plan([[1, 1, nx, ny]], 0, nx, ny, g["ew_boundary_type"], g["ns_boundary_type"]), dtype=np.int32)
+    assert len(plan) > 0 and (plan[:, 1] == 0).all()
+    dom = {}
+    for name in ("uvel", "vvel"):
+        a = np.full((ny + 2, ld), np.nan)
+        a[1:ny + 1, 1:nx + 1] = c.fields[name][0][1:-1, 1:-1]
+        a[1:ny + 1, 0], a[1:ny + 1, nx + 1] = a[1:ny + 1, nx].copy(), a[1:ny + 1, 1].copy()    # the compute kernels' E-W wrap stores
+        dom[name] = np.ascontiguousarray(a.reshape(-1))
+    dst, c1 = np.ascontiguousarray(plan[:, 0]), np.ascontiguousarray(plan[:, 2])
+    c2 = np.ascontiguousarray(np.where(plan[:, 3] < 0, plan[:, 2], plan[:, 4]).astype(np.int32))
+    code = np.ascontiguousarray(plan[:, 5].astype(np.int8))
+    pd, pi = (lambda a: a.ctypes.data_as(C.POINTER(C.c_double))), (lambda a: a.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert emu.emu_halo_local(pd(dom["uvel"]), pd(dom["vvel"]), pi(dst), pi(c1), pi(c2), code.ctypes.data_as(C.POINTER(C.c_int8)), len(plan)) == 0
+    for name, t in (("uvel", tu), ("vvel", tv)):
+        got = dom[name].reshape(ny + 2, ld)[:, :nx + 2]
+        want = t[0]
+        ok = ~np.isnan(want)
+        assert ok[1:-1, :].all() and ok[-1, 1:-1].all()           # interior rows incl. E-W ghosts, and the tripole ghost row
+        assert np.array_equal(got[ok].view(np.int64), want[ok].view(np.int64)), name

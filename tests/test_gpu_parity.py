@@ -390,6 +390,20 @@ def test_derived_geometry_variants(oracle_mod, evp_lib, monkeypatch, variant):
             assert_bitwise(f, ref)
 
 
+@CANDIDATES
+@pytest.mark.parametrize("mode", ["1", "2"], ids=["one-kernel", "one-kernel-pdl"])
+def test_tripole_fold_as_one_kernel(oracle_mod, evp_lib, monkeypatch, mode):
+    """EVP_B200_HALO_FUSED=1|2: on one rank the tripole fold runs as one kernel (evp_halo_local.cuh) instead of pack + apply, with
+    mode 2 inside the programmatic-dependent-launch chain.  Host-emulated against the oracle's halo in tests/test_emu_bgrid.py."""
+    monkeypatch.setenv("EVP_B200_HALO_FUSED", mode)
+    for c in (synth.make_case("tiny", seed=15, ns="tripole", ew="cyclic", kmt="none", ndte=12),
+              synth.make_case("tiny", nx=62, ny=21, seed=16, ns="tripole", ew="cyclic", kmt="none", ndte=7),
+              synth.make_case("tx1", ndte=30)):
+        ref = run_oracle(oracle_mod, c)
+        for kernel in (abi.KERNEL_FUSED, abi.KERNEL_SPLIT):
+            assert_bitwise(run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=kernel), ref)
+
+
 def test_interleaved_divsqrt_hits_the_fallback(oracle_mod, evp_lib, monkeypatch):
     """operands outside the fast path of the hand-scheduled division / square root (zero and denormal-range
     strain rates and numerators: ice at rest, zero forcing) must take the built-in operators and stay bit-identical."""
