@@ -1150,8 +1150,13 @@ static int do_run_cdgrid(const evp_b200_params_t *p, evp_b200_cdfields_t *f) {
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t le = cudaSuccess;
-    for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub)
+    const char *epdl = getenv("EVP_B200_CDGRID_PDL");
+    const bool cd_pdl = epdl && epdl[0] == '1';   // round-2 candidate: the four kernels chained by programmatic dependent launch
+    for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub) {
+      if (cd_pdl) le = exact ? exact::launch_cdgrid_subcycle_pdl(c, k, g.stream, &nl) : fast::launch_cdgrid_subcycle_pdl(c, k, g.stream, &nl);
+      else
       le = exact ? exact::launch_cdgrid_subcycle(c, k, g.stream, &nl) : fast::launch_cdgrid_subcycle(c, k, g.stream, &nl);
+    }
     cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
     if (le != cudaSuccess || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail("evp_b200_run_cdgrid: capture failed: %s", cudaGetErrorString(le != cudaSuccess ? le : ce)); }
     CK(cudaGraphInstantiate(&g.cdexec, graph, 0));

@@ -494,7 +494,9 @@ __device__ __forceinline__ double t2u_S(const CDom &d, const double *__restrict_
   return (mc * src[c] * wc + me * src[e] * we + mn * src[n] * wn + mne * src[ne] * wne) / wtmp;
 }
 
+template <bool PDL = false>
 __global__ void __launch_bounds__(256) kcd1_stress_T(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  if (PDL) pdl_enter();
   CELL_IJ(d.wrap_ew ? d.nx : d.nx + 1, d.wrap_ns ? d.ny : d.ny + 1);
   const int c = AT(i, j);
   if (!d.maskT[c]) return;
@@ -518,7 +520,9 @@ __global__ void __launch_bounds__(256) kcd1_stress_T(const __grid_constant__ CDo
   ring_store(d, d.stress12T, i, j, s12, 3, false);
 }
 
+template <bool PDL = false>
 __global__ void __launch_bounds__(256) kcd2_stress_U(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  if (PDL) pdl_enter();
   CELL_IJ(d.nx, d.ny);
   const int c = AT(i, j);
   double zetax2U = 0.0, etax2U = 0.0, strengthU = 0.0;
@@ -578,7 +582,9 @@ __device__ __forceinline__ void stepuv_cd_at(const KParams &k, double uold, doub
   tauby = -vn * Cb;
 }
 
+template <bool PDL = false>
 __global__ void __launch_bounds__(256) kcd3_momentum(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
+  if (PDL) pdl_enter();
   CELL_IJ(d.nx, d.ny);
   const int c = AT(i, j), e = c + 1, n = c + d.ld, s = c - d.ld, w = c - 1;
   if (d.maskE[c]) {
@@ -621,7 +627,9 @@ __global__ void __launch_bounds__(256) kcd3_momentum(const __grid_constant__ CDo
   }
 }
 
+template <bool PDL = false>
 __global__ void __launch_bounds__(256) kcd4_interp(const __grid_constant__ CDom d) {
+  if (PDL) pdl_enter();
   CELL_IJ(d.nx, d.ny);
   const int c = AT(i, j), e = c + 1, n = c + d.ld;
   double num, den;
@@ -636,12 +644,22 @@ __global__ void __launch_bounds__(256) kcd4_interp(const __grid_constant__ CDom 
 #ifndef EVP_HOST_EMU  // launchers (and the cooperative kernel): not part of the host emulation (tests/emu_cgrid.cpp)
 cudaError_t launch_cdgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches) {
   dim3 b(32, 8), gU((d.nx + 31) / 32, (d.ny + 7) / 8), gT((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8);
-  kcd1_stress_T<<<gT, b, 0, s>>>(d, p);
-  kcd2_stress_U<<<gU, b, 0, s>>>(d, p);
-  kcd3_momentum<<<gU, b, 0, s>>>(d, p);
-  kcd4_interp<<<gU, b, 0, s>>>(d);
+  kcd1_stress_T<false><<<gT, b, 0, s>>>(d, p);
+  kcd2_stress_U<false><<<gU, b, 0, s>>>(d, p);
+  kcd3_momentum<false><<<gU, b, 0, s>>>(d, p);
+  kcd4_interp<false><<<gU, b, 0, s>>>(d);
   *launches += 4;
   return cudaGetLastError();
+}
+// the same four kernels chained by programmatic dependent launch (EVP_B200_CDGRID_PDL=1; round-2 candidate)
+cudaError_t launch_cdgrid_subcycle_pdl(const CDom &d, const KParams &p, cudaStream_t s, int *launches) {
+  dim3 b(32, 8), gU((d.nx + 31) / 32, (d.ny + 7) / 8), gT((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8);
+  cudaError_t e = launch_pdl(kcd1_stress_T<true>, gT, b, s, d, p);
+  if (e == cudaSuccess) e = launch_pdl(kcd2_stress_U<true>, gU, b, s, d, p);
+  if (e == cudaSuccess) e = launch_pdl(kcd3_momentum<true>, gU, b, s, d, p);
+  if (e == cudaSuccess) e = launch_pdl(kcd4_interp<true>, gU, b, s, d);
+  *launches += 4;
+  return e;
 }
 #endif  // EVP_HOST_EMU
 

@@ -125,6 +125,7 @@ struct PersistPlan {
   cudaError_t launch_cgrid_static(const CDom &d, double *rhalf_dyE, double *r_dxE, double *rhalf_dxN, double *r_dyN, double *uareaavgr, cudaStream_t s); \
   cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur, int shape, cudaStream_t s, int *launches);  \
   cudaError_t launch_cdgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \
+  cudaError_t launch_cdgrid_subcycle_pdl(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \
   cudaError_t launch_cgrid_coop(const CDom &d, const KParams &p, int ndte, unsigned *bar, int max_ctas, cudaStream_t s); \
   int cgrid_coop_max_ctas(int num_sms); \
   }

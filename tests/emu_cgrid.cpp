@@ -133,10 +133,10 @@ extern "C" int emu_cdgrid_run(const evp_b200_grid_t *g, const evp_b200_cgrid_t *
   const KParams k = kparams(p);
   const emu::Idx b{32, 8, 1}, gU{(c.nx + 31) / 32, (c.ny + 7) / 8, 1}, gT{(c.nx + 1 + 31) / 32, (c.ny + 1 + 7) / 8, 1};
   for (int ks = 0; ks < p->ndte; ++ks) {
-    emu::launch(gT, b, [&] { kcd1_stress_T(c, k); });
-    emu::launch(gU, b, [&] { kcd2_stress_U(c, k); });
-    emu::launch(gU, b, [&] { kcd3_momentum(c, k); });
-    emu::launch(gU, b, [&] { kcd4_interp(c); });
+    emu::launch(gT, b, [&] { kcd1_stress_T<false>(c, k); });
+    emu::launch(gU, b, [&] { kcd2_stress_U<false>(c, k); });
+    emu::launch(gU, b, [&] { kcd3_momentum<false>(c, k); });
+    emu::launch(gU, b, [&] { kcd4_interp<false>(c); });
   }
   return 0;
 }

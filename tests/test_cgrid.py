@@ -325,3 +325,16 @@ def test_cdgrid_repeat_and_fast_mode(oracle_mod, evp_lib):
             assert np.abs(fast[n] - one[n]).max() / den <= 1e-10, n
     finally:
         evp_lib.dyn_evp_b200_finalize()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("EVP_B200_TEST_CANDIDATES", "0") != "1",
+                    reason="round-2 candidate: written after the round-1 GPU budget was spent; set EVP_B200_TEST_CANDIDATES=1")
+def test_cdgrid_with_programmatic_dependent_launch(oracle_mod, evp_lib, monkeypatch):
+    """EVP_B200_CDGRID_PDL=1: the four CD-grid kernels chained by programmatic dependent launch (same kernels, same arithmetic)."""
+    monkeypatch.setenv("EVP_B200_CDGRID_PDL", "1")
+    for cfg, kw in (("tiny", dict(seed=3, ndte=7)), ("tiny", dict(seed=7, ew="cyclic", ns="cyclic", kmt="none")), ("gx3", dict(ndte=15))):
+        c = synth.make_cdcase(cfg, **kw)
+        ref = run_oracle_cd(oracle_mod, c)
+        got = run_gpu_cd(evp_lib, c, mode=abi.MODE_EXACT)
+        _cd_compare(got, ref, c.params)
