@@ -859,6 +859,9 @@ cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s
     case 48: return launch_fused2_t<16, 8, 3, true, 0, true>(d, p, cur, s, pdl, last);   // 42 with speculative operand loads
     case 49: return launch_fused2_t<32, 8, 2, true, 1, true>(d, p, cur, s, pdl, last);   // 50 with speculative operand loads
     case 50: return launch_fused2_t<32, 8, 2, true, 1>(d, p, cur, s, pdl, last);   // warp-uniform roles, shared-memory swap
+    case 54: return launch_fused2_t<32, 8, 2, true, 2>(d, p, cur, s, pdl, last);   // 50 with one specialised code path per role
+    case 55: return launch_fused2_t<32, 4, 4, true, 2>(d, p, cur, s, pdl, last);
+    case 56: return launch_fused2_t<32, 8, 2, true, 2, true>(d, p, cur, s, pdl, last);   // 54 with speculative operand loads
     case 51: return launch_fused2_t<32, 8, 1, true, 1>(d, p, cur, s, pdl, last);
     case 52: return launch_fused2_t<32, 4, 3, true, 1>(d, p, cur, s, pdl, last);
     case 53: return launch_fused2_t<32, 4, 4, true, 1>(d, p, cur, s, pdl, last);

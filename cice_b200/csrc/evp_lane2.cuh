@@ -12,6 +12,7 @@
 // host emulation in tests/emu_bgrid.cpp.
 //
 //   MAP 0: lanes 2q and 2q+1 of a warp share T cell q; stresses swapped with __shfl_xor_sync
+//   MAP 2: MAP 1 with the two roles as two specialised code paths (`north` a compile-time constant in each)
 //   MAP 1: threads [0, PX*PY) are the north lanes, [PX*PY, 2*PX*PY) the south lanes of the same cells (`north` is
 //          warp-uniform, loads fully coalesced); stresses swapped through shared memory behind a 64-thread named
 //          barrier per row (needs PX == 32: one warp per row and role)
@@ -21,21 +22,12 @@
 //          round trip instead of mask -> operands), static ones even before the grid dependency resolves
 //   P2P:   the in-kernel NVLink halo of fused_kernel<..., P2P = true>: (tbx, tby) come from the edge-first tile
 //          table, boundary U points are also stored into the neighbour GPUs' ghost cells
-template <int PX, int PY, bool IL, int MAP, bool SPT, bool P2P>
-__device__ __forceinline__ void lane2_body(const Dom &d, const KParams &k, int cur, int last, int tbx, int tby, const P2PParams *pp) {
-  static_assert(MAP == 0 || (PX == 32 && PY <= 15), "MAP 1 pairs one north warp with one south warp per row");
-  static_assert(MAP != 0 || PX % 16 == 0, "MAP 0 keeps the 16 cells of a warp on one row");
-  __shared__ double sstr[8][PY][PX];
-  __shared__ double sx[MAP == 1 ? 12 : 1][PY][PX];  // MAP 1: [0..5] the north lanes' stresses, [6..11] the south lanes'
-  const int t = threadIdx.x;
-  const bool north = MAP == 0 ? !(t & 1) : t < PX * PY;
-  const int cell = MAP == 0 ? (t >> 1) : (north ? t : t - PX * PY);
-  const int cx = cell % PX, cy = cell / PX;
-  const int i = 1 + tbx * (PX - 1) + cx;  // T cell of this lane pair
-  const int j = 1 + tby * (PY - 1) + cy;
+// the stress half of the kernel for one lane.  `north` may be a compile-time constant at the call site (MAP 2): the function is
+// always inlined, so the selections on it fold away
+template <int PX, int PY, bool IL, int MAP, bool SPT, int NSX>
+__device__ __forceinline__ void lane2_stress(const Dom &d, const KParams &k, int cur, const bool north, int cx, int cy, int i, int j,
+                                             bool inT, int c, double (&sstr)[8][PY][PX], double (&sx)[NSX][PY][PX]) {
   const int nxt = cur ^ 1;
-  const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
-  const int c = at(d, inT ? i : 1, inT ? j : 1);
   if (SPT) {
     // corner numbering 0 NE, 1 NW, 2 SW, 3 SE: the lane's E corner is NE or SE, its W corner NW or SW
     const int qE = north ? NE : SE, qW = north ? NW : SW;
@@ -133,6 +125,31 @@ __device__ __forceinline__ void lane2_body(const Dom &d, const KParams &k, int c
   sstr[north ? 4 : 5][cy][cx] = out[2];
   sstr[north ? 6 : 7][cy][cx] = out[3];
   }  // !SPT
+}
+
+template <int PX, int PY, bool IL, int MAP, bool SPT, bool P2P>
+__device__ __forceinline__ void lane2_body(const Dom &d, const KParams &k, int cur, int last, int tbx, int tby, const P2PParams *pp) {
+  static_assert(MAP == 0 || (PX == 32 && PY <= 15), "MAP 1, 2 pair one north warp with one south warp per row");
+  static_assert(MAP != 0 || PX % 16 == 0, "MAP 0 keeps the 16 cells of a warp on one row");
+  __shared__ double sstr[8][PY][PX];
+  constexpr int NSX = MAP == 0 ? 1 : 12;
+  __shared__ double sx[NSX][PY][PX];  // MAP 1, 2: [0..5] the north lanes' stresses, [6..11] the south lanes'
+  const int t = threadIdx.x;
+  const bool north = MAP == 0 ? !(t & 1) : t < PX * PY;
+  const int cell = MAP == 0 ? (t >> 1) : (north ? t : t - PX * PY);
+  const int cx = cell % PX, cy = cell / PX;
+  const int i = 1 + tbx * (PX - 1) + cx;  // T cell of this lane pair
+  const int j = 1 + tby * (PY - 1) + cy;
+  const int nxt = cur ^ 1;
+  const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
+  const int c = at(d, inT ? i : 1, inT ? j : 1);
+  if (MAP == 2) {
+    // warp-uniform roles as MAP 1, and each role runs its own specialised copy of the stress code (no selections on `north`)
+    if (north) lane2_stress<PX, PY, IL, 1, SPT, NSX>(d, k, cur, true, cx, cy, i, j, inT, c, sstr, sx);
+    else lane2_stress<PX, PY, IL, 1, SPT, NSX>(d, k, cur, false, cx, cy, i, j, inT, c, sstr, sx);
+  } else {
+    lane2_stress<PX, PY, IL, MAP, SPT, NSX>(d, k, cur, north, cx, cy, i, j, inT, c, sstr, sx);
+  }
   __syncthreads();
 
   if (t < PX * PY) {

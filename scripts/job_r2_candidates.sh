@@ -17,7 +17,7 @@ echo "== gx1 C grid (ndte=600): default vs programmatic dependent launch"
 for sh in 0 16 18; do echo "cgrid shape $sh: $(EVP_B200_CGRID_SHAPE=$sh b --grid C)"; done
 echo "== gx1, ms per step and roofline fraction"
 echo "default: $(b)"
-for v in 40 41 42 43 44 45 46 47 48 49 50 51 52 53; do echo "variant $v: $(EVP_B200_FUSED_VARIANT=$v b)"; done
+for v in 40 41 42 43 44 45 46 47 48 49 50 51 52 53 54 55 56; do echo "variant $v: $(EVP_B200_FUSED_VARIANT=$v b)"; done
 echo "== derived geometry (two metric arrays instead of seven): gx1 variant 63 vs 23, 3600x2400 variant 59 vs 19"
 echo "gx1 v63: $(EVP_B200_FUSED_VARIANT=63 b)"
 echo "p1deg v19 (default): $(b --workload p1deg --steps 3 --warmup 2)"

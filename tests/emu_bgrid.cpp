@@ -35,7 +35,7 @@ void lane2_step(const Dom &d, const KParams &k, int cur, int flags) {
 // kind 1: fused_kernel<32,8,2,false,false,SPEC>               sub: SPEC (0 1 2 3 4 5 7 12 16 35 36; 4 is the default form)
 // kind 2: strip_kernel                                        sub: chunks per CTA
 // kind 3: fused4_kernel (four lanes per cell)                 sub: unused
-// kind 4: fused2_kernel (two lanes per cell)                  sub: shape/mapping 0..5, +8 for IL = true, 16..18 speculative loads
+// kind 4: fused2_kernel (two lanes per cell)                  sub: shape/mapping 0..5, +8 for IL = true, 16..18 speculative loads, 20..22 specialised roles
 // kind 5: fused_kernel<32,8,2,false,true,4> without peers     sub: 0 = edge tiles first and counted, 1 = none counted
 // kind 6: fused2_p2p_kernel (two lanes + in-kernel halo form)  sub: bit 0 none counted, bit 1 warp-pair mapping, bit 2 constant tile table
 // One block in the reference's layout (nghost = 1) IS a dom: ld = nx_block, interior 1..nx_block-2.
@@ -127,6 +127,9 @@ extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, i
         case 16: lane2_step<32, 8, true, 0, true>(d, k, cur, flags); break;   // speculative operand loads
         case 17: lane2_step<16, 8, true, 0, true>(d, k, cur, flags); break;
         case 18: lane2_step<32, 8, true, 1, true>(d, k, cur, flags); break;
+        case 20: lane2_step<32, 8, true, 2>(d, k, cur, flags); break;         // one specialised code path per role
+        case 21: lane2_step<32, 4, true, 2>(d, k, cur, flags); break;
+        case 22: lane2_step<32, 8, true, 2, true>(d, k, cur, flags); break;
         default: return 1;
       }
     } else if (kind == 5) {

@@ -37,6 +37,7 @@ KERNELS = {
     "two-lanes-32x8-shuffle-IL": (4, 8), "two-lanes-16x8-shuffle-IL": (4, 9), "two-lanes-32x4-shuffle-IL": (4, 10),
     "two-lanes-16x16-shuffle-IL": (4, 11), "two-lanes-32x8-warp-pairs-IL": (4, 12), "two-lanes-32x4-warp-pairs-IL": (4, 13),
     "two-lanes-32x8-shuffle-IL-spec": (4, 16), "two-lanes-16x8-shuffle-IL-spec": (4, 17), "two-lanes-32x8-warp-pairs-IL-spec": (4, 18),
+    "two-lanes-32x8-roles-IL": (4, 20), "two-lanes-32x4-roles-IL": (4, 21), "two-lanes-32x8-roles-IL-spec": (4, 22),
     "p2p-no-peers-edge-first": (5, 0), "p2p-no-peers-no-counter": (5, 1),
     "two-lanes-p2p-no-peers": (6, 0), "two-lanes-p2p-no-peers-no-counter": (6, 1), "two-lanes-p2p-warp-pairs": (6, 2),
     "two-lanes-p2p-constant-tiles": (6, 4),

@@ -337,7 +337,7 @@ def test_fused_variants_bitwise(oracle_mod, evp_lib, monkeypatch, variant, extra
 
 
 @CANDIDATES
-@pytest.mark.parametrize("variant", ["40", "41", "42", "43", "44", "45", "46", "47", "48", "49", "50", "51", "52", "53"])
+@pytest.mark.parametrize("variant", ["40", "41", "42", "43", "44", "45", "46", "47", "48", "49", "50", "51", "52", "53", "54", "55", "56"])
 def test_two_lane_variants(oracle_mod, evp_lib, monkeypatch, variant):
     monkeypatch.setenv("EVP_B200_FUSED_VARIANT", variant)
     cases = [synth.make_case("tiny", seed=11, block_size=(12, 10), ndte=9),
