@@ -887,10 +887,11 @@ cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = (last & 4) ? 1 : 0;
   const int flags = last & 3;
-  if ((variant & 0xff) == 40 || (variant & 0xff) == 50) {  // two lanes per T cell (evp_lane2.cuh), same 32 x 8 tile table
+  if ((variant & 0xff) == 40 || (variant & 0xff) == 50 || (variant & 0xff) == 54) {  // two lanes per T cell (evp_lane2.cuh), same 32 x 8 tile table
     cfg.blockDim = dim3(512);
     const int ctiles = (variant & 0x100) ? 1 : 0;
     if ((variant & 0xff) == 40) return cudaLaunchKernelEx(&cfg, fused2_p2p_kernel<32, 8, 2, true, 0>, d, p, cur, pp, ksub, flags, ctiles);
+    if ((variant & 0xff) == 54) return cudaLaunchKernelEx(&cfg, fused2_p2p_kernel<32, 8, 2, true, 2>, d, p, cur, pp, ksub, flags, ctiles);
     return cudaLaunchKernelEx(&cfg, fused2_p2p_kernel<32, 8, 2, true, 1>, d, p, cur, pp, ksub, flags, ctiles);
   }
   if ((variant & 0xff) == 59) return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 3 | 32>, d, p, cur, pp, ksub, flags);

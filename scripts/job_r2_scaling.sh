@@ -15,8 +15,9 @@ echo "== weak scaling, gx1-sized sub-domain per GPU"
 timeout 300 python bench.py --gpus 1 --steps 8 --warmup 3 --no-cpu 2>/dev/null | tail -1 > gpurun_out/r2_scale_n1.json
 run 29742 bench.py --gpus $N --steps 8 --warmup 3 2>gpurun_out/r2_scale_n$N.err | tail -1 > gpurun_out/r2_scale_n$N.json
 EVP_B200_P2P_CONST_TILES=1 run 29743 bench.py --gpus $N --steps 8 --warmup 3 2>/dev/null | tail -1 > gpurun_out/r2_scale_n${N}_ctiles.json
+EVP_B200_FUSED_VARIANT=54 run 29746 bench.py --gpus $N --steps 8 --warmup 3 2>/dev/null | tail -1 > gpurun_out/r2_scale_n${N}_v54.json
 EVP_B200_FUSED_VARIANT=40 run 29745 bench.py --gpus $N --steps 8 --warmup 3 2>/dev/null | tail -1 > gpurun_out/r2_scale_n${N}_v40.json
-for f in gpurun_out/r2_scale_n${N}_v40.json gpurun_out/r2_scale_n1.json gpurun_out/r2_scale_n$N.json gpurun_out/r2_scale_n${N}_ctiles.json; do
+for f in gpurun_out/r2_scale_n${N}_v54.json gpurun_out/r2_scale_n${N}_v40.json gpurun_out/r2_scale_n1.json gpurun_out/r2_scale_n$N.json gpurun_out/r2_scale_n${N}_ctiles.json; do
   python -c "
 import json
 d=json.loads(open('$f').read().strip().splitlines()[-1])

@@ -37,7 +37,7 @@ void lane2_step(const Dom &d, const KParams &k, int cur, int flags) {
 // kind 3: fused4_kernel (four lanes per cell)                 sub: unused
 // kind 4: fused2_kernel (two lanes per cell)                  sub: shape/mapping 0..5, +8 for IL = true, 16..18 speculative loads, 20..22 specialised roles
 // kind 5: fused_kernel<32,8,2,false,true,4> without peers     sub: 0 = edge tiles first and counted, 1 = none counted
-// kind 6: fused2_p2p_kernel (two lanes + in-kernel halo form)  sub: bit 0 none counted, bit 1 warp-pair mapping, bit 2 constant tile table
+// kind 6: fused2_p2p_kernel (two lanes + in-kernel halo form)  sub: bit 0 none counted, bit 1 warp-pair mapping, bit 2 constant tile table, bit 3 specialised roles
 // One block in the reference's layout (nghost = 1) IS a dom: ld = nx_block, interior 1..nx_block-2.
 extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, int wrap_ns, const KParams *kp, int ndte,
                              const int32_t *maskT, const int32_t *maskU, double *sig /*[12][n]*/, double *u, double *v,
@@ -137,7 +137,9 @@ extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, i
       if (err) return 2;
     } else if (kind == 6) {   // sub bit 0: no edge counter, bit 1: warp-pair mapping, bit 2: tile table from the "constant" array
       if (sub & 4) memcpy(c_tile_order, order.data(), order.size() * sizeof(int));
-      if (sub & 2)
+      if (sub & 8)
+        emu::launch({pp.ntx * pp.nty, 1, 1}, {512, 1, 1}, [&] { fused2_p2p_kernel<32, 8, 2, true, 2>(d, k, cur, pp, ks, flags, (sub & 4) ? 1 : 0); });
+      else if (sub & 2)
         emu::launch({pp.ntx * pp.nty, 1, 1}, {512, 1, 1}, [&] { fused2_p2p_kernel<32, 8, 2, true, 1>(d, k, cur, pp, ks, flags, (sub & 4) ? 1 : 0); });
       else
         emu::launch({pp.ntx * pp.nty, 1, 1}, {512, 1, 1}, [&] { fused2_p2p_kernel<32, 8, 2, true, 0>(d, k, cur, pp, ks, flags, (sub & 4) ? 1 : 0); });

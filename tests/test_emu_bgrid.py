@@ -40,7 +40,7 @@ KERNELS = {
     "two-lanes-32x8-roles-IL": (4, 20), "two-lanes-32x4-roles-IL": (4, 21), "two-lanes-32x8-roles-IL-spec": (4, 22),
     "p2p-no-peers-edge-first": (5, 0), "p2p-no-peers-no-counter": (5, 1),
     "two-lanes-p2p-no-peers": (6, 0), "two-lanes-p2p-no-peers-no-counter": (6, 1), "two-lanes-p2p-warp-pairs": (6, 2),
-    "two-lanes-p2p-constant-tiles": (6, 4),
+    "two-lanes-p2p-constant-tiles": (6, 4), "two-lanes-p2p-roles": (6, 8),
 }
 
 
