@@ -13,7 +13,7 @@ SYMBOLS = (
     "evp_b200_get_unique_id", "evp_b200_comm_init", "evp_b200_set_device", "evp_b200_init", "evp_b200_finalize",
     "evp_b200_last_error", "evp_b200_run_bgrid", "evp_b200_upload", "evp_b200_subcycle", "evp_b200_download",
     "evp_b200_last_loop_ms", "evp_b200_last_launches", "evp_b200_stream", "evp_b200_describe",
-    "evp_b200_halo_plan", "evp_b200_dom_pitch", "evp_b200_init_cgrid", "evp_b200_run_cgrid", "evp_b200_deformations", "evp_b200_dyn_finish", "evp_b200_set_metric",
+    "evp_b200_halo_plan", "evp_b200_dom_pitch", "evp_b200_init_cgrid", "evp_b200_run_cgrid", "evp_b200_deformations", "evp_b200_dyn_finish", "evp_b200_set_metric", "evp_b200_pin_host", "evp_b200_unpin_host",
     "evp_b200_run_bgrid_resident", "evp_b200_download_stress", "evp_b200_allow_partial_domain", "evp_b200_run_cdgrid",
 )
 
@@ -60,6 +60,8 @@ def load():
     L.evp_b200_run_cdgrid.argtypes = [pp, C.POINTER(abi.CDFields)]
     L.evp_b200_deformations.argtypes = [C.POINTER(abi.Deform)]
     L.evp_b200_dyn_finish.argtypes = [C.POINTER(abi.Finish)]
+    L.evp_b200_pin_host.argtypes = [C.c_void_p, C.c_size_t]
+    L.evp_b200_unpin_host.argtypes = [C.c_void_p]
     L.evp_b200_set_metric.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_int32)]
     L.evp_b200_upload.argtypes = [pf]
     L.evp_b200_run_bgrid_resident.argtypes = [pp, pf, C.c_int32]

@@ -1232,6 +1232,21 @@ int evp_b200_finalize(void) {
 }
 
 int evp_b200_deformations(evp_b200_deform_t *d) { return do_deformations(d); }
+int evp_b200_pin_host(void *ptr, size_t bytes) {
+  if (!ptr || !bytes) return fail("evp_b200_pin_host: null argument");
+  if (g.device >= 0) CK(cudaSetDevice(g.device));
+  const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+  if (e != cudaSuccess) return fail("evp_b200_pin_host: %s", cudaGetErrorString(e));
+  return 0;
+}
+int evp_b200_unpin_host(void *ptr) {
+  if (!ptr) return fail("evp_b200_unpin_host: null argument");
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return 0; }
+  if (e != cudaSuccess) return fail("evp_b200_unpin_host: %s", cudaGetErrorString(e));
+  return 0;
+}
 int evp_b200_dyn_finish(evp_b200_finish_t *f) { return do_dyn_finish(f); }
 int evp_b200_set_metric(const double *HTN, const double *HTE, double deltaminEVP, int32_t *mismatches) {
   return do_set_metric(HTN, HTE, deltaminEVP, mismatches);

@@ -126,6 +126,15 @@ def dyn_finish(d, rhow, cosw=1.0, sinw=0.0):
     return d
 
 
+def pin_host(a):
+    """page-lock a numpy array that is passed to the library every step (evp_b200_pin_host)."""
+    check(load().evp_b200_pin_host(a.ctypes.data, a.nbytes), "evp_b200_pin_host")
+
+
+def unpin_host(a):
+    check(load().evp_b200_unpin_host(a.ctypes.data), "evp_b200_unpin_host")
+
+
 def set_metric(HTN, HTE, deltaminEVP):
     """hand HTN, HTE (block arrays) to the library; returns the number of T cells on which the reference's expressions do NOT
     reproduce dxhy, dyhx, cxp, cyp, cxm, cym, DminTarea bit for bit (0 = the derived-geometry kernels, variants 59/63, may be used)."""

@@ -90,6 +90,11 @@ module ice_dyn_evp_b200
   end type evp_b200_finish_t
 
   interface
+     integer(c_int) function evp_b200_pin_host(ptr, bytes) bind(C, name='evp_b200_pin_host')
+       import :: c_int, c_ptr, c_size_t
+       type(c_ptr), value :: ptr
+       integer(c_size_t), value :: bytes
+     end function evp_b200_pin_host
      integer(c_int) function evp_b200_set_metric(HTN, HTE, deltaminEVP, mismatches) bind(C, name='evp_b200_set_metric')
        import :: c_int, c_int32_t, c_double, c_ptr
        type(c_ptr), value :: HTN, HTE
@@ -162,6 +167,7 @@ module ice_dyn_evp_b200
   integer(c_int32_t), allocatable, target, save :: b_iglob(:,:), b_jglob(:,:)
   integer(c_int32_t), allocatable, target, save :: imaskT(:,:,:), imaskU(:,:,:)
   integer(c_int32_t), allocatable, target, save :: imaskE(:,:,:), imaskN(:,:,:)   ! C grid
+  logical, save :: pinned = .false.   ! the B-grid field arrays have been page-locked (evp_b200_pin_host)
 
 contains
 
@@ -302,6 +308,21 @@ contains
     f%taubxU = c_loc(taubxU);      f%taubyU = c_loc(taubyU);      f%uvel = c_loc(uvel);        f%vvel = c_loc(vvel)
     f%iceTmask = c_loc(imaskT);    f%iceUmask = c_loc(imaskU)
 
+    ! the arrays are module variables of ice_dyn_evp / ice_flux / ice_state and never move: page-lock them on the first call, so
+    ! that every later copy runs at the PCIe rate instead of through the driver's staging of pageable memory
+    if (.not. pinned) then
+       call pin(stressp_1);  call pin(stressp_2);  call pin(stressp_3);  call pin(stressp_4)
+       call pin(stressm_1);  call pin(stressm_2);  call pin(stressm_3);  call pin(stressm_4)
+       call pin(stress12_1); call pin(stress12_2); call pin(stress12_3); call pin(stress12_4)
+       call pin(strength);   call pin(cdn_ocnU);   call pin(aiU);        call pin(uocnU);     call pin(vocnU)
+       call pin(waterxU);    call pin(wateryU);    call pin(forcexU);    call pin(forceyU);   call pin(umassdti);  call pin(fmU)
+       call pin(strintxU);   call pin(strintyU);   call pin(TbU);        call pin(taubxU);    call pin(taubyU)
+       call pin(uvel);       call pin(vvel)
+       call check(evp_b200_pin_host(c_loc(imaskT), int(size(imaskT), c_size_t) * 4_c_size_t), 'evp_b200_pin_host')
+       call check(evp_b200_pin_host(c_loc(imaskU), int(size(imaskU), c_size_t) * 4_c_size_t), 'evp_b200_pin_host')
+       pinned = .true.
+    endif
+
     flags = 0
     if (present(stress_on_host)) then
        flags = 1                               ! EVP_B200_KEEP_STRESS
@@ -313,6 +334,11 @@ contains
        call check(evp_b200_run_bgrid(p, f), 'evp_b200_run_bgrid')
     endif
   end subroutine dyn_evp_b200_run
+
+  subroutine pin(a)
+    real(kind=dbl_kind), dimension(:,:,:), intent(in), target, contiguous :: a
+    call check(evp_b200_pin_host(c_loc(a), int(size(a), c_size_t) * 8_c_size_t), 'evp_b200_pin_host')
+  end subroutine pin
 
   !---------------------------------------------------------------------
   ! `deformations` (ice_dyn_shared.F90:1756-1860; the per-block call at ice_dyn_evp.F90:920-934) for all blocks at once, from

@@ -34,6 +34,7 @@
 #ifndef EVP_B200_H
 #define EVP_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -256,6 +257,15 @@ typedef struct {
   double rhow, cosw, sinw;       /* icepack rhow; ice_dyn_shared.F90:66-70 */
 } evp_b200_finish_t;
 int evp_b200_dyn_finish(evp_b200_finish_t *f);
+
+/* ---- optional: page-locking the caller's arrays -------------------------------------------------------
+ * Fortran allocatables are pageable memory: copies from and to them are staged by the driver, run at a fraction of the PCIe
+ * rate and block the calling thread.  A host that passes the same arrays every step (CICE does: module variables of
+ * ice_dyn_evp / ice_flux / ice_state) can page-lock them once; evp_b200_run_bgrid then copies at the rate bench.py's `e2e`
+ * line reports (which is measured from pinned memory).  Thin wrappers over cudaHostRegister / cudaHostUnregister; an array
+ * that is already page-locked is accepted.  Unpin before the array is deallocated. */
+int evp_b200_pin_host(void *ptr, size_t bytes);
+int evp_b200_unpin_host(void *ptr);
 
 /* ---- optional: metric arrays for the derived-geometry kernels ---------------------------------------------
  * dxhy, dyhx, cxp, cyp, cxm, cym and DminTarea of evp_b200_grid_t are functions of HTN, HTE, dxT, dyT and deltaminEVP

@@ -7,7 +7,7 @@
 mkdir -p gpurun_out
 {
 echo "== parity of variants 40-53"
-EVP_B200_TEST_CANDIDATES=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "two_lane or dyn_finish or derived_geometry or tripole_fold_as_one" 2>&1 | tail -15
+EVP_B200_TEST_CANDIDATES=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "two_lane or dyn_finish or derived_geometry or tripole_fold_as_one or pinning" 2>&1 | tail -15
 b() { timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu "$@" 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], round(d['roofline']['frac'],4))"; }
 EVP_B200_TEST_CANDIDATES=1 timeout 600 python -m pytest tests/test_cgrid.py -m gpu -q -k programmatic 2>&1 | tail -3
 echo "== gx1 CD grid (ndte=600): four kernels per subcycle, plain vs programmatic dependent launch"

@@ -404,6 +404,28 @@ def test_tripole_fold_as_one_kernel(oracle_mod, evp_lib, monkeypatch, mode):
             assert_bitwise(run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=kernel), ref)
 
 
+@CANDIDATES
+def test_pinning_the_callers_arrays(oracle_mod, evp_lib):
+    """evp_b200_pin_host / evp_b200_unpin_host: page-locking pageable caller arrays (what Fortran allocatables are) changes the copy
+    rate, not the result; pinning twice and unpinning an array that was never pinned are accepted."""
+    c = synth.make_case("gx3", seed=18, ndte=10)
+    ref = run_oracle(oracle_mod, c)
+    f = c.copy_fields()
+    evp_lib.dyn_evp_b200_init(c.grid)
+    try:
+        arrays = [v for k, v in f.items() if isinstance(v, np.ndarray)]
+        for a in arrays:
+            evp_lib.pin_host(a)
+        evp_lib.pin_host(arrays[0])
+        evp_lib.dyn_evp_b200_run(dict(c.params, mode=abi.MODE_EXACT), f)
+        for a in arrays:
+            evp_lib.unpin_host(a)
+        evp_lib.unpin_host(arrays[0])
+    finally:
+        evp_lib.dyn_evp_b200_finalize()
+    assert_bitwise(f, ref)
+
+
 def test_interleaved_divsqrt_hits_the_fallback(oracle_mod, evp_lib, monkeypatch):
     """operands outside the fast path of the hand-scheduled division / square root (zero and denormal-range
     strain rates and numerators: ice at rest, zero forcing) must take the built-in operators and stay bit-identical."""
