@@ -251,6 +251,85 @@ __device__ __forceinline__ void momentum_at(const CDom &d, const KParams &k, int
   }
 }
 
+// momentum_at with the two square roots and the two divisions of a point (E and N) taken together through sqrt_fast / div_fast, so
+// that the four ~100-cycle chains interleave instead of running one after the other behind two separate mask branches.  Same
+// expressions, same bits (the fast paths are the built-in operators' own sequences, evp_math.cuh); a masked-off half runs on
+// harmless in-range dummies.  Selected with EVP_B200_CGRID_SHAPE=17/19 (round-2 candidate, not yet measured).
+__device__ __forceinline__ void momentum_il_at(const CDom &d, const KParams &k, int i, int j, int c, double s12c, double s12s, double s12w) {
+  const bool mE = d.maskE[c] != 0, mN = d.maskN[c] != 0;
+  if (!(mE || mN)) return;
+  double strintx = 0.0, uoE = 0.0, voE = 0.0, xE = 1.0, strinty = 0.0, uoN = 0.0, voN = 0.0, xN = 1.0;
+  if (mE) {
+    const int e = c + 1, s = c - d.ld;
+    const double dyE = d.dyE[c], dyTe = d.dyT[e], dyTc = d.dyT[c], dxUc = d.dxU[c], dxUs = d.dxU[s];
+    strintx = d.rheofactE[c] * d.earear[c] *
+              (0.5 * dyE * (d.stresspT[e] - d.stresspT[c]) +
+               d.rhalf_dyE[c] * ((dyTe * dyTe) * d.stressmT[e] - (dyTc * dyTc) * d.stressmT[c]) +
+               d.r_dxE[c] * ((dxUc * dxUc) * s12c - (dxUs * dxUs) * s12s));
+    d.strintxE[c] = strintx;
+    uoE = d.uvelE[c]; voE = d.vvelE[c];
+    const double du = d.uocnE[c] - uoE, dv = d.vocnE[c] - voE;
+    xE = du * du + dv * dv;
+  }
+  if (mN) {
+    const int n = c + d.ld, w = c - 1;
+    const double dxN = d.dxN[c], dxTn = d.dxT[n], dxTc = d.dxT[c], dyUc = d.dyU[c], dyUw = d.dyU[w];
+    strinty = d.rheofactN[c] * d.narear[c] *
+              (0.5 * dxN * (d.stresspT[n] - d.stresspT[c]) -
+               d.rhalf_dxN[c] * ((dxTn * dxTn) * d.stressmT[n] - (dxTc * dxTc) * d.stressmT[c]) +
+               d.r_dyN[c] * ((dyUc * dyUc) * s12c - (dyUw * dyUw) * s12w));
+    d.strintyN[c] = strinty;
+    uoN = d.uvelN[c]; voN = d.vvelN[c];
+    const double du = d.uocnN[c] - uoN, dv = d.vocnN[c] - voN;
+    xN = du * du + dv * dv;
+  }
+  bool okE, okN;
+  double sE = sqrt_fast(xE, okE), sN = sqrt_fast(xN, okN);
+  if (!(okE && okN)) {
+    if (!okE) sE = sqrt_ieee(xE);
+    if (!okN) sN = sqrt_ieee(xN);
+  }
+  double numE = 1.0, denE = 1.0, CbE = 0.0, numN = 1.0, denN = 1.0, CbN = 0.0;
+  if (mE) {
+    const double vrel = d.aiE[c] * k.rhow * d.cdnE[c] * sE;
+    const double taux = vrel * d.waterxE[c];
+    const double Tb = d.TbE[c];
+    CbE = (Tb == 0.0 && k.u0 > 0.0) ? Tb : Tb / (sqrt(uoE * uoE + voE * voE) + k.u0);
+    const double m = d.emassdti[c], fm = d.fmE[c];
+    const double cca = (k.brlx + k.revp) * m + vrel * k.cosw + CbE;
+    const double ccb = fm + copysign(1.0, fm) * vrel * k.sinw;
+    const double cc1 = strintx + d.forcexE[c] + taux + m * (k.brlx * uoE + k.revp * d.uvelE_init[c]);
+    numE = ccb * voE + cc1;
+    denE = cca;
+  }
+  if (mN) {
+    const double vrel = d.aiN[c] * k.rhow * d.cdnN[c] * sN;
+    const double tauy = vrel * d.wateryN[c];
+    const double Tb = d.TbN[c];
+    CbN = (Tb == 0.0 && k.u0 > 0.0) ? Tb : Tb / (sqrt(uoN * uoN + voN * voN) + k.u0);
+    const double m = d.nmassdti[c], fm = d.fmN[c];
+    const double cca = (k.brlx + k.revp) * m + vrel * k.cosw + CbN;
+    const double ccb = fm + copysign(1.0, fm) * vrel * k.sinw;
+    const double cc2 = strinty + d.forceyN[c] + tauy + m * (k.brlx * voN + k.revp * d.vvelN_init[c]);
+    numN = -ccb * uoN + cc2;
+    denN = cca;
+  }
+  bool okdE, okdN;
+  double un = div_fast(numE, denE, okdE), vn = div_fast(numN, denN, okdN);
+  if (!(okdE && okdN)) {
+    if (!okdE) un = div_ieee(numE, denE);
+    if (!okdN) vn = div_ieee(numN, denN);
+  }
+  if (mE) {
+    ring_store(d, d.uvelE, i, j, un, 3, false);
+    d.taubxE[c] = -un * CbE;
+  }
+  if (mN) {
+    ring_store(d, d.vvelN, i, j, vn, 3, false);
+    d.taubyN[c] = -vn * CbN;
+  }
+}
+
 template <bool CG>
 __device__ __forceinline__ void p4_momentum(const CDom &d, const KParams &k, int i, int j) {
   if (i > d.nx || j > d.ny) return;
@@ -373,7 +452,7 @@ __global__ void __launch_bounds__(GBX *GBY, MINB) kA_strainU_stressT(const __gri
   }
 }
 
-template <int GBY, int MINB, bool PDL = false>
+template <int GBY, int MINB, bool PDL = false, bool ILM = false>
 __global__ void __launch_bounds__(GBX *GBY, MINB) kB_stressU_momentum(const __grid_constant__ CDom d, const __grid_constant__ KParams k, int cur) {
   if (PDL) pdl_enter();
   __shared__ double sh[GBY][GBX];
@@ -400,7 +479,10 @@ __global__ void __launch_bounds__(GBX *GBY, MINB) kB_stressU_momentum(const __gr
   sh[ty][tx] = s12;
   __syncthreads();
   // phase 2: the E and N points (i,j)
-  if (tx >= 1 && ty >= 1 && i <= d.nx && j <= d.ny) momentum_at(d, k, i, j, AT(i, j), sh[ty][tx], sh[ty - 1][tx], sh[ty][tx - 1]);
+  if (tx >= 1 && ty >= 1 && i <= d.nx && j <= d.ny) {
+    if (ILM) momentum_il_at(d, k, i, j, AT(i, j), sh[ty][tx], sh[ty - 1][tx], sh[ty][tx - 1]);
+    else momentum_at(d, k, i, j, AT(i, j), sh[ty][tx], sh[ty - 1][tx], sh[ty][tx - 1]);
+  }
 }
 
 __global__ void __launch_bounds__(256) k5_pdl(const __grid_constant__ CDom d) {
@@ -448,12 +530,12 @@ static cudaError_t launch_pdl(K kern, dim3 g, dim3 b, cudaStream_t s, A... args)
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
-template <int GBY, int MINB>
+template <int GBY, int MINB, bool ILM = false>
 static cudaError_t launch_AB5_pdl(const CDom &d, const KParams &p, int cur, cudaStream_t s, int *launches) {
   dim3 b(GBX, GBY), g((d.nx + 1 + GBX - 2) / (GBX - 1), (d.ny + 1 + GBY - 2) / (GBY - 1));
   dim3 b5(32, 8), g5((d.nx + 31) / 32, (d.ny + 7) / 8);
   cudaError_t e = launch_pdl(kA_strainU_stressT<GBY, MINB, true>, g, b, s, d, p);
-  if (e == cudaSuccess) e = launch_pdl(kB_stressU_momentum<GBY, MINB, true>, g, b, s, d, p, cur);
+  if (e == cudaSuccess) e = launch_pdl(kB_stressU_momentum<GBY, MINB, true, ILM>, g, b, s, d, p, cur);
   if (e == cudaSuccess) e = launch_pdl(k5_pdl, g5, b5, s, d);
   *launches += 3;
   return e;
@@ -467,6 +549,14 @@ cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur
     case 4: launch_AB<4, 8>(d, p, cur, s); break;
     case 16: return launch_AB5_pdl<8, 4>(d, p, cur, s, launches);    // the default shape with programmatic dependent launch
     case 18: return launch_AB5_pdl<16, 2>(d, p, cur, s, launches);
+    case 17: return launch_AB5_pdl<8, 4, true>(d, p, cur, s, launches);     // 16 + interleaved sqrt / division in the momentum step
+    case 19: return launch_AB5_pdl<16, 2, true>(d, p, cur, s, launches);
+    case 5: {  // the default shape and launch form with the interleaved momentum step only
+      dim3 b(GBX, 8), g((d.nx + 1 + GBX - 2) / (GBX - 1), (d.ny + 1 + 8 - 2) / (8 - 1));
+      kA_strainU_stressT<8, 4><<<g, b, 0, s>>>(d, p);
+      kB_stressU_momentum<8, 4, false, true><<<g, b, 0, s>>>(d, p, cur);
+      break;
+    }
     default: launch_AB<8, 4>(d, p, cur, s); break;  // 62 registers, 4 CTAs per SM; the other shapes measure within 4 % (profiles/)
   }
   k5_interp<<<g5, b5, 0, s>>>(d);

@@ -14,7 +14,7 @@ echo "== gx1 CD grid (ndte=600): four kernels per subcycle, plain vs programmati
 echo "cd plain: $(timeout 300 python scripts/cdgrid_time.py 2>&1 | tail -1)"
 echo "cd pdl:   $(EVP_B200_CDGRID_PDL=1 timeout 300 python scripts/cdgrid_time.py 2>&1 | tail -1)"
 echo "== gx1 C grid (ndte=600): default vs programmatic dependent launch"
-for sh in 0 16 18; do echo "cgrid shape $sh: $(EVP_B200_CGRID_SHAPE=$sh b --grid C)"; done
+for sh in 0 5 16 17 18 19; do echo "cgrid shape $sh: $(EVP_B200_CGRID_SHAPE=$sh b --grid C)"; done
 echo "== gx1, ms per step and roofline fraction"
 echo "default: $(b)"
 for v in 40 41 42 43 44 45 46 47 48 49 50 51 52 53 54 55 56; do echo "variant $v: $(EVP_B200_FUSED_VARIANT=$v b)"; done

@@ -53,7 +53,7 @@ void common(Host &h, const evp_b200_grid_t *g, const evp_b200_cgrid_t *cg, const
 void zero(double *a, size_t n) { memset(a, 0, n * sizeof(double)); }
 }  // namespace
 
-// form 0: k1..k5; 1: kA<8,4> kB<8,4> k5 (the default); 2: <16,2>; 3: <12,3>; 4: <4,8>
+// form 0: k1..k5; 1: kA<8,4> kB<8,4> k5 (the default); 2: <16,2>; 3: <12,3>; 4: <4,8>; 5: <8,4> with momentum_il_at
 extern "C" int emu_cgrid_run(int form, const evp_b200_grid_t *g, const evp_b200_cgrid_t *cg, const evp_b200_params_t *p, evp_b200_cfields_t *f) {
   if (g->nblocks != 1) return 1;
   Host h;
@@ -97,6 +97,12 @@ extern "C" int emu_cgrid_run(int form, const evp_b200_grid_t *g, const evp_b200_
       case 2: AB(integral_constant<int, 16>{}, integral_constant<int, 2>{}); break;
       case 3: AB(integral_constant<int, 12>{}, integral_constant<int, 3>{}); break;
       case 4: AB(integral_constant<int, 4>{}, integral_constant<int, 8>{}); break;
+      case 5: {  // interleaved sqrt / division in the momentum step
+        const emu::Idx bb{GBX, 8, 1}, gg{(c.nx + 1 + GBX - 2) / (GBX - 1), (c.ny + 1 + 8 - 2) / (8 - 1), 1};
+        emu::launch(gg, bb, [&] { kA_strainU_stressT<8, 4>(c, k); });
+        emu::launch(gg, bb, [&] { kB_stressU_momentum<8, 4, false, true>(c, k, cur); });
+        break;
+      }
       default: return 1;
     }
     emu::launch(gU, b, [&] { k5_interp(c); });

@@ -144,9 +144,10 @@ def test_cgrid_five_kernel_form(oracle_mod, evp_lib, monkeypatch, cfg, kw):
 @pytest.mark.gpu
 @pytest.mark.skipif(os.environ.get("EVP_B200_TEST_CANDIDATES", "0") != "1",
                     reason="round-2 candidate: written after the round-1 GPU budget was spent; set EVP_B200_TEST_CANDIDATES=1")
-@pytest.mark.parametrize("shape", ["16", "18"])
+@pytest.mark.parametrize("shape", ["16", "18", "17", "19", "5"])
 def test_cgrid_fused_with_programmatic_dependent_launch(oracle_mod, evp_lib, monkeypatch, shape):
-    """EVP_B200_CGRID_SHAPE=16/18: kA, kB, k5 chained by programmatic dependent launch (same arithmetic, same tiles)."""
+    """EVP_B200_CGRID_SHAPE=16/18: kA, kB, k5 chained by programmatic dependent launch (same arithmetic, same tiles); 17/19: also the
+    interleaved square roots / divisions in the momentum step (momentum_il_at); 5: only that, in the default launch form."""
     monkeypatch.setenv("EVP_B200_CGRID_SHAPE", shape)
     for cfg, kw in (("tiny", dict(seed=12, ndte=7)), ("tiny", dict(seed=14, ew="cyclic", ns="cyclic", kmt="none")),
                     ("tiny", dict(seed=15, visc_method=abi.VISC_AVG_STRENGTH, block_size=(12, 10))), ("gx3", dict(ndte=31))):

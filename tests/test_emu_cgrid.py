@@ -52,7 +52,7 @@ CCASES = {
     "tiny-closed": dict(config="tiny", seed=6, ew="closed", ns="closed", ndte=3),
     "tiny-cyclic2": dict(config="tiny", seed=7, ew="cyclic", ns="cyclic", kmt="none", ndte=3),
 }
-FORMS = {0: "five-kernels", 1: "fused-32x8", 2: "fused-32x16", 3: "fused-32x12", 4: "fused-32x4"}
+FORMS = {0: "five-kernels", 1: "fused-32x8", 2: "fused-32x16", 3: "fused-32x12", 4: "fused-32x4", 5: "fused-32x8-interleaved-momentum"}
 
 
 @pytest.mark.parametrize("form", sorted(FORMS), ids=[FORMS[k] for k in sorted(FORMS)])
@@ -112,4 +112,22 @@ def test_cgrid_cta_order_does_not_matter(oracle_mod, emu, form, order):
         assert emu.emu_cgrid_run(form, C.byref(g), C.byref(cg), C.byref(p), C.byref(s)) == 0
     finally:
         emu.emu_set_cta_order(0)
+    block_equal(f, ref, abi.CFIELDS_INOUT + abi.CFIELDS_OUT, ("strengthU",))
+
+
+def test_cgrid_interleaved_momentum_fallbacks_on_the_host(oracle_mod, emu):
+    """ice and ocean at rest: the square-root operand is zero and the numerators are tiny, so the fast paths of momentum_il_at must
+    report out-of-range and hand over to the built-in operators (same bits as the plain form)."""
+    c = synth.make_ccase("tiny", seed=9, ndte=3)
+    for n in ("uvelE", "vvelE", "uvelN", "vvelN", "uvel", "vvel", "uocnE", "vocnE", "uocnN", "vocnN", "forcexE", "forceyN", "waterxE", "wateryN"):
+        c.fields[n][...] = 0.0
+    c.fields["strength"][...] *= 1e-300
+    ref = c.copy_fields()
+    oracle_mod.evp_run_cgrid(c.grid, c.cgrid, c.params, ref)
+    f = c.copy_fields()
+    g, kg = abi.make_grid(c.grid)
+    cg, kcg = abi.make_cgrid(c.cgrid, _npl(c.grid))
+    p = abi.make_params(c.params)
+    s, ks = abi.make_cfields(f, _npl(c.grid))
+    assert emu.emu_cgrid_run(5, C.byref(g), C.byref(cg), C.byref(p), C.byref(s)) == 0
     block_equal(f, ref, abi.CFIELDS_INOUT + abi.CFIELDS_OUT, ("strengthU",))
