@@ -164,27 +164,18 @@ struct Ctx {
   unsigned char *cmask[4] = {};
   cudaGraphExec_t cexec = nullptr;  // cached graph of the C-grid loop (dies with the context: it bakes pointers and wrap flags)
   evp_b200_params_t cparams{};
-  unsigned *d_cbar = nullptr;       // grid-barrier counter of the cooperative C-grid kernel
   int cgraph_launches = 0;
-  int c_shape = 0;                   // tile shape / residency of kA, kB (EVP_B200_CGRID_SHAPE)
-  bool c_fused = true;               // three kernels per subcycle (kA, kB, k5) instead of five
-  int c_max_ctas[2] = {0, 0};       // co-resident CTAs of that kernel (exact, fast); 0 = use the five-kernel form
+  bool c_fused = true;               // three kernels per subcycle (kA, kB, k5); params->kernel == SPLIT selects the five-kernel form
 
   // KERNEL_PERSISTENT
   PersistPlan pplan{};
   bool persist_ok = false;
   std::string persist_why;
   unsigned *d_progress = nullptr;
-  unsigned *d_qprogress = nullptr, *d_qcounter = nullptr;  // KERNEL_QUEUE
-  int q_ntiles = 0, q_nctas = 0;
   int num_sms = 0;
-  int fused_variant = 0;
-  bool derived_ok = false;   // evp_b200_set_metric: HTN/HTE reproduce the seven derived geometry arrays bit for bit (variants 59/63 usable)
+  bool streaming = false;    // the sub-domain's arrays exceed L2: HBM-streaming form of the fused kernel
+  bool derived_ok = false;   // evp_b200_set_metric: HTN/HTE reproduce the seven derived geometry arrays bit for bit
   int metric_mismatches = -1;
-  int p2p_variant_bits = 0;  // 0x100: the in-kernel-halo kernel reads its tile table from constant memory (EVP_B200_P2P_CONST_TILES=1)
-  int strip_m = 1;  // chunks per CTA of strip_kernel (fused_variant 30)
-  bool fused_pdl = true;
-  bool pdl_trigger = true;  // early programmatic-launch trigger in the fused kernel
 };
 static Ctx g;
 static CommState g_comm;
@@ -230,8 +221,7 @@ static int free_all() {
   for (auto &p : g.dstr) F(p);
   F(g.dmaskT); F(g.dmaskU);
   for (auto &p : g.stage) F(p);
-  F(g.d_cbar);
-  F(g.stage_mask); F(g.stage_mask2); F(g.d_ever_off); F(g.d_gsrc); F(g.d_progress); F(g.d_qprogress); F(g.d_qcounter);
+  F(g.stage_mask); F(g.stage_mask2); F(g.d_ever_off); F(g.d_gsrc); F(g.d_progress);
   F(g.d_uv_lin); F(g.d_uv_dom); F(g.d_sig_lin); F(g.d_sig_dom); F(g.d_int_lin); F(g.d_int_dom);
   g.halo.release();
   for (auto &e : g.ev_field) if (e) cudaEventDestroy(e);
@@ -239,7 +229,9 @@ static int free_all() {
   if (g.ev0) cudaEventDestroy(g.ev0);
   if (g.ev1) cudaEventDestroy(g.ev1);
   if (g.stream) cudaStreamDestroy(g.stream);
+  const int dev = g.device;
   g = Ctx{};
+  g.device = dev;  // the device chosen with evp_b200_set_device survives a failed or repeated init
   return 0;
 }
 
@@ -299,7 +291,7 @@ static int do_init(const evp_b200_grid_t *gr) {
   if (gr->nx_block < 3 || gr->ny_block < 3) return fail("evp_b200_init: block too small");
   if (gr->ns_boundary_type == EVP_B200_BNDY_TRIPOLE && gr->ew_boundary_type != EVP_B200_BNDY_CYCLIC)
     return fail("evp_b200_init: tripole requires ew_boundary_type cyclic");
-  if (g.inited) { const int dev = g.device; free_all(); g.device = dev; }
+  if (g.inited) free_all();
 
   if (g.device < 0) CK(cudaGetDevice(&g.device));
   CK(cudaSetDevice(g.device));
@@ -341,7 +333,7 @@ static int do_init(const evp_b200_grid_t *gr) {
   Dom &d = g.dom;
   d.nx = nx; d.ny = ny; d.nyd = ny + 2;
   d.ld = ((nx + 2 + 15) / 16) * 16;
-  g.ndom = (size_t)d.ld * d.nyd;
+  g.ndom = dom_cells(nx, ny);  // ghost ring + two staging rows (tripole fold, evp_halo.cu)
   if (g.ndom > 0x7fffffffULL) return fail("evp_b200_init: sub-domain exceeds 2^31 cells");
 
   // ---- index maps -------------------------------------------------------------------------------
@@ -426,51 +418,27 @@ static int do_init(const evp_b200_grid_t *gr) {
   if (g.halo.build(g_comm, gi0, gj0, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, g_allow_partial, g_err, sizeof g_err)) return 1;
   d.wrap_ew = g.halo.wrap_ew; d.wrap_ns = g.halo.wrap_ns;
   CK(cudaStreamSynchronize(g.stream));
-  if (g.p2p.setup(g_comm, g.halo, g.dshare, g.ndom, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, g_err, sizeof g_err)) return 1;
-  g.p2p_variant_bits = 0;
-  if (const char *e = getenv("EVP_B200_P2P_CONST_TILES")) {
-    const int nt = g.p2p.prm.ntx * g.p2p.prm.nty;
-    if (e[0] == '1' && g.p2p.enabled && nt <= P2P_CONST_TILES) {
-      std::vector<int> tiles(nt);
-      CK(cudaMemcpy(tiles.data(), g.p2p.d_tile_order, sizeof(int) * nt, cudaMemcpyDeviceToHost));
-      CK(exact::set_p2p_tiles(tiles.data(), nt));
-      CK(fast::set_p2p_tiles(tiles.data(), nt));
-      g.p2p_variant_bits = 0x100;
-    }
-  }
+  if (g_comm.nranks == 1 && g.halo.build_local_fold(g.nxg, g.nyg, g.ew, g.ns, exact::fold_max_entries(), g_err, sizeof g_err)) return 1;
+  if (g.p2p.setup(g_comm, g.halo, g.dshare, g.ndom, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, exact::fold_max_entries(), g_err, sizeof g_err)) return 1;
 
   // fused kernel form.  Sub-domains whose arrays fit the 126 MB L2 run latency-bound: both masks requested at once and the
-  // IEEE division / square-root expansions of the four corners interleaved (variant 23).  Larger ones stream from HBM and
-  // want every operand in flight early: speculative T-cell loads + momentum operands through cp.async (variant 19).
-  // Measured on B200 (profiles/r1_fused_variants.txt): gx1 2.27 (v23) vs 2.39 (v19) ms per step; 3600x2400 164 (v19) vs 182 (v16).
-  g.fused_variant = (g.ndom * sizeof(double) * 50 > (size_t)96 << 20) ? 19 : 23;
-  if (const char *e = getenv("EVP_B200_FUSED_VARIANT")) g.fused_variant = atoi(e);
-  if (const char *e = getenv("EVP_B200_PDL")) g.fused_pdl = (e[0] != '0');
-  if (const char *e = getenv("EVP_B200_PDL_TRIGGER")) g.pdl_trigger = (e[0] != '0');
-  CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, g.device));
-  {
-    // strip_kernel: chunks per CTA.  cost = waves of co-resident CTAs (2 per SM) x work per CTA (m chunks + prologue)
-    const int slots = 2 * g.num_sms, ntx = (nx + 30) / 31;
-    double best = 0;
-    for (int m = 1; m <= 8; ++m) {
-      const long ctas = (long)ntx * ((ny + 8 * m - 2) / (8 * m - 1));
-      const double cost = (double)((ctas + slots - 1) / slots) * (m + 0.5);
-      if (m == 1 || cost < best) { best = cost; g.strip_m = m; }
-    }
-    if (const char *e = getenv("EVP_B200_STRIP_M")) g.strip_m = std::max(1, atoi(e));
+  // IEEE division / square-root expansions of the four corners interleaved.  Larger ones stream from HBM and want every operand
+  // in flight early: speculative T-cell loads + momentum operands through cp.async, and -- once evp_b200_set_metric has verified
+  // them -- seven geometry arrays derived from two.  Measured on B200 (profiles/): gx1 2.22 vs 2.39 ms per step; 3600x2400
+  // 164 (derived) / 170 (streaming) / 182 (resident form).
+  g.streaming = (g.ndom * sizeof(double) * 50 > (size_t)96 << 20);
+  if (const char *e = getenv("EVP_B200_P2P_TIMEOUT_S")) {  // bound of the in-kernel halo waits (default 60 s)
+    const unsigned long long ns = (unsigned long long)(std::max(atof(e), 0.001) * 1e9);
+    CK(exact::set_wait_timeout(ns));
+    CK(fast::set_wait_timeout(ns));
   }
+  CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, g.device));
   // ---- persistent tiling ---------------------------------------------------------------------------
   plan_persist();
   if (g.persist_ok) {
     CK(cudaMalloc(&g.d_progress, sizeof(unsigned) * g.pplan.ntx * g.pplan.nty));
     g.pplan.progress = g.d_progress;
   }
-
-  // KERNEL_QUEUE: progress counter per 31x7 patch, two resident CTAs per SM
-  g.q_ntiles = ((nx + 30) / 31) * ((ny + 6) / 7);
-  g.q_nctas = std::min(2 * g.num_sms, g.q_ntiles);
-  CK(cudaMalloc(&g.d_qprogress, sizeof(unsigned) * g.q_ntiles));
-  CK(cudaMalloc(&g.d_qcounter, sizeof(unsigned)));
 
   CK(cudaStreamSynchronize(g.stream));
   g.inited = true;
@@ -598,15 +566,15 @@ static KParams kparams(const evp_b200_params_t *p) {
   return k;
 }
 
-// variants 59 / 63 (derived geometry) need the metric arrays of evp_b200_set_metric and its bitwise check; otherwise 19 / 23
-static int fused_variant_now() {
-  if ((g.fused_variant == 59 || g.fused_variant == 63) && !g.derived_ok) return g.fused_variant == 59 ? 19 : 23;
-  return g.fused_variant;
+// form of the fused kernel: 0 L2-resident, 1 HBM-streaming, 2 HBM-streaming with derived geometry (evp_kernels.cu)
+static int fused_form(const evp_b200_params_t *p) {
+  const bool stream = (p->kernel == EVP_B200_KERNEL_FUSED_STREAM) || (p->kernel != EVP_B200_KERNEL_FUSED_RESIDENT && g.streaming);
+  return stream ? (g.derived_ok ? 2 : 1) : 0;
 }
 
 static int choose_kernel(const evp_b200_params_t *p) {
   int kern = p->kernel;
-  if (kern == EVP_B200_KERNEL_AUTO) kern = EVP_B200_KERNEL_FUSED;  // measured faster than PERSISTENT at gx1 (profiles/)
+  if (kern == EVP_B200_KERNEL_AUTO || kern == EVP_B200_KERNEL_FUSED_STREAM || kern == EVP_B200_KERNEL_FUSED_RESIDENT) kern = EVP_B200_KERNEL_FUSED;
   return kern;
 }
 
@@ -636,32 +604,24 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
     CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -1, 0, 0, g.stream) : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -1, 0, 0, g.stream));
     ++nl;
   }
-  if (kern == EVP_B200_KERNEL_QUEUE) {
-    if (g.halo.n_dst != 0 || !g.halo.peers.empty())
-      return fail("evp_b200_subcycle: the queue kernel needs a halo that is an on-rank wrap (one rank, no tripole fold)");
-    if (p->ndte > 0) {
-      CK(cudaMemsetAsync(g.d_qprogress, 0, sizeof(unsigned) * g.q_ntiles, g.stream));
-      CK(cudaMemsetAsync(g.d_qcounter, 0, sizeof(unsigned), g.stream));
-      CK(exact ? exact::launch_queue(g.dom, k, p->ndte, g.d_qprogress, g.d_qcounter, g.q_nctas, g.stream)
-               : fast::launch_queue(g.dom, k, p->ndte, g.d_qprogress, g.d_qcounter, g.q_nctas, g.stream));
-    }
-    *cur_end = p->ndte & 1;
-    *launches = p->ndte > 0 ? 1 : 0;
-    return 0;
-  }
   // early programmatic-launch trigger: pays when the grid is more than one wave of co-resident CTAs (gx1 2.29 -> 2.21 ms), costs
   // on grids far smaller than the machine (gx3 0.56 -> 0.64 ms)
-  const int pdl_trig = (g.fused_pdl && g.pdl_trigger && (long)((g.dom.nx + 30) / 31) * ((g.dom.ny + 6) / 7) > 2L * g.num_sms) ? 2 : 0;
-  // in-kernel NVLink halo: programmatic dependent launch between the subcycle kernels (EVP_B200_P2P_PDL=0: off, 1: attribute only, 2: + early trigger)
-  int p2p_pdl = 6;  // default: attribute + early trigger (no-peer self test on one GPU: 2.74 -> 2.60 ms per step)
-  if (const char *e = getenv("EVP_B200_P2P_PDL")) p2p_pdl = (e[0] == '1') ? 4 : (e[0] == '2') ? 6 : 0;
+  const int pdl_trig = ((long)((g.dom.nx + 30) / 31) * ((g.dom.ny + 6) / 7) > 2L * g.num_sms) ? 2 : 0;
+  // in-kernel NVLink halo: PDL attribute + early trigger (no-peer self test on one GPU: 2.74 -> 2.60 ms per step)
+  const int p2p_pdl = 6;
+  const int form = fused_form(p);
   for (int ksub = 0; ksub < p->ndte; ++ksub) {
     const int last = (ksub == p->ndte - 1);
     if (p2p) {
-      CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, fused_variant_now() | g.p2p_variant_bits, g.stream)
-               : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, fused_variant_now() | g.p2p_variant_bits, g.stream));
+      CK(exact ? exact::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, form, g.stream)
+               : fast::launch_fused_p2p(g.dom, k, g.p2p.prm, cur, ksub, last | p2p_pdl, form, g.stream));
       cur ^= 1;
       ++nl;
+      if (g.p2p.fold_n > 0) {  // tripole fold: what this rank combines itself once the peers' stores of this subcycle are in
+        CK(exact::launch_fold(g.p2p.prm, g.dom.u[cur], g.dom.v[cur], g.p2p.d_fold_dst, g.p2p.d_fold_c1, g.p2p.d_fold_c2, g.p2p.d_fold_code,
+                              g.p2p.fold_n, ksub, g.stream));
+        ++nl;
+      }
       continue;
     }
     if (kern == EVP_B200_KERNEL_SPLIT) {
@@ -669,12 +629,8 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
       CK(exact ? exact::launch_stepu(g.dom, k, cur, g.stream) : fast::launch_stepu(g.dom, k, cur, g.stream));
       nl += 2;
     } else if (kern == EVP_B200_KERNEL_FUSED) {
-      if (g.fused_variant == 30)
-        CK(exact ? exact::launch_strip(g.dom, k, cur, g.strip_m, g.stream, g.fused_pdl, last)
-                 : fast::launch_strip(g.dom, k, cur, g.strip_m, g.stream, g.fused_pdl, last));
-      else
-        CK(exact ? exact::launch_fused(g.dom, k, cur, g.stream, fused_variant_now(), g.fused_pdl, last | (pdl_trig))
-                 : fast::launch_fused(g.dom, k, cur, g.stream, fused_variant_now(), g.fused_pdl, last | (pdl_trig)));
+      CK(exact ? exact::launch_fused(g.dom, k, cur, g.stream, form, true, last | pdl_trig)
+               : fast::launch_fused(g.dom, k, cur, g.stream, form, true, last | pdl_trig));
       cur ^= 1;
       nl += 1;
     } else {
@@ -770,7 +726,11 @@ static int do_subcycle(const evp_b200_params_t *p) {
                 g_comm.rank, g.last_ms, dur / cnt / 1e3, gap / cnt / 1e3, t_rel / cnt / 1e3, t_edge / cnt / 1e3, t_push / cnt / 1e3, t_flag / cnt / 1e3,
                 w[1] ? (double)w[0] / (double)w[1] : 0.0, w[2]);
     }
-    if (e) return fail("evp_b200_subcycle: a neighbour GPU did not deliver its halo in time (in-kernel NVLink hand-over timed out)");
+    if (e) {
+      CK(cudaMemset(g.p2p.d_err, 0, sizeof(int)));  // reported once; a later loop starts clean
+      return fail("evp_b200_subcycle: a neighbour GPU did not deliver its halo in time (in-kernel NVLink hand-over timed out; "
+                  "EVP_B200_P2P_TIMEOUT_S sets the bound)");
+    }
   }
   return 0;
 }
@@ -940,19 +900,8 @@ static int do_init_cgrid(const evp_b200_cgrid_t *cg) {
     g.cstage.push_back(st);
   }
   if (calloc_dom(c.uvelE_init) || calloc_dom(c.vvelN_init) || calloc_dom(c.stress12Ub)) return 1;
-  g.c_fused = true;
-  if (const char *e = getenv("EVP_B200_CGRID_FUSED")) g.c_fused = (e[0] != '0');
-  if (const char *e = getenv("EVP_B200_CGRID_SHAPE")) g.c_shape = atoi(e);
   for (int q = 0; q < 4; ++q) { CK(cudaMalloc(&g.cmask[q], g.ndom)); CK(cudaMemsetAsync(g.cmask[q], 0, g.ndom, g.stream)); }
   c.maskT = g.cmask[0]; c.maskU = g.cmask[1]; c.maskE = g.cmask[2]; c.maskN = g.cmask[3];
-  CK(cudaMalloc(&g.d_cbar, sizeof(unsigned)));
-  // the single-launch cooperative form (EVP_B200_CGRID_COOP=1) is bit-identical but measured slower than five kernels per
-  // subcycle at gx1 (26.3 vs 23.3 us per subcycle): a grid barrier costs what a kernel boundary costs here
-  g.c_max_ctas[0] = g.c_max_ctas[1] = 0;
-  if (const char *e = getenv("EVP_B200_CGRID_COOP")) if (e[0] == '1') {
-    g.c_max_ctas[0] = exact::cgrid_coop_max_ctas(g.num_sms);
-    g.c_max_ctas[1] = fast::cgrid_coop_max_ctas(g.num_sms);
-  }
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(g.stream));
   g.cinit = true;
@@ -964,8 +913,10 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
   if (!p || !f) return fail("evp_b200_run_cgrid: null argument");
   if (p->ndte < 0) return fail("evp_b200_run_cgrid: ndte < 0");
   if (p->visc_method != EVP_B200_VISC_AVG_ZETA && p->visc_method != EVP_B200_VISC_AVG_STRENGTH) return fail("evp_b200_run_cgrid: unknown visc_method %d", p->visc_method);
+  if (p->mode != EVP_B200_MODE_EXACT && p->mode != EVP_B200_MODE_FAST) return fail("evp_b200_run_cgrid: unknown mode %d", p->mode);
   CK(cudaSetDevice(g.device));
   CDom &c = g.cdom;
+  g.c_fused = (p->kernel != EVP_B200_KERNEL_SPLIT);  // SPLIT: the five-kernel first form, cut where the reference has a halo point
   const size_t bblk = g.nblk_elems * sizeof(double), bdom = g.ndom * sizeof(double);
   // host pointer, device array, how it moves: 'i' in, 'r' inout ring, 's' inout T cells the loop owns (N/E ghost incl.),
   // 'n' inout interior, 'z' out: the reference zero-fills the whole block, writes interiors, halo-updates;
@@ -1023,17 +974,9 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t le = cudaSuccess;
-    const int max_ctas = g.c_max_ctas[exact ? 0 : 1];
-    if (max_ctas > 0 && p->ndte > 0) {
-      // one cooperative launch for the whole loop, grid barriers where the five-kernel form has kernel boundaries
-      le = cudaMemsetAsync(g.d_cbar, 0, sizeof(unsigned), g.stream);
-      if (le == cudaSuccess)
-        le = exact ? exact::launch_cgrid_coop(c, k, p->ndte, g.d_cbar, max_ctas, g.stream)
-                   : fast::launch_cgrid_coop(c, k, p->ndte, g.d_cbar, max_ctas, g.stream);
-      nl = 1;
-    } else if (g.c_fused) {
+    if (g.c_fused) {
       for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub)
-        le = exact ? exact::launch_cgrid_subcycle_fused(c, k, ksub & 1, g.c_shape, g.stream, &nl) : fast::launch_cgrid_subcycle_fused(c, k, ksub & 1, g.c_shape, g.stream, &nl);
+        le = exact ? exact::launch_cgrid_subcycle_fused(c, k, ksub & 1, g.stream, &nl) : fast::launch_cgrid_subcycle_fused(c, k, ksub & 1, g.stream, &nl);
     } else {
       for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub)
         le = exact ? exact::launch_cgrid_subcycle(c, k, g.stream, &nl) : fast::launch_cgrid_subcycle(c, k, g.stream, &nl);
@@ -1062,7 +1005,7 @@ static int do_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) {
     else if (t.kind == 'n' || t.kind == 'y')
       unpack_f64<<<grid_blocks(g.n_int), 256, 0, g.stream>>>(g.cstage[q], t.dv, g.d_int_lin, g.d_int_dom, g.n_int);
     else {
-      const bool in_b = (t.dv == c.stress12U) && g.c_fused && g.c_max_ctas[exact ? 0 : 1] == 0 && (p->ndte & 1);
+      const bool in_b = (t.dv == c.stress12U) && g.c_fused && (p->ndte & 1);
       unpack_f64<<<grid_blocks(g.n_uv), 256, 0, g.stream>>>(g.cstage[q], in_b ? c.stress12Ub : t.dv, g.d_uv_lin, g.d_uv_dom, g.n_uv);
     }
     CK(cudaMemcpyAsync((void *)t.h, g.cstage[q], bblk, cudaMemcpyDeviceToHost, g.stream));
@@ -1150,13 +1093,8 @@ static int do_run_cdgrid(const evp_b200_params_t *p, evp_b200_cdfields_t *f) {
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t le = cudaSuccess;
-    const char *epdl = getenv("EVP_B200_CDGRID_PDL");
-    const bool cd_pdl = epdl && epdl[0] == '1';   // round-2 candidate: the four kernels chained by programmatic dependent launch
-    for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub) {
-      if (cd_pdl) le = exact ? exact::launch_cdgrid_subcycle_pdl(c, k, g.stream, &nl) : fast::launch_cdgrid_subcycle_pdl(c, k, g.stream, &nl);
-      else
+    for (int ksub = 0; ksub < p->ndte && le == cudaSuccess; ++ksub)
       le = exact ? exact::launch_cdgrid_subcycle(c, k, g.stream, &nl) : fast::launch_cdgrid_subcycle(c, k, g.stream, &nl);
-    }
     cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
     if (le != cudaSuccess || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail("evp_b200_run_cdgrid: capture failed: %s", cudaGetErrorString(le != cudaSuccess ? le : ce)); }
     CK(cudaGraphInstantiate(&g.cdexec, graph, 0));
@@ -1255,7 +1193,13 @@ int evp_b200_init_cgrid(const evp_b200_cgrid_t *cg) { return do_init_cgrid(cg); 
 int evp_b200_run_cgrid(const evp_b200_params_t *p, evp_b200_cfields_t *f) { return do_run_cgrid(p, f); }
 int evp_b200_run_cdgrid(const evp_b200_params_t *p, evp_b200_cdfields_t *f) { return do_run_cdgrid(p, f); }
 
-int evp_b200_upload(const evp_b200_fields_t *f) { return do_upload(f, false); }
+int evp_b200_upload(const evp_b200_fields_t *f) {
+  if (do_upload(f, false)) return 1;
+  // "keeps no host pointer past the return of a call": the copies out of the caller's arrays are complete when this returns
+  // (run_bgrid keeps them asynchronous internally; its download synchronises)
+  CK(cudaStreamSynchronize(g.xfer));
+  return 0;
+}
 int evp_b200_subcycle(const evp_b200_params_t *p) { return do_subcycle(p); }
 int evp_b200_download(evp_b200_fields_t *f) { return do_download(f, 3); }
 
@@ -1281,7 +1225,16 @@ int evp_b200_halo_plan(int32_t nranks, const int32_t *rects, int32_t rank, int32
   if (!rects || !n || (!out && cap > 0) || nranks < 1 || rank < 0 || rank >= nranks) return fail("evp_b200_halo_plan: bad arguments");
   return halo_plan_host(nranks, rects, rank, nxg, nyg, ew, ns, n, out, cap);
 }
+int evp_b200_p2p_plan(int32_t nranks, const int32_t *rects, int32_t rank, int32_t nxg, int32_t nyg, int32_t ew, int32_t ns,
+                      int32_t *n_push, int32_t *push_out, int32_t *n_fold, int32_t *fold_out, int32_t cap) {
+  if (!rects || !n_push || !n_fold || (cap > 0 && (!push_out || !fold_out)) || nranks < 1 || rank < 0 || rank >= nranks)
+    return fail("evp_b200_p2p_plan: bad arguments");
+  const int rc = p2p_plan_host(nranks, rects, rank, nxg, nyg, ew, ns, n_push, push_out, n_fold, fold_out, cap);
+  if (rc) return fail("evp_b200_p2p_plan: the staging rows of a rank overflow");
+  return 0;
+}
 int32_t evp_b200_dom_pitch(int32_t nx) { return dom_pitch(nx); }
+int64_t evp_b200_dom_cells(int32_t nx, int32_t ny) { return (int64_t)dom_cells(nx, ny); }
 
 int evp_b200_last_loop_ms(double *ms) { if (!ms) return fail("null"); *ms = g.last_ms; return 0; }
 int evp_b200_last_launches(int64_t *n) { if (!n) return fail("null"); *n = g.last_launches; return 0; }

@@ -254,7 +254,7 @@ __device__ __forceinline__ void momentum_at(const CDom &d, const KParams &k, int
 // momentum_at with the two square roots and the two divisions of a point (E and N) taken together through sqrt_fast / div_fast, so
 // that the four ~100-cycle chains interleave instead of running one after the other behind two separate mask branches.  Same
 // expressions, same bits (the fast paths are the built-in operators' own sequences, evp_math.cuh); a masked-off half runs on
-// harmless in-range dummies.  Selected with EVP_B200_CGRID_SHAPE=17/19 (round-2 candidate, not yet measured).
+// harmless in-range dummies.  The form kB uses (measured 12.46 vs 12.52 ms per step at gx1).
 __device__ __forceinline__ void momentum_il_at(const CDom &d, const KParams &k, int i, int j, int c, double s12c, double s12s, double s12w) {
   const bool mE = d.maskE[c] != 0, mN = d.maskN[c] != 0;
   if (!(mE || mN)) return;
@@ -407,20 +407,8 @@ __device__ __forceinline__ bool alias_point(const CDom &d, int &i, int &j) {
   return i >= 1 && i <= d.nx && j >= 1 && j <= d.ny;
 }
 
-// programmatic dependent launch (EVP_B200_CGRID_SHAPE >= 16; round-2 candidate, not yet measured): the kernel lets its
-// successor be scheduled as soon as all of its own CTAs have started, and itself waits for its predecessor's completion and
-// memory flush before it touches anything -- the kernel-boundary gap of the three launches per subcycle overlaps with the
-// predecessor's tail, as on the B grid
-__device__ __forceinline__ void pdl_enter() {
-#ifndef EVP_HOST_EMU
-  cudaTriggerProgrammaticLaunchCompletion();
-  cudaGridDependencySynchronize();
-#endif
-}
-
-template <int GBY, int MINB, bool PDL = false>
+template <int GBY, int MINB>
 __global__ void __launch_bounds__(GBX *GBY, MINB) kA_strainU_stressT(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
-  if (PDL) pdl_enter();
   __shared__ double sh[GBY][GBX];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i = blockIdx.x * (GBX - 1) + tx, j = blockIdx.y * (GBY - 1) + ty;  // ti = 1 + bx*(GBX-1), point ti-1+tx
@@ -452,9 +440,8 @@ __global__ void __launch_bounds__(GBX *GBY, MINB) kA_strainU_stressT(const __gri
   }
 }
 
-template <int GBY, int MINB, bool PDL = false, bool ILM = false>
+template <int GBY, int MINB, bool ILM>
 __global__ void __launch_bounds__(GBX *GBY, MINB) kB_stressU_momentum(const __grid_constant__ CDom d, const __grid_constant__ KParams k, int cur) {
-  if (PDL) pdl_enter();
   __shared__ double sh[GBY][GBX];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i = blockIdx.x * (GBX - 1) + tx, j = blockIdx.y * (GBY - 1) + ty;
@@ -485,11 +472,6 @@ __global__ void __launch_bounds__(GBX *GBY, MINB) kB_stressU_momentum(const __gr
   }
 }
 
-__global__ void __launch_bounds__(256) k5_pdl(const __grid_constant__ CDom d) {
-  pdl_enter();
-  p5_interp<false>(d, 1 + blockIdx.x * blockDim.x + threadIdx.x, 1 + blockIdx.y * blockDim.y + threadIdx.y);
-}
-
 // quotients of static geometry that the reference re-divides every subcycle (ice_dyn_evp.F90:2230-2240, 2398-2408,
 // ice_dyn_shared.F90:2296): an IEEE division of the same operands gives the same bits whenever it is done, so they are
 // divided once here
@@ -513,52 +495,14 @@ cudaError_t launch_cgrid_static(const CDom &d, double *rhalf_dyE, double *r_dxE,
 }
 #endif  // EVP_HOST_EMU
 
-#ifndef EVP_HOST_EMU  // launchers (and the cooperative kernel): not part of the host emulation (tests/emu_cgrid.cpp)
-template <int GBY, int MINB>
-static void launch_AB(const CDom &d, const KParams &p, int cur, cudaStream_t s) {
-  dim3 b(GBX, GBY), g((d.nx + 1 + GBX - 2) / (GBX - 1), (d.ny + 1 + GBY - 2) / (GBY - 1));
-  kA_strainU_stressT<GBY, MINB><<<g, b, 0, s>>>(d, p);
-  kB_stressU_momentum<GBY, MINB><<<g, b, 0, s>>>(d, p, cur);
-}
-template <class K, class... A>
-static cudaError_t launch_pdl(K kern, dim3 g, dim3 b, cudaStream_t s, A... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = 0; cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, args...);
-}
-template <int GBY, int MINB, bool ILM = false>
-static cudaError_t launch_AB5_pdl(const CDom &d, const KParams &p, int cur, cudaStream_t s, int *launches) {
-  dim3 b(GBX, GBY), g((d.nx + 1 + GBX - 2) / (GBX - 1), (d.ny + 1 + GBY - 2) / (GBY - 1));
+#ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_cgrid.cpp)
+// 32 x 8 tiles, 4 CTAs per SM (62 registers); 32x{4,12,16} tiles measured within 4 % of it, chaining the three launches by
+// programmatic dependent launch and a single cooperative launch with grid barriers both measured slower (profiles/)
+cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur, cudaStream_t s, int *launches) {
+  dim3 b(GBX, 8), g((d.nx + 1 + GBX - 2) / (GBX - 1), (d.ny + 1 + 8 - 2) / (8 - 1));
   dim3 b5(32, 8), g5((d.nx + 31) / 32, (d.ny + 7) / 8);
-  cudaError_t e = launch_pdl(kA_strainU_stressT<GBY, MINB, true>, g, b, s, d, p);
-  if (e == cudaSuccess) e = launch_pdl(kB_stressU_momentum<GBY, MINB, true, ILM>, g, b, s, d, p, cur);
-  if (e == cudaSuccess) e = launch_pdl(k5_pdl, g5, b5, s, d);
-  *launches += 3;
-  return e;
-}
-cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur, int shape, cudaStream_t s, int *launches) {
-  dim3 b5(32, 8), g5((d.nx + 31) / 32, (d.ny + 7) / 8);
-  switch (shape) {
-    case 1: launch_AB<8, 5>(d, p, cur, s); break;
-    case 2: launch_AB<16, 2>(d, p, cur, s); break;
-    case 3: launch_AB<12, 3>(d, p, cur, s); break;
-    case 4: launch_AB<4, 8>(d, p, cur, s); break;
-    case 16: return launch_AB5_pdl<8, 4>(d, p, cur, s, launches);    // the default shape with programmatic dependent launch
-    case 18: return launch_AB5_pdl<16, 2>(d, p, cur, s, launches);
-    case 17: return launch_AB5_pdl<8, 4, true>(d, p, cur, s, launches);     // 16 + interleaved sqrt / division in the momentum step
-    case 19: return launch_AB5_pdl<16, 2, true>(d, p, cur, s, launches);
-    case 5: {  // the default shape and launch form with the interleaved momentum step only
-      dim3 b(GBX, 8), g((d.nx + 1 + GBX - 2) / (GBX - 1), (d.ny + 1 + 8 - 2) / (8 - 1));
-      kA_strainU_stressT<8, 4><<<g, b, 0, s>>>(d, p);
-      kB_stressU_momentum<8, 4, false, true><<<g, b, 0, s>>>(d, p, cur);
-      break;
-    }
-    default: launch_AB<8, 4>(d, p, cur, s); break;  // 62 registers, 4 CTAs per SM; the other shapes measure within 4 % (profiles/)
-  }
+  kA_strainU_stressT<8, 4><<<g, b, 0, s>>>(d, p);
+  kB_stressU_momentum<8, 4, true><<<g, b, 0, s>>>(d, p, cur);
   k5_interp<<<g5, b5, 0, s>>>(d);
   *launches += 3;
   return cudaGetLastError();
@@ -584,9 +528,7 @@ __device__ __forceinline__ double t2u_S(const CDom &d, const double *__restrict_
   return (mc * src[c] * wc + me * src[e] * we + mn * src[n] * wn + mne * src[ne] * wne) / wtmp;
 }
 
-template <bool PDL = false>
 __global__ void __launch_bounds__(256) kcd1_stress_T(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
-  if (PDL) pdl_enter();
   CELL_IJ(d.wrap_ew ? d.nx : d.nx + 1, d.wrap_ns ? d.ny : d.ny + 1);
   const int c = AT(i, j);
   if (!d.maskT[c]) return;
@@ -610,9 +552,7 @@ __global__ void __launch_bounds__(256) kcd1_stress_T(const __grid_constant__ CDo
   ring_store(d, d.stress12T, i, j, s12, 3, false);
 }
 
-template <bool PDL = false>
 __global__ void __launch_bounds__(256) kcd2_stress_U(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
-  if (PDL) pdl_enter();
   CELL_IJ(d.nx, d.ny);
   const int c = AT(i, j);
   double zetax2U = 0.0, etax2U = 0.0, strengthU = 0.0;
@@ -672,9 +612,7 @@ __device__ __forceinline__ void stepuv_cd_at(const KParams &k, double uold, doub
   tauby = -vn * Cb;
 }
 
-template <bool PDL = false>
 __global__ void __launch_bounds__(256) kcd3_momentum(const __grid_constant__ CDom d, const __grid_constant__ KParams k) {
-  if (PDL) pdl_enter();
   CELL_IJ(d.nx, d.ny);
   const int c = AT(i, j), e = c + 1, n = c + d.ld, s = c - d.ld, w = c - 1;
   if (d.maskE[c]) {
@@ -717,9 +655,7 @@ __global__ void __launch_bounds__(256) kcd3_momentum(const __grid_constant__ CDo
   }
 }
 
-template <bool PDL = false>
 __global__ void __launch_bounds__(256) kcd4_interp(const __grid_constant__ CDom d) {
-  if (PDL) pdl_enter();
   CELL_IJ(d.nx, d.ny);
   const int c = AT(i, j), e = c + 1, n = c + d.ld;
   double num, den;
@@ -734,76 +670,16 @@ __global__ void __launch_bounds__(256) kcd4_interp(const __grid_constant__ CDom 
 #ifndef EVP_HOST_EMU  // launchers (and the cooperative kernel): not part of the host emulation (tests/emu_cgrid.cpp)
 cudaError_t launch_cdgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches) {
   dim3 b(32, 8), gU((d.nx + 31) / 32, (d.ny + 7) / 8), gT((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8);
-  kcd1_stress_T<false><<<gT, b, 0, s>>>(d, p);
-  kcd2_stress_U<false><<<gU, b, 0, s>>>(d, p);
-  kcd3_momentum<false><<<gU, b, 0, s>>>(d, p);
-  kcd4_interp<false><<<gU, b, 0, s>>>(d);
+  kcd1_stress_T<<<gT, b, 0, s>>>(d, p);
+  kcd2_stress_U<<<gU, b, 0, s>>>(d, p);
+  kcd3_momentum<<<gU, b, 0, s>>>(d, p);
+  kcd4_interp<<<gU, b, 0, s>>>(d);
   *launches += 4;
   return cudaGetLastError();
 }
-// the same four kernels chained by programmatic dependent launch (EVP_B200_CDGRID_PDL=1; round-2 candidate)
-cudaError_t launch_cdgrid_subcycle_pdl(const CDom &d, const KParams &p, cudaStream_t s, int *launches) {
-  dim3 b(32, 8), gU((d.nx + 31) / 32, (d.ny + 7) / 8), gT((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8);
-  cudaError_t e = launch_pdl(kcd1_stress_T<true>, gT, b, s, d, p);
-  if (e == cudaSuccess) e = launch_pdl(kcd2_stress_U<true>, gU, b, s, d, p);
-  if (e == cudaSuccess) e = launch_pdl(kcd3_momentum<true>, gU, b, s, d, p);
-  if (e == cudaSuccess) e = launch_pdl(kcd4_interp<true>, gU, b, s, d);
-  *launches += 4;
-  return e;
-}
 #endif  // EVP_HOST_EMU
 
-#ifndef EVP_HOST_EMU  // launchers (and the cooperative kernel): not part of the host emulation (tests/emu_cgrid.cpp)
-// ---- all ndte subcycles in ONE cooperative launch -----------------------------------------------------------
-// 148 x 2 co-resident CTAs of 32 x 16 threads; every thread keeps the same cell for the whole loop (larger sub-domains:
-// a fixed list of tiles per CTA).  The five kernel boundaries of a subcycle become five grid barriers (one
-// red.release + ld.acquire spin on a monotonic counter, ~1 us instead of a ~2.5 us kernel boundary plus tail).
-constexpr int CBX = 32, CBY = 16;
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target, unsigned nctas) {
-  __syncthreads();
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
-    target += nctas;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-    unsigned v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-    } while (v < target);
-  }
-  __syncthreads();
-}
-__global__ void __launch_bounds__(CBX *CBY, 2) cgrid_coop_kernel(const __grid_constant__ CDom d, const __grid_constant__ KParams k,
-                                                                  int ndte, int ntx, int ntiles, unsigned *bar) {
-  unsigned target = 0;
-  const unsigned nctas = gridDim.x;
-  for (int ksub = 0; ksub < ndte; ++ksub) {
-#define CG_PHASE(CALL)                                                        \
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {                      \
-    const int i = 1 + (t % ntx) * CBX + threadIdx.x, j = 1 + (t / ntx) * CBY + threadIdx.y; \
-    CALL;                                                                     \
-  }                                                                           \
-  grid_barrier(bar, target, nctas)
-    CG_PHASE(p1_strain_U<true>(d, k, i, j));
-    CG_PHASE(p2_stress_T<true>(d, k, i, j));
-    CG_PHASE(p3_stress_U<true>(d, k, i, j));
-    CG_PHASE(p4_momentum<true>(d, k, i, j));
-    CG_PHASE(p5_interp<true>(d, i, j));
-#undef CG_PHASE
-  }
-}
-
-cudaError_t launch_cgrid_coop(const CDom &d, const KParams &p, int ndte, unsigned *bar, int max_ctas, cudaStream_t s) {
-  int ntx = (d.nx + 1 + CBX - 1) / CBX, nty = (d.ny + 1 + CBY - 1) / CBY;
-  int ntiles = ntx * nty;
-  int nctas = ntiles < max_ctas ? ntiles : max_ctas;
-  void *args[] = {(void *)&d, (void *)&p, (void *)&ndte, (void *)&ntx, (void *)&ntiles, (void *)&bar};
-  return cudaLaunchCooperativeKernel((const void *)cgrid_coop_kernel, dim3(nctas), dim3(CBX, CBY), args, 0, s);
-}
-int cgrid_coop_max_ctas(int num_sms) {
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cgrid_coop_kernel, CBX * CBY, 0) != cudaSuccess) return 0;
-  return per_sm * num_sms;
-}
-
+#ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_cgrid.cpp)
 cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches) {
   dim3 b(32, 8), gU((d.nx + 31) / 32, (d.ny + 7) / 8), gT((d.nx + 1 + 31) / 32, (d.ny + 1 + 7) / 8);
   k1_strain_U<<<gU, b, 0, s>>>(d, p);

@@ -19,7 +19,6 @@
 #include <cstring>
 
 #include "evp_b200.h"
-#include "evp_halo_local.cuh"
 
 namespace evp {
 
@@ -104,6 +103,8 @@ __global__ void halo_apply(double *__restrict__ U, double *__restrict__ V, const
 
 struct Rect { int gi0, gj0, nx, ny; };
 static inline int ld_of(int nx) { return ((nx + 2 + 15) / 16) * 16; }
+// rows of a dom array: ny + ghost ring + two staging rows for raw values that cross a tripole fold (P2PState::setup)
+size_t dom_cells(int nx, int ny) { return (size_t)ld_of(nx) * (size_t)(ny + 4); }
 
 struct Entry { int dst; int r1, c1, r2, c2; signed char code; };  // sources as (rank, dom index)
 
@@ -283,39 +284,16 @@ int HaloPlan::build(CommState &cs, int gi0, int gj0, int nx, int ny, int ld, int
   HCK(cudaMalloc(&d_recvbuf, sizeof(double) * 2 * std::max(n_recv, 1)));
   const char *eg = getenv("EVP_B200_GRAPH");
   allow_graph = !(eg && eg[0] == '0');
-  // opt-in: one kernel instead of pack + apply when every source is on this rank
-  local_fused = false;
-  if (const char *ef = getenv("EVP_B200_HALO_FUSED")) {
-    if (ef[0] != '0' && cs.nranks == 1 && n_dst > 0 && n_dst <= HALO_LOCAL_MAX) {
-      std::vector<int> h_c1, h_c2;
-      bool all_local = true;
-      for (const Entry &e : mine) {
-        all_local = all_local && e.r1 == me && (e.r2 < 0 || e.r2 == me);
-        h_c1.push_back(e.c1);
-        h_c2.push_back(e.r2 < 0 ? e.c1 : e.c2);
-      }
-      if (all_local) {
-        if (up(d_c1, h_c1, err, nerr) || up(d_c2, h_c2, err, nerr)) return 1;
-        local_fused = true;
-      }
-      local_pdl = (ef[0] == '2') ? 1 : 0;   // 2: also chained by programmatic dependent launch
-    }
-  }
   return 0;
 }
 
 int HaloPlan::exchange(CommState &cs, double *U, double *V, cudaStream_t s, int *launches, char *err, size_t nerr) {
   *launches = 0;
   if (n_dst == 0 && n_pack == 0) return 0;
-  if (local_fused) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(1); cfg.blockDim = dim3(HALO_LOCAL_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = local_pdl ? 1 : 0;
-    HCK(cudaLaunchKernelEx(&cfg, halo_local_kernel, U, V, (const int *)d_dst, (const int *)d_c1, (const int *)d_c2,
-                           (const signed char *)d_code, n_dst, local_pdl));
+  if (fold_n > 0 && !no_fold_kernel) {
+    // one rank: every source is local and the whole update is the fold list -- one kernel instead of pack + apply
+    static const P2PParams nopeers{};
+    HCK(exact::launch_fold(nopeers, U, V, d_fold_dst, d_fold_c1, d_fold_c2, d_fold_code, fold_n, 0, s));
     ++*launches;
     return 0;
   }
@@ -341,31 +319,118 @@ int HaloPlan::exchange(CommState &cs, double *U, double *V, cudaStream_t s, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// P2P: map the neighbours' velocity arrays, build the push table and the edge-first tile order
+// P2P: map the neighbours' velocity arrays, build the push table, the local fold list and the edge-first tile order
 // ------------------------------------------------------------------------------------------------
+// How one rank's plan entries (enumerate) are served without a staged exchange:
+//   copy / negate of ANOTHER rank's cell   -> that rank's subcycle kernel stores the value (negated across the fold) straight into
+//                                             the destination cell over NVLink (push table);
+//   0.5*(a-b) forms (tripole top row)      -> every source that lives on another rank is pushed RAW into a staging slot of the
+//                                             destination rank (rows ny+2, ny+3 of its own u/v arrays, slots numbered in the
+//                                             entry order every rank can reproduce); the destination rank combines them itself
+//                                             (fold list, p2p_fold_kernel) once the peers' epoch flags are up;
+//   anything whose sources are all local   -> fold list as well (ghost row below the fold fed from the rank's own row ny-1,
+//                                             pole points, symmetrised pairs held by one rank).
+struct FoldEntry { int dst, c1, c2; signed char code; };
+struct PushEntry { int src, rank, dst, neg; };
+
+// fold list of rank q and (optionally) what rank `me` has to push to q; returns false when q's staging rows overflow
+static bool split_entries(const std::vector<Rect> &R, int q, int me, int nxg, int nyg, int ew, int ns, std::vector<FoldEntry> *fold,
+                          std::vector<PushEntry> *push_from_me, std::vector<int> *remote_ranks) {
+  std::vector<Entry> es;
+  enumerate(R, q, nxg, nyg, ew, ns, es);
+  const int ldq = ld_of(R[q].nx), stg_base = (R[q].ny + 2) * ldq, stg_cap = 2 * ldq;
+  int slot = 0;
+  for (const Entry &e : es) {
+    const bool avg = (e.code == OP_AVGM || e.code == OP_AVGH);
+    if (!avg) {
+      if (e.r1 == q) {
+        if (fold) fold->push_back(FoldEntry{e.dst, e.c1, e.c1, e.code});
+      } else {
+        if (remote_ranks) remote_ranks->push_back(e.r1);
+        if (push_from_me && e.r1 == me) push_from_me->push_back(PushEntry{e.c1, q, e.dst, e.code == OP_NEG ? 1 : 0});
+      }
+      continue;
+    }
+    int s[2] = {e.c1, e.c2};
+    const int rr[2] = {e.r1, e.r2};
+    for (int w = 0; w < 2; ++w) {
+      if (rr[w] == q) continue;
+      if (slot >= stg_cap) return false;
+      const int idx = stg_base + slot++;
+      if (remote_ranks) remote_ranks->push_back(rr[w]);
+      if (push_from_me && rr[w] == me) push_from_me->push_back(PushEntry{s[w], q, idx, 0});
+      s[w] = idx;
+    }
+    if (fold) fold->push_back(FoldEntry{e.dst, s[0], s[1], e.code});
+  }
+  return true;
+}
+
+// host-only: the push list and the fold list of `rank` (what P2PState::setup builds), for the CPU tests of the multi-rank logic
+int p2p_plan_host(int nranks, const int *rects, int rank, int nxg, int nyg, int ew, int ns, int *n_push, int *push_out, int *n_fold,
+                  int *fold_out, int cap) {
+  std::vector<Rect> R(nranks);
+  for (int q = 0; q < nranks; ++q) R[q] = Rect{rects[4 * q], rects[4 * q + 1], rects[4 * q + 2], rects[4 * q + 3]};
+  std::vector<PushEntry> pushes;
+  std::vector<FoldEntry> fold;
+  for (int q = 0; q < nranks; ++q) {
+    const bool ok = (q == rank) ? split_entries(R, q, rank, nxg, nyg, ew, ns, &fold, nullptr, nullptr)
+                                : split_entries(R, q, rank, nxg, nyg, ew, ns, nullptr, &pushes, nullptr);
+    if (!ok) return 2;
+  }
+  *n_push = (int)pushes.size();
+  *n_fold = (int)fold.size();
+  for (int k = 0; k < (int)pushes.size() && k < cap; ++k) {
+    int *o = push_out + 4 * k;
+    o[0] = pushes[k].src; o[1] = pushes[k].rank; o[2] = pushes[k].dst; o[3] = pushes[k].neg;
+  }
+  for (int k = 0; k < (int)fold.size() && k < cap; ++k) {
+    int *o = fold_out + 4 * k;
+    o[0] = fold[k].dst; o[1] = fold[k].c1; o[2] = fold[k].c2; o[3] = fold[k].code;
+  }
+  return 0;
+}
+
+static int upload_fold(const std::vector<FoldEntry> &f, int *&d_dst, int *&d_c1, int *&d_c2, signed char *&d_code, char *err, size_t nerr) {
+  std::vector<int> a, b, c;
+  std::vector<signed char> k;
+  for (const FoldEntry &e : f) { a.push_back(e.dst); b.push_back(e.c1); c.push_back(e.c2); k.push_back(e.code); }
+  if (up(d_dst, a, err, nerr) || up(d_c1, b, err, nerr) || up(d_c2, c, err, nerr) || up(d_code, k, err, nerr)) return 1;
+  return 0;
+}
+
+// one rank: every source of the fold is local, the whole exchange is the fold list (p2p_fold_kernel without peers)
+int HaloPlan::build_local_fold(int nxg, int nyg, int ew, int ns, int max_entries, char *err, size_t nerr) {
+  fold_n = 0;
+  if (rects.size() != 4 || n_dst == 0) return 0;
+  std::vector<Rect> R(1, Rect{rects[0], rects[1], rects[2], rects[3]});
+  std::vector<FoldEntry> fold;
+  std::vector<int> remote;
+  if (!split_entries(R, 0, 0, nxg, nyg, ew, ns, &fold, nullptr, &remote) || !remote.empty()) return 0;
+  if ((int)fold.size() > max_entries || fold.size() != (size_t)n_dst) return 0;
+  if (upload_fold(fold, d_fold_dst, d_fold_c1, d_fold_c2, d_fold_code, err, nerr)) return 1;
+  fold_n = (int)fold.size();
+  return 0;
+}
+
 int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t ndom, int nx, int ny, int ld, int nxg, int nyg,
-                    int ew, int ns, char *err, size_t nerr) {
+                    int ew, int ns, int max_fold, char *err, size_t nerr) {
   release();
   enabled = false;
   const bool selftest = cs.nranks < 2 && getenv("EVP_B200_P2P_SELFTEST");
   if (cs.nranks < 2 && !selftest) { why = "single rank"; return 0; }
+  const int ntx = (nx + 30) / 31, nty = (ny + 6) / 7;
   if (selftest) {
     // one rank, no peers: runs the edge-first tile order, the edge-CTA counter and the hand-shake kernels
     // without any NVLink traffic (timing / parity of the kernel structure itself)
-    const int ntx = (nx + 30) / 31, nty = (ny + 6) / 7;
-    std::vector<int> order, start(2 * nx + 2 * (ny - 2) + 1, 0), none;
+    std::vector<int> order, start(3 * nx + 2 * (ny - 2) + 1, 0), none;
     int n_edge = 0;
-    const bool rev = getenv("EVP_B200_P2P_SELFTEST")[0] == '2';
     for (int pass = 0; pass < 2; ++pass)
       for (int t = 0; t < ntx * nty; ++t) {
         const int bx = t % ntx, by = t / ntx;
         const bool edge = (bx == 0 || bx == ntx - 1 || by == 0 || by == nty - 1);
         if (edge == (pass == 0)) { order.push_back(t); n_edge += edge; }
       }
-    const char stm = getenv("EVP_B200_P2P_SELFTEST")[0];
-    if (rev) { order.clear(); for (int t = 0; t < ntx * nty; ++t) order.push_back(t); n_edge = 0; }
-    if (stm == '3') n_edge = 0;                                                     // edge-first order, no counter
-    if (stm == '4') { order.clear(); for (int t = 0; t < ntx * nty; ++t) order.push_back(t); }  // natural order, counter on the first n_edge tiles
     if (ntx > 0xffff || nty > 0x7fff) HFAIL("p2p: tile grid too large");
     for (int &t : order) t = ((t / ntx) << 16) | (t % ntx);  // packed (tby, tbx): see fused_kernel
     if (up(d_tile_order, order, err, nerr) || up(d_push_start, start, err, nerr) || up(d_push_peer, none, err, nerr) || up(d_push_dst, none, err, nerr)) return 1;
@@ -384,34 +449,33 @@ int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t 
   const int me = cs.rank;
   std::vector<Rect> R(cs.nranks);
   for (int q = 0; q < cs.nranks; ++q) R[q] = Rect{plan.rects[4 * q], plan.rects[4 * q + 1], plan.rects[4 * q + 2], plan.rects[4 * q + 3]};
+  const bool tripole = (ns == EVP_B200_BNDY_TRIPOLE);
+  const int fold_row = (tripole && R[me].gj0 + ny - 1 == nyg) ? ny - 1 : 0;
 
-  // push table: every ghost cell of another rank whose source is one of my interior cells
-  struct Push { int src, rank, dst; };
-  std::vector<Push> pushes;
+  // what I push to whom, what I combine myself, who pushes to me
+  std::vector<PushEntry> pushes;
+  std::vector<FoldEntry> fold;
   std::vector<int> peer_ranks;
-  bool fold = plan.has_fold;
   auto slot_of = [&](int rk) {
     for (size_t q = 0; q < peer_ranks.size(); ++q) if (peer_ranks[q] == rk) return (int)q;
     peer_ranks.push_back(rk);
     return (int)peer_ranks.size() - 1;
   };
   for (int q = 0; q < cs.nranks; ++q) {
-    if (q == me) continue;
-    std::vector<Entry> theirs;
-    enumerate(R, q, nxg, nyg, ew, ns, theirs);
-    for (const Entry &e : theirs) {
-      if (e.code != OP_COPY || e.r1 == q) fold = true;
-      if (e.r1 == me) { pushes.push_back(Push{e.c1, q, e.dst}); slot_of(q); }
-    }
+    std::vector<int> remote;
+    const bool ok = (q == me) ? split_entries(R, q, me, nxg, nyg, ew, ns, &fold, nullptr, &remote)
+                              : split_entries(R, q, me, nxg, nyg, ew, ns, nullptr, &pushes, nullptr);
+    if (!ok) { want = 0; why = "fold staging rows too small"; }
+    for (int rk : remote) slot_of(rk);   // ranks that push to me
   }
-  {
-    std::vector<Entry> mine;
-    enumerate(R, me, nxg, nyg, ew, ns, mine);
-    for (const Entry &e : mine) if (e.r1 != me && e.r1 >= 0) slot_of(e.r1);
-  }
-  if (fold) { want = 0; why = "tripole fold / on-rank copies need the staged exchange"; }
+  for (const PushEntry &p : pushes) slot_of(p.rank);
   if ((int)peer_ranks.size() > P2P_MAXPEER) { want = 0; why = "too many peers"; }
+  if ((int)fold.size() > max_fold) { want = 0; why = "too many fold entries for one CTA"; }
   if (nx < 2 || ny < 3) { want = 0; why = "sub-domain too small"; }
+  for (const PushEntry &p : pushes) {
+    const int i = p.src % ld, j = p.src / ld;
+    if (!(i == 1 || i == nx || j == 1 || j == ny || (fold_row && j == fold_row))) { want = 0; why = "a push source is not on the sub-domain edge"; }
+  }
 
   // exchange IPC handles of the shared segment and try to map every peer
   cudaIpcMemHandle_t myh;
@@ -440,7 +504,7 @@ int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t 
       }
       peer_base[q] = (double *)ptr;
       const Rect &A = R[peer_ranks[q]];
-      peer_ndom[q] = (size_t)ld_of(A.nx) * (A.ny + 2);
+      peer_ndom[q] = dom_cells(A.nx, A.ny);
     }
   }
   // every rank must take the same path
@@ -453,51 +517,50 @@ int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t 
   HCK(cudaMemcpy(&all, dflag, sizeof(int), cudaMemcpyDeviceToHost));
   HCK(cudaFree(dflag));
   if (!all) {
-    if (want) why = "a peer rank could not map the shared segment";
+    if (want) why = "a peer rank could not use the in-kernel halo";
     for (int q = 0; q < npeers; ++q) if (peer_base[q]) { cudaIpcCloseMemHandle(peer_base[q]); peer_base[q] = nullptr; }
     npeers = 0;
     return 0;
   }
 
-  // CSR over the edge index of the source cell
-  const int nedge = 2 * nx + 2 * (ny - 2);
+  // CSR over the edge index of the source cell (device twin: edge_index in evp_kernels.cu)
+  const int nedge = 3 * nx + 2 * (ny - 2);
   std::vector<int> start(nedge + 1, 0), ppeer(pushes.size()), pdst(pushes.size());
   auto eidx = [&](int c) {
     const int i = c % ld, j = c / ld;
     if (j == 1) return i - 1;
     if (j == ny) return nx + i - 1;
+    if (fold_row && j == fold_row) return 2 * nx + 2 * (ny - 2) + (i - 1);
     if (i == 1) return 2 * nx + (j - 2);
     return 2 * nx + (ny - 2) + (j - 2);
   };
-  for (const Push &p : pushes) {
-    const int i = p.src % ld, j = p.src / ld;
-    if (!(i == 1 || i == nx || j == 1 || j == ny)) HFAIL("p2p: a push source is not on the sub-domain edge");
-    start[eidx(p.src) + 1]++;
-  }
+  for (const PushEntry &p : pushes) start[eidx(p.src) + 1]++;
   for (int e = 0; e < nedge; ++e) start[e + 1] += start[e];
   {
     std::vector<int> fill(start.begin(), start.end() - 1);
-    for (const Push &p : pushes) {
+    for (const PushEntry &p : pushes) {
       const int k = fill[eidx(p.src)]++;
-      ppeer[k] = slot_of(p.rank);
+      ppeer[k] = slot_of(p.rank) | (p.neg ? 0x100 : 0);
       pdst[k] = p.dst;
     }
   }
-  // tile order of the 32x8 fused kernel, edge tiles first
-  const int ntx = (nx + 30) / 31, nty = (ny + 6) / 7;
+  // tile order of the 32x8 fused kernel, edge tiles first; below a tripole fold the tile row that holds row ny-1 counts as edge
+  const int fold_tby = fold_row ? (fold_row - 1) / 7 : -1;
   std::vector<int> order;
   int n_edge = 0;
   for (int pass = 0; pass < 2; ++pass)
     for (int t = 0; t < ntx * nty; ++t) {
       const int bx = t % ntx, by = t / ntx;
-      const bool edge = (bx == 0 || bx == ntx - 1 || by == 0 || by == nty - 1);
+      const bool edge = (bx == 0 || bx == ntx - 1 || by == 0 || by == nty - 1 || by == fold_tby);
       if (edge == (pass == 0)) { order.push_back(t); n_edge += edge; }
     }
-  if (ntx > 0xffff || nty > 0x7fff) { why = "tile grid too large"; }
+  if (ntx > 0xffff || nty > 0x7fff) HFAIL("p2p: tile grid too large");
   for (int &t : order) t = ((t / ntx) << 16) | (t % ntx);  // packed (tby, tbx): see fused_kernel
   if (up(d_tile_order, order, err, nerr) || up(d_push_start, start, err, nerr) || up(d_push_peer, ppeer, err, nerr) ||
       up(d_push_dst, pdst, err, nerr))
     return 1;
+  if (upload_fold(fold, d_fold_dst, d_fold_c1, d_fold_c2, d_fold_code, err, nerr)) return 1;
+  fold_n = (int)fold.size();
   HCK(cudaMalloc(&d_done, sizeof(unsigned long long)));
   HCK(cudaMalloc(&d_epoch, sizeof(unsigned long long)));
   HCK(cudaMalloc(&d_err, sizeof(int)));
@@ -512,7 +575,8 @@ int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t 
   prm = P2PParams{};
   prm.enabled = 1; prm.npeers = npeers; prm.n_edge_tiles = n_edge; prm.ntx = ntx; prm.nty = nty;
   prm.tile_order = d_tile_order;
-  prm.n_push = (int)pushes.size(); prm.push_start = d_push_start; prm.push_peer = d_push_peer; prm.push_dst = d_push_dst;
+  prm.n_push = (int)pushes.size(); prm.fold_row = fold_row;
+  prm.push_start = d_push_start; prm.push_peer = d_push_peer; prm.push_dst = d_push_dst;
   prm.my_flags = (const unsigned long long *)(dshare + 4 * ndom);
   for (int q = 0; q < npeers; ++q) {
     prm.peer_rank[q] = peer_ranks[q];
@@ -525,8 +589,9 @@ int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t 
   NCK(ncclAllReduce(d_err, d_err, 1, ncclInt32, ncclMax, cs.comm, 0));
   HCK(cudaStreamSynchronize(0));
   enabled = true;
-  char b[160];
-  snprintf(b, sizeof b, "in-kernel NVLink stores to %d peer(s), %zu pushed cells, %d edge tiles of %d", npeers, pushes.size(), n_edge, ntx * nty);
+  char b[200];
+  snprintf(b, sizeof b, "in-kernel NVLink stores to %d peer(s), %zu pushed cells, %d edge tiles of %d, %d fold entries", npeers, pushes.size(),
+           n_edge, ntx * nty, fold_n);
   why = b;
   return 0;
 }
@@ -548,6 +613,8 @@ void P2PState::release() {
   }
   auto F = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
   F(d_tile_order); F(d_push_start); F(d_push_peer); F(d_push_dst); F(d_done); F(d_epoch); F(d_err); F(d_dbg);
+  F(d_fold_dst); F(d_fold_c1); F(d_fold_c2); F(d_fold_code);
+  fold_n = 0;
   enabled = false;
   npeers = 0;
   prm = P2PParams{};
@@ -561,8 +628,9 @@ std::string HaloPlan::describe() const {
 
 void HaloPlan::release() {
   auto F = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
-  F(d_pack_idx); F(d_dst); F(d_s1); F(d_s2); F(d_code); F(d_packbuf); F(d_recvbuf); F(d_c1); F(d_c2);
-  local_fused = false;
+  F(d_pack_idx); F(d_dst); F(d_s1); F(d_s2); F(d_code); F(d_packbuf); F(d_recvbuf);
+  F(d_fold_dst); F(d_fold_c1); F(d_fold_c2); F(d_fold_code);
+  fold_n = 0;
   peers.clear();
   n_dst = n_pack = n_loc = n_recv = 0;
   wrap_ew = wrap_ns = 0;

@@ -22,7 +22,10 @@ int comm_init(CommState &cs, int rank, int nranks, const void *id128, char *err,
 void comm_destroy(CommState &cs);
 
 int halo_plan_host(int nranks, const int *rects, int rank, int nxg, int nyg, int ew, int ns, int *n, int *out, int cap);
+int p2p_plan_host(int nranks, const int *rects, int rank, int nxg, int nyg, int ew, int ns, int *n_push, int *push_out, int *n_fold,
+                  int *fold_out, int cap);
 int dom_pitch(int nx);
+size_t dom_cells(int nx, int ny);  // pitch * (ny + 2 ghost rows + 2 staging rows)
 
 // What one exchange does, for every destination cell e of this rank (ghost ring, plus the top interior
 // row on a tripole grid):  dst = op(code, s1, s2), where s1/s2 were staged from this rank's interior
@@ -38,10 +41,12 @@ struct HaloPlan {
   int *d_dst = nullptr, *d_s1 = nullptr, *d_s2 = nullptr;  // [n_dst] dom index to write, slot refs
   signed char *d_code = nullptr;             // [n_dst]
   double *d_packbuf = nullptr, *d_recvbuf = nullptr;       // 2 doubles (u,v) per slot
-  // one rank, every source local (tripole fold on one GPU): pack + apply as one kernel (evp_halo_local.cuh, EVP_B200_HALO_FUSED=1)
-  bool local_fused = false;
-  int local_pdl = 0;
-  int *d_c1 = nullptr, *d_c2 = nullptr;                    // [n_dst] dom index of the sources
+  // one rank, every source local (tripole fold on one GPU): the whole update as one kernel (p2p_fold_kernel, evp_kernels.cu)
+  int fold_n = 0;
+  bool no_fold_kernel = false;                             // EVP_B200_P2P=0: keep the staged pack + apply form
+  int *d_fold_dst = nullptr, *d_fold_c1 = nullptr, *d_fold_c2 = nullptr;
+  signed char *d_fold_code = nullptr;
+  int build_local_fold(int nxg, int nyg, int ew, int ns, int max_entries, char *err, size_t nerr);
 
   struct Peer { int rank, send_off, nsend, recv_off, nrecv; };
   std::vector<Peer> peers;
@@ -68,13 +73,17 @@ struct P2PState {
   double *peer_base[P2P_MAXPEER] = {};
   size_t peer_ndom[P2P_MAXPEER] = {};
   int *d_tile_order = nullptr, *d_push_start = nullptr, *d_push_peer = nullptr, *d_push_dst = nullptr;
+  // what this rank combines itself once its peers' stores have arrived (tripole fold): p2p_fold_kernel after every subcycle kernel
+  int fold_n = 0;
+  int *d_fold_dst = nullptr, *d_fold_c1 = nullptr, *d_fold_c2 = nullptr;
+  signed char *d_fold_code = nullptr;
   unsigned long long *d_done = nullptr, *d_epoch = nullptr;
   int *d_err = nullptr;
   unsigned long long *d_dbg = nullptr;
 
   // dshare = [u0 | u1 | v0 | v1] (ndom doubles each) followed by 64 u64 flags, one cudaMalloc
   int setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t ndom, int nx, int ny, int ld, int nxg, int nyg,
-            int ew, int ns, char *err, size_t nerr);
+            int ew, int ns, int max_fold, char *err, size_t nerr);
   void set_parity(int swapped_);
   void release();
 };

@@ -70,17 +70,17 @@ struct KParams {
 // In-kernel NVLink halo (see evp_halo.cu, fused_kernel): edge CTAs store new edge velocities straight into the
 // neighbour GPUs' ghost cells (CUDA-IPC mapped peer memory) and hand over with per-peer epoch flags.
 #define P2P_MAXPEER 16
-#define P2P_CONST_TILES 8192  // capacity of the constant-memory copy of tile_order (evp_kernels.cu)
 struct P2PParams {
   int enabled;
   int npeers;
   int n_edge_tiles;              // tiles touching the sub-domain boundary; they are scheduled first
   int ntx, nty;                  // tile grid of the fused kernel
   const int *tile_order;         // [ntx*nty] tile ids, edge tiles first
-  int n_push;                    // ghost cells of neighbour ranks that are fed from this rank
-  const int *push_start;         // CSR over the edge index of a boundary U point (see edge_index)
-  const int *push_peer;          // peer slot
-  const int *push_dst;           // cell index inside that peer's sub-domain array
+  int n_push;                    // cells of other ranks (ghost cells, fold staging slots) that are fed from this rank
+  int fold_row;                  // 0, or the interior row (ny-1) below a tripole fold whose U points are push sources too
+  const int *push_start;         // CSR over the edge index of a push source (see edge_index)
+  const int *push_peer;          // peer slot in bits 0-7, bit 8: the value arrives negated (it crosses the tripole fold)
+  const int *push_dst;           // cell index inside that peer's sub-domain array (staging rows ny+2, ny+3 included)
   double *peer_u[2][P2P_MAXPEER], *peer_v[2][P2P_MAXPEER];
   unsigned long long *peer_flag[P2P_MAXPEER];  // the peer's flags[my rank]
   const unsigned long long *my_flags;          // my flags[], indexed by peer rank
@@ -113,21 +113,18 @@ struct PersistPlan {
   cudaError_t launch_stepu(const Dom &d, const KParams &p, int cur, cudaStream_t s);                \
   cudaError_t launch_deform(const Dom &d, int cur, const double *dxU, const double *dyU, const double *tarear, double *divu, double *shear, double *vort, double *rdg_conv, double *rdg_shear, double e_factor, cudaStream_t s); \
   cudaError_t launch_finish(const Dom &d, int cur, double *strocnx, double *strocny, double rhow, double cosw, double sinw, cudaStream_t s); \
-  cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl, int last); \
-  cudaError_t launch_strip(const Dom &d, const KParams &p, int cur, int m, cudaStream_t s, bool pdl, int last); \
-  cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, int last, int variant, cudaStream_t s); \
-  cudaError_t set_p2p_tiles(const int *host_tiles, int n); \
+  cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int form, bool pdl, int last); \
+  cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, int last, int form, cudaStream_t s); \
+  cudaError_t launch_fold(const P2PParams &pp, double *U, double *V, const int *dst, const int *c1, const int *c2, const signed char *code, int n, int ksub, cudaStream_t s); \
+  int fold_max_entries(); \
+  cudaError_t set_wait_timeout(unsigned long long ns); \
   cudaError_t set_metric(const double *HTN, const double *HTE, double deltamin); \
   cudaError_t launch_metric_verify(const Dom &d, const double *HTN, const double *HTE, double deltamin, int skip_e, int skip_n, int *mismatches, cudaStream_t s); \
   cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s); \
-  cudaError_t launch_queue(const Dom &d, const KParams &p, int ndte, unsigned *progress, unsigned *counter, int nctas, cudaStream_t s); \
   cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \
   cudaError_t launch_cgrid_static(const CDom &d, double *rhalf_dyE, double *r_dxE, double *rhalf_dxN, double *r_dyN, double *uareaavgr, cudaStream_t s); \
-  cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur, int shape, cudaStream_t s, int *launches);  \
+  cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur, cudaStream_t s, int *launches);  \
   cudaError_t launch_cdgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \
-  cudaError_t launch_cdgrid_subcycle_pdl(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \
-  cudaError_t launch_cgrid_coop(const CDom &d, const KParams &p, int ndte, unsigned *bar, int max_ctas, cudaStream_t s); \
-  int cgrid_coop_max_ctas(int num_sms); \
   }
 EVP_DECLARE_LAUNCHERS(exact)
 EVP_DECLARE_LAUNCHERS(fast)

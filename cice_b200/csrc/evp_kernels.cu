@@ -6,11 +6,14 @@
 //   stress_kernel / stepu_kernel : the reference's two sweeps, one thread per cell, `str` through
 //                                  global memory (the first correct path; KERNEL_SPLIT)
 //   fused_kernel                 : one launch per subcycle; a CTA relaxes the stresses of a
-//                                  BX x BY patch of T cells, hands the 8 `str` terms to the momentum
-//                                  step through shared memory and advances the (BX-1) x (BY-1) U
-//                                  points the patch closes.  Reads only the `cur` copies of the
-//                                  carried state and writes only the other copy, so overlapping
-//                                  patches never race (KERNEL_FUSED)
+//                                  32 x 8 patch of T cells, hands the 8 `str` terms to the momentum
+//                                  step through shared memory and advances the 31 x 7 U points the
+//                                  patch closes.  Reads only the `cur` copies of the carried state and
+//                                  writes only the other copy, so overlapping patches never race
+//                                  (KERNEL_FUSED).  Three forms: L2-resident, HBM-streaming, HBM-streaming
+//                                  with derived geometry; each also with the in-kernel NVLink halo (P2P)
+//   p2p_fold_kernel              : what the halo update does beyond copying a neighbour's value (tripole
+//                                  fold, ice_boundary.F90:1550-1724), after the peers' stores have arrived
 // Neither is GEMM shaped; both are bandwidth/latency bound fp64 stencils -> no tensor cores.
 #include "evp_math.cuh"
 #include "evp_dom.cuh"
@@ -189,37 +192,29 @@ cudaError_t launch_stepu(const Dom &d, const KParams &p, int cur, cudaStream_t s
 // ---------------------------------------------------------------------------------------------
 // FBX x FBY threads relax an FBX x FBY patch of T cells and advance the (FBX-1) x (FBY-1) U points it closes.
 // MINB = CTAs per SM the register allocation is bounded for.
-// edge index of a boundary U point (i==1 | i==nx | j==1 | j==ny), the row index of the push CSR
-__device__ __forceinline__ int edge_index(const Dom &d, int i, int j) {
+
+// row index of the push CSR for a U point whose value some other sub-domain (or this one's own ghost ring, across a tripole
+// fold) needs: the boundary points (i==1 | i==nx | j==1 | j==ny) and, on ranks below a tripole fold, row `fold_row` = ny-1
+// (the ghost row ny+1 is fed from it, ice_boundary.F90:1689-1722).  Host twin: P2PState::setup (evp_halo.cu).
+__device__ __forceinline__ bool is_push_point(const Dom &d, int fold_row, int i, int j) {
+  return i == 1 || i == d.nx || j == 1 || j == d.ny || j == fold_row;
+}
+__device__ __forceinline__ int edge_index(const Dom &d, int fold_row, int i, int j) {
   if (j == 1) return i - 1;
   if (j == d.ny) return d.nx + i - 1;
+  if (j == fold_row) return 2 * d.nx + 2 * (d.ny - 2) + (i - 1);
   if (i == 1) return 2 * d.nx + (j - 2);
   return 2 * d.nx + (d.ny - 2) + (j - 2);
 }
 
-// The speculative body of fused_kernel (SPEC = true, the default): same arithmetic, same ownership rules, but
-//  * every operand of the T cell is requested before the ice masks are known (addresses are always inside the dom);
-//  * static operands (geometry, strength, masks) and the momentum operands are requested BEFORE the programmatic
-//    grid dependency is resolved, i.e. while the previous subcycle's kernel is still draining;
-//  * the 12 momentum operands go global -> shared with cp.async and are picked up after the CTA barrier.
-// the in-kernel-halo form's edge-first tile table in CONSTANT memory (SPEC bit 4, EVP_B200_P2P_CONST_TILES=1): the table
-// lookup is the first thing a CTA does and every address depends on it; from global memory that is one more serialised L2
-// round trip per CTA, from the constant cache it is a few cycles.  Round-2 candidate, not yet measured.
-__constant__ int c_tile_order[P2P_CONST_TILES];
-#ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
-cudaError_t set_p2p_tiles(const int *host_tiles, int n) {
-  if (n > P2P_CONST_TILES) return cudaErrorInvalidValue;
-  return cudaMemcpyToSymbol(c_tile_order, host_tiles, sizeof(int) * (size_t)n);
-}
-#endif  // EVP_HOST_EMU
-
-// Derived geometry (SPEC bit 5, EVP_B200_FUSED_VARIANT=59/63 after evp_b200_set_metric; round-2 candidate, not yet measured).
+// Derived geometry (SPEC bit 5, after evp_b200_set_metric).
 // Seven of the ten static T-cell arrays are functions of the two metric arrays HTN, HTE and of dxT, dyT
 // (ice_dyn_shared.F90:384-388, 401-441): on sub-domains that stream from HBM, reading HTN/HTE (their i-1 / j-1 neighbours come
 // from the same cache lines) instead of dxhy, dyhx, cxp, cyp, cxm, cym, DminTarea moves 360 instead of 400 B per cell and
-// subcycle -- the algorithmic figure of SURVEY 8d.  The expressions are the reference's, operation for operation; whether they
-// reproduce the host's arrays bit for bit on every cell the loop can touch is CHECKED on the device when the metric arrays are
-// handed over (metric_verify_kernel); if a single cell differs the library keeps reading the arrays.
+// subcycle -- the algorithmic figure of SURVEY 8d (measured on B200: 3600x2400 164.4 vs 170.4 ms per step).  The expressions are
+// the reference's, operation for operation; whether they reproduce the host's arrays bit for bit on every cell the loop can touch
+// is CHECKED on the device when the metric arrays are handed over (metric_verify_kernel); if a single cell differs the library
+// keeps reading the arrays.
 __constant__ const double *c_HTN, *c_HTE;
 __constant__ double c_deltamin;
 __device__ __forceinline__ void derive_geometry(double hn, double hs, double he, double hw, double dxT, double dyT, double deltamin,
@@ -264,14 +259,21 @@ cudaError_t launch_metric_verify(const Dom &d, const double *HTN, const double *
 }
 #endif  // EVP_HOST_EMU
 
+// The forms of fused_kernel (SPEC bits).  Same arithmetic, same ownership rules in all of them:
+//  bit 0 (SPT)  every operand of the T cell is requested before the ice masks are known (addresses are always inside the dom),
+//               static operands even BEFORE the programmatic grid dependency is resolved, i.e. while the previous subcycle's
+//               kernel is still draining;
+//  bit 1 (CPU)  the 12 momentum operands go global -> shared with cp.async and are picked up after the CTA barrier;
+//  bit 2 (IL)   the IEEE divisions / square roots of the four corners as interleaved fast-path sequences (evp_math.cuh);
+//  bit 5 (DER)  derived geometry (above).
+// FORM_RESIDENT = IL: sub-domains whose arrays fit the 126 MB L2 are latency bound (gx1: 2.22 ms per step against 2.39 for SPT|CPU);
+// FORM_STREAM = SPT|CPU: larger ones stream from HBM and want every load in flight early (3600x2400: 164 vs 182 ms per step).
+constexpr int FORM_RESIDENT = 4, FORM_STREAM = 3, FORM_STREAM_DER = 3 | 32;
 constexpr int NUOP = 12;
-// SPEC bit 0: speculative T-cell operand loads; bit 1: momentum operands through cp.async
 template <int FBX, int FBY, bool P2P, int SPEC>
-__device__ __forceinline__ void fused_spec_body(const Dom &d, const KParams &k, int cur, const P2PParams &pp, int last, int i, int j,
-                                                bool inT, int c, double (&sstr)[8][FBY][FBX]) {
-  constexpr bool SPT = (SPEC & 1) != 0, CPU = (SPEC & 2) != 0, IL = (SPEC & 4) != 0;  // bit 2: interleaved div/sqrt
-  constexpr bool PAIR = (SPEC & 8) != 0;                                                 // bit 3: pairwise named barriers
-  constexpr bool DER = (SPEC & 32) != 0;                                                 // bit 5: derived geometry (see above)
+__device__ __forceinline__ void fused_body(const Dom &d, const KParams &k, int cur, const P2PParams &pp, int last, int i, int j,
+                                           bool inT, int c, double (&sstr)[8][FBY][FBX]) {
+  constexpr bool SPT = (SPEC & 1) != 0, CPU = (SPEC & 2) != 0, IL = (SPEC & 4) != 0, DER = (SPEC & 32) != 0;
   __shared__ double sU[CPU ? NUOP : 1][FBY * FBX];
   const int tx = threadIdx.x, ty = threadIdx.y, t = ty * FBX + tx;
   const int nxt = cur ^ 1;
@@ -319,6 +321,7 @@ __device__ __forceinline__ void fused_spec_body(const Dom &d, const KParams &k, 
     }
     if (inT && mT) {
       stress_point<IL>(ucc, vcc, uee, vee, use_, vse, une, vne, dxT, dyT, dxhy, dyhx, cxp, cyp, cxm, cym, dmin, strength, k, sg, str);
+      // each T cell is stored by exactly one CTA: the one that holds it off its E/N overlap edge
       const bool own = (tx < FBX - 1 || i == d.nx + 1) && (ty < FBY - 1 || j == d.ny + 1);
       if (own) store_sigma(d, nxt, c, sg);
     }
@@ -341,15 +344,7 @@ __device__ __forceinline__ void fused_spec_body(const Dom &d, const KParams &k, 
 #pragma unroll
   for (int q = 0; q < 8; ++q) sstr[q][ty][tx] = str[q];
   if (CPU) cp_async_wait_all();  // own copies only: each thread reads back what it requested itself
-  if (PAIR && FBX == 32) {
-    // U row ty needs the str terms of T rows ty and ty+1 only, and a row is one warp: instead of a CTA-wide barrier, warp
-    // ty+1 arrives on named barrier ty+1 once its terms are in shared memory and warp ty waits there (64 threads each,
-    // every barrier used once per launch), so a warp is held up by one neighbour, not by the slowest of eight
-    if (ty >= 1) bar_arrive64(ty);
-    if (ty < FBY - 1) bar_sync64(ty + 1);
-  } else {
-    __syncthreads();
-  }
+  __syncthreads();
   if (uspot && mU) {
     double uo[NUOP];
     if (CPU) {
@@ -366,24 +361,30 @@ __device__ __forceinline__ void fused_spec_body(const Dom &d, const KParams &k, 
                                sstr[5][ty + 1][tx], sstr[6][ty][tx + 1], sstr[7][ty + 1][tx + 1], k);
     store_uv(d, d.u[nxt], d.v[nxt], i, j, o.u, o.v);
     if (last) {
+      // the loop overwrites these every subcycle and nothing reads them in between (ice_dyn_shared.F90:948-965);
+      // only the last subcycle's values survive, as in the reference's own 1-D solver (calc_diag_1d, ice_dyn_core1d.F90:607)
       d.strintx[c] = o.strintx;
       d.strinty[c] = o.strinty;
       d.taubx[c] = o.taubx;
       d.tauby[c] = o.tauby;
     }
-    if (P2P && (i == 1 || i == d.nx || j == 1 || j == d.ny)) {
-      const int e = edge_index(d, i, j);
+    if (P2P && is_push_point(d, pp.fold_row, i, j)) {
+      // this point is a ghost cell (or a fold source) of up to three other sub-domains: store it there over NVLink right away,
+      // so the traffic is spread over the kernel and long acknowledged when the hand-over fence below is issued.  Bit 8 of the
+      // peer word: the value crosses the tripole fold and arrives negated (ice_boundary.F90:1689-1722, field_type_vector).
+      const int e = edge_index(d, pp.fold_row, i, j);
       for (int q = pp.push_start[e]; q < pp.push_start[e + 1]; ++q) {
-        const int pr = pp.push_peer[q];
+        const int pw = pp.push_peer[q], pr = pw & 0xff;
         const int dst = pp.push_dst[q];
-        pp.peer_u[nxt][pr][dst] = o.u;
-        pp.peer_v[nxt][pr][dst] = o.v;
+        const bool neg = (pw & 0x100) != 0;
+        pp.peer_u[nxt][pr][dst] = neg ? -o.u : o.u;
+        pp.peer_v[nxt][pr][dst] = neg ? -o.v : o.v;
       }
     }
   }
 }
 
-template <int FBX, int FBY, int MINB, bool HOIST, bool P2P = false, int SPEC = 0>
+template <int FBX, int FBY, int MINB, bool P2P, int SPEC>
 __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_constant__ Dom d,
                                                                 const __grid_constant__ KParams k, int cur,
                                                                 const __grid_constant__ P2PParams pp, int ksub, int flags) {
@@ -402,14 +403,13 @@ __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_cons
     const int b = blockIdx.x;
     // edge tiles first; the table holds (tby << 16 | tbx) so that no runtime integer division (~80 instructions and a MUFU
     // round trip at the top of every CTA) is needed to decode it
-    const int tile = (SPEC & 16) ? c_tile_order[b] : pp.tile_order[b];
+    const int tile = pp.tile_order[b];
     tbx = tile & 0xffff;
     tby = tile >> 16;
     edge_tile = b < pp.n_edge_tiles;
   }
   const int i = 1 + tbx * (FBX - 1) + tx;  // T cell of this thread
   const int j = 1 + tby * (FBY - 1) + ty;
-  const int nxt = cur ^ 1;
   unsigned long long base = 0;
   unsigned long long *tl = (P2P && pp.dbg) ? pp.dbg + 8 + 8 * (size_t)ksub : nullptr;  // per-kernel timeline (ns)
   if (tl && tx == 0 && ty == 0) atomicMin(tl + 0, gtime());
@@ -430,64 +430,7 @@ __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_cons
   }
   const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
   const int c = at(d, inT ? i : 1, inT ? j : 1);
-  if (SPEC) {
-    fused_spec_body<FBX, FBY, P2P, SPEC>(d, k, cur, pp, last, i, j, inT, c, sstr);
-  } else {
-#if EVP_USE_PDL
-  // programmatic dependent launch: everything above overlaps the previous subcycle's tail
-  cudaGridDependencySynchronize();
-#endif
-
-  // the momentum step's operands are requested before the stress arithmetic so that their L2 latency
-  // hides under it (the U point of this thread is its own T cell index)
-  const bool doU = tx < FBX - 1 && ty < FBY - 1 && i <= d.nx && j <= d.ny && d.maskU[c];
-  double uin[16];
-  if (HOIST && doU) {
-    load_uin(d, k, cur, c, uin);
-  }
-
-  double str[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (inT && d.maskT[c]) {
-    Sigma sg;
-    stress_at(d, k, cur, i, j, sg, str);
-    // each T cell is stored by exactly one CTA: the one that holds it off its E/N overlap edge
-    const bool own = (tx < FBX - 1 || i == d.nx + 1) && (ty < FBY - 1 || j == d.ny + 1);
-    if (own) store_sigma(d, nxt, c, sg);
-  }
-#pragma unroll
-  for (int q = 0; q < 8; ++q) sstr[q][ty][tx] = str[q];
-  __syncthreads();
-
-  if (doU) {
-    if (!HOIST) {
-      load_uin(d, k, cur, c, uin);
-    }
-    const UOut o = stepu_point(uin[0], uin[1], uin[2], uin[3], uin[4], uin[5], uin[6], uin[7], uin[8], uin[9], uin[10], uin[11],
-                               uin[12], uin[13], uin[14], uin[15], sstr[0][ty][tx], sstr[1][ty][tx + 1],
-                               sstr[2][ty + 1][tx], sstr[3][ty + 1][tx + 1], sstr[4][ty][tx], sstr[5][ty + 1][tx],
-                               sstr[6][ty][tx + 1], sstr[7][ty + 1][tx + 1], k);
-    store_uv(d, d.u[nxt], d.v[nxt], i, j, o.u, o.v);
-    if (last) {
-      // the loop overwrites these every subcycle and nothing reads them in between (ice_dyn_shared.F90:948-965);
-      // only the last subcycle's values survive, as in the reference's own 1-D solver (calc_diag_1d, ice_dyn_core1d.F90:607)
-      d.strintx[c] = o.strintx;
-      d.strinty[c] = o.strinty;
-      d.taubx[c] = o.taubx;
-      d.tauby[c] = o.tauby;
-    }
-    if (P2P && (i == 1 || i == d.nx || j == 1 || j == d.ny)) {
-      // this point is a ghost cell of up to three neighbour GPUs: store it there over NVLink right away, so the
-      // traffic is spread over the kernel and long acknowledged when the hand-over fence below is issued
-      const int e = edge_index(d, i, j);
-      for (int q = pp.push_start[e]; q < pp.push_start[e + 1]; ++q) {
-        const int pr = pp.push_peer[q];
-        const int dst = pp.push_dst[q];
-        pp.peer_u[nxt][pr][dst] = o.u;
-        pp.peer_v[nxt][pr][dst] = o.v;
-      }
-    }
-  }
-  }  // !SPEC
+  fused_body<FBX, FBY, P2P, SPEC>(d, k, cur, pp, last, i, j, inT, c, sstr);
   if (P2P && edge_tile) {
     // Hand-over.  Every edge CTA counts itself done with gpu-scope ordering (a system-scope fence per CTA costs
     // ~3 us per kernel).  The CTA that arrives last issues the ONE system-scope fence -- cumulative over the NVLink
@@ -510,88 +453,6 @@ __global__ void __launch_bounds__(FBX *FBY, MINB) fused_kernel(const __grid_cons
   if (tl && tx == 0 && ty == 0) atomicMax(tl + 1, gtime());
 }
 
-// ---------------------------------------------------------------------------------------------
-// KERNEL_FUSED, strip form (the default without in-kernel NVLink halo).
-// A CTA of 32 x 8 threads walks up a strip of 31 U columns in `m` chunks of 8 T rows.  The `str` terms of a chunk's
-// top T row stay in shared memory (row 0) for the next chunk, so inside a strip no T row is relaxed twice: a CTA
-// relaxes 8m T rows and advances 8m-1 U rows (fused_kernel: 8 and 7).  `m` is chosen on the host so that the whole
-// grid is one wave of co-resident CTAs when the sub-domain is small (gx1: m = 2, 286 CTAs on 296 slots instead of
-// 605 CTAs = 2.04 waves).  Ownership and ping-pong rules are those of fused_kernel.
-// ---------------------------------------------------------------------------------------------
-constexpr int SBX = 32, SBY = 8;
-__global__ void __launch_bounds__(SBX *SBY, 2) strip_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
-                                                            int cur, int m, int last) {
-  __shared__ double sstr[8][SBY + 1][SBX];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int nxt = cur ^ 1;
-  const int i = 1 + blockIdx.x * (SBX - 1) + tx;
-  const int j0 = 1 + blockIdx.y * (SBY * m - 1);
-#if EVP_USE_PDL
-  cudaGridDependencySynchronize();
-#endif
-  for (int ch = 0; ch < m; ++ch) {
-    const int jT = j0 + SBY * ch + ty;
-    if (jT - ty > d.ny + 1) break;  // uniform: the strip has left the sub-domain
-    const bool inT = (i <= d.nx + 1) && (jT <= d.ny + 1);
-    const int c = at(d, inT ? i : 1, inT ? jT : 1);
-    double str[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (inT && d.maskT[c]) {
-      Sigma sg;
-      stress_at(d, k, cur, i, jT, sg, str);
-      // the strip's last T row is relaxed again by the strip above (as its first row), which stores it
-      const bool own = (tx < SBX - 1 || i == d.nx + 1) && (!(ch == m - 1 && ty == SBY - 1) || jT == d.ny + 1);
-      if (own) store_sigma(d, nxt, c, sg);
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) sstr[q][ty + 1][tx] = str[q];
-    __syncthreads();
-    // chunk 0 closes the U rows of its own first 7 T rows; later chunks close 8: the row carried in shared-memory
-    // row 0 plus their own first 7
-    const int jU = ch == 0 ? jT : jT - 1;
-    const int r = ch == 0 ? ty + 1 : ty;
-    const bool doU = (ch > 0 || ty < SBY - 1) && tx < SBX - 1 && i <= d.nx && jU <= d.ny;
-    if (doU) {
-      const int cu = at(d, i, jU);
-      if (d.maskU[cu]) {
-        double uin[16];
-        load_uin(d, k, cur, cu, uin);
-        const UOut o = stepu_point(uin[0], uin[1], uin[2], uin[3], uin[4], uin[5], uin[6], uin[7], uin[8], uin[9], uin[10], uin[11],
-                                   uin[12], uin[13], uin[14], uin[15], sstr[0][r][tx], sstr[1][r][tx + 1], sstr[2][r + 1][tx],
-                                   sstr[3][r + 1][tx + 1], sstr[4][r][tx], sstr[5][r + 1][tx], sstr[6][r][tx + 1],
-                                   sstr[7][r + 1][tx + 1], k);
-        store_uv(d, d.u[nxt], d.v[nxt], i, jU, o.u, o.v);
-        if (last) {
-          d.strintx[cu] = o.strintx;
-          d.strinty[cu] = o.strinty;
-          d.taubx[cu] = o.taubx;
-          d.tauby[cu] = o.tauby;
-        }
-      }
-    }
-    if (ch + 1 < m) {
-      __syncthreads();  // every read of this chunk's rows is done
-      if (ty == SBY - 1) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) sstr[q][0][tx] = str[q];
-      }
-    }
-  }
-}
-
-#ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
-cudaError_t launch_strip(const Dom &d, const KParams &p, int cur, int m, cudaStream_t s, bool pdl, int last) {
-  dim3 b(SBX, SBY), g((d.nx + SBX - 2) / (SBX - 1), (d.ny + SBY * m - 2) / (SBY * m - 1));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = 0; cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, strip_kernel, d, p, cur, m, last);
-}
-
-#endif  // EVP_HOST_EMU
-
 // loop hand-shake: "I have entered loop `base`" (my buffers are ready to be written), and the closing wait
 __global__ void p2p_start_kernel(const __grid_constant__ P2PParams pp) {
   if (threadIdx.x == 0) {
@@ -608,195 +469,66 @@ __global__ void p2p_finish_kernel(const __grid_constant__ P2PParams pp, int ndte
 }
 
 // ---------------------------------------------------------------------------------------------
-// KERNEL_FUSED, corner-parallel: 1024 threads = a 32 x 8 patch of T cells x 4 corner lanes (stress_lane).
-// Same patch geometry, ownership rule and ping-pong as fused_kernel; the momentum step runs on the first 256
-// threads, one per U point.
+// The part of the (uvel,vvel) halo update that is more than copying a neighbour's value: the tripole fold
+// (ice_boundary.F90:1550-1724).  One CTA per sub-domain that has such entries, once per subcycle, after the subcycle kernel:
+//   * waits until every peer's stores of subcycle `ksub` have arrived (the same epoch flags the next subcycle kernel's edge
+//     CTAs wait for) -- raw top-row values from other ranks sit in the staging rows ny+2, ny+3 of this rank's own arrays;
+//   * reads ALL its sources (every output is a function of pre-update values only, evp_halo.cu), synchronises, writes.
+// codes as in evp_halo.cu: 0 copy, 1 negate, 2 0.5*(a-b), 3 -(0.5*(a-b)).  With no peers (one rank) it is the whole fold.
 // ---------------------------------------------------------------------------------------------
-constexpr int F4X = 32, F4Y = 8;
-__global__ void __launch_bounds__(F4X *F4Y * 4, 1) fused4_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k, int cur) {
-  __shared__ double sstr[8][F4Y][F4X];
-  __shared__ double su[F4Y + 1][F4X + 1], sv[F4Y + 1][F4X + 1];
-  const int t = threadIdx.x;
-  const int nxt = cur ^ 1;
-  const int i0 = 1 + blockIdx.x * (F4X - 1), j0 = 1 + blockIdx.y * (F4Y - 1);
-  {
-    const double *__restrict__ U = d.u[cur];
-    const double *__restrict__ V = d.v[cur];
-    for (int q = t; q < (F4X + 1) * (F4Y + 1); q += F4X * F4Y * 4) {
-      const int a = q % (F4X + 1), b = q / (F4X + 1);
-      const int gi = i0 - 1 + a, gj = j0 - 1 + b;
-      const bool in = (gi <= d.nx + 1) && (gj <= d.ny + 1);
-      su[b][a] = in ? U[at(d, gi, gj)] : 0.0;
-      sv[b][a] = in ? V[at(d, gi, gj)] : 0.0;
-    }
+constexpr int FOLD_THREADS = 1024, FOLD_PER_THREAD = 8, FOLD_MAX = FOLD_THREADS * FOLD_PER_THREAD;
+__global__ void __launch_bounds__(FOLD_THREADS) p2p_fold_kernel(const __grid_constant__ P2PParams pp, double *U, double *V,
+                                                                const int *__restrict__ dst, const int *__restrict__ c1,
+                                                                const int *__restrict__ c2, const signed char *__restrict__ code,
+                                                                int n, int ksub) {
+  if (pp.npeers > 0) {
+    const unsigned long long base = *pp.epoch_base;
+    if ((int)threadIdx.x < pp.npeers)
+      wait_flag(pp.my_flags + pp.peer_rank[threadIdx.x], base + (unsigned long long)ksub + 1ULL, pp.err);
+    __syncthreads();
   }
-  __syncthreads();
-  {
-    const int corner = t & 3, cell = t >> 2, cx = cell & (F4X - 1), cy = cell / F4X;
-    const int i = i0 + cx, j = j0 + cy;
-    const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
-    const int c = at(d, inT ? i : 1, inT ? j : 1);
-    double str_u = 0.0, str_v = 0.0;
-    if (inT && d.maskT[c]) {
-      const int a = cx + 1, b = cy + 1;
-      const int sa = a - ((corner == NW || corner == SW) ? 1 : 0), sb = b - ((corner >= SW) ? 1 : 0);
-      const int xa = 2 * a - 1 - sa, yb = 2 * b - 1 - sb;
-      double sp = d.sig[cur][corner][c], sm = d.sig[cur][4 + corner][c], s12 = d.sig[cur][8 + corner][c];
-      const unsigned gmask = 0xFu << ((t & 31) & ~3);
-      stress_lane(corner, su[sb][sa], sv[sb][sa], su[sb][xa], sv[sb][xa], su[yb][sa], sv[yb][sa], d.dxT[c], d.dyT[c], d.dxhy[c],
-                  d.dyhx[c], d.cxp[c], d.cyp[c], d.cxm[c], d.cym[c], d.DminTarea[c], d.strength[c], k, gmask, sp, sm, s12, str_u, str_v);
-      const bool own = (cx < F4X - 1 || i == d.nx + 1) && (cy < F4Y - 1 || j == d.ny + 1);
-      if (own) {
-        d.sig[nxt][corner][c] = sp;
-        d.sig[nxt][4 + corner][c] = sm;
-        d.sig[nxt][8 + corner][c] = s12;
-      }
-    }
-    // NE: str1,str5  NW: str2,str7  SW: str4,str8  SE: str3,str6
-    const int qu = (corner == NE) ? 0 : (corner == NW) ? 1 : (corner == SW) ? 3 : 2;
-    const int qv = (corner == NE) ? 4 : (corner == NW) ? 6 : (corner == SW) ? 7 : 5;
-    sstr[qu][cy][cx] = str_u;
-    sstr[qv][cy][cx] = str_v;
-  }
-  __syncthreads();
-  if (t < F4X * F4Y) {
-    const int tx = t & (F4X - 1), ty = t / F4X;
-    const int i = i0 + tx, j = j0 + ty;
-    if (tx < F4X - 1 && ty < F4Y - 1 && i <= d.nx && j <= d.ny) {
-      const int c = at(d, i, j);
-      if (d.maskU[c]) {
-        const UOut o = stepu_point(su[ty + 1][tx + 1], sv[ty + 1][tx + 1], d.cdn[c], d.aiu[c], d.uocn[c], d.vocn[c], d.waterx[c],
-                                   d.watery[c], d.forcex[c], d.forcey[c], d.umassdti[c], d.fm[c], d.uarear[c], d.TbU[c],
-                                   d.uinit[c], d.vinit[c], sstr[0][ty][tx], sstr[1][ty][tx + 1], sstr[2][ty + 1][tx],
-                                   sstr[3][ty + 1][tx + 1], sstr[4][ty][tx], sstr[5][ty + 1][tx], sstr[6][ty][tx + 1],
-                                   sstr[7][ty + 1][tx + 1], k);
-        store_uv(d, d.u[nxt], d.v[nxt], i, j, o.u, o.v);
-        d.strintx[c] = o.strintx;
-        d.strinty[c] = o.strinty;
-        d.taubx[c] = o.taubx;
-        d.tauby[c] = o.tauby;
+  double u[FOLD_PER_THREAD], v[FOLD_PER_THREAD];
+#pragma unroll
+  for (int q = 0; q < FOLD_PER_THREAD; ++q) {
+    const int kk = threadIdx.x + q * FOLD_THREADS;
+    u[q] = 0.0; v[q] = 0.0;
+    if (kk < n) {
+      const int a = c1[kk], op = code[kk];
+      // written by other SMs / other GPUs during this launch sequence: read through L2, never a stale L1 line
+      u[q] = ld_cg_f64(U + a); v[q] = ld_cg_f64(V + a);
+      if (op == 1) {
+        u[q] = neg_f64(u[q]); v[q] = neg_f64(v[q]);
+      } else if (op == 2 || op == 3) {
+        // xavg = 0.5*(x1 + isign*x2) with isign = -1, x1 the partner with the lower i (ice_boundary.F90:1641-1646).  The lower
+        // partner receives xavg, the upper one isign*xavg: -(0.5*(x1-x2)) and 0.5*(x2-x1) differ in the sign of a zero result
+        const int b = c2[kk];
+        u[q] = 0.5 * (u[q] - ld_cg_f64(U + b));
+        v[q] = 0.5 * (v[q] - ld_cg_f64(V + b));
+        if (op == 3) { u[q] = neg_f64(u[q]); v[q] = neg_f64(v[q]); }
       }
     }
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// KERNEL_QUEUE: the fused patches of ALL subcycles as one work queue in a single launch.
-// Item w = (subcycle w / ntiles, patch w % ntiles).  A CTA claims the next item with an atomic counter, waits
-// until the patch itself and its (up to 8, cyclically wrapped) neighbour patches have published the previous
-// subcycle (per-patch progress counters, release/acquire through L2), then does exactly what fused_kernel does.
-// The same wait also covers the write-after-read hazard of the ping-pong copies.  Items are claimed in order,
-// so the oldest unfinished item always has its dependencies met: no deadlock as long as all CTAs are resident
-// (cooperative launch).  No kernel boundaries, no partial last wave, subcycles overlap at the patch level.
-// ---------------------------------------------------------------------------------------------
-constexpr int QBX = 32, QBY = 8;
-__global__ void __launch_bounds__(QBX *QBY, 2) queue_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
-                                                            int ndte, int ntx, int nty, unsigned *__restrict__ progress,
-                                                            unsigned *__restrict__ counter) {
-  __shared__ double sstr[8][QBY][QBX];
-  __shared__ unsigned s_item;
-  const int tx = threadIdx.x, ty = threadIdx.y, t = ty * QBX + tx;
-  const unsigned ntiles = (unsigned)(ntx * nty), nitems = ntiles * (unsigned)ndte;
-  for (;;) {
-    if (t == 0) s_item = atomicAdd(counter, 1u);
-    __syncthreads();
-    const unsigned item = s_item;
-    if (item >= nitems) break;
-    const int ksub = (int)(item / ntiles), tile = (int)(item % ntiles);
-    const int tbx = tile % ntx, tby = tile / ntx;
-    const int cur = ksub & 1, nxt = cur ^ 1;
-    if (ksub > 0 && t < 9) {
-      int nx_ = tbx + (t % 3) - 1, ny_ = tby + (t / 3) - 1;
-      if (d.wrap_ew) nx_ = (nx_ + ntx) % ntx;
-      if (d.wrap_ns) ny_ = (ny_ + nty) % nty;
-      if (nx_ >= 0 && nx_ < ntx && ny_ >= 0 && ny_ < nty) {
-        const unsigned *f = progress + ny_ * ntx + nx_;
-        while (ld_acquire_gpu(f) < (unsigned)ksub) {}
-      }
-    }
-    __syncthreads();
-
-    const int i = 1 + tbx * (QBX - 1) + tx, j = 1 + tby * (QBY - 1) + ty;
-    const bool inT = (i <= d.nx + 1) && (j <= d.ny + 1);
-    const int c = at(d, inT ? i : 1, inT ? j : 1);
-    double str[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    double uc = 0.0, vc = 0.0;
-    if (inT && d.maskT[c]) {
-      const int w = c - 1, s = c - d.ld, sw = s - 1;
-      // state written by other CTAs inside this launch: read through L2 (ld.cg), never a stale L1 line
-      const double *__restrict__ U = d.u[cur];
-      const double *__restrict__ V = d.v[cur];
-      uc = __ldcg(U + c); vc = __ldcg(V + c);
-      Sigma sg;
+  __syncthreads();  // every source has been read
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        sg.p[q] = __ldcg(d.sig[cur][q] + c);
-        sg.m[q] = __ldcg(d.sig[cur][4 + q] + c);
-        sg.s12[q] = __ldcg(d.sig[cur][8 + q] + c);
-      }
-      stress_point(uc, vc, __ldcg(U + w), __ldcg(V + w), __ldcg(U + s), __ldcg(V + s), __ldcg(U + sw), __ldcg(V + sw), d.dxT[c],
-                   d.dyT[c], d.dxhy[c], d.dyhx[c], d.cxp[c], d.cyp[c], d.cxm[c], d.cym[c], d.DminTarea[c], d.strength[c], k, sg, str);
-      const bool own = (tx < QBX - 1 || i == d.nx + 1) && (ty < QBY - 1 || j == d.ny + 1);
-      if (own) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          __stcg(d.sig[nxt][q] + c, sg.p[q]);
-          __stcg(d.sig[nxt][4 + q] + c, sg.m[q]);
-          __stcg(d.sig[nxt][8 + q] + c, sg.s12[q]);
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) sstr[q][ty][tx] = str[q];
-    __syncthreads();
-    if (tx < QBX - 1 && ty < QBY - 1 && i <= d.nx && j <= d.ny && d.maskU[c]) {
-      if (!d.maskT[c]) { uc = __ldcg(d.u[cur] + c); vc = __ldcg(d.v[cur] + c); }
-      const UOut o = stepu_point(uc, vc, d.cdn[c], d.aiu[c], d.uocn[c], d.vocn[c], d.waterx[c], d.watery[c], d.forcex[c],
-                                 d.forcey[c], d.umassdti[c], d.fm[c], d.uarear[c], d.TbU[c], d.uinit[c], d.vinit[c],
-                                 sstr[0][ty][tx], sstr[1][ty][tx + 1], sstr[2][ty + 1][tx], sstr[3][ty + 1][tx + 1],
-                                 sstr[4][ty][tx], sstr[5][ty + 1][tx], sstr[6][ty][tx + 1], sstr[7][ty + 1][tx + 1], k);
-      store_uv(d, d.u[nxt], d.v[nxt], i, j, o.u, o.v);
-      if (ksub == ndte - 1) {
-        d.strintx[c] = o.strintx;
-        d.strinty[c] = o.strinty;
-        d.taubx[c] = o.taubx;
-        d.tauby[c] = o.tauby;
-      }
-    }
-    __syncthreads();  // every store of the patch is issued; also protects sstr and s_item for the next item
-    if (t == 0) {
-      __threadfence();
-      st_release_gpu(progress + tile, (unsigned)(ksub + 1));
-    }
+  for (int q = 0; q < FOLD_PER_THREAD; ++q) {
+    const int kk = threadIdx.x + q * FOLD_THREADS;
+    if (kk < n) { U[dst[kk]] = u[q]; V[dst[kk]] = v[q]; }
   }
 }
 
 #ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
-cudaError_t launch_queue(const Dom &d, const KParams &p, int ndte, unsigned *progress, unsigned *counter, int nctas, cudaStream_t s) {
-  int ntx = (d.nx + QBX - 2) / (QBX - 1), nty = (d.ny + QBY - 2) / (QBY - 1);
-  void *args[] = {(void *)&d, (void *)&p, (void *)&ndte, (void *)&ntx, (void *)&nty, (void *)&progress, (void *)&counter};
-  return cudaLaunchCooperativeKernel((const void *)queue_kernel, dim3(nctas), dim3(QBX, QBY), args, 0, s);
+cudaError_t launch_fold(const P2PParams &pp, double *U, double *V, const int *dst, const int *c1, const int *c2,
+                        const signed char *code, int n, int ksub, cudaStream_t s) {
+  if (n > FOLD_MAX) return cudaErrorInvalidValue;
+  p2p_fold_kernel<<<1, FOLD_THREADS, 0, s>>>(pp, U, V, dst, c1, c2, code, n, ksub);
+  return cudaGetLastError();
 }
+int fold_max_entries() { return FOLD_MAX; }
+cudaError_t set_wait_timeout(unsigned long long ns) { return cudaMemcpyToSymbol(g_wait_timeout_ns, &ns, sizeof ns); }
 
-#endif  // EVP_HOST_EMU
-
-#include "evp_lane2.cuh"
-
-#ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
-template <int PX, int PY, int MINB, bool IL, int MAP, bool SPT = false>
-static cudaError_t launch_fused2_t(const Dom &d, const KParams &p, int cur, cudaStream_t s, bool pdl, int last) {
-  dim3 b(2 * PX * PY), g((d.nx + PX - 2) / (PX - 1), (d.ny + PY - 2) / (PY - 1));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = 0; cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, fused2_kernel<PX, PY, MINB, IL, MAP, SPT>, d, p, cur, last);
-}
-
-template <int FBX, int FBY, int MINB, bool HOIST = false, int SPEC = 0>
+template <int SPEC>
 static cudaError_t launch_fused_t(const Dom &d, const KParams &p, int cur, cudaStream_t s, bool pdl, int last) {
+  constexpr int FBX = 32, FBY = 8;
   dim3 b(FBX, FBY), g((d.nx + FBX - 2) / (FBX - 1), (d.ny + FBY - 2) / (FBY - 1));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = 0; cfg.stream = s;
@@ -805,77 +537,25 @@ static cudaError_t launch_fused_t(const Dom &d, const KParams &p, int cur, cudaS
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
   static const P2PParams nop2p{};
-  return cudaLaunchKernelEx(&cfg, fused_kernel<FBX, FBY, MINB, HOIST, false, SPEC>, d, p, cur, nop2p, 0, last);  // last: bit 0 = last subcycle, bit 1 = early PDL trigger
+  return cudaLaunchKernelEx(&cfg, fused_kernel<FBX, FBY, 2, false, SPEC>, d, p, cur, nop2p, 0, last);  // last: bit 0 = last subcycle, bit 1 = early PDL trigger
 }
 
-cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int variant, bool pdl, int last) {
-  if (variant == 20) {
-    dim3 g4((d.nx + F4X - 2) / (F4X - 1), (d.ny + F4Y - 2) / (F4Y - 1));
-    fused4_kernel<<<g4, F4X * F4Y * 4, 0, s>>>(d, p, cur);
-    return cudaGetLastError();
-  }
-  switch (variant) {
-    case 1: return launch_fused_t<32, 8, 3>(d, p, cur, s, pdl, last);
-    case 2: return launch_fused_t<32, 8, 4>(d, p, cur, s, pdl, last);
-    case 3: return launch_fused_t<32, 4, 4>(d, p, cur, s, pdl, last);
-    case 4: return launch_fused_t<32, 16, 1>(d, p, cur, s, pdl, last);
-    case 5: return launch_fused_t<64, 4, 2>(d, p, cur, s, pdl, last);
-    case 6: return launch_fused_t<32, 6, 3>(d, p, cur, s, pdl, last);
-    case 7: return launch_fused_t<32, 8, 2, true>(d, p, cur, s, pdl, last);
-    case 8: return launch_fused_t<33, 8, 2, false>(d, p, cur, s, pdl, last);
-    case 9: return launch_fused_t<33, 8, 2, true>(d, p, cur, s, pdl, last);
-    case 10: return launch_fused_t<32, 4, 4, true>(d, p, cur, s, pdl, last);
-    case 11: return launch_fused_t<32, 9, 2>(d, p, cur, s, pdl, last);
-    case 12: return launch_fused_t<32, 10, 2>(d, p, cur, s, pdl, last);
-    case 13: return launch_fused_t<32, 7, 3>(d, p, cur, s, pdl, last);
-    case 14: return launch_fused_t<32, 5, 4>(d, p, cur, s, pdl, last);
-    case 15: return launch_fused_t<32, 11, 1>(d, p, cur, s, pdl, last);
-    case 16: return launch_fused_t<32, 8, 2>(d, p, cur, s, pdl, last);  // the non-speculative form (round-1 default)
-    case 17: return launch_fused_t<32, 8, 2, false, 1>(d, p, cur, s, pdl, last);  // speculative T loads only
-    case 18: return launch_fused_t<32, 8, 2, false, 2>(d, p, cur, s, pdl, last);  // cp.async momentum operands only
-    case 19: return launch_fused_t<32, 8, 2, false, 3>(d, p, cur, s, pdl, last);  // both
-    case 21: return launch_fused_t<32, 8, 2, false, 5>(d, p, cur, s, pdl, last);  // 17 + interleaved div/sqrt
-    case 22: return launch_fused_t<32, 8, 2, false, 7>(d, p, cur, s, pdl, last);  // 19 + interleaved div/sqrt
-    case 23: return launch_fused_t<32, 8, 2, false, 4>(d, p, cur, s, pdl, last);  // 16 + interleaved div/sqrt
-    case 31: return launch_fused_t<32, 8, 2, false, 12>(d, p, cur, s, pdl, last);  // 23 + pairwise named barriers
-    case 32: return launch_fused_t<32, 8, 2, false, 11>(d, p, cur, s, pdl, last);  // 19 + pairwise named barriers
-    case 24: return launch_fused_t<32, 8, 3, false, 4>(d, p, cur, s, pdl, last);  // 23 with other CTA shapes / residency
-    case 25: return launch_fused_t<32, 6, 3, false, 4>(d, p, cur, s, pdl, last);
-    case 26: return launch_fused_t<32, 5, 4, false, 4>(d, p, cur, s, pdl, last);
-    case 27: return launch_fused_t<32, 4, 4, false, 4>(d, p, cur, s, pdl, last);
-    case 28: return launch_fused_t<32, 16, 1, false, 4>(d, p, cur, s, pdl, last);
-    case 29: return launch_fused_t<32, 12, 1, false, 4>(d, p, cur, s, pdl, last);
-    case 59: return launch_fused_t<32, 8, 2, false, 3 | 32>(d, p, cur, s, pdl, last);  // 19 + derived geometry (after set_metric)
-    case 63: return launch_fused_t<32, 8, 2, false, 4 | 32>(d, p, cur, s, pdl, last);  // 23 + derived geometry
-    // two lanes per T cell (evp_lane2.cuh): <patch x, patch y, CTAs per SM, interleaved div/sqrt, lane mapping>
-    case 40: return launch_fused2_t<32, 8, 2, true, 0>(d, p, cur, s, pdl, last);   // 512 threads, 64 registers
-    case 41: return launch_fused2_t<32, 8, 1, true, 0>(d, p, cur, s, pdl, last);   // 512 threads, 128 registers
-    case 42: return launch_fused2_t<16, 8, 3, true, 0>(d, p, cur, s, pdl, last);   // 256 threads, 80 registers
-    case 43: return launch_fused2_t<16, 8, 4, true, 0>(d, p, cur, s, pdl, last);   // 256 threads, 64 registers
-    case 44: return launch_fused2_t<32, 4, 3, true, 0>(d, p, cur, s, pdl, last);   // 256 threads, 80 registers
-    case 45: return launch_fused2_t<16, 16, 2, true, 0>(d, p, cur, s, pdl, last);  // 512 threads, 64 registers
-    case 46: return launch_fused2_t<32, 8, 2, false, 0>(d, p, cur, s, pdl, last);  // 40 with the built-in / and sqrt
-    case 47: return launch_fused2_t<32, 8, 2, true, 0, true>(d, p, cur, s, pdl, last);   // 40 with speculative operand loads
-    case 48: return launch_fused2_t<16, 8, 3, true, 0, true>(d, p, cur, s, pdl, last);   // 42 with speculative operand loads
-    case 49: return launch_fused2_t<32, 8, 2, true, 1, true>(d, p, cur, s, pdl, last);   // 50 with speculative operand loads
-    case 50: return launch_fused2_t<32, 8, 2, true, 1>(d, p, cur, s, pdl, last);   // warp-uniform roles, shared-memory swap
-    case 54: return launch_fused2_t<32, 8, 2, true, 2>(d, p, cur, s, pdl, last);   // 50 with one specialised code path per role
-    case 55: return launch_fused2_t<32, 4, 4, true, 2>(d, p, cur, s, pdl, last);
-    case 56: return launch_fused2_t<32, 8, 2, true, 2, true>(d, p, cur, s, pdl, last);   // 54 with speculative operand loads
-    case 51: return launch_fused2_t<32, 8, 1, true, 1>(d, p, cur, s, pdl, last);
-    case 52: return launch_fused2_t<32, 4, 3, true, 1>(d, p, cur, s, pdl, last);
-    case 53: return launch_fused2_t<32, 4, 4, true, 1>(d, p, cur, s, pdl, last);
-    default: return launch_fused_t<32, 8, 2, false, 4>(d, p, cur, s, pdl, last);
+// form: 0 L2-resident, 1 HBM-streaming, 2 HBM-streaming with derived geometry (evp_abi.cu chooses from the sub-domain size)
+cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int form, bool pdl, int last) {
+  switch (form) {
+    case 1: return launch_fused_t<FORM_STREAM>(d, p, cur, s, pdl, last);
+    case 2: return launch_fused_t<FORM_STREAM_DER>(d, p, cur, s, pdl, last);
+    default: return launch_fused_t<FORM_RESIDENT>(d, p, cur, s, pdl, last);
   }
 }
 
-// ksub = -1: loop start hand-shake; ksub = -2 - ndte ... no: see launch_p2p_aux
-cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, int last, int variant, cudaStream_t s) {
+// ksub = -1: loop start hand-shake; ksub <= -2: closing wait after -2-ksub subcycles
+cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, int last, int form, cudaStream_t s) {
   if (ksub == -1) {
     p2p_start_kernel<<<1, 32, 0, s>>>(pp);
     return cudaGetLastError();
   }
-  if (ksub <= -2) {  // closing wait after -2-ksub subcycles
+  if (ksub <= -2) {
     p2p_finish_kernel<<<1, 32, 0, s>>>(pp, -2 - ksub);
     return cudaGetLastError();
   }
@@ -887,22 +567,11 @@ cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = (last & 4) ? 1 : 0;
   const int flags = last & 3;
-  if ((variant & 0xff) == 40 || (variant & 0xff) == 50 || (variant & 0xff) == 54) {  // two lanes per T cell (evp_lane2.cuh), same 32 x 8 tile table
-    cfg.blockDim = dim3(512);
-    const int ctiles = (variant & 0x100) ? 1 : 0;
-    if ((variant & 0xff) == 40) return cudaLaunchKernelEx(&cfg, fused2_p2p_kernel<32, 8, 2, true, 0>, d, p, cur, pp, ksub, flags, ctiles);
-    if ((variant & 0xff) == 54) return cudaLaunchKernelEx(&cfg, fused2_p2p_kernel<32, 8, 2, true, 2>, d, p, cur, pp, ksub, flags, ctiles);
-    return cudaLaunchKernelEx(&cfg, fused2_p2p_kernel<32, 8, 2, true, 1>, d, p, cur, pp, ksub, flags, ctiles);
+  switch (form) {
+    case 1: return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, true, FORM_STREAM>, d, p, cur, pp, ksub, flags);
+    case 2: return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, true, FORM_STREAM_DER>, d, p, cur, pp, ksub, flags);
+    default: return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, true, FORM_RESIDENT>, d, p, cur, pp, ksub, flags);
   }
-  if ((variant & 0xff) == 59) return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 3 | 32>, d, p, cur, pp, ksub, flags);
-  if ((variant & 0xff) == 63) return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 4 | 32>, d, p, cur, pp, ksub, flags);
-  if (variant & 0x100) {  // tile table in constant memory (set_p2p_tiles)
-    if ((variant & 0xff) == 19) return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 3 | 16>, d, p, cur, pp, ksub, flags);
-    return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 4 | 16>, d, p, cur, pp, ksub, flags);
-  }
-  if (variant == 19) return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 3>, d, p, cur, pp, ksub, flags);
-  return cudaLaunchKernelEx(&cfg, fused_kernel<32, 8, 2, false, true, 4>, d, p, cur, pp, ksub, flags);
-  return cudaGetLastError();
 }
 #endif  // EVP_HOST_EMU
 

@@ -23,11 +23,15 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// wait until flag >= want; bounded so that a lost peer cannot hang the GPU (sets *err instead)
+// wait until flag >= want; bounded so that a lost peer cannot hang the GPU (sets *err instead).  The bound is wall-clock
+// (%globaltimer, ns) and generous -- 60 s unless EVP_B200_P2P_TIMEOUT_S says otherwise (evp_abi.cu -> set_wait_timeout) -- because
+// rank skew of seconds is ordinary: first-call graph instantiation or module load on one rank, MPS time slicing, a debugger.
+static __device__ unsigned long long g_wait_timeout_ns = 60000000000ULL;
 __device__ __forceinline__ void wait_flag(const unsigned long long *flag, unsigned long long want, int *err) {
-  const long long t0 = clock64();
+  if (ld_acquire_sys(flag) >= want) return;
+  const unsigned long long t0 = gtime();
   while (ld_acquire_sys(flag) < want) {
-    if (clock64() - t0 > 6000000000LL) { atomicExch(err, 1); break; }
+    if (gtime() - t0 > g_wait_timeout_ns) { atomicExch(err, 1); break; }
   }
 }
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
@@ -45,6 +49,12 @@ __device__ __forceinline__ double ld_f64(const double *p) {
 __device__ __forceinline__ double ld_nc_f64(const double *p) {  // never written while the loop runs
   double v;
   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+// data written by other SMs (or other GPUs) since this SM last saw the line: always served by L2
+__device__ __forceinline__ double ld_cg_f64(const double *p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned ld_nc_u8(const unsigned char *p) {
@@ -86,6 +96,7 @@ inline void wait_flag(const unsigned long long *flag, unsigned long long want, i
 }
 inline double ld_f64(const double *p) { return *(const volatile double *)p; }
 inline double ld_nc_f64(const double *p) { return *p; }
+inline double ld_cg_f64(const double *p) { return *(const volatile double *)p; }
 inline unsigned ld_nc_u8(const unsigned char *p) { return *p; }
 inline void cp_async8(double *smem, const double *g) { *smem = *g; }
 inline void cp_async_commit() {}
@@ -96,5 +107,9 @@ inline unsigned ld_acquire_gpu(const unsigned *p) { return __atomic_load_n(p, __
 inline void st_release_gpu(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 
 #endif
+
+// -x as a flip of the sign bit, whatever the compiler would make of `-x`: the tripole fold negates values that are often zeros
+// (land, open water) and the reference's -0.0 / +0.0 must come out bit for bit
+__device__ __forceinline__ double neg_f64(double x) { return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x)); }
 
 }  // namespace evp

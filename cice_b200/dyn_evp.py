@@ -195,8 +195,27 @@ def halo_plan(rects, rank, nx_global, ny_global, ew, ns):
     return out[:n.value]
 
 
+def p2p_plan(rects, rank, nx_global, ny_global, ew, ns):
+    """host-only: the halo as the in-kernel NVLink form serves it.  Returns (push, fold): push (n,4) {src, dst rank, dst cell, negate},
+    fold (m,4) {dst, src1, src2, op}; cells index the owning rank's sub-domain array, staging rows included (dom_cells)."""
+    L = load()
+    r = np.ascontiguousarray(rects, dtype=np.int32)
+    npush, nfold = C.c_int32(), C.c_int32()
+    pi = C.POINTER(C.c_int32)
+    args = (len(r), r.ctypes.data_as(pi), rank, nx_global, ny_global, ew, ns)
+    check(L.evp_b200_p2p_plan(*args, C.byref(npush), None, C.byref(nfold), None, 0), "p2p_plan")
+    cap = max(npush.value, nfold.value, 1)
+    push, fold = np.zeros((cap, 4), np.int32), np.zeros((cap, 4), np.int32)
+    check(L.evp_b200_p2p_plan(*args, C.byref(npush), push.ctypes.data_as(pi), C.byref(nfold), fold.ctypes.data_as(pi), cap), "p2p_plan")
+    return push[:npush.value], fold[:nfold.value]
+
+
 def dom_pitch(nx):
     return load().evp_b200_dom_pitch(int(nx))
+
+
+def dom_cells(nx, ny):
+    return int(load().evp_b200_dom_cells(int(nx), int(ny)))
 
 
 def describe():

@@ -27,7 +27,7 @@ module ice_dyn_evp_b200
   public :: dyn_evp_b200_init_cgrid, dyn_evp_b200_run_cgrid   ! grid_ice = 'C' (ice_dyn_evp.F90:936-1101)
   public :: dyn_evp_b200_deformations, dyn_evp_b200_finish    ! the two steps right after the loop, from the device-resident velocities
 
-  integer(c_int32_t), parameter :: EVP_B200_ABI_VERSION = 2
+  integer(c_int32_t), parameter :: EVP_B200_ABI_VERSION = 3
   integer(c_int32_t), parameter :: BNDY_OPEN = 0, BNDY_CLOSED = 1, BNDY_CYCLIC = 2, BNDY_TRIPOLE = 3
 
   ! evp_b200_grid_t
@@ -248,13 +248,13 @@ contains
     g%ns_boundary_type = bndy_code(ns_boundary_type)
     g%ilo = c_loc(b_ilo);  g%ihi = c_loc(b_ihi);  g%jlo = c_loc(b_jlo);  g%jhi = c_loc(b_jhi)
     g%i_glob = c_loc(b_iglob);  g%j_glob = c_loc(b_jglob)
-    g%dxT = c_loc(dxT);    g%dyT = c_loc(dyT);    g%dxhy = c_loc(dxhy);  g%dyhx = c_loc(dyhx)
-    g%cxp = c_loc(cxp);    g%cyp = c_loc(cyp);    g%cxm = c_loc(cxm);    g%cym = c_loc(cym)
-    g%DminTarea = c_loc(DminTarea);  g%uarear = c_loc(uarear)
+    g%dxT = loc3(dxT);    g%dyT = loc3(dyT);    g%dxhy = loc3(dxhy);  g%dyhx = loc3(dyhx)
+    g%cxp = loc3(cxp);    g%cyp = loc3(cyp);    g%cxm = loc3(cxm);    g%cym = loc3(cym)
+    g%DminTarea = loc3(DminTarea);  g%uarear = loc3(uarear)
     call check(evp_b200_init(g), 'evp_b200_init')
     ! optional: the metric arrays behind dxhy, dyhx, cxp, cyp, cxm, cym, DminTarea; the library checks on the device that they
     ! reproduce those arrays bit for bit before any kernel may derive them (include/evp_b200.h); a non-zero count is not an error
-    call check(evp_b200_set_metric(c_loc(HTN), c_loc(HTE), deltaminEVP, nbad), 'evp_b200_set_metric')
+    call check(evp_b200_set_metric(loc3(HTN), loc3(HTE), deltaminEVP, nbad), 'evp_b200_set_metric')
   end subroutine dyn_evp_b200_init
 
   !---------------------------------------------------------------------
@@ -340,6 +340,16 @@ contains
     call check(evp_b200_pin_host(c_loc(a), int(size(a), c_size_t) * 8_c_size_t), 'evp_b200_pin_host')
   end subroutine pin
 
+  ! C address of a use-associated module array.  The reference declares its grid and dynamics arrays without TARGET
+  ! (ice_grid.F90:78-140, ice_dyn_shared.F90:100-130), and C_LOC requires POINTER or TARGET (gfortran: "shall have either the
+  ! POINTER or the TARGET attribute"), so the address is taken of a TARGET, CONTIGUOUS dummy instead: the arrays are whole
+  ! allocatables, hence contiguous, hence passed by reference without copy-in, and the address stays valid for the run.
+  function loc3(a) result(p)
+    real(kind=dbl_kind), dimension(:,:,:), intent(in), target, contiguous :: a
+    type(c_ptr) :: p
+    p = c_loc(a)
+  end function loc3
+
   !---------------------------------------------------------------------
   ! `deformations` (ice_dyn_shared.F90:1756-1860; the per-block call at ice_dyn_evp.F90:920-934) for all blocks at once, from
   ! the velocities dyn_evp_b200_run left on the device.  The five arrays keep their values off the ice T cells.
@@ -348,7 +358,7 @@ contains
     use ice_dyn_shared, only: e_factor
     real(kind=dbl_kind), dimension(:,:,:), intent(inout), target, contiguous :: divu, shear, vort, rdg_conv, rdg_shear
     type(evp_b200_deform_t) :: d
-    d%dxU = c_loc(dxU);  d%dyU = c_loc(dyU);  d%tarear = c_loc(tarear)
+    d%dxU = loc3(dxU);  d%dyU = loc3(dyU);  d%tarear = loc3(tarear)
     d%divu = c_loc(divu);  d%shear = c_loc(shear);  d%vort = c_loc(vort);  d%rdg_conv = c_loc(rdg_conv);  d%rdg_shear = c_loc(rdg_shear)
     d%e_factor = e_factor
     call check(evp_b200_deformations(d), 'evp_b200_deformations')
@@ -375,11 +385,11 @@ contains
     use ice_grid,    only: dxN, dyE, dxE, dyN, dxU, dyU, tarea, uarea, earea, narea, earear, narear, hm, uvm, epm, npm
     use ice_dyn_evp, only: ratiodxN, ratiodxNr, ratiodyE, ratiodyEr
     type(evp_b200_cgrid_t) :: cg
-    cg%dxN = c_loc(dxN);  cg%dyE = c_loc(dyE);  cg%dxE = c_loc(dxE);  cg%dyN = c_loc(dyN);  cg%dxU = c_loc(dxU);  cg%dyU = c_loc(dyU)
-    cg%tarea = c_loc(tarea);  cg%uarea = c_loc(uarea);  cg%earea = c_loc(earea);  cg%narea = c_loc(narea)
-    cg%earear = c_loc(earear);  cg%narear = c_loc(narear)
-    cg%ratiodxN = c_loc(ratiodxN);  cg%ratiodxNr = c_loc(ratiodxNr);  cg%ratiodyE = c_loc(ratiodyE);  cg%ratiodyEr = c_loc(ratiodyEr)
-    cg%hm = c_loc(hm);  cg%uvm = c_loc(uvm);  cg%epm = c_loc(epm);  cg%npm = c_loc(npm)
+    cg%dxN = loc3(dxN);  cg%dyE = loc3(dyE);  cg%dxE = loc3(dxE);  cg%dyN = loc3(dyN);  cg%dxU = loc3(dxU);  cg%dyU = loc3(dyU)
+    cg%tarea = loc3(tarea);  cg%uarea = loc3(uarea);  cg%earea = loc3(earea);  cg%narea = loc3(narea)
+    cg%earear = loc3(earear);  cg%narear = loc3(narear)
+    cg%ratiodxN = loc3(ratiodxN);  cg%ratiodxNr = loc3(ratiodxNr);  cg%ratiodyE = loc3(ratiodyE);  cg%ratiodyEr = loc3(ratiodyEr)
+    cg%hm = loc3(hm);  cg%uvm = loc3(uvm);  cg%epm = loc3(epm);  cg%npm = loc3(npm)
     allocate(imaskE(nx_block, ny_block, max_blocks), imaskN(nx_block, ny_block, max_blocks))
     call check(evp_b200_init_cgrid(cg), 'evp_b200_init_cgrid')
   end subroutine dyn_evp_b200_init_cgrid

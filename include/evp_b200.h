@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define EVP_B200_ABI_VERSION 2
+#define EVP_B200_ABI_VERSION 3
 
 /* boundary types: domain_nml ew_boundary_type / ns_boundary_type
  * (cicecore/cicedyn/infrastructure/ice_domain.F90:186-240) */
@@ -61,12 +61,14 @@ enum {
 
 /* kernel strategy (0 lets the library choose from the sub-domain size) */
 enum {
-  EVP_B200_KERNEL_AUTO       = 0,
-  EVP_B200_KERNEL_SPLIT      = 1,  /* stress kernel + stepu kernel per subcycle (first correct path) */
-  EVP_B200_KERNEL_FUSED      = 2,  /* one fused stress+stepu kernel per subcycle, CUDA-graphed */
-  EVP_B200_KERNEL_PERSISTENT = 3,  /* all ndte subcycles in one cooperative launch, state on chip */
-  EVP_B200_KERNEL_QUEUE      = 4   /* all ndte subcycles in one launch: the fused patches of every subcycle form one
-                                      work queue, ordered by per-patch progress counters instead of kernel boundaries */
+  EVP_B200_KERNEL_AUTO           = 0,
+  EVP_B200_KERNEL_SPLIT          = 1,  /* stress kernel + stepu kernel per subcycle, the reference's two sweeps (first correct
+                                          path; on the C grid: the five-kernel form cut at the reference's halo points) */
+  EVP_B200_KERNEL_FUSED          = 2,  /* one fused stress+stepu kernel per subcycle, CUDA-graphed; the form follows the
+                                          sub-domain size (L2-resident or HBM-streaming) */
+  EVP_B200_KERNEL_PERSISTENT     = 3,  /* all ndte subcycles in one cooperative launch, state on chip */
+  EVP_B200_KERNEL_FUSED_STREAM   = 4,  /* FUSED, HBM-streaming form forced (operands requested early, cp.async staging) */
+  EVP_B200_KERNEL_FUSED_RESIDENT = 5   /* FUSED, L2-resident form forced (interleaved division / square-root chains) */
 };
 
 /*
@@ -272,8 +274,8 @@ int evp_b200_unpin_host(void *ptr);
  * (ice_dyn_shared.F90:384-388, 401-441; the reference's own 1-D solver recomputes them from HTE, HTN every subcycle,
  * ice_dyn_core1d.F90:191-199).  Given HTN and HTE (ice_grid.F90, (nx_block,ny_block,max_blocks)), the library checks ON THE
  * DEVICE that the reference's expressions reproduce the seven arrays bit for bit on every T cell the loop can touch; only then
- * may the kernels that read two arrays instead of seven be selected (EVP_B200_FUSED_VARIANT=59|63: 360 instead of 400 B per cell
- * and subcycle on sub-domains that stream from HBM).  *mismatches (may be NULL) receives the number of cells that differ;
+ * do the kernels of sub-domains that stream from HBM read two arrays instead of seven (360 instead of 400 B per cell and
+ * subcycle; measured 164 vs 170 ms per step on 3600x2400).  *mismatches (may be NULL) receives the number of cells that differ;
  * a non-zero count is not an error, the arrays simply stay in use.  Call after evp_b200_init. */
 int evp_b200_set_metric(const double *HTN, const double *HTE, double deltaminEVP, int32_t *mismatches);
 
@@ -321,6 +323,16 @@ const char *evp_b200_describe(void);
 int evp_b200_halo_plan(int32_t nranks, const int32_t *rects, int32_t rank, int32_t nx_global, int32_t ny_global,
                        int32_t ew_boundary_type, int32_t ns_boundary_type, int32_t *n, int32_t *out, int32_t cap);
 int32_t evp_b200_dom_pitch(int32_t nx);
+/* cells of one sub-domain array: pitch * (ny + 2 ghost rows + 2 staging rows for raw values that cross a tripole fold) */
+int64_t evp_b200_dom_cells(int32_t nx, int32_t ny);
+/* The same halo as the in-kernel NVLink form serves it (no staged exchange): what `rank` stores into OTHER ranks' arrays while it
+ * advances a subcycle -- up to `cap` entries of 4 ints {src cell of rank, destination rank, destination cell, negate 0/1} in
+ * push_out; destination cells include the staging rows ny+2, ny+3 -- and what it combines itself once its peers' stores have
+ * arrived -- entries {dst, src1, src2, op} (all cells of its own array, op as in evp_b200_halo_plan) in fold_out.
+ * Replaces ice_HaloUpdate's message build for the dyn fields (ice_boundary.F90:7910-9050) incl. the tripole buffers (:8079-8157). */
+int evp_b200_p2p_plan(int32_t nranks, const int32_t *rects, int32_t rank, int32_t nx_global, int32_t ny_global,
+                      int32_t ew_boundary_type, int32_t ns_boundary_type, int32_t *n_push, int32_t *push_out, int32_t *n_fold,
+                      int32_t *fold_out, int32_t cap);
 
 #ifdef __cplusplus
 }

@@ -1,4 +1,4 @@
-// emu_bgrid.cpp -- the B-grid CUDA kernels of cice_b200/csrc/evp_kernels.cu (+ evp_lane2.cuh) run THREAD BY THREAD ON THE HOST.
+// emu_bgrid.cpp -- the B-grid CUDA kernels of cice_b200/csrc/evp_kernels.cu run THREAD BY THREAD ON THE HOST.
 //
 // Test infrastructure only (tests/test_emu_bgrid.py); nothing in the product links this.  The kernel translation unit is
 // included unchanged with EVP_HOST_EMU defined (launchers compiled out, PTX helpers replaced by their plain C++ meaning:
@@ -23,21 +23,14 @@ struct Host {
 template <int SPEC>
 void fused_step(const Dom &d, const KParams &k, int cur, int flags) {
   static const P2PParams nop2p{};
-  emu::launch({(d.nx + 30) / 31, (d.ny + 6) / 7, 1}, {32, 8, 1}, [&] { fused_kernel<32, 8, 2, false, false, SPEC>(d, k, cur, nop2p, 0, flags); });
-}
-template <int PX, int PY, bool IL, int MAP, bool SPT = false>
-void lane2_step(const Dom &d, const KParams &k, int cur, int flags) {
-  emu::launch({(d.nx + PX - 2) / (PX - 1), (d.ny + PY - 2) / (PY - 1), 1}, {2 * PX * PY, 1, 1}, [&] { fused2_kernel<PX, PY, 1, IL, MAP, SPT>(d, k, cur, flags); });
+  emu::launch({(d.nx + 30) / 31, (d.ny + 6) / 7, 1}, {32, 8, 1}, [&] { fused_kernel<32, 8, 2, false, SPEC>(d, k, cur, nop2p, 0, flags); });
 }
 }  // namespace
 
 // kind 0: stress_kernel + stepu_kernel (in place)            sub: unused
-// kind 1: fused_kernel<32,8,2,false,false,SPEC>               sub: SPEC (0 1 2 3 4 5 7 12 16 35 36; 4 is the default form)
-// kind 2: strip_kernel                                        sub: chunks per CTA
-// kind 3: fused4_kernel (four lanes per cell)                 sub: unused
-// kind 4: fused2_kernel (two lanes per cell)                  sub: shape/mapping 0..5, +8 for IL = true, 16..18 speculative loads, 20..22 specialised roles
-// kind 5: fused_kernel<32,8,2,false,true,4> without peers     sub: 0 = edge tiles first and counted, 1 = none counted
-// kind 6: fused2_p2p_kernel (two lanes + in-kernel halo form)  sub: bit 0 none counted, bit 1 warp-pair mapping, bit 2 constant tile table, bit 3 specialised roles
+// kind 1: fused_kernel<32,8,2,false,SPEC>                     sub: SPEC bits (1 speculative loads, 2 cp.async, 4 interleaved div/sqrt, 32 derived
+//                                                                  geometry); 4 = L2-resident form, 3 = HBM-streaming form, 35 = streaming + derived
+// kind 5: fused_kernel<32,8,2,true,4> without peers           sub: 0 = edge tiles first and counted, 1 = none counted
 // One block in the reference's layout (nghost = 1) IS a dom: ld = nx_block, interior 1..nx_block-2.
 extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, int wrap_ns, const KParams *kp, int ndte,
                              const int32_t *maskT, const int32_t *maskU, double *sig /*[12][n]*/, double *u, double *v,
@@ -68,7 +61,7 @@ extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, i
   std::vector<int> order, push_start(2 * d.nx + 2 * d.ny + 8, 0);
   unsigned long long done = 0, epoch = 1, flags_mem[64] = {};
   int err = 0;
-  if (kind == 5 || kind == 6) {
+  if (kind == 5) {
     const int ntx = (d.nx + 30) / 31, nty = (d.ny + 6) / 7;
     int n_edge = 0;
     for (int pass = 0; pass < 2; ++pass)
@@ -91,58 +84,18 @@ extern "C" int emu_bgrid_run(int kind, int sub, int nxb, int nyb, int wrap_ew, i
       continue;  // in place
     } else if (kind == 1) {
       switch (sub) {
-        case 0: fused_step<0>(d, k, cur, flags); break;
         case 1: fused_step<1>(d, k, cur, flags); break;
         case 2: fused_step<2>(d, k, cur, flags); break;
         case 3: fused_step<3>(d, k, cur, flags); break;
         case 4: fused_step<4>(d, k, cur, flags); break;
         case 5: fused_step<5>(d, k, cur, flags); break;
         case 7: fused_step<7>(d, k, cur, flags); break;
-        case 12: fused_step<12>(d, k, cur, flags); break;
-        case 16: fused_step<16>(d, k, cur, flags); break;
-        case 35: fused_step<3 | 32>(d, k, cur, flags); break;   // variant 59: 19 + derived geometry (emu_set_metric first)
-        case 36: fused_step<4 | 32>(d, k, cur, flags); break;   // variant 63: 23 + derived geometry
-        default: return 1;
-      }
-    } else if (kind == 2) {
-      const int m = sub;
-      emu::launch({(d.nx + SBX - 2) / (SBX - 1), (d.ny + SBY * m - 2) / (SBY * m - 1), 1}, {SBX, SBY, 1}, [&] { strip_kernel(d, k, cur, m, flags); });
-    } else if (kind == 3) {
-      // fused4_kernel writes the diagnostics every subcycle
-      emu::launch({(d.nx + F4X - 2) / (F4X - 1), (d.ny + F4Y - 2) / (F4Y - 1), 1}, {F4X * F4Y * 4, 1, 1}, [&] { fused4_kernel(d, k, cur); });
-    } else if (kind == 4) {
-      switch (sub) {
-        case 0: lane2_step<32, 8, false, 0>(d, k, cur, flags); break;
-        case 1: lane2_step<16, 8, false, 0>(d, k, cur, flags); break;
-        case 2: lane2_step<32, 4, false, 0>(d, k, cur, flags); break;
-        case 3: lane2_step<16, 16, false, 0>(d, k, cur, flags); break;
-        case 4: lane2_step<32, 8, false, 1>(d, k, cur, flags); break;
-        case 5: lane2_step<32, 4, false, 1>(d, k, cur, flags); break;
-        case 8: lane2_step<32, 8, true, 0>(d, k, cur, flags); break;
-        case 9: lane2_step<16, 8, true, 0>(d, k, cur, flags); break;
-        case 10: lane2_step<32, 4, true, 0>(d, k, cur, flags); break;
-        case 11: lane2_step<16, 16, true, 0>(d, k, cur, flags); break;
-        case 12: lane2_step<32, 8, true, 1>(d, k, cur, flags); break;
-        case 13: lane2_step<32, 4, true, 1>(d, k, cur, flags); break;
-        case 16: lane2_step<32, 8, true, 0, true>(d, k, cur, flags); break;   // speculative operand loads
-        case 17: lane2_step<16, 8, true, 0, true>(d, k, cur, flags); break;
-        case 18: lane2_step<32, 8, true, 1, true>(d, k, cur, flags); break;
-        case 20: lane2_step<32, 8, true, 2>(d, k, cur, flags); break;         // one specialised code path per role
-        case 21: lane2_step<32, 4, true, 2>(d, k, cur, flags); break;
-        case 22: lane2_step<32, 8, true, 2, true>(d, k, cur, flags); break;
+        case 35: fused_step<3 | 32>(d, k, cur, flags); break;   // streaming form + derived geometry (emu_set_metric first)
+        case 36: fused_step<4 | 32>(d, k, cur, flags); break;   // resident form + derived geometry
         default: return 1;
       }
     } else if (kind == 5) {
-      emu::launch({pp.ntx * pp.nty, 1, 1}, {32, 8, 1}, [&] { fused_kernel<32, 8, 2, false, true, 4>(d, k, cur, pp, ks, flags); });
-      if (err) return 2;
-    } else if (kind == 6) {   // sub bit 0: no edge counter, bit 1: warp-pair mapping, bit 2: tile table from the "constant" array
-      if (sub & 4) memcpy(c_tile_order, order.data(), order.size() * sizeof(int));
-      if (sub & 8)
-        emu::launch({pp.ntx * pp.nty, 1, 1}, {512, 1, 1}, [&] { fused2_p2p_kernel<32, 8, 2, true, 2>(d, k, cur, pp, ks, flags, (sub & 4) ? 1 : 0); });
-      else if (sub & 2)
-        emu::launch({pp.ntx * pp.nty, 1, 1}, {512, 1, 1}, [&] { fused2_p2p_kernel<32, 8, 2, true, 1>(d, k, cur, pp, ks, flags, (sub & 4) ? 1 : 0); });
-      else
-        emu::launch({pp.ntx * pp.nty, 1, 1}, {512, 1, 1}, [&] { fused2_p2p_kernel<32, 8, 2, true, 0>(d, k, cur, pp, ks, flags, (sub & 4) ? 1 : 0); });
+      emu::launch({pp.ntx * pp.nty, 1, 1}, {32, 8, 1}, [&] { fused_kernel<32, 8, 2, true, 4>(d, k, cur, pp, ks, flags); });
       if (err) return 2;
     } else {
       return 1;
@@ -199,10 +152,10 @@ extern "C" int emu_set_metric(int nxb, int nyb, const double *geo /*[10][n]*/, c
   return bad;
 }
 
-// the one-kernel halo update of a single rank (tripole fold): evp_halo_local.cuh on the host-exported plan
-#include "evp_halo_local.cuh"
+// the one-kernel halo update of a single rank (tripole fold): p2p_fold_kernel without peers on the host-exported plan
 extern "C" int emu_halo_local(double *U, double *V, const int *dst, const int *c1, const int *c2, const signed char *code, int n) {
-  if (n > HALO_LOCAL_MAX) return 1;
-  emu::launch({1, 1, 1}, {HALO_LOCAL_THREADS, 1, 1}, [&] { halo_local_kernel(U, V, dst, c1, c2, code, n, 0); });
+  if (n > FOLD_MAX) return 1;
+  static const P2PParams nop2p{};
+  emu::launch({1, 1, 1}, {FOLD_THREADS, 1, 1}, [&] { p2p_fold_kernel(nop2p, U, V, dst, c1, c2, code, n, 0); });
   return 0;
 }

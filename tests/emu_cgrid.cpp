@@ -53,7 +53,7 @@ void common(Host &h, const evp_b200_grid_t *g, const evp_b200_cgrid_t *cg, const
 void zero(double *a, size_t n) { memset(a, 0, n * sizeof(double)); }
 }  // namespace
 
-// form 0: k1..k5; 1: kA<8,4> kB<8,4> k5 (the default); 2: <16,2>; 3: <12,3>; 4: <4,8>; 5: <8,4> with momentum_il_at
+// form 0: k1..k5; 1: kA<8,4> kB<8,4> k5 with momentum_at; 2: <16,2>; 3: <12,3>; 4: <4,8>; 5: <8,4> with momentum_il_at (the default)
 extern "C" int emu_cgrid_run(int form, const evp_b200_grid_t *g, const evp_b200_cgrid_t *cg, const evp_b200_params_t *p, evp_b200_cfields_t *f) {
   if (g->nblocks != 1) return 1;
   Host h;
@@ -83,7 +83,7 @@ extern "C" int emu_cgrid_run(int form, const evp_b200_grid_t *g, const evp_b200_
       constexpr int GBY = decltype(gby)::value, MINB = decltype(minb)::value;
       const emu::Idx bb{GBX, GBY, 1}, gg{(c.nx + 1 + GBX - 2) / (GBX - 1), (c.ny + 1 + GBY - 2) / (GBY - 1), 1};
       emu::launch(gg, bb, [&] { kA_strainU_stressT<GBY, MINB>(c, k); });
-      emu::launch(gg, bb, [&] { kB_stressU_momentum<GBY, MINB>(c, k, cur); });
+      emu::launch(gg, bb, [&] { kB_stressU_momentum<GBY, MINB, false>(c, k, cur); });
     };
     using std::integral_constant;
     switch (form) {
@@ -100,7 +100,7 @@ extern "C" int emu_cgrid_run(int form, const evp_b200_grid_t *g, const evp_b200_
       case 5: {  // interleaved sqrt / division in the momentum step
         const emu::Idx bb{GBX, 8, 1}, gg{(c.nx + 1 + GBX - 2) / (GBX - 1), (c.ny + 1 + 8 - 2) / (8 - 1), 1};
         emu::launch(gg, bb, [&] { kA_strainU_stressT<8, 4>(c, k); });
-        emu::launch(gg, bb, [&] { kB_stressU_momentum<8, 4, false, true>(c, k, cur); });
+        emu::launch(gg, bb, [&] { kB_stressU_momentum<8, 4, true>(c, k, cur); });
         break;
       }
       default: return 1;
@@ -139,10 +139,10 @@ extern "C" int emu_cdgrid_run(const evp_b200_grid_t *g, const evp_b200_cgrid_t *
   const KParams k = kparams(p);
   const emu::Idx b{32, 8, 1}, gU{(c.nx + 31) / 32, (c.ny + 7) / 8, 1}, gT{(c.nx + 1 + 31) / 32, (c.ny + 1 + 7) / 8, 1};
   for (int ks = 0; ks < p->ndte; ++ks) {
-    emu::launch(gT, b, [&] { kcd1_stress_T<false>(c, k); });
-    emu::launch(gU, b, [&] { kcd2_stress_U<false>(c, k); });
-    emu::launch(gU, b, [&] { kcd3_momentum<false>(c, k); });
-    emu::launch(gU, b, [&] { kcd4_interp<false>(c); });
+    emu::launch(gT, b, [&] { kcd1_stress_T(c, k); });
+    emu::launch(gU, b, [&] { kcd2_stress_U(c, k); });
+    emu::launch(gU, b, [&] { kcd3_momentum(c, k); });
+    emu::launch(gU, b, [&] { kcd4_interp(c); });
   }
   return 0;
 }

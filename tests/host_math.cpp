@@ -20,31 +20,10 @@ static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
-static inline double __shfl_sync(unsigned, double v, int, int) { return v; }   // stress_lane (corner-parallel form) is not instantiated here
 
 #include "evp_math.cuh"
 
 using namespace evp;
-
-// 0 = stress_point (one thread per T cell), 1 = lane2_relax + lane2_str (two lanes per T cell, the lanes' exchange done by hand)
-static int g_form = 0;
-extern "C" void host_math_set_form(int form) { g_form = form; }
-
-static void stress_two_lanes(double ucc, double vcc, double uee, double vee, double use_, double vse, double une, double vne, double dxT,
-                             double dyT, double dxhy, double dyhx, double cxp, double cyp, double cxm, double cym, double dmin,
-                             double strength, const KParams &k, Sigma &sg, double (&st)[8]) {
-  Half n = {sg.p[NE], sg.p[NW], sg.m[NE], sg.m[NW], sg.s12[NE], sg.s12[NW]};
-  Half s = {sg.p[SE], sg.p[SW], sg.m[SE], sg.m[SW], sg.s12[SE], sg.s12[SW]};
-  lane2_relax<false>(true, ucc, vcc, uee, vee, use_, vse, une, vne, dxT, dyT, cxp, cyp, cxm, cym, dmin, strength, k, n);
-  lane2_relax<false>(false, use_, vse, une, vne, ucc, vcc, uee, vee, dxT, dyT, cxp, cyp, cxm, cym, dmin, strength, k, s);
-  double on[4], os[4];
-  lane2_str(true, n, s, dxT, dyT, dxhy, dyhx, on);
-  lane2_str(false, s, n, dxT, dyT, dxhy, dyhx, os);
-  sg.p[NE] = n.pE; sg.p[NW] = n.pW; sg.m[NE] = n.mE; sg.m[NW] = n.mW; sg.s12[NE] = n.sE; sg.s12[NW] = n.sW;
-  sg.p[SE] = s.pE; sg.p[SW] = s.pW; sg.m[SE] = s.mE; sg.m[SW] = s.mW; sg.s12[SE] = s.sE; sg.s12[SW] = s.sW;
-  st[0] = on[0]; st[1] = on[1]; st[4] = on[2]; st[6] = on[3];   // str1 str2 str5 str7
-  st[2] = os[0]; st[3] = os[1]; st[5] = os[2]; st[7] = os[3];   // str3 str4 str6 str8
-}
 
 extern "C" int host_math_one_subcycle(int nxb, int nyb, int ilo, int ihi, int jlo, int jhi, const KParams *kp, const int32_t *maskT,
                                       const int32_t *maskU, double *sig /*[12][n]*/, double *u, double *v, const double *geo /*[10][n]*/,
@@ -63,11 +42,7 @@ extern "C" int host_math_one_subcycle(int nxb, int nyb, int ilo, int ihi, int jl
       Sigma sg;
       for (int q = 0; q < 4; ++q) { sg.p[q] = sig[q * n + c]; sg.m[q] = sig[(4 + q) * n + c]; sg.s12[q] = sig[(8 + q) * n + c]; }
       double st[8];
-      if (g_form == 1)
-        stress_two_lanes(u[c], v[c], u[w], v[w], u[s], v[s], u[sw], v[sw], dxT[c], dyT[c], dxhy[c], dyhx[c], cxp[c], cyp[c], cxm[c],
-                         cym[c], dmin[c], strength[c], k, sg, st);
-      else
-        stress_point<false>(u[c], v[c], u[w], v[w], u[s], v[s], u[sw], v[sw], dxT[c], dyT[c], dxhy[c], dyhx[c], cxp[c], cyp[c], cxm[c],
+      stress_point<false>(u[c], v[c], u[w], v[w], u[s], v[s], u[sw], v[sw], dxT[c], dyT[c], dxhy[c], dyhx[c], cxp[c], cyp[c], cxm[c],
                             cym[c], dmin[c], strength[c], k, sg, st);
       for (int q = 0; q < 4; ++q) { sig[q * n + c] = sg.p[q]; sig[(4 + q) * n + c] = sg.m[q]; sig[(8 + q) * n + c] = sg.s12[q]; }
       for (int q = 0; q < 8; ++q) str[q * n + c] = st[q];

@@ -36,7 +36,7 @@ def main():
     dyn_evp.comm_init(rank, world, ids[0])
 
     case = synth.make_case(cfg, block_size=(bsx, bsy), seed=31, ndte=ndte, ns=ns,
-                           kmt="none" if ns == "tripole" else ("continents" if elim else None))
+                           kmt=(None if cfg == "tx1" else "none") if ns == "tripole" else ("continents" if elim else None))
     owner, pg = decomp.cartesian_owner(case.blocks, world)
     if elim:
         for n in range(case.blocks.nblocks_tot):

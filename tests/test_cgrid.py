@@ -108,33 +108,16 @@ def test_cgrid_refused_where_unsupported(evp_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cfg,kw", [("tiny", dict(seed=9)), ("tiny", dict(seed=10, ew="closed", ns="closed")),
-                                    ("tiny", dict(seed=11, visc_method=abi.VISC_AVG_STRENGTH)), ("gx3", dict(ndte=30))],
-                         ids=["tiny", "tiny-closed", "tiny-avgstrength", "gx3"])
-def test_cgrid_cooperative_single_launch(oracle_mod, evp_lib, monkeypatch, cfg, kw):
-    """EVP_B200_CGRID_COOP=1: the whole ndte loop as one cooperative launch with grid barriers."""
-    monkeypatch.setenv("EVP_B200_CGRID_COOP", "1")
-    c = synth.make_ccase(cfg, **kw)
-    ref = run_oracle_c(oracle_mod, c)
-    got = run_gpu_c(evp_lib, c, mode=abi.MODE_EXACT)
-    skip = "etax2U" if c.params["visc_method"] == abi.VISC_AVG_STRENGTH else "strengthU"
-    for n in abi.CFIELDS_INOUT + abi.CFIELDS_OUT:
-        if n != skip:
-            assert np.array_equal(got[n].view(np.int64), ref[n].view(np.int64)), n
-
-
-@pytest.mark.gpu
 @pytest.mark.parametrize("cfg,kw", [("tiny", dict(seed=12)), ("tiny", dict(seed=13, ew="closed", ns="closed")),
                                     ("tiny", dict(seed=14, ew="cyclic", ns="cyclic", kmt="none")),
                                     ("tiny", dict(seed=15, visc_method=abi.VISC_AVG_STRENGTH, block_size=(12, 10))),
                                     ("gx3", dict(ndte=31))],
                          ids=["tiny", "tiny-closed", "tiny-cyclic2", "tiny-avgstrength-4blocks", "gx3-odd"])
-def test_cgrid_five_kernel_form(oracle_mod, evp_lib, monkeypatch, cfg, kw):
-    """EVP_B200_CGRID_FUSED=0: the first correct form, five kernels per subcycle (the default is three: kA, kB, k5)."""
-    monkeypatch.setenv("EVP_B200_CGRID_FUSED", "0")
+def test_cgrid_five_kernel_form(oracle_mod, evp_lib, cfg, kw):
+    """params.kernel = SPLIT: the first correct form, five kernels per subcycle (the default is three: kA, kB, k5)."""
     c = synth.make_ccase(cfg, **kw)
     ref = run_oracle_c(oracle_mod, c)
-    got = run_gpu_c(evp_lib, c, mode=abi.MODE_EXACT)
+    got = run_gpu_c(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_SPLIT)
     skip = "etax2U" if c.params["visc_method"] == abi.VISC_AVG_STRENGTH else "strengthU"
     for n in abi.CFIELDS_INOUT + abi.CFIELDS_OUT:
         if n != skip:
@@ -142,13 +125,9 @@ def test_cgrid_five_kernel_form(oracle_mod, evp_lib, monkeypatch, cfg, kw):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("EVP_B200_TEST_CANDIDATES", "0") != "1",
-                    reason="round-2 candidate: written after the round-1 GPU budget was spent; set EVP_B200_TEST_CANDIDATES=1")
-@pytest.mark.parametrize("shape", ["16", "18", "17", "19", "5"])
-def test_cgrid_fused_with_programmatic_dependent_launch(oracle_mod, evp_lib, monkeypatch, shape):
-    """EVP_B200_CGRID_SHAPE=16/18: kA, kB, k5 chained by programmatic dependent launch (same arithmetic, same tiles); 17/19: also the
-    interleaved square roots / divisions in the momentum step (momentum_il_at); 5: only that, in the default launch form."""
-    monkeypatch.setenv("EVP_B200_CGRID_SHAPE", shape)
+def test_cgrid_fused_form_more_cases(oracle_mod, evp_lib):
+    """the default three-kernel form (kB with the interleaved square roots / divisions of momentum_il_at) on odd loops, doubly cyclic
+    wrap, avg_strength on several blocks, gx3."""
     for cfg, kw in (("tiny", dict(seed=12, ndte=7)), ("tiny", dict(seed=14, ew="cyclic", ns="cyclic", kmt="none")),
                     ("tiny", dict(seed=15, visc_method=abi.VISC_AVG_STRENGTH, block_size=(12, 10))), ("gx3", dict(ndte=31))):
         c = synth.make_ccase(cfg, **kw)
@@ -210,10 +189,9 @@ def test_cgrid_oracle_matches_vectors_from_reference_source(oracle_mod):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fused", ["1", "0"], ids=["three-kernel", "five-kernel"])
-def test_cgrid_gpu_matches_vectors_from_reference_source(evp_lib, monkeypatch, fused):
-    monkeypatch.setenv("EVP_B200_CGRID_FUSED", fused)
-    check_cgrid_against_ref_source_vectors(lambda c: run_gpu_c(evp_lib, c, mode=abi.MODE_EXACT))
+@pytest.mark.parametrize("kernel", [abi.KERNEL_AUTO, abi.KERNEL_SPLIT], ids=["three-kernel", "five-kernel"])
+def test_cgrid_gpu_matches_vectors_from_reference_source(evp_lib, kernel):
+    check_cgrid_against_ref_source_vectors(lambda c: run_gpu_c(evp_lib, c, mode=abi.MODE_EXACT, kernel=kernel))
 
 
 # ---- CD grid ----
@@ -326,16 +304,3 @@ def test_cdgrid_repeat_and_fast_mode(oracle_mod, evp_lib):
             assert np.abs(fast[n] - one[n]).max() / den <= 1e-10, n
     finally:
         evp_lib.dyn_evp_b200_finalize()
-
-
-@pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("EVP_B200_TEST_CANDIDATES", "0") != "1",
-                    reason="round-2 candidate: written after the round-1 GPU budget was spent; set EVP_B200_TEST_CANDIDATES=1")
-def test_cdgrid_with_programmatic_dependent_launch(oracle_mod, evp_lib, monkeypatch):
-    """EVP_B200_CDGRID_PDL=1: the four CD-grid kernels chained by programmatic dependent launch (same kernels, same arithmetic)."""
-    monkeypatch.setenv("EVP_B200_CDGRID_PDL", "1")
-    for cfg, kw in (("tiny", dict(seed=3, ndte=7)), ("tiny", dict(seed=7, ew="cyclic", ns="cyclic", kmt="none")), ("gx3", dict(ndte=15))):
-        c = synth.make_cdcase(cfg, **kw)
-        ref = run_oracle_cd(oracle_mod, c)
-        got = run_gpu_cd(evp_lib, c, mode=abi.MODE_EXACT)
-        _cd_compare(got, ref, c.params)

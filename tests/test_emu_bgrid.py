@@ -5,8 +5,7 @@ out, the inline-PTX helpers of evp_ptx.cuh replaced by their plain C++ meaning) 
 thread of a CTA a host thread (pthread barriers for __syncthreads, counters for named barriers, mailboxes for warp shuffles, GCC
 atomics).  Several subcycles of the ping-pong on one block must equal the oracle bit for bit -- stresses, velocities including the
 on-rank cyclic ghost copies, the last subcycle's diagnostics -- for the split kernels, every selectable form of the fused kernel
-(the default one included), the strip kernel, the four- and two-lanes-per-cell kernels and the in-kernel-halo instantiation
-without peers.  This is the CPU-side check of the kernels' index logic, ownership rules and hand-overs; the hardware's own
+(the default one included) and the in-kernel-halo instantiation without peers.  This is the CPU-side check of the kernels' index logic, ownership rules and hand-overs; the hardware's own
 division / square-root seeds, timing and inter-CTA memory ordering are what the -m gpu tests add."""
 import ctypes as C
 import os
@@ -28,19 +27,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # (kind, sub) of emu_bgrid_run
 KERNELS = {
     "split": (0, 0),
-    "fused-v16": (1, 0), "fused-v17-spec-loads": (1, 1), "fused-v18-cp-async": (1, 2), "fused-v19-both": (1, 3),
-    "fused-v23-default": (1, 4), "fused-v21": (1, 5), "fused-v22": (1, 7), "fused-v31-pair-barriers": (1, 12), "fused-spec-body-plain": (1, 16),
-    "strip-m1": (2, 1), "strip-m2": (2, 2), "strip-m3": (2, 3),
-    "four-lanes": (3, 0),
-    "two-lanes-32x8-shuffle": (4, 0), "two-lanes-16x8-shuffle": (4, 1), "two-lanes-32x4-shuffle": (4, 2), "two-lanes-16x16-shuffle": (4, 3),
-    "two-lanes-32x8-warp-pairs": (4, 4), "two-lanes-32x4-warp-pairs": (4, 5),
-    "two-lanes-32x8-shuffle-IL": (4, 8), "two-lanes-16x8-shuffle-IL": (4, 9), "two-lanes-32x4-shuffle-IL": (4, 10),
-    "two-lanes-16x16-shuffle-IL": (4, 11), "two-lanes-32x8-warp-pairs-IL": (4, 12), "two-lanes-32x4-warp-pairs-IL": (4, 13),
-    "two-lanes-32x8-shuffle-IL-spec": (4, 16), "two-lanes-16x8-shuffle-IL-spec": (4, 17), "two-lanes-32x8-warp-pairs-IL-spec": (4, 18),
-    "two-lanes-32x8-roles-IL": (4, 20), "two-lanes-32x4-roles-IL": (4, 21), "two-lanes-32x8-roles-IL-spec": (4, 22),
+    "fused-spec-loads": (1, 1), "fused-cp-async": (1, 2), "fused-stream": (1, 3),
+    "fused-resident-default": (1, 4), "fused-spec-loads-IL": (1, 5), "fused-stream-IL": (1, 7),
     "p2p-no-peers-edge-first": (5, 0), "p2p-no-peers-no-counter": (5, 1),
-    "two-lanes-p2p-no-peers": (6, 0), "two-lanes-p2p-no-peers-no-counter": (6, 1), "two-lanes-p2p-warp-pairs": (6, 2),
-    "two-lanes-p2p-constant-tiles": (6, 4), "two-lanes-p2p-roles": (6, 8),
 }
 
 
@@ -115,7 +104,7 @@ def test_fast_path_fallbacks_on_the_host(oracle_mod, emu):
     c.fields["strength"][...] *= 1e-300
     ref = c.copy_fields()
     oracle_mod.evp_run_bgrid(c.grid, c.params, ref)
-    for kernel in ("fused-v23-default", "two-lanes-32x8-shuffle-IL"):
+    for kernel in ("fused-resident-default", "fused-stream-IL"):
         got = run_emulated(emu, c, *KERNELS[kernel])
         for nm in abi.STRESS + ("uvel", "vvel", "strintxU", "strintyU", "taubxU", "taubyU"):
             assert np.array_equal(got[nm].view(np.int64), ref[nm][0].view(np.int64)), (kernel, nm)
@@ -162,7 +151,7 @@ def test_post_loop_kernels_on_the_host(oracle_mod, emu):
 
 @pytest.mark.parametrize("case", ["tiny-4sub", "tiny-5sub-revised", "wide-3sub", "doubly-cyclic-3sub", "aligned-32x8-16x16"])
 def test_derived_geometry_kernels_on_the_host(oracle_mod, emu, case):
-    """variants 59 / 63: dxhy, dyhx, cxp, cyp, cxm, cym, DminTarea derived in the kernel from HTN, HTE, dxT, dyT with the reference's
+    """derived-geometry forms: dxhy, dyhx, cxp, cyp, cxm, cym, DminTarea derived in the kernel from HTN, HTE, dxT, dyT with the reference's
     expressions (ice_dyn_shared.F90:384-441).  The device-side check must find no differing cell on the synthetic grids (ghost cells
     outside a closed edge excluded), must notice a perturbed metric array, and the kernels must equal the oracle bit for bit."""
     c = synth.make_case(**CASES[case])
@@ -189,8 +178,7 @@ def test_derived_geometry_kernels_on_the_host(oracle_mod, emu, case):
 
 
 @pytest.mark.parametrize("order", [1, 2], ids=["backwards", "alternating"])
-@pytest.mark.parametrize("kernel", ["fused-v23-default", "fused-v19-both", "strip-m2", "two-lanes-32x8-shuffle-IL", "two-lanes-32x8-warp-pairs-IL-spec",
-                                    "p2p-no-peers-edge-first", "two-lanes-p2p-no-peers"])
+@pytest.mark.parametrize("kernel", ["fused-resident-default", "fused-stream", "p2p-no-peers-edge-first"])
 def test_cta_order_does_not_matter(oracle_mod, emu, kernel, order):
     """the emulation runs the CTAs of a launch one after the other, so a hazard BETWEEN CTAs (one reading what another writes in the
     same launch) would show as a dependence on their order: run them backwards and interleaved from both ends."""
@@ -208,7 +196,7 @@ def test_cta_order_does_not_matter(oracle_mod, emu, kernel, order):
 
 @pytest.mark.parametrize("nx,ny", [(24, 20), (62, 21)])
 def test_local_halo_kernel_on_the_host_equals_the_oracle_halo(oracle_mod, emu, evp_lib, nx, ny):
-    """EVP_B200_HALO_FUSED: pack + apply of the (uvel,vvel) halo as one kernel when every source is on the rank (tripole fold on one
+    """p2p_fold_kernel: the (uvel,vvel) halo update as one kernel when every source is on the rank (tripole fold on one
     GPU).  The kernel text runs on the host-exported plan (evp_b200_halo_plan, the enumeration the GPU exchange is built from) and
     must reproduce the oracle's halo update -- ghost row, symmetrised top row with its signed zeros, pole points."""
     from cice_b200 import dyn_evp

@@ -18,14 +18,11 @@ from tests.util import run_oracle, run_gpu, assert_bitwise, assert_close
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
-# Two lanes per T cell (cice_b200/csrc/evp_lane2.cuh): written at the end of round 1 after the GPU budget was spent.  The kernel text
-# is checked bit for bit against the oracle on the host (tests/test_emu_bgrid.py) but has not run on a GPU yet, so this test is
-# opt-in until it has (EVP_B200_TEST_CANDIDATES=1; scripts/job_r2_candidates.sh runs it first thing in round 2).
-CANDIDATES = pytest.mark.skipif(os.environ.get("EVP_B200_TEST_CANDIDATES", "0") != "1",
-                                reason="round-2 candidate kernels: host-emulated only so far; set EVP_B200_TEST_CANDIDATES=1")
-
-KERNELS = [abi.KERNEL_SPLIT, abi.KERNEL_FUSED, abi.KERNEL_PERSISTENT, abi.KERNEL_QUEUE]
-KNAME = {abi.KERNEL_SPLIT: "split", abi.KERNEL_FUSED: "fused", abi.KERNEL_PERSISTENT: "persistent", abi.KERNEL_QUEUE: "queue"}
+# every kernel strategy of include/evp_b200.h: the reference's two sweeps, the fused kernel in both of its forms (the library picks
+# one from the sub-domain size; both are forced here), the on-chip persistent kernel
+KERNELS = [abi.KERNEL_SPLIT, abi.KERNEL_FUSED, abi.KERNEL_FUSED_STREAM, abi.KERNEL_FUSED_RESIDENT, abi.KERNEL_PERSISTENT]
+KNAME = {abi.KERNEL_SPLIT: "split", abi.KERNEL_FUSED: "fused", abi.KERNEL_FUSED_STREAM: "fused-stream",
+         abi.KERNEL_FUSED_RESIDENT: "fused-resident", abi.KERNEL_PERSISTENT: "persistent"}
 
 
 @pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
@@ -155,7 +152,7 @@ def test_large_grid_properties(evp_lib):
     # the on-chip persistent kernel cannot hold 7300 cells per SM: it must refuse, not fall back silently
     with pytest.raises(evp_lib.EvpB200Error, match="persistent kernel unavailable"):
         run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_PERSISTENT)
-    outs = [run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=k) for k in (abi.KERNEL_SPLIT, abi.KERNEL_FUSED, abi.KERNEL_QUEUE, abi.KERNEL_AUTO)]
+    outs = [run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=k) for k in (abi.KERNEL_SPLIT, abi.KERNEL_FUSED, abi.KERNEL_FUSED_RESIDENT, abi.KERNEL_AUTO)]
     for o in outs[1:]:
         assert_bitwise(o, outs[0])
     o = outs[0]
@@ -194,11 +191,14 @@ def test_tx1_tripole_full(oracle_mod, evp_lib):
     ["gx3", "50", "58", "15", "split"],
     ["tiny", "12", "10", "16", "fused", "tripole"],
     ["gx3", "10", "10", "20", "fused", "-", "elim"],
-], ids=["gx3-16blocks-fused", "gx3-4blocks-split", "tiny-tripole", "gx3-land-blocks-eliminated"])
+    ["tx1", "90", "60", "60", "fused", "tripole"],
+    ["tx1", "45", "40", "25", "split", "tripole"],
+], ids=["gx3-16blocks-fused", "gx3-4blocks-split", "tiny-tripole", "gx3-land-blocks-eliminated", "tx1-tripole-fused", "tx1-tripole-split"])
 def test_multi_gpu_halo(args, p2p):
     """N>1: one process per GPU; the (uvel,vvel) halo goes either through in-kernel NVLink stores into the
-    neighbours' ghost cells (default for the fused kernel) or through the staged NCCL send/recv exchange
-    (split kernel, tripole fold, EVP_B200_P2P=0).  Bit-identical to the oracle either way.
+    neighbours' ghost cells (default for the fused kernel; across a tripole fold the values arrive negated or as raw
+    operands that the receiving rank's fold kernel combines) or through the staged NCCL send/recv exchange
+    (split kernel, EVP_B200_P2P=0).  Bit-identical to the oracle either way.
     Runs when the box exposes at least 2 GPUs (gpurun --gpus 2); the 1-GPU round-end run skips it."""
     import subprocess
     import sys
@@ -213,7 +213,7 @@ def test_multi_gpu_halo(args, p2p):
            "--master-port", "29611", os.path.join(root, "tests", "mgpu_check.py")] + args
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, EVP_B200_P2P=p2p))
     assert "MGPU PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
-    if p2p == "1" and args[4] == "fused" and (len(args) < 6 or args[5] == "-"):
+    if p2p == "1" and args[4] == "fused":
         assert "in-kernel NVLink stores" in r.stdout, r.stdout[-2000:]
 
 
@@ -255,7 +255,6 @@ def test_deformations_after_loop(oracle_mod, evp_lib, bs):
         assert (got[n][ref["iceTmask"] == 0] == -7.0).all(), n
 
 
-@CANDIDATES
 @pytest.mark.parametrize("bs", [None, (25, 29)], ids=["1block", "16blocks"])
 def test_dyn_finish_after_loop(oracle_mod, evp_lib, bs):
     """next row: `dyn_finish` (ice_dyn_shared.F90:1291-1365) from the velocities and U-point inputs the loop left
@@ -314,32 +313,10 @@ def test_edge_cases_no_ice_and_odd_loops(oracle_mod, evp_lib, kernel):
     assert_bitwise(g1, ref)
 
 
-# every form of the fused kernel that can be selected (EVP_B200_FUSED_VARIANT, read in evp_b200_init): 16 = round-1 form,
-# 17 = speculative T-cell loads, 19 = + cp.async momentum operands (default on sub-domains larger than L2),
-# 23 = interleaved IEEE division / square root (default on L2-resident sub-domains), 21/22 combinations, 30 = strip
-@pytest.mark.parametrize("variant,extra", [("16", {}), ("17", {}), ("18", {}), ("19", {}), ("21", {}), ("22", {}), ("23", {}),
-                                           ("30", {"EVP_B200_STRIP_M": "1"}), ("30", {"EVP_B200_STRIP_M": "2"}),
-                                           ("30", {"EVP_B200_STRIP_M": "3"})],
-                         ids=["v16", "v17", "v18", "v19", "v21", "v22", "v23", "strip1", "strip2", "strip3"])
-def test_fused_variants_bitwise(oracle_mod, evp_lib, monkeypatch, variant, extra):
-    monkeypatch.setenv("EVP_B200_FUSED_VARIANT", variant)
-    for k, v in extra.items():
-        monkeypatch.setenv(k, v)
-    cases = [synth.make_case("tiny", seed=11, block_size=(12, 10), ndte=9),
-             synth.make_case("tiny", seed=12, revised_evp=True),
-             synth.make_case("tiny", seed=13, ew="closed", ns="closed", kmt="boxislands"),
-             synth.make_case("gx3", seed=14, ndte=25),
-             synth.make_case("tiny", seed=15, ns="tripole", ew="cyclic", kmt="none", ndte=12)]
-    for c in cases:
-        ref = run_oracle(oracle_mod, c)
-        got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED)
-        assert_bitwise(got, ref)
-
-
-@CANDIDATES
-@pytest.mark.parametrize("variant", ["40", "41", "42", "43", "44", "45", "46", "47", "48", "49", "50", "51", "52", "53", "54", "55", "56"])
-def test_two_lane_variants(oracle_mod, evp_lib, monkeypatch, variant):
-    monkeypatch.setenv("EVP_B200_FUSED_VARIANT", variant)
+@pytest.mark.parametrize("kernel", [abi.KERNEL_FUSED_STREAM, abi.KERNEL_FUSED_RESIDENT], ids=KNAME.get)
+def test_fused_forms_bitwise(oracle_mod, evp_lib, kernel):
+    """both forms of the fused kernel on block decompositions, revised EVP, closed boundaries, gx3, a tripole fold, operands that
+    push the interleaved division / square root onto their fallbacks; fast mode within the floating-point tolerance."""
     cases = [synth.make_case("tiny", seed=11, block_size=(12, 10), ndte=9),
              synth.make_case("tiny", seed=12, revised_evp=True),
              synth.make_case("tiny", seed=13, ew="closed", ns="closed", kmt="boxislands"),
@@ -348,26 +325,21 @@ def test_two_lane_variants(oracle_mod, evp_lib, monkeypatch, variant):
              synth.make_case("tiny", seed=15, ns="tripole", ew="cyclic", kmt="none", ndte=12)]
     for c in cases:
         ref = run_oracle(oracle_mod, c)
-        got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED)
+        got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=kernel)
         assert_bitwise(got, ref)
-    # zero and denormal-range operands: the fast paths of the interleaved division / square root must fall back
     c = synth.make_case("tiny", seed=21, ndte=6)
     for n in ("uvel", "vvel", "uocnU", "vocnU", "forcexU", "forceyU", "waterxU", "wateryU"):
         c.fields[n][...] = 0.0
     c.fields["strength"][...] *= 1e-300
-    assert_bitwise(run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED), run_oracle(oracle_mod, c))
-    # fast mode: within the floating-point tolerance of the other fast kernels
+    assert_bitwise(run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=kernel), run_oracle(oracle_mod, c))
     c = synth.make_case("gx3")
-    assert_close(run_gpu(evp_lib, c, mode=abi.MODE_FAST, kernel=abi.KERNEL_FUSED), run_oracle(oracle_mod, c), TOL)
+    assert_close(run_gpu(evp_lib, c, mode=abi.MODE_FAST, kernel=kernel), run_oracle(oracle_mod, c), TOL)
 
 
-@CANDIDATES
-@pytest.mark.parametrize("variant", ["59", "63"])
-def test_derived_geometry_variants(oracle_mod, evp_lib, monkeypatch, variant):
-    """EVP_B200_FUSED_VARIANT=59|63 after evp_b200_set_metric: seven geometry arrays derived in the kernel from HTN, HTE (two arrays
+def test_derived_geometry(oracle_mod, evp_lib):
+    """the HBM-streaming form after evp_b200_set_metric: seven geometry arrays derived in the kernel from HTN, HTE (two arrays
     read instead of seven).  The device-side check must accept the synthetic metric arrays, reject a perturbed one (the kernels then
     keep reading the arrays), and the results stay bit-identical either way.  Host-emulated in tests/test_emu_bgrid.py."""
-    monkeypatch.setenv("EVP_B200_FUSED_VARIANT", variant)
     cases = [synth.make_case("tiny", seed=11, block_size=(12, 10), ndte=9), synth.make_case("tiny", seed=12, revised_evp=True),
              synth.make_case("tiny", seed=13, ew="closed", ns="closed", kmt="boxislands"), synth.make_case("gx3", seed=14, ndte=25),
              synth.make_case("tiny", seed=15, ns="tripole", ew="cyclic", kmt="none", ndte=12)]
@@ -384,27 +356,30 @@ def test_derived_geometry_variants(oracle_mod, evp_lib, monkeypatch, variant):
                 bad = evp_lib.set_metric(h, HTE, 1e-11)
                 tripole = c.grid["ns_boundary_type"] == abi.BNDY_NAMES["tripole"]
                 assert (bad > 0) == (perturb or tripole), (n, perturb, bad)     # the tripole ghost row holds sign-flipped dxhy, dyhx
-                evp_lib.dyn_evp_b200_run(dict(c.params, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED), f)
+                assert ("derived geometry available" in evp_lib.describe()) == (bad == 0)
+                evp_lib.dyn_evp_b200_run(dict(c.params, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED_STREAM), f)
             finally:
                 evp_lib.dyn_evp_b200_finalize()
             assert_bitwise(f, ref)
 
 
-@CANDIDATES
-@pytest.mark.parametrize("mode", ["1", "2"], ids=["one-kernel", "one-kernel-pdl"])
-def test_tripole_fold_as_one_kernel(oracle_mod, evp_lib, monkeypatch, mode):
-    """EVP_B200_HALO_FUSED=1|2: on one rank the tripole fold runs as one kernel (evp_halo_local.cuh) instead of pack + apply, with
-    mode 2 inside the programmatic-dependent-launch chain.  Host-emulated against the oracle's halo in tests/test_emu_bgrid.py."""
-    monkeypatch.setenv("EVP_B200_HALO_FUSED", mode)
+@pytest.mark.parametrize("p2p", ["1", "0"], ids=["fold-kernel", "pack-apply"])
+def test_tripole_fold_one_rank_both_forms(oracle_mod, evp_lib, monkeypatch, p2p):
+    """on one rank every source of the tripole fold is local: the halo update after each subcycle kernel is ONE kernel
+    (p2p_fold_kernel) -- or, with EVP_B200_P2P=0, the staged pack + apply pair the multi-rank NCCL fallback uses."""
+    monkeypatch.setenv("EVP_B200_P2P", p2p)
     for c in (synth.make_case("tiny", seed=15, ns="tripole", ew="cyclic", kmt="none", ndte=12),
               synth.make_case("tiny", nx=62, ny=21, seed=16, ns="tripole", ew="cyclic", kmt="none", ndte=7),
               synth.make_case("tx1", ndte=30)):
         ref = run_oracle(oracle_mod, c)
         for kernel in (abi.KERNEL_FUSED, abi.KERNEL_SPLIT):
-            assert_bitwise(run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=kernel), ref)
+            got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=kernel)
+            for n in ("uvel", "vvel"):   # name the cells: a sign-of-zero slip shows up as max|d| = 0
+                d = np.argwhere(got[n].view(np.int64) != ref[n].view(np.int64))
+                assert len(d) == 0, (n, kernel, c.grid["nx_global"], d[:8].tolist(), [(got[n][tuple(q)], ref[n][tuple(q)]) for q in d[:8]])
+            assert_bitwise(got, ref)
 
 
-@CANDIDATES
 def test_pinning_the_callers_arrays(oracle_mod, evp_lib):
     """evp_b200_pin_host / evp_b200_unpin_host: page-locking pageable caller arrays (what Fortran allocatables are) changes the copy
     rate, not the result; pinning twice and unpinning an array that was never pinned are accepted."""
@@ -426,16 +401,15 @@ def test_pinning_the_callers_arrays(oracle_mod, evp_lib):
     assert_bitwise(f, ref)
 
 
-def test_interleaved_divsqrt_hits_the_fallback(oracle_mod, evp_lib, monkeypatch):
+def test_interleaved_divsqrt_hits_the_fallback(oracle_mod, evp_lib):
     """operands outside the fast path of the hand-scheduled division / square root (zero and denormal-range
     strain rates and numerators: ice at rest, zero forcing) must take the built-in operators and stay bit-identical."""
-    monkeypatch.setenv("EVP_B200_FUSED_VARIANT", "23")
     c = synth.make_case("tiny", seed=21, ndte=6)
     for n in ("uvel", "vvel", "uocnU", "vocnU", "forcexU", "forceyU", "waterxU", "wateryU"):
         c.fields[n][...] = 0.0
     c.fields["strength"][...] *= 1e-300  # Delta = 0 -> dmin branch; tiny numerators -> slow-path range test
     ref = run_oracle(oracle_mod, c)
-    got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED)
+    got = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED_RESIDENT)
     assert_bitwise(got, ref)
 
 

@@ -32,11 +32,9 @@ def host_math(tmp_path_factory):
     return C.CDLL(out)
 
 
-@pytest.mark.parametrize("form", [0, 1], ids=["cell", "two-lanes"])
 @pytest.mark.parametrize("kw", [dict(seed=121), dict(seed=122, revised_evp=True), dict(), dict(seed=123, kmt="continents")],
                          ids=["S2", "S2-revised", "S1", "S2-continents"])
-def test_device_math_on_the_host_equals_the_oracle(oracle_mod, host_math, kw, form):
-    host_math.host_math_set_form(form)
+def test_device_math_on_the_host_equals_the_oracle(oracle_mod, host_math, kw):
     c = synth.make_case("tiny", ndte=1, **kw)
     if kw.get("seed") == 121:
         c.params.update(capping=0.0, Ktens=0.2, cosw=0.9, sinw=0.4358898943540674)   # general branches too

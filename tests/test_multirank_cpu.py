@@ -150,6 +150,121 @@ def test_halo_plan_two_processes_gloo(ew, ns, world):
         assert bad == 0, f"rank {rank}: {bad} cells differ from the oracle halo ({n} plan entries)"
 
 
+def _worker_push(rank, world, port, ew, ns, cfg, bs, q):
+    """the in-kernel NVLink form of the halo on numpy arrays: every rank executes ITS push list (stores into other ranks' arrays,
+    here delivered through gloo), then its fold list (all sources read before any destination is written)."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from cice_b200 import abi, decomp, dyn_evp, synth
+    from oracle import oracle
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        kmt = "boxislands" if ns == "tripole" else "none"
+        case = synth.make_case(cfg, block_size=bs, seed=21, ew=ew, ns=ns, kmt=kmt)
+        owner, _ = decomp.cartesian_owner(case.blocks, world)
+        rects = _rects(case, owner, world)
+        ewi, nsi = case.grid["ew_boundary_type"], case.grid["ns_boundary_type"]
+        nxg, nyg = case.grid["nx_global"], case.grid["ny_global"]
+        whole = synth.make_case(cfg, seed=21, ew=ew, ns=ns, kmt=kmt)
+        tu, tv = whole.fields["uvel"].copy(), whole.fields["vvel"].copy()
+        for a in (tu, tv):
+            a[0, 0, :] = a[0, -1, :] = np.nan
+            a[0, :, 0] = a[0, :, -1] = np.nan
+        oracle.halo_update(whole.grid, [tu, tv], field_loc=1, field_type=1)
+
+        gi0, gj0, nx, ny = rects[rank]
+        ld = dyn_evp.dom_pitch(nx)
+        assert dyn_evp.dom_cells(nx, ny) == ld * (ny + 4)
+        X = whole.X
+        dom = {}
+        for name in ("uvel", "vvel"):
+            a = np.full((ny + 4, ld), np.nan)      # ghost ring + the two staging rows
+            a[1:ny + 1, 1:nx + 1] = X[name][gj0:gj0 + ny, gi0:gi0 + nx]
+            dom[name] = a.reshape(-1)
+        wrap_ew = ewi == abi.BNDY_CYCLIC and nx == nxg
+        wrap_ns = nsi == abi.BNDY_CYCLIC and ny == nyg
+        for name in ("uvel", "vvel"):
+            a = dom[name].reshape(ny + 4, ld)
+            if wrap_ew:
+                a[1:ny + 1, 0], a[1:ny + 1, nx + 1] = a[1:ny + 1, nx].copy(), a[1:ny + 1, 1].copy()
+            if wrap_ns:
+                a[0, 1:nx + 1], a[ny + 1, 1:nx + 1] = a[ny, 1:nx + 1].copy(), a[1, 1:nx + 1].copy()
+            if wrap_ew and wrap_ns:
+                a[0, 0], a[0, nx + 1], a[ny + 1, 0], a[ny + 1, nx + 1] = a[ny, nx], a[ny, 1], a[1, nx], a[1, 1]
+
+        push, fold = dyn_evp.p2p_plan(rects, rank, nxg, nyg, ewi, nsi)
+        tripole_top = nsi == abi.BNDY_TRIPOLE and gj0 + ny - 1 == nyg
+        outbox = {r: [] for r in range(world)}
+        for src, dr, dst, neg in push:
+            i, j = src % ld, src // ld
+            # the kernel's push condition: boundary points, and row ny-1 below a tripole fold
+            assert i in (1, nx) or j in (1, ny) or (tripole_top and j == ny - 1), (i, j)
+            assert dr != rank
+            sgn = -1.0 if neg else 1.0
+            outbox[int(dr)].append((int(dst), sgn * dom["uvel"][src], sgn * dom["vvel"][src]))
+        boxes = [None] * world
+        dist.all_gather_object(boxes, outbox)
+        for r in range(world):
+            for dst, u, v in boxes[r][rank]:
+                dom["uvel"][dst], dom["vvel"][dst] = u, v
+        staged = []
+        for dst, c1, c2, op in fold:
+            staged.append((dst, op, (dom["uvel"][c1], dom["vvel"][c1]), (dom["uvel"][c2], dom["vvel"][c2])))
+        for dst, op, a, b in staged:
+            if op == 0:
+                u, v = a
+            elif op == 1:
+                u, v = -a[0], -a[1]
+            elif op == 2:
+                u, v = 0.5 * (a[0] - b[0]), 0.5 * (a[1] - b[1])
+            else:
+                u, v = -(0.5 * (a[0] - b[0])), -(0.5 * (a[1] - b[1]))
+            dom["uvel"][dst], dom["vvel"][dst] = u, v
+
+        bad = 0
+        for name, truth in (("uvel", tu[0]), ("vvel", tv[0])):
+            a = dom[name].reshape(ny + 4, ld)
+            for dj in range(ny + 2):
+                for di in range(nx + 2):
+                    gi, gj = gi0 + di - 1, gj0 + dj - 1
+                    if ewi == abi.BNDY_CYCLIC:
+                        gi = (gi - 1) % nxg + 1
+                    if nsi == abi.BNDY_CYCLIC:
+                        gj = (gj - 1) % nyg + 1
+                    if 0 <= gi <= nxg + 1 and 0 <= gj <= nyg + 1:
+                        want, got = truth[gj, gi], a[dj, di]
+                        ok = np.isnan(got) if np.isnan(want) else ((got == want) and (np.signbit(got) == np.signbit(want)))
+                        bad += 0 if ok else 1
+        q.put((rank, bad, len(push) + len(fold)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ew,ns,cfg,bs", [("cyclic", "closed", "tiny", (12, 10)), ("cyclic", "cyclic", "tiny", (12, 10)),
+                                          ("cyclic", "tripole", "tiny", (12, 10)), ("cyclic", "tripole", "tiny", (6, 5)),
+                                          ("cyclic", "tripole", "tx1", (90, 60))],
+                         ids=["cyclic-closed", "cyclic-cyclic", "tripole", "tripole-small-blocks", "tx1-tripole"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_push_and_fold_plan_gloo(ew, ns, cfg, bs, world):
+    """the halo without a staged exchange (in-kernel NVLink stores + fold kernel, configs[3]): push lists and fold lists of
+    evp_b200_p2p_plan executed by 2 and 4 gloo processes reproduce the oracle's halo update, signed zeros included."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() * 7 + hash((ew, ns, cfg, bs, world))) % 2000
+    procs = [ctx.Process(target=_worker_push, args=(r, world, port, ew, ns, cfg, bs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, bad, n in res:
+        assert bad == 0, f"rank {rank}: {bad} cells differ from the oracle halo ({n} plan entries)"
+        assert n > 0
+
+
 def test_halo_plan_single_rank_is_empty_without_tripole():
     from cice_b200 import abi, dyn_evp
     for ew, ns in ((abi.BNDY_CYCLIC, abi.BNDY_CLOSED), (abi.BNDY_CYCLIC, abi.BNDY_CYCLIC), (abi.BNDY_CLOSED, abi.BNDY_OPEN)):
