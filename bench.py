@@ -1,23 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- EVP grid-cells x subcycles / s (fp64) and the HBM-roofline fraction of the subcycle kernel.
+"""bench.py -- EVP grid-cells x subcycles / s (fp64) and the roofline fraction of the subcycle kernel.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--kernel auto|split|fused|persistent] [--mode fast|exact] [--workload gx1|gx3|p1deg]
+                    [--workload gx1|gx3|tx1|p1deg] [--layout weak|strong] [--sub NXxNY]
+                    [--kernel auto|split|fused|stream|resident|persistent] [--mode exact|fast] [--grid B|C]
 
 A "step" is one dynamics step of the hot path: the whole `do ksub = 1,ndte` loop of
 ice_dyn_evp.F90:859-913 over one synthetic box2001 state.
   N = 1 : configs[1] of BASELINE.json -- gx1 320x384 B grid, ndte = 240, one block, one GPU.
-  N > 1 : weak scaling -- every GPU owns one gx1-sized sub-domain (320x384) of a (px*320)x(py*384)
-          cyclic/closed domain; (uvel,vvel) halo exchanged every subcycle.
+  N > 1 : --layout weak (default for gx1/gx3): every GPU owns one sub-domain of --sub cells (default: the workload's own size) of a
+          (px*nx) x (py*ny) domain;  --layout strong (default for tx1, p1deg): the workload's global grid is cut into px x py
+          rectangles (configs[3]: tx1 360x240 tripole on 2x2; configs[4]: 3600x2400 on 4x2).  (uvel,vvel) halo every subcycle.
+`parity`  untimed pre-check, every N: the bench's own decomposition at reduced ndte through the C ABI against the CPU oracle
+          (exact build) run by rank 0 on the undecomposed grid; sha256 per field per rank, i.e. bit for bit.
 `value`   device-resident: fields are uploaded once, the timed region is K subcycle loops
-          (CUDA events on the library's stream, per step, L2 flushed between steps).
-`e2e`     the same metric through evp_b200_run_bgrid with HOST buffers (pinned), H2D + loop + D2H timed.
+          (CUDA events on the library's stream, per step, L2 flushed and all ranks aligned before each step).
+`e2e`     the same metric through the C ABI with HOST buffers (pinned), H2D + loop + D2H timed;
+          `e2e_pageable`: the same call from plain pageable numpy arrays, and after evp_b200_pin_host (what the Fortran shim does).
 `roofline` algorithmic bytes (360 B per cell-subcycle) / measured duration of the
-          subcycle kernel vs the measured HBM peak of MEASURED_PEAKS.json.
+          subcycle kernel vs the measured HBM peak of MEASURED_PEAKS.json; beside it the fp64-pipe ceiling that binds at gx1.
 `cpu_baseline` / `--impl reference`: the CPU restatement of the reference loops (oracle, "port": the
           Fortran reference cannot be built in this image) on the box's host cores.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -29,20 +35,19 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line (the image sets NCCL_DEBUG=VERSION)
 
 ALGO_BYTES_PER_CELL_SUBCYCLE = 360.0  # 31 doubles read + 14 written
 METRIC = "EVP grid-cells*subcycles/sec at gx1 (fp64)"
 UNIT = "cell-subcycles/s"
+PARITY_NDTE = 24
 
 
-def measured_traffic(kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json)."""
+def kernel_counters(kernel):
+    """ncu counters of the dominant kernel per launch (profiles/traffic.json, from the committed --set full captures)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             t = json.load(fh)
-        e = t.get(kernel) or t.get("fused")
-        return e
+        return t.get(kernel) or t.get("fused")
     except Exception:
         return None
 
@@ -93,18 +98,40 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_case(workload, world, rank, ndte=None):
+def layout_of(args):
+    return args.layout or ("strong" if args.workload in ("tx1", "p1deg") else "weak")
+
+
+def geometry(args, world):
+    """(global nx, ny), (block nx, ny) = one rank's rectangle, processor grid"""
     from cice_b200 import decomp, synth
+    base = synth.CONFIGS[args.workload]
+    px, py = decomp.proc_grid(world, world, world) if world > 1 else (1, 1)
+    if layout_of(args) == "weak" or world == 1:
+        sx, sy = (int(v) for v in args.sub.lower().split("x")) if args.sub else (base["nx"], base["ny"])
+        return (sx * px, sy * py), (sx, sy), (px, py)
+    nx, ny = base["nx"], base["ny"]
+    if nx % px or ny % py:
+        raise SystemExit(f"--layout strong: {nx}x{ny} does not split into {px}x{py} equal rectangles")
+    return (nx, ny), (nx // px, ny // py), (px, py)
+
+
+def build_case(args, world, rank, ndte=None):
+    from cice_b200 import decomp, synth
+    (nx, ny), (sx, sy), (px, py) = geometry(args, world)
+    c = synth.make_case(args.workload, nx=nx, ny=ny, block_size=(sx, sy), ndte=ndte)
     if world == 1:
-        c = synth.make_case(workload, ndte=ndte)
-        return c, c.grid, c.fields, (1, 1)
-    base = synth.CONFIGS[workload]
-    px, py = decomp.proc_grid(world, world, world)
-    nx, ny = base["nx"] * px, base["ny"] * py
-    c = synth.make_case(workload, nx=nx, ny=ny, block_size=(base["nx"], base["ny"]), ndte=ndte)
+        return c, c.grid, c.fields, np.arange(c.blocks.nblocks_tot), (px, py)
     owner, _ = decomp.cartesian_owner(c.blocks, world)
     g, f, ids = c.rank_view(owner, rank)
-    return c, g, f, (px, py)
+    return c, g, f, ids, (px, py)
+
+
+def workload_string(args, world, ndte):
+    (nx, ny), (sx, sy), (px, py) = geometry(args, world)
+    bnd = "tripole" if args.workload == "tx1" else "cyclic/closed"
+    return (f"{args.workload} {sx}x{sy} per GPU, B-grid EVP ndte={ndte}, {px}x{py} GPUs, global {nx}x{ny} ({bnd}), "
+            f"box2001 synthetic, {layout_of(args) if world > 1 else 'single'} layout")
 
 
 def pin(fields):
@@ -133,36 +160,90 @@ def cpu_baseline(case, steps, warmup, nthreads=0):
     return float(np.mean(ts)), nthreads
 
 
+def cpu_blocks(args, nx, ny):
+    """the reference's own block choice for <=16 PEs at gx1 is 40x48 (configuration/scripts/cice_decomp.csh:93-96)"""
+    if args.workload == "gx1":
+        return (40, 48)
+    if args.workload == "tx1":
+        return (45, 40)
+    if args.workload == "p1deg":
+        return (100, 100)
+    return (max(nx // 8, 8), max(ny // 8, 8))
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (restated; see module docstring) on the host cores, on the
-    same global grid as our arm at this GPU count (weak scaling: px*320 x py*384)."""
+    same global grid as our arm at this GPU count."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from cice_b200 import decomp, synth
-    wl = args.workload
-    base = synth.CONFIGS[wl]
+    from cice_b200 import synth
     world = max(int(os.environ.get("WORLD_SIZE", "1")), args.gpus, 1)
-    px, py = decomp.proc_grid(world, world, world)
-    nx, ny = base["nx"] * px, base["ny"] * py
-    # the reference's own block choice for <=16 PEs at gx1 is 40x48 (configuration/scripts/cice_decomp.csh:93-96)
-    bs = (40, 48) if wl == "gx1" else (max(base["nx"] // 8, 8), max(base["ny"] // 8, 8))
-    case = synth.make_case(wl, nx=nx, ny=ny, block_size=bs)
+    (nx, ny), _, _ = geometry(args, world)
+    bs = cpu_blocks(args, nx, ny)
+    # a bounded sample: full dynamics steps while the grid is small, fewer subcycles of the same step on the 0.1-degree grid
+    ndte_full = synth.CONFIGS[args.workload]["ndte"]
+    ndte = ndte_full if nx * ny <= 1280 * 768 else 12
+    case = synth.make_case(args.workload, nx=nx, ny=ny, block_size=bs, ndte=ndte)
+    case.params.update(synth.evp_params(ndte_full), ndte=ndte)   # constants of the full loop, fewer subcycles
     sec, nth = cpu_baseline(case, args.steps, max(args.warmup, 1))
-    cells = nx * ny * case.params["ndte"]
-    val = cells / sec
+    val = nx * ny * ndte / sec
+    sample = (f"{args.steps} full dynamics step(s) of the {nx}x{ny} grid, ndte={ndte}" if ndte == ndte_full else
+              f"{args.steps} x the first {ndte} of {ndte_full} subcycles of one dynamics step of the {nx}x{ny} grid")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{wl} {base['nx']}x{base['ny']} per GPU, B-grid EVP ndte={case.params['ndte']}, "
-                                   f"{px}x{py} GPUs, global {nx}x{ny}, box2001 synthetic",
+            "warmup": args.warmup, "ms_per_step": sec * 1e3 * ndte_full / ndte, "higher_is_better": True,
+            "scaling": layout_of(args) if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_string(args, world, ndte_full),
                        "cpu": f"CPU restatement of the reference loops (oracle port, -O3 AVX2/FMA, OpenMP over {bs[0]}x{bs[1]} blocks); "
                               "the Fortran reference cannot be built in this image"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": nth, "kind": "port",
-                             "sample": f"{args.steps} full dynamics step(s) of the {nx}x{ny} grid, ndte={case.params['ndte']}"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def parity_precheck(args, dyn_evp, abi, dist, world, rank, params, case, grid, fields):
+    """untimed: the bench's own decomposition, PARITY_NDTE subcycles with the constants of the full loop, through evp_b200_run_bgrid;
+    rank 0 runs the oracle (exact build) on the undecomposed grid and every rank compares sha256 digests of its 18 inout arrays."""
+    import torch
+    t0 = time.perf_counter()
+    p = dict(params, ndte=PARITY_NDTE)
+    got = {k: v.copy() for k, v in fields.items()}
+    dyn_evp.dyn_evp_b200_init(grid)
+    try:
+        dyn_evp.dyn_evp_b200_run(p, got)
+        desc = dyn_evp.describe()
+    finally:
+        dyn_evp.dyn_evp_b200_finalize()
+    want = [None]
+    if rank == 0:
+        from cice_b200 import decomp
+        from oracle import oracle
+        oracle.build()
+        ref = case.copy_fields()
+        oracle.evp_run_bgrid(case.grid, dict(case.params, ndte=PARITY_NDTE), ref, nthreads=os.cpu_count() or 1, variant="exact")
+        if world > 1:
+            owner, _ = decomp.cartesian_owner(case.blocks, world)
+            want[0] = [{n: digest(ref[n][np.nonzero(owner == r)[0]]) for n in abi.FIELDS_INOUT} for r in range(world)]
+        else:
+            want[0] = [{n: digest(ref[n]) for n in abi.FIELDS_INOUT}]
+    if world > 1:
+        dist.broadcast_object_list(want, src=0)
+    bad = [n for n in abi.FIELDS_INOUT if digest(got[n]) != want[0][rank][n]]
+    nbad = len(bad)
+    if world > 1:
+        t = torch.tensor([nbad], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        nbad = int(t.item())
+    (nx, ny), (sx, sy), (px, py) = geometry(args, world)
+    return {"ok": nbad == 0, "bitwise": True, "mismatching_arrays": nbad, "arrays_per_rank": len(abi.FIELDS_INOUT), "ranks": world,
+            "case": f"{args.workload} global {nx}x{ny} as {px}x{py} rectangles of {sx}x{sy}, first {PARITY_NDTE} subcycles of the step, "
+                    f"mode {args.mode}", "checker": "CPU oracle (exact build) on the undecomposed grid, sha256 per array per rank",
+            "first_bad": bad[:3], "halo": desc.split("p2p: ")[-1], "seconds": round(time.perf_counter() - t0, 2)}
 
 
 def run_ours(args):
@@ -181,23 +262,23 @@ def run_ours(args):
         dist.broadcast_object_list(ids, src=0)
         dyn_evp.comm_init(rank, world, ids[0])
 
-    case, grid, fields, (px, py) = build_case(args.workload, world, rank)
-    base = synth.CONFIGS[args.workload]
+    case, grid, fields, bids, (px, py) = build_case(args, world, rank)
+    (nxg, nyg), (sx, sy), _ = geometry(args, world)
     params = dict(case.params, mode=abi.MODE_FAST if args.mode == "fast" else abi.MODE_EXACT,
                   kernel=abi.KERNEL_NAMES[args.kernel])
     ndte = params["ndte"]
-    cells_global = base["nx"] * px * base["ny"] * py
+    cells_global = nxg * nyg
+
+    parity = None
+    if not args.no_parity:
+        parity = parity_precheck(args, dyn_evp, abi, dist, world, rank, params, case, grid, fields) if args.mode == "exact" else \
+            {"ok": None, "note": "fast mode is not bit-identical by construction (FMA contraction); see tests for its tolerance checks"}
+
     dyn_evp.dyn_evp_b200_init(grid)
-    if os.environ.get("EVP_B200_FUSED_VARIANT") in ("59", "63"):
-        # derived-geometry kernels (round-2 candidate): hand over HTN, HTE; the library checks them bit for bit on the device
-        from cice_b200 import decomp
-        sel = slice(None)
-        if world > 1:
-            owner, _ = decomp.cartesian_owner(case.blocks, world)
-            sel = case.rank_view(owner, rank)[2]
-        bad = dyn_evp.set_metric(synth.scatter(case.X["HTN"], case.blocks)[sel], synth.scatter(case.X["HTE"], case.blocks)[sel], 1e-11)
-        if rank == 0:
-            print(f"# set_metric: {bad} cells differ", file=sys.stderr)
+    # the metric arrays behind the derived geometry (evp_b200_set_metric, what the Fortran shim hands over in its init): the
+    # library verifies them bit for bit on the device; the HBM-streaming form then reads two arrays instead of seven
+    bad = dyn_evp.set_metric(synth.scatter(case.X["HTN"], case.blocks)[bids], synth.scatter(case.X["HTE"], case.blocks)[bids],
+                             case.params["deltaminEVP"])
     desc = dyn_evp.describe()
 
     hf = pin(fields)
@@ -223,7 +304,7 @@ def run_ours(args):
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()               # L2 flush between timed iterations (torch stream)
-        torch.cuda.synchronize()
+        barrier()                   # every rank enters the step together: no peer lateness inside the timed region
         ev[k][0].record(stream)
         dyn_evp.subcycle(params)    # syncs its stream before returning
         ev[k][1].record(stream)
@@ -266,6 +347,23 @@ def run_ours(args):
         h2d = 30 * nblk * 8 + 2 * nblk * 4
         d2h = 18 * nblk * 8
         e2e_how = "evp_b200_run_bgrid: every field crosses both ways (tripole grid)"
+    # (c) what a Fortran caller hands over: pageable arrays; then the same arrays page-locked once (evp_b200_pin_host)
+    e2e_pageable = None
+    if world == 1 and not args.no_pageable:
+        pf = {k: v.copy() for k, v in fields.items()}
+        run_pf = (lambda: dyn_evp.dyn_evp_b200_run_resident(params, pf, keep_stress=True)) if resident_ok else \
+            (lambda: dyn_evp.dyn_evp_b200_run(params, pf))
+        s_page = time_e2e(run_pf)
+        arrays = [v for v in pf.values() if isinstance(v, np.ndarray)]
+        for a in arrays:
+            dyn_evp.pin_host(a)
+        s_reg = time_e2e(run_pf)
+        for a in arrays:
+            dyn_evp.unpin_host(a)
+        e2e_pageable = {"pageable": {"value": cells_global * ndte / s_page, "ms_per_step": s_page * 1e3},
+                        "after_evp_b200_pin_host": {"value": cells_global * ndte / s_reg, "ms_per_step": s_reg * 1e3},
+                        "unit": UNIT, "how": "the e2e call from plain numpy arrays (what Fortran allocatables are), then from the same "
+                                             "arrays page-locked once with evp_b200_pin_host as the Fortran shim does on its first call"}
 
     if world > 1:
         t = torch.tensor([total_ms, e2e_s, kernel_ms, e2e_full_s], dtype=torch.float64, device="cuda")
@@ -276,19 +374,40 @@ def run_ours(args):
     if rank == 0:
         value = cells_global * ndte * args.steps / (total_ms * 1e-3)
         peak, peak_src = measured_peak()
-        per_gpu_cells = base["nx"] * base["ny"]
+        per_gpu_cells = sx * sy
         nl_step = launches / args.steps
-        traffic = measured_traffic("fused" if args.kernel in ("auto", "fused") else args.kernel)
+        kname = "persistent" if args.kernel == "persistent" else "fused"
+        ctr = kernel_counters(kname) or {}
         # dominant kernel: the subcycle kernel; one launch advances the rank's sub-domain by ndte/launches subcycles
-        sub_per_launch = ndte / max(nl_step, 1) if args.kernel != "split" else 0.5
+        sub_per_launch = ndte if args.kernel == "persistent" else (0.5 if args.kernel == "split" else 1.0)
         ach = per_gpu_cells * ndte * ALGO_BYTES_PER_CELL_SUBCYCLE / (kernel_ms * 1e-3) / 1e9
+        us_per_subcycle = kernel_ms * 1e3 / ndte
+        cold, warm = ctr.get("dram_bytes_per_launch_cold"), ctr.get("dram_bytes_per_launch_warm")
+        same_shape = (args.workload == "gx1" and (sx, sy) == (320, 384))
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                # the loop is 1 cold launch + (ndte-1) launches that find the working set in L2: the launch-weighted mean
+                "traffic": (None if not (same_shape and cold and warm) else (cold + (ndte - 1) * warm) / ndte),
+                "traffic_cold": cold if same_shape else None, "traffic_warm": warm if same_shape else None,
+                "traffic_how": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures of this "
+                               "kernel at gx1 (cold: caches flushed by ncu; warm: --cache-control none, the state of 239 of 240 launches); "
+                               "not re-measured in this run" if same_shape else "no ncu capture for this workload shape",
+                "traffic_detail": ctr if same_shape else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_cell_subcycle": ALGO_BYTES_PER_CELL_SUBCYCLE,
+                "kernel_ms_per_step": kernel_ms, "us_per_subcycle": us_per_subcycle, "subcycles_per_launch": sub_per_launch}
+        if same_shape and ctr.get("fp64_floor_us_per_subcycle"):
+            # the ceiling that binds when the working set is L2 resident: the fp64 pipe (0.5 warp-instructions / clk / sub-partition)
+            fl = ctr["fp64_floor_us_per_subcycle"]
+            roof["fp64_pipe"] = {"floor_us_per_subcycle": fl, "frac": fl / us_per_subcycle,
+                                 "how": ctr.get("fp64_floor_how", "fp64 warp-instructions per launch (ncu) x 2 cycles / (592 sub-partitions x SM clock)")}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": layout_of(args) if world > 1 else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"{args.workload} {base['nx']}x{base['ny']} per GPU, B-grid EVP ndte={ndte}, "
-                                       f"{px}x{py} GPUs, global {base['nx']*px}x{base['ny']*py}, box2001 synthetic",
-                           "kernel": args.kernel, "mode": args.mode, "l2": "flushed between timed steps (256 MiB memset)",
-                           "layout": desc},
+                "config": {"workload": workload_string(args, world, ndte),
+                           "kernel": args.kernel, "mode": args.mode,
+                           "l2": "flushed between timed steps (256 MiB memset); all ranks barrier before every timed step",
+                           "layout": desc, "derived_geometry_mismatches": bad},
+                "parity": parity,
                 "clocks": clocks,
                 "e2e": {"value": cells_global * ndte / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3, "how": e2e_how},
@@ -296,25 +415,25 @@ def run_ours(args):
                                   "d2h_bytes_per_step": 18 * nblk * 8, "ms_per_step": e2e_full_s * 1e3,
                                   "how": "evp_b200_run_bgrid: every field crosses both ways"},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                             "traffic": (traffic or {}).get("dram_bytes_per_launch_cold"), "traffic_detail": traffic,
-                             "peak_source": peak_src,
-                             "algorithmic_bytes_per_cell_subcycle": ALGO_BYTES_PER_CELL_SUBCYCLE,
-                             "kernel_ms_per_step": kernel_ms, "subcycles_per_launch": sub_per_launch},
+                "roofline": roof,
                 "wall_s": t_wall}
-        # the active-cell rate beside R (T cells that carry ice; rank 0's sub-domain, the same on every rank up to the
-        # synthetic ice edge)
+        if e2e_pageable:
+            line["e2e_pageable"] = e2e_pageable
+        # the active-cell rate beside R (T cells that carry ice; rank 0's sub-domain)
         act = int(np.count_nonzero(np.asarray(fields["iceTmask"])[:, 1:-1, 1:-1]))
         line["active_cells"] = {"icellT_rank0": act, "fraction_rank0": act / float(per_gpu_cells),
                                 "active_cell_subcycles_per_s": value * act / float(per_gpu_cells)}
         if world == 1 and not args.no_cpu:
-            bs = (40, 48) if args.workload == "gx1" else (max(base["nx"] // 8, 8), max(base["ny"] // 8, 8))
-            ccase = synth.make_case(args.workload, block_size=bs)
-            ncpu = 12 if args.workload in ("gx1", "gx3", "tx1") else 2   # ~3 s of wall time on 16 threads at gx1 (~50 core-seconds)
+            bs = cpu_blocks(args, nxg, nyg)
+            big = nxg * nyg > 1280 * 768
+            cnd = 12 if big else ndte
+            ccase = synth.make_case(args.workload, nx=nxg, ny=nyg, block_size=bs, ndte=cnd)
+            ccase.params.update(synth.evp_params(ndte), ndte=cnd)
+            ncpu = 2 if big else 12   # ~3 s of wall time on 16 threads at gx1 (~50 core-seconds)
             sec, nth = cpu_baseline(ccase, ncpu, 1)
-            line["cpu_baseline"] = {"value": per_gpu_cells * ndte / sec, "unit": UNIT, "cores": nth, "kind": "port",
-                                    "sample": f"{ncpu} full dynamics steps of {args.workload} (ndte={ndte}), blocks {bs[0]}x{bs[1]}, "
-                                              f"{sec:.3f} s each"}
+            line["cpu_baseline"] = {"value": nxg * nyg * cnd / sec, "unit": UNIT, "cores": nth, "kind": "port",
+                                    "sample": f"{ncpu} x {cnd} subcycles of {args.workload} {nxg}x{nyg} (full loop: ndte={ndte}), "
+                                              f"blocks {bs[0]}x{bs[1]}, {sec:.3f} s each"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -353,35 +472,61 @@ def run_cgrid(args):
     c = synth.make_ccase(args.workload, ndte=ndte)
     torch.cuda.set_device(0)
     dyn_evp.set_device(0)
+    p = dict(c.params, mode=abi.MODE_FAST if args.mode == "fast" else abi.MODE_EXACT,
+             kernel=abi.KERNEL_SPLIT if args.kernel == "split" else abi.KERNEL_AUTO)
+    parity = None
+    if not args.no_parity and args.mode == "exact":
+        from oracle import oracle
+        oracle.build()
+        pc = synth.make_ccase(args.workload, ndte=PARITY_NDTE)
+        pc.params.update(synth.evp_params(ndte), ndte=PARITY_NDTE, visc_method=c.params["visc_method"], deltaminEVP=c.params["deltaminEVP"])
+        ref, got = pc.copy_fields(), pc.copy_fields()
+        oracle.evp_run_cgrid(pc.grid, pc.cgrid, pc.params, ref, nthreads=os.cpu_count() or 1, variant="exact")
+        dyn_evp.dyn_evp_b200_init(pc.grid)
+        try:
+            dyn_evp.dyn_evp_b200_init_cgrid(pc.cgrid)
+            dyn_evp.dyn_evp_b200_run_cgrid(dict(pc.params, mode=p["mode"], kernel=p["kernel"]), got)
+        finally:
+            dyn_evp.dyn_evp_b200_finalize()
+        names = [n for n in abi.CFIELDS_INOUT + abi.CFIELDS_OUT if n != "strengthU"]
+        badn = [n for n in names if digest(got[n]) != digest(ref[n])]
+        parity = {"ok": not badn, "bitwise": True, "mismatching_arrays": len(badn), "arrays_per_rank": len(names), "ranks": 1,
+                  "case": f"{args.workload} C grid, first {PARITY_NDTE} subcycles of the step", "first_bad": badn[:3],
+                  "checker": "CPU oracle (exact build), sha256 per array"}
     dyn_evp.dyn_evp_b200_init(c.grid)
     dyn_evp.dyn_evp_b200_init_cgrid(c.cgrid)
-    p = dict(c.params, mode=abi.MODE_FAST if args.mode == "fast" else abi.MODE_EXACT)
     f = pin(c.copy_fields())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    sampler = ClockSampler(0)
     loop, call = [], []
     for it in range(max(args.warmup, 3) + args.steps):
+        if it == max(args.warmup, 3):
+            sampler.start()
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         dyn_evp.dyn_evp_b200_run_cgrid(p, f)
         call.append(time.perf_counter() - t0)
         loop.append(dyn_evp.last_loop_ms())
+    clocks = sampler.stop()
     loop, call = loop[-args.steps:], call[-args.steps:]
     ms = float(np.mean(loop))
     peak, peak_src = measured_peak()
     ach = cells * ndte * C_ALGO_BYTES / (ms * 1e-3) / 1e9
     nblk = int(np.prod(c.fields["uvel"].shape))
+    nl = int(dyn_evp.last_launches())
     print(json.dumps({"metric": METRIC.replace("gx1", "gx1 C-grid"), "value": cells * ndte / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
                       "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": {"workload": f"{args.workload} {base['nx']}x{base['ny']} C-grid EVP (standard_2d) ndte={ndte}, 1 GPU, box2001 synthetic",
                                  "mode": args.mode, "l2": "flushed between timed steps (256 MiB memset)", "layout": dyn_evp.describe()},
+                      "parity": parity, "clocks": clocks,
                       "e2e": {"value": cells * ndte / float(np.mean(call)), "unit": UNIT, "h2d_bytes_per_step": 37 * nblk * 8 + 4 * nblk * 4,
                               "d2h_bytes_per_step": 21 * nblk * 8, "ms_per_step": float(np.mean(call)) * 1e3},
-                      "gpu_launches": int(dyn_evp.last_launches()) * args.steps,
+                      "gpu_launches": nl * args.steps,
                       "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                                    "peak_source": peak_src, "algorithmic_bytes_per_cell_subcycle": C_ALGO_BYTES,
-                                   "kernels_per_subcycle": 5}}))
+                                   "kernels_per_subcycle": nl // ndte, "us_per_subcycle": ms * 1e3 / ndte}}))
     dyn_evp.dyn_evp_b200_finalize()
 
 
@@ -391,10 +536,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "split", "fused", "persistent", "queue"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "split", "fused", "stream", "resident", "persistent"])
     ap.add_argument("--mode", default="exact", choices=["fast", "exact"])
     ap.add_argument("--workload", default="gx1")
+    ap.add_argument("--layout", default=None, choices=["weak", "strong"],
+                    help="N > 1: weak = one --sub sized sub-domain per GPU (default for gx1, gx3); strong = the workload's global grid cut "
+                         "into px x py rectangles (default for tx1, p1deg: configs[3], configs[4])")
+    ap.add_argument("--sub", default=None, help="weak layout: per-GPU sub-domain NXxNY (the weak-scaling halo sweep), default the workload's size")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true")
     ap.add_argument("--grid", default="B", choices=["B", "C"], help="C: configs[2], gx1 C-grid EVP, ndte=600 (one GPU)")
     args = ap.parse_args()
     if args.grid == "C":

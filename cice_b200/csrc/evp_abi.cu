@@ -417,6 +417,7 @@ static int do_init(const evp_b200_grid_t *gr) {
   // ---- halo plan ----------------------------------------------------------------------------------
   if (g.halo.build(g_comm, gi0, gj0, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, g_allow_partial, g_err, sizeof g_err)) return 1;
   d.wrap_ew = g.halo.wrap_ew; d.wrap_ns = g.halo.wrap_ns;
+  d.fold_top = (g.ns == EVP_B200_BNDY_TRIPOLE && gj0 + ny - 1 == g.nyg) ? 1 : 0;
   CK(cudaStreamSynchronize(g.stream));
   if (g_comm.nranks == 1 && g.halo.build_local_fold(g.nxg, g.nyg, g.ew, g.ns, exact::fold_max_entries(), g_err, sizeof g_err)) return 1;
   if (g.p2p.setup(g_comm, g.halo, g.dshare, g.ndom, nx, ny, d.ld, g.nxg, g.nyg, g.ew, g.ns, exact::fold_max_entries(), g_err, sizeof g_err)) return 1;
@@ -619,7 +620,7 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
       ++nl;
       if (g.p2p.fold_n > 0) {  // tripole fold: what this rank combines itself once the peers' stores of this subcycle are in
         CK(exact::launch_fold(g.p2p.prm, g.dom.u[cur], g.dom.v[cur], g.p2p.d_fold_dst, g.p2p.d_fold_c1, g.p2p.d_fold_c2, g.p2p.d_fold_code,
-                              g.p2p.fold_n, ksub, g.stream));
+                              g.p2p.fold_n, ksub, 1, g.stream));
         ++nl;
       }
       continue;
@@ -638,6 +639,7 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
     }
     // the part of dyn_haloUpdate(uvel,vvel) that is not an on-rank wrap: neighbour ranks, tripole fold
     int hl = 0;
+    g.halo.fold_pdl = (kern == EVP_B200_KERNEL_FUSED);
     if (g.halo.exchange(g_comm, g.dom.u[cur], g.dom.v[cur], g.stream, &hl, g_err, sizeof g_err)) return 1;
     nl += hl;
   }

@@ -284,6 +284,8 @@ int HaloPlan::build(CommState &cs, int gi0, int gj0, int nx, int ny, int ld, int
   HCK(cudaMalloc(&d_recvbuf, sizeof(double) * 2 * std::max(n_recv, 1)));
   const char *eg = getenv("EVP_B200_GRAPH");
   allow_graph = !(eg && eg[0] == '0');
+  const char *ep = getenv("EVP_B200_P2P");
+  no_fold_kernel = (ep && ep[0] == '0');
   return 0;
 }
 
@@ -293,7 +295,7 @@ int HaloPlan::exchange(CommState &cs, double *U, double *V, cudaStream_t s, int 
   if (fold_n > 0 && !no_fold_kernel) {
     // one rank: every source is local and the whole update is the fold list -- one kernel instead of pack + apply
     static const P2PParams nopeers{};
-    HCK(exact::launch_fold(nopeers, U, V, d_fold_dst, d_fold_c1, d_fold_c2, d_fold_code, fold_n, 0, s));
+    HCK(exact::launch_fold(nopeers, U, V, d_fold_dst, d_fold_c1, d_fold_c2, d_fold_code, fold_n, 0, fold_pdl ? 1 : 0, s));
     ++*launches;
     return 0;
   }

@@ -44,6 +44,7 @@ struct HaloPlan {
   // one rank, every source local (tripole fold on one GPU): the whole update as one kernel (p2p_fold_kernel, evp_kernels.cu)
   int fold_n = 0;
   bool no_fold_kernel = false;                             // EVP_B200_P2P=0: keep the staged pack + apply form
+  bool fold_pdl = false;                                   // the kernel in front of it is a fused subcycle kernel (PDL chain)
   int *d_fold_dst = nullptr, *d_fold_c1 = nullptr, *d_fold_c2 = nullptr;
   signed char *d_fold_code = nullptr;
   int build_local_fold(int nxg, int nyg, int ew, int ns, int max_entries, char *err, size_t nerr);

@@ -16,6 +16,7 @@ struct Dom {
   int nyd;     // ny + 2
   int wrap_ew; // E-W ghost columns are the rank's own opposite interior columns (cyclic, whole width local)
   int wrap_ns; // same for N-S (cyclic)
+  int fold_top; // row ny is the row below a tripole fold: its off-ice U points are carried across the ping-pong copies (fused_body)
 
   // carried state
   double *u[2], *v[2];  // velocity ping-pong (fused kernels read [cur], write [cur^1])
@@ -115,7 +116,7 @@ struct PersistPlan {
   cudaError_t launch_finish(const Dom &d, int cur, double *strocnx, double *strocny, double rhow, double cosw, double sinw, cudaStream_t s); \
   cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int form, bool pdl, int last); \
   cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, int last, int form, cudaStream_t s); \
-  cudaError_t launch_fold(const P2PParams &pp, double *U, double *V, const int *dst, const int *c1, const int *c2, const signed char *code, int n, int ksub, cudaStream_t s); \
+  cudaError_t launch_fold(const P2PParams &pp, double *U, double *V, const int *dst, const int *c1, const int *c2, const signed char *code, int n, int ksub, int pdl, cudaStream_t s); \
   int fold_max_entries(); \
   cudaError_t set_wait_timeout(unsigned long long ns); \
   cudaError_t set_metric(const double *HTN, const double *HTE, double deltamin); \

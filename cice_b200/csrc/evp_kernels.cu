@@ -345,7 +345,12 @@ __device__ __forceinline__ void fused_body(const Dom &d, const KParams &k, int c
   for (int q = 0; q < 8; ++q) sstr[q][ty][tx] = str[q];
   if (CPU) cp_async_wait_all();  // own copies only: each thread reads back what it requested itself
   __syncthreads();
-  if (uspot && mU) {
+  // An off-ice point of the row below a tripole fold is not advanced by the momentum step but REWRITTEN by every halo update
+  // (0.5*(own - mirror), pole points negated: ice_boundary.F90:1641-1649), so unlike every other off-ice cell it changes during the
+  // loop: its current value travels to the other ping-pong copy (and to the peers) like a computed one.
+  const bool doU = uspot && mU, carry = uspot && !mU && d.fold_top && j == d.ny;
+  double un = ucc, vn = vcc;
+  if (doU) {
     double uo[NUOP];
     if (CPU) {
 #pragma unroll
@@ -359,7 +364,7 @@ __device__ __forceinline__ void fused_body(const Dom &d, const KParams &k, int c
     const UOut o = stepu_point<IL>(ucc, vcc, uo[0], uo[1], uo[2], uo[3], uo[4], uo[5], uo[6], uo[7], uo[8], uo[9], uo[10], uo[11], ui, vi,
                                sstr[0][ty][tx], sstr[1][ty][tx + 1], sstr[2][ty + 1][tx], sstr[3][ty + 1][tx + 1], sstr[4][ty][tx],
                                sstr[5][ty + 1][tx], sstr[6][ty][tx + 1], sstr[7][ty + 1][tx + 1], k);
-    store_uv(d, d.u[nxt], d.v[nxt], i, j, o.u, o.v);
+    un = o.u; vn = o.v;
     if (last) {
       // the loop overwrites these every subcycle and nothing reads them in between (ice_dyn_shared.F90:948-965);
       // only the last subcycle's values survive, as in the reference's own 1-D solver (calc_diag_1d, ice_dyn_core1d.F90:607)
@@ -368,6 +373,9 @@ __device__ __forceinline__ void fused_body(const Dom &d, const KParams &k, int c
       d.taubx[c] = o.taubx;
       d.tauby[c] = o.tauby;
     }
+  }
+  if (doU || carry) {
+    store_uv(d, d.u[nxt], d.v[nxt], i, j, un, vn);
     if (P2P && is_push_point(d, pp.fold_row, i, j)) {
       // this point is a ghost cell (or a fold source) of up to three other sub-domains: store it there over NVLink right away,
       // so the traffic is spread over the kernel and long acknowledged when the hand-over fence below is issued.  Bit 8 of the
@@ -377,8 +385,8 @@ __device__ __forceinline__ void fused_body(const Dom &d, const KParams &k, int c
         const int pw = pp.push_peer[q], pr = pw & 0xff;
         const int dst = pp.push_dst[q];
         const bool neg = (pw & 0x100) != 0;
-        pp.peer_u[nxt][pr][dst] = neg ? -o.u : o.u;
-        pp.peer_v[nxt][pr][dst] = neg ? -o.v : o.v;
+        pp.peer_u[nxt][pr][dst] = neg ? neg_f64(un) : un;
+        pp.peer_v[nxt][pr][dst] = neg ? neg_f64(vn) : vn;
       }
     }
   }
@@ -480,7 +488,21 @@ constexpr int FOLD_THREADS = 1024, FOLD_PER_THREAD = 8, FOLD_MAX = FOLD_THREADS 
 __global__ void __launch_bounds__(FOLD_THREADS) p2p_fold_kernel(const __grid_constant__ P2PParams pp, double *U, double *V,
                                                                 const int *__restrict__ dst, const int *__restrict__ c1,
                                                                 const int *__restrict__ c2, const signed char *__restrict__ code,
-                                                                int n, int ksub) {
+                                                                int n, int ksub, int pdl) {
+  // the index lists are static: fetched while the subcycle kernel in front of this one is still running (programmatic launch)
+  int kd[FOLD_PER_THREAD], ka[FOLD_PER_THREAD], kb[FOLD_PER_THREAD], kop[FOLD_PER_THREAD];
+#pragma unroll
+  for (int q = 0; q < FOLD_PER_THREAD; ++q) {
+    const int kk = threadIdx.x + q * FOLD_THREADS;
+    kd[q] = ka[q] = kb[q] = kop[q] = 0;
+    if (kk < n) { kd[q] = dst[kk]; ka[q] = c1[kk]; kb[q] = c2[kk]; kop[q] = code[kk]; }
+  }
+#if EVP_USE_PDL
+  if (pdl) {
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
+  }
+#endif
   if (pp.npeers > 0) {
     const unsigned long long base = *pp.epoch_base;
     if ((int)threadIdx.x < pp.npeers)
@@ -493,7 +515,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) p2p_fold_kernel(const __grid_con
     const int kk = threadIdx.x + q * FOLD_THREADS;
     u[q] = 0.0; v[q] = 0.0;
     if (kk < n) {
-      const int a = c1[kk], op = code[kk];
+      const int a = ka[q], op = kop[q];
       // written by other SMs / other GPUs during this launch sequence: read through L2, never a stale L1 line
       u[q] = ld_cg_f64(U + a); v[q] = ld_cg_f64(V + a);
       if (op == 1) {
@@ -501,7 +523,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) p2p_fold_kernel(const __grid_con
       } else if (op == 2 || op == 3) {
         // xavg = 0.5*(x1 + isign*x2) with isign = -1, x1 the partner with the lower i (ice_boundary.F90:1641-1646).  The lower
         // partner receives xavg, the upper one isign*xavg: -(0.5*(x1-x2)) and 0.5*(x2-x1) differ in the sign of a zero result
-        const int b = c2[kk];
+        const int b = kb[q];
         u[q] = 0.5 * (u[q] - ld_cg_f64(U + b));
         v[q] = 0.5 * (v[q] - ld_cg_f64(V + b));
         if (op == 3) { u[q] = neg_f64(u[q]); v[q] = neg_f64(v[q]); }
@@ -512,16 +534,21 @@ __global__ void __launch_bounds__(FOLD_THREADS) p2p_fold_kernel(const __grid_con
 #pragma unroll
   for (int q = 0; q < FOLD_PER_THREAD; ++q) {
     const int kk = threadIdx.x + q * FOLD_THREADS;
-    if (kk < n) { U[dst[kk]] = u[q]; V[dst[kk]] = v[q]; }
+    if (kk < n) { U[kd[q]] = u[q]; V[kd[q]] = v[q]; }
   }
 }
 
 #ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
 cudaError_t launch_fold(const P2PParams &pp, double *U, double *V, const int *dst, const int *c1, const int *c2,
-                        const signed char *code, int n, int ksub, cudaStream_t s) {
+                        const signed char *code, int n, int ksub, int pdl, cudaStream_t s) {
   if (n > FOLD_MAX) return cudaErrorInvalidValue;
-  p2p_fold_kernel<<<1, FOLD_THREADS, 0, s>>>(pp, U, V, dst, c1, c2, code, n, ksub);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1); cfg.blockDim = dim3(FOLD_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, p2p_fold_kernel, pp, U, V, dst, c1, c2, code, n, ksub, pdl);
 }
 int fold_max_entries() { return FOLD_MAX; }
 cudaError_t set_wait_timeout(unsigned long long ns) { return cudaMemcpyToSymbol(g_wait_timeout_ns, &ns, sizeof ns); }

@@ -156,6 +156,6 @@ extern "C" int emu_set_metric(int nxb, int nyb, const double *geo /*[10][n]*/, c
 extern "C" int emu_halo_local(double *U, double *V, const int *dst, const int *c1, const int *c2, const signed char *code, int n) {
   if (n > FOLD_MAX) return 1;
   static const P2PParams nop2p{};
-  emu::launch({1, 1, 1}, {FOLD_THREADS, 1, 1}, [&] { p2p_fold_kernel(nop2p, U, V, dst, c1, c2, code, n, 0); });
+  emu::launch({1, 1, 1}, {FOLD_THREADS, 1, 1}, [&] { p2p_fold_kernel(nop2p, U, V, dst, c1, c2, code, n, 0, 0); });
   return 0;
 }

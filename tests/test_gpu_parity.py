@@ -206,6 +206,8 @@ def test_multi_gpu_halo(args, p2p):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
+    if p2p == "0" and args[4] == "split":
+        pytest.skip("the split kernels use the staged exchange either way (covered by the nvlink-stores id)")
     world = 4 if n >= 4 else 2
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
