@@ -213,12 +213,9 @@ def parity_precheck(args, dyn_evp, abi, dist, world, rank, params, case, grid, f
     t0 = time.perf_counter()
     p = dict(params, ndte=PARITY_NDTE)
     got = {k: v.copy() for k, v in fields.items()}
-    dyn_evp.dyn_evp_b200_init(grid)
-    try:
-        dyn_evp.dyn_evp_b200_run(p, got)
-        desc = dyn_evp.describe()
-    finally:
-        dyn_evp.dyn_evp_b200_finalize()
+    dyn_evp.dyn_evp_b200_init(grid)   # not finalized here: evp_b200_finalize also ends the NCCL communicator; the timed part's
+    dyn_evp.dyn_evp_b200_run(p, got)  # own evp_b200_init releases this context
+    desc = dyn_evp.describe()
     want = [None]
     if rank == 0:
         from cice_b200 import decomp
