@@ -16,6 +16,7 @@
 
 #include "evp_b200.h"
 #include "evp_internal.h"
+#include "evp_persist_plan.h"
 #include "evp_halo.h"
 
 namespace evp {
@@ -172,6 +173,9 @@ struct Ctx {
   bool persist_ok = false;
   std::string persist_why;
   unsigned *d_progress = nullptr;
+  unsigned *d_ptab[2] = {nullptr, nullptr};  // (slot, thread) -> cell tables
+  int *d_perr = nullptr;
+  long long *d_pdbg = nullptr;
   int num_sms = 0;
   bool streaming = false;    // the sub-domain's arrays exceed L2: HBM-streaming form of the fused kernel
   bool derived_ok = false;   // evp_b200_set_metric: HTN/HTE reproduce the seven derived geometry arrays bit for bit
@@ -221,7 +225,7 @@ static int free_all() {
   for (auto &p : g.dstr) F(p);
   F(g.dmaskT); F(g.dmaskU);
   for (auto &p : g.stage) F(p);
-  F(g.stage_mask); F(g.stage_mask2); F(g.d_ever_off); F(g.d_gsrc); F(g.d_progress);
+  F(g.stage_mask); F(g.stage_mask2); F(g.d_ever_off); F(g.d_gsrc); F(g.d_progress); F(g.d_ptab[0]); F(g.d_ptab[1]); F(g.d_perr); F(g.d_pdbg);
   F(g.d_uv_lin); F(g.d_uv_dom); F(g.d_sig_lin); F(g.d_sig_dom); F(g.d_int_lin); F(g.d_int_dom);
   g.halo.release();
   for (auto &e : g.ev_field) if (e) cudaEventDestroy(e);
@@ -242,45 +246,28 @@ static int upload_vec(T *&dptr, const std::vector<T> &h) {
   return 0;
 }
 
-// choose the persistent tiling: at most one tile per SM, every tile's T cells fit 2 per thread, smallest
-// tile wins (it bounds the time of a subcycle); then keep as many static arrays in shared memory as fit
-static void plan_persist() {
-  const Dom &d = g.dom;
-  const int cap_cells = 2 * PERSIST_THREADS;
-  const size_t smem_max = 232448;  // 227 KB per CTA on sm_100
-  PersistPlan best{};
-  long best_cost = -1;
-  for (int ntx = 1; ntx <= g.num_sms; ++ntx) {
-    for (int nty = 1; ntx * nty <= g.num_sms; ++nty) {
-      const int bx = (d.nx + ntx - 1) / ntx, by = (d.ny + nty - 1) / nty;
-      const int tx2 = (d.nx + bx - 1) / bx, ty2 = (d.ny + by - 1) / by;  // drop empty tiles
-      if (tx2 != ntx || ty2 != nty) continue;
-      const int nT = (bx + 1) * (by + 1), nU = bx * by, nring = (bx + 2) * (by + 2);
-      if (nT > cap_cells) continue;
-      const size_t base = 8ull * (2 * nring + 8 * nT + nU) + nT + nU;  // u, v, str, cvrel + masks
-      if (base > smem_max) continue;
-      const long cost = (long)nT * 4096 - bx;  // smallest tile, then the widest rows
-      if (best_cost < 0 || cost < best_cost) {
-        best_cost = cost;
-        best.ntx = ntx; best.nty = nty; best.bx = bx; best.by = by; best.nT = nT; best.nU = nU;
-      }
-    }
-  }
+// KERNEL_PERSISTENT: tiling, shared-memory layout and (slot, thread) tables (evp_persist_plan.h)
+static int plan_persist() {
   g.persist_ok = false;
-  if (best_cost < 0) { g.persist_why = "no tiling with <= 1 tile per SM fits the sub-domain on chip"; return; }
-  if (g.halo.n_dst != 0 || !g.halo.peers.empty()) { g.persist_why = "the halo needs an exchange between subcycles (neighbour ranks or tripole fold)"; return; }
-  PersistPlan &pp = best;
-  const int nring = (pp.bx + 2) * (pp.by + 2);
-  size_t used = 8ull * (2 * nring + 8 * pp.nT + pp.nU) + pp.nT + pp.nU;
-  pp.kT = 0; pp.kU = 1;
-  while (pp.kT < 10 && used + 8ull * pp.nT <= smem_max) { ++pp.kT; used += 8ull * pp.nT; }
-  while (pp.kU < 11 && used + 8ull * pp.nU <= smem_max) { ++pp.kU; used += 8ull * pp.nU; }
-  pp.off_u = 0; pp.off_v = nring; pp.off_str = 2 * nring; pp.off_T = pp.off_str + 8 * pp.nT;
-  pp.off_U = pp.off_T + pp.kT * pp.nT;
-  pp.off_mask = 8 * (pp.off_U + pp.kU * pp.nU);
-  pp.smem_bytes = (unsigned)(pp.off_mask + pp.nT + pp.nU);
+  if (g.halo.n_dst != 0 || !g.halo.peers.empty()) { g.persist_why = "the halo needs an exchange between subcycles (neighbour ranks or tripole fold)"; return 0; }
+  PersistPlan pp{};
+  PersistTables tb;
+  if (!persist_plan(g.dom.nx, g.dom.ny, g.num_sms, PERSIST_THREADS, 232448, pp, tb, g.persist_why)) return 0;
+  unsigned *dt = nullptr, *du = nullptr;
+  if (upload_vec(dt, tb.tslot) || upload_vec(du, tb.uslot)) return 1;
+  g.d_ptab[0] = dt; g.d_ptab[1] = du;
+  CK(cudaMalloc(&g.d_progress, sizeof(unsigned) * PERSIST_CTR_STRIDE * pp.ntx * pp.nty));
+  CK(cudaMalloc(&g.d_perr, sizeof(int)));
+  CK(cudaMemset(g.d_perr, 0, sizeof(int)));
+  pp.tslot = dt; pp.uslot = du; pp.progress = g.d_progress; pp.err = g.d_perr;
+  if (getenv("EVP_B200_PERSIST_DEBUG")) {  // per-warp cycle accounting, printed after every loop
+    CK(cudaMalloc(&g.d_pdbg, sizeof(long long) * (5 * (PERSIST_THREADS / 32) + 32) * pp.ntx * pp.nty));
+    CK(cudaMemset(g.d_pdbg, 0, sizeof(long long) * (5 * (PERSIST_THREADS / 32) + 32) * pp.ntx * pp.nty));
+    pp.dbg = g.d_pdbg;
+  }
   g.pplan = pp;
   g.persist_ok = true;
+  return 0;
 }
 
 static int do_init(const evp_b200_grid_t *gr) {
@@ -435,18 +422,14 @@ static int do_init(const evp_b200_grid_t *gr) {
   }
   CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, g.device));
   // ---- persistent tiling ---------------------------------------------------------------------------
-  plan_persist();
-  if (g.persist_ok) {
-    CK(cudaMalloc(&g.d_progress, sizeof(unsigned) * g.pplan.ntx * g.pplan.nty));
-    g.pplan.progress = g.d_progress;
-  }
+  if (plan_persist()) return 1;
 
   CK(cudaStreamSynchronize(g.stream));
   g.inited = true;
   char buf[512], pbuf[200];
   if (g.persist_ok)
-    snprintf(pbuf, sizeof pbuf, "persistent: %dx%d tiles of %dx%d on %d SMs, smem %u B, kT=%d kU=%d", g.pplan.ntx, g.pplan.nty,
-             g.pplan.bx, g.pplan.by, g.num_sms, g.pplan.smem_bytes, g.pplan.kT, g.pplan.kU);
+    snprintf(pbuf, sizeof pbuf, "persistent: %dx%d tiles of %dx%d on %d SMs, smem %u B, kT=%d kU=%d, edge warps T %d U %d", g.pplan.ntx, g.pplan.nty,
+             g.pplan.bx, g.pplan.by, g.num_sms, g.pplan.smem_bytes, g.pplan.kT, g.pplan.kU, g.pplan.ewT[0], g.pplan.ewU[0]);
   else
     snprintf(pbuf, sizeof pbuf, "persistent: unavailable (%s)", g.persist_why.c_str());
   snprintf(buf, sizeof buf, "dom %dx%d (ld %d) at global (%d,%d) of %dx%d; %d block(s) %dx%d, %zu hole cell(s); rank %d/%d; halo: %s; %s",
@@ -592,7 +575,7 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
       PersistPlan pp = g.pplan;
       pp.ndte = p->ndte;
       pp.use_init = (p->revp != 0.0);
-      CK(cudaMemsetAsync(g.d_progress, 0, sizeof(unsigned) * pp.ntx * pp.nty, g.stream));
+      CK(cudaMemsetAsync(g.d_progress, 0, sizeof(unsigned) * PERSIST_CTR_STRIDE * pp.ntx * pp.nty, g.stream));
       CK(exact ? exact::launch_persist(g.dom, k, pp, g.stream) : fast::launch_persist(g.dom, k, pp, g.stream));
     }
     *cur_end = p->ndte & 1;
@@ -703,6 +686,76 @@ static int do_subcycle(const evp_b200_params_t *p) {
   g.last_launches = nl;
   CK(cudaStreamSynchronize(g.stream));
   CK(cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1));
+  if (choose_kernel(p) == EVP_B200_KERNEL_PERSISTENT && g.d_pdbg && p->ndte > 0) {
+    const int nw = PERSIST_THREADS / 32, nt = g.pplan.ntx * g.pplan.nty;
+    std::vector<long long> w((size_t)5 * nw * nt);
+    CK(cudaMemcpy(w.data(), g.d_pdbg, w.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    // tile in the middle of the tile grid, every warp; then the mean over all tiles and warps
+    const int mid = (g.pplan.nty / 2) * g.pplan.ntx + g.pplan.ntx / 2;
+    fprintf(stderr, "[evp_b200 persistent] loop %.3f ms, %d subcycles; cycles per subcycle and warp of tile %d: phase A (ring wait+refresh) | barrier | phase C | barrier\n",
+            g.last_ms, p->ndte, mid);
+    for (int wv = 0; wv < nw; ++wv) {
+      const long long *a = &w[((size_t)mid * nw + wv) * 5];
+      fprintf(stderr, "  warp %2d: %6.0f (%5.0f) | %6.0f | %6.0f | %6.0f\n", wv, (double)a[0] / p->ndte, (double)a[1] / p->ndte, (double)a[2] / p->ndte,
+              (double)a[3] / p->ndte, (double)a[4] / p->ndte);
+    }
+    if (p->ndte >= PERSIST_TL0 + 4) {  // timeline of four subcycles: the middle tile and its W, E, S, N neighbours, ns relative to the tile's own
+      std::vector<unsigned long long> tl((size_t)nt * 32);      // phase A start of the first of them
+      CK(cudaMemcpy(tl.data(), g.d_pdbg + (size_t)5 * nw * nt, tl.size() * 8, cudaMemcpyDeviceToHost));
+      int slow = 0;   // the tile that waits least for its neighbours sets the pace
+      long long wmin = 1LL << 60;
+      for (int t = 0; t < nt; ++t) {
+        long long wsum = 0;
+        for (int ks = 0; ks < 4; ++ks) wsum += (long long)(tl[(size_t)t * 32 + ks * 8 + 1] - tl[(size_t)t * 32 + ks * 8]);
+        if (wsum < wmin) { wmin = wsum; slow = t; }
+      }
+      const int nbs[5] = {mid, mid - 1, mid + 1, mid - g.pplan.ntx, slow};
+      const unsigned long long t0 = tl[(size_t)mid * 32];
+      fprintf(stderr, "  timeline (ns after tile %d began subcycle %d): A start | flags seen | ring refreshed | past barrier B (warp 0) | published | past barrier D | B (last warp)\n", mid, PERSIST_TL0);
+      for (int q = 0; q < 5; ++q)
+        for (int ks = 0; ks < 4; ++ks) {
+          const unsigned long long *e = &tl[(size_t)nbs[q] * 32 + ks * 8];
+          fprintf(stderr, "   tile %3d k+%d: %7lld %7lld %7lld %7lld %7lld %7lld %7lld\n", nbs[q], ks, (long long)(e[0] - t0), (long long)(e[1] - t0), (long long)(e[2] - t0),
+                  (long long)(e[3] - t0), (long long)(e[4] - t0), (long long)(e[5] - t0), (long long)(e[6] - t0));
+        }
+    }
+    if (p->ndte >= PERSIST_TL0 + 4 && getenv("EVP_B200_PERSIST_DEBUG") && atoi(getenv("EVP_B200_PERSIST_DEBUG")) > 1) {
+      std::vector<unsigned long long> tl((size_t)nt * 32);
+      CK(cudaMemcpy(tl.data(), g.d_pdbg + (size_t)5 * nw * nt, tl.size() * 8, cudaMemcpyDeviceToHost));
+      const unsigned long long t0 = tl[(size_t)mid * 32 + 8];
+      const char *what[5] = {"A start of subcycle k+1 (ns, relative to the middle tile)", "first warp at barrier B - A start", "flags seen - A start",
+                             "published - last warp at barrier B", "next A start - A start (period)"};
+      for (int w = 0; w < 5; ++w) {
+        fprintf(stderr, "  %s, tile rows from the north:\n", what[w]);
+        for (int ty = g.pplan.nty - 1; ty >= 0; --ty) {
+          fprintf(stderr, "   ");
+          for (int tx = 0; tx < g.pplan.ntx; ++tx) {
+            const unsigned long long *e = &tl[(size_t)(ty * g.pplan.ntx + tx) * 32 + 8];
+            long long v = 0;
+            if (w == 0) v = (long long)(e[0] - t0);
+            if (w == 1) v = (long long)(e[3] - e[0]);
+            if (w == 2) v = (long long)(e[1] - e[0]);
+            if (w == 3) v = (long long)(e[4] - e[6]);
+            if (w == 4) v = (long long)(e[8] - e[0]);
+            fprintf(stderr, " %6lld", v);
+          }
+          fprintf(stderr, "\n");
+        }
+      }
+    }
+    double m[5] = {0, 0, 0, 0, 0};
+    for (int t = 0; t < nt * nw; ++t) for (int q = 0; q < 5; ++q) m[q] += (double)w[(size_t)t * 5 + q];
+    fprintf(stderr, "  mean   : %6.0f (%5.0f) | %6.0f | %6.0f | %6.0f\n", m[0] / nt / nw / p->ndte, m[1] / nt / nw / p->ndte, m[2] / nt / nw / p->ndte,
+            m[3] / nt / nw / p->ndte, m[4] / nt / nw / p->ndte);
+  }
+  if (choose_kernel(p) == EVP_B200_KERNEL_PERSISTENT && g.d_perr) {
+    int e = 0;
+    CK(cudaMemcpy(&e, g.d_perr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) {
+      CK(cudaMemset(g.d_perr, 0, sizeof(int)));
+      return fail("evp_b200_subcycle: persistent kernel: a tile waited for a neighbour tile longer than 2 s (CTAs not co-resident?)");
+    }
+  }
   if (g.p2p.enabled) {
     int e = 0;
     CK(cudaMemcpy(&e, g.p2p.d_err, sizeof(int), cudaMemcpyDeviceToHost));

@@ -92,18 +92,30 @@ struct P2PParams {
   unsigned long long *dbg;                     // [0] sum of wait cycles of lane 0 of edge CTAs, [1] number of waits, [2] max wait
 };
 
-// KERNEL_PERSISTENT tiling (see evp_persist.cu)
+// KERNEL_PERSISTENT (evp_persist.cu): one CTA per SM owns a tile of the sub-domain for the whole loop.  The plan is built on the
+// host (evp_persist_plan.h); the tables say which T cell / U point each (slot, thread) of a CTA advances.
 #define PERSIST_THREADS 512
+#define PERSIST_SLOTS 2      // cells per thread and subcycle
+#define PERSIST_NONE_W 0xffffffffu  // table word of an empty (slot, thread)
+#define PERSIST_TL0 100              // first subcycle of the debug timeline
+#define PERSIST_CTR_STRIDE 32       // progress counters sit 128 B apart: one L2 line (and slice) each
 struct PersistPlan {
   int ntx, nty;   // tile grid (one CTA per tile, all co-resident)
-  int bx, by;     // U points per tile
-  int nT, nU;     // (bx+1)*(by+1) T cells, bx*by U points
+  int bx, by;     // U points per full tile; tiles of the last column / row may be narrower
+  int nT, nU;     // (bx+1)*(by+1) T cells, bx*by U points of a full tile
+  int nring;      // (bx+2)*(by+2): u, v of the tile with its one-cell ring
   int ndte;
-  int kT, kU;     // how many static T / U arrays are kept in shared memory
+  int kT, kU;     // how many static T / U arrays the instantiation keeps in shared memory
   int use_init;   // revised EVP reads uvel_init/vvel_init
-  unsigned *progress;  // [ntx*nty] subcycles published by each tile
-  int off_u, off_v, off_str, off_T, off_U;  // shared-memory offsets in doubles
-  int off_mask;                             // in bytes
+  int nthreads;   // threads per CTA the tables were built for
+  unsigned *progress;   // [ntx*nty * PERSIST_CTR_STRIDE] edge-U warps that have published, summed over the subcycles so far
+  // [4 tile shapes][PERSIST_SLOTS * nthreads] packed words (evp_persist_plan.h: persist_word); shape = (last column) + 2*(last row)
+  const unsigned *tslot, *uslot;
+  int ewT[4], ewU[4];   // warps (from the top) whose slot 1 holds the tile-edge T cells; warps (from 0) whose slot 0 holds the tile-edge U points
+  int lw0[4], nlw[4];   // "light" warps (no slot-1 T cell): they refresh the ring for the edge warps; nlw = 0: the edge warps do it themselves
+  int *err;             // set when a wait on a neighbour tile times out (never, unless CTAs are not co-resident)
+  long long *dbg;       // null, or [tiles][warps][5] cycle counters (EVP_B200_PERSIST_DEBUG)
+  int off_uv, off_str, off_sig, off_T, off_U;  // shared-memory offsets in doubles
   unsigned smem_bytes;
 };
 

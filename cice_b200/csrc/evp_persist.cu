@@ -1,18 +1,30 @@
-// evp_persist.cu -- KERNEL_PERSISTENT: all ndte subcycles of the EVP loop in ONE cooperative launch.
+// evp_persist.cu -- KERNEL_PERSISTENT: all ndte subcycles of the EVP loop (ice_dyn_evp.F90:859-913) in ONE cooperative launch.
 //
-// One CTA per SM owns a bx x by tile of U points for the whole loop (ice_dyn_evp.F90:859-913):
-//   * the 12 stress components of its (bx+1) x (by+1) T cells live in REGISTERS (2 cells per thread),
-//   * u, v of the tile plus a one-cell ring, the 8 `str` terms, the ice masks and as many of the static
-//     per-cell coefficients as fit live in SHARED MEMORY (the rest is re-read through L1/L2),
-//   * per subcycle only the tile's edge velocities go through global memory (L2): the tile stores them
-//     into the ping-pong velocity arrays, publishes a per-tile progress counter with a release store,
-//     and its up-to-8 neighbours spin on that counter (acquire) before they refresh their ring.
-//     There is no grid-wide barrier; tiles drift by at most one subcycle (double buffering covers it).
-//   * T cells on a tile's E/N overlap edge are relaxed redundantly by both tiles (same inputs, same
-//     arithmetic -> identical bits), exactly like the reference evaluates N/E ghost T cells per block
-//     (ice_dyn_shared.F90:740-749).
-// Compiled twice like evp_kernels.cu (namespace exact: -fmad=false; namespace fast).
+// One CTA per SM owns a bx x by tile of U points (and the (bx+1) x (by+1) T cells that close them) for the whole loop:
+//   * the carried state of the tile -- 12 stresses per T cell, (u,v) with a one-cell ring -- the 8 `str` terms and the static
+//     operands that are needed first (KT of the 10 T arrays, KU of the 11 U arrays) live in SHARED MEMORY for the whole loop;
+//     the remaining static operands are read through L2 where their latency hides: dxhy, dyhx, strength, DminTarea are requested
+//     when a T cell is started and used hundreds of cycles later, the momentum operands are requested BEFORE the CTA barrier
+//     that separates the two phases;
+//   * threads are not tied to a corner or a lane role: every thread advances PERSIST_SLOTS T cells and PERSIST_SLOTS U points per
+//     subcycle, which ones is a table built on the host (evp_persist_plan.h).  The table orders the work so that the exchange
+//     between tiles is off the critical path:
+//        phase A (stress)   : T cells that read only the tile's own velocities first; the tile-edge T cells -- the only readers of
+//                             the ring -- last, by the last warps, after those warps have refreshed the ring;
+//        phase C (momentum) : the tile-edge U points first; their warps store them to the ping-pong arrays in global memory (L2)
+//                             and publish (fence + one atomic per warp) BEFORE the interior U points are advanced.
+//     A neighbour therefore has the whole interior momentum phase and the whole interior stress phase of slack before it reads.
+//   * no grid-wide barrier: a tile waits for its <= 8 neighbours' counters only (acquire), tiles drift by at most one subcycle,
+//     which the two copies of (u,v) in global memory cover (the same argument as for the launch-per-subcycle kernels' ping-pong);
+//   * T cells on a tile's E/N overlap edge are relaxed by both tiles (same inputs, same arithmetic -> identical bits), exactly like
+//     the reference evaluates N/E ghost T cells per block (ice_dyn_shared.F90:740-749).
+// The arithmetic is evp_math.cuh's (stress_point / stepu_cv, interleaved division / square-root form), so the bits are those of
+// the other kernels.  Compiled twice like evp_kernels.cu (namespace exact: -fmad=false; namespace fast).
 #include "evp_math.cuh"
+#include "evp_dom.cuh"
+#include "evp_ptx.cuh"
+
+#include <type_traits>
 
 #ifndef EVP_NS
 #error "compile with -DEVP_NS=exact or -DEVP_NS=fast"
@@ -21,255 +33,329 @@
 namespace evp {
 namespace EVP_NS {
 
-constexpr int PNT = PERSIST_THREADS;  // threads per CTA
-constexpr int PCELLS = 2;             // T cells (and U points) per thread
+// static per-cell arrays in the order they are needed (= shared-memory priority); on chip they are stored as pairs (double2)
+enum { T_CXP = 0, T_CYP, T_CXM, T_CYM, T_DXT, T_DYT, T_DMIN, T_STRENGTH, T_DXHY, T_DYHX, T_COUNT };
+enum { U_CV = 0, U_UOCN, U_VOCN, U_UMASSDTI, U_FM, U_WATERX, U_WATERY, U_FORCEX, U_FORCEY, U_UAREAR, U_TBU, U_COUNT };
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(unsigned *p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
+__device__ __forceinline__ double2 mk2(double a, double b) { double2 r; r.x = a; r.y = b; return r; }
 
-// static per-cell arrays, in smem-priority order
-enum { T_STRENGTH = 0, T_DXT, T_DYT, T_DXHY, T_DYHX, T_CXP, T_CYP, T_CXM, T_CYM, T_DMIN, T_COUNT };
-enum { U_CVREL = 0, U_UOCN, U_VOCN, U_WATERX, U_WATERY, U_FORCEX, U_FORCEY, U_UMASSDTI, U_FM, U_UAREAR, U_TBU, U_COUNT };
-
-__global__ void __launch_bounds__(PNT, 1)
+template <int NT, int KT, int KU, bool DBG = false>
+__global__ void __launch_bounds__(NT, 1)
 persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k, const __grid_constant__ PersistPlan pp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *sm = reinterpret_cast<double *>(smem_raw);
-  const int tid = threadIdx.x;
+  static_assert(KT % 2 == 0 && KU % 2 == 1 && KU >= 1, "static operands are kept on chip as pairs; cv (U operand 0) always");
+  constexpr int NW = NT / 32, SL = PERSIST_SLOTS;
+  double *sm = reinterpret_cast<double *>(dyn_smem());
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
   const int ttx = tile % pp.ntx, tty = tile / pp.ntx;
   const int bx = pp.bx, by = pp.by;
-  const int i0 = 1 + ttx * bx, j0 = 1 + tty * by;  // first U point / T cell of the tile (dom coords)
+  const int i0 = 1 + ttx * bx, j0 = 1 + tty * by;  // first U point / T cell of the tile (dom coordinates)
   const int tw = bx + 1, nT = pp.nT, nU = pp.nU;    // T pitch
   const int uw = bx + 2;                            // u/v pitch (ring included)
-  const int nring = (bx + 2) * (by + 2);
-  // a tile on the E/N edge of the sub-domain may be narrower than bx x by: its ring sits right
-  // after its last valid column/row
-  const int ebx = min(bx, d.nx - i0 + 1), eby = min(by, d.ny - j0 + 1);
+  // a tile in the last column / row may be narrower than bx x by: its ring sits right after its last valid column / row
+  const int ebx = (d.nx - i0 + 1 < bx) ? d.nx - i0 + 1 : bx, eby = (d.ny - j0 + 1 < by) ? d.ny - j0 + 1 : by;
+  const int shape = (ttx == pp.ntx - 1 ? 1 : 0) | (tty == pp.nty - 1 ? 2 : 0);
+  const int ewT = pp.ewT[shape], ewU = pp.ewU[shape];
+  // who refreshes the ring: the light warps while the others relax their first cell, or (none) the edge warps before their last
+  const int nlw = pp.nlw[shape];
+  const int rw0 = nlw ? pp.lw0[shape] : NW - ewT, nrw = nlw ? nlw : ewT;
+  const bool edge_warp = warp >= NW - ewT, refresh_warp = warp >= rw0 && warp < rw0 + nrw;
 
-  double *su = sm + pp.off_u, *sv = sm + pp.off_v, *sstr = sm + pp.off_str;
-  double *sT = sm + pp.off_T, *sU = sm + pp.off_U;
-  unsigned char *smT = smem_raw + pp.off_mask, *smU = smT + nT;
+  double2 *suv = reinterpret_cast<double2 *>(sm + pp.off_uv);     // (u, v) of the tile with its ring
+  double2 *sstr = reinterpret_cast<double2 *>(sm + pp.off_str);   // 4 x nT: (str1,str5) (str2,str7) (str3,str6) (str4,str8) by T position
+  double2 *ssig = reinterpret_cast<double2 *>(sm + pp.off_sig);   // 6 x nT by pidx: stressp_1..4, stressm_1..4, stress12_1..4 in pairs
+  double2 *sT = reinterpret_cast<double2 *>(sm + pp.off_T);       // KT/2 x nT by pidx
+  double2 *sU = reinterpret_cast<double2 *>(sm + pp.off_U);       // (KU-1)/2 x nU by pidx, then cv
+  double *scv = sm + pp.off_U + (KU - 1) * nU;
 
-  const double *gT[T_COUNT] = {d.strength, d.dxT, d.dyT, d.dxhy, d.dyhx, d.cxp, d.cyp, d.cxm, d.cym, d.DminTarea};
-  const double *gU[U_COUNT] = {nullptr, d.uocn, d.vocn, d.waterx, d.watery, d.forcex, d.forcey, d.umassdti, d.fm, d.uarear, d.TbU};
+  const double *gT[T_COUNT] = {d.cxp, d.cyp, d.cxm, d.cym, d.dxT, d.dyT, d.DminTarea, d.strength, d.dxhy, d.dyhx};
+  const double *gU[U_COUNT] = {nullptr, d.uocn, d.vocn, d.umassdti, d.fm, d.waterx, d.watery, d.forcex, d.forcey, d.uarear, d.TbU};
 
-  // ---------------- prologue: make the tile resident ------------------------------------------------
-  Sigma sg[PCELLS];
-  size_t gcT[PCELLS];  // global index of my T cells
-  bool actT[PCELLS], ownT[PCELLS];
+  // ---------------- prologue: make the tile resident ------------------------------------------------------------------
+  unsigned wT[SL], wU[SL];   // packed table words: t | li << 10 | lj << 16 | pidx << 22
+  unsigned flags = 0;        // bit r: T cell of slot r carries ice; bit 2+r: ... and this tile stores it; bit 4+r: U point of slot r is advanced
 #pragma unroll
-  for (int r = 0; r < PCELLS; ++r) {
-    const int t = tid + r * PNT;
-    const int li = t % tw, lj = t / tw;
-    const int i = i0 + li, j = j0 + lj;
-    const bool in = (t < nT) && (i <= d.nx + 1) && (j <= d.ny + 1);
-    gcT[r] = in ? (size_t)j * d.ld + i : (size_t)d.ld + 1;
-    actT[r] = in && d.maskT[gcT[r]];
-    ownT[r] = actT[r] && (li < bx || i == d.nx + 1) && (lj < by || j == d.ny + 1);
-    if (t < nT) {
-      smT[t] = actT[r];
-#pragma unroll
-      for (int q = 0; q < T_COUNT; ++q)
-        if (q < pp.kT) sT[q * nT + t] = in ? gT[q][gcT[r]] : 0.0;
-    }
-    if (actT[r]) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        sg[r].p[q] = d.sig[0][q][gcT[r]];
-        sg[r].m[q] = d.sig[0][4 + q][gcT[r]];
-        sg[r].s12[q] = d.sig[0][8 + q][gcT[r]];
+  for (int r = 0; r < SL; ++r) {
+    wT[r] = pp.tslot[(shape * SL + r) * NT + tid];
+    wU[r] = pp.uslot[(shape * SL + r) * NT + tid];
+    if (wT[r] != PERSIST_NONE_W) {
+      const int li = (wT[r] >> 10) & 63, lj = (wT[r] >> 16) & 63, p = wT[r] >> 22;
+      const int g = at(d, i0 + li, j0 + lj);
+      if (d.maskT[g]) {
+        flags |= 1u << r;
+        if ((li < bx || i0 + li == d.nx + 1) && (lj < by || j0 + lj == d.ny + 1)) flags |= 4u << r;
       }
+#pragma unroll
+      for (int q = 0; q < KT / 2; ++q) sT[q * nT + p] = mk2(gT[2 * q][g], gT[2 * q + 1][g]);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) ssig[q * nT + p] = mk2(d.sig[0][2 * q][g], d.sig[0][2 * q + 1][g]);
+    }
+    if (wU[r] != PERSIST_NONE_W) {
+      const int li = (wU[r] >> 10) & 63, lj = (wU[r] >> 16) & 63, p = wU[r] >> 22;
+      const int g = at(d, i0 + li, j0 + lj);
+      if (d.maskU[g]) flags |= 16u << r;
+      scv[p] = d.aiu[g] * k.rhow * d.cdn[g];  // aiX*rhow*Cw, left to right (stepu_cv)
+#pragma unroll
+      for (int q = 0; q < (KU - 1) / 2; ++q) sU[q * nU + p] = mk2(gU[1 + 2 * q][g], gU[2 + 2 * q][g]);
     }
   }
-  size_t gcU[PCELLS];
-  bool actU[PCELLS];
-  int edgeU[PCELLS];
-#pragma unroll
-  for (int r = 0; r < PCELLS; ++r) {
-    const int uu = tid + r * PNT;
-    const int li = uu % bx, lj = uu / bx;
-    const int i = i0 + li, j = j0 + lj;
-    const bool in = (uu < nU) && (i <= d.nx) && (j <= d.ny);
-    gcU[r] = in ? (size_t)j * d.ld + i : (size_t)d.ld + 1;
-    actU[r] = in && d.maskU[gcU[r]];
-    // points whose value a neighbouring tile (or a wrapped ghost copy) needs
-    edgeU[r] = in && (li == 0 || li == bx - 1 || lj == 0 || lj == by - 1 || i == d.nx || j == d.ny);
-    if (uu < nU) {
-      smU[uu] = actU[r];
-      if (in) {
-        sU[U_CVREL * nU + uu] = d.aiu[gcU[r]] * k.rhow * d.cdn[gcU[r]];  // aiX*rhow*Cw, left to right
-#pragma unroll
-        for (int q = 1; q < U_COUNT; ++q)
-          if (q < pp.kU) sU[q * nU + uu] = gU[q][gcU[r]];
-      }
-    }
-  }
-  // u, v of the tile and its ring (copy 0 holds the state at entry)
-  for (int c = tid; c < nring; c += PNT) {
+  for (int t = tid; t < 4 * nT; t += NT) sstr[t] = mk2(0.0, 0.0);  // cells off the ice are never visited: `str(:,:,:) = c0` (ice_dyn_evp.F90:1537)
+  for (int c = tid; c < pp.nring; c += NT) {  // u, v of the tile and its ring: copy 0 holds the state at entry
     const int li = c % uw, lj = c / uw;
     const int i = i0 - 1 + li, j = j0 - 1 + lj;
     const bool in = (i <= d.nx + 1) && (j <= d.ny + 1);
-    const size_t g = in ? (size_t)j * d.ld + i : 0;
-    su[c] = in ? d.u[0][g] : 0.0;
-    sv[c] = in ? d.v[0][g] : 0.0;
+    const int g = in ? at(d, i, j) : 0;
+    suv[c] = in ? mk2(d.u[0][g], d.v[0][g]) : mk2(0.0, 0.0);
   }
-  // neighbour tiles whose edge values feed my ring (E-W / N-S wrap where the ghost ring aliases the interior)
+  // neighbour tiles whose edge values feed my ring (E-W / N-S wrap where the ghost ring aliases the interior); lane q < 8 of the
+  // ring-refreshing warps watches neighbour q, which publishes ewU[its shape] times per subcycle
   int nb = -1;
-  if (tid < 8) {
+  unsigned nb_per = 0;
+  if (lane < 8) {
     const int dxs[8] = {-1, 1, 0, 0, -1, 1, -1, 1}, dys[8] = {0, 0, -1, 1, -1, -1, 1, 1};
-    int nx_ = ttx + dxs[tid], ny_ = tty + dys[tid];
+    int nx_ = ttx + dxs[lane], ny_ = tty + dys[lane];
     if (d.wrap_ew) nx_ = (nx_ + pp.ntx) % pp.ntx;
     if (d.wrap_ns) ny_ = (ny_ + pp.nty) % pp.nty;
     if (nx_ >= 0 && nx_ < pp.ntx && ny_ >= 0 && ny_ < pp.nty) nb = ny_ * pp.ntx + nx_;
     if (nb == tile) nb = -1;
+    if (nb >= 0) nb_per = (unsigned)pp.ewU[(nx_ == pp.ntx - 1 ? 1 : 0) | (ny_ == pp.nty - 1 ? 2 : 0)];
   }
   __syncthreads();
 
-  // ---------------- the subcycle loop ----------------------------------------------------------------
+  // per-warp cycle accounting (EVP_B200_PERSIST_DEBUG=1): [0] phase A, [1] of which ring wait + refresh, [2] barrier after A,
+  // [3] phase C, [4] barrier after C
+  long long acc[5] = {0, 0, 0, 0, 0};
+  constexpr bool dbg = DBG;
+  // timeline (DBG): %globaltimer of six events of subcycles PERSIST_TL0 .. PERSIST_TL0+3, per tile, behind the cycle counters
+  unsigned long long *tl = dbg ? reinterpret_cast<unsigned long long *>(pp.dbg + (size_t)pp.ntx * pp.nty * NW * 5) + (size_t)tile * 4 * 8 : nullptr;
+  auto mark = [&](int ksub, int ev) {
+    if (dbg && lane == 0 && ksub >= PERSIST_TL0 && ksub < PERSIST_TL0 + 4) tl[(ksub - PERSIST_TL0) * 8 + ev] = gtime();
+  };
+
+  // one T cell: relax the stresses in place (shared memory), str -> shared memory
+  auto relax = [&](unsigned w) {
+    const int t = w & 1023, li = (w >> 10) & 63, lj = (w >> 16) & 63, p = w >> 22;
+    const int c = (lj + 1) * uw + li + 1;
+    double tv[T_COUNT];
+    if (KT < T_COUNT) {
+      const int g = at(d, i0 + li, j0 + lj);
+#pragma unroll
+      for (int q = KT; q < T_COUNT; ++q) tv[q] = ld_nc_f64(gT[q] + g);  // used late: the L2 round trip hides behind the strain rates
+    }
+#pragma unroll
+    for (int q = 0; q < KT / 2; ++q) { const double2 x = sT[q * nT + p]; tv[2 * q] = x.x; tv[2 * q + 1] = x.y; }
+    const double2 cc = suv[c], ee = suv[c - 1], se = suv[c - uw], ne = suv[c - uw - 1];
+    Sigma sg;
+    {
+      const double2 a = ssig[0 * nT + p], b = ssig[1 * nT + p], m0 = ssig[2 * nT + p], m1 = ssig[3 * nT + p], s0 = ssig[4 * nT + p], s1 = ssig[5 * nT + p];
+      sg.p[0] = a.x; sg.p[1] = a.y; sg.p[2] = b.x; sg.p[3] = b.y;
+      sg.m[0] = m0.x; sg.m[1] = m0.y; sg.m[2] = m1.x; sg.m[3] = m1.y;
+      sg.s12[0] = s0.x; sg.s12[1] = s0.y; sg.s12[2] = s1.x; sg.s12[3] = s1.y;
+    }
+    double str[8];
+    stress_point<true>(cc.x, cc.y, ee.x, ee.y, se.x, se.y, ne.x, ne.y, tv[T_DXT], tv[T_DYT], tv[T_DXHY], tv[T_DYHX], tv[T_CXP], tv[T_CYP], tv[T_CXM],
+                       tv[T_CYM], tv[T_DMIN], tv[T_STRENGTH], k, sg, str);
+    ssig[0 * nT + p] = mk2(sg.p[0], sg.p[1]); ssig[1 * nT + p] = mk2(sg.p[2], sg.p[3]);
+    ssig[2 * nT + p] = mk2(sg.m[0], sg.m[1]); ssig[3 * nT + p] = mk2(sg.m[2], sg.m[3]);
+    ssig[4 * nT + p] = mk2(sg.s12[0], sg.s12[1]); ssig[5 * nT + p] = mk2(sg.s12[2], sg.s12[3]);
+    // paired by the U point that reads them: (str1,str5) at (i,j), (str2,str7) at (i+1,j), (str3,str6) at (i,j+1), (str4,str8) at (i+1,j+1)
+    sstr[0 * nT + t] = mk2(str[0], str[4]); sstr[1 * nT + t] = mk2(str[1], str[6]);
+    sstr[2 * nT + t] = mk2(str[2], str[5]); sstr[3 * nT + t] = mk2(str[3], str[7]);
+  };
+
+  // N U points of this thread at once (N = 2: both slots in one instruction stream; called with at least one of them active)
+  auto advance = [&](auto nconst, const unsigned (&ws)[decltype(nconst)::value], const bool (&act)[decltype(nconst)::value],
+                     const double (&pre)[decltype(nconst)::value][U_COUNT - KU + 1], bool publish_edge, int nxt, bool last) {
+    constexpr int N = decltype(nconst)::value;
+    double uold[N], vold[N], uo[U_COUNT][N], ui[N], vi[N], s[N][8];
+    int cs[N], gs[N], is[N], js[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      // an inactive slot repeats the thread's active one (same operands, nothing stored): operands of an arbitrary cell -- zeros on
+      // land -- would send the square root and both divisions through their out-of-range calls every subcycle
+      const unsigned w = act[n] ? ws[n] : ws[N - 1 - n];
+      const int t0 = w & 1023, li = (w >> 10) & 63, lj = (w >> 16) & 63, p = w >> 22;
+      const int t = lj * tw + li;
+      (void)t0;
+      cs[n] = (lj + 1) * uw + li + 1;
+      is[n] = i0 + li; js[n] = j0 + lj;
+      gs[n] = at(d, is[n], js[n]);
+#pragma unroll
+      for (int q = KU; q < U_COUNT; ++q) uo[q][n] = act[n] ? pre[n][q - KU] : pre[N - 1 - n][q - KU];
+      uo[U_CV][n] = scv[p];
+#pragma unroll
+      for (int q = 0; q < (KU - 1) / 2; ++q) { const double2 x = sU[q * nU + p]; uo[1 + 2 * q][n] = x.x; uo[2 + 2 * q][n] = x.y; }
+      const double2 uv = suv[cs[n]];
+      uold[n] = uv.x; vold[n] = uv.y;
+      const double2 a = sstr[0 * nT + t], b = sstr[1 * nT + t + 1], c2 = sstr[2 * nT + t + tw], e = sstr[3 * nT + t + tw + 1];
+      s[n][0] = a.x; s[n][1] = b.x; s[n][2] = c2.x; s[n][3] = e.x;   // str1(i,j) str2(i+1,j) str3(i,j+1) str4(i+1,j+1)
+      s[n][4] = a.y; s[n][5] = c2.y; s[n][6] = b.y; s[n][7] = e.y;   // str5(i,j) str6(i,j+1) str7(i+1,j) str8(i+1,j+1)
+      ui[n] = 0.0; vi[n] = 0.0;
+      if (k.revp != 0.0 || uold[n] == 0.0 || vold[n] == 0.0) { ui[n] = d.uinit[gs[n]]; vi[n] = d.vinit[gs[n]]; }  // see load_uin (evp_dom.cuh)
+    }
+    UOut o[N];
+    stepu_cv_n<N>(uold, vold, uo[U_CV], uo[U_UOCN], uo[U_VOCN], uo[U_WATERX], uo[U_WATERY], uo[U_FORCEX], uo[U_FORCEY], uo[U_UMASSDTI], uo[U_FM],
+                  uo[U_UAREAR], uo[U_TBU], ui, vi, s, k, o);
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      if (!act[n]) continue;
+      suv[cs[n]] = mk2(o[n].u, o[n].v);
+      if (publish_edge || last) {
+        double *Un = d.u[nxt];
+        double *Vn = d.v[nxt];
+        const int i = is[n], j = js[n], g = gs[n];
+        __stcg(Un + g, o[n].u);
+        __stcg(Vn + g, o[n].v);
+        int ig = -1, jg = -1;
+        if (d.wrap_ew) ig = (i == 1) ? d.nx + 1 : (i == d.nx ? 0 : -1);
+        if (d.wrap_ns) jg = (j == 1) ? d.ny + 1 : (j == d.ny ? 0 : -1);
+        if (ig >= 0) { __stcg(Un + at(d, ig, j), o[n].u); __stcg(Vn + at(d, ig, j), o[n].v); }
+        if (jg >= 0) { __stcg(Un + at(d, i, jg), o[n].u); __stcg(Vn + at(d, i, jg), o[n].v); }
+        if (ig >= 0 && jg >= 0) { __stcg(Un + at(d, ig, jg), o[n].u); __stcg(Vn + at(d, ig, jg), o[n].v); }
+        // a 1-wide interior aliases both ghosts (store_uv)
+        if (d.wrap_ew && d.nx == 1) { __stcg(Un + at(d, 0, j), o[n].u); __stcg(Vn + at(d, 0, j), o[n].v); }
+        if (d.wrap_ns && d.ny == 1) { __stcg(Un + at(d, i, 0), o[n].u); __stcg(Vn + at(d, i, 0), o[n].v); }
+      }
+      if (last) {
+        // only the last subcycle's values survive (ice_dyn_shared.F90:948-965; calc_diag_1d, ice_dyn_core1d.F90:607)
+        const int g = gs[n];
+        d.strintx[g] = o[n].strintx;
+        d.strinty[g] = o[n].strinty;
+        d.taubx[g] = o[n].taubx;
+        d.tauby[g] = o[n].tauby;
+      }
+    }
+  };
+
+  // ---------------- the subcycle loop ------------------------------------------------------------------------------------
   for (int ksub = 0; ksub < pp.ndte; ++ksub) {
     const int cur = ksub & 1, nxt = cur ^ 1;
-    if (ksub > 0) {
-      // wait until every neighbour has published subcycle ksub, then refresh the ring from copy `cur`
-      if (nb >= 0)
-        while (ld_acquire(pp.progress + nb) < (unsigned)ksub) {}
-      __syncthreads();
-      const double *__restrict__ U = d.u[cur];
-      const double *__restrict__ V = d.v[cur];
+    const bool last = (ksub == pp.ndte - 1);
+    long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
+    if (dbg) tk0 = clk();
+    if (warp == 0) mark(ksub, 0);
+
+    // ---- phase A: relax my T cells, str -> shared ----------------------------------------------------------------------
+    // The tile-edge T cells (slot 1 of the edge warps) are the only readers of the ring.  It is refreshed from copy `cur` -- once
+    // every neighbour has published subcycle ksub-1 -- by the light warps at the top of the phase (they have no second cell), or,
+    // when the tile has none, by the edge warps themselves before their second cell.
+    auto refresh_ring = [&]() {
+      long long tw0 = 0;
+      if (dbg) tw0 = clk();
+      if (warp == rw0) {  // one warp polls (lane q watches neighbour q), the other refreshing warps wait for it at a named barrier
+        if (nb >= 0) wait_progress(pp.progress + PERSIST_CTR_STRIDE * nb, nb_per * (unsigned)ksub, pp.err);
+        syncwarp();
+        mark(ksub, 1);
+      }
+      if (nrw > 1) bar_sync_n(2, 32 * nrw);
+      const double *U = d.u[cur];
+      const double *V = d.v[cur];
       const int nedge = 2 * (ebx + 2) + 2 * eby;
-      for (int e = tid; e < nedge; e += PNT) {
+      for (int e = (warp - rw0) * 32 + lane; e < nedge; e += 32 * nrw) {
         int li, lj;
         if (e < ebx + 2) { li = e; lj = 0; }
         else if (e < 2 * (ebx + 2)) { li = e - (ebx + 2); lj = eby + 1; }
         else if (e < 2 * (ebx + 2) + eby) { li = 0; lj = 1 + e - 2 * (ebx + 2); }
         else { li = ebx + 1; lj = 1 + e - 2 * (ebx + 2) - eby; }
-        const int i = i0 - 1 + li, j = j0 - 1 + lj;
-        if (i <= d.nx + 1 && j <= d.ny + 1) {
-          const size_t g = (size_t)j * d.ld + i;
-          su[lj * uw + li] = __ldcg(U + g);  // written by another SM: bypass L1
-          sv[lj * uw + li] = __ldcg(V + g);
-        }
+        const int g = at(d, i0 - 1 + li, j0 - 1 + lj);
+        suv[lj * uw + li] = mk2(ld_cg_f64(U + g), ld_cg_f64(V + g));  // written by another SM: served by L2, never a stale L1 line
       }
-      __syncthreads();
+      if (dbg) acc[1] += clk() - tw0;
+      if (warp == rw0) mark(ksub, 2);
+    };
+    if (ksub > 0 && nlw && refresh_warp) {
+      refresh_ring();
+      bar_arrive_n(1, 32 * (nrw + ewT));
     }
-
-    // ---- stress: relax my T cells, str -> shared -----------------------------------------------------
+    if (flags & 1u) relax(wT[0]);
+    if (ksub > 0 && edge_warp) {
+      if (!nlw) refresh_ring();
+      bar_sync_n(1, nlw ? 32 * (nrw + ewT) : 32 * ewT);
+    }
+    if (flags & 2u) relax(wT[1]);
+    // momentum operands that are not on chip: requested HERE (the asm's memory clobber keeps the loads below the stores above), so the
+    // L2 round trip overlaps with the wait at the barrier instead of heading the momentum phase
+    double upre[SL][U_COUNT - KU + 1];
 #pragma unroll
-    for (int r = 0; r < PCELLS; ++r) {
-      const int t = tid + r * PNT;
-      double str[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (actT[r]) {
-        const int li = t % tw, lj = t / tw;
-        const int c = (lj + 1) * uw + (li + 1);
-        double tv[T_COUNT];
+    for (int r = 0; r < SL; ++r) {
 #pragma unroll
-        for (int q = 0; q < T_COUNT; ++q) tv[q] = (q < pp.kT) ? sT[q * nT + t] : __ldg(gT[q] + gcT[r]);
-        stress_point(su[c], sv[c], su[c - 1], sv[c - 1], su[c - uw], sv[c - uw], su[c - uw - 1], sv[c - uw - 1],
-                     tv[T_DXT], tv[T_DYT], tv[T_DXHY], tv[T_DYHX], tv[T_CXP], tv[T_CYP], tv[T_CXM], tv[T_CYM],
-                     tv[T_DMIN], tv[T_STRENGTH], k, sg[r], str);
-      }
-      if (t < nT) {
+      for (int q = 0; q < U_COUNT - KU + 1; ++q) upre[r][q] = 0.0;
+      if (flags & (16u << r)) {
+        const int g = at(d, i0 + (int)((wU[r] >> 10) & 63), j0 + (int)((wU[r] >> 16) & 63));
 #pragma unroll
-        for (int q = 0; q < 8; ++q) sstr[q * nT + t] = str[q];
+        for (int q = KU; q < U_COUNT; ++q) upre[r][q - KU] = ld_nc_f64_pinned(gU[q] + g);
       }
     }
+    if (dbg) tk1 = clk();
     __syncthreads();
+    if (dbg) tk2 = clk();
+    if (warp == 0) mark(ksub, 3);
+    if (warp == NW - 1) mark(ksub, 6);
 
-    // ---- momentum: advance my U points ---------------------------------------------------------------
-    const bool last = (ksub == pp.ndte - 1);
+    // ---- phase C: advance my U points -----------------------------------------------------------------------------------
+    if (warp < ewU) {
+      // slot 0 of the first ewU warps: the points other tiles (or wrapped ghost copies) read.  Publish: the stores of this warp's
+      // lanes are ordered before lane 0's fence by the warp barrier, the fence makes them visible at gpu scope before the counter moves
+      const unsigned w1[1] = {wU[0]};
+      const bool a1[1] = {(flags & 16u) != 0};
+      double p1[1][U_COUNT - KU + 1], p2[1][U_COUNT - KU + 1];
 #pragma unroll
-    for (int r = 0; r < PCELLS; ++r) {
-      if (actU[r]) {
-        const int uu = tid + r * PNT;
-        const int li = uu % bx, lj = uu / bx;
-        const int c = (lj + 1) * uw + (li + 1);
-        const int t = lj * tw + li;
-        double uv_[U_COUNT];
-#pragma unroll
-        for (int q = 0; q < U_COUNT; ++q) uv_[q] = (q < pp.kU) ? sU[q * nU + uu] : __ldg(gU[q] + gcU[r]);
-        double ui = 0.0, vi = 0.0;
-        if (pp.use_init) { ui = __ldg(d.uinit + gcU[r]); vi = __ldg(d.vinit + gcU[r]); }
-        const double uold = su[c], vold = sv[c];
-        // stepu_point with aiX*rhow*Cw folded: pass Cw = 1-free form by giving aiX=cvrel, rhow*Cw via params is not
-        // bit-safe, so the product is formed here exactly as (aiX*rhow)*Cw was in the prologue.
-        const double du = uv_[U_UOCN] - uold, dv = uv_[U_VOCN] - vold;
-        const double vrel = uv_[U_CVREL] * sqrt(du * du + dv * dv);
-        const double taux = vrel * uv_[U_WATERX];
-        const double tauy = vrel * uv_[U_WATERY];
-        const double Cb = uv_[U_TBU] / (sqrt(uold * uold + vold * vold) + k.u0);
-        const double cca = (k.brlx + k.revp) * uv_[U_UMASSDTI] + vrel * k.cosw + Cb;
-        const double ccb = uv_[U_FM] + copysign(1.0, uv_[U_FM]) * vrel * k.sinw;
-        const double ab2 = cca * cca + ccb * ccb;
-        const double strintx = uv_[U_UAREAR] * (sstr[0 * nT + t] + sstr[1 * nT + t + 1] + sstr[2 * nT + t + tw] + sstr[3 * nT + t + tw + 1]);
-        const double strinty = uv_[U_UAREAR] * (sstr[4 * nT + t] + sstr[5 * nT + t + tw] + sstr[6 * nT + t + 1] + sstr[7 * nT + t + tw + 1]);
-        const double cc1 = strintx + uv_[U_FORCEX] + taux + uv_[U_UMASSDTI] * (k.brlx * uold + k.revp * ui);
-        const double cc2 = strinty + uv_[U_FORCEY] + tauy + uv_[U_UMASSDTI] * (k.brlx * vold + k.revp * vi);
-        const double un = (cca * cc1 + ccb * cc2) / ab2;
-        const double vn = (cca * cc2 - ccb * cc1) / ab2;
-        su[c] = un;
-        sv[c] = vn;
-        if (edgeU[r] || last) {
-          const int i = i0 + li, j = j0 + lj;
-          double *__restrict__ Un = d.u[nxt];
-          double *__restrict__ Vn = d.v[nxt];
-          const size_t g = gcU[r];
-          __stcg(Un + g, un);
-          __stcg(Vn + g, vn);
-          int ig = -1, jg = -1;
-          if (d.wrap_ew) ig = (i == 1) ? d.nx + 1 : (i == d.nx ? 0 : -1);
-          if (d.wrap_ns) jg = (j == 1) ? d.ny + 1 : (j == d.ny ? 0 : -1);
-          if (ig >= 0) { __stcg(Un + (size_t)j * d.ld + ig, un); __stcg(Vn + (size_t)j * d.ld + ig, vn); }
-          if (jg >= 0) { __stcg(Un + (size_t)jg * d.ld + i, un); __stcg(Vn + (size_t)jg * d.ld + i, vn); }
-          if (ig >= 0 && jg >= 0) { __stcg(Un + (size_t)jg * d.ld + ig, un); __stcg(Vn + (size_t)jg * d.ld + ig, vn); }
-        }
-        if (last) {
-          d.strintx[gcU[r]] = strintx;
-          d.strinty[gcU[r]] = strinty;
-          d.taubx[gcU[r]] = -un * Cb;
-          d.tauby[gcU[r]] = -vn * Cb;
-        }
-      }
+      for (int q = 0; q < U_COUNT - KU + 1; ++q) { p1[0][q] = upre[0][q]; p2[0][q] = upre[1][q]; }
+      if (a1[0]) advance(std::integral_constant<int, 1>{}, w1, a1, p1, true, nxt, last);
+      syncwarp();
+      if (lane == 0) publish_progress(pp.progress + PERSIST_CTR_STRIDE * tile);
+      if (warp == 0) mark(ksub, 4);
+      const unsigned w2[1] = {wU[1]};
+      const bool a2[1] = {(flags & 32u) != 0};
+      if (a2[0]) advance(std::integral_constant<int, 1>{}, w2, a2, p2, false, nxt, last);
+    } else if (flags & 48u) {
+      const unsigned w2[2] = {wU[0], wU[1]};
+      const bool a2[2] = {(flags & 16u) != 0, (flags & 32u) != 0};
+      advance(std::integral_constant<int, 2>{}, w2, a2, upre, false, nxt, last);
     }
+    if (dbg) tk3 = clk();
     __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      st_release(pp.progress + tile, (unsigned)(ksub + 1));
-    }
+    if (warp == 0) mark(ksub, 5);
+    if (dbg) { acc[0] += tk1 - tk0; acc[2] += tk2 - tk1; acc[3] += tk3 - tk2; acc[4] += clk() - tk3; }
+  }
+  if (dbg && lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) pp.dbg[((size_t)tile * NW + warp) * 5 + q] = acc[q];
   }
 
-  // ---------------- epilogue: the carried stress state goes back to copy (ndte & 1) -------------------
+  // ---------------- epilogue: the carried stress state goes back to copy (ndte & 1) ------------------------------------------
   const int fin = pp.ndte & 1;
 #pragma unroll
-  for (int r = 0; r < PCELLS; ++r) {
-    if (ownT[r]) {
+  for (int r = 0; r < SL; ++r)
+    if (flags & (4u << r)) {
+      const int li = (wT[r] >> 10) & 63, lj = (wT[r] >> 16) & 63, p = wT[r] >> 22;
+      const int g = at(d, i0 + li, j0 + lj);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        d.sig[fin][q][gcT[r]] = sg[r].p[q];
-        d.sig[fin][4 + q][gcT[r]] = sg[r].m[q];
-        d.sig[fin][8 + q][gcT[r]] = sg[r].s12[q];
-      }
+      for (int q = 0; q < 6; ++q) { const double2 x = ssig[q * nT + p]; d.sig[fin][2 * q][g] = x.x; d.sig[fin][2 * q + 1][g] = x.y; }
     }
-  }
 }
 
-size_t persist_smem_bytes(const PersistPlan &pp) { return pp.smem_bytes; }
-
-cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s) {
+#ifndef EVP_HOST_EMU  // launcher: not part of the host emulation (tests/emu_persist.cpp)
+template <int KT, int KU, bool DBG>
+static cudaError_t launch_persist_t(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s) {
   static bool attr_set = false;
+  auto kern = persist_kernel<PERSIST_THREADS, KT, KU, DBG>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   void *args[] = {(void *)&d, (void *)&p, (void *)&pp};
-  return cudaLaunchCooperativeKernel((const void *)persist_kernel, dim3(pp.ntx * pp.nty), dim3(PNT), args, pp.smem_bytes, s);
+  return cudaLaunchCooperativeKernel((const void *)kern, dim3(pp.ntx * pp.nty), dim3(PERSIST_THREADS), args, pp.smem_bytes, s);
 }
+
+cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s) {
+  if (pp.nthreads != PERSIST_THREADS) return cudaErrorInvalidValue;
+  if (pp.kT == 10 && pp.kU == 11) return pp.dbg ? launch_persist_t<10, 11, true>(d, p, pp, s) : launch_persist_t<10, 11, false>(d, p, pp, s);
+  if (pp.kT == 6 && pp.kU == 3) return pp.dbg ? launch_persist_t<6, 3, true>(d, p, pp, s) : launch_persist_t<6, 3, false>(d, p, pp, s);
+  return cudaErrorInvalidValue;
+}
+#endif  // EVP_HOST_EMU
 
 }  // namespace EVP_NS
 }  // namespace evp

@@ -46,6 +46,11 @@ __device__ __forceinline__ double ld_f64(const double *p) {
   asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ double ld_nc_f64_pinned(const double *p) {  // ... and not to be moved across memory operations either
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ double ld_nc_f64(const double *p) {  // never written while the loop runs
   double v;
   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
@@ -82,6 +87,42 @@ __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// KERNEL_PERSISTENT (evp_persist.cu): a named barrier over n threads, the warp barrier, the dynamic shared memory of the CTA, and the
+// bounded wait on a neighbour tile's progress counter (co-resident CTAs of one cooperative launch: the bound only turns a
+// programming error into an error code instead of a hung GPU)
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void syncwarp() { __syncwarp(); }
+// cycle counter that stays where it is written (the memory clobber pins it against barriers and memory operations)
+__device__ __forceinline__ long long clk() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
+__device__ __forceinline__ unsigned char *dyn_smem() {
+  extern __shared__ __align__(16) unsigned char evp_dyn_smem[];
+  return evp_dyn_smem;
+}
+// Tile progress counters (KERNEL_PERSISTENT).  Publishing is one release-add by one lane per warp; waiting polls with RELAXED loads
+// (an acquire load invalidates the SM's L1 on every iteration; one warp per tile polls, counters sit on separate L2 lines) and turns
+// into an acquire with one fence after the value has been seen.
+__device__ __forceinline__ void publish_progress(unsigned *p) { asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory"); }
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void wait_progress(const unsigned *p, unsigned want, int *err) {
+  if (ld_relaxed_gpu(p) < want) {
+    const unsigned long long t0 = gtime();
+    while (ld_relaxed_gpu(p) < want) {
+      if (gtime() - t0 > 2000000000ULL) { atomicExch(err, 1); break; }
+    }
+  }
+  fence_acq_rel_gpu();
+}
+
 #else  // EVP_HOST_EMU: see the header comment; emu:: is provided by tests/cuda_emu.h
 
 inline unsigned long long gtime() { return 0; }
@@ -96,6 +137,7 @@ inline void wait_flag(const unsigned long long *flag, unsigned long long want, i
 }
 inline double ld_f64(const double *p) { return *(const volatile double *)p; }
 inline double ld_nc_f64(const double *p) { return *p; }
+inline double ld_nc_f64_pinned(const double *p) { return *p; }
 inline double ld_cg_f64(const double *p) { return *(const volatile double *)p; }
 inline unsigned ld_nc_u8(const unsigned char *p) { return *p; }
 inline void cp_async8(double *smem, const double *g) { *smem = *g; }
@@ -105,6 +147,19 @@ inline void bar_arrive64(int id) { emu::bar_arrive(id, 64); }
 inline void bar_sync64(int id) { emu::bar_sync(id, 64); }
 inline unsigned ld_acquire_gpu(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline void st_release_gpu(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+
+inline void bar_sync_n(int id, int n) { emu::bar_sync(id, n); }
+inline void bar_arrive_n(int id, int n) { emu::bar_arrive(id, n); }
+inline void syncwarp() { emu::syncwarp(); }
+inline long long clk() { return 0; }
+inline unsigned char *dyn_smem() { return emu::dyn_smem(); }
+inline void publish_progress(unsigned *p) { __atomic_fetch_add(p, 1u, __ATOMIC_RELEASE); }
+inline void wait_progress(const unsigned *p, unsigned want, int *err) {
+  for (long spins = 0; ld_acquire_gpu(p) < want; ++spins) {
+    if (spins > 200000000L) { *err = 1; break; }
+    emu::yield();
+  }
+}
 
 #endif
 

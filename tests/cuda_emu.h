@@ -45,18 +45,30 @@ struct NamedBar { std::atomic<int> count; std::atomic<unsigned> gen; };
 static NamedBar named[16];
 static int cta_order = 0;  // 0 forwards, 1 backwards, 2 alternating from both ends
 
+// CTAs that run CONCURRENTLY (launch_concurrent, for kernels whose CTAs wait for each other): each CTA has its own barriers and
+// its own dynamic shared memory; the sequential launch() above keeps using the process-wide ones
+struct Cta {
+  pthread_barrier_t bar;
+  NamedBar named[16];
+  NamedBar warp[MAXT / 32];
+  std::vector<unsigned char> smem;
+};
+thread_local Cta *cta = nullptr;
+
 inline void yield() { sched_yield(); }
-inline void syncthreads() { pthread_barrier_wait(&cta_barrier); }
+inline void syncthreads() { pthread_barrier_wait(cta ? &cta->bar : &cta_barrier); }
 inline void bar_arrive(int id, int n) {
-  NamedBar &b = named[id];
+  NamedBar &b = cta ? cta->named[id] : named[id];
   if (b.count.fetch_add(1) + 1 == n) { b.count.store(0); b.gen.fetch_add(1); }
 }
-inline void bar_sync(int id, int n) {
-  NamedBar &b = named[id];
+inline void bar_wait_on(NamedBar &b, int n) {
   const unsigned g = b.gen.load();
   if (b.count.fetch_add(1) + 1 == n) { b.count.store(0); b.gen.fetch_add(1); }
   else while (b.gen.load() == g) yield();
 }
+inline void bar_sync(int id, int n) { bar_wait_on(cta ? cta->named[id] : named[id], n); }
+inline void syncwarp() { if (cta) bar_wait_on(cta->warp[lin / 32], 32); }   // (sequential mode: kernels there use shuffles only)
+inline unsigned char *dyn_smem() { return cta ? cta->smem.data() : nullptr; }
 // publish v, then read the value lane `src` (linear id inside the CTA) published in the same shuffle.  A lane may run up to
 // RING shuffles ahead of a reader before it overwrites a slot; CTA barriers bound the lead (kernels here: <= 12).
 inline double shfl_from(double v, int src) {
@@ -97,6 +109,34 @@ inline void launch(Idx grid, Idx block, F kernel) {
     });
   for (auto &x : th) x.join();
   pthread_barrier_destroy(&cta_barrier);
+}
+
+// every CTA of the grid at once: grid.x * block.x host threads (1-D), `smem_bytes` of dynamic shared memory per CTA.  For kernels
+// with waits between CTAs (evp_persist.cu); keep grid and block small.
+template <class F>
+inline void launch_concurrent(int nctas, int nthreads, size_t smem_bytes, F kernel) {
+  std::vector<Cta> ctas(nctas);
+  for (auto &c : ctas) {
+    pthread_barrier_init(&c.bar, nullptr, nthreads);
+    for (auto &b : c.named) { b.count.store(0); b.gen.store(0); }
+    for (auto &b : c.warp) { b.count.store(0); b.gen.store(0); }
+    c.smem.assign(smem_bytes + 16, 0xff);   // poisoned: a read of something never written shows up as a NaN
+  }
+  std::vector<std::thread> th;
+  th.reserve((size_t)nctas * nthreads);
+  for (int q = 0; q < nctas; ++q)
+    for (int t = 0; t < nthreads; ++t)
+      th.emplace_back([&, q, t] {
+        cta = &ctas[q];
+        lin = t;
+        tid = {t, 0, 0};
+        bdim = {nthreads, 1, 1};
+        gdim = {nctas, 1, 1};
+        bid = {q, 0, 0};
+        kernel();
+      });
+  for (auto &x : th) x.join();
+  for (auto &c : ctas) pthread_barrier_destroy(&c.bar);
 }
 }  // namespace emu
 
