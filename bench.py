@@ -373,17 +373,19 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         per_gpu_cells = sx * sy
         nl_step = launches / args.steps
-        kname = "persistent" if args.kernel == "persistent" else "fused"
+        persistent = (nl_step == 1 and ndte > 1)   # the library ran the whole loop as one cooperative launch (KERNEL_PERSISTENT, AUTO's choice when it fits)
+        kname = "persistent" if persistent else "fused"
         ctr = kernel_counters(kname) or {}
         # dominant kernel: the subcycle kernel; one launch advances the rank's sub-domain by ndte/launches subcycles
-        sub_per_launch = ndte if args.kernel == "persistent" else (0.5 if args.kernel == "split" else 1.0)
+        sub_per_launch = ndte if persistent else (0.5 if args.kernel == "split" else 1.0)
         ach = per_gpu_cells * ndte * ALGO_BYTES_PER_CELL_SUBCYCLE / (kernel_ms * 1e-3) / 1e9
         us_per_subcycle = kernel_ms * 1e3 / ndte
         cold, warm = ctr.get("dram_bytes_per_launch_cold"), ctr.get("dram_bytes_per_launch_warm")
         same_shape = (args.workload == "gx1" and (sx, sy) == (320, 384))
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 # the loop is 1 cold launch + (ndte-1) launches that find the working set in L2: the launch-weighted mean
-                "traffic": (None if not (same_shape and cold and warm) else (cold + (ndte - 1) * warm) / ndte),
+                # (persistent kernel: ONE launch per step on a flushed L2, so the cold capture is the state of every timed launch)
+                "traffic": (None if not (same_shape and cold) else cold if persistent else None if not warm else (cold + (ndte - 1) * warm) / ndte),
                 "traffic_cold": cold if same_shape else None, "traffic_warm": warm if same_shape else None,
                 "traffic_how": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures of this "
                                "kernel at gx1 (cold: caches flushed by ncu; warm: --cache-control none, the state of 239 of 240 launches); "
@@ -401,7 +403,7 @@ def run_ours(args):
                 "scaling": layout_of(args) if world > 1 else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_string(args, world, ndte),
-                           "kernel": args.kernel, "mode": args.mode,
+                           "kernel": args.kernel + (" -> persistent (one cooperative launch per step)" if persistent and args.kernel == "auto" else ""), "mode": args.mode,
                            "l2": "flushed between timed steps (256 MiB memset); all ranks barrier before every timed step",
                            "layout": desc, "derived_geometry_mismatches": bad},
                 "parity": parity,

@@ -171,6 +171,7 @@ struct Ctx {
   // KERNEL_PERSISTENT
   PersistPlan pplan{};
   bool persist_ok = false;
+  bool persist_p2p = false;  // the persistent kernel's in-kernel NVLink halo form (neighbour ranks)
   std::string persist_why;
   unsigned *d_progress = nullptr;
   unsigned *d_ptab[2] = {nullptr, nullptr};  // (slot, thread) -> cell tables
@@ -249,7 +250,13 @@ static int upload_vec(T *&dptr, const std::vector<T> &h) {
 // KERNEL_PERSISTENT: tiling, shared-memory layout and (slot, thread) tables (evp_persist_plan.h)
 static int plan_persist() {
   g.persist_ok = false;
-  if (g.halo.n_dst != 0 || !g.halo.peers.empty()) { g.persist_why = "the halo needs an exchange between subcycles (neighbour ranks or tripole fold)"; return 0; }
+  // between subcycles the tiles exchange through the rank's own arrays; neighbour ranks are reached by in-kernel NVLink stores
+  // (P2PState).  A staged exchange (NCCL fallback) or a tripole fold kernel between subcycles cannot run inside one launch.
+  const bool halo_in_kernel = g.p2p.enabled && g.p2p.npeers > 0 && g.p2p.fold_n == 0 && g.ns != EVP_B200_BNDY_TRIPOLE;
+  if ((g.halo.n_dst != 0 || !g.halo.peers.empty()) && !halo_in_kernel) {
+    g.persist_why = "the halo needs an exchange between subcycles (staged exchange with neighbour ranks, or tripole fold)";
+    return 0;
+  }
   PersistPlan pp{};
   PersistTables tb;
   if (!persist_plan(g.dom.nx, g.dom.ny, g.num_sms, PERSIST_THREADS, 232448, pp, tb, g.persist_why)) return 0;
@@ -260,6 +267,11 @@ static int plan_persist() {
   CK(cudaMalloc(&g.d_perr, sizeof(int)));
   CK(cudaMemset(g.d_perr, 0, sizeof(int)));
   pp.tslot = dt; pp.uslot = du; pp.progress = g.d_progress; pp.err = g.d_perr;
+  pp.n_sig = 0;
+  for (int ty = 0; ty < pp.nty; ++ty)
+    for (int tx = 0; tx < pp.ntx; ++tx)
+      if (tx == 0 || tx == pp.ntx - 1 || ty == 0 || ty == pp.nty - 1) pp.n_sig += pp.ewU[(tx == pp.ntx - 1 ? 1 : 0) | (ty == pp.nty - 1 ? 2 : 0)];
+  g.persist_p2p = halo_in_kernel;
   if (getenv("EVP_B200_PERSIST_DEBUG")) {  // per-warp cycle accounting, printed after every loop
     CK(cudaMalloc(&g.d_pdbg, sizeof(long long) * (5 * (PERSIST_THREADS / 32) + 32) * pp.ntx * pp.nty));
     CK(cudaMemset(g.d_pdbg, 0, sizeof(long long) * (5 * (PERSIST_THREADS / 32) + 32) * pp.ntx * pp.nty));
@@ -419,6 +431,8 @@ static int do_init(const evp_b200_grid_t *gr) {
     const unsigned long long ns = (unsigned long long)(std::max(atof(e), 0.001) * 1e9);
     CK(exact::set_wait_timeout(ns));
     CK(fast::set_wait_timeout(ns));
+    CK(exact::set_wait_timeout_persist(ns));
+    CK(fast::set_wait_timeout_persist(ns));
   }
   CK(cudaDeviceGetAttribute(&g.num_sms, cudaDevAttrMultiProcessorCount, g.device));
   // ---- persistent tiling ---------------------------------------------------------------------------
@@ -556,9 +570,12 @@ static int fused_form(const evp_b200_params_t *p) {
   return stream ? (g.derived_ok ? 2 : 1) : 0;
 }
 
+// AUTO: the persistent kernel wherever a sub-domain's carried state fits on chip (one tile per SM; measured on B200 at gx1
+// 1.80 vs 2.20 ms per step, gx3 0.52 vs 0.63), else the fused kernel in the form fused_form() picks
 static int choose_kernel(const evp_b200_params_t *p) {
   int kern = p->kernel;
-  if (kern == EVP_B200_KERNEL_AUTO || kern == EVP_B200_KERNEL_FUSED_STREAM || kern == EVP_B200_KERNEL_FUSED_RESIDENT) kern = EVP_B200_KERNEL_FUSED;
+  if (kern == EVP_B200_KERNEL_AUTO) kern = g.persist_ok ? EVP_B200_KERNEL_PERSISTENT : EVP_B200_KERNEL_FUSED;
+  if (kern == EVP_B200_KERNEL_FUSED_STREAM || kern == EVP_B200_KERNEL_FUSED_RESIDENT) kern = EVP_B200_KERNEL_FUSED;
   return kern;
 }
 
@@ -576,10 +593,21 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
       pp.ndte = p->ndte;
       pp.use_init = (p->revp != 0.0);
       CK(cudaMemsetAsync(g.d_progress, 0, sizeof(unsigned) * PERSIST_CTR_STRIDE * pp.ntx * pp.nty, g.stream));
-      CK(exact ? exact::launch_persist(g.dom, k, pp, g.stream) : fast::launch_persist(g.dom, k, pp, g.stream));
+      const P2PParams *px = g.persist_p2p ? &g.p2p.prm : nullptr;
+      if (px) {  // loop hand-shake with the neighbour GPUs around the one launch, as for the fused kernel below
+        CK(cudaMemsetAsync(g.p2p.d_done, 0, sizeof(unsigned long long), g.stream));
+        CK(exact::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -1, 0, 0, g.stream));
+        ++nl;
+      }
+      CK(exact ? exact::launch_persist(g.dom, k, pp, px, g.stream) : fast::launch_persist(g.dom, k, pp, px, g.stream));
+      ++nl;
+      if (px) {
+        CK(exact::launch_fused_p2p(g.dom, k, g.p2p.prm, 0, -2 - p->ndte, 0, 0, g.stream));
+        ++nl;
+      }
     }
     *cur_end = p->ndte & 1;
-    *launches = p->ndte > 0 ? 1 : 0;
+    *launches = nl;
     return 0;
   }
   const bool p2p = g.p2p.enabled && kern == EVP_B200_KERNEL_FUSED;

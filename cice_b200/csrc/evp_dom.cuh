@@ -27,6 +27,21 @@ __device__ __forceinline__ void store_uv(const Dom &d, double *__restrict__ U, d
   if (d.wrap_ns && d.ny == 1) { U[at(d, i, 0)] = un; V[at(d, i, 0)] = vn; }
 }
 
+// row index of the push CSR for a U point whose value some other sub-domain (or this one's own ghost ring, across a tripole
+// fold) needs: the boundary points (i==1 | i==nx | j==1 | j==ny) and, on ranks below a tripole fold, row `fold_row` = ny-1
+// (the ghost row ny+1 is fed from it, ice_boundary.F90:1689-1722).  Host twin: P2PState::setup (evp_halo.cu).  Shared by fused_kernel<..,P2P> and
+// persist_kernel<..,P2P>.
+__device__ __forceinline__ bool is_push_point(const Dom &d, int fold_row, int i, int j) {
+  return i == 1 || i == d.nx || j == 1 || j == d.ny || j == fold_row;
+}
+__device__ __forceinline__ int edge_index(const Dom &d, int fold_row, int i, int j) {
+  if (j == 1) return i - 1;
+  if (j == d.ny) return d.nx + i - 1;
+  if (j == fold_row) return 2 * d.nx + 2 * (d.ny - 2) + (i - 1);
+  if (i == 1) return 2 * d.nx + (j - 2);
+  return 2 * d.nx + (d.ny - 2) + (j - 2);
+}
+
 // operands of one U point.  uvel_init/vvel_init enter stepu only as revp * uvel_init (ice_dyn_shared.F90:957-958);
 // in classic EVP revp = 0 and the product is a zero that can change the sum brlx*uold + 0 only when that sum is
 // itself a zero, so the two arrays are read only then (or when revp != 0): same bits, 16 B per point less traffic.

@@ -108,6 +108,7 @@ struct PersistPlan {
   int kT, kU;     // how many static T / U arrays the instantiation keeps in shared memory
   int use_init;   // revised EVP reads uvel_init/vvel_init
   int nthreads;   // threads per CTA the tables were built for
+  int n_sig;      // multi-GPU: publishing warps of all tiles on the sub-domain edge (what the hand-over counter reaches per subcycle)
   unsigned *progress;   // [ntx*nty * PERSIST_CTR_STRIDE] edge-U warps that have published, summed over the subcycles so far
   // [4 tile shapes][PERSIST_SLOTS * nthreads] packed words (evp_persist_plan.h: persist_word); shape = (last column) + 2*(last row)
   const unsigned *tslot, *uslot;
@@ -131,9 +132,10 @@ struct PersistPlan {
   cudaError_t launch_fold(const P2PParams &pp, double *U, double *V, const int *dst, const int *c1, const int *c2, const signed char *code, int n, int ksub, int pdl, cudaStream_t s); \
   int fold_max_entries(); \
   cudaError_t set_wait_timeout(unsigned long long ns); \
+  cudaError_t set_wait_timeout_persist(unsigned long long ns); \
   cudaError_t set_metric(const double *HTN, const double *HTE, double deltamin); \
   cudaError_t launch_metric_verify(const Dom &d, const double *HTN, const double *HTE, double deltamin, int skip_e, int skip_n, int *mismatches, cudaStream_t s); \
-  cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s); \
+  cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, const P2PParams *px, cudaStream_t s); \
   cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \
   cudaError_t launch_cgrid_static(const CDom &d, double *rhalf_dyE, double *r_dxE, double *rhalf_dxN, double *r_dyN, double *uareaavgr, cudaStream_t s); \
   cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur, cudaStream_t s, int *launches);  \

@@ -193,20 +193,6 @@ cudaError_t launch_stepu(const Dom &d, const KParams &p, int cur, cudaStream_t s
 // FBX x FBY threads relax an FBX x FBY patch of T cells and advance the (FBX-1) x (FBY-1) U points it closes.
 // MINB = CTAs per SM the register allocation is bounded for.
 
-// row index of the push CSR for a U point whose value some other sub-domain (or this one's own ghost ring, across a tripole
-// fold) needs: the boundary points (i==1 | i==nx | j==1 | j==ny) and, on ranks below a tripole fold, row `fold_row` = ny-1
-// (the ghost row ny+1 is fed from it, ice_boundary.F90:1689-1722).  Host twin: P2PState::setup (evp_halo.cu).
-__device__ __forceinline__ bool is_push_point(const Dom &d, int fold_row, int i, int j) {
-  return i == 1 || i == d.nx || j == 1 || j == d.ny || j == fold_row;
-}
-__device__ __forceinline__ int edge_index(const Dom &d, int fold_row, int i, int j) {
-  if (j == 1) return i - 1;
-  if (j == d.ny) return d.nx + i - 1;
-  if (j == fold_row) return 2 * d.nx + 2 * (d.ny - 2) + (i - 1);
-  if (i == 1) return 2 * d.nx + (j - 2);
-  return 2 * d.nx + (d.ny - 2) + (j - 2);
-}
-
 // Derived geometry (SPEC bit 5, after evp_b200_set_metric).
 // Seven of the ten static T-cell arrays are functions of the two metric arrays HTN, HTE and of dxT, dyT
 // (ice_dyn_shared.F90:384-388, 401-441): on sub-domains that stream from HBM, reading HTN/HTE (their i-1 / j-1 neighbours come

@@ -39,9 +39,13 @@ enum { U_CV = 0, U_UOCN, U_VOCN, U_UMASSDTI, U_FM, U_WATERX, U_WATERY, U_FORCEX,
 
 __device__ __forceinline__ double2 mk2(double a, double b) { double2 r; r.x = a; r.y = b; return r; }
 
-template <int NT, int KT, int KU, bool DBG = false>
+// P2P: the sub-domain has neighbour GPUs.  Their edge velocities arrive in this rank's ghost cells as NVLink stores (the peers' tiles
+// push them exactly like fused_kernel<..,P2P> does, evp_kernels.cu), per-peer epoch flags say when; this rank's tiles on the
+// sub-domain edge push theirs, count themselves done, and the last one hands over with one system-scope fence + flag stores.
+template <int NT, int KT, int KU, bool DBG = false, bool P2P = false>
 __global__ void __launch_bounds__(NT, 1)
-persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k, const __grid_constant__ PersistPlan pp) {
+persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k, const __grid_constant__ PersistPlan pp,
+               const __grid_constant__ P2PParams px) {
   static_assert(KT % 2 == 0 && KU % 2 == 1 && KU >= 1, "static operands are kept on chip as pairs; cv (U operand 0) always");
   constexpr int NW = NT / 32, SL = PERSIST_SLOTS;
   double *sm = reinterpret_cast<double *>(dyn_smem());
@@ -60,6 +64,9 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
   const int nlw = pp.nlw[shape];
   const int rw0 = nlw ? pp.lw0[shape] : NW - ewT, nrw = nlw ? nlw : ewT;
   const bool edge_warp = warp >= NW - ewT, refresh_warp = warp >= rw0 && warp < rw0 + nrw;
+  // tiles on the sub-domain edge talk to the neighbour GPUs
+  const bool rank_edge = P2P && (ttx == 0 || ttx == pp.ntx - 1 || tty == 0 || tty == pp.nty - 1);
+  const unsigned long long ebase = P2P ? *px.epoch_base : 0ULL;
 
   double2 *suv = reinterpret_cast<double2 *>(sm + pp.off_uv);     // (u, v) of the tile with its ring
   double2 *sstr = reinterpret_cast<double2 *>(sm + pp.off_str);   // 4 x nT: (str1,str5) (str2,str7) (str3,str6) (str4,str8) by T position
@@ -215,6 +222,15 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
         // a 1-wide interior aliases both ghosts (store_uv)
         if (d.wrap_ew && d.nx == 1) { __stcg(Un + at(d, 0, j), o[n].u); __stcg(Vn + at(d, 0, j), o[n].v); }
         if (d.wrap_ns && d.ny == 1) { __stcg(Un + at(d, i, 0), o[n].u); __stcg(Vn + at(d, i, 0), o[n].v); }
+        if (P2P && publish_edge && is_push_point(d, 0, i, j)) {
+          // a ghost cell of up to three other sub-domains: stored there over NVLink right away (push table: evp_halo.cu)
+          const int e = edge_index(d, 0, i, j);
+          for (int q = px.push_start[e]; q < px.push_start[e + 1]; ++q) {
+            const int pr = px.push_peer[q] & 0xff, dst = px.push_dst[q];
+            px.peer_u[nxt][pr][dst] = o[n].u;
+            px.peer_v[nxt][pr][dst] = o[n].v;
+          }
+        }
       }
       if (last) {
         // only the last subcycle's values survive (ice_dyn_shared.F90:948-965; calc_diag_1d, ice_dyn_core1d.F90:607)
@@ -244,6 +260,8 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
       if (dbg) tw0 = clk();
       if (warp == rw0) {  // one warp polls (lane q watches neighbour q), the other refreshing warps wait for it at a named barrier
         if (nb >= 0) wait_progress(pp.progress + PERSIST_CTR_STRIDE * nb, nb_per * (unsigned)ksub, pp.err);
+        // ... and lanes 8.. the neighbour GPUs: their stores of subcycle ksub-1 into this rank's ghost cells have arrived
+        if (rank_edge && lane >= 8 && lane - 8 < px.npeers) wait_flag(px.my_flags + px.peer_rank[lane - 8], ebase + (unsigned long long)ksub, px.err);
         syncwarp();
         mark(ksub, 1);
       }
@@ -301,9 +319,25 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
       double p1[1][U_COUNT - KU + 1], p2[1][U_COUNT - KU + 1];
 #pragma unroll
       for (int q = 0; q < U_COUNT - KU + 1; ++q) { p1[0][q] = upre[0][q]; p2[0][q] = upre[1][q]; }
+      if (P2P && rank_edge && ksub == 0) {
+        // nothing may be stored into a neighbour GPU before it has entered this loop (p2p_start_kernel over there)
+        if (lane < px.npeers) wait_flag(px.my_flags + px.peer_rank[lane], ebase, px.err);
+        syncwarp();
+      }
       if (a1[0]) advance(std::integral_constant<int, 1>{}, w1, a1, p1, true, nxt, last);
       syncwarp();
       if (lane == 0) publish_progress(pp.progress + PERSIST_CTR_STRIDE * tile);
+      if (P2P && rank_edge && lane == 0) {
+        // hand-over to the neighbour GPUs: every publishing warp of every edge tile counts itself done with gpu-scope ordering; the
+        // one that arrives last issues the ONE system-scope fence -- cumulative over the NVLink stores of all the warps it has
+        // synchronised with through the counter -- and raises the peers' flags (same protocol as fused_kernel<..,P2P>)
+        __threadfence();
+        const unsigned long long old = atomicAdd(px.done_ctr, 1ULL);
+        if (old + 1 == (unsigned long long)pp.n_sig * (unsigned long long)(ksub + 1)) {
+          __threadfence_system();
+          for (int q = 0; q < px.npeers; ++q) st_relaxed_sys(px.peer_flag[q], ebase + (unsigned long long)ksub + 1ULL);
+        }
+      }
       if (warp == 0) mark(ksub, 4);
       const unsigned w2[1] = {wU[1]};
       const bool a2[1] = {(flags & 32u) != 0};
@@ -336,23 +370,32 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
 }
 
 #ifndef EVP_HOST_EMU  // launcher: not part of the host emulation (tests/emu_persist.cpp)
-template <int KT, int KU, bool DBG>
-static cudaError_t launch_persist_t(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s) {
+template <int KT, int KU, bool DBG, bool P2P>
+static cudaError_t launch_persist_t(const Dom &d, const KParams &p, const PersistPlan &pp, const P2PParams &px, cudaStream_t s) {
   static bool attr_set = false;
-  auto kern = persist_kernel<PERSIST_THREADS, KT, KU, DBG>;
+  auto kern = persist_kernel<PERSIST_THREADS, KT, KU, DBG, P2P>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  void *args[] = {(void *)&d, (void *)&p, (void *)&pp};
+  void *args[] = {(void *)&d, (void *)&p, (void *)&pp, (void *)&px};
   return cudaLaunchCooperativeKernel((const void *)kern, dim3(pp.ntx * pp.nty), dim3(PERSIST_THREADS), args, pp.smem_bytes, s);
 }
+template <int KT, int KU>
+static cudaError_t launch_persist_k(const Dom &d, const KParams &p, const PersistPlan &pp, const P2PParams *px, cudaStream_t s) {
+  static const P2PParams nop2p{};
+  if (px) return launch_persist_t<KT, KU, false, true>(d, p, pp, *px, s);   // (no cycle accounting in the multi-GPU form)
+  return pp.dbg ? launch_persist_t<KT, KU, true, false>(d, p, pp, nop2p, s) : launch_persist_t<KT, KU, false, false>(d, p, pp, nop2p, s);
+}
 
-cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, cudaStream_t s) {
+cudaError_t set_wait_timeout_persist(unsigned long long ns) { return cudaMemcpyToSymbol(g_wait_timeout_ns, &ns, sizeof ns); }
+
+// px: null on a single rank, else the in-kernel NVLink halo parameters (evp_halo.cu)
+cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, const P2PParams *px, cudaStream_t s) {
   if (pp.nthreads != PERSIST_THREADS) return cudaErrorInvalidValue;
-  if (pp.kT == 10 && pp.kU == 11) return pp.dbg ? launch_persist_t<10, 11, true>(d, p, pp, s) : launch_persist_t<10, 11, false>(d, p, pp, s);
-  if (pp.kT == 6 && pp.kU == 3) return pp.dbg ? launch_persist_t<6, 3, true>(d, p, pp, s) : launch_persist_t<6, 3, false>(d, p, pp, s);
+  if (pp.kT == 10 && pp.kU == 11) return launch_persist_k<10, 11>(d, p, pp, px, s);
+  if (pp.kT == 6 && pp.kU == 3) return launch_persist_k<6, 3>(d, p, pp, px, s);
   return cudaErrorInvalidValue;
 }
 #endif  // EVP_HOST_EMU

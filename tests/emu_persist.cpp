@@ -23,8 +23,9 @@ using namespace evp::exact;
 template <int NT>
 static int run_nt(const Dom &d, const KParams &k, PersistPlan &pp) {
   const int nctas = pp.ntx * pp.nty;
-  if (pp.kT == 10 && pp.kU == 11) emu::launch_concurrent(nctas, NT, pp.smem_bytes, [&] { persist_kernel<NT, 10, 11>(d, k, pp); });
-  else if (pp.kT == 6 && pp.kU == 3) emu::launch_concurrent(nctas, NT, pp.smem_bytes, [&] { persist_kernel<NT, 6, 3>(d, k, pp); });
+  static const P2PParams nop2p{};
+  if (pp.kT == 10 && pp.kU == 11) emu::launch_concurrent(nctas, NT, pp.smem_bytes, [&] { persist_kernel<NT, 10, 11>(d, k, pp, nop2p); });
+  else if (pp.kT == 6 && pp.kU == 3) emu::launch_concurrent(nctas, NT, pp.smem_bytes, [&] { persist_kernel<NT, 6, 3>(d, k, pp, nop2p); });
   else return 3;
   return 0;
 }

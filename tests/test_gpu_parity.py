@@ -188,12 +188,14 @@ def test_tx1_tripole_full(oracle_mod, evp_lib):
 @pytest.mark.parametrize("p2p", ["1", "0"], ids=["nvlink-stores", "nccl"])
 @pytest.mark.parametrize("args", [
     ["gx3", "25", "29", "40", "fused"],
+    ["gx3", "25", "29", "41", "persistent"],
+    ["gx1", "80", "96", "30", "auto"],
     ["gx3", "50", "58", "15", "split"],
     ["tiny", "12", "10", "16", "fused", "tripole"],
     ["gx3", "10", "10", "20", "fused", "-", "elim"],
     ["tx1", "90", "60", "60", "fused", "tripole"],
     ["tx1", "45", "40", "25", "split", "tripole"],
-], ids=["gx3-16blocks-fused", "gx3-4blocks-split", "tiny-tripole", "gx3-land-blocks-eliminated", "tx1-tripole-fused", "tx1-tripole-split"])
+], ids=["gx3-16blocks-fused", "gx3-16blocks-persistent", "gx1-16blocks-auto", "gx3-4blocks-split", "tiny-tripole", "gx3-land-blocks-eliminated", "tx1-tripole-fused", "tx1-tripole-split"])
 def test_multi_gpu_halo(args, p2p):
     """N>1: one process per GPU; the (uvel,vvel) halo goes either through in-kernel NVLink stores into the
     neighbours' ghost cells (default for the fused kernel; across a tripole fold the values arrive negated or as raw
@@ -208,6 +210,8 @@ def test_multi_gpu_halo(args, p2p):
         pytest.skip("needs >= 2 GPUs")
     if p2p == "0" and args[4] == "split":
         pytest.skip("the split kernels use the staged exchange either way (covered by the nvlink-stores id)")
+    if p2p == "0" and args[4] == "persistent":
+        pytest.skip("the persistent kernel needs the in-kernel halo (with EVP_B200_P2P=0 it refuses, AUTO falls back to the fused kernel)")
     world = 4 if n >= 4 else 2
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -215,8 +219,10 @@ def test_multi_gpu_halo(args, p2p):
            "--master-port", "29611", os.path.join(root, "tests", "mgpu_check.py")] + args
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, EVP_B200_P2P=p2p))
     assert "MGPU PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
-    if p2p == "1" and args[4] == "fused":
+    if p2p == "1" and args[4] in ("fused", "persistent", "auto"):
         assert "in-kernel NVLink stores" in r.stdout, r.stdout[-2000:]
+    if p2p == "1" and args[4] in ("persistent", "auto"):
+        assert "launches/rank=3 " in r.stdout, r.stdout[-2000:]   # hand-shake, ONE cooperative launch for the whole loop, closing wait
 
 
 def test_errors_are_reported_not_fatal(evp_lib):
