@@ -370,8 +370,8 @@ static int do_init(const evp_b200_grid_t *gr) {
 
   // ---- device memory ----------------------------------------------------------------------------
   const size_t bdom = g.ndom * sizeof(double), bblk = g.nblk_elems * sizeof(double);
-  CK(cudaMalloc(&g.dshare, 4 * bdom + 64 * sizeof(unsigned long long)));
-  CK(cudaMemsetAsync(g.dshare, 0, 4 * bdom + 64 * sizeof(unsigned long long), g.stream));
+  CK(cudaMalloc(&g.dshare, P2PState::share_bytes(g.ndom, nx, ny)));
+  CK(cudaMemsetAsync(g.dshare, 0, P2PState::share_bytes(g.ndom, nx, ny), g.stream));
   for (int f = 0; f < NF_TOTAL; ++f) {
     if (f == F_U || f == F_V) continue;
     CK(cudaMalloc(&g.dfield[f], bdom)); CK(cudaMemsetAsync(g.dfield[f], 0, bdom, g.stream));

@@ -415,6 +415,14 @@ int HaloPlan::build_local_fold(int nxg, int nyg, int ew, int ns, int max_entries
   return 0;
 }
 
+// setup only: tell a neighbour GPU which of its ghost cells this rank feeds (tag 1 in every word of the slot, both parities)
+__global__ void ll_mark_kernel(unsigned long long *ll, const int *slot, int n, int ring) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n || slot[k] < 0) return;
+  for (int par = 0; par < 2; ++par)
+    for (int w = 0; w < 4; ++w) ll[((size_t)par * ring + slot[k]) * 4 + w] = 1ULL << 32;
+}
+
 int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t ndom, int nx, int ny, int ld, int nxg, int nyg,
                     int ew, int ns, int max_fold, char *err, size_t nerr) {
   release();
@@ -538,12 +546,16 @@ int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t 
   };
   for (const PushEntry &p : pushes) start[eidx(p.src) + 1]++;
   for (int e = 0; e < nedge; ++e) start[e + 1] += start[e];
+  std::vector<int> pll(pushes.size(), -1);   // ring index of the destination ghost cell in the peer's sub-domain (-1: not a ring cell)
   {
     std::vector<int> fill(start.begin(), start.end() - 1);
     for (const PushEntry &p : pushes) {
       const int k = fill[eidx(p.src)]++;
       ppeer[k] = slot_of(p.rank) | (p.neg ? 0x100 : 0);
       pdst[k] = p.dst;
+      const Rect &A = R[p.rank];
+      const int ldr = ((A.nx + 2 + 15) / 16) * 16, di = p.dst % ldr, dj = p.dst / ldr;
+      if (dj <= A.ny + 1 && (di == 0 || di == A.nx + 1 || dj == 0 || dj == A.ny + 1)) pll[k] = ring_index(A.nx, A.ny, di, dj);
     }
   }
   // tile order of the 32x8 fused kernel, edge tiles first; below a tripole fold the tile row that holds row ny-1 counts as edge
@@ -559,7 +571,7 @@ int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t 
   if (ntx > 0xffff || nty > 0x7fff) HFAIL("p2p: tile grid too large");
   for (int &t : order) t = ((t / ntx) << 16) | (t % ntx);  // packed (tby, tbx): see fused_kernel
   if (up(d_tile_order, order, err, nerr) || up(d_push_start, start, err, nerr) || up(d_push_peer, ppeer, err, nerr) ||
-      up(d_push_dst, pdst, err, nerr))
+      up(d_push_dst, pdst, err, nerr) || up(d_push_ll, pll, err, nerr))
     return 1;
   if (upload_fold(fold, d_fold_dst, d_fold_c1, d_fold_c2, d_fold_code, err, nerr)) return 1;
   fold_n = (int)fold.size();
@@ -590,6 +602,35 @@ int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t 
   // nobody may be written to before every rank has zeroed its flags
   NCK(ncclAllReduce(d_err, d_err, 1, ncclInt32, ncclMax, cs.comm, 0));
   HCK(cudaStreamSynchronize(0));
+  // low-latency slots: learn which of my ghost cells the neighbour GPUs feed (they mark them), then clear the slots again
+  prm.my_ring = ring_cells(nx, ny);
+  prm.my_ll = (unsigned long long *)(dshare + 4 * ndom) + 64;
+  prm.push_ll = d_push_ll;
+  for (int q = 0; q < npeers; ++q) {
+    const Rect &A = R[peer_ranks[q]];
+    prm.peer_ring[q] = ring_cells(A.nx, A.ny);
+    prm.peer_ll[q] = (unsigned long long *)(peer_base[q] + 4 * peer_ndom[q]) + 64;
+    std::vector<int> mine;
+    for (size_t k = 0; k < pll.size(); ++k) if ((ppeer[k] & 0xff) == q) mine.push_back(pll[k]);
+    int *dm = nullptr;
+    if (up(dm, mine, err, nerr)) return 1;
+    if (!mine.empty()) ll_mark_kernel<<<((int)mine.size() + 127) / 128, 128>>>(prm.peer_ll[q], dm, (int)mine.size(), prm.peer_ring[q]);
+    HCK(cudaDeviceSynchronize());
+    HCK(cudaFree(dm));
+  }
+  NCK(ncclAllReduce(d_err, d_err, 1, ncclInt32, ncclMax, cs.comm, 0));   // every mark has landed
+  HCK(cudaStreamSynchronize(0));
+  {
+    std::vector<unsigned long long> w((size_t)2 * prm.my_ring * 4);
+    HCK(cudaMemcpy(w.data(), prm.my_ll, w.size() * 8, cudaMemcpyDeviceToHost));
+    std::vector<unsigned char> fed(prm.my_ring, 0);
+    for (int r = 0; r < prm.my_ring; ++r) fed[r] = (w[(size_t)r * 4] >> 32) == 1ULL;
+    if (up(d_ll_fed, fed, err, nerr)) return 1;
+    prm.ll_fed = d_ll_fed;
+    HCK(cudaMemset(prm.my_ll, 0, w.size() * 8));
+  }
+  NCK(ncclAllReduce(d_err, d_err, 1, ncclInt32, ncclMax, cs.comm, 0));   // ... and every rank has cleared its slots before anyone runs
+  HCK(cudaStreamSynchronize(0));
   enabled = true;
   char b[200];
   snprintf(b, sizeof b, "in-kernel NVLink stores to %d peer(s), %zu pushed cells, %d edge tiles of %d, %d fold entries", npeers, pushes.size(),
@@ -614,7 +655,7 @@ void P2PState::release() {
     peer_base[q] = nullptr;
   }
   auto F = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
-  F(d_tile_order); F(d_push_start); F(d_push_peer); F(d_push_dst); F(d_done); F(d_epoch); F(d_err); F(d_dbg);
+  F(d_tile_order); F(d_push_start); F(d_push_peer); F(d_push_dst); F(d_done); F(d_epoch); F(d_err); F(d_dbg); F(d_push_ll); F(d_ll_fed);
   F(d_fold_dst); F(d_fold_c1); F(d_fold_c2); F(d_fold_code);
   fold_n = 0;
   enabled = false;

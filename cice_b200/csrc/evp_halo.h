@@ -81,11 +81,14 @@ struct P2PState {
   unsigned long long *d_done = nullptr, *d_epoch = nullptr;
   int *d_err = nullptr;
   unsigned long long *d_dbg = nullptr;
+  int *d_push_ll = nullptr;
+  unsigned char *d_ll_fed = nullptr;
 
-  // dshare = [u0 | u1 | v0 | v1] (ndom doubles each) followed by 64 u64 flags, one cudaMalloc
+  // dshare = [u0 | u1 | v0 | v1] (ndom doubles each), 64 u64 flags, then the low-latency slots (p2p_share_bytes), one cudaMalloc
   int setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t ndom, int nx, int ny, int ld, int nxg, int nyg,
             int ew, int ns, int max_fold, char *err, size_t nerr);
   void set_parity(int swapped_);
+  static size_t share_bytes(size_t ndom, int nx, int ny) { return 4 * ndom * sizeof(double) + 64 * 8 + (size_t)2 * ring_cells(nx, ny) * 4 * 8; }
   void release();
 };
 

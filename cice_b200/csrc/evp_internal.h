@@ -90,7 +90,25 @@ struct P2PParams {
   unsigned long long *epoch_base;              // device-resident: epoch of the current loop
   int *err;                                    // set when a wait times out
   unsigned long long *dbg;                     // [0] sum of wait cycles of lane 0 of edge CTAs, [1] number of waits, [2] max wait
+  // Low-latency slots (persistent kernel): every ghost cell that a neighbour GPU feeds has, per ping-pong parity, four 8-byte words
+  // (lo32(u) | tag << 32, hi32(u) | tag << 32, the same for v) in the receiver's memory.  A value validates itself -- tag = low 32
+  // bits of epoch + subcycle -- so the exchange inside the loop needs no fence and no flag: one NVLink store latency.
+  unsigned long long *peer_ll[P2P_MAXPEER];    // that peer's slots
+  int peer_ring[P2P_MAXPEER];                  // ghost-ring cells of that peer's sub-domain (slots per parity)
+  const int *push_ll;                          // per push entry: ring index of the destination ghost cell over there (ring_index)
+  unsigned long long *my_ll;                   // this rank's slots
+  const unsigned char *ll_fed;                 // [my_ring] 1 where a neighbour GPU feeds the ghost cell
+  int my_ring;
 };
+
+// position of ghost cell (i,j) of an nx x ny sub-domain in its ring: S row, N row, W column, E column
+__host__ __device__ inline int ring_cells(int nx, int ny) { return 2 * (nx + 2) + 2 * ny; }
+__host__ __device__ inline int ring_index(int nx, int ny, int i, int j) {
+  if (j == 0) return i;
+  if (j == ny + 1) return (nx + 2) + i;
+  if (i == 0) return 2 * (nx + 2) + (j - 1);
+  return 2 * (nx + 2) + ny + (j - 1);
+}
 
 // KERNEL_PERSISTENT (evp_persist.cu): one CTA per SM owns a tile of the sub-domain for the whole loop.  The plan is built on the
 // host (evp_persist_plan.h); the tables say which T cell / U point each (slot, thread) of a CTA advances.

@@ -39,9 +39,10 @@ enum { U_CV = 0, U_UOCN, U_VOCN, U_UMASSDTI, U_FM, U_WATERX, U_WATERY, U_FORCEX,
 
 __device__ __forceinline__ double2 mk2(double a, double b) { double2 r; r.x = a; r.y = b; return r; }
 
-// P2P: the sub-domain has neighbour GPUs.  Their edge velocities arrive in this rank's ghost cells as NVLink stores (the peers' tiles
-// push them exactly like fused_kernel<..,P2P> does, evp_kernels.cu), per-peer epoch flags say when; this rank's tiles on the
-// sub-domain edge push theirs, count themselves done, and the last one hands over with one system-scope fence + flag stores.
+// P2P: the sub-domain has neighbour GPUs.  Inside the loop their edge velocities arrive over NVLink as self-validating words in this
+// rank's low-latency slots (P2PParams: value halves tagged with epoch + subcycle; no fence, no flag -- one store latency), and the
+// tiles on this rank's edge push theirs the same way.  Only the last subcycle's values go into the neighbours' arrays themselves,
+// handed over with a counter, one system-scope fence and the per-peer epoch flags (as fused_kernel<..,P2P> does every subcycle).
 template <int NT, int KT, int KU, bool DBG = false, bool P2P = false>
 __global__ void __launch_bounds__(NT, 1)
 persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k, const __grid_constant__ PersistPlan pp,
@@ -170,9 +171,24 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
     sstr[2 * nT + t] = mk2(str[2], str[5]); sstr[3 * nT + t] = mk2(str[3], str[7]);
   };
 
+  // one edge value into the low-latency slots of the neighbour GPUs that hold (i,j) as a ghost cell; tagged for subcycle ksub
+  auto push_ll = [&](int i, int j, double u, double v, int nxt, int ksub) {
+    const unsigned long long tag = ((ebase + (unsigned long long)ksub + 1ULL) & 0xffffffffULL) << 32;
+    const int e = edge_index(d, 0, i, j);
+    for (int q = px.push_start[e]; q < px.push_start[e + 1]; ++q) {
+      const int pr = px.push_peer[q] & 0xff;
+      unsigned long long *sl = px.peer_ll[pr] + ((size_t)nxt * px.peer_ring[pr] + px.push_ll[q]) * 4;
+      const unsigned long long ub = (unsigned long long)__double_as_longlong(u), vb = (unsigned long long)__double_as_longlong(v);
+      st_relaxed_sys(sl + 0, (ub & 0xffffffffULL) | tag);
+      st_relaxed_sys(sl + 1, (ub >> 32) | tag);
+      st_relaxed_sys(sl + 2, (vb & 0xffffffffULL) | tag);
+      st_relaxed_sys(sl + 3, (vb >> 32) | tag);
+    }
+  };
+
   // N U points of this thread at once (N = 2: both slots in one instruction stream; called with at least one of them active)
   auto advance = [&](auto nconst, const unsigned (&ws)[decltype(nconst)::value], const bool (&act)[decltype(nconst)::value],
-                     const double (&pre)[decltype(nconst)::value][U_COUNT - KU + 1], bool publish_edge, int nxt, bool last) {
+                     const double (&pre)[decltype(nconst)::value][U_COUNT - KU + 1], bool publish_edge, int nxt, bool last, int ksub) {
     constexpr int N = decltype(nconst)::value;
     double uold[N], vold[N], uo[U_COUNT][N], ui[N], vi[N], s[N][8];
     int cs[N], gs[N], is[N], js[N];
@@ -225,10 +241,16 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
         if (P2P && publish_edge && is_push_point(d, 0, i, j)) {
           // a ghost cell of up to three other sub-domains: stored there over NVLink right away (push table: evp_halo.cu)
           const int e = edge_index(d, 0, i, j);
-          for (int q = px.push_start[e]; q < px.push_start[e + 1]; ++q) {
-            const int pr = px.push_peer[q] & 0xff, dst = px.push_dst[q];
-            px.peer_u[nxt][pr][dst] = o[n].u;
-            px.peer_v[nxt][pr][dst] = o[n].v;
+          if (last) {
+            // the loop's last values go into the neighbours' arrays themselves (what their download and their next loop read);
+            // handed over with the counter + fence + flag below
+            for (int q = px.push_start[e]; q < px.push_start[e + 1]; ++q) {
+              const int pr = px.push_peer[q] & 0xff, dst = px.push_dst[q];
+              px.peer_u[nxt][pr][dst] = o[n].u;
+              px.peer_v[nxt][pr][dst] = o[n].v;
+            }
+          } else {
+            push_ll(i, j, o[n].u, o[n].v, nxt, ksub);  // inside the loop: self-validating words, nothing else
           }
         }
       }
@@ -260,8 +282,6 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
       if (dbg) tw0 = clk();
       if (warp == rw0) {  // one warp polls (lane q watches neighbour q), the other refreshing warps wait for it at a named barrier
         if (nb >= 0) wait_progress(pp.progress + PERSIST_CTR_STRIDE * nb, nb_per * (unsigned)ksub, pp.err);
-        // ... and lanes 8.. the neighbour GPUs: their stores of subcycle ksub-1 into this rank's ghost cells have arrived
-        if (rank_edge && lane >= 8 && lane - 8 < px.npeers) wait_flag(px.my_flags + px.peer_rank[lane - 8], ebase + (unsigned long long)ksub, px.err);
         syncwarp();
         mark(ksub, 1);
       }
@@ -275,7 +295,26 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
         else if (e < 2 * (ebx + 2)) { li = e - (ebx + 2); lj = eby + 1; }
         else if (e < 2 * (ebx + 2) + eby) { li = 0; lj = 1 + e - 2 * (ebx + 2); }
         else { li = ebx + 1; lj = 1 + e - 2 * (ebx + 2) - eby; }
-        const int g = at(d, i0 - 1 + li, j0 - 1 + lj);
+        const int gi = i0 - 1 + li, gj = j0 - 1 + lj;
+        if (P2P && rank_edge && (gi == 0 || gi == d.nx + 1 || gj == 0 || gj == d.ny + 1)) {
+          const int r = ring_index(d.nx, d.ny, gi, gj);
+          if (px.ll_fed[r]) {
+            // fed by a neighbour GPU: spin on the slot of parity `cur` until all four words carry this subcycle's tag
+            const unsigned long long *sl = px.my_ll + ((size_t)cur * px.my_ring + r) * 4;
+            const unsigned long long want = (ebase + (unsigned long long)ksub) & 0xffffffffULL;
+            unsigned long long w0, w1, w2, w3;
+            const unsigned long long t0 = gtime();
+            for (;;) {
+              w0 = ld_relaxed_sys(sl + 0); w1 = ld_relaxed_sys(sl + 1); w2 = ld_relaxed_sys(sl + 2); w3 = ld_relaxed_sys(sl + 3);
+              if ((w0 >> 32) == want && (w1 >> 32) == want && (w2 >> 32) == want && (w3 >> 32) == want) break;
+              if (gtime() - t0 > g_wait_timeout_ns) { atomicExch(px.err, 1); break; }
+            }
+            suv[lj * uw + li] = mk2(__longlong_as_double((long long)((w0 & 0xffffffffULL) | (w1 << 32))),
+                                    __longlong_as_double((long long)((w2 & 0xffffffffULL) | (w3 << 32))));
+            continue;
+          }
+        }
+        const int g = at(d, gi, gj);
         suv[lj * uw + li] = mk2(ld_cg_f64(U + g), ld_cg_f64(V + g));  // written by another SM: served by L2, never a stale L1 line
       }
       if (dbg) acc[1] += clk() - tw0;
@@ -324,16 +363,24 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
         if (lane < px.npeers) wait_flag(px.my_flags + px.peer_rank[lane], ebase, px.err);
         syncwarp();
       }
-      if (a1[0]) advance(std::integral_constant<int, 1>{}, w1, a1, p1, true, nxt, last);
+      if (a1[0]) advance(std::integral_constant<int, 1>{}, w1, a1, p1, true, nxt, last, ksub);
+      if (P2P && rank_edge && !last && !a1[0] && wU[0] != PERSIST_NONE_W) {
+        // a point off the ice never changes, but the neighbour GPU's ring refresh waits for EVERY ghost cell it is fed: send what is there
+        const int li = (wU[0] >> 10) & 63, lj = (wU[0] >> 16) & 63;
+        if (is_push_point(d, 0, i0 + li, j0 + lj)) {
+          const double2 uv = suv[(lj + 1) * uw + li + 1];
+          push_ll(i0 + li, j0 + lj, uv.x, uv.y, nxt, ksub);
+        }
+      }
       syncwarp();
       if (lane == 0) publish_progress(pp.progress + PERSIST_CTR_STRIDE * tile);
-      if (P2P && rank_edge && lane == 0) {
-        // hand-over to the neighbour GPUs: every publishing warp of every edge tile counts itself done with gpu-scope ordering; the
-        // one that arrives last issues the ONE system-scope fence -- cumulative over the NVLink stores of all the warps it has
-        // synchronised with through the counter -- and raises the peers' flags (same protocol as fused_kernel<..,P2P>)
+      if (P2P && rank_edge && last && lane == 0) {
+        // hand-over of the LAST subcycle's plain stores: every publishing warp of every edge tile counts itself done with gpu-scope
+        // ordering; the one that arrives last issues the ONE system-scope fence -- cumulative over the NVLink stores of all the warps it
+        // has synchronised with through the counter -- and raises the peers' flags to epoch + ndte, which p2p_finish_kernel waits for
         __threadfence();
         const unsigned long long old = atomicAdd(px.done_ctr, 1ULL);
-        if (old + 1 == (unsigned long long)pp.n_sig * (unsigned long long)(ksub + 1)) {
+        if (old + 1 == (unsigned long long)pp.n_sig) {
           __threadfence_system();
           for (int q = 0; q < px.npeers; ++q) st_relaxed_sys(px.peer_flag[q], ebase + (unsigned long long)ksub + 1ULL);
         }
@@ -341,11 +388,11 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
       if (warp == 0) mark(ksub, 4);
       const unsigned w2[1] = {wU[1]};
       const bool a2[1] = {(flags & 32u) != 0};
-      if (a2[0]) advance(std::integral_constant<int, 1>{}, w2, a2, p2, false, nxt, last);
+      if (a2[0]) advance(std::integral_constant<int, 1>{}, w2, a2, p2, false, nxt, last, ksub);
     } else if (flags & 48u) {
       const unsigned w2[2] = {wU[0], wU[1]};
       const bool a2[2] = {(flags & 16u) != 0, (flags & 32u) != 0};
-      advance(std::integral_constant<int, 2>{}, w2, a2, upre, false, nxt, last);
+      advance(std::integral_constant<int, 2>{}, w2, a2, upre, false, nxt, last, ksub);
     }
     if (dbg) tk3 = clk();
     __syncthreads();

@@ -34,6 +34,11 @@ __device__ __forceinline__ void wait_flag(const unsigned long long *flag, unsign
     if (gtime() - t0 > g_wait_timeout_ns) { atomicExch(err, 1); break; }
   }
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -129,6 +134,8 @@ inline unsigned long long gtime() { return 0; }
 inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline void st_release_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline void st_relaxed_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long ld_relaxed_sys(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+static unsigned long long g_wait_timeout_ns = ~0ULL;
 inline void wait_flag(const unsigned long long *flag, unsigned long long want, int *err) {
   for (long spins = 0; ld_acquire_sys(flag) < want; ++spins) {
     if (spins > 200000000L) { *err = 1; break; }

@@ -157,6 +157,7 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline long long __double_as_longlong(double x) { long long b; memcpy(&b, &x, 8); return b; }
+static inline double __longlong_as_double(long long b) { double x; memcpy(&x, &b, 8); return x; }
 static inline long long clock64() { return 0; }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
