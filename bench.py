@@ -332,10 +332,11 @@ def run_ours(args):
         barrier()
         return (time.perf_counter() - t0) / e2e_steps
 
-    e2e_full_s = time_e2e(lambda: dyn_evp.dyn_evp_b200_run(params, hf))
+    hfc = {k: v for k, v in hf.items() if not k.startswith("_keep_")}
+    e2e_full_s = time_e2e(dyn_evp.bind("run", params, hfc))   # C structs built once, like a compiled caller: the loop times the C ABI
     resident_ok = grid["ns_boundary_type"] != abi.BNDY_NAMES["tripole"]
     if resident_ok:
-        e2e_s = time_e2e(lambda: dyn_evp.dyn_evp_b200_run_resident(params, hf, keep_stress=True))
+        e2e_s = time_e2e(dyn_evp.bind("run_resident", params, hfc, keep_stress=True))
         h2d = 18 * nblk * 8 + 2 * nblk * 4
         d2h = 6 * nblk * 8
         e2e_how = "evp_b200_run_bgrid_resident(EVP_B200_KEEP_STRESS): stresses stay on the device, everything else crosses"
@@ -344,12 +345,37 @@ def run_ours(args):
         h2d = 30 * nblk * 8 + 2 * nblk * 4
         d2h = 18 * nblk * 8
         e2e_how = "evp_b200_run_bgrid: every field crosses both ways (tripole grid)"
+    # (d) the step preparation on the device too (evp_b200_step_resident): per step the nine T-point
+    #     inputs + strength + iceTmask go in, the velocities come out; velocities, stresses and iceUmask stay on the device.
+    #     One rank, no tripole fold in this version.
+    e2e_step = None
+    if world == 1 and resident_ok:
+        static, prep = synth.step_inputs(case)
+        pst = pin({k: v for k, v in static.items() if k != "umask"})
+        pst["umask"] = static["umask"]
+        ppr = pin({k: v for k, v in prep.items() if isinstance(v, np.ndarray) and v.dtype == np.float64})
+        for k, v in prep.items():
+            if k not in ppr:
+                ppr[k] = v
+        import torch as _t
+        tm = _t.from_numpy(prep["iceTmask"].copy()).pin_memory()
+        ppr["iceTmask"] = tm.numpy()
+        dyn_evp.dyn_evp_b200_prep_init({k: v for k, v in pst.items() if not k.startswith("_keep_")})
+        sf = {k: v for k, v in hf.items() if not k.startswith("_keep_")}
+        prep_clean = {k: v for k, v in ppr.items() if not k.startswith("_keep_")}
+        dyn_evp.dyn_evp_b200_step_resident(params, prep_clean, sf, init_state=True)
+        out = {"uvel": hf["uvel"], "vvel": hf["vvel"]}
+        s_step = time_e2e(dyn_evp.bind("step_resident", params, out, prep=prep_clean))
+        e2e_step = {"value": cells_global * ndte / s_step, "unit": UNIT, "ms_per_step": s_step * 1e3,
+                    "h2d_bytes_per_step": 8 * nblk * 8 + nblk * 4, "d2h_bytes_per_step": 2 * nblk * 8,
+                    "how": "evp_b200_step_resident: T-point inputs of the step in (tmass, aice_init, cdn_ocn, uocn, vocn, strairxT, strairyT, "
+                           "strength, iceTmask; pinned), T->U averages + dyn_prep2 + the whole subcycle loop on the device, uvel and vvel out; "
+                           "velocities, stresses and iceUmask resident"}
     # (c) what a Fortran caller hands over: pageable arrays; then the same arrays page-locked once (evp_b200_pin_host)
     e2e_pageable = None
     if world == 1 and not args.no_pageable:
         pf = {k: v.copy() for k, v in fields.items()}
-        run_pf = (lambda: dyn_evp.dyn_evp_b200_run_resident(params, pf, keep_stress=True)) if resident_ok else \
-            (lambda: dyn_evp.dyn_evp_b200_run(params, pf))
+        run_pf = dyn_evp.bind("run_resident", params, pf, keep_stress=True) if resident_ok else dyn_evp.bind("run", params, pf)
         s_page = time_e2e(run_pf)
         arrays = [v for v in pf.values() if isinstance(v, np.ndarray)]
         for a in arrays:
@@ -418,6 +444,10 @@ def run_ours(args):
                 "wall_s": t_wall}
         if e2e_pageable:
             line["e2e_pageable"] = e2e_pageable
+        if e2e_step:
+            # the headline end-to-end number is the call that does the most on the device; the two older entry points stay beside it
+            line["e2e_resident_stress"] = line["e2e"]
+            line["e2e"] = e2e_step
         # the active-cell rate beside R (T cells that carry ice; rank 0's sub-domain)
         act = int(np.count_nonzero(np.asarray(fields["iceTmask"])[:, 1:-1, 1:-1]))
         line["active_cells"] = {"icellT_rank0": act, "fraction_rank0": act / float(per_gpu_cells),

@@ -18,6 +18,8 @@ KERNEL_NAMES = {"auto": 0, "split": 1, "fused": 2, "persistent": 3, "stream": 4,
 
 UNIQUE_ID_BYTES = 128
 KEEP_STRESS, FETCH_STRESS = 1, 2  # evp_b200_run_bgrid_resident flags
+STEP_INIT_STATE, STEP_FETCH_DIAG, STEP_FETCH_STATE = 1, 2, 4  # evp_b200_step_resident flags
+SSH_GEOSTROPHIC, SSH_COUPLED = 0, 1
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int32)
@@ -221,4 +223,70 @@ def make_fields(f, npl_total):
         assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"] and a.size == npl_total, n
         keep[n] = a
         setattr(s, n, _ptr(a, C.c_int32))
+    return s, keep
+
+
+# ---- evp_b200_prep_init / evp_b200_step_resident -----------------------------------------------------
+PREP_STATIC = ("hm", "tarea", "uarea", "fcor")
+PREP_T = ("tmass", "aice_init", "cdn_ocn", "uocn", "vocn", "ss_tltx", "ss_tlty", "strairxT", "strairyT", "strength")
+PREP_OPTIONAL = ("ss_tltx", "ss_tlty", "TbU")
+
+
+class PrepStatic(C.Structure):
+    _fields_ = [(n, _pd) for n in PREP_STATIC] + [("umask", _pi)]
+
+
+class Prep(C.Structure):
+    _fields_ = ([(n, _pd) for n in PREP_T] + [("iceTmask", _pi), ("TbU", _pd)]
+                + [(n, C.c_double) for n in ("dt", "dyn_area_min", "dyn_mass_min", "gravit")] + [("ssh_stress", C.c_int32)])
+
+
+def make_prep_static(d, npl_total):
+    s, keep = PrepStatic(), {}
+    for n in PREP_STATIC:
+        a = d[n]
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == npl_total, n
+        keep[n] = a
+        setattr(s, n, _ptr(a, C.c_double))
+    a = d["umask"]
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"] and a.size == npl_total
+    keep["umask"] = a
+    s.umask = _ptr(a, C.c_int32)
+    return s, keep
+
+
+def make_prep(d, npl_total):
+    s, keep = Prep(), {}
+    for n in PREP_T + ("TbU",):
+        a = d.get(n)
+        if a is None:
+            assert n in PREP_OPTIONAL, n
+            continue
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == npl_total, n
+        keep[n] = a
+        setattr(s, n, _ptr(a, C.c_double))
+    a = d["iceTmask"]
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"] and a.size == npl_total
+    keep["iceTmask"] = a
+    s.iceTmask = _ptr(a, C.c_int32)
+    s.dt, s.dyn_area_min, s.dyn_mass_min = float(d["dt"]), float(d["dyn_area_min"]), float(d["dyn_mass_min"])
+    s.gravit, s.ssh_stress = float(d.get("gravit", 9.80616)), int(d.get("ssh_stress", SSH_GEOSTROPHIC))
+    return s, keep
+
+
+def make_fields_partial(f, npl_total):
+    """Fields with only the arrays present in `f` set (evp_b200_step_resident reads what its flags ask for)."""
+    s, keep = Fields(), {}
+    for n in FIELDS_ORDER:
+        if n in f:
+            a = f[n]
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == npl_total, n
+            keep[n] = a
+            setattr(s, n, _ptr(a, C.c_double))
+    for n in FIELDS_MASK:
+        if n in f:
+            a = f[n]
+            assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"] and a.size == npl_total, n
+            keep[n] = a
+            setattr(s, n, _ptr(a, C.c_int32))
     return s, keep

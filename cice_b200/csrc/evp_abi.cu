@@ -170,6 +170,11 @@ struct Ctx {
 
   // KERNEL_PERSISTENT
   PersistPlan pplan{};
+  // step preparation on the device (evp_b200_prep_init / evp_b200_step_resident)
+  double *prep_static[4] = {};   // hm, tarea, uarea, fcor
+  unsigned char *prep_umask = nullptr;
+  double *prepT[10] = {};        // tmass, aice_init, cdn_ocn, uocn, vocn, ss_tltx, ss_tlty, strairxT, strairyT, TbU
+  bool prep_ok = false, state_resident = false;
   bool persist_ok = false;
   bool persist_p2p = false;  // the persistent kernel's in-kernel NVLink halo form (neighbour ranks)
   std::string persist_why;
@@ -227,6 +232,9 @@ static int free_all() {
   F(g.dmaskT); F(g.dmaskU);
   for (auto &p : g.stage) F(p);
   F(g.stage_mask); F(g.stage_mask2); F(g.d_ever_off); F(g.d_gsrc); F(g.d_progress); F(g.d_ptab[0]); F(g.d_ptab[1]); F(g.d_perr); F(g.d_pdbg);
+  for (auto &p : g.prep_static) F(p);
+  for (auto &p : g.prepT) F(p);
+  F(g.prep_umask);
   F(g.d_uv_lin); F(g.d_uv_dom); F(g.d_sig_lin); F(g.d_sig_dom); F(g.d_int_lin); F(g.d_int_dom);
   g.halo.release();
   for (auto &e : g.ev_field) if (e) cudaEventDestroy(e);
@@ -515,8 +523,8 @@ static int do_upload(const evp_b200_fields_t *f, bool keep_stress = false) {
   return 0;
 }
 
-// what: bit 0 stresses, bit 1 everything else the loop writes (diagnostics, velocities)
-static int do_download(evp_b200_fields_t *f, int what = 3) {
+// what: bit 0 stresses, bit 1 diagnostics (strintxU, strintyU, taubxU, taubyU), bit 2 velocities
+static int do_download(evp_b200_fields_t *f, int what = 7) {
   if (!g.inited || !g.uploaded) return fail("evp_b200_download: nothing uploaded");
   if (!f) return fail("evp_b200_download: null fields");
   double *dst[18] = {f->stressp_1, f->stressp_2, f->stressp_3, f->stressp_4, f->stressm_1, f->stressm_2,
@@ -526,7 +534,7 @@ static int do_download(evp_b200_fields_t *f, int what = 3) {
   CK(cudaSetDevice(g.device));
   const Dom &d = g.dom;
   for (int q = 0; q < 18; ++q) {
-    if (!((q < 12) ? (what & 1) : (what & 2))) continue;
+    if (!((q < 12) ? (what & 1) : (q < 16) ? (what & 2) : (what & 4))) continue;
     if (!dst[q]) return fail("evp_b200_download: null field %d", q);
     if (q < 12 && !g.stress_uploaded_this_call) {
       // resident stresses are being fetched: the staging copy is stale, start from the caller's array and apply the zeroing
@@ -1284,7 +1292,7 @@ int evp_b200_upload(const evp_b200_fields_t *f) {
   return 0;
 }
 int evp_b200_subcycle(const evp_b200_params_t *p) { return do_subcycle(p); }
-int evp_b200_download(evp_b200_fields_t *f) { return do_download(f, 3); }
+int evp_b200_download(evp_b200_fields_t *f) { return do_download(f, 7); }
 
 int evp_b200_run_bgrid_resident(const evp_b200_params_t *p, evp_b200_fields_t *f, int32_t flags) {
   if ((flags & EVP_B200_KEEP_STRESS) && g.inited && g.ns == EVP_B200_BNDY_TRIPOLE)
@@ -1293,14 +1301,143 @@ int evp_b200_run_bgrid_resident(const evp_b200_params_t *p, evp_b200_fields_t *f
   if (do_upload(f, (flags & EVP_B200_KEEP_STRESS) != 0)) return 1;
   if (do_subcycle(p)) return 1;
   const bool stress_back = !(flags & EVP_B200_KEEP_STRESS) || (flags & EVP_B200_FETCH_STRESS);
-  return do_download(f, stress_back ? 3 : 2);
+  return do_download(f, stress_back ? 7 : 6);
 }
 int evp_b200_download_stress(evp_b200_fields_t *f) { return do_download(f, 1); }
+
+// ---- the step preparation on the device --------------------------------------------------------------
+__global__ void unpack_mask(int *__restrict__ dst_blk, const unsigned char *__restrict__ src_dom, const int *__restrict__ lin,
+                            const int *__restrict__ dom, int n) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) dst_blk[lin[k]] = src_dom[dom[k]] ? -1 : 0;  // .true.
+}
+
+int evp_b200_prep_init(const evp_b200_prep_static_t *st) {
+  if (!g.inited) return fail("evp_b200_prep_init: call evp_b200_init first");
+  if (!st || !st->hm || !st->tarea || !st->uarea || !st->fcor || !st->umask) return fail("evp_b200_prep_init: null argument");
+  if (g_comm.nranks > 1 || g.halo.n_dst != 0 || !g.halo.peers.empty())
+    return fail("evp_b200_prep_init: one rank and no tripole fold in this version (the velocity halo update after dyn_prep2 is the on-rank wrap only)");
+  CK(cudaSetDevice(g.device));
+  const size_t bdom = g.ndom * sizeof(double), bblk = g.nblk_elems * sizeof(double);
+  const int nd = (int)g.ndom, nb = grid_blocks(g.ndom);
+  const double *src[4] = {st->hm, st->tarea, st->uarea, st->fcor};
+  for (int q = 0; q < 4; ++q) {
+    if (!g.prep_static[q]) CK(cudaMalloc(&g.prep_static[q], bdom));
+    CK(cudaMemcpyAsync(g.stage[q], src[q], bblk, cudaMemcpyHostToDevice, g.stream));
+    pack_f64<<<nb, 256, 0, g.stream>>>(g.prep_static[q], g.stage[q], g.d_gsrc, nd);
+  }
+  for (auto &p : g.prepT)
+    if (!p) { CK(cudaMalloc(&p, bdom)); CK(cudaMemsetAsync(p, 0, bdom, g.stream)); }
+  if (!g.prep_umask) CK(cudaMalloc(&g.prep_umask, g.ndom));
+  CK(cudaMemcpyAsync(g.stage_mask, st->umask, g.nblk_elems * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+  pack_mask<<<nb, 256, 0, g.stream>>>(g.prep_umask, g.stage_mask, g.d_gsrc, nd);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(g.stream));
+  g.prep_ok = true;
+  g.state_resident = false;
+  return 0;
+}
+
+int evp_b200_step_resident(const evp_b200_params_t *p, const evp_b200_prep_t *pr, evp_b200_fields_t *f, int32_t flags) {
+  if (!g.inited || !g.prep_ok) return fail("evp_b200_step_resident: call evp_b200_init and evp_b200_prep_init first");
+  if (!p || !pr || !f) return fail("evp_b200_step_resident: null argument");
+  if (!pr->tmass || !pr->aice_init || !pr->cdn_ocn || !pr->uocn || !pr->vocn || !pr->strairxT || !pr->strairyT || !pr->strength || !pr->iceTmask)
+    return fail("evp_b200_step_resident: null input array");
+  if (pr->ssh_stress != 0 && pr->ssh_stress != 1) return fail("evp_b200_step_resident: ssh_stress %d (0 geostrophic, 1 coupled)", pr->ssh_stress);
+  if (pr->ssh_stress == 1 && (!pr->ss_tltx || !pr->ss_tlty)) return fail("evp_b200_step_resident: coupled ssh_stress needs ss_tltx, ss_tlty");
+  if (!(pr->dt > 0.0)) return fail("evp_b200_step_resident: dt must be positive");
+  if (!f->uvel || !f->vvel) return fail("evp_b200_step_resident: fields->uvel / vvel are written every step");
+  CK(cudaSetDevice(g.device));
+  const size_t bblk = g.nblk_elems * sizeof(double);
+  const int nd = (int)g.ndom, nb = grid_blocks(g.ndom);
+  const bool init = (flags & EVP_B200_STEP_INIT_STATE) || !g.state_resident;
+  // everything below is packed into copy 0 (and 1) of the carried state: normalise as do_subcycle would
+  if (g.cur == 1) {
+    std::swap(g.dom.u[0], g.dom.u[1]);
+    std::swap(g.dom.v[0], g.dom.v[1]);
+    for (int q = 0; q < 12; ++q) std::swap(g.dom.sig[0][q], g.dom.sig[1][q]);
+    g.cur = 0;
+    destroy_graph();
+  }
+  if (init) {
+    // the carried state comes from the host once: 12 stresses, velocities, the old iceUmask; the staging copies of the four
+    // diagnostics too (cells the loop does not own are returned as they came)
+    double *src[18] = {f->stressp_1, f->stressp_2, f->stressp_3, f->stressp_4, f->stressm_1, f->stressm_2, f->stressm_3, f->stressm_4,
+                       f->stress12_1, f->stress12_2, f->stress12_3, f->stress12_4, f->strintxU, f->strintyU, f->taubxU, f->taubyU, f->uvel, f->vvel};
+    for (int q = 0; q < 18; ++q) if (!src[q]) return fail("evp_b200_step_resident: EVP_B200_STEP_INIT_STATE needs field %d", q);
+    if (!f->iceUmask) return fail("evp_b200_step_resident: EVP_B200_STEP_INIT_STATE needs iceUmask (the mask of the previous step)");
+    for (int q = 0; q < 18; ++q) {
+      CK(cudaMemcpyAsync(g.stage[q], src[q], bblk, cudaMemcpyHostToDevice, g.stream));
+      if (q < 12) pack2_f64<<<nb, 256, 0, g.stream>>>(g.dom.sig[0][q], g.dom.sig[1][q], g.stage[q], g.d_gsrc, nd);
+      else if (q == F_U) pack2_f64<<<nb, 256, 0, g.stream>>>(g.dom.u[0], g.dom.u[1], g.stage[q], g.d_gsrc, nd);
+      else if (q == F_V) pack2_f64<<<nb, 256, 0, g.stream>>>(g.dom.v[0], g.dom.v[1], g.stage[q], g.d_gsrc, nd);
+      else pack_f64<<<nb, 256, 0, g.stream>>>(g.dfield[q], g.stage[q], g.d_gsrc, nd);
+    }
+    CK(cudaMemcpyAsync(g.stage_mask2, f->iceUmask, g.nblk_elems * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+    pack_mask<<<nb, 256, 0, g.stream>>>(g.dmaskU, g.stage_mask2, g.d_gsrc, nd);
+    CK(cudaMemsetAsync(g.d_ever_off, 0, g.nblk_elems, g.stream));
+  }
+  // per step: iceTmask, strength, the T-point inputs (copies on the transfer stream, packs on the compute stream as they land)
+  CK(cudaEventRecord(g.ev_field[29], g.stream));
+  CK(cudaStreamWaitEvent(g.xfer, g.ev_field[29], 0));   // the staging buffers are free again
+  CK(cudaMemcpyAsync(g.stage_mask, pr->iceTmask, g.nblk_elems * sizeof(int), cudaMemcpyHostToDevice, g.xfer));
+  CK(cudaEventRecord(g.ev_field[30], g.xfer));
+  const double *tin[11] = {pr->strength, pr->tmass, pr->aice_init, pr->cdn_ocn, pr->uocn, pr->vocn, pr->ss_tltx, pr->ss_tlty, pr->strairxT, pr->strairyT, pr->TbU};
+  for (int q = 0; q < 11; ++q) {
+    if (!tin[q]) continue;
+    CK(cudaMemcpyAsync(g.stage[18 + q], tin[q], bblk, cudaMemcpyHostToDevice, g.xfer));
+    CK(cudaEventRecord(g.ev_field[18 + q], g.xfer));
+  }
+  CK(cudaStreamWaitEvent(g.stream, g.ev_field[30], 0));
+  pack_mask<<<nb, 256, 0, g.stream>>>(g.dmaskT, g.stage_mask, g.d_gsrc, nd);
+  {  // dyn_prep2's zeroing of the stresses off the ice (ice_dyn_shared.F90:717-730), on the device
+    note_off_ice<<<grid_blocks(g.nblk_elems), 256, 0, g.stream>>>(g.d_ever_off, g.stage_mask, (int)g.nblk_elems);
+    SigPtrs sp;
+    for (int q = 0; q < 12; ++q) { sp.p[q] = g.dom.sig[0][q]; sp.p[12 + q] = g.dom.sig[1][q]; }
+    zero_stress_off_ice<<<nb, 256, 0, g.stream>>>(sp, g.dmaskT, nd);
+  }
+  for (int q = 0; q < 11; ++q) {
+    if (!tin[q]) continue;
+    CK(cudaStreamWaitEvent(g.stream, g.ev_field[18 + q], 0));
+    pack_f64<<<nb, 256, 0, g.stream>>>(q == 0 ? g.dfield[F_STRENGTH] : g.prepT[q - 1], g.stage[18 + q], g.d_gsrc, nd);
+  }
+  PrepArgs a{};
+  a.hm = g.prep_static[0]; a.tarea = g.prep_static[1]; a.uarea = g.prep_static[2]; a.fcor = g.prep_static[3]; a.umask = g.prep_umask;
+  a.tmass = g.prepT[0]; a.aice = g.prepT[1]; a.cdn = g.prepT[2]; a.uocn = g.prepT[3]; a.vocn = g.prepT[4];
+  a.tltx = g.prepT[5]; a.tlty = g.prepT[6]; a.sax = g.prepT[7]; a.say = g.prepT[8];
+  a.TbU_in = pr->TbU ? g.prepT[9] : nullptr;
+  a.cdnU = g.dfield[F_CDN]; a.aiU = g.dfield[F_AIU]; a.uocnU = g.dfield[F_UOCN]; a.vocnU = g.dfield[F_VOCN];
+  a.waterx = g.dfield[F_WATERX]; a.watery = g.dfield[F_WATERY]; a.forcex = g.dfield[F_FORCEX]; a.forcey = g.dfield[F_FORCEY];
+  a.umassdti = g.dfield[F_UMASSDTI]; a.fm = g.dfield[F_FM]; a.TbU = g.dfield[F_TBU];
+  a.strintx = g.dfield[F_STRINTX]; a.strinty = g.dfield[F_STRINTY]; a.taubx = g.dfield[F_TAUBX]; a.tauby = g.dfield[F_TAUBY];
+  a.maskU = g.dmaskU;
+  a.dt = pr->dt; a.cosw = p->cosw; a.sinw = p->sinw; a.area_min = pr->dyn_area_min; a.mass_min = pr->dyn_mass_min; a.gravit = pr->gravit;
+  a.coupled_tilt = pr->ssh_stress;
+  CK(exact::launch_prep(g.dom, a, g.stream));
+  CK(cudaGetLastError());
+  g.uploaded = true;
+  g.stress_resident = true;
+  g.state_resident = true;
+  g.stress_uploaded_this_call = init;
+  if (do_subcycle(p)) return 1;
+  // out: the velocities always; diagnostics, stresses and the new iceUmask on request
+  int what = 4;
+  if (flags & EVP_B200_STEP_FETCH_DIAG) what |= 2;
+  if (flags & EVP_B200_STEP_FETCH_STATE) what |= 1;
+  if ((what & 2) && (!f->strintxU || !f->strintyU || !f->taubxU || !f->taubyU)) return fail("evp_b200_step_resident: EVP_B200_STEP_FETCH_DIAG needs the four arrays");
+  if (flags & EVP_B200_STEP_FETCH_STATE) {
+    if (!f->iceUmask) return fail("evp_b200_step_resident: EVP_B200_STEP_FETCH_STATE needs iceUmask");
+    // the mask array is intent(inout) on the interior only: start from the caller's copy
+    CK(cudaMemcpyAsync(g.stage_mask2, f->iceUmask, g.nblk_elems * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+    unpack_mask<<<grid_blocks(g.n_int), 256, 0, g.stream>>>(g.stage_mask2, g.dmaskU, g.d_int_lin, g.d_int_dom, g.n_int);
+    CK(cudaMemcpyAsync(const_cast<int32_t *>(f->iceUmask), g.stage_mask2, g.nblk_elems * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  }
+  return do_download(f, what);
+}
 
 int evp_b200_run_bgrid(const evp_b200_params_t *p, evp_b200_fields_t *f) {
   if (do_upload(f, false)) return 1;
   if (do_subcycle(p)) return 1;
-  return do_download(f, 3);
+  return do_download(f, 7);
 }
 
 int evp_b200_halo_plan(int32_t nranks, const int32_t *rects, int32_t rank, int32_t nxg, int32_t nyg, int32_t ew, int32_t ns,

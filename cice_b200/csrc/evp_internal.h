@@ -138,12 +138,25 @@ struct PersistPlan {
   unsigned smem_bytes;
 };
 
+// arguments of prep_kernel (evp_kernels.cu): the step preparation on the device
+struct PrepArgs {
+  const double *hm, *tarea, *uarea, *fcor;      // static: T land mask as 0/1 real, T-cell area, U-cell area, Coriolis parameter at U
+  const unsigned char *umask;                   // static: U-point land mask
+  const double *tmass, *aice, *cdn, *uocn, *vocn, *tltx, *tlty, *sax, *say;   // T points, halos filled by the caller
+  const double *TbU_in;                         // null: no seabed stress (TbU = 0)
+  double *cdnU, *aiU, *uocnU, *vocnU, *waterx, *watery, *forcex, *forcey, *umassdti, *fm, *TbU, *strintx, *strinty, *taubx, *tauby;
+  unsigned char *maskU;
+  double dt, cosw, sinw, area_min, mass_min, gravit;
+  int coupled_tilt;                             // ssh_stress: 0 geostrophic, 1 coupled
+};
+
 // launchers implemented once per arithmetic mode (namespace exact / fast)
 #define EVP_DECLARE_LAUNCHERS(NS)                                                                   \
   namespace NS {                                                                                    \
   cudaError_t launch_stress(const Dom &d, const KParams &p, int cur, cudaStream_t s);               \
   cudaError_t launch_stepu(const Dom &d, const KParams &p, int cur, cudaStream_t s);                \
   cudaError_t launch_deform(const Dom &d, int cur, const double *dxU, const double *dyU, const double *tarear, double *divu, double *shear, double *vort, double *rdg_conv, double *rdg_shear, double e_factor, cudaStream_t s); \
+  cudaError_t launch_prep(const Dom &d, const PrepArgs &args, cudaStream_t s); \
   cudaError_t launch_finish(const Dom &d, int cur, double *strocnx, double *strocny, double rhow, double cosw, double sinw, cudaStream_t s); \
   cudaError_t launch_fused(const Dom &d, const KParams &p, int cur, cudaStream_t s, int form, bool pdl, int last); \
   cudaError_t launch_fused_p2p(const Dom &d, const KParams &p, const P2PParams &pp, int cur, int ksub, int last, int form, cudaStream_t s); \

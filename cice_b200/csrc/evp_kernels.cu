@@ -161,7 +161,71 @@ __global__ void __launch_bounds__(256) finish_kernel(const __grid_constant__ Dom
   strocny[c] = vrel * (dv * cosw + du * sinw * sg);
 }
 
+// The step preparation of evp() between the halo updates of the T-point inputs and the subcycle loop, one
+// thread per U point of the sub-domain:
+//   * grid_average_X2YS 'NE' (ice_grid.F90:4187-4205) of tmass, aice_init, cdn_ocn, uocn, vocn (, ss_tltx, ss_tlty): masked,
+//     area-weighted four-point averages, every product and sum in the reference's order;
+//   * grid_average_X2YF 'NE' (ice_grid.F90:4644-4655) of the wind stress;
+//   * dyn_prep2 (ice_dyn_shared.F90:705-837) at the U point: new ice mask from the OLD one the device kept, velocity of new ice
+//     points = ocean current, zero where masked out, Coriolis, water and forcing terms (geostrophic or coupled tilt).
+// Writes the eleven U-point inputs of the loop, the new mask and the velocities (both ping-pong copies, wrap ghosts included).
+__global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ Dom d, const __grid_constant__ PrepArgs a) {
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > d.nx || j > d.ny) return;
+  const int c = at(d, i, j), e = c + 1, n = c + d.ld, ne = n + 1;
+  const double mc = a.hm[c], me = a.hm[e], mn = a.hm[n], mne = a.hm[ne];
+  const double tc = a.tarea[c], te = a.tarea[e], tn = a.tarea[n], tne = a.tarea[ne];
+  const double wtmp = mc * tc + me * te + mn * tn + mne * tne;
+  auto avgS = [&](const double *w) {
+    double r = 0.0;
+    if (wtmp != 0.0) r = (mc * w[c] * tc + me * w[e] * te + mn * w[n] * tn + mne * w[ne] * tne) / wtmp;
+    return r;
+  };
+  auto avgF = [&](const double *w) { return 0.25 * (w[c] * tc + w[e] * te + w[n] * tn + w[ne] * tne) / a.uarea[c]; };
+  const double umass = avgS(a.tmass), aiU = avgS(a.aice), cdnU = avgS(a.cdn), uo = avgS(a.uocn), vo = avgS(a.vocn);
+  const double sax = avgF(a.sax), say = avgF(a.say);
+  const bool old = a.maskU[c] != 0;
+  const bool ice = a.umask[c] && aiU > a.area_min && umass > a.mass_min;
+  double u = d.u[0][c], v = d.v[0][c];
+  double waterx = 0.0, watery = 0.0, forcex = 0.0, forcey = 0.0, umassdti = 0.0, fm = a.fm[c];
+  if (ice) {
+    if (!old) { u = uo; v = vo; }   // new ice points start from the ocean surface current
+    umassdti = umass / a.dt;
+    fm = a.fcor[c] * umass;
+    const double sg = copysign(1.0, fm);
+    waterx = uo * a.cosw - vo * a.sinw * sg;
+    watery = vo * a.cosw + uo * a.sinw * sg;
+    double tx, ty;
+    if (a.coupled_tilt) {
+      tx = -a.gravit * umass * avgS(a.tltx);
+      ty = -a.gravit * umass * avgS(a.tlty);
+    } else {
+      tx = -fm * vo;
+      ty = fm * uo;
+    }
+    forcex = sax + tx;
+    forcey = say + ty;
+  } else {
+    u = 0.0; v = 0.0;
+    a.strintx[c] = 0.0; a.strinty[c] = 0.0;
+  }
+  a.maskU[c] = ice ? 1 : 0;
+  a.cdnU[c] = cdnU; a.aiU[c] = aiU; a.uocnU[c] = uo; a.vocnU[c] = vo;
+  a.waterx[c] = waterx; a.watery[c] = watery; a.forcex[c] = forcex; a.forcey[c] = forcey;
+  a.umassdti[c] = umassdti; a.fm[c] = fm;
+  a.TbU[c] = a.TbU_in ? a.TbU_in[c] : 0.0;
+  a.taubx[c] = 0.0; a.tauby[c] = 0.0;   // dyn_prep2 clears them everywhere; the loop's last subcycle sets them on the ice
+  store_uv(d, d.u[0], d.v[0], i, j, u, v);
+  store_uv(d, d.u[1], d.v[1], i, j, u, v);
+}
+
 #ifndef EVP_HOST_EMU  // launchers: not part of the host emulation (tests/emu_bgrid.cpp)
+cudaError_t launch_prep(const Dom &d, const PrepArgs &args, cudaStream_t s) {
+  dim3 b(32, 8), g((d.nx + b.x - 1) / b.x, (d.ny + b.y - 1) / b.y);
+  prep_kernel<<<g, b, 0, s>>>(d, args);
+  return cudaGetLastError();
+}
 cudaError_t launch_finish(const Dom &d, int cur, double *strocnx, double *strocny, double rhow, double cosw, double sinw, cudaStream_t s) {
   dim3 b(32, 8), g((d.nx + b.x - 1) / b.x, (d.ny + b.y - 1) / b.y);
   finish_kernel<<<g, b, 0, s>>>(d, d.u[cur], d.v[cur], strocnx, strocny, rhow, cosw, sinw);

@@ -78,6 +78,53 @@ def dyn_evp_b200_run_resident(params, fields, keep_stress=True, fetch_stress=Fal
     return fields
 
 
+def dyn_evp_b200_prep_init(static):
+    """static inputs of the device-side step preparation: hm, tarea, uarea, fcor, umask (after dyn_evp_b200_init)."""
+    st, keep = abi.make_prep_static(static, _state["npl"])
+    check(load().evp_b200_prep_init(C.byref(st)), "evp_b200_prep_init")
+    _state["pkeep"] = keep
+
+
+def dyn_evp_b200_step_resident(params, prep, fields, init_state=False, fetch_diag=False, fetch_state=False):
+    """one dynamics step with the preparation on the device (T -> U averages, dyn_prep2) and the whole dynamics state resident:
+    `prep` holds the T-point inputs of the step, `fields` receives uvel, vvel (and what the flags ask for)."""
+    p = abi.make_params(params)
+    pr, k1 = abi.make_prep(prep, _state["npl"])
+    f, k2 = abi.make_fields_partial(fields, _state["npl"])
+    flags = (abi.STEP_INIT_STATE if init_state else 0) | (abi.STEP_FETCH_DIAG if fetch_diag else 0) | (abi.STEP_FETCH_STATE if fetch_state else 0)
+    check(load().evp_b200_step_resident(C.byref(p), C.byref(pr), C.byref(f), flags), "evp_b200_step_resident")
+    return fields
+
+
+def bind(entry, params, fields, prep=None, **flags):
+    """A zero-argument callable for one of the per-step entry points with its C structs built ONCE: what a compiled caller does
+    (the Fortran shim fills its structs once per run).  entry: "run" (evp_b200_run_bgrid), "run_resident"
+    (evp_b200_run_bgrid_resident, keep_stress / fetch_stress) or "step_resident" (evp_b200_step_resident, init_state / fetch_diag /
+    fetch_state).  The arrays must stay alive and in place; timing loops use this so that they time the C ABI, not ctypes marshalling."""
+    L = load()
+    p = abi.make_params(params)
+    if entry == "run":
+        f, keep = _fields(fields)
+        fn, args, what = L.evp_b200_run_bgrid, (C.byref(p), C.byref(f)), "evp_b200_run_bgrid"
+    elif entry == "run_resident":
+        f, keep = _fields(fields)
+        fl = (abi.KEEP_STRESS if flags.get("keep_stress", True) else 0) | (abi.FETCH_STRESS if flags.get("fetch_stress") else 0)
+        fn, args, what = L.evp_b200_run_bgrid_resident, (C.byref(p), C.byref(f), fl), "evp_b200_run_bgrid_resident"
+    elif entry == "step_resident":
+        pr, k1 = abi.make_prep(prep, _state["npl"])
+        f, keep = abi.make_fields_partial(fields, _state["npl"])
+        keep = (keep, k1, pr)
+        fl = ((abi.STEP_INIT_STATE if flags.get("init_state") else 0) | (abi.STEP_FETCH_DIAG if flags.get("fetch_diag") else 0)
+              | (abi.STEP_FETCH_STATE if flags.get("fetch_state") else 0))
+        fn, args, what = L.evp_b200_step_resident, (C.byref(p), C.byref(pr), C.byref(f), fl), "evp_b200_step_resident"
+    else:
+        raise ValueError(entry)
+
+    def call(_keep=(p, f, keep)):
+        check(fn(*args), what)
+    return call
+
+
 def download_stress(fields):
     """fetch the device-resident stresses into the host arrays (restart / history)."""
     f, keep = _fields(fields)

@@ -563,6 +563,20 @@ def make_cdcase(config="gx3", block_size=None, seed=None, ndte=None, mode=abi.MO
 U_PREP = ("umassdti", "fmU", "waterxU", "wateryU", "forcexU", "forceyU", "TbU")  # interior-only after dyn_prep2
 
 
+def step_inputs(c, max_blocks=None):
+    """(static, prep) of cice_b200.dyn_evp.dyn_evp_b200_prep_init / dyn_evp_b200_step_resident for a Case: the T-point inputs of the
+    step and the static arrays, in the reference's block layout, from the same global state the U-point inputs of c.fields were
+    derived from -- the device-side preparation must reproduce those bit for bit."""
+    X, B = c.X, c.blocks
+    sc = lambda a: np.ascontiguousarray(scatter(np.asarray(a, dtype=np.float64), B, max_blocks))
+    static = dict(hm=sc(X["hm"]), tarea=sc(X["tarea"]), uarea=sc(X["uarea"]), fcor=np.full_like(sc(X["hm"]), FCOR_CONST),
+                  umask=np.ascontiguousarray(scatter((X["uvm"] > 0.5).astype(np.int32), B, max_blocks)))
+    prep = dict(tmass=sc(X["tmass"]), aice_init=sc(X["aice"]), cdn_ocn=np.full_like(sc(X["hm"]), CDN_OCN), uocn=sc(X["uocn"]),
+                vocn=sc(X["vocn"]), strairxT=sc(X["strax"]), strairyT=sc(X["stray"]), strength=c.fields["strength"].copy(),
+                iceTmask=c.fields["iceTmask"].copy(), dt=3600.0, dyn_area_min=1e-11, dyn_mass_min=1e-10)
+    return static, prep
+
+
 class Case:
     """One synthetic EVP step in the reference's block layout, ready for the C ABI."""
 

@@ -302,6 +302,45 @@ enum {
 int evp_b200_run_bgrid_resident(const evp_b200_params_t *params, evp_b200_fields_t *fields, int32_t flags);
 int evp_b200_download_stress(evp_b200_fields_t *fields);
 
+/* ---- next rows: the step preparation on the device, the whole dynamics state resident ----------
+ * Replaces, between the halo updates of the T-point inputs and the subcycle loop of evp() (ice_dyn_evp.F90:428-560):
+ *   grid_average_X2Y('S', tmass|aice_init|cdn_ocn|uocn|vocn|ss_tltx|ss_tlty, 'T', .., 'U')   ice_grid.F90:4159-4211
+ *   grid_average_X2Y('F', strairxT|strairyT, 'T', .., 'U')                                       ice_grid.F90:4620-4660
+ *   dyn_prep2                                                                                    ice_dyn_shared.F90:593-839
+ * so that a step uploads NINE T-point arrays + strength + iceTmask instead of the eleven U-point inputs, the velocities, both
+ * masks and (first form) the stresses, and downloads the velocities only (diagnostics on request).  Carried on the device
+ * between steps: velocities, stresses, and iceUmask -- dyn_prep2 needs the OLD mask to find new ice points (:765-783).
+ * One rank only in this version (the velocity halo update that follows dyn_prep2, ice_dyn_evp.F90:735-739, is the on-rank wrap);
+ * not for tripole grids (see EVP_B200_KEEP_STRESS).  Ice strength stays with the caller (Icepack). */
+typedef struct {
+  /* static, arrays (nx_block, ny_block, max_blocks) like everything else */
+  const double *hm;      /* T land mask as 0/1 real (ice_grid.F90: hm)   */
+  const double *tarea;   /* T-cell area                                  */
+  const double *uarea;   /* U-cell area                                  */
+  const double *fcor;    /* Coriolis parameter at U points (fcor_blk)    */
+  const int32_t *umask;  /* U-point land mask, Fortran logical           */
+} evp_b200_prep_static_t;
+int evp_b200_prep_init(const evp_b200_prep_static_t *st);
+
+typedef struct {
+  /* per step, T points, ghost cells filled (the caller's ice_HaloUpdate calls of ice_dyn_evp.F90:419-426, 471-474 stay) */
+  const double *tmass, *aice_init, *cdn_ocn, *uocn, *vocn;
+  const double *ss_tltx, *ss_tlty;     /* read only when ssh_stress is coupled; may be NULL otherwise */
+  const double *strairxT, *strairyT;
+  const double *strength;              /* after its halo update (ice_dyn_evp.F90:731-733) */
+  const int32_t *iceTmask;             /* after its halo update (:415-418) */
+  const double *TbU;                   /* seabed stress factor at U points, or NULL (seabed_stress = .false.) */
+  double dt, dyn_area_min, dyn_mass_min, gravit;
+  int32_t ssh_stress;                  /* 0 geostrophic, 1 coupled */
+} evp_b200_prep_t;
+enum {
+  EVP_B200_STEP_INIT_STATE = 1,   /* take uvel, vvel, iceUmask and the 12 stresses from `fields` first (first step, after a restart read) */
+  EVP_B200_STEP_FETCH_DIAG = 2,   /* copy strintxU, strintyU, taubxU, taubyU back as well (history steps) */
+  EVP_B200_STEP_FETCH_STATE = 4   /* copy the 12 stresses and iceUmask back as well (restart steps) */
+};
+/* one dynamics step: preparation + the whole subcycle loop; fields->uvel, vvel are written, the rest of `fields` as the flags say */
+int evp_b200_step_resident(const evp_b200_params_t *params, const evp_b200_prep_t *prep, evp_b200_fields_t *fields, int32_t flags);
+
 /* ---- measurement hooks (not part of the reference seam) ---------------------------------- */
 /* device time of the most recent evp_b200_subcycle in ms (CUDA events on the library's stream) */
 int evp_b200_last_loop_ms(double *ms);

@@ -545,3 +545,48 @@ def test_deformations_between_subcycle_and_download(oracle_mod, evp_lib):
     finally:
         evp_lib.dyn_evp_b200_finalize()
     assert_bitwise(f, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [dict(config="gx3", block_size=(50, 58), ndte=12), dict(config="gx3", ndte=9, kmt="continents"),
+                                 dict(config="tiny", ndte=7, ns="cyclic", kmt="none")], ids=["gx3-4blocks", "gx3-continents", "tiny-doubly-cyclic"])
+def test_step_preparation_on_the_device(oracle_mod, evp_lib, cfg):
+    """evp_b200_step_resident takes the T-point inputs of a step, forms the U-point inputs itself
+    (grid_average_X2Y 'S' and 'F', dyn_prep2) and keeps velocities, stresses and iceUmask on the device.  Started from rest with
+    no ice mask (every ice point is a new ice point and takes the ocean current, ice_dyn_shared.F90:772-775) it must give, bit for
+    bit, what the oracle gives on the host-prepared inputs -- and again for a second step that uploads no carried state at all."""
+    c = synth.make_case(**cfg)
+    static, prep = synth.step_inputs(c)
+    ref = c.copy_fields()
+    run_oracle_inplace = lambda f: oracle_mod.evp_run_bgrid(c.grid, c.params, f)
+    run_oracle_inplace(ref)
+    got = {n: c.fields[n].copy() for n in abi.STRESS}
+    for n in ("uvel", "vvel", "strintxU", "strintyU", "taubxU", "taubyU"):
+        got[n] = np.zeros_like(c.fields["uvel"])
+    got["iceUmask"] = np.zeros_like(c.fields["iceUmask"])
+    p = dict(c.params, mode=abi.MODE_EXACT, kernel=abi.KERNEL_AUTO)
+    evp_lib.dyn_evp_b200_init(c.grid)
+    try:
+        evp_lib.dyn_evp_b200_prep_init(static)
+        evp_lib.dyn_evp_b200_step_resident(p, prep, got, init_state=True, fetch_diag=True, fetch_state=True)
+        assert_bitwise(got, ref)
+        assert np.array_equal(got["iceUmask"] != 0, c.fields["iceUmask"] != 0)
+        # second step: same forcing, nothing carried crosses; only uvel, vvel come back
+        ref2 = {k: v.copy() for k, v in ref.items()}
+        for n in ("taubxU", "taubyU"):
+            ref2[n][...] = 0.0     # dyn_prep2 clears them (ice_dyn_shared.F90:712-713)
+        run_oracle_inplace(ref2)
+        out2 = {"uvel": np.zeros_like(got["uvel"]), "vvel": np.zeros_like(got["vvel"])}
+        evp_lib.dyn_evp_b200_step_resident(p, prep, out2)
+        assert_bitwise(out2, ref2, names=("uvel", "vvel"))
+        # ... and the state that stayed on the device is the oracle's, fetched on a third call's request
+        got3 = {n: np.zeros_like(got["uvel"]) for n in abi.FIELDS_INOUT}
+        got3["iceUmask"] = np.zeros_like(c.fields["iceUmask"])
+        ref3 = {k: v.copy() for k, v in ref2.items()}
+        for n in ("taubxU", "taubyU"):
+            ref3[n][...] = 0.0
+        run_oracle_inplace(ref3)
+        evp_lib.dyn_evp_b200_step_resident(p, prep, got3, fetch_diag=True, fetch_state=True)
+        assert_bitwise(got3, ref3)
+    finally:
+        evp_lib.dyn_evp_b200_finalize()
