@@ -26,6 +26,7 @@ module ice_dyn_evp_b200
   public :: dyn_evp_b200_init, dyn_evp_b200_run, dyn_evp_b200_finalize
   public :: dyn_evp_b200_init_cgrid, dyn_evp_b200_run_cgrid   ! grid_ice = 'C' (ice_dyn_evp.F90:936-1101)
   public :: dyn_evp_b200_deformations, dyn_evp_b200_finish    ! the two steps right after the loop, from the device-resident velocities
+  public :: dyn_evp_b200_prep_init, dyn_evp_b200_step         ! step preparation on the device, dynamics state resident (SURVEY 8f ranks 1, 3)
 
   integer(c_int32_t), parameter :: EVP_B200_ABI_VERSION = 3
   integer(c_int32_t), parameter :: BNDY_OPEN = 0, BNDY_CLOSED = 1, BNDY_CYCLIC = 2, BNDY_TRIPOLE = 3
@@ -89,7 +90,29 @@ module ice_dyn_evp_b200
      real(c_double) :: rhow, cosw, sinw
   end type evp_b200_finish_t
 
+  ! evp_b200_prep_static_t, evp_b200_prep_t (include/evp_b200.h)
+  type, bind(C) :: evp_b200_prep_static_t
+     type(c_ptr) :: hm, tarea, uarea, fcor, umask
+  end type evp_b200_prep_static_t
+  type, bind(C) :: evp_b200_prep_t
+     type(c_ptr) :: tmass, aice_init, cdn_ocn, uocn, vocn, ss_tltx, ss_tlty, strairxT, strairyT, strength
+     type(c_ptr) :: iceTmask, TbU
+     real(c_double) :: dt, dyn_area_min, dyn_mass_min, gravit
+     integer(c_int32_t) :: ssh_stress
+  end type evp_b200_prep_t
+
   interface
+     integer(c_int) function evp_b200_prep_init(st) bind(C, name='evp_b200_prep_init')
+       import :: c_int, evp_b200_prep_static_t
+       type(evp_b200_prep_static_t), intent(in) :: st
+     end function evp_b200_prep_init
+     integer(c_int) function evp_b200_step_resident(params, prep, fields, flags) bind(C, name='evp_b200_step_resident')
+       import :: c_int, c_int32_t, evp_b200_params_t, evp_b200_prep_t, evp_b200_fields_t
+       type(evp_b200_params_t), intent(in) :: params
+       type(evp_b200_prep_t), intent(in) :: prep
+       type(evp_b200_fields_t), intent(inout) :: fields
+       integer(c_int32_t), value :: flags
+     end function evp_b200_step_resident
      integer(c_int) function evp_b200_pin_host(ptr, bytes) bind(C, name='evp_b200_pin_host')
        import :: c_int, c_ptr, c_size_t
        type(c_ptr), value :: ptr
@@ -167,6 +190,7 @@ module ice_dyn_evp_b200
   integer(c_int32_t), allocatable, target, save :: b_iglob(:,:), b_jglob(:,:)
   integer(c_int32_t), allocatable, target, save :: imaskT(:,:,:), imaskU(:,:,:)
   integer(c_int32_t), allocatable, target, save :: imaskE(:,:,:), imaskN(:,:,:)   ! C grid
+  integer(c_int32_t), allocatable, target, save :: iumask(:,:,:)                  ! step preparation: umask as 0/1
   logical, save :: pinned = .false.   ! the B-grid field arrays have been page-locked (evp_b200_pin_host)
 
 contains
@@ -378,6 +402,80 @@ contains
     f%rhow = rhow;  f%cosw = cosw;  f%sinw = sinw
     call check(evp_b200_dyn_finish(f), 'evp_b200_dyn_finish')
   end subroutine dyn_evp_b200_finish
+
+  !---------------------------------------------------------------------
+  ! Step preparation on the device (SURVEY 8f ranks 1 and 3; include/evp_b200.h: evp_b200_prep_init / evp_b200_step_resident).
+  ! Once, after dyn_evp_b200_init: the static inputs of grid_average_X2Y 'S'/'F' (ice_grid.F90:4159-4211, 4620-4660) and of dyn_prep2.
+  subroutine dyn_evp_b200_prep_init
+    use ice_grid,       only: hm, tarea, uarea, umask
+    use ice_dyn_shared, only: fcor_blk
+    type(evp_b200_prep_static_t) :: st
+    allocate(iumask(nx_block, ny_block, max_blocks))
+    iumask = merge(1_c_int32_t, 0_c_int32_t, umask)
+    st%hm = loc3(hm);  st%tarea = loc3(tarea);  st%uarea = loc3(uarea);  st%fcor = loc3(fcor_blk);  st%umask = c_loc(iumask)
+    call check(evp_b200_prep_init(st), 'evp_b200_prep_init')
+  end subroutine dyn_evp_b200_prep_init
+
+  ! One dynamics step: replaces ice_dyn_evp.F90:428-531 (T -> U averages, dyn_prep2), :735-739 (velocity halo update) and the
+  ! subcycle loop :859-913.  The T-point arrays have had their halo updates (:419-426, 471-474), strength its own (:731-733).
+  ! Velocities, stresses and iceUmask live on the device; uvel, vvel are returned every step.
+  subroutine dyn_evp_b200_step(tmass, aice_init, cdn_ocn, uocn, vocn, ss_tltx, ss_tlty, strairxT, strairyT, strength, iceTmask, &
+                               uvel, vvel, first_step, want_diag, want_state,                                                    &
+                               stressp_1 , stressp_2 , stressp_3 , stressp_4 , stressm_1 , stressm_2 , stressm_3 , stressm_4 ,   &
+                               stress12_1, stress12_2, stress12_3, stress12_4, strintxU, strintyU, taubxU, taubyU, iceUmask, TbU)
+    use ice_dyn_shared, only: ndte, arlx1i, denom1, revp, brlx, e_factor, epp2i, capping, Ktens, u0, cosw, sinw, deltaminEVP, &
+                              dyn_area_min, dyn_mass_min, ssh_stress
+    use ice_calendar,   only: dt_dyn
+    use icepack_intfc,  only: icepack_query_parameters
+    real(kind=dbl_kind), dimension(:,:,:), intent(in), target, contiguous :: &
+         tmass, aice_init, cdn_ocn, uocn, vocn, ss_tltx, ss_tlty, strairxT, strairyT, strength
+    logical(kind=log_kind), dimension(:,:,:), intent(in) :: iceTmask
+    real(kind=dbl_kind), dimension(:,:,:), intent(inout), target, contiguous :: uvel, vvel
+    logical(kind=log_kind), intent(in) :: first_step, want_diag, want_state
+    ! carried state and diagnostics: read when first_step, written when want_state / want_diag
+    real(kind=dbl_kind), dimension(:,:,:), intent(inout), target, contiguous :: &
+         stressp_1 , stressp_2 , stressp_3 , stressp_4 , stressm_1 , stressm_2 , stressm_3 , stressm_4 , &
+         stress12_1, stress12_2, stress12_3, stress12_4, strintxU, strintyU, taubxU, taubyU
+    logical(kind=log_kind), dimension(:,:,:), intent(inout) :: iceUmask
+    real(kind=dbl_kind), dimension(:,:,:), intent(in), target, contiguous, optional :: TbU   ! seabed_stress = .true. only
+    type(evp_b200_params_t) :: p
+    type(evp_b200_prep_t)   :: pr
+    type(evp_b200_fields_t) :: f
+    integer(c_int32_t) :: flags
+    real(kind=dbl_kind) :: rhow, gravit
+
+    call icepack_query_parameters(rhow_out=rhow, gravit_out=gravit)
+    p%ndte = ndte;  p%mode = 0;  p%kernel = 0;  p%visc_method = 0
+    p%arlx1i = arlx1i;  p%denom1 = denom1;  p%revp = revp;  p%brlx = brlx
+    p%e_factor = e_factor;  p%epp2i = epp2i;  p%capping = capping;  p%Ktens = Ktens
+    p%u0 = u0;  p%cosw = cosw;  p%sinw = sinw;  p%rhow = rhow;  p%deltaminEVP = deltaminEVP
+
+    imaskT = merge(1_c_int32_t, 0_c_int32_t, iceTmask)
+    pr%tmass = c_loc(tmass);  pr%aice_init = c_loc(aice_init);  pr%cdn_ocn = c_loc(cdn_ocn)
+    pr%uocn = c_loc(uocn);    pr%vocn = c_loc(vocn);            pr%ss_tltx = c_loc(ss_tltx);  pr%ss_tlty = c_loc(ss_tlty)
+    pr%strairxT = c_loc(strairxT);  pr%strairyT = c_loc(strairyT);  pr%strength = c_loc(strength)
+    pr%iceTmask = c_loc(imaskT)
+    pr%TbU = c_null_ptr
+    if (present(TbU)) pr%TbU = c_loc(TbU)
+    pr%dt = dt_dyn;  pr%dyn_area_min = dyn_area_min;  pr%dyn_mass_min = dyn_mass_min;  pr%gravit = gravit
+    pr%ssh_stress = 0
+    if (trim(ssh_stress) == 'coupled') pr%ssh_stress = 1
+
+    f%stressp_1 = c_loc(stressp_1);   f%stressp_2 = c_loc(stressp_2);   f%stressp_3 = c_loc(stressp_3);   f%stressp_4 = c_loc(stressp_4)
+    f%stressm_1 = c_loc(stressm_1);   f%stressm_2 = c_loc(stressm_2);   f%stressm_3 = c_loc(stressm_3);   f%stressm_4 = c_loc(stressm_4)
+    f%stress12_1 = c_loc(stress12_1); f%stress12_2 = c_loc(stress12_2); f%stress12_3 = c_loc(stress12_3); f%stress12_4 = c_loc(stress12_4)
+    f%strintxU = c_loc(strintxU);  f%strintyU = c_loc(strintyU);  f%taubxU = c_loc(taubxU);  f%taubyU = c_loc(taubyU)
+    f%uvel = c_loc(uvel);  f%vvel = c_loc(vvel)
+    imaskU = merge(1_c_int32_t, 0_c_int32_t, iceUmask)
+    f%iceTmask = c_loc(imaskT);  f%iceUmask = c_loc(imaskU)
+
+    flags = 0
+    if (first_step) flags = flags + 1          ! EVP_B200_STEP_INIT_STATE
+    if (want_diag)  flags = flags + 2          ! EVP_B200_STEP_FETCH_DIAG
+    if (want_state) flags = flags + 4          ! EVP_B200_STEP_FETCH_STATE
+    call check(evp_b200_step_resident(p, pr, f, flags), 'evp_b200_step_resident')
+    if (want_state) iceUmask = (imaskU /= 0)
+  end subroutine dyn_evp_b200_step
 
   !---------------------------------------------------------------------
   ! grid_ice = 'C': once, after dyn_evp_b200_init (the ratio arrays exist after init_evp, ice_dyn_evp.F90:218-240)
