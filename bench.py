@@ -61,14 +61,46 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and clock-event reasons DURING the timed region, sampled every 2 ms through NVML (nvidia_ml_py) -- the timed region of
+    the default run is ~20 ms of GPU time, shorter than one period of `nvidia-smi -lms 100` -- with nvidia-smi as the fallback
+    (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu=0):
-        self.gpu, self.proc, self.lines = gpu, None, []
+        self.gpu, self.proc, self.lines, self.nvml, self.samples, self.stop_flag = gpu, None, [], None, [], False
+
+    def _nvml_loop(self):
+        import pynvml as N
+        h = self.nvml
+        names = (("hw_slowdown", N.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", N.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksEventReasonSwPowerCap),
+                 ("hw_power_brake", N.nvmlClocksEventReasonHwPowerBrakeSlowdown))
+        while not self.stop_flag:
+            try:
+                mhz = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.samples.append((mhz, tuple(n for n, bit in names if r & bit)))
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            self.nvml = N.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = N.nvmlDeviceGetMaxClockInfo(self.nvml, N.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
@@ -78,6 +110,13 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=2)
+            sm = [m for m, _ in self.samples]
+            reasons = sorted({r for _, rs in self.samples for r in rs})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                    "sm_max_mhz": float(self.max_mhz), "reasons": reasons, "samples": len(sm), "source": "NVML, every 2 ms during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -95,7 +134,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def layout_of(args):
