@@ -386,10 +386,13 @@ def run_ours(args):
         e2e_how = "evp_b200_run_bgrid: every field crosses both ways (tripole grid)"
     # (d) the step preparation on the device too (evp_b200_step_resident): per step the nine T-point
     #     inputs + strength + iceTmask go in, the velocities come out; velocities, stresses and iceUmask stay on the device.
-    #     One rank, no tripole fold in this version.
+    #     Not for tripole grids in this version; between ranks the velocity halo after dyn_prep2 is one staged exchange per step.
     e2e_step = None
-    if world == 1 and resident_ok:
+    if resident_ok:
         static, prep = synth.step_inputs(case)
+        if world > 1:   # this rank's blocks
+            static = {k: (np.ascontiguousarray(v[bids]) if isinstance(v, np.ndarray) else v) for k, v in static.items()}
+            prep = {k: (np.ascontiguousarray(v[bids]) if isinstance(v, np.ndarray) else v) for k, v in prep.items()}
         pst = pin({k: v for k, v in static.items() if k != "umask"})
         pst["umask"] = static["umask"]
         ppr = pin({k: v for k, v in prep.items() if isinstance(v, np.ndarray) and v.dtype == np.float64})
@@ -428,9 +431,11 @@ def run_ours(args):
                                              "arrays page-locked once with evp_b200_pin_host as the Fortran shim does on its first call"}
 
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s, kernel_ms, e2e_full_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([total_ms, e2e_s, kernel_ms, e2e_full_s, e2e_step["ms_per_step"] if e2e_step else 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, kernel_ms, e2e_full_s = (float(x) for x in t.tolist())
+        total_ms, e2e_s, kernel_ms, e2e_full_s, step_ms = (float(x) for x in t.tolist())
+        if e2e_step:
+            e2e_step.update(ms_per_step=step_ms, value=cells_global * ndte / (step_ms * 1e-3))
     dyn_evp.dyn_evp_b200_finalize()
 
     if rank == 0:

@@ -1314,8 +1314,8 @@ __global__ void unpack_mask(int *__restrict__ dst_blk, const unsigned char *__re
 int evp_b200_prep_init(const evp_b200_prep_static_t *st) {
   if (!g.inited) return fail("evp_b200_prep_init: call evp_b200_init first");
   if (!st || !st->hm || !st->tarea || !st->uarea || !st->fcor || !st->umask) return fail("evp_b200_prep_init: null argument");
-  if (g_comm.nranks > 1 || g.halo.n_dst != 0 || !g.halo.peers.empty())
-    return fail("evp_b200_prep_init: one rank and no tripole fold in this version (the velocity halo update after dyn_prep2 is the on-rank wrap only)");
+  if (g.ns == EVP_B200_BNDY_TRIPOLE || g.halo.has_fold)
+    return fail("evp_b200_prep_init: not for tripole grids in this version (the host symmetrises the stresses across the fold, ice_dyn_evp.F90:1322-1389)");
   CK(cudaSetDevice(g.device));
   const size_t bdom = g.ndom * sizeof(double), bblk = g.nblk_elems * sizeof(double);
   const int nd = (int)g.ndom, nb = grid_blocks(g.ndom);
@@ -1414,6 +1414,14 @@ int evp_b200_step_resident(const evp_b200_params_t *p, const evp_b200_prep_t *pr
   a.coupled_tilt = pr->ssh_stress;
   CK(exact::launch_prep(g.dom, a, g.stream));
   CK(cudaGetLastError());
+  // "velocities may have changed in dyn_prep2" (ice_dyn_evp.F90:735-739): the ghost cells that neighbour ranks own are refreshed once,
+  // in both ping-pong copies, by the staged exchange (the on-rank wrap was written by the kernel itself)
+  if (g.halo.n_dst != 0 || !g.halo.peers.empty()) {
+    for (int b = 0; b < 2; ++b) {
+      int hl = 0;
+      if (g.halo.exchange(g_comm, g.dom.u[b], g.dom.v[b], g.stream, &hl, g_err, sizeof g_err)) return 1;
+    }
+  }
   g.uploaded = true;
   g.stress_resident = true;
   g.state_resident = true;

@@ -310,8 +310,8 @@ int evp_b200_download_stress(evp_b200_fields_t *fields);
  * so that a step uploads NINE T-point arrays + strength + iceTmask instead of the eleven U-point inputs, the velocities, both
  * masks and (first form) the stresses, and downloads the velocities only (diagnostics on request).  Carried on the device
  * between steps: velocities, stresses, and iceUmask -- dyn_prep2 needs the OLD mask to find new ice points (:765-783).
- * One rank only in this version (the velocity halo update that follows dyn_prep2, ice_dyn_evp.F90:735-739, is the on-rank wrap);
- * not for tripole grids (see EVP_B200_KEEP_STRESS).  Ice strength stays with the caller (Icepack). */
+ * The velocity halo update that follows dyn_prep2 (ice_dyn_evp.F90:735-739) is the on-rank wrap plus, between ranks, one staged
+ * exchange per step.  Not for tripole grids (see EVP_B200_KEEP_STRESS).  Ice strength stays with the caller (Icepack). */
 typedef struct {
   /* static, arrays (nx_block, ny_block, max_blocks) like everything else */
   const double *hm;      /* T land mask as 0/1 real (ice_grid.F90: hm)   */

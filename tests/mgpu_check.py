@@ -35,7 +35,8 @@ def main():
     dist.broadcast_object_list(ids, src=0)
     dyn_evp.comm_init(rank, world, ids[0])
 
-    case = synth.make_case(cfg, block_size=(bsx, bsy), seed=31, ndte=ndte, ns=ns,
+    # (the step-resident mode starts from rest with no ice mask, like the first step of a run: set S1, no random state on top)
+    case = synth.make_case(cfg, block_size=(bsx, bsy), seed=None if kernel == "step" else 31, ndte=ndte, ns=ns,
                            kmt=(None if cfg == "tx1" else "none") if ns == "tripole" else ("continents" if elim else None))
     owner, pg = decomp.cartesian_owner(case.blocks, world)
     if elim:
@@ -43,10 +44,21 @@ def main():
             if not case.fields["iceTmask"][n][1:-1, 1:-1].any() and not case.fields["iceUmask"][n].any():
                 owner[n] = -1
     g, f, bids = case.rank_view(owner, rank)
-    p = dict(case.params, mode=abi.MODE_EXACT, kernel=abi.KERNEL_NAMES[kernel])
+    step = kernel == "step"   # the step preparation on the device, state resident (evp_b200_step_resident), two consecutive steps
+    p = dict(case.params, mode=abi.MODE_EXACT, kernel=abi.KERNEL_NAMES["auto" if step else kernel])
     dyn_evp.dyn_evp_b200_init(g)
     desc = dyn_evp.describe()
-    dyn_evp.dyn_evp_b200_run(p, f)
+    if step:
+        static, prep = synth.step_inputs(case)
+        sel = lambda dct: {k: (np.ascontiguousarray(v[bids]) if isinstance(v, np.ndarray) else v) for k, v in dct.items()}
+        static, prep = sel(static), sel(prep)
+        f = {n: (f[n] if n in abi.STRESS else np.zeros_like(f["uvel"])) for n in abi.FIELDS_INOUT}
+        f["iceUmask"] = np.zeros(f["uvel"].shape, dtype=np.int32)
+        dyn_evp.dyn_evp_b200_prep_init(static)
+        dyn_evp.dyn_evp_b200_step_resident(p, prep, f, init_state=True)
+        dyn_evp.dyn_evp_b200_step_resident(p, prep, f, fetch_diag=True, fetch_state=True)
+    else:
+        dyn_evp.dyn_evp_b200_run(p, f)
     nl = dyn_evp.last_launches()
     dyn_evp.dyn_evp_b200_finalize()
 
@@ -57,6 +69,10 @@ def main():
         from oracle import oracle
         ref = case.copy_fields()
         oracle.evp_run_bgrid(case.grid, case.params, ref)   # all blocks: elimination does not change the kept ones (test_oracle.py)
+        if step:   # second step: dyn_prep2 clears taubx/tauby, everything else carries over
+            for n in ("taubxU", "taubyU"):
+                ref[n][...] = 0.0
+            oracle.evp_run_bgrid(case.grid, case.params, ref)
         nbad = 0
         for bids_r, fr, desc_r, nl_r in out:
             for n in abi.FIELDS_INOUT:
