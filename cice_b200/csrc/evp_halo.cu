@@ -419,7 +419,7 @@ int HaloPlan::build_local_fold(int nxg, int nyg, int ew, int ns, int max_entries
 __global__ void ll_mark_kernel(unsigned long long *ll, const int *slot, int n, int ring) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n || slot[k] < 0) return;
-  for (int par = 0; par < 2; ++par)
+  for (int par = 0; par < P2P_LL_SLOTS; ++par)
     for (int w = 0; w < 4; ++w) ll[((size_t)par * ring + slot[k]) * 4 + w] = 1ULL << 32;
 }
 
@@ -621,7 +621,7 @@ int P2PState::setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t 
   NCK(ncclAllReduce(d_err, d_err, 1, ncclInt32, ncclMax, cs.comm, 0));   // every mark has landed
   HCK(cudaStreamSynchronize(0));
   {
-    std::vector<unsigned long long> w((size_t)2 * prm.my_ring * 4);
+    std::vector<unsigned long long> w((size_t)P2P_LL_SLOTS * prm.my_ring * 4);
     HCK(cudaMemcpy(w.data(), prm.my_ll, w.size() * 8, cudaMemcpyDeviceToHost));
     std::vector<unsigned char> fed(prm.my_ring, 0);
     for (int r = 0; r < prm.my_ring; ++r) fed[r] = (w[(size_t)r * 4] >> 32) == 1ULL;

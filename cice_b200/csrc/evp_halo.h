@@ -88,7 +88,7 @@ struct P2PState {
   int setup(CommState &cs, const HaloPlan &plan, double *dshare, size_t ndom, int nx, int ny, int ld, int nxg, int nyg,
             int ew, int ns, int max_fold, char *err, size_t nerr);
   void set_parity(int swapped_);
-  static size_t share_bytes(size_t ndom, int nx, int ny) { return 4 * ndom * sizeof(double) + 64 * 8 + (size_t)2 * ring_cells(nx, ny) * 4 * 8; }
+  static size_t share_bytes(size_t ndom, int nx, int ny) { return 4 * ndom * sizeof(double) + 64 * 8 + (size_t)P2P_LL_SLOTS * ring_cells(nx, ny) * 4 * 8; }
   void release();
 };
 

@@ -71,6 +71,7 @@ struct KParams {
 // In-kernel NVLink halo (see evp_halo.cu, fused_kernel): edge CTAs store new edge velocities straight into the
 // neighbour GPUs' ghost cells (CUDA-IPC mapped peer memory) and hand over with per-peer epoch flags.
 #define P2P_MAXPEER 16
+#define P2P_LL_SLOTS 3   // copies of the low-latency slots, used round robin by subcycle (see P2PParams)
 struct P2PParams {
   int enabled;
   int npeers;
@@ -90,7 +91,9 @@ struct P2PParams {
   unsigned long long *epoch_base;              // device-resident: epoch of the current loop
   int *err;                                    // set when a wait times out
   unsigned long long *dbg;                     // [0] sum of wait cycles of lane 0 of edge CTAs, [1] number of waits, [2] max wait
-  // Low-latency slots (persistent kernel): every ghost cell that a neighbour GPU feeds has, per ping-pong parity, four 8-byte words
+  // Low-latency slots (persistent kernel): every ghost cell that a neighbour GPU feeds has, in each of P2P_LL_SLOTS copies used round
+  // robin by subcycle (one more than the ping-pong needs: a sender is never less than two subcycles from a copy still being read,
+  // whatever the tilings of the two ranks), four 8-byte words
   // (lo32(u) | tag << 32, hi32(u) | tag << 32, the same for v) in the receiver's memory.  A value validates itself -- tag = low 32
   // bits of epoch + subcycle -- so the exchange inside the loop needs no fence and no flag: one NVLink store latency.
   unsigned long long *peer_ll[P2P_MAXPEER];    // that peer's slots

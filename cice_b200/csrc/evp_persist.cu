@@ -177,7 +177,7 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
     const int e = edge_index(d, 0, i, j);
     for (int q = px.push_start[e]; q < px.push_start[e + 1]; ++q) {
       const int pr = px.push_peer[q] & 0xff;
-      unsigned long long *sl = px.peer_ll[pr] + ((size_t)nxt * px.peer_ring[pr] + px.push_ll[q]) * 4;
+      unsigned long long *sl = px.peer_ll[pr] + ((size_t)((ksub + 1) % P2P_LL_SLOTS) * px.peer_ring[pr] + px.push_ll[q]) * 4;
       const unsigned long long ub = (unsigned long long)__double_as_longlong(u), vb = (unsigned long long)__double_as_longlong(v);
       st_relaxed_sys(sl + 0, (ub & 0xffffffffULL) | tag);
       st_relaxed_sys(sl + 1, (ub >> 32) | tag);
@@ -300,7 +300,7 @@ persist_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
           const int r = ring_index(d.nx, d.ny, gi, gj);
           if (px.ll_fed[r]) {
             // fed by a neighbour GPU: spin on the slot of parity `cur` until all four words carry this subcycle's tag
-            const unsigned long long *sl = px.my_ll + ((size_t)cur * px.my_ring + r) * 4;
+            const unsigned long long *sl = px.my_ll + ((size_t)(ksub % P2P_LL_SLOTS) * px.my_ring + r) * 4;
             const unsigned long long want = (ebase + (unsigned long long)ksub) & 0xffffffffULL;
             unsigned long long w0, w1, w2, w3;
             const unsigned long long t0 = gtime();
