@@ -1356,6 +1356,7 @@ int evp_b200_step_resident(const evp_b200_params_t *p, const evp_b200_prep_t *pr
     std::swap(g.dom.v[0], g.dom.v[1]);
     for (int q = 0; q < 12; ++q) std::swap(g.dom.sig[0][q], g.dom.sig[1][q]);
     g.cur = 0;
+    if (g.p2p.enabled) g.p2p.set_parity(g.p2p.swapped ^ 1);   // the neighbours' copies are addressed by the same parity
     destroy_graph();
   }
   if (init) {

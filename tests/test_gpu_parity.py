@@ -190,7 +190,7 @@ def test_tx1_tripole_full(oracle_mod, evp_lib):
     ["gx3", "25", "29", "40", "fused"],
     ["gx3", "25", "29", "41", "persistent"],
     ["gx1", "80", "96", "30", "auto"],
-    ["gx3", "25", "29", "12", "step"],
+    ["gx3", "25", "29", "13", "step"],
     ["gx3", "50", "58", "15", "split"],
     ["tiny", "12", "10", "16", "fused", "tripole"],
     ["gx3", "10", "10", "20", "fused", "-", "elim"],
