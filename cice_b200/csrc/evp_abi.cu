@@ -268,6 +268,14 @@ static int plan_persist() {
   PersistPlan pp{};
   PersistTables tb;
   if (!persist_plan(g.dom.nx, g.dom.ny, g.num_sms, PERSIST_THREADS, 232448, pp, tb, g.persist_why)) return 0;
+  {
+    int per_sm = 0;
+    CK(exact::persist_ctas_per_sm(pp, halo_in_kernel, &per_sm));
+    if (per_sm < 1 || pp.ntx * pp.nty > per_sm * g.num_sms) {
+      g.persist_why = "the driver cannot keep every tile's CTA resident at once (cooperative launch)";
+      return 0;
+    }
+  }
   unsigned *dt = nullptr, *du = nullptr;
   if (upload_vec(dt, tb.tslot) || upload_vec(du, tb.uslot)) return 1;
   g.d_ptab[0] = dt; g.d_ptab[1] = du;

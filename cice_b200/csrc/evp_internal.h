@@ -167,6 +167,7 @@ struct PrepArgs {
   int fold_max_entries(); \
   cudaError_t set_wait_timeout(unsigned long long ns); \
   cudaError_t set_wait_timeout_persist(unsigned long long ns); \
+  cudaError_t persist_ctas_per_sm(const PersistPlan &pp, bool p2p, int *n); \
   cudaError_t set_metric(const double *HTN, const double *HTE, double deltamin); \
   cudaError_t launch_metric_verify(const Dom &d, const double *HTN, const double *HTE, double deltamin, int skip_e, int skip_n, int *mismatches, cudaStream_t s); \
   cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, const P2PParams *px, cudaStream_t s); \

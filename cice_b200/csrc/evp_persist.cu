@@ -436,6 +436,19 @@ static cudaError_t launch_persist_k(const Dom &d, const KParams &p, const Persis
   return pp.dbg ? launch_persist_t<KT, KU, true, false>(d, p, pp, nop2p, s) : launch_persist_t<KT, KU, false, false>(d, p, pp, nop2p, s);
 }
 
+// how many CTAs of the instantiation the plan selects fit one SM (0: it cannot be launched at all): a cooperative launch needs every
+// tile co-resident, and the planner's own shared-memory arithmetic is checked against the driver's here
+cudaError_t persist_ctas_per_sm(const PersistPlan &pp, bool p2p, int *n) {
+  *n = 0;
+  const void *kern = nullptr;
+  if (pp.kT == 10 && pp.kU == 11) kern = p2p ? (const void *)persist_kernel<PERSIST_THREADS, 10, 11, false, true> : (const void *)persist_kernel<PERSIST_THREADS, 10, 11, false, false>;
+  else if (pp.kT == 6 && pp.kU == 3) kern = p2p ? (const void *)persist_kernel<PERSIST_THREADS, 6, 3, false, true> : (const void *)persist_kernel<PERSIST_THREADS, 6, 3, false, false>;
+  else return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, kern, PERSIST_THREADS, pp.smem_bytes);
+}
+
 cudaError_t set_wait_timeout_persist(unsigned long long ns) { return cudaMemcpyToSymbol(g_wait_timeout_ns, &ns, sizeof ns); }
 
 // px: null on a single rank, else the in-kernel NVLink halo parameters (evp_halo.cu)
