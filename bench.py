@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload gx1|gx3|tx1|p1deg] [--layout weak|strong] [--sub NXxNY]
-                    [--kernel auto|split|fused|stream|resident|persistent] [--mode exact|fast] [--grid B|C]
+                    [--kernel auto|split|fused|stream|resident|persistent|tstream] [--mode exact|fast] [--grid B|C]
 
 A "step" is one dynamics step of the hot path: the whole `do ksub = 1,ndte` loop of
 ice_dyn_evp.F90:859-913 over one synthetic box2001 state.
@@ -352,6 +352,8 @@ def run_ours(args):
     total_ms = float(sum(step_ms))
     launches = dyn_evp.last_launches() * args.steps
     kernel_ms = float(np.mean(loop_ms))  # events inside the library, around the launches only
+    desc = dyn_evp.describe()            # (names the tile-streaming plan once its tensor maps exist)
+    tstream = "; tstream:" in desc
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------
     # (a) every field crosses both ways every step (evp_b200_run_bgrid, the plain drop-in);
@@ -473,7 +475,9 @@ def run_ours(args):
                 "scaling": layout_of(args) if world > 1 else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_string(args, world, ndte),
-                           "kernel": args.kernel + (" -> persistent (one cooperative launch per step)" if persistent and args.kernel == "auto" else ""), "mode": args.mode,
+                           "kernel": args.kernel + (" -> persistent (one cooperative launch per step)" if persistent and args.kernel == "auto" else
+                                                    " -> tstream (TMA tile-streaming kernel, one launch per subcycle)" if tstream and args.kernel == "auto" else ""),
+                           "mode": args.mode,
                            "l2": "flushed between timed steps (256 MiB memset); all ranks barrier before every timed step",
                            "layout": desc, "derived_geometry_mismatches": bad},
                 "parity": parity,
@@ -609,7 +613,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "split", "fused", "stream", "resident", "persistent"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "split", "fused", "stream", "resident", "persistent", "tstream"])
     ap.add_argument("--mode", default="exact", choices=["fast", "exact"])
     ap.add_argument("--workload", default="gx1")
     ap.add_argument("--layout", default=None, choices=["weak", "strong"],

@@ -13,8 +13,8 @@ BNDY_OPEN, BNDY_CLOSED, BNDY_CYCLIC, BNDY_TRIPOLE = 0, 1, 2, 3
 BNDY_NAMES = {"open": BNDY_OPEN, "closed": BNDY_CLOSED, "cyclic": BNDY_CYCLIC, "tripole": BNDY_TRIPOLE}
 
 MODE_EXACT, MODE_FAST = 0, 1
-KERNEL_AUTO, KERNEL_SPLIT, KERNEL_FUSED, KERNEL_PERSISTENT, KERNEL_FUSED_STREAM, KERNEL_FUSED_RESIDENT = 0, 1, 2, 3, 4, 5
-KERNEL_NAMES = {"auto": 0, "split": 1, "fused": 2, "persistent": 3, "stream": 4, "resident": 5}
+KERNEL_AUTO, KERNEL_SPLIT, KERNEL_FUSED, KERNEL_PERSISTENT, KERNEL_FUSED_STREAM, KERNEL_FUSED_RESIDENT, KERNEL_TSTREAM = 0, 1, 2, 3, 4, 5, 6
+KERNEL_NAMES = {"auto": 0, "split": 1, "fused": 2, "persistent": 3, "stream": 4, "resident": 5, "tstream": 6}
 
 UNIQUE_ID_BYTES = 128
 KEEP_STRESS, FETCH_STRESS = 1, 2  # evp_b200_run_bgrid_resident flags

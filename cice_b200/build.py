@@ -26,6 +26,8 @@ UNITS = [
     ("evp_kernels_fast.o", "evp_kernels.cu", ["-DEVP_NS=fast"]),
     ("evp_persist_exact.o", "evp_persist.cu", ["-DEVP_NS=exact", "-fmad=false"]),
     ("evp_persist_fast.o", "evp_persist.cu", ["-DEVP_NS=fast"]),
+    ("evp_tstream_exact.o", "evp_tstream.cu", ["-DEVP_NS=exact", "-fmad=false"]),
+    ("evp_tstream_fast.o", "evp_tstream.cu", ["-DEVP_NS=fast"]),
     ("evp_cgrid_exact.o", "evp_cgrid.cu", ["-DEVP_NS=exact", "-fmad=false"]),
     ("evp_cgrid_fast.o", "evp_cgrid.cu", ["-DEVP_NS=fast"]),
     ("evp_halo.o", "evp_halo.cu", []),

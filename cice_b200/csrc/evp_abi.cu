@@ -186,6 +186,15 @@ struct Ctx {
   bool streaming = false;    // the sub-domain's arrays exceed L2: HBM-streaming form of the fused kernel
   bool derived_ok = false;   // evp_b200_set_metric: HTN/HTE reproduce the seven derived geometry arrays bit for bit
   int metric_mismatches = -1;
+  // KERNEL_TSTREAM (evp_tstream.cu): the TMA tile-streaming form for sub-domains that stream from HBM
+  double *d_HTN = nullptr, *d_HTE = nullptr;   // metric arrays on the dom layout (owned by cbuf)
+  double deltamin = 0.0;
+  std::vector<unsigned char> ts_hmaps;         // TS_NMAPS tensor maps (host copy: they travel as a kernel parameter)
+  int *d_tserr = nullptr;
+  TsPlan tsplan{};
+  int ts_rows = 12;                            // T rows per block: 12 (one CTA per SM) or 6 (two); EVP_B200_TSTREAM_ROWS
+  const void *ts_key[3] = {nullptr, nullptr, nullptr};   // what the maps were encoded for: u[0], sig[0][0], rows
+  std::string ts_why;
 };
 static Ctx g;
 static CommState g_comm;
@@ -232,6 +241,7 @@ static int free_all() {
   F(g.dmaskT); F(g.dmaskU);
   for (auto &p : g.stage) F(p);
   F(g.stage_mask); F(g.stage_mask2); F(g.d_ever_off); F(g.d_gsrc); F(g.d_progress); F(g.d_ptab[0]); F(g.d_ptab[1]); F(g.d_perr); F(g.d_pdbg);
+  F(g.d_tserr);
   for (auto &p : g.prep_static) F(p);
   for (auto &p : g.prepT) F(p);
   F(g.prep_umask);
@@ -588,11 +598,48 @@ static int fused_form(const evp_b200_params_t *p) {
 
 // AUTO: the persistent kernel wherever a sub-domain's carried state fits on chip (one tile per SM; measured on B200 at gx1
 // 1.80 vs 2.20 ms per step, gx3 0.52 vs 0.63), else the fused kernel in the form fused_form() picks
+// KERNEL_TSTREAM needs the metric arrays (derived geometry) and is the single-rank / staged-exchange form: between GPUs with the
+// in-kernel NVLink halo the fused kernel's P2P instantiation stays in charge
+static bool tstream_available() { return g.derived_ok && g.d_HTN && g.d_HTE && !g.p2p.enabled; }
 static int choose_kernel(const evp_b200_params_t *p) {
   int kern = p->kernel;
-  if (kern == EVP_B200_KERNEL_AUTO) kern = g.persist_ok ? EVP_B200_KERNEL_PERSISTENT : EVP_B200_KERNEL_FUSED;
+  if (kern == EVP_B200_KERNEL_AUTO) {
+    kern = g.persist_ok ? EVP_B200_KERNEL_PERSISTENT : EVP_B200_KERNEL_FUSED;
+    if (kern == EVP_B200_KERNEL_FUSED && g.streaming && tstream_available()) kern = EVP_B200_KERNEL_TSTREAM;
+  }
   if (kern == EVP_B200_KERNEL_FUSED_STREAM || kern == EVP_B200_KERNEL_FUSED_RESIDENT) kern = EVP_B200_KERNEL_FUSED;
   return kern;
+}
+
+// tensor maps and cut of KERNEL_TSTREAM for the arrays as they are bound right now (the ping-pong copies swap when a loop ends on
+// copy 1); called outside graph capture
+static int tstream_prepare() {
+  if (!tstream_available())
+    return fail("evp_b200_subcycle: the TMA tile-streaming kernel needs evp_b200_set_metric to have accepted the metric arrays and no in-kernel NVLink halo (%s)",
+                g.p2p.enabled ? "neighbour ranks use it" : (g.derived_ok ? "metric arrays missing" : "derived geometry unavailable"));
+  if (const char *e = getenv("EVP_B200_TSTREAM_ROWS")) g.ts_rows = atoi(e);
+  const void *key[3] = {g.dom.u[0], g.dom.sig[0][0], (const void *)(intptr_t)g.ts_rows};
+  if (!g.ts_hmaps.empty() && memcmp(key, g.ts_key, sizeof key) == 0) return 0;
+  g.ts_hmaps.resize(exact::tstream_map_bytes() + 64);
+  void *hmaps = (void *)(((uintptr_t)g.ts_hmaps.data() + 63) & ~(uintptr_t)63);
+  TsPlan ts{};
+  char why[200] = "";
+  if (exact::tstream_plan(g.dom, g.ndom / (size_t)g.dom.ld, g.d_HTN, g.d_HTE, g.num_sms, g.ts_rows, hmaps, &ts, why, sizeof why)) {
+    g.ts_hmaps.clear();
+    return fail("evp_b200_subcycle: TMA tile-streaming kernel unavailable: %s", why);
+  }
+  if (!g.d_tserr) { CK(cudaMalloc(&g.d_tserr, sizeof(int))); CK(cudaMemset(g.d_tserr, 0, sizeof(int))); }
+  ts.maps = hmaps; ts.err = g.d_tserr; ts.deltamin = g.deltamin;
+  g.tsplan = ts;
+  memcpy(g.ts_key, key, sizeof key);
+  if (g.desc.find("; tstream:") == std::string::npos) {
+    char b[200];
+    snprintf(b, sizeof b, "; tstream: %d CTAs x %d threads, %d strips x %d segments of %d blocks of %d rows", ts.ctas, 32 * ts.rows, ts.nstrips, ts.nseg,
+             ts.nb, ts.rows);
+    g.desc += b;
+  }
+  destroy_graph();
+  return 0;
 }
 
 // enqueue the whole `do ksub = 1,ndte` loop (ice_dyn_evp.F90:859-913) on g.stream, starting from cur=0
@@ -661,12 +708,17 @@ static int enqueue_loop(const evp_b200_params_t *p, int *cur_end, int64_t *launc
                : fast::launch_fused(g.dom, k, cur, g.stream, form, true, last | pdl_trig));
       cur ^= 1;
       nl += 1;
+    } else if (kern == EVP_B200_KERNEL_TSTREAM) {
+      CK(exact ? exact::launch_tstream(g.dom, k, g.tsplan, cur, last, true, g.stream)
+               : fast::launch_tstream(g.dom, k, g.tsplan, cur, last, true, g.stream));
+      cur ^= 1;
+      nl += 1;
     } else {
       return fail("evp_b200_subcycle: kernel strategy %d not available", kern);
     }
     // the part of dyn_haloUpdate(uvel,vvel) that is not an on-rank wrap: neighbour ranks, tripole fold
     int hl = 0;
-    g.halo.fold_pdl = (kern == EVP_B200_KERNEL_FUSED);
+    g.halo.fold_pdl = (kern == EVP_B200_KERNEL_FUSED || kern == EVP_B200_KERNEL_TSTREAM);
     if (g.halo.exchange(g_comm, g.dom.u[cur], g.dom.v[cur], g.stream, &hl, g_err, sizeof g_err)) return 1;
     nl += hl;
   }
@@ -701,6 +753,7 @@ static int do_subcycle(const evp_b200_params_t *p) {
   CK(cudaMemcpyAsync(g.duinit, g.dom.u[0], bdom, cudaMemcpyDeviceToDevice, g.stream));
   CK(cudaMemcpyAsync(g.dvinit, g.dom.v[0], bdom, cudaMemcpyDeviceToDevice, g.stream));
 
+  if (choose_kernel(p) == EVP_B200_KERNEL_TSTREAM && tstream_prepare()) return 1;
   const bool use_graph = g.halo.graph_safe();
   int cur_end = 0;
   int64_t nl = 0;
@@ -798,6 +851,14 @@ static int do_subcycle(const evp_b200_params_t *p) {
     if (e) {
       CK(cudaMemset(g.d_perr, 0, sizeof(int)));
       return fail("evp_b200_subcycle: persistent kernel: a tile waited for a neighbour tile longer than 2 s (CTAs not co-resident?)");
+    }
+  }
+  if (choose_kernel(p) == EVP_B200_KERNEL_TSTREAM && g.d_tserr) {
+    int e = 0;
+    CK(cudaMemcpy(&e, g.d_tserr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) {
+      CK(cudaMemset(g.d_tserr, 0, sizeof(int)));
+      return fail("evp_b200_subcycle: TMA tile-streaming kernel: a box load did not complete within 2 s");
     }
   }
   if (g.p2p.enabled) {
@@ -914,7 +975,11 @@ static int do_set_metric(const double *HTN, const double *HTE, double deltaminEV
   if (g.derived_ok) {
     CK(exact::set_metric(dm[0], dm[1], deltaminEVP));
     CK(fast::set_metric(dm[0], dm[1], deltaminEVP));
+    g.d_HTN = dm[0]; g.d_HTE = dm[1]; g.deltamin = deltaminEVP;
+    g.ts_key[0] = nullptr;   // tensor maps of an earlier metric are stale
     destroy_graph();  // a cached graph may hold the array-reading form
+  } else {
+    g.d_HTN = g.d_HTE = nullptr;
   }
   if (mismatches) *mismatches = bad;
   char b[160];

@@ -141,6 +141,36 @@ struct PersistPlan {
   unsigned smem_bytes;
 };
 
+// KERNEL_TSTREAM (evp_tstream.cu): sub-domains that stream from HBM, advanced by persistent CTAs that walk column strips of the
+// sub-domain; every operand of a block of cells arrives in shared memory as a TMA box load one block ahead of the arithmetic.
+#define TS_W 32              // columns of an fp64 box: 31 T cells of a strip row and the west neighbour of the first
+#define TS_STRIDE 30         // U points a strip advances per row = distance between strips (even: box loads start on 16-byte boundaries)
+#define TS_MW 48             // columns of a mask box (bytes): it starts at the 16-column boundary at or below the fp64 box
+#define TS_NMAPS 47          // tensor maps: u[2] v[2] sig[2][12] strength dxT dyT HTN HTE uop[12] maskT maskU
+#define TS_MAP_U 0
+#define TS_MAP_V 2
+#define TS_MAP_SIG 4
+#define TS_MAP_STRENGTH 28
+#define TS_MAP_DXT 29
+#define TS_MAP_DYT 30
+#define TS_MAP_HTN 31
+#define TS_MAP_HTE 32
+#define TS_MAP_UOP 33
+#define TS_MAP_MASKT 45
+#define TS_MAP_MASKU 46
+struct TsPlan {
+  const void *maps;    // HOST copy of the TS_NMAPS tensor maps (evp_tma.cuh: TsMaps), boxes sized for `rows`; the launcher passes them
+                       // to the kernel by value as a __grid_constant__ parameter (the TMA unit reads them from the constant bank)
+  int rows;            // T rows per block (threads per CTA = 32 * rows)
+  int nstrips;         // strips of TS_W - 1 T columns, stride TS_STRIDE
+  int nseg;            // segments of a strip: rows * nb T rows each, stride rows * nb - 1
+  int nb;              // blocks per (full) segment
+  int nitems;          // nstrips * nseg work items, dealt round robin to the CTAs
+  int ctas;            // grid size
+  int *err;            // set when a wait for a box load times out (never, unless the byte count is wrong)
+  double deltamin;     // deltaminEVP (derived geometry)
+};
+
 // arguments of prep_kernel (evp_kernels.cu): the step preparation on the device
 struct PrepArgs {
   const double *hm, *tarea, *uarea, *fcor;      // static: T land mask as 0/1 real, T-cell area, U-cell area, Coriolis parameter at U
@@ -171,6 +201,9 @@ struct PrepArgs {
   cudaError_t set_metric(const double *HTN, const double *HTE, double deltamin); \
   cudaError_t launch_metric_verify(const Dom &d, const double *HTN, const double *HTE, double deltamin, int skip_e, int skip_n, int *mismatches, cudaStream_t s); \
   cudaError_t launch_persist(const Dom &d, const KParams &p, const PersistPlan &pp, const P2PParams *px, cudaStream_t s); \
+  cudaError_t launch_tstream(const Dom &d, const KParams &p, const TsPlan &ts, int cur, int last, bool pdl, cudaStream_t s); \
+  int tstream_plan(const Dom &d, size_t dom_rows, const double *HTN, const double *HTE, int num_sms, int rows, void *host_maps, TsPlan *ts, char *why, size_t nwhy); \
+  size_t tstream_map_bytes(); \
   cudaError_t launch_cgrid_subcycle(const CDom &d, const KParams &p, cudaStream_t s, int *launches);  \
   cudaError_t launch_cgrid_static(const CDom &d, double *rhalf_dyE, double *r_dxE, double *rhalf_dxN, double *r_dyN, double *uareaavgr, cudaStream_t s); \
   cudaError_t launch_cgrid_subcycle_fused(const CDom &d, const KParams &p, int cur, cudaStream_t s, int *launches);  \

@@ -267,17 +267,7 @@ cudaError_t launch_stepu(const Dom &d, const KParams &p, int cur, cudaStream_t s
 // keeps reading the arrays.
 __constant__ const double *c_HTN, *c_HTE;
 __constant__ double c_deltamin;
-__device__ __forceinline__ void derive_geometry(double hn, double hs, double he, double hw, double dxT, double dyT, double deltamin,
-                                                double &dxhy, double &dyhx, double &cxp, double &cyp, double &cxm, double &cym,
-                                                double &dmin) {
-  dxhy = 0.5 * (he - hw);            // p5*(HTE(i,j) - HTE(i-1,j))
-  dyhx = 0.5 * (hn - hs);            // p5*(HTN(i,j) - HTN(i,j-1))
-  cyp = (1.5 * he - 0.5 * hw);       // c1p5*HTE(i,j) - p5*HTE(i-1,j)
-  cxp = (1.5 * hn - 0.5 * hs);
-  cym = -(1.5 * hw - 0.5 * he);
-  cxm = -(1.5 * hs - 0.5 * hn);
-  dmin = deltamin * (dxT * dyT);     // deltaminEVP*tarea, tarea = dxT*dyT (ice_grid.F90:681-715)
-}
+// (derive_geometry itself: evp_math.cuh)
 // counts the T cells (1..nx+1-skip_e, 1..ny+1-skip_n) on which the derived values differ from the arrays in any bit
 __global__ void __launch_bounds__(256) metric_verify_kernel(const __grid_constant__ Dom d, const double *__restrict__ HTN,
                                                             const double *__restrict__ HTE, double deltamin, int skip_e, int skip_n,

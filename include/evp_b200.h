@@ -68,7 +68,11 @@ enum {
                                           sub-domain size (L2-resident or HBM-streaming) */
   EVP_B200_KERNEL_PERSISTENT     = 3,  /* all ndte subcycles in one cooperative launch, state on chip */
   EVP_B200_KERNEL_FUSED_STREAM   = 4,  /* FUSED, HBM-streaming form forced (operands requested early, cp.async staging) */
-  EVP_B200_KERNEL_FUSED_RESIDENT = 5   /* FUSED, L2-resident form forced (interleaved division / square-root chains) */
+  EVP_B200_KERNEL_FUSED_RESIDENT = 5,  /* FUSED, L2-resident form forced (interleaved division / square-root chains) */
+  EVP_B200_KERNEL_TSTREAM        = 6   /* one launch per subcycle by persistent CTAs that walk column strips of the sub-domain; every
+                                          operand staged global -> shared by TMA box loads (cp.async.bulk.tensor) one block ahead of
+                                          the arithmetic.  AUTO's choice for sub-domains that stream from HBM once
+                                          evp_b200_set_metric has accepted the metric arrays (single rank / staged exchange) */
 };
 
 /*

@@ -14,9 +14,12 @@ reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 c = synth.make_case(wl, ndte=ndte)
 p = dict(c.params, mode=abi.MODE_EXACT if mode == "exact" else abi.MODE_FAST, kernel=abi.KERNEL_NAMES[kernel])
 dyn_evp.dyn_evp_b200_init(c.grid)
+# the metric arrays (what the Fortran shim hands over in its init): derived geometry for the streaming forms, required by tstream
+bad = dyn_evp.set_metric(synth.scatter(c.X["HTN"], c.blocks), synth.scatter(c.X["HTE"], c.blocks), c.params["deltaminEVP"])
 f = c.copy_fields()
 dyn_evp.upload(f)
 for _ in range(reps):
     dyn_evp.subcycle(p)
     print("loop ms", dyn_evp.last_loop_ms(), "launches", dyn_evp.last_launches())
+print("metric mismatches", bad, "|", dyn_evp.describe()[-160:])
 dyn_evp.dyn_evp_b200_finalize()

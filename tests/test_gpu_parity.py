@@ -372,6 +372,72 @@ def test_derived_geometry(oracle_mod, evp_lib):
             assert_bitwise(f, ref)
 
 
+def _run_tstream(evp_lib, c, kernel=abi.KERNEL_TSTREAM, split_loops=None):
+    """init, hand over the metric arrays, run the loop with the TMA tile-streaming kernel (or AUTO)"""
+    f = c.copy_fields()
+    HTN, HTE = synth.scatter(c.X["HTN"], c.blocks), synth.scatter(c.X["HTE"], c.blocks)
+    evp_lib.dyn_evp_b200_init(c.grid)
+    try:
+        assert evp_lib.set_metric(HTN, HTE, 1e-11) == 0
+        p = dict(c.params, mode=abi.MODE_EXACT, kernel=kernel)
+        if split_loops:
+            evp_lib.upload(f)
+            for n in split_loops:
+                evp_lib.subcycle(dict(p, ndte=n))
+            evp_lib.download(f)
+        else:
+            evp_lib.dyn_evp_b200_run(p, f)
+        assert "; tstream:" in evp_lib.describe()    # the kernel that ran (the plan is described when its tensor maps are built)
+    finally:
+        evp_lib.dyn_evp_b200_finalize()
+    return f
+
+
+@pytest.mark.parametrize("rows", ["12", "6"], ids=["12rows-1cta", "6rows-2ctas"])
+def test_tstream_bitwise(oracle_mod, evp_lib, monkeypatch, rows):
+    """KERNEL_TSTREAM (evp_tstream.cu): persistent CTAs walking column strips, every operand through TMA box loads
+    (cp.async.bulk.tensor.2d + mbarrier), against the oracle bit for bit: block decompositions, revised EVP, closed boundaries with
+    islands, doubly cyclic, gx3, a grid with several segments per strip and several items per CTA, the division / square-root
+    fallbacks, and loops that end on either ping-pong copy (the tensor maps follow the swap).  Host-emulated in
+    tests/test_emu_tstream.py; this is the hardware's TMA unit and mbarrier."""
+    monkeypatch.setenv("EVP_B200_TSTREAM_ROWS", rows)
+    cases = [synth.make_case("tiny", seed=11, block_size=(12, 10), ndte=9),
+             synth.make_case("tiny", seed=12, revised_evp=True),
+             synth.make_case("tiny", seed=13, ew="closed", ns="closed", kmt="boxislands"),
+             synth.make_case("tiny", nx=62, ny=30, seed=136, ns="cyclic", ndte=5),
+             synth.make_case("gx3", seed=14, ndte=25),
+             synth.make_case("tiny", nx=700, ny=520, seed=19, kmt="continents", ndte=4)]
+    for c in cases:
+        assert_bitwise(_run_tstream(evp_lib, c), run_oracle(oracle_mod, c))
+    c = synth.make_case("tiny", seed=21, ndte=6)
+    for n in ("uvel", "vvel", "uocnU", "vocnU", "forcexU", "forceyU", "waterxU", "wateryU"):
+        c.fields[n][...] = 0.0
+    c.fields["strength"][...] *= 1e-300
+    assert_bitwise(_run_tstream(evp_lib, c), run_oracle(oracle_mod, c))
+    # 1 + 2 + 5 subcycles in three loops on resident state == 8 in one: the second loop starts from copy 1
+    c = synth.make_case("gx3", seed=23, ndte=8)
+    assert_bitwise(_run_tstream(evp_lib, c, split_loops=(1, 2, 5)), run_oracle(oracle_mod, c))
+
+
+def test_tstream_needs_the_metric_arrays(evp_lib):
+    """without evp_b200_set_metric (or on a tripole grid, whose ghost row fails the device-side check) the kernel refuses loudly"""
+    c = synth.make_case("tiny", seed=11, ndte=3)
+    with pytest.raises(evp_lib.EvpB200Error, match="evp_b200_set_metric"):
+        run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_TSTREAM)
+
+
+def test_tstream_large_grid_is_autos_choice(evp_lib):
+    """0.1-degree-sized sub-domain (900x1200, the per-GPU share of configs[4]) streams from HBM: once the metric arrays are in, AUTO
+    runs the TMA tile-streaming kernel, and it agrees bit for bit with the launch-per-subcycle kernel and the two-sweep kernels."""
+    c = synth.make_case("p1deg", nx=900, ny=1200, ndte=6, seed=77)
+    ref = run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_SPLIT)
+    assert_bitwise(run_gpu(evp_lib, c, mode=abi.MODE_EXACT, kernel=abi.KERNEL_FUSED), ref)
+    for kernel in (abi.KERNEL_TSTREAM, abi.KERNEL_AUTO):
+        got = _run_tstream(evp_lib, c, kernel=kernel)
+        assert_bitwise(got, ref)
+        assert np.array_equal(got["uvel"][0][:, 0], got["uvel"][0][:, -2])
+
+
 @pytest.mark.parametrize("p2p", ["1", "0"], ids=["fold-kernel", "pack-apply"])
 def test_tripole_fold_one_rank_both_forms(oracle_mod, evp_lib, monkeypatch, p2p):
     """on one rank every source of the tripole fold is local: the halo update after each subcycle kernel is ONE kernel
