@@ -14,7 +14,7 @@ SYMBOLS = (
     "evp_b200_last_error", "evp_b200_run_bgrid", "evp_b200_upload", "evp_b200_subcycle", "evp_b200_download",
     "evp_b200_last_loop_ms", "evp_b200_last_launches", "evp_b200_stream", "evp_b200_describe",
     "evp_b200_halo_plan", "evp_b200_dom_pitch", "evp_b200_dom_cells", "evp_b200_p2p_plan", "evp_b200_init_cgrid", "evp_b200_run_cgrid", "evp_b200_deformations", "evp_b200_dyn_finish", "evp_b200_set_metric", "evp_b200_pin_host", "evp_b200_unpin_host",
-    "evp_b200_run_bgrid_resident", "evp_b200_download_stress", "evp_b200_allow_partial_domain", "evp_b200_run_cdgrid",
+    "evp_b200_run_bgrid_resident", "evp_b200_download_stress", "evp_b200_stress_symmetrise", "evp_b200_allow_partial_domain", "evp_b200_run_cdgrid",
     "evp_b200_prep_init", "evp_b200_step_resident",
 )
 

@@ -134,6 +134,8 @@ struct Ctx {
   int *d_uv_lin = nullptr, *d_uv_dom = nullptr, n_uv = 0;
   int *d_sig_lin = nullptr, *d_sig_dom = nullptr, n_sig = 0;
   int *d_int_lin = nullptr, *d_int_dom = nullptr, n_int = 0;
+  int *d_symw_lin = nullptr, *d_symw_dom = nullptr, n_symw = 0;  // tripole: west-ghost corner of the north ghost row of every top block
+  bool sym_applied = false;                                       // the device stresses carry the symmetrisation across the fold
 
   // loop state
   int cur = 0;
@@ -245,7 +247,7 @@ static int free_all() {
   for (auto &p : g.prep_static) F(p);
   for (auto &p : g.prepT) F(p);
   F(g.prep_umask);
-  F(g.d_uv_lin); F(g.d_uv_dom); F(g.d_sig_lin); F(g.d_sig_dom); F(g.d_int_lin); F(g.d_int_dom);
+  F(g.d_symw_lin); F(g.d_symw_dom); F(g.d_uv_lin); F(g.d_uv_dom); F(g.d_sig_lin); F(g.d_sig_dom); F(g.d_int_lin); F(g.d_int_dom);
   g.halo.release();
   for (auto &e : g.ev_field) if (e) cudaEventDestroy(e);
   if (g.xfer) cudaStreamDestroy(g.xfer);
@@ -362,7 +364,7 @@ static int do_init(const evp_b200_grid_t *gr) {
   if (g.ndom > 0x7fffffffULL) return fail("evp_b200_init: sub-domain exceeds 2^31 cells");
 
   // ---- index maps -------------------------------------------------------------------------------
-  std::vector<int> gsrc(g.ndom, -1), uv_lin, uv_dom, sig_lin, sig_dom, int_lin, int_dom;
+  std::vector<int> gsrc(g.ndom, -1), uv_lin, uv_dom, sig_lin, sig_dom, int_lin, int_dom, symw_lin, symw_dom;
   std::vector<unsigned char> owned(g.ndom, 0);
   for (int b = 0; b < g.nblocks; ++b) {
     const int32_t *ig = gr->i_glob + (size_t)b * nxb, *jg = gr->j_glob + (size_t)b * nyb;
@@ -386,8 +388,14 @@ static int do_init(const evp_b200_grid_t *gr) {
         }
         uv_lin.push_back(lin); uv_dom.push_back(dm);
         if (li >= ilo && lj >= jlo) { sig_lin.push_back(lin); sig_dom.push_back(dm); }
+        // ice_HaloUpdate_stress also writes the west ghost column of the north ghost row (ice_boundary.F90:8141: i = 1 ..)
+        if (gr->ns_boundary_type == EVP_B200_BNDY_TRIPOLE && jg[jhi - 1] == g.nyg && li == ilo - 1 && lj == jhi + 1) {
+          symw_lin.push_back(lin); symw_dom.push_back(dm);
+        }
       }
   }
+  g.n_symw = (int)symw_lin.size();
+  if (g.n_symw && (upload_vec(g.d_symw_lin, symw_lin) || upload_vec(g.d_symw_dom, symw_dom))) return 1;
   g.n_uv = (int)uv_lin.size(); g.n_sig = (int)sig_lin.size(); g.n_int = (int)int_lin.size();
   if (upload_vec(g.d_gsrc, gsrc) || upload_vec(g.d_uv_lin, uv_lin) || upload_vec(g.d_uv_dom, uv_dom) ||
       upload_vec(g.d_sig_lin, sig_lin) || upload_vec(g.d_sig_dom, sig_dom) || upload_vec(g.d_int_lin, int_lin) ||
@@ -561,9 +569,11 @@ static int do_download(evp_b200_fields_t *f, int what = 7) {
       zero_where<<<grid_blocks(g.nblk_elems), 256, 0, g.stream>>>(g.stage[q], g.d_ever_off, (int)g.nblk_elems);
     }
     // the staging copy still holds the host array as uploaded: cells the loop does not own keep their values
-    if (q < 12)
+    if (q < 12) {
       unpack_f64<<<grid_blocks(g.n_sig), 256, 0, g.stream>>>(g.stage[q], d.sig[g.cur][q], g.d_sig_lin, g.d_sig_dom, g.n_sig);
-    else if (q < 16)
+      if (g.sym_applied && g.n_symw)
+        unpack_f64<<<grid_blocks(g.n_symw), 256, 0, g.stream>>>(g.stage[q], d.sig[g.cur][q], g.d_symw_lin, g.d_symw_dom, g.n_symw);
+    } else if (q < 16)
       unpack_f64<<<grid_blocks(g.n_int), 256, 0, g.stream>>>(g.stage[q], g.dfield[q], g.d_int_lin, g.d_int_dom, g.n_int);
     else
       unpack_f64<<<grid_blocks(g.n_uv), 256, 0, g.stream>>>(g.stage[q], q == 16 ? d.u[g.cur] : d.v[g.cur], g.d_uv_lin, g.d_uv_dom, g.n_uv);
@@ -618,7 +628,8 @@ static int tstream_prepare() {
     return fail("evp_b200_subcycle: the TMA tile-streaming kernel needs evp_b200_set_metric to have accepted the metric arrays and no in-kernel NVLink halo (%s)",
                 g.p2p.enabled ? "neighbour ranks use it" : (g.derived_ok ? "metric arrays missing" : "derived geometry unavailable"));
   if (const char *e = getenv("EVP_B200_TSTREAM_ROWS")) g.ts_rows = atoi(e);
-  const void *key[3] = {g.dom.u[0], g.dom.sig[0][0], (const void *)(intptr_t)g.ts_rows};
+  const char *ie = getenv("EVP_B200_TSTREAM_ISSUE");
+  const void *key[3] = {g.dom.u[0], g.dom.sig[0][0], (const void *)(intptr_t)(g.ts_rows * 2 + ((ie && !atoi(ie)) ? 0 : 1))};
   if (!g.ts_hmaps.empty() && memcmp(key, g.ts_key, sizeof key) == 0) return 0;
   g.ts_hmaps.resize(exact::tstream_map_bytes() + 64);
   void *hmaps = (void *)(((uintptr_t)g.ts_hmaps.data() + 63) & ~(uintptr_t)63);
@@ -630,6 +641,8 @@ static int tstream_prepare() {
   }
   if (!g.d_tserr) { CK(cudaMalloc(&g.d_tserr, sizeof(int))); CK(cudaMemset(g.d_tserr, 0, sizeof(int))); }
   ts.maps = hmaps; ts.err = g.d_tserr; ts.deltamin = g.deltamin;
+  ts.issue = 1;
+  if (const char *e = getenv("EVP_B200_TSTREAM_ISSUE")) ts.issue = atoi(e) ? 1 : 0;
   g.tsplan = ts;
   memcpy(g.ts_key, key, sizeof key);
   if (g.desc.find("; tstream:") == std::string::npos) {
@@ -780,6 +793,7 @@ static int do_subcycle(const evp_b200_params_t *p) {
     CK(cudaEventRecord(g.ev1, g.stream));
   }
   g.cur = cur_end;
+  g.sym_applied = false;
   g.last_launches = nl;
   CK(cudaStreamSynchronize(g.stream));
   CK(cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1));
@@ -1367,12 +1381,48 @@ int evp_b200_upload(const evp_b200_fields_t *f) {
 int evp_b200_subcycle(const evp_b200_params_t *p) { return do_subcycle(p); }
 int evp_b200_download(evp_b200_fields_t *f) { return do_download(f, 7); }
 
+// Tripole grids: "force symmetry across the tripole seam" (ice_dyn_evp.F90:1321-1388) on the stresses the device holds.  Each of the
+// twelve ice_HaloUpdate_stress(array1, array2) calls writes the north ghost row of array1 on the blocks of the top row -- every local
+// column, ghost columns included -- from the top PHYSICAL row of array2 at the mirrored global column nx_global - i_glob + 1
+// (ice_boundary.F90:7760-7794, addresses :8117-8157; centre location, scalar: no offsets, no sign).  Pairs 1<->3, 2<->4 of stressp,
+// stressm, stress12.  Reads row ny, writes row ny+1 of the same copy: one thread per (array, ghost cell), no ordering needed.
+__global__ void stress_fold_kernel(const __grid_constant__ Dom d, int cur, int gi0, int nxg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
+  if (i > d.nx + 1) return;
+  int ig = gi0 + i - 1;
+  if (ig < 1) ig += nxg;
+  if (ig > nxg) ig -= nxg;
+  const int ic = (nxg - ig + 1) - gi0 + 1;            // dom column of the mirrored cell (the rank holds the whole top row)
+  const int src = (q / 4) * 4 + ((q % 4) + 2) % 4;
+  d.sig[cur][q][(size_t)(d.ny + 1) * d.ld + i] = d.sig[cur][src][(size_t)d.ny * d.ld + ic];
+}
+static bool symmetrise_here() { return g.ns == EVP_B200_BNDY_TRIPOLE && g.gj0 + g.dom.ny - 1 == g.nyg; }
+static bool symmetrise_possible() { return !symmetrise_here() || (g.gi0 == 1 && g.dom.nx == g.nxg); }
+static int do_stress_symmetrise() {
+  if (!g.inited || !g.uploaded) return fail("evp_b200_stress_symmetrise: no stresses on the device");
+  if (g.ns != EVP_B200_BNDY_TRIPOLE) return 0;
+  if (!symmetrise_possible())
+    return fail("evp_b200_stress_symmetrise: the top row of the tripole grid is spread over several ranks (not in this version)");
+  if (symmetrise_here()) {
+    CK(cudaSetDevice(g.device));
+    dim3 b(128), gr((g.dom.nx + 2 + b.x - 1) / b.x, 12);
+    stress_fold_kernel<<<gr, b, 0, g.stream>>>(g.dom, g.cur, g.gi0, g.nxg);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(g.stream));
+  }
+  g.sym_applied = true;
+  return 0;
+}
+int evp_b200_stress_symmetrise(void) { return do_stress_symmetrise(); }
+
 int evp_b200_run_bgrid_resident(const evp_b200_params_t *p, evp_b200_fields_t *f, int32_t flags) {
-  if ((flags & EVP_B200_KEEP_STRESS) && g.inited && g.ns == EVP_B200_BNDY_TRIPOLE)
-    return fail("evp_b200_run_bgrid_resident: EVP_B200_KEEP_STRESS is not available on tripole grids (the host symmetrises the "
-                "stresses across the fold after the loop, ice_dyn_evp.F90:1322-1389)");
+  const bool sym = (flags & EVP_B200_KEEP_STRESS) && g.inited && g.ns == EVP_B200_BNDY_TRIPOLE;
+  if (sym && (g_comm.nranks > 1 || !symmetrise_possible()))
+    return fail("evp_b200_run_bgrid_resident: EVP_B200_KEEP_STRESS on a tripole grid needs the whole top row on one rank (the "
+                "symmetrisation of the stresses across the fold, ice_dyn_evp.F90:1321-1388, is done on the device only then)");
   if (do_upload(f, (flags & EVP_B200_KEEP_STRESS) != 0)) return 1;
   if (do_subcycle(p)) return 1;
+  if (sym && do_stress_symmetrise()) return 1;
   const bool stress_back = !(flags & EVP_B200_KEEP_STRESS) || (flags & EVP_B200_FETCH_STRESS);
   return do_download(f, stress_back ? 7 : 6);
 }

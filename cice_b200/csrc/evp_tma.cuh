@@ -39,6 +39,13 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const TmaMap *map, int x,
                ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
                : "memory");
 }
+// one lane of a converged warp (elect.sync), and a value the compiler may treat as the same in every lane of the warp
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void tma_prefetch_map(const TmaMap *map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
 // wait for phase number `phase` (0, 1, 2 ... in the order the barrier completes them).  Bounded like every other in-kernel wait
 // of this library: a programming error (byte count that never arrives) becomes an error code, not a hung GPU.
@@ -72,18 +79,33 @@ struct TmaMap {
   long long pitch;          // bytes between rows
   int box0, box1;           // box extent in elements
 };
-struct MBar { std::atomic<unsigned> done; unsigned pad; };
+// arrivals and transaction bytes counted like the hardware does (several threads issue the loads of one phase, one of them arrives):
+// phase p is complete when p+1 arrivals have been made and the bytes announced up to then have landed
+struct MBar {
+  std::atomic<unsigned> arrivals;
+  std::atomic<long long> landed;      // bytes copied so far (all phases)
+  std::atomic<long long> announced;   // bytes announced so far
+  std::atomic<long long> due[4];      // `announced` after arrival number p (ring by p & 3)
+};
+static_assert(sizeof(MBar) <= 64, "two barriers share 128 bytes of the CTA's shared memory");
 
 inline unsigned char *smem_align128(unsigned char *base) { return (unsigned char *)(((uintptr_t)base + 127) & ~(uintptr_t)127); }
-inline void mbar_init(MBar *bar, int) { bar->done.store(0); }
+inline void mbar_init(MBar *bar, int) {
+  bar->arrivals.store(0); bar->landed.store(0); bar->announced.store(0);
+  for (auto &d : bar->due) d.store(0);
+}
 inline void mbar_fence_init() {}
 inline void fence_proxy_async() {}
-inline void mbar_arrive_expect_tx(MBar *bar, unsigned) { bar->done.fetch_add(1, std::memory_order_release); }   // the copies below are synchronous
+inline void mbar_arrive_expect_tx(MBar *bar, unsigned bytes) {
+  const long long a = bar->announced.fetch_add(bytes) + bytes;
+  bar->due[bar->arrivals.load() & 3].store(a);
+  bar->arrivals.fetch_add(1, std::memory_order_release);
+}
 // the hardware's rules that a plain copy would not notice: the box must start on a 16-byte boundary of its row (B200: anything else
 // is an illegal instruction), its rows are a multiple of 16 bytes, the destination is 128-byte aligned.  (The row pitch is a multiple of 16
 // bytes in the product -- Dom::ld is a multiple of 16 cells -- but not in the emulation, where one block of the caller IS the dom.)
 static std::atomic<int> emu_tma_misaligned{0};
-inline void tma_load_2d(void *dst, const TmaMap *m, int x, int y, MBar *) {
+inline void tma_load_2d(void *dst, const TmaMap *m, int x, int y, MBar *bar) {
   if (((long long)x * m->elem) % 16 != 0 || (m->box0 * m->elem) % 16 != 0 || ((uintptr_t)dst & 127) != 0) emu_tma_misaligned.store(1);
   unsigned char *o = (unsigned char *)dst;
   for (int r = 0; r < m->box1; ++r)
@@ -92,10 +114,14 @@ inline void tma_load_2d(void *dst, const TmaMap *m, int x, int y, MBar *) {
       if (gx >= 0 && gx < m->dim0 && gy >= 0 && gy < m->dim1) memcpy(o, (const unsigned char *)m->base + gy * m->pitch + (long long)gx * m->elem, m->elem);
       else memset(o, 0, m->elem);
     }
+  bar->landed.fetch_add((long long)m->box0 * m->box1 * m->elem, std::memory_order_release);
 }
+inline bool elect_one() { return (emu::lin & 31) == 0; }
+inline int warp_uniform(int v) { return v; }
 inline void tma_prefetch_map(const TmaMap *) {}
 inline void mbar_wait(MBar *bar, unsigned phase, int *err) {
-  for (long spins = 0; bar->done.load(std::memory_order_acquire) <= phase; ++spins) {
+  for (long spins = 0;; ++spins) {
+    if (bar->arrivals.load(std::memory_order_acquire) > phase && bar->landed.load(std::memory_order_acquire) >= bar->due[phase & 3].load()) break;
     if (spins > 200000000L) { *err = 1; break; }
     emu::yield();
   }

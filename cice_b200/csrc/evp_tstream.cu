@@ -101,7 +101,7 @@ __device__ __forceinline__ void ts_issue(const TsMaps &tm, int cur, unsigned cha
   mbar_arrive_expect_tx(bar, L::TX_BYTES);
 }
 
-template <int R, int MINB>
+template <int R, int MINB, int UNI>
 __global__ void __launch_bounds__(32 * R, MINB) tstream_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
                                                                const __grid_constant__ TsPlan ts, const __grid_constant__ TsMaps tm,
                                                                int cur, int last) {
@@ -125,13 +125,17 @@ __global__ void __launch_bounds__(32 * R, MINB) tstream_kernel(const __grid_cons
   ci.item = blockIdx.x;
   ts_setup<R>(d, ts, ci);
   pi = ci;
-  if (t == 0) {
-    for (int s = 0; s < 2; ++s)
-      if (pi.item < ts.nitems) {
-        ts_issue<R>(tm, cur, smem + s * L::STAGE, &bars[s], pi.i0, pi.j0 + R * pi.b);
-        ts_next<R>(d, ts, pi, G);
-      }
-  }
+  // who issues the box loads.  UNI = 1: an elected lane of warp 0 inside a branch the compiler knows to be the same for the whole warp,
+  // so that the operands stay in uniform registers (5 instructions per load); UNI = 0: thread 0, which costs a waterfall loop per load
+  // (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~15 instructions) -- kept selectable (EVP_B200_TSTREAM_ISSUE) for A/B runs on one box
+  const bool issuer_warp = UNI ? (warp_uniform(ty) == 0) : (t == 0);
+  // (every thread steps the prefetch iterator, so that the operands of the box loads are uniform values the compiler keeps in uniform
+  // registers; only the instructions themselves are thread 0's)
+  for (int s = 0; s < 2; ++s)
+    if (pi.item < ts.nitems) {
+      if (issuer_warp && (!UNI || elect_one())) ts_issue<R>(tm, cur, smem + s * L::STAGE, &bars[s], pi.i0, pi.j0 + R * pi.b);
+      ts_next<R>(d, ts, pi, G);
+    }
   for (unsigned q = 0; ci.item < ts.nitems; ++q) {
     const int s = q & 1;
     unsigned char *st = smem + s * L::STAGE;
@@ -221,9 +225,11 @@ __global__ void __launch_bounds__(32 * R, MINB) tstream_kernel(const __grid_cons
     __syncthreads();   // the stage and the str terms have been read by everyone
 
     // ---- the stage is free: fetch the block after the next one into it -------------------------------------------------------
-    if (t == 0 && pi.item < ts.nitems) {
-      fence_proxy_async();
-      ts_issue<R>(tm, cur, st, &bars[s], pi.i0, pi.j0 + R * pi.b);
+    if (pi.item < ts.nitems) {
+      if (issuer_warp && (!UNI || elect_one())) {
+        fence_proxy_async();
+        ts_issue<R>(tm, cur, st, &bars[s], pi.i0, pi.j0 + R * pi.b);
+      }
       ts_next<R>(d, ts, pi, G);
     }
     ts_next<R>(d, ts, ci, G);
@@ -261,10 +267,10 @@ static void tstream_cut(int nx, int ny, int num_sms, int rows, TsPlan *ts) {
 
 #ifndef EVP_HOST_EMU
 
-template <int R, int MINB>
+template <int R, int MINB, int UNI>
 static cudaError_t launch_tstream_t(const Dom &d, const KParams &p, const TsPlan &ts, int cur, int last, bool pdl, cudaStream_t s) {
   const int smem = TsL<R>::TOTAL + 128;
-  cudaError_t e = cudaFuncSetAttribute(tstream_kernel<R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(tstream_kernel<R, MINB, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ts.ctas); cfg.blockDim = dim3(32 * R); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -272,13 +278,13 @@ static cudaError_t launch_tstream_t(const Dom &d, const KParams &p, const TsPlan
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, tstream_kernel<R, MINB>, d, p, ts, *(const TsMaps *)ts.maps, cur, last);
+  return cudaLaunchKernelEx(&cfg, tstream_kernel<R, MINB, UNI>, d, p, ts, *(const TsMaps *)ts.maps, cur, last);
 }
 
 cudaError_t launch_tstream(const Dom &d, const KParams &p, const TsPlan &ts, int cur, int last, bool pdl, cudaStream_t s) {
   switch (ts.rows) {
-    case 12: return launch_tstream_t<12, 1>(d, p, ts, cur, last, pdl, s);
-    case 6: return launch_tstream_t<6, 2>(d, p, ts, cur, last, pdl, s);
+    case 12: return ts.issue ? launch_tstream_t<12, 1, 1>(d, p, ts, cur, last, pdl, s) : launch_tstream_t<12, 1, 0>(d, p, ts, cur, last, pdl, s);
+    case 6: return ts.issue ? launch_tstream_t<6, 2, 1>(d, p, ts, cur, last, pdl, s) : launch_tstream_t<6, 2, 0>(d, p, ts, cur, last, pdl, s);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -125,6 +125,11 @@ def bind(entry, params, fields, prep=None, **flags):
     return call
 
 
+def stress_symmetrise():
+    """tripole grids: force the symmetry of the device-resident stresses across the fold (ice_dyn_evp.F90:1321-1388)"""
+    check(load().evp_b200_stress_symmetrise(), "evp_b200_stress_symmetrise")
+
+
 def download_stress(fields):
     """fetch the device-resident stresses into the host arrays (restart / history)."""
     f, keep = _fields(fields)

@@ -177,6 +177,11 @@ module ice_dyn_evp_b200
        import :: c_int, evp_b200_fields_t
        type(evp_b200_fields_t), intent(inout) :: fields
      end function
+     ! tripole grids, stresses resident: the twelve ice_HaloUpdate_stress calls of ice_dyn_evp.F90:1321-1388 on the device
+     ! (evp_b200_run_bgrid_resident calls it itself; for users of the upload / subcycle / download split)
+     integer(c_int) function evp_b200_stress_symmetrise() bind(C, name='evp_b200_stress_symmetrise')
+       import :: c_int
+     end function
      integer(c_int) function evp_b200_finalize() bind(C, name='evp_b200_finalize')
        import :: c_int
      end function

@@ -297,14 +297,21 @@ int evp_b200_download(evp_b200_fields_t *fields);
  * applies that zeroing itself from the iceTmask of the call, and neither reads nor writes the host's stress arrays
  * (24 of the 48 field transfers of a step).  The first call after evp_b200_init uploads them regardless.
  * EVP_B200_FETCH_STRESS additionally copies them back in this call (restart / history steps);
- * evp_b200_download_stress does the same outside a step.  Not for tripole grids, where the host symmetrises the
- * stresses across the fold after the loop (ice_dyn_evp.F90:1322-1389). */
+ * evp_b200_download_stress does the same outside a step.
+ * Tripole grids: after the loop the reference forces the symmetry of the stress tensor across the fold -- twelve
+ * ice_HaloUpdate_stress calls (ice_dyn_evp.F90:1321-1388; ice_boundary.F90:7440-7825) that copy the mirrored top physical row
+ * of stressX_3 into the north ghost row of stressX_1 and so on.  With the stresses on the device the library does that itself
+ * (evp_b200_stress_symmetrise, called by evp_b200_run_bgrid_resident after the loop), when the rank holds the whole top row
+ * of the grid; EVP_B200_KEEP_STRESS is refused on a tripole grid whose top row is spread over several ranks. */
 enum {
   EVP_B200_KEEP_STRESS  = 1,
   EVP_B200_FETCH_STRESS = 2
 };
 int evp_b200_run_bgrid_resident(const evp_b200_params_t *params, evp_b200_fields_t *fields, int32_t flags);
 int evp_b200_download_stress(evp_b200_fields_t *fields);
+/* the symmetrisation alone, on the stresses the device holds (for callers of the upload / subcycle / download split); no-op on
+ * grids without a tripole fold and on ranks below the top row */
+int evp_b200_stress_symmetrise(void);
 
 /* ---- next rows: the step preparation on the device, the whole dynamics state resident ----------
  * Replaces, between the halo updates of the T-point inputs and the subcycle loop of evp() (ice_dyn_evp.F90:428-560):

@@ -441,6 +441,58 @@ int orc_halo_update(const evp_b200_grid_t *g, double **flds, int nfld, int field
 }
 
 /* ---------------------------------------------------------------------------------------
+ * Tripole grids: "Force symmetry across the tripole seam" after the loop, evp.F90:1321-1388 --
+ * twelve calls ice_HaloUpdate_stress(array1, array2, halo_info, field_loc_center, field_type_scalar)
+ * with (array1, array2) = (stressp_1, stressp_3), (stressp_3, stressp_1), (stressp_2, stressp_4),
+ * (stressp_4, stressp_2) and the same for stressm and stress12.
+ *
+ * ice_HaloUpdate_stress (boundary.F90:7440-7825) moves nothing but the tripole rows: the top physical
+ * row(s) of ARRAY2 go into the global tripole buffer (local copies :7641-7660, messages :7674-7688; rows
+ * ny_global-1 and ny_global are buffer rows 1 and 2, address build :8117-8133), and the copy-out
+ * (:7760-7794) writes ARRAY1 on every block whose top interior row is ny_global, for every local column
+ * i = 1 .. ihi+nghost (ghost columns included, :8136-8157):
+ *     array1(i, jhi+1) = isign * buf(nx_global - i_glob(i) + 1, 2)        isign = +1 (scalar)
+ * -- centre location on a u-fold: ioffset = joffset = 0 (:7729-7732), so buffer row 3 - 1 = "replace the top
+ * physical row" falls out of range and is skipped (:7779-7785).  A source cell of an eliminated land block
+ * leaves the buffer at its fill value 0 (:7538).  All twelve calls read physical rows and write ghost
+ * rows only: their order does not matter.
+ * sig: the 12 arrays in the order of evp_b200_fields_t (stressp_1..4, stressm_1..4, stress12_1..4).
+ * ------------------------------------------------------------------------------------- */
+int orc_stress_symmetrise(const evp_b200_grid_t *g, double **sig) {
+  if (g->ns_boundary_type != EVP_B200_BNDY_TRIPOLE) return 0;
+  owner_map_t m;
+  if (build_owner_map(g, &m)) return 1;
+  const int nxg = g->nx_global, nyg = g->ny_global, nx_block = g->nx_block;
+  const size_t npl = (size_t)g->nx_block * g->ny_block;
+  static const int partner[4] = {2, 3, 0, 1}; /* 1<->3, 2<->4 */
+  double *rowtop = (double *)malloc(sizeof(double) * 12 * (size_t)nxg);
+  if (!rowtop) { free_owner_map(&m); ORC_FAIL("stress symmetrise: out of memory"); }
+  for (int q = 0; q < 12; ++q)
+    for (int gi = 1; gi <= nxg; ++gi) {
+      const size_t k = (size_t)(nyg - 1) * nxg + (gi - 1);
+      rowtop[(size_t)q * nxg + gi - 1] = (m.blk[k] >= 0) ? sig[q][(size_t)m.blk[k] * npl + m.loc[k]] : 0.0;
+    }
+  for (int b = 0; b < g->nblocks; ++b) {
+    const int *ig = g->i_glob + (size_t)b * g->nx_block;
+    const int *jg = g->j_glob + (size_t)b * g->ny_block;
+    const int ihi = g->ihi[b], jhi = g->jhi[b];
+    if (jg[jhi - 1] != nyg) continue;
+    for (int q = 0; q < 12; ++q) {
+      const int src = (q / 4) * 4 + partner[q % 4];
+      double *ab = sig[q] + (size_t)b * npl;
+      for (int i = 1; i <= ihi + 1; ++i) {
+        const int gi = ig[i - 1];
+        if (gi < 1 || gi > nxg) continue; /* padding */
+        ab[IX(i, jhi + 1)] = rowtop[(size_t)src * nxg + (nxg - gi + 1) - 1];
+      }
+    }
+  }
+  free(rowtop);
+  free_owner_map(&m);
+  return 0;
+}
+
+/* ---------------------------------------------------------------------------------------
  * The subcycling loop, 2-D blocked: evp.F90:859-913.
  * Index lists are rebuilt from the masks exactly as dyn_prep2 does (shared.F90:740-789):
  * T cells over (ilo:ihi+1, jlo:jhi+1), U cells over (ilo:ihi, jlo:jhi), j outer / i inner.

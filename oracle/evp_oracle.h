@@ -65,6 +65,11 @@ int orc_dyn_finish(const evp_b200_grid_t *grid, const int32_t *iceUmask, const d
 int orc_halo_update(const evp_b200_grid_t *grid, double **flds, int nfld,
                     int field_loc, int field_type);
 
+/* Tripole grids: the twelve ice_HaloUpdate_stress calls that force symmetry of the stress tensor across the fold after
+ * the loop (ice_dyn_evp.F90:1321-1388; ice_boundary.F90:7440-7825).  sig: the 12 stress arrays in the order of
+ * evp_b200_fields_t.  No-op on other grids. */
+int orc_stress_symmetrise(const evp_b200_grid_t *grid, double **sig);
+
 /* single calls, for kernel-level tests (one block, arrays (nx_block,ny_block)) */
 void orc_stress_block(int nx_block, int ny_block, int icellT, const int *indxTi, const int *indxTj,
                       const double *uvel, const double *vvel,

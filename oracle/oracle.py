@@ -60,6 +60,8 @@ def lib(variant="exact"):
         L.orc_dyn_finish.restype = C.c_int
         L.orc_halo_update.argtypes = [C.POINTER(abi.Grid), C.POINTER(C.POINTER(C.c_double)), C.c_int, C.c_int, C.c_int]
         L.orc_halo_update.restype = C.c_int
+        L.orc_stress_symmetrise.argtypes = [C.POINTER(abi.Grid), C.POINTER(C.POINTER(C.c_double))]
+        L.orc_stress_symmetrise.restype = C.c_int
         L.orc_last_error.restype = C.c_char_p
         L.orc_num_threads.restype = C.c_int
         _libs[variant] = L
@@ -151,6 +153,15 @@ def dyn_finish(grid, fields, d, rhow, cosw, sinw, variant="exact"):
     if rc:
         raise RuntimeError("oracle dyn_finish: " + L.orc_last_error().decode())
     return d
+
+
+def stress_symmetrise(grid, fields, variant="exact"):
+    """tripole grids: force symmetry of the 12 stress arrays across the fold (ice_dyn_evp.F90:1321-1388), in place"""
+    L = lib(variant)
+    g, kg = abi.make_grid(grid)
+    ptrs = (C.POINTER(C.c_double) * 12)(*[fields[n].ctypes.data_as(C.POINTER(C.c_double)) for n in abi.STRESS])
+    if L.orc_stress_symmetrise(C.byref(g), ptrs):
+        raise RuntimeError("oracle stress symmetrise: " + L.orc_last_error().decode())
 
 
 def halo_update(grid, arrays, field_loc=1, field_type=1, variant="exact"):

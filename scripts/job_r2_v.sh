@@ -1,0 +1,16 @@
+#!/bin/bash
+# round 2, GPU job V (1 GPU): tile-streaming kernel with the str terms in the stage's own stress slots and the box loads issued by all
+# warps: parity, then loop times at 3600x2400 for 14 / 12 rows (one CTA per SM), 6 rows (two), 4 rows (three)
+mkdir -p gpurun_out
+{
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
+echo "== parity"
+timeout 420 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tstream" 2>&1 | tail -12 > gpurun_out/r2_v_pytest.txt; cat gpurun_out/r2_v_pytest.txt
+if ! grep -q "failed\|error" gpurun_out/r2_v_pytest.txt; then
+  echo "== 3600x2400, 24 subcycles per loop"
+  echo "-- stream"; timeout 200 python scripts/prof_step.py p1deg stream exact 24 4 2>&1 | tail -5 | head -4
+  for r in 14 12 6 4; do
+    echo "-- tstream rows $r"; EVP_B200_TSTREAM_ROWS=$r timeout 200 python scripts/prof_step.py p1deg tstream exact 24 5 2>&1 | tail -6 | cut -c1-300
+  done
+fi
+} 2>&1 | tee gpurun_out/r2_v.txt

@@ -372,6 +372,38 @@ def test_derived_geometry(oracle_mod, evp_lib):
             assert_bitwise(f, ref)
 
 
+@pytest.mark.parametrize("bs", [None, (12, 10)], ids=["1block", "4blocks"])
+def test_tripole_stresses_resident_and_symmetrised(oracle_mod, evp_lib, bs):
+    """tripole grid with the stresses kept on the device: after every loop the library forces their symmetry across the fold itself
+    (evp_b200_stress_symmetrise: the twelve ice_HaloUpdate_stress calls of ice_dyn_evp.F90:1321-1388, which the host can no longer
+    apply to arrays it does not hold).  Three consecutive steps == the oracle stepping with the symmetrisation after each loop, bit
+    for bit, ghost cells included; and the split upload / subcycle / symmetrise / download sequence."""
+    c = synth.make_case("tiny", seed=61, ns="tripole", ew="cyclic", kmt="none", ndte=9, block_size=bs)
+    ref, got = c.copy_fields(), c.copy_fields()
+    not_stress = [n for n in abi.FIELDS_INOUT if n not in abi.STRESS]
+    evp_lib.dyn_evp_b200_init(c.grid)
+    try:
+        for step in range(3):
+            oracle_mod.evp_run_bgrid(c.grid, c.params, ref)
+            oracle_mod.stress_symmetrise(c.grid, ref)
+            evp_lib.dyn_evp_b200_run_resident(dict(c.params, mode=abi.MODE_EXACT), got, keep_stress=True, fetch_stress=(step == 2))
+            assert_bitwise(got, ref, names=not_stress)
+        assert_bitwise(got, ref)
+        # the split API on the same state: one more step
+        oracle_mod.evp_run_bgrid(c.grid, c.params, ref)
+        oracle_mod.stress_symmetrise(c.grid, ref)
+        evp_lib.upload(got)
+        evp_lib.subcycle(dict(c.params, mode=abi.MODE_EXACT))
+        evp_lib.stress_symmetrise()
+        evp_lib.download(got)
+        assert_bitwise(got, ref)
+    finally:
+        evp_lib.dyn_evp_b200_finalize()
+    # the plain call leaves the symmetrisation to the host (the reference runs it after the seam): unchanged
+    c2 = synth.make_case("tiny", seed=62, ns="tripole", ew="cyclic", kmt="none", ndte=5, block_size=bs)
+    assert_bitwise(run_gpu(evp_lib, c2, mode=abi.MODE_EXACT), run_oracle(oracle_mod, c2))
+
+
 def _run_tstream(evp_lib, c, kernel=abi.KERNEL_TSTREAM, split_loops=None):
     """init, hand over the metric arrays, run the loop with the TMA tile-streaming kernel (or AUTO)"""
     f = c.copy_fields()
@@ -542,13 +574,13 @@ def test_resident_stress_equals_host_round_trip(oracle_mod, evp_lib, ndte, bs):
         evp_lib.dyn_evp_b200_finalize()
 
 
-def test_resident_stress_refused_on_tripole(evp_lib):
+def test_step_preparation_refused_on_tripole(evp_lib):
+    """the device-side step preparation (evp_b200_prep_init) is not built for tripole grids: it must say so"""
     c = synth.make_case("tiny", seed=41, ns="tripole", kmt="none", ndte=2)
-    f = c.copy_fields()
     evp_lib.dyn_evp_b200_init(c.grid)
     try:
         with pytest.raises(evp_lib.EvpB200Error, match="tripole"):
-            evp_lib.dyn_evp_b200_run_resident(dict(c.params, mode=abi.MODE_EXACT), f)
+            evp_lib.dyn_evp_b200_prep_init(synth.step_inputs(c)[0])
     finally:
         evp_lib.dyn_evp_b200_finalize()
 

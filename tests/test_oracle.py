@@ -342,3 +342,60 @@ def test_evp_constants_follow_reference_set_evp_parameters(ndte, revised):
     mine = synth.evp_params(ndte, revised_evp=revised)
     for k, v in ref.items():
         assert mine[k] == v, k
+
+
+def _halo_update_stress_literal(grid, a1, a2):
+    """ice_HaloUpdate_stress(array1, array2, halo, field_loc_center, field_type_scalar) on one task, loop for loop
+    (/root/reference/cicecore/cicedyn/infrastructure/comm/mpi/ice_boundary.F90): the tripole buffer is filled from array2 through the
+    "srcBlock > 0, dstBlock < 0" local copies (:7641-7652; addresses built at :8117-8133: the top tripoleRows = nghost+1 physical rows,
+    buffer column = global i), and copied out into array1 through the "srcBlock < 0" entries (:7760-7794; addresses :8136-8157), with
+    ioffset = joffset = 0 and isign = +1 for a centre-located scalar on a u-fold (:7729-7732, :7702)."""
+    nghost, nxg = 1, grid["nx_global"]
+    rows = nghost + 1                                   # halo%tripoleRows
+    buf = np.zeros((rows + 1, nxg + 1))                 # bufTripole(1:nxGlobal, 1:tripoleRows), 1-based; = fill (0)
+    top = [b for b in range(grid["nblocks"]) if grid["j_glob"][b][grid["jhi"][b] - 1] == grid["ny_global"]]
+    for b in top:                                       # copy into the buffer
+        ib, ie, je = grid["ilo"][b], grid["ihi"][b], grid["jhi"][b]
+        for j in range(1, rows + 1):
+            for i in range(1, ie - ib + 2):
+                buf[j, grid["i_glob"][b][ib + i - 1 - 1]] = a2[b, je - rows + j - 1, ib + i - 1 - 1]
+    for b in top:                                       # copy out of the buffer
+        ie, je = grid["ihi"][b], grid["jhi"][b]
+        for j in range(1, rows + 1):
+            for i in range(1, ie + nghost + 1):
+                ig = grid["i_glob"][b][i - 1]
+                if ig < 1:
+                    continue                            # padded column
+                isrc, jsrc = nxg - ig + 1, nghost + 3 - j
+                jdst = -1 if j > nghost + 1 else je + j - 1
+                if isrc < 1:
+                    isrc += nxg
+                if isrc > nxg:
+                    isrc -= nxg
+                if 0 < jsrc <= rows and jdst > 0:
+                    a1[b, jdst - 1, i - 1] = buf[jsrc, isrc]
+
+
+@pytest.mark.parametrize("bs", [None, (12, 10), (8, 7)], ids=["1block", "4blocks", "padded-blocks"])
+def test_stress_symmetrise_equals_the_literal_halo_update_stress(oracle_mod, bs):
+    """the symmetrisation of the stress tensor across the tripole fold after the loop (ice_dyn_evp.F90:1321-1388): the oracle's closed
+    form against the reference's twelve ice_HaloUpdate_stress calls restated loop for loop; only north ghost rows of top blocks change."""
+    c = synth.make_case("tiny", seed=51, ns="tripole", ew="cyclic", kmt="none", ndte=1, block_size=bs)
+    rng = np.random.default_rng(5)
+    f = {n: rng.normal(size=c.fields[n].shape) for n in abi.STRESS}
+    want = {n: a.copy() for n, a in f.items()}
+    for k in ("p", "m", "12"):
+        for a, b in ((1, 3), (3, 1), (2, 4), (4, 2)):   # the order of ice_dyn_evp.F90:1347-1386
+            _halo_update_stress_literal(c.grid, want[f"stress{k}_{a}"], want[f"stress{k}_{b}"])
+    got = {n: a.copy() for n, a in f.items()}
+    oracle_mod.stress_symmetrise(c.grid, got)
+    changed = 0
+    for n in abi.STRESS:
+        assert np.array_equal(got[n].view(np.int64), want[n].view(np.int64)), n
+        changed += int((got[n] != f[n]).sum())
+    assert changed > 0
+    # a grid without a fold is left alone
+    c2 = synth.make_case("tiny", seed=52, ndte=1)
+    g2 = {n: c2.fields[n].copy() for n in abi.STRESS}
+    oracle_mod.stress_symmetrise(c2.grid, g2)
+    assert all(np.array_equal(g2[n], c2.fields[n]) for n in abi.STRESS)
