@@ -454,6 +454,7 @@ def run_ours(args):
         us_per_subcycle = kernel_ms * 1e3 / ndte
         cold, warm = ctr.get("dram_bytes_per_launch_cold"), ctr.get("dram_bytes_per_launch_warm")
         same_shape = (args.workload == "gx1" and (sx, sy) == (320, 384))
+        ts_ctr = kernel_counters("tstream_p1deg") if (tstream and (sx, sy) == (3600, 2400)) else None
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 # the loop is 1 cold launch + (ndte-1) launches that find the working set in L2: the launch-weighted mean
                 # (persistent kernel: ONE launch per step on a flushed L2, so the cold capture is the state of every timed launch)
@@ -465,6 +466,12 @@ def run_ours(args):
                 "traffic_detail": ctr if same_shape else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_cell_subcycle": ALGO_BYTES_PER_CELL_SUBCYCLE,
                 "kernel_ms_per_step": kernel_ms, "us_per_subcycle": us_per_subcycle, "subcycles_per_launch": sub_per_launch}
+        if ts_ctr and ts_ctr.get("shape") == [sx, sy]:
+            # the tile-streaming kernel at this very shape: every launch streams the whole working set, one ncu capture is the state of all
+            roof.update({"traffic": ts_ctr["dram_bytes_per_launch"], "traffic_cold": ts_ctr["dram_bytes_per_launch"],
+                         "traffic_warm": ts_ctr["dram_bytes_per_launch"], "traffic_detail": ts_ctr,
+                         "traffic_how": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape from the committed "
+                                        "ncu --set full capture (" + ts_ctr["source"] + "); not re-measured in this run"})
         if same_shape and ctr.get("fp64_floor_us_per_subcycle"):
             # the ceiling that binds when the working set is L2 resident: the fp64 pipe (0.5 warp-instructions / clk / sub-partition)
             fl = ctr["fp64_floor_us_per_subcycle"]
