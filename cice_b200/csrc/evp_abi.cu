@@ -628,8 +628,7 @@ static int tstream_prepare() {
     return fail("evp_b200_subcycle: the TMA tile-streaming kernel needs evp_b200_set_metric to have accepted the metric arrays and no in-kernel NVLink halo (%s)",
                 g.p2p.enabled ? "neighbour ranks use it" : (g.derived_ok ? "metric arrays missing" : "derived geometry unavailable"));
   if (const char *e = getenv("EVP_B200_TSTREAM_ROWS")) g.ts_rows = atoi(e);
-  const char *ie = getenv("EVP_B200_TSTREAM_ISSUE");
-  const void *key[3] = {g.dom.u[0], g.dom.sig[0][0], (const void *)(intptr_t)(g.ts_rows * 2 + ((ie && !atoi(ie)) ? 0 : 1))};
+  const void *key[3] = {g.dom.u[0], g.dom.sig[0][0], (const void *)(intptr_t)g.ts_rows};
   if (!g.ts_hmaps.empty() && memcmp(key, g.ts_key, sizeof key) == 0) return 0;
   g.ts_hmaps.resize(exact::tstream_map_bytes() + 64);
   void *hmaps = (void *)(((uintptr_t)g.ts_hmaps.data() + 63) & ~(uintptr_t)63);
@@ -641,8 +640,6 @@ static int tstream_prepare() {
   }
   if (!g.d_tserr) { CK(cudaMalloc(&g.d_tserr, sizeof(int))); CK(cudaMemset(g.d_tserr, 0, sizeof(int))); }
   ts.maps = hmaps; ts.err = g.d_tserr; ts.deltamin = g.deltamin;
-  ts.issue = 1;
-  if (const char *e = getenv("EVP_B200_TSTREAM_ISSUE")) ts.issue = atoi(e) ? 1 : 0;
   g.tsplan = ts;
   memcpy(g.ts_key, key, sizeof key);
   if (g.desc.find("; tstream:") == std::string::npos) {

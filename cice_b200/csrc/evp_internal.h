@@ -167,7 +167,6 @@ struct TsPlan {
   int nb;              // blocks per (full) segment
   int nitems;          // nstrips * nseg work items, dealt round robin to the CTAs
   int ctas;            // grid size
-  int issue;           // 1: box loads issued from uniform registers by an elected lane; 0: by thread 0 (waterfall loops)
   int *err;            // set when a wait for a box load times out (never, unless the byte count is wrong)
   double deltamin;     // deltaminEVP (derived geometry)
 };

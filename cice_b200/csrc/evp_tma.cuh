@@ -39,13 +39,6 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const TmaMap *map, int x,
                ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
                : "memory");
 }
-// one lane of a converged warp (elect.sync), and a value the compiler may treat as the same in every lane of the warp
-__device__ __forceinline__ bool elect_one() {
-  unsigned pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void tma_prefetch_map(const TmaMap *map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
 // wait for phase number `phase` (0, 1, 2 ... in the order the barrier completes them).  Bounded like every other in-kernel wait
 // of this library: a programming error (byte count that never arrives) becomes an error code, not a hung GPU.
@@ -116,8 +109,6 @@ inline void tma_load_2d(void *dst, const TmaMap *m, int x, int y, MBar *bar) {
     }
   bar->landed.fetch_add((long long)m->box0 * m->box1 * m->elem, std::memory_order_release);
 }
-inline bool elect_one() { return (emu::lin & 31) == 0; }
-inline int warp_uniform(int v) { return v; }
 inline void tma_prefetch_map(const TmaMap *) {}
 inline void mbar_wait(MBar *bar, unsigned phase, int *err) {
   for (long spins = 0;; ++spins) {

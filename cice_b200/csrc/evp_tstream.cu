@@ -29,6 +29,7 @@
 #include "evp_ptx.cuh"
 #include "evp_tma.cuh"
 #include <stdio.h>
+#include <stdlib.h>
 
 #ifndef EVP_USE_PDL
 #define EVP_USE_PDL 1
@@ -101,7 +102,7 @@ __device__ __forceinline__ void ts_issue(const TsMaps &tm, int cur, unsigned cha
   mbar_arrive_expect_tx(bar, L::TX_BYTES);
 }
 
-template <int R, int MINB, int UNI>
+template <int R, int MINB>
 __global__ void __launch_bounds__(32 * R, MINB) tstream_kernel(const __grid_constant__ Dom d, const __grid_constant__ KParams k,
                                                                const __grid_constant__ TsPlan ts, const __grid_constant__ TsMaps tm,
                                                                int cur, int last) {
@@ -125,15 +126,14 @@ __global__ void __launch_bounds__(32 * R, MINB) tstream_kernel(const __grid_cons
   ci.item = blockIdx.x;
   ts_setup<R>(d, ts, ci);
   pi = ci;
-  // who issues the box loads.  UNI = 1: an elected lane of warp 0 inside a branch the compiler knows to be the same for the whole warp,
-  // so that the operands stay in uniform registers (5 instructions per load); UNI = 0: thread 0, which costs a waterfall loop per load
-  // (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~15 instructions) -- kept selectable (EVP_B200_TSTREAM_ISSUE) for A/B runs on one box
-  const bool issuer_warp = UNI ? (warp_uniform(ty) == 0) : (t == 0);
-  // (every thread steps the prefetch iterator, so that the operands of the box loads are uniform values the compiler keeps in uniform
-  // registers; only the instructions themselves are thread 0's)
+  // Thread 0 issues the box loads.  (An elected lane of warp 0 inside a warp-uniform branch keeps the operands in uniform registers --
+  // 5 instead of ~15 instructions per load, no ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop -- and was 4 % SLOWER at 12 rows and
+  // 15 % at 6 in the one-box A/B, profiles/r2_tstream_ab.txt: 160 registers instead of 151 and uniform-register spills.)
+  const bool issuer = (t == 0);
+  // (every thread steps the prefetch iterator; only the box loads themselves are thread 0's)
   for (int s = 0; s < 2; ++s)
     if (pi.item < ts.nitems) {
-      if (issuer_warp && (!UNI || elect_one())) ts_issue<R>(tm, cur, smem + s * L::STAGE, &bars[s], pi.i0, pi.j0 + R * pi.b);
+      if (issuer) ts_issue<R>(tm, cur, smem + s * L::STAGE, &bars[s], pi.i0, pi.j0 + R * pi.b);
       ts_next<R>(d, ts, pi, G);
     }
   for (unsigned q = 0; ci.item < ts.nitems; ++q) {
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(32 * R, MINB) tstream_kernel(const __grid_cons
 
     // ---- the stage is free: fetch the block after the next one into it -------------------------------------------------------
     if (pi.item < ts.nitems) {
-      if (issuer_warp && (!UNI || elect_one())) {
+      if (issuer) {
         fence_proxy_async();
         ts_issue<R>(tm, cur, st, &bars[s], pi.i0, pi.j0 + R * pi.b);
       }
@@ -267,10 +267,10 @@ static void tstream_cut(int nx, int ny, int num_sms, int rows, TsPlan *ts) {
 
 #ifndef EVP_HOST_EMU
 
-template <int R, int MINB, int UNI>
+template <int R, int MINB>
 static cudaError_t launch_tstream_t(const Dom &d, const KParams &p, const TsPlan &ts, int cur, int last, bool pdl, cudaStream_t s) {
   const int smem = TsL<R>::TOTAL + 128;
-  cudaError_t e = cudaFuncSetAttribute(tstream_kernel<R, MINB, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(tstream_kernel<R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ts.ctas); cfg.blockDim = dim3(32 * R); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -278,13 +278,13 @@ static cudaError_t launch_tstream_t(const Dom &d, const KParams &p, const TsPlan
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, tstream_kernel<R, MINB, UNI>, d, p, ts, *(const TsMaps *)ts.maps, cur, last);
+  return cudaLaunchKernelEx(&cfg, tstream_kernel<R, MINB>, d, p, ts, *(const TsMaps *)ts.maps, cur, last);
 }
 
 cudaError_t launch_tstream(const Dom &d, const KParams &p, const TsPlan &ts, int cur, int last, bool pdl, cudaStream_t s) {
   switch (ts.rows) {
-    case 12: return ts.issue ? launch_tstream_t<12, 1, 1>(d, p, ts, cur, last, pdl, s) : launch_tstream_t<12, 1, 0>(d, p, ts, cur, last, pdl, s);
-    case 6: return ts.issue ? launch_tstream_t<6, 2, 1>(d, p, ts, cur, last, pdl, s) : launch_tstream_t<6, 2, 0>(d, p, ts, cur, last, pdl, s);
+    case 12: return launch_tstream_t<12, 1>(d, p, ts, cur, last, pdl, s);
+    case 6: return launch_tstream_t<6, 2>(d, p, ts, cur, last, pdl, s);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -312,6 +312,9 @@ int tstream_plan(const Dom &d, size_t dom_rows, const double *HTN, const double 
   // Driver workaround, as CUTLASS applies it in make_tma_copy_desc: drivers up to CUDA 13.1 may set bit 21 of the second descriptor word
   // for tensors of less than 128 KiB (small sub-domains, byte masks), which the TMA unit does not accept.  (Driver 580 on the B200 pool
   // did not set it; what its TMA unit rejected were box starts off a 16-byte boundary -- see the header comment.)
+  // L2 promotion of the box loads (the granule the TMA unit asks L2 to fetch): none, 128 B and 256 B measured the same within 1 %
+  // (profiles/r2_tstream_ab.txt)
+  const CUtensorMapL2promotion l2p = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   int drv = 0;
   cudaDriverGetVersion(&drv);
   auto small_fix = [&](TmaMap &t, size_t bytes) {
@@ -321,7 +324,7 @@ int tstream_plan(const Dom &d, size_t dom_rows, const double *HTN, const double 
     const cuuint64_t dims[2] = {(cuuint64_t)d.ld, (cuuint64_t)dom_rows}, strides[1] = {(cuuint64_t)d.ld * 8};
     const cuuint32_t box[2] = {(cuuint32_t)bx, (cuuint32_t)by}, es[2] = {1, 1};
     if (encode(&m[idx].m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+               CU_TENSOR_MAP_SWIZZLE_NONE, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       ++bad;
     small_fix(m[idx], (size_t)d.ld * dom_rows * 8);
   };
@@ -329,7 +332,7 @@ int tstream_plan(const Dom &d, size_t dom_rows, const double *HTN, const double 
     const cuuint64_t dims[2] = {(cuuint64_t)d.ld, (cuuint64_t)dom_rows}, strides[1] = {(cuuint64_t)d.ld};
     const cuuint32_t box[2] = {TS_MW, (cuuint32_t)rows}, es[2] = {1, 1};
     if (encode(&m[idx].m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+               CU_TENSOR_MAP_SWIZZLE_NONE, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       ++bad;
     small_fix(m[idx], (size_t)d.ld * dom_rows);
   };

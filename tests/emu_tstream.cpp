@@ -72,14 +72,13 @@ extern "C" int emu_tstream_run(int rows, int nb_override, int nctas, int nxb, in
   if (plan_out) { plan_out[0] = ts.nstrips; plan_out[1] = ts.nseg; plan_out[2] = ts.nb; plan_out[3] = ts.nitems; plan_out[4] = ts.ctas; }
 
   const KParams &k = *kp;
-  const int issue = (nb_override & 1) ? 0 : 1;   // both issue modes get exercised
   int cur = 0;
   for (int ks = 0; ks < ndte; ++ks) {
     const int last = (ks == ndte - 1) ? 1 : 0;
     if (rows == 12)
-      emu::launch_concurrent(ts.ctas, 32 * 12, TsL<12>::TOTAL + 128, [&] { (issue ? tstream_kernel<12, 1, 1>(d, k, ts, tmaps, cur, last) : tstream_kernel<12, 1, 0>(d, k, ts, tmaps, cur, last)); });
+      emu::launch_concurrent(ts.ctas, 32 * 12, TsL<12>::TOTAL + 128, [&] { tstream_kernel<12, 1>(d, k, ts, tmaps, cur, last); });
     else if (rows == 6)
-      emu::launch_concurrent(ts.ctas, 32 * 6, TsL<6>::TOTAL + 128, [&] { (issue ? tstream_kernel<6, 2, 1>(d, k, ts, tmaps, cur, last) : tstream_kernel<6, 2, 0>(d, k, ts, tmaps, cur, last)); });
+      emu::launch_concurrent(ts.ctas, 32 * 6, TsL<6>::TOTAL + 128, [&] { tstream_kernel<6, 2>(d, k, ts, tmaps, cur, last); });
     else
       return 1;
     if (err) return 2;
