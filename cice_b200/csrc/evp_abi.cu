@@ -136,6 +136,7 @@ struct Ctx {
   int *d_int_lin = nullptr, *d_int_dom = nullptr, n_int = 0;
   int *d_symw_lin = nullptr, *d_symw_dom = nullptr, n_symw = 0;  // tripole: west-ghost corner of the north ghost row of every top block
   bool sym_applied = false;                                       // the device stresses carry the symmetrisation across the fold
+  double *d_symrow = nullptr;                                     // [12][nx_global]: the top physical row of every stress array (ranks of the top row)
 
   // loop state
   int cur = 0;
@@ -247,7 +248,7 @@ static int free_all() {
   for (auto &p : g.prep_static) F(p);
   for (auto &p : g.prepT) F(p);
   F(g.prep_umask);
-  F(g.d_symw_lin); F(g.d_symw_dom); F(g.d_uv_lin); F(g.d_uv_dom); F(g.d_sig_lin); F(g.d_sig_dom); F(g.d_int_lin); F(g.d_int_dom);
+  F(g.d_symw_lin); F(g.d_symw_dom); F(g.d_symrow); F(g.d_uv_lin); F(g.d_uv_dom); F(g.d_sig_lin); F(g.d_sig_dom); F(g.d_int_lin); F(g.d_int_dom);
   g.halo.release();
   for (auto &e : g.ev_field) if (e) cudaEventDestroy(e);
   if (g.xfer) cudaStreamDestroy(g.xfer);
@@ -1393,17 +1394,33 @@ __global__ void stress_fold_kernel(const __grid_constant__ Dom d, int cur, int g
   const int src = (q / 4) * 4 + ((q % 4) + 2) % 4;
   d.sig[cur][q][(size_t)(d.ny + 1) * d.ld + i] = d.sig[cur][src][(size_t)d.ny * d.ld + ic];
 }
+// the same with the mirrored cells taken from the gathered top row (rowtop[12][nxg]): the top row is spread over several ranks
+__global__ void stress_fold_rows_kernel(const __grid_constant__ Dom d, int cur, int gi0, int nxg, const double *__restrict__ rowtop) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
+  if (i > d.nx + 1) return;
+  int ig = gi0 + i - 1;
+  if (ig < 1) ig += nxg;
+  if (ig > nxg) ig -= nxg;
+  const int src = (q / 4) * 4 + ((q % 4) + 2) % 4;
+  d.sig[cur][q][(size_t)(d.ny + 1) * d.ld + i] = rowtop[(size_t)src * nxg + (nxg - ig + 1) - 1];
+}
 static bool symmetrise_here() { return g.ns == EVP_B200_BNDY_TRIPOLE && g.gj0 + g.dom.ny - 1 == g.nyg; }
-static bool symmetrise_possible() { return !symmetrise_here() || (g.gi0 == 1 && g.dom.nx == g.nxg); }
 static int do_stress_symmetrise() {
   if (!g.inited || !g.uploaded) return fail("evp_b200_stress_symmetrise: no stresses on the device");
   if (g.ns != EVP_B200_BNDY_TRIPOLE) return 0;
-  if (!symmetrise_possible())
-    return fail("evp_b200_stress_symmetrise: the top row of the tripole grid is spread over several ranks (not in this version)");
   if (symmetrise_here()) {
     CK(cudaSetDevice(g.device));
     dim3 b(128), gr((g.dom.nx + 2 + b.x - 1) / b.x, 12);
-    stress_fold_kernel<<<gr, b, 0, g.stream>>>(g.dom, g.cur, g.gi0, g.nxg);
+    if (g.gi0 == 1 && g.dom.nx == g.nxg) {   // the whole top row is this rank's
+      stress_fold_kernel<<<gr, b, 0, g.stream>>>(g.dom, g.cur, g.gi0, g.nxg);
+    } else {                                 // gather it from the other ranks of the top row (NCCL, once per step)
+      if (g_comm.nranks < 2) return fail("evp_b200_stress_symmetrise: the rank holds a part of the tripole top row and there is no communicator");
+      if (!g.d_symrow) CK(cudaMalloc(&g.d_symrow, sizeof(double) * 12 * (size_t)g.nxg));
+      if (stress_rows_exchange(g_comm, g.halo.rects, g.nxg, g.nyg, g.dom.sig[g.cur], g.dom.ld, g.dom.nx, g.dom.ny, g.gi0, g.gj0, g.d_symrow, g.stream,
+                               g_err, sizeof g_err))
+        return 1;
+      stress_fold_rows_kernel<<<gr, b, 0, g.stream>>>(g.dom, g.cur, g.gi0, g.nxg, g.d_symrow);
+    }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(g.stream));
   }
@@ -1414,9 +1431,6 @@ int evp_b200_stress_symmetrise(void) { return do_stress_symmetrise(); }
 
 int evp_b200_run_bgrid_resident(const evp_b200_params_t *p, evp_b200_fields_t *f, int32_t flags) {
   const bool sym = (flags & EVP_B200_KEEP_STRESS) && g.inited && g.ns == EVP_B200_BNDY_TRIPOLE;
-  if (sym && (g_comm.nranks > 1 || !symmetrise_possible()))
-    return fail("evp_b200_run_bgrid_resident: EVP_B200_KEEP_STRESS on a tripole grid needs the whole top row on one rank (the "
-                "symmetrisation of the stresses across the fold, ice_dyn_evp.F90:1321-1388, is done on the device only then)");
   if (do_upload(f, (flags & EVP_B200_KEEP_STRESS) != 0)) return 1;
   if (do_subcycle(p)) return 1;
   if (sym && do_stress_symmetrise()) return 1;

@@ -64,6 +64,29 @@ void comm_destroy(CommState &cs) {
   cs = CommState{};
 }
 
+int stress_rows_exchange(CommState &cs, const std::vector<int> &rects, int nxg, int nyg, double *const *sig, int ld, int nx, int ny, int gi0,
+                         int gj0, double *rowtop, cudaStream_t s, char *err, size_t nerr) {
+  if (gj0 + ny - 1 != nyg) return 0;
+  HCK(cudaMemsetAsync(rowtop, 0, sizeof(double) * 12 * (size_t)nxg, s));
+  for (int q = 0; q < 12; ++q)
+    HCK(cudaMemcpyAsync(rowtop + (size_t)q * nxg + (gi0 - 1), sig[q] + (size_t)ny * ld + 1, sizeof(double) * nx, cudaMemcpyDeviceToDevice, s));
+  if (cs.nranks < 2) return 0;
+  if (!cs.comm || (int)rects.size() < 4 * cs.nranks) HFAIL("stress symmetrisation: no communicator / rank table");
+  // every pair of top-row ranks swaps its twelve row segments; same order on both sides
+  NCK(ncclGroupStart());
+  for (int t = 0; t < cs.nranks; ++t) {
+    if (t == cs.rank) continue;
+    const int ti0 = rects[4 * t], tj0 = rects[4 * t + 1], tnx = rects[4 * t + 2], tny = rects[4 * t + 3];
+    if (tnx < 1 || tny < 1 || tj0 + tny - 1 != nyg) continue;
+    for (int q = 0; q < 12; ++q) {
+      NCK(ncclSend(sig[q] + (size_t)ny * ld + 1, (size_t)nx, ncclDouble, t, cs.comm, s));
+      NCK(ncclRecv(rowtop + (size_t)q * nxg + (ti0 - 1), (size_t)tnx, ncclDouble, t, cs.comm, s));
+    }
+  }
+  NCK(ncclGroupEnd());
+  return 0;
+}
+
 __global__ void halo_pack(const double *__restrict__ U, const double *__restrict__ V, const int *__restrict__ idx, int n,
                           double *__restrict__ buf) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {

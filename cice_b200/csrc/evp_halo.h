@@ -64,6 +64,13 @@ struct HaloPlan {
   void release();
 };
 
+// Tripole grids, stresses resident: the top physical row of the 12 stress arrays of every rank of the top row, gathered into
+// rowtop[12][nxg] on each of those ranks (what ice_HaloUpdate_stress moves through its tripole buffer, ice_boundary.F90:7596-7688).
+// rects as HaloPlan::rects; sig: the 12 dom arrays of the current copy.  Ranks below the top row return at once; rowtop is zeroed
+// first (columns nobody holds -- eliminated land blocks -- stay at the reference's fill value).
+int stress_rows_exchange(CommState &cs, const std::vector<int> &rects, int nxg, int nyg, double *const *sig, int ld, int nx, int ny, int gi0,
+                         int gj0, double *rowtop, cudaStream_t s, char *err, size_t nerr);
+
 // In-kernel NVLink halo: peers' velocity arrays and flags mapped through CUDA IPC (one process per GPU).
 struct P2PState {
   bool enabled = false;

@@ -301,8 +301,8 @@ int evp_b200_download(evp_b200_fields_t *fields);
  * Tripole grids: after the loop the reference forces the symmetry of the stress tensor across the fold -- twelve
  * ice_HaloUpdate_stress calls (ice_dyn_evp.F90:1321-1388; ice_boundary.F90:7440-7825) that copy the mirrored top physical row
  * of stressX_3 into the north ghost row of stressX_1 and so on.  With the stresses on the device the library does that itself
- * (evp_b200_stress_symmetrise, called by evp_b200_run_bgrid_resident after the loop), when the rank holds the whole top row
- * of the grid; EVP_B200_KEEP_STRESS is refused on a tripole grid whose top row is spread over several ranks. */
+ * (evp_b200_stress_symmetrise, called by evp_b200_run_bgrid_resident after the loop): a rank that holds the whole top row of the
+ * grid mirrors it locally, ranks that share the top row first swap their twelve row segments (NCCL send/recv, once per step). */
 enum {
   EVP_B200_KEEP_STRESS  = 1,
   EVP_B200_FETCH_STRESS = 2
@@ -310,7 +310,7 @@ enum {
 int evp_b200_run_bgrid_resident(const evp_b200_params_t *params, evp_b200_fields_t *fields, int32_t flags);
 int evp_b200_download_stress(evp_b200_fields_t *fields);
 /* the symmetrisation alone, on the stresses the device holds (for callers of the upload / subcycle / download split); no-op on
- * grids without a tripole fold and on ranks below the top row */
+ * grids without a tripole fold and on ranks below the top row.  Collective over the ranks of the top row when they are several. */
 int evp_b200_stress_symmetrise(void);
 
 /* ---- next rows: the step preparation on the device, the whole dynamics state resident ----------

@@ -45,7 +45,9 @@ def main():
                 owner[n] = -1
     g, f, bids = case.rank_view(owner, rank)
     step = kernel == "step"   # the step preparation on the device, state resident (evp_b200_step_resident), two consecutive steps
-    p = dict(case.params, mode=abi.MODE_EXACT, kernel=abi.KERNEL_NAMES["auto" if step else kernel])
+    resident = kernel == "resident"   # stresses resident over two steps (evp_b200_run_bgrid_resident); on a tripole grid with the
+    #                                   symmetrisation across the fold on the device, the top-row segments exchanged between ranks
+    p = dict(case.params, mode=abi.MODE_EXACT, kernel=abi.KERNEL_NAMES["auto" if step or resident else kernel])
     dyn_evp.dyn_evp_b200_init(g)
     desc = dyn_evp.describe()
     if step:
@@ -57,6 +59,9 @@ def main():
         dyn_evp.dyn_evp_b200_prep_init(static)
         dyn_evp.dyn_evp_b200_step_resident(p, prep, f, init_state=True)
         dyn_evp.dyn_evp_b200_step_resident(p, prep, f, fetch_diag=True, fetch_state=True)
+    elif resident:
+        dyn_evp.dyn_evp_b200_run_resident(p, f, keep_stress=True, fetch_stress=False)
+        dyn_evp.dyn_evp_b200_run_resident(p, f, keep_stress=True, fetch_stress=True)
     else:
         dyn_evp.dyn_evp_b200_run(p, f)
     nl = dyn_evp.last_launches()
@@ -69,6 +74,10 @@ def main():
         from oracle import oracle
         ref = case.copy_fields()
         oracle.evp_run_bgrid(case.grid, case.params, ref)   # all blocks: elimination does not change the kept ones (test_oracle.py)
+        if resident:   # after each loop the stresses are symmetrised across the fold (ice_dyn_evp.F90:1321-1388; no-op without a fold)
+            oracle.stress_symmetrise(case.grid, ref)
+            oracle.evp_run_bgrid(case.grid, case.params, ref)
+            oracle.stress_symmetrise(case.grid, ref)
         if step:   # second step: dyn_prep2 clears taubx/tauby, everything else carries over
             for n in ("taubxU", "taubyU"):
                 ref[n][...] = 0.0
