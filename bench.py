@@ -359,7 +359,8 @@ def run_ours(args):
     # (a) every field crosses both ways every step (evp_b200_run_bgrid, the plain drop-in);
     # (b) the 12 carried stress arrays stay on the device (evp_b200_run_bgrid_resident, EVP_B200_KEEP_STRESS): velocities,
     #     the 12 per-step inputs, masks and diagnostics still cross every step.  (b) is what INTEGRATION.md wires up for
-    #     every step that does not write a restart/history file; not available on tripole grids.
+    #     every step that does not write a restart/history file.  On tripole grids the library then symmetrises the stresses across
+    #     the fold itself after the loop (evp_b200_stress_symmetrise; between the ranks of the top row by one NCCL swap per step).
     e2e_steps = max(2, min(args.steps, 5))
     nblk = int(np.prod(fields["uvel"].shape))
 
@@ -375,12 +376,14 @@ def run_ours(args):
 
     hfc = {k: v for k, v in hf.items() if not k.startswith("_keep_")}
     e2e_full_s = time_e2e(dyn_evp.bind("run", params, hfc))   # C structs built once, like a compiled caller: the loop times the C ABI
-    resident_ok = grid["ns_boundary_type"] != abi.BNDY_NAMES["tripole"]
+    resident_ok = True
+    step_ok = grid["ns_boundary_type"] != abi.BNDY_NAMES["tripole"]   # the device-side step preparation is not built for tripole grids
     if resident_ok:
         e2e_s = time_e2e(dyn_evp.bind("run_resident", params, hfc, keep_stress=True))
         h2d = 18 * nblk * 8 + 2 * nblk * 4
         d2h = 6 * nblk * 8
-        e2e_how = "evp_b200_run_bgrid_resident(EVP_B200_KEEP_STRESS): stresses stay on the device, everything else crosses"
+        e2e_how = "evp_b200_run_bgrid_resident(EVP_B200_KEEP_STRESS): stresses stay on the device, everything else crosses" + \
+                  ("" if step_ok else "; tripole grid: the stresses are symmetrised across the fold on the device after the loop")
     else:
         e2e_s = e2e_full_s
         h2d = 30 * nblk * 8 + 2 * nblk * 4
@@ -390,7 +393,7 @@ def run_ours(args):
     #     inputs + strength + iceTmask go in, the velocities come out; velocities, stresses and iceUmask stay on the device.
     #     Not for tripole grids in this version; between ranks the velocity halo after dyn_prep2 is one staged exchange per step.
     e2e_step = None
-    if resident_ok:
+    if step_ok:
         static, prep = synth.step_inputs(case)
         if world > 1:   # this rank's blocks
             static = {k: (np.ascontiguousarray(v[bids]) if isinstance(v, np.ndarray) else v) for k, v in static.items()}
