@@ -399,3 +399,88 @@ def test_stress_symmetrise_equals_the_literal_halo_update_stress(oracle_mod, bs)
     g2 = {n: c2.fields[n].copy() for n in abi.STRESS}
     oracle_mod.stress_symmetrise(c2.grid, g2)
     assert all(np.array_equal(g2[n], c2.fields[n]) for n in abi.STRESS)
+
+
+def _halo_update_literal(grid, a, field_loc, field_type):
+    """ice_HaloUpdate2DR8 on one task for a centre- or NE-corner-located field on a u-fold tripole (or any other) grid, with the
+    tripole part restated loop for loop from /root/reference/cicecore/cicedyn/infrastructure/comm/mpi/ice_boundary.F90:
+      * ordinary ghost cells: the local copies built by ice_HaloMsgCreate (east/west/north/south/corner cases, :7975-8100, 8160-8400)
+        give a ghost cell the interior value of the block that owns its global index (cyclic wrap is in i_glob/j_glob,
+        ice_blocks.F90:222-276); cells outside a closed/open edge are not touched (no fill requested, :1173-1181);
+      * tripole buffer: the top tripoleRows = nghost+1 physical rows, buffer column = global i (:1372-1395, addresses :8117-8133);
+      * NE corner on a u-fold: ioffset = joffset = 1 and the top buffer row is symmetrised pairwise, i = 1 .. nxGlobal/2 - 1 with
+        iDst = nxGlobal - i (:1689-1703); centre: no offsets, no averaging (:1685-1688);
+      * copy-out over every column of every top block, rows j = 1 .. tripoleRows (:1724-1756, addresses :8136-8157):
+        iSrc = nxGlobal - i_glob(i) + 1 - ioffset (wrapped), jSrc = nghost + 3 - j - joffset, jDst = jhi + j - 1,
+        array(i, jDst) = isign * buf(iSrc, jSrc) when 0 < jSrc <= tripoleRows."""
+    nghost, nxg, nyg = 1, grid["nx_global"], grid["ny_global"]
+    nb = grid["nblocks"]
+    ig_, jg_ = grid["i_glob"], grid["j_glob"]
+    tripole = grid["ns_boundary_type"] == abi.BNDY_NAMES["tripole"]
+    isign = -1.0 if field_type == 1 else 1.0
+    # global interior values as the blocks hold them (sources are physical cells only: the order of the copies does not matter)
+    G = np.zeros((nyg + 1, nxg + 1))
+    for b in range(nb):
+        for j in range(grid["jlo"][b], grid["jhi"][b] + 1):
+            for i in range(grid["ilo"][b], grid["ihi"][b] + 1):
+                G[jg_[b][j - 1], ig_[b][i - 1]] = a[b, j - 1, i - 1]
+    for b in range(nb):
+        ilo, ihi, jlo, jhi = grid["ilo"][b], grid["ihi"][b], grid["jlo"][b], grid["jhi"][b]
+        for j in range(jlo - nghost, jhi + nghost + 1):
+            for i in range(ilo - nghost, ihi + nghost + 1):
+                if ilo <= i <= ihi and jlo <= j <= jhi:
+                    continue
+                gi, gj = ig_[b][i - 1], jg_[b][j - 1]
+                if 1 <= gi <= nxg and 1 <= gj <= nyg:
+                    a[b, j - 1, i - 1] = G[gj, gi]
+    if not tripole:
+        return
+    rows = nghost + 1
+    buf = np.zeros((rows + 1, nxg + 1))
+    for j in range(1, rows + 1):
+        buf[j, 1:] = G[nyg - rows + j, 1:]
+    if field_loc == 1:                       # field_loc_NEcorner, u-fold
+        ioffset = joffset = 1
+        for i in range(1, nxg // 2):         # do i = 1, nxGlobal/2 - 1
+            idst = nxg - i
+            x1, x2 = buf[rows, i], buf[rows, idst]
+            xavg = 0.5 * (x1 + isign * x2)
+            buf[rows, i] = xavg
+            buf[rows, idst] = isign * xavg
+    else:                                    # field_loc_center
+        ioffset = joffset = 0
+    for b in range(nb):
+        if jg_[b][grid["jhi"][b] - 1] != nyg:
+            continue
+        ie, je = grid["ihi"][b], grid["jhi"][b]
+        for j in range(1, rows + 1):
+            for i in range(1, ie + nghost + 1):
+                gi = ig_[b][i - 1]
+                if gi < 1:
+                    continue
+                isrc, jsrc = nxg - gi + 1 - ioffset, nghost + 3 - j - joffset
+                jdst = je + j - 1
+                if isrc < 1:
+                    isrc += nxg
+                if isrc > nxg:
+                    isrc -= nxg
+                if 0 < jsrc <= rows and jdst > 0:
+                    a[b, jdst - 1, i - 1] = isign * buf[jsrc, isrc]
+
+
+@pytest.mark.parametrize("bs", [None, (12, 10), (8, 7)], ids=["1block", "4blocks", "padded-blocks"])
+@pytest.mark.parametrize("ns", ["tripole", "closed", "cyclic"])
+def test_halo_update_equals_the_literal_reference_loops(oracle_mod, bs, ns):
+    """the oracle's halo update (closed form, oracle/evp_oracle.c: orc_halo_update) against the reference's own sequence restated loop
+    for loop -- tripole buffer, pairwise symmetrisation of the top row, copy-out with the location offsets -- for the velocity pair
+    (NE corner, vector: sign flip across the fold) and for a centre-located scalar, bit for bit including the signs of zeros."""
+    c = synth.make_case("tiny", seed=71, ns=ns, ew="cyclic", kmt="none", ndte=1, block_size=bs)
+    rng = np.random.default_rng(9)
+    for loc, typ in ((1, 1), (0, 0)):
+        a = rng.normal(size=c.fields["uvel"].shape)
+        a[rng.random(a.shape) < 0.2] = 0.0                     # zeros: -0.0 / +0.0 must come out as in the reference
+        want, got = a.copy(), a.copy()
+        _halo_update_literal(c.grid, want, loc, typ)
+        oracle_mod.halo_update(c.grid, [got], field_loc=loc, field_type=typ)
+        bad = np.argwhere(got.view(np.int64) != want.view(np.int64))
+        assert len(bad) == 0, (loc, typ, len(bad), bad[:6].tolist(), [(got[tuple(q)], want[tuple(q)]) for q in bad[:6]])
