@@ -39,7 +39,6 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const TmaMap *map, int x,
                ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tma_prefetch_map(const TmaMap *map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
 // wait for phase number `phase` (0, 1, 2 ... in the order the barrier completes them).  Bounded like every other in-kernel wait
 // of this library: a programming error (byte count that never arrives) becomes an error code, not a hung GPU.
 __device__ __forceinline__ void mbar_wait(MBar *bar, unsigned phase, int *err) {
@@ -109,7 +108,6 @@ inline void tma_load_2d(void *dst, const TmaMap *m, int x, int y, MBar *bar) {
     }
   bar->landed.fetch_add((long long)m->box0 * m->box1 * m->elem, std::memory_order_release);
 }
-inline void tma_prefetch_map(const TmaMap *) {}
 inline void mbar_wait(MBar *bar, unsigned phase, int *err) {
   for (long spins = 0;; ++spins) {
     if (bar->arrivals.load(std::memory_order_acquire) > phase && bar->landed.load(std::memory_order_acquire) >= bar->due[phase & 3].load()) break;

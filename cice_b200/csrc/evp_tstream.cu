@@ -4,7 +4,7 @@
 // Compiled twice like the other kernel units (-DEVP_NS=exact -fmad=false / -DEVP_NS=fast).
 //
 // Why another kernel form.  The launch-per-subcycle kernel (evp_kernels.cu: fused_kernel) advances a cell in the same time whether
-// its operands come from L2 or from HBM (9.2 us x 70 at 3600x2400 = 647 us against 671 measured): it is bound by the latency its
+// its operands come from L2 or from HBM (9.2 us x 70 at 3600x2400 = 647 us against 641-671 measured): it is bound by the latency its
 // warps see -- request, wait, compute, CTA barrier, request, wait -- and by the 18 % of T cells its overlapping 32 x 8 patches relax
 // twice, not by bandwidth.  Here the requests are taken off the warps altogether:
 //   * the sub-domain is cut into column STRIPS of 31 T cells (30 U points; neighbouring strips share one T column) and every strip
@@ -16,14 +16,17 @@
 //     stresses, (u,v) with the west/south neighbours, dxT, dyT, the two metric arrays the other seven geometry values derive from
 //     (evp_math.cuh: derive_geometry, after evp_b200_set_metric), strength, both ice masks and the 12 momentum operands of the U
 //     points the block closes: 33 arrays -- is fetched by 33 `cp.async.bulk.tensor.2d` box loads issued by ONE thread into one of
-//     two shared-memory stages, a whole block (3.2 us of arithmetic) ahead of its use; the loads complete on the stage's mbarrier.
+//     two shared-memory stages, a whole block (3 us of arithmetic) ahead of its use; the loads complete on the stage's mbarrier.
 //     No thread ever waits for a global load it issued itself, no register holds a value in flight;
 //   * the stress divergence terms go from the stress phase to the momentum phase through shared memory (as in fused_kernel), and the
 //     top row of every block is CARRIED to the next block of the segment, so a T row is relaxed twice only where two segments meet
 //     (1 row in rows*nb) and a T column only where two strips meet (1 in 31): 4 % redundant work instead of 18 %;
 //   * reads only copy `cur` of the carried state, writes only copy `cur^1` (plain coalesced stores): no race between CTAs, the
 //     launch boundary is the only synchronisation, exactly as for fused_kernel -- and the same bits.
-// Shared memory: 2 stages x 97.5 KB + 28 KB at rows = 12 (one CTA of 384 threads per SM), 2 x 49 KB + 16 KB at rows = 6 (two CTAs).
+// Shared memory: 2 stages x 94.9 KB + 28 KB at rows = 12 (one CTA of 384 threads per SM, the default), 2 x 48 KB + 16 KB at rows = 6 (two
+// CTAs of 192; EVP_B200_TSTREAM_ROWS).  Measured on B200 at 3600x2400 (DESIGN.md sections 3, 4, 8; profiles/r2_tstream_*): 563 us per
+// subcycle against 641 for the launch-per-subcycle kernel (605 / 685 once the board sits at its power cap), DRAM traffic 0.99 x the
+// algorithmic 3.11 GB per launch.
 #include "evp_math.cuh"
 #include "evp_dom.cuh"
 #include "evp_ptx.cuh"
