@@ -13,7 +13,7 @@ SYMBOLS = (
     "evp_b200_get_unique_id", "evp_b200_comm_init", "evp_b200_set_device", "evp_b200_init", "evp_b200_finalize",
     "evp_b200_last_error", "evp_b200_run_bgrid", "evp_b200_upload", "evp_b200_subcycle", "evp_b200_download",
     "evp_b200_last_loop_ms", "evp_b200_last_launches", "evp_b200_stream", "evp_b200_describe",
-    "evp_b200_halo_plan", "evp_b200_dom_pitch", "evp_b200_dom_cells", "evp_b200_p2p_plan", "evp_b200_init_cgrid", "evp_b200_run_cgrid", "evp_b200_deformations", "evp_b200_dyn_finish", "evp_b200_set_metric", "evp_b200_pin_host", "evp_b200_unpin_host",
+    "evp_b200_halo_plan", "evp_b200_dom_pitch", "evp_b200_dom_cells", "evp_b200_p2p_plan", "evp_b200_stress_fold_plan", "evp_b200_init_cgrid", "evp_b200_run_cgrid", "evp_b200_deformations", "evp_b200_dyn_finish", "evp_b200_set_metric", "evp_b200_pin_host", "evp_b200_unpin_host",
     "evp_b200_run_bgrid_resident", "evp_b200_download_stress", "evp_b200_stress_symmetrise", "evp_b200_allow_partial_domain", "evp_b200_run_cdgrid",
     "evp_b200_prep_init", "evp_b200_step_resident",
 )
@@ -76,6 +76,7 @@ def load():
     L.evp_b200_halo_plan.argtypes = [C.c_int32, pi32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, pi32, pi32, C.c_int32]
     L.evp_b200_dom_pitch.argtypes = [C.c_int32]
     L.evp_b200_dom_cells.argtypes = [C.c_int32, C.c_int32]
+    L.evp_b200_stress_fold_plan.argtypes = [C.c_int32, pi32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, pi32, pi32, pi32, pi32, C.c_int32]
     L.evp_b200_p2p_plan.argtypes = [C.c_int32, pi32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, pi32, pi32, pi32, pi32, C.c_int32]
     for n in SYMBOLS:
         getattr(L, n).restype = C.c_int

@@ -1387,10 +1387,7 @@ int evp_b200_download(evp_b200_fields_t *f) { return do_download(f, 7); }
 __global__ void stress_fold_kernel(const __grid_constant__ Dom d, int cur, int gi0, int nxg) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
   if (i > d.nx + 1) return;
-  int ig = gi0 + i - 1;
-  if (ig < 1) ig += nxg;
-  if (ig > nxg) ig -= nxg;
-  const int ic = (nxg - ig + 1) - gi0 + 1;            // dom column of the mirrored cell (the rank holds the whole top row)
+  const int ic = fold_mirror_col(nxg, gi0, i) - gi0 + 1;   // dom column of the mirrored cell (the rank holds the whole top row)
   const int src = (q / 4) * 4 + ((q % 4) + 2) % 4;
   d.sig[cur][q][(size_t)(d.ny + 1) * d.ld + i] = d.sig[cur][src][(size_t)d.ny * d.ld + ic];
 }
@@ -1398,11 +1395,8 @@ __global__ void stress_fold_kernel(const __grid_constant__ Dom d, int cur, int g
 __global__ void stress_fold_rows_kernel(const __grid_constant__ Dom d, int cur, int gi0, int nxg, const double *__restrict__ rowtop) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
   if (i > d.nx + 1) return;
-  int ig = gi0 + i - 1;
-  if (ig < 1) ig += nxg;
-  if (ig > nxg) ig -= nxg;
   const int src = (q / 4) * 4 + ((q % 4) + 2) % 4;
-  d.sig[cur][q][(size_t)(d.ny + 1) * d.ld + i] = rowtop[(size_t)src * nxg + (nxg - ig + 1) - 1];
+  d.sig[cur][q][(size_t)(d.ny + 1) * d.ld + i] = rowtop[(size_t)src * nxg + fold_mirror_col(nxg, gi0, i) - 1];
 }
 static bool symmetrise_here() { return g.ns == EVP_B200_BNDY_TRIPOLE && g.gj0 + g.dom.ny - 1 == g.nyg; }
 static int do_stress_symmetrise() {
@@ -1594,6 +1588,14 @@ int evp_b200_p2p_plan(int32_t nranks, const int32_t *rects, int32_t rank, int32_
     return fail("evp_b200_p2p_plan: bad arguments");
   const int rc = p2p_plan_host(nranks, rects, rank, nxg, nyg, ew, ns, n_push, push_out, n_fold, fold_out, cap);
   if (rc) return fail("evp_b200_p2p_plan: the staging rows of a rank overflow");
+  return 0;
+}
+int evp_b200_stress_fold_plan(int32_t nranks, const int32_t *rects, int32_t rank, int32_t nxg, int32_t nyg, int32_t ns, int32_t *n_seg,
+                              int32_t *seg_out, int32_t *n_cell, int32_t *cell_out, int32_t cap) {
+  if (!rects || !n_seg || !n_cell || (cap > 0 && (!seg_out || !cell_out)) || nranks < 1 || rank < 0 || rank >= nranks)
+    return fail("evp_b200_stress_fold_plan: bad arguments");
+  const int rc = stress_fold_plan_host(nranks, rects, rank, nxg, nyg, ns, n_seg, seg_out, n_cell, cell_out, cap);
+  if (rc && cap > 0) return fail("evp_b200_stress_fold_plan: %d entries do not hold the lists (%d segments, %d cells)", cap, *n_seg, *n_cell);
   return 0;
 }
 int32_t evp_b200_dom_pitch(int32_t nx) { return dom_pitch(nx); }

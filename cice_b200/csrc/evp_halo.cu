@@ -64,6 +64,31 @@ void comm_destroy(CommState &cs) {
   cs = CommState{};
 }
 
+int stress_fold_plan_host(int nranks, const int *rects, int rank, int nxg, int nyg, int ns, int *n_seg, int *seg_out, int *n_cell,
+                          int *cell_out, int cap) {
+  *n_seg = 0; *n_cell = 0;
+  const int gi0 = rects[4 * rank], gj0 = rects[4 * rank + 1], nx = rects[4 * rank + 2], ny = rects[4 * rank + 3];
+  if (ns != EVP_B200_BNDY_TRIPOLE || nx < 1 || ny < 1 || gj0 + ny - 1 != nyg) return 0;
+  int rc = 0;
+  auto top = [&](int t) { return rects[4 * t + 2] >= 1 && rects[4 * t + 3] >= 1 && rects[4 * t + 1] + rects[4 * t + 3] - 1 == nyg; };
+  for (int t = 0; t < nranks; ++t) {
+    if (t == rank || !top(t)) continue;
+    if (*n_seg < cap && seg_out) { seg_out[3 * *n_seg] = t; seg_out[3 * *n_seg + 1] = rects[4 * t]; seg_out[3 * *n_seg + 2] = rects[4 * t + 2]; }
+    else rc = 1;
+    ++*n_seg;
+  }
+  for (int i = 0; i <= nx + 1; ++i) {
+    const int im = fold_mirror_col(nxg, gi0, i);
+    int src = -1, col = 0;
+    for (int t = 0; t < nranks; ++t)
+      if (top(t) && im >= rects[4 * t] && im < rects[4 * t] + rects[4 * t + 2]) { src = t; col = im - rects[4 * t] + 1; break; }
+    if (*n_cell < cap && cell_out) { cell_out[3 * *n_cell] = i; cell_out[3 * *n_cell + 1] = src; cell_out[3 * *n_cell + 2] = col; }
+    else rc = 1;
+    ++*n_cell;
+  }
+  return rc;
+}
+
 int stress_rows_exchange(CommState &cs, const std::vector<int> &rects, int nxg, int nyg, double *const *sig, int ld, int nx, int ny, int gi0,
                          int gj0, double *rowtop, cudaStream_t s, char *err, size_t nerr) {
   if (gj0 + ny - 1 != nyg) return 0;
@@ -72,12 +97,15 @@ int stress_rows_exchange(CommState &cs, const std::vector<int> &rects, int nxg, 
     HCK(cudaMemcpyAsync(rowtop + (size_t)q * nxg + (gi0 - 1), sig[q] + (size_t)ny * ld + 1, sizeof(double) * nx, cudaMemcpyDeviceToDevice, s));
   if (cs.nranks < 2) return 0;
   if (!cs.comm || (int)rects.size() < 4 * cs.nranks) HFAIL("stress symmetrisation: no communicator / rank table");
-  // every pair of top-row ranks swaps its twelve row segments; same order on both sides
+  // every pair of top-row ranks swaps its twelve row segments; same order on both sides (the segment list: stress_fold_plan_host)
+  std::vector<int> seg(3 * (size_t)cs.nranks), cell(3 * (size_t)(nx + 2));
+  int nseg = 0, ncell = 0;
+  if (stress_fold_plan_host(cs.nranks, rects.data(), cs.rank, nxg, nyg, EVP_B200_BNDY_TRIPOLE, &nseg, seg.data(), &ncell, cell.data(),
+                            std::max(cs.nranks, nx + 2)))
+    HFAIL("stress symmetrisation: internal: plan overflow");
   NCK(ncclGroupStart());
-  for (int t = 0; t < cs.nranks; ++t) {
-    if (t == cs.rank) continue;
-    const int ti0 = rects[4 * t], tj0 = rects[4 * t + 1], tnx = rects[4 * t + 2], tny = rects[4 * t + 3];
-    if (tnx < 1 || tny < 1 || tj0 + tny - 1 != nyg) continue;
+  for (int k = 0; k < nseg; ++k) {
+    const int t = seg[3 * k], ti0 = seg[3 * k + 1], tnx = seg[3 * k + 2];
     for (int q = 0; q < 12; ++q) {
       NCK(ncclSend(sig[q] + (size_t)ny * ld + 1, (size_t)nx, ncclDouble, t, cs.comm, s));
       NCK(ncclRecv(rowtop + (size_t)q * nxg + (ti0 - 1), (size_t)tnx, ncclDouble, t, cs.comm, s));

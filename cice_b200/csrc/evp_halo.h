@@ -68,6 +68,12 @@ struct HaloPlan {
 // rowtop[12][nxg] on each of those ranks (what ice_HaloUpdate_stress moves through its tripole buffer, ice_boundary.F90:7596-7688).
 // rects as HaloPlan::rects; sig: the 12 dom arrays of the current copy.  Ranks below the top row return at once; rowtop is zeroed
 // first (columns nobody holds -- eliminated land blocks -- stay at the reference's fill value).
+// host side of it: which other ranks of the top row this rank swaps its row segment with -- 3 ints {rank, gi0, nx} each, in rank order --
+// and, per ghost cell of its north ghost row (dst column 0 .. nx+1), the rank and the column of that rank's top row that is mirrored
+// into it -- 3 ints {dst column, source rank or -1 (nobody holds the column: land), source column 1 .. nx_source}.  Empty on ranks
+// below the top row and on grids without a fold.  Returns 1 when `cap` entries do not hold a list (counts are still returned).
+int stress_fold_plan_host(int nranks, const int *rects, int rank, int nxg, int nyg, int ns, int *n_seg, int *seg_out, int *n_cell,
+                          int *cell_out, int cap);
 int stress_rows_exchange(CommState &cs, const std::vector<int> &rects, int nxg, int nyg, double *const *sig, int ld, int nx, int ny, int gi0,
                          int gj0, double *rowtop, cudaStream_t s, char *err, size_t nerr);
 

@@ -113,6 +113,16 @@ __host__ __device__ inline int ring_index(int nx, int ny, int i, int j) {
   return 2 * (nx + 2) + ny + (j - 1);
 }
 
+// Tripole fold, centre-located fields (the stress symmetrisation, ice_boundary.F90:8136-8157 with ioffset = 0): the global column whose
+// top physical row is mirrored into ghost cell `i` (0 .. nx+1) of the north ghost row of a sub-domain that starts at global column gi0.
+// One definition for the device kernels and for the host-side plan (evp_b200_stress_fold_plan).
+__host__ __device__ inline int fold_mirror_col(int nxg, int gi0, int i) {
+  int ig = gi0 + i - 1;
+  if (ig < 1) ig += nxg;
+  if (ig > nxg) ig -= nxg;
+  return nxg - ig + 1;
+}
+
 // KERNEL_PERSISTENT (evp_persist.cu): one CTA per SM owns a tile of the sub-domain for the whole loop.  The plan is built on the
 // host (evp_persist_plan.h); the tables say which T cell / U point each (slot, thread) of a CTA advances.
 #define PERSIST_THREADS 512

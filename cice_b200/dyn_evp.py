@@ -262,6 +262,21 @@ def p2p_plan(rects, rank, nx_global, ny_global, ew, ns):
     return push[:npush.value], fold[:nfold.value]
 
 
+def stress_fold_plan(rects, rank, nx_global, ny_global, ns):
+    """host-only: the stress symmetrisation across a tripole fold between ranks.  Returns (seg, cell): seg (n,3) {rank, gi0, nx} of the
+    other top-row ranks, cell (m,3) {ghost column, source rank or -1, source column} for the rank's north ghost row."""
+    L = load()
+    r = np.ascontiguousarray(rects, dtype=np.int32)
+    nseg, ncell = C.c_int32(), C.c_int32()
+    pi = C.POINTER(C.c_int32)
+    args = (len(r), r.ctypes.data_as(pi), rank, nx_global, ny_global, ns)
+    check(L.evp_b200_stress_fold_plan(*args, C.byref(nseg), None, C.byref(ncell), None, 0), "stress_fold_plan")
+    cap = max(nseg.value, ncell.value, 1)
+    seg, cell = np.zeros((cap, 3), np.int32), np.zeros((cap, 3), np.int32)
+    check(L.evp_b200_stress_fold_plan(*args, C.byref(nseg), seg.ctypes.data_as(pi), C.byref(ncell), cell.ctypes.data_as(pi), cap), "stress_fold_plan")
+    return seg[:nseg.value], cell[:ncell.value]
+
+
 def dom_pitch(nx):
     return load().evp_b200_dom_pitch(int(nx))
 

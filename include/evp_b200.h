@@ -384,6 +384,14 @@ int evp_b200_p2p_plan(int32_t nranks, const int32_t *rects, int32_t rank, int32_
                       int32_t ew_boundary_type, int32_t ns_boundary_type, int32_t *n_push, int32_t *push_out, int32_t *n_fold,
                       int32_t *fold_out, int32_t cap);
 
+/* The stress symmetrisation across a tripole fold between ranks (evp_b200_stress_symmetrise), as a plan: the other ranks of the top row
+ * `rank` swaps its top-row segment with -- entries {rank, gi0, nx} in seg_out -- and, for every cell of its north ghost row (column
+ * 0 .. nx+1), the rank and the column (1 .. nx of that rank) of the top physical row that is mirrored into it -- entries {dst column,
+ * source rank or -1 where no rank holds the column, source column} in cell_out.  What ice_HaloUpdate_stress derives from its tripole
+ * buffer addresses (ice_boundary.F90:8117-8157, field_loc_center).  Empty below the top row and without a fold.  cap = 0: counts only. */
+int evp_b200_stress_fold_plan(int32_t nranks, const int32_t *rects, int32_t rank, int32_t nx_global, int32_t ny_global,
+                              int32_t ns_boundary_type, int32_t *n_seg, int32_t *seg_out, int32_t *n_cell, int32_t *cell_out, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -293,3 +293,74 @@ def test_halo_plan_with_eliminated_land_blocks():
     # rank 1 (global rows 1..20): its ghost columns have a source only where rank 0 exists, global rows 5..20
     assert all(e[1] == 0 and e[5] == 0 for e in p1)
     assert sorted(set(int(e[0]) // ld for e in p1)) == list(range(5, 21)) and len(p1) == 2 * 16
+
+
+def _worker_stress_fold(rank, world, port, q):
+    """the stress symmetrisation across a tripole fold between ranks on numpy arrays: every rank of the top row swaps the top physical
+    row of its twelve stress arrays with the ranks evp_b200_stress_fold_plan names (here through gloo, on the GPU one NCCL group) and
+    mirrors the assembled row into its north ghost row cell by cell as the plan says."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from cice_b200 import abi, decomp, dyn_evp, synth
+    from oracle import oracle
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        case = synth.make_case("tiny", block_size=(12, 10), seed=23, ew="cyclic", ns="tripole", kmt="none")
+        owner, _ = decomp.cartesian_owner(case.blocks, world)
+        rects = _rects(case, owner, world)
+        nxg, nyg = case.grid["nx_global"], case.grid["ny_global"]
+        whole = synth.make_case("tiny", seed=23, ew="cyclic", ns="tripole", kmt="none")
+        rng = np.random.default_rng(3)
+        G = {n: rng.normal(size=(nyg + 2, nxg + 2)) for n in abi.STRESS}          # the same on every rank
+        truth = {n: G[n][None].copy() for n in abi.STRESS}
+        oracle.stress_symmetrise(whole.grid, truth)
+
+        gi0, gj0, nx, ny = (int(v) for v in rects[rank])
+        dom = {n: G[n][gj0 - 1:gj0 + ny + 1, gi0 - 1:gi0 + nx + 1].copy() for n in abi.STRESS}   # (ny+2, nx+2) with its ring
+        seg, cell = dyn_evp.stress_fold_plan(rects, rank, nxg, nyg, whole.grid["ns_boundary_type"])
+        top = gj0 + ny - 1 == nyg
+        ntop = sum(1 for r in rects if r[1] + r[3] - 1 == nyg)
+        assert len(cell) == (nx + 2 if top else 0) and len(seg) == (ntop - 1 if top else 0)
+        rows = {rank: np.stack([dom[n][ny, 1:nx + 1] for n in abi.STRESS])}        # [12][nx]
+        reqs, bufs = [], {}
+        for t, ti0, tnx in seg:                                                    # swap with every other rank of the top row
+            bufs[int(t)] = torch.zeros(12, int(tnx), dtype=torch.float64)
+            reqs.append(dist.isend(torch.from_numpy(rows[rank].copy()), dst=int(t)))
+            reqs.append(dist.irecv(bufs[int(t)], src=int(t)))
+        for r in reqs:
+            r.wait()
+        for t, b in bufs.items():
+            rows[t] = b.numpy()
+        partner = lambda k: (k // 4) * 4 + (k % 4 + 2) % 4
+        for k, n in enumerate(abi.STRESS):
+            for i, src, col in cell:
+                dom[n][ny + 1, i] = rows[int(src)][partner(k), col - 1] if src >= 0 else 0.0
+        bad = 0
+        for n in abi.STRESS:
+            want = truth[n][0][gj0 - 1:gj0 + ny + 1, gi0 - 1:gi0 + nx + 1]
+            bad += int(np.count_nonzero(dom[n].view(np.int64) != want.view(np.int64)))
+        q.put((rank, bad, len(seg), len(cell)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_stress_fold_plan_processes_gloo(world):
+    """SURVEY 8f rank 2 between ranks: executing the host-side plan of the stress symmetrisation on numpy sub-domains over gloo gives the
+    oracle's result (ice_dyn_evp.F90:1321-1388) on every rank, ghost corners included; ranks below the top row have nothing to do."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() * 11 + 17 * world) % 2000
+    procs = [ctx.Process(target=_worker_stress_fold, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, bad, nseg, ncell in res:
+        assert bad == 0, f"rank {rank}: {bad} cells differ from the oracle ({nseg} segments, {ncell} ghost cells)"
+    assert sum(1 for r in res if r[3] > 0) == 2    # 2x1 and 2x2 processor grids: two ranks hold the top row
