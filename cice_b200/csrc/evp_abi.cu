@@ -609,9 +609,9 @@ static int fused_form(const evp_b200_params_t *p) {
 
 // AUTO: the persistent kernel wherever a sub-domain's carried state fits on chip (one tile per SM; measured on B200 at gx1
 // 1.80 vs 2.20 ms per step, gx3 0.52 vs 0.63), else the fused kernel in the form fused_form() picks
-// KERNEL_TSTREAM needs the metric arrays (derived geometry) and is the single-rank / staged-exchange form: between GPUs with the
-// in-kernel NVLink halo the fused kernel's P2P instantiation stays in charge
-static bool tstream_available() { return g.derived_ok && g.d_HTN && g.d_HTE && !g.p2p.enabled; }
+// KERNEL_TSTREAM needs the metric arrays (derived geometry) and is the single-rank form (tested as such): between GPUs the fused
+// kernel stays in charge, with the in-kernel NVLink halo or the staged exchange
+static bool tstream_available() { return g.derived_ok && g.d_HTN && g.d_HTE && !g.p2p.enabled && g_comm.nranks == 1; }
 static int choose_kernel(const evp_b200_params_t *p) {
   int kern = p->kernel;
   if (kern == EVP_B200_KERNEL_AUTO) {
@@ -626,8 +626,8 @@ static int choose_kernel(const evp_b200_params_t *p) {
 // copy 1); called outside graph capture
 static int tstream_prepare() {
   if (!tstream_available())
-    return fail("evp_b200_subcycle: the TMA tile-streaming kernel needs evp_b200_set_metric to have accepted the metric arrays and no in-kernel NVLink halo (%s)",
-                g.p2p.enabled ? "neighbour ranks use it" : (g.derived_ok ? "metric arrays missing" : "derived geometry unavailable"));
+    return fail("evp_b200_subcycle: the TMA tile-streaming kernel needs evp_b200_set_metric to have accepted the metric arrays and a single rank (%s)",
+                (g.p2p.enabled || g_comm.nranks > 1) ? "several ranks" : (g.derived_ok ? "metric arrays missing" : "derived geometry unavailable"));
   if (const char *e = getenv("EVP_B200_TSTREAM_ROWS")) g.ts_rows = atoi(e);
   const void *key[3] = {g.dom.u[0], g.dom.sig[0][0], (const void *)(intptr_t)g.ts_rows};
   if (!g.ts_hmaps.empty() && memcmp(key, g.ts_key, sizeof key) == 0) return 0;

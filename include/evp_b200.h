@@ -72,7 +72,7 @@ enum {
   EVP_B200_KERNEL_TSTREAM        = 6   /* one launch per subcycle by persistent CTAs that walk column strips of the sub-domain; every
                                           operand staged global -> shared by TMA box loads (cp.async.bulk.tensor) one block ahead of
                                           the arithmetic.  AUTO's choice for sub-domains that stream from HBM once
-                                          evp_b200_set_metric has accepted the metric arrays (single rank / staged exchange) */
+                                          evp_b200_set_metric has accepted the metric arrays (single rank) */
 };
 
 /*
