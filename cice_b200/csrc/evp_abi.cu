@@ -1443,7 +1443,8 @@ int evp_b200_prep_init(const evp_b200_prep_static_t *st) {
   if (!g.inited) return fail("evp_b200_prep_init: call evp_b200_init first");
   if (!st || !st->hm || !st->tarea || !st->uarea || !st->fcor || !st->umask) return fail("evp_b200_prep_init: null argument");
   if (g.ns == EVP_B200_BNDY_TRIPOLE || g.halo.has_fold)
-    return fail("evp_b200_prep_init: not for tripole grids in this version (the host symmetrises the stresses across the fold, ice_dyn_evp.F90:1322-1389)");
+    return fail("evp_b200_prep_init: not for tripole grids in this version (the T->U averages and the velocity halo update after dyn_prep2 "
+                "at the fold are not built; evp_b200_run_bgrid_resident keeps the stresses on the device there)");
   CK(cudaSetDevice(g.device));
   const size_t bdom = g.ndom * sizeof(double), bblk = g.nblk_elems * sizeof(double);
   const int nd = (int)g.ndom, nb = grid_blocks(g.ndom);

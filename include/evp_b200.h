@@ -322,7 +322,8 @@ int evp_b200_stress_symmetrise(void);
  * masks and (first form) the stresses, and downloads the velocities only (diagnostics on request).  Carried on the device
  * between steps: velocities, stresses, and iceUmask -- dyn_prep2 needs the OLD mask to find new ice points (:765-783).
  * The velocity halo update that follows dyn_prep2 (ice_dyn_evp.F90:735-739) is the on-rank wrap plus, between ranks, one staged
- * exchange per step.  Not for tripole grids (see EVP_B200_KEEP_STRESS).  Ice strength stays with the caller (Icepack). */
+ * exchange per step.  Not for tripole grids in this version (the averages and that halo update at the fold are not built; the stresses
+ * alone can stay resident there, EVP_B200_KEEP_STRESS).  Ice strength stays with the caller (Icepack). */
 typedef struct {
   /* static, arrays (nx_block, ny_block, max_blocks) like everything else */
   const double *hm;      /* T land mask as 0/1 real (ice_grid.F90: hm)   */
