@@ -128,3 +128,19 @@ def test_planner_covers_the_subdomain_evenly(emu):
             blocks[it % ctas] += min(nb, (ny + 2 - j0 + rows - 1) // rows)
         if nx >= 900:
             assert blocks.max() <= 1.06 * blocks.mean(), (nx, ny, rows, nb, blocks.max(), blocks.mean())
+
+
+def test_random_cuts_on_the_host(oracle_mod, emu):
+    """random sub-domain sizes, blocks per segment and grid sizes (seeded): whatever the cut, the same bits"""
+    rng = np.random.default_rng(20261017)
+    for _ in range(10):
+        nx, ny = int(rng.integers(20, 95)), int(rng.integers(20, 60))
+        rows = int(rng.choice([12, 6]))
+        nb = int(rng.integers(0, 5))                   # 0: the planner's own choice; 1: every block is a segment of its own
+        nctas = int(rng.integers(0, 9))
+        c = synth.make_case("tiny", nx=nx, ny=ny, ndte=2, seed=int(rng.integers(1, 1000)), ns=str(rng.choice(["closed", "cyclic"])),
+                            kmt=str(rng.choice(["none", "continents"])))
+        ref = reference(oracle_mod, c)
+        got, plan = run_emulated(emu, c, rows, nb, nctas)
+        for nm in FIELDS:
+            assert np.array_equal(got[nm].view(np.int64), ref[nm][0].view(np.int64)), (nm, nx, ny, rows, nb, nctas, plan.tolist())
